@@ -1,0 +1,127 @@
+"""Pattern-directory writer for the reference's on-disk template format.
+
+The engine reads `<pattern_dir>/<ps>/pattern_{edge,vertex,vertex_data,edge_data,
+stat,nlc,non_local_constraint}` exactly like the reference driver
+(/root/reference/src/run_pattern_matching_beta.cpp:433-441,473-475; grammar in
+include/havoqgt/graph.hpp:181-270,337-358 and include/havoqgt/pattern_util.hpp:172-210,
+254-278).  This module only WRITES such directories from a small Python
+description, so tests and bench.py can create their templates without shipping
+data files.
+
+A spec is a dict:
+  labels      : list, label of template vertex i
+  edges       : list of undirected (a, b)
+  diameter    : number of LCC supersteps per call (pattern_stat "diameter")
+  constraints : list of dicts {walk: [template ids], cycle: bool,
+                               interleave: bool (default True), tds: bool}
+Constraints flagged tds must come last: the reference switches to template
+driven search by constraint INDEX (`pl >= 4`, beta.cpp:762), which the engine
+exposes as the `tds_from_pl` option; `tds_from_pl(spec)` returns that index.
+"""
+import os
+
+
+def _enum_indices(walk):
+    # pattern_non_local_constraint field 2: position of the first occurrence of
+    # walk[h] ("new vertex" when it equals h, "must equal visited[e]" when smaller;
+    # token_passing_pattern_matching_nonunique_tds_batch_1.hpp:284-302)
+    return [walk.index(w) for w in walk]
+
+
+def tds_from_pl(spec):
+    for i, c in enumerate(spec.get("constraints", [])):
+        if c.get("tds"):
+            return i
+    return -1
+
+
+def write_pattern_dir(base, spec, ps=0):
+    """Writes `<base>/<ps>/pattern_*`; returns `<base>/<ps>`."""
+    d = os.path.join(base, str(ps))
+    os.makedirs(d, exist_ok=True)
+    labels = spec["labels"]
+    both = sorted(set((a, b) for a, b in spec["edges"]) | set((b, a) for a, b in spec["edges"]))
+    eid = {}
+    for a, b in spec["edges"]:
+        eid[(a, b)] = eid[(b, a)] = len(eid) // 2
+    with open(os.path.join(d, "pattern_edge"), "w") as f:
+        for a, b in both:
+            f.write("%d %d\n" % (a, b))
+    with open(os.path.join(d, "pattern_edge_data"), "w") as f:
+        for a, b in both:
+            f.write("%d %d %d 55\n" % (a, b, eid[(a, b)]))
+    with open(os.path.join(d, "pattern_vertex"), "w") as f:
+        f.write("\n")
+    with open(os.path.join(d, "pattern_vertex_data"), "w") as f:
+        for i, l in enumerate(labels):
+            f.write("%d %d\n" % (i, l))
+    with open(os.path.join(d, "pattern_stat"), "w") as f:
+        f.write("diameter : %d\n" % spec["diameter"])
+    seen_tds = False
+    with open(os.path.join(d, "pattern_nlc"), "w") as f, \
+            open(os.path.join(d, "pattern_non_local_constraint"), "w") as g:
+        for c in spec.get("constraints", []):
+            if seen_tds and not c.get("tds"):
+                raise ValueError("tds constraints must come last (beta.cpp:762)")
+            seen_tds = seen_tds or bool(c.get("tds"))
+            walk = c["walk"]
+            f.write("%s : %s : %d : %d : %d : 0\n" % (
+                " ".join(str(labels[w]) for w in walk), " ".join(str(w) for w in walk),
+                len(walk) - 2, int(bool(c.get("cycle"))), int(c.get("interleave", True))))
+            agg = [0] * len(walk) if not c.get("tds") else [0] + [1] * (len(walk) - 1)
+            g.write("%s : %s : %s\n" % (" ".join(str(w) for w in walk),
+                                        " ".join(str(e) for e in _enum_indices(walk)),
+                                        " ".join(str(a) for a in agg)))
+    return d
+
+
+# The README's example template (examples/rmat_log2_tree_pattern/0): a 7-vertex
+# tree with degree-log2 labels 3,4,7,2,3,5,7; four path constraints between the
+# repeated labels (3..3 and 7..7, both directions) and one full-template walk.
+RMAT_LOG2_TREE = {
+    "labels": [3, 4, 7, 2, 3, 5, 7],
+    "edges": [(0, 1), (1, 2), (1, 3), (3, 5), (4, 5), (5, 6)],
+    "diameter": 8,
+    "constraints": [
+        {"walk": [4, 5, 3, 1, 0]},
+        {"walk": [0, 1, 3, 5, 4]},
+        {"walk": [2, 1, 3, 5, 6]},
+        {"walk": [6, 5, 3, 1, 2]},
+        {"walk": [0, 1, 2, 1, 3, 5, 4, 5, 6], "tds": True},
+    ],
+}
+
+
+def triangle(la, lb, lc):
+    return {
+        "labels": [la, lb, lc],
+        "edges": [(0, 1), (1, 2), (0, 2)],
+        "diameter": 2,
+        "constraints": [{"walk": [0, 1, 2, 0], "cycle": True},
+                        {"walk": [0, 1, 2, 0], "cycle": True, "tds": True}],
+    }
+
+
+def cycle4(la, lb, lc, ld):
+    return {
+        "labels": [la, lb, lc, ld],
+        "edges": [(0, 1), (1, 2), (2, 3), (0, 3)],
+        "diameter": 3,
+        "constraints": [{"walk": [0, 1, 2, 3, 0], "cycle": True},
+                        {"walk": [0, 1, 2, 3, 0], "cycle": True, "tds": True}],
+    }
+
+
+def cycle6_chords(labels):
+    """6-cycle 0-1-2-3-4-5-0 with chords (0,3) and (1,4); `labels` has 6 entries."""
+    assert len(labels) == 6
+    return {
+        "labels": list(labels),
+        "edges": [(0, 1), (1, 2), (2, 3), (3, 4), (4, 5), (0, 5), (0, 3), (1, 4)],
+        "diameter": 3,
+        "constraints": [{"walk": [0, 1, 2, 3, 4, 5, 0], "cycle": True},
+                        {"walk": [0, 1, 2, 3, 0], "cycle": True},
+                        {"walk": [1, 2, 3, 4, 1], "cycle": True},
+                        # one walk that covers every template edge
+                        {"walk": [0, 1, 2, 3, 4, 5, 0, 3, 4, 1], "tds": True}],
+    }

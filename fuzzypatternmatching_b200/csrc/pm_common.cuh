@@ -1,0 +1,163 @@
+// pm_common.cuh — context, device-side constants and small helpers shared by the
+// kernels of libpmgpu.so (sm_100a only; no CPU fallback, no multi-backend dispatch).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/pmgpu.h"
+#include "pm_pattern.hpp"
+
+#define PM_SENTINEL 0xFFFFFFFFu  // padding slot in the adjacency arrays
+#define PM_IDMASK 0x7FFFFFFFu    // bit 31 of a working-adjacency slot = "flag set outside LCC" 
+#define PM_NOCLASS 16            // class id of a label no template vertex carries
+
+// degree bins (current active degree) -> kernel shape
+#define PM_SMALL_MAX 32u    // <= 32 slots: one 8-lane group, one pass of uint4 loads
+#define PM_MID_MAX 4096u    // <= 4096 slots: one warp per vertex
+                            // larger: one CTA per vertex
+
+namespace pm {
+
+// Template (pattern) constants, uploaded once per pattern.
+struct PatConst {
+  uint16_t N[16];      // N[p]: template neighbours of template vertex p
+  uint16_t LMc[17];    // class -> bitmask of template vertices carrying that label; [16] = 0
+  uint64_t clabel[16]; // class -> label value
+  int ncls;
+};
+
+struct NlcConst {      // one non-local constraint (walk)
+  uint8_t cls[16];     // class of P[h]  (PM_NOCLASS if the label is not in the template)
+  uint8_t I[16];       // template vertex id at hop h
+  uint8_t e[16];       // enumeration index (TDS history rule)
+  int n;               // walk length = C + 2
+  int C;               // max itr_count
+  int valid_cycle;
+};
+
+struct DevCounters {
+  uint32_t fr_n[2][4];          // frontier sizes [buffer][bin]; [.][3] unused
+  uint32_t nf;                  // a vertex left the vertex_state_map in this LCC call
+  uint32_t found;               // NLCC: a walk completed
+  uint32_t deleted;             // NLCC: a source failed
+  uint32_t overflow;            // NLCC: token pool / hash set exhausted
+  uint32_t n_src;               // NLCC: number of sources
+  uint32_t pad0;
+  unsigned long long pool_n;    // NLCC: tokens in the pool
+  unsigned long long matches;   // TDS: completed walks
+  unsigned long long fanout;    // NLCC: adjacency slots walked by tokens
+  unsigned long long hash_n;    // NLCC: keys in the (vertex, source) set
+};
+
+struct RowStat {                // one result row, accumulated on the device
+  unsigned long long nv, ne, scanned;
+};
+
+}  // namespace pm
+
+struct pm_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  uint64_t launches = 0;
+  int rank = 0, n_ranks = 1;
+
+  // ---- graph store (device) -------------------------------------------------
+  uint64_t V = 0, nloc = 0, E_multi = 0, E = 0, Epad = 0, max_deg = 0, graph_bytes = 0;
+  uint32_t* rowblk = nullptr;  // [V+1] row start in units of 8 slots (32-byte sectors)
+  uint32_t* deg = nullptr;     // [V] distinct-neighbour degree
+  uint32_t* degm = nullptr;    // [V] multigraph out-degree (duplicates + self loops) -> labels
+  uint32_t* col0 = nullptr;    // [Epad] pristine adjacency: sorted, distinct, rows padded to 8 with PM_SENTINEL
+  uint32_t* colw = nullptr;    // [Epad] working adjacency: first adeg[v] slots of a row = keys(E_v)
+  uint64_t* label = nullptr;   // [V] vertex labels
+  bool has_graph = false, has_labels = false;
+
+  // ---- pattern ----------------------------------------------------------------
+  pm::Pattern pat;
+  pm::PatConst pc;
+  bool has_pattern = false;
+
+  // ---- per-pattern state (device) -----------------------------------------------
+  uint16_t* S = nullptr;    // [V] template_vertices[v] (T_arr) while v is active and in the map, else 0
+  uint16_t* Tst = nullptr;  // [V] vertex_state.template_vertices (T_state)
+  uint32_t* adeg = nullptr; // [V] |E_v|
+  uint8_t* cls = nullptr;   // [V] label class (index into the template's distinct labels, PM_NOCLASS = none)
+  uint32_t* fr[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};  // frontier lists by bin
+  int cur = 0;              // which frontier buffer is current
+  pm::DevCounters* cnt = nullptr;      // device
+  pm::DevCounters* h_cnt = nullptr;    // pinned host mirror
+  pm::RowStat* rowstat = nullptr;      // device, [diameter + 1]
+  pm::RowStat* h_rowstat = nullptr;    // pinned
+  bool state_ready = false;
+
+  // ---- NLCC scratch -----------------------------------------------------------------
+  uint8_t* ok = nullptr;            // [V] token_source_map value of source s
+  uint32_t* src_list = nullptr;     // [V] sources of the current constraint
+  unsigned long long* hset = nullptr;  // (vertex, source) set, open addressing
+  uint64_t hset_cap = 0;
+  uint2* pool = nullptr;            // token pool: nem_1 (vertex, source); TDS (parent index, vertex)
+  uint64_t pool_cap = 0;
+  uint32_t* match_rows = nullptr;   // TDS: materialised walks of the last run of each constraint
+  std::vector<std::vector<uint32_t>> subgraphs;  // host copies per constraint
+  std::vector<int> subgraph_width;
+  std::vector<uint64_t> subgraph_count;
+  bool keep_subgraphs = true;       // materialise enumerated walks on the host
+
+  // ---- run bookkeeping -----------------------------------------------------------------
+  std::vector<pm_row_t> rows;
+  std::vector<std::pair<uint64_t, double>> step_rows;  // result_step
+  std::vector<double> iter_seconds;                    // result_iteration
+  uint64_t itr = 0;
+  pm_run_summary_t summary{};
+  std::vector<cudaEvent_t> events;
+};
+
+namespace pm {
+
+inline int fail(pm_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg;
+  return code;
+}
+
+#define PM_CUDA(ctx, call)                                                              \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess)                                                              \
+      return pm::fail((ctx), PM_ERR_CUDA,                                               \
+                      std::string(#call) + ": " + cudaGetErrorString(e_) + " (" +       \
+                          __FILE__ + ":" + std::to_string(__LINE__) + ")");             \
+  } while (0)
+
+#define PM_LAUNCH_CHECK(ctx)                                \
+  do {                                                      \
+    (ctx)->launches++;                                      \
+    PM_CUDA((ctx), cudaGetLastError());                     \
+  } while (0)
+
+template <class T>
+inline int dev_alloc(pm_ctx* c, T** p, uint64_t n, uint64_t* tally = nullptr) {
+  *p = nullptr;
+  if (n == 0) n = 1;
+  PM_CUDA(c, cudaMalloc((void**)p, n * sizeof(T)));
+  if (tally) *tally += n * sizeof(T);
+  return 0;
+}
+template <class T>
+inline void dev_free(T*& p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+
+// persistent-style launch geometry: a multiple of the 148 SMs
+static const int kBlock = 256;
+static const int kGridPerSM = 8;
+inline int grid_for(uint64_t work_items_per_thread_hint = 0) {
+  (void)work_items_per_thread_hint;
+  return 148 * kGridPerSM;
+}
+
+}  // namespace pm

@@ -1,0 +1,207 @@
+// pm_graph.cuh — device-resident graph store.
+//
+// Replaces delegate_partitioned_graph construction
+// (/root/reference/include/havoqgt/impl/delegate_partitioned_graph.ipp:112-165:
+//  count_edge_degrees -> partition_low/high_degree) with a radix-sort based CSR
+// build that runs entirely on the GPU:
+//   degm[v]   multigraph out-degree, duplicates and self loops counted (ipp:437-470);
+//             this is what the degree labels are derived from
+//   col0      distinct neighbours of v, ascending; the reference keeps parallel
+//             edges in its CSR but everything downstream of the first superstep is
+//             keyed by neighbour id (vertex_active_edges_map, beta.cpp:293-294), so
+//             a distinct-neighbour CSR carries the same information
+//   rows are padded to multiples of 8 slots (one 32-byte sector) so that every
+//   row starts sector- and uint4-aligned; rowblk[v] is the row start in sectors.
+#pragma once
+
+#include <cub/cub.cuh>
+
+#include "pm_common.cuh"
+
+namespace pm {
+
+__global__ void k_degm_and_keys(const uint32_t* __restrict__ src, const uint32_t* __restrict__ dst,
+                                uint64_t n, uint32_t* __restrict__ degm,
+                                unsigned long long* __restrict__ keys) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    uint32_t s = src[i], d = dst[i];
+    atomicAdd(&degm[s], 1u);
+    keys[i] = ((unsigned long long)s << 32) | d;
+  }
+}
+
+__global__ void k_distinct_degree(const unsigned long long* __restrict__ ukeys, uint64_t n,
+                                  uint32_t* __restrict__ deg) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) atomicAdd(&deg[(uint32_t)(ukeys[i] >> 32)], 1u);
+}
+
+__global__ void k_row_sectors(const uint32_t* __restrict__ deg, uint64_t V,
+                              uint32_t* __restrict__ sectors, unsigned long long* __restrict__ deg64) {
+  uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; v <= V; v += stride) {
+    uint32_t d = v < V ? deg[v] : 0u;
+    sectors[v] = (d + 7u) >> 3;
+    deg64[v] = d;
+  }
+}
+
+__global__ void k_scatter_cols(const unsigned long long* __restrict__ ukeys, uint64_t n,
+                               const uint32_t* __restrict__ rowblk,
+                               const unsigned long long* __restrict__ ustart,
+                               uint32_t* __restrict__ col0) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    unsigned long long k = ukeys[i];
+    uint32_t v = (uint32_t)(k >> 32);
+    uint64_t pos = (uint64_t)rowblk[v] * 8 + (i - ustart[v]);
+    col0[pos] = (uint32_t)k;
+  }
+}
+
+// label = ceil(log2(degree + 1)) == bit length of the degree
+// (include/havoqgt/vertex_data_db_degree.hpp:109; exact integer form)
+__global__ void k_labels_degree_log2(const uint32_t* __restrict__ degm, uint64_t V,
+                                     uint64_t* __restrict__ label) {
+  uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; v < V; v += stride) label[v] = (uint64_t)(32 - __clz(degm[v]));
+}
+
+inline void graph_free(pm_ctx* c) {
+  dev_free(c->rowblk);
+  dev_free(c->deg);
+  dev_free(c->degm);
+  dev_free(c->col0);
+  dev_free(c->colw);
+  dev_free(c->label);
+  c->has_graph = c->has_labels = false;
+  c->graph_bytes = 0;
+}
+
+// d_src / d_dst: device arrays of n directed slots (consumed, freed by the caller).
+inline int graph_build_from_device_slots(pm_ctx* c, uint64_t V, uint64_t n, const uint32_t* d_src,
+                                         const uint32_t* d_dst) {
+  if (V == 0 || V > (1ull << 31)) return fail(c, PM_ERR_ARG, "n_vertices must be in [1, 2^31]");
+  graph_free(c);
+  cudaStream_t st = c->stream;
+  c->V = c->nloc = V;
+  c->E_multi = n;
+  uint64_t bytes = 0;
+  int rc;
+  if ((rc = dev_alloc(c, &c->degm, V, &bytes))) return rc;
+  if ((rc = dev_alloc(c, &c->deg, V, &bytes))) return rc;
+  if ((rc = dev_alloc(c, &c->rowblk, V + 1, &bytes))) return rc;
+  PM_CUDA(c, cudaMemsetAsync(c->degm, 0, V * sizeof(uint32_t), st));
+  PM_CUDA(c, cudaMemsetAsync(c->deg, 0, V * sizeof(uint32_t), st));
+
+  unsigned long long *keys = nullptr, *keys2 = nullptr, *ustart = nullptr, *d_nuniq = nullptr;
+  uint32_t* sectors = nullptr;
+  void* tmp = nullptr;
+  auto cleanup = [&]() {
+    dev_free(keys); dev_free(keys2); dev_free(ustart); dev_free(d_nuniq); dev_free(sectors);
+    if (tmp) cudaFree(tmp);
+    tmp = nullptr;
+  };
+#define PM_G(call) do { int rc_ = (call); if (rc_) { cleanup(); return rc_; } } while (0)
+#define PM_GC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); \
+    return fail(c, PM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
+  PM_G(dev_alloc(c, &keys, n));
+  PM_G(dev_alloc(c, &keys2, n));
+  PM_G(dev_alloc(c, &d_nuniq, 1));
+  const int grid = grid_for();
+  if (n) {
+    k_degm_and_keys<<<grid, kBlock, 0, st>>>(d_src, d_dst, n, c->degm, keys);
+    c->launches++;
+    PM_GC(cudaGetLastError());
+  }
+  // sort (src,dst) keys; only the bits that can be set take part
+  int bits = 32;
+  while (bits < 64 && (V - 1) >> (bits - 32)) ++bits;
+  size_t tmp_bytes = 0, tb2 = 0;
+  cub::DoubleBuffer<unsigned long long> db(keys, keys2);
+  PM_GC(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, db, (int64_t)n, 0, bits, st));
+  PM_GC(cub::DeviceSelect::Unique(nullptr, tb2, keys, keys2, d_nuniq, (int64_t)n, st));
+  tmp_bytes = std::max(tmp_bytes, tb2);
+  PM_GC(cudaMalloc(&tmp, std::max<size_t>(tmp_bytes, 16)));
+  PM_GC(cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, db, (int64_t)n, 0, bits, st));
+  unsigned long long* sorted = db.Current();
+  unsigned long long* ukeys = db.Alternate();
+  PM_GC(cub::DeviceSelect::Unique(tmp, tmp_bytes, sorted, ukeys, d_nuniq, (int64_t)n, st));
+  unsigned long long h_nuniq = 0;
+  PM_GC(cudaMemcpyAsync(&h_nuniq, d_nuniq, sizeof(h_nuniq), cudaMemcpyDeviceToHost, st));
+  PM_GC(cudaStreamSynchronize(st));
+  c->E = h_nuniq;
+  if (h_nuniq) {
+    k_distinct_degree<<<grid, kBlock, 0, st>>>(ukeys, h_nuniq, c->deg);
+    c->launches++;
+    PM_GC(cudaGetLastError());
+  }
+  // row starts (in sectors) and starts in the unique list
+  PM_G(dev_alloc(c, &sectors, V + 1));
+  PM_G(dev_alloc(c, &ustart, V + 1));
+  unsigned long long* deg64 = nullptr;
+  PM_G(dev_alloc(c, &deg64, V + 1));
+  k_row_sectors<<<grid, kBlock, 0, st>>>(c->deg, V, sectors, deg64);
+  c->launches++;
+  size_t tb3 = 0, tb4 = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tb3, sectors, c->rowblk, (int64_t)(V + 1), st);
+  cub::DeviceScan::ExclusiveSum(nullptr, tb4, deg64, ustart, (int64_t)(V + 1), st);
+  if (std::max(tb3, tb4) > tmp_bytes) {
+    cudaFree(tmp);
+    tmp = nullptr;
+    tmp_bytes = std::max(tb3, tb4);
+    PM_GC(cudaMalloc(&tmp, tmp_bytes));
+  }
+  PM_GC(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, sectors, c->rowblk, (int64_t)(V + 1), st));
+  PM_GC(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, deg64, ustart, (int64_t)(V + 1), st));
+  uint32_t h_total_sectors = 0;
+  PM_GC(cudaMemcpyAsync(&h_total_sectors, c->rowblk + V, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  // largest multigraph degree
+  uint32_t* d_max = (uint32_t*)d_nuniq;
+  size_t tb5 = 0;
+  cub::DeviceReduce::Max(nullptr, tb5, c->degm, d_max, (int64_t)V, st);
+  if (tb5 > tmp_bytes) {
+    cudaFree(tmp);
+    tmp = nullptr;
+    tmp_bytes = tb5;
+    PM_GC(cudaMalloc(&tmp, tmp_bytes));
+  }
+  PM_GC(cub::DeviceReduce::Max(tmp, tmp_bytes, c->degm, d_max, (int64_t)V, st));
+  uint32_t h_max = 0;
+  PM_GC(cudaMemcpyAsync(&h_max, d_max, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  PM_GC(cudaStreamSynchronize(st));
+  c->max_deg = h_max;
+  // +64 slots of slack: the scan kernels read whole uint4 windows
+  c->Epad = (uint64_t)h_total_sectors * 8;
+  const uint64_t alloc_slots = c->Epad + 64;
+  {
+    int rc2 = dev_alloc(c, &c->col0, alloc_slots, &bytes);
+    if (rc2) { cleanup(); dev_free(deg64); return rc2; }
+    rc2 = dev_alloc(c, &c->colw, alloc_slots, &bytes);
+    if (rc2) { cleanup(); dev_free(deg64); return rc2; }
+  }
+  PM_GC(cudaMemsetAsync(c->col0, 0xFF, alloc_slots * sizeof(uint32_t), st));
+  PM_GC(cudaMemsetAsync(c->colw, 0xFF, alloc_slots * sizeof(uint32_t), st));
+  if (h_nuniq) {
+    k_scatter_cols<<<grid, kBlock, 0, st>>>(ukeys, h_nuniq, c->rowblk, ustart, c->col0);
+    c->launches++;
+    PM_GC(cudaGetLastError());
+  }
+  PM_GC(cudaStreamSynchronize(st));
+  dev_free(deg64);
+  cleanup();
+#undef PM_G
+#undef PM_GC
+  c->graph_bytes = bytes;
+  c->has_graph = true;
+  c->state_ready = false;
+  return 0;
+}
+
+}  // namespace pm

@@ -1,0 +1,341 @@
+// pm_nlcc.cuh — non-local constraint checking (NLCC) as a batched GPU token queue.
+//
+// Replaces the reference's asynchronous token visitors
+//   nem_1  tppm_visitor      (token_passing_pattern_matching_nonunique_nem_1.hpp:98-303, 311-861)
+//   TDS    tppm_visitor_tds  (token_passing_pattern_matching_nonunique_tds_batch_1.hpp:122-335, 347-919)
+// and the driver's post-processing of token_source_map (src/run_pattern_matching_beta.cpp:956-1062).
+// Paths relative to /root/reference (headers under include/havoqgt/).
+//
+// Formulation.  Nothing a token reads (vertex_active, template_vertices,
+// vertex_active_edges_map keys) is written while a constraint runs, so the walk
+// can be advanced one hop per kernel: level h of the token pool holds the tokens
+// ACCEPTED at hop h; k_*_expand walks E_v of every token's vertex v and applies
+// the receiver's pre_visit tests of hop h+1 at emission time, so only accepted
+// tokens are ever stored.
+//   nem_1: token = (vertex, source); per-(vertex, source) work aggregation
+//          (vertex_token_source_set, nem_1.hpp:131-139, 270-285) is an
+//          open-addressing device hash set.  The final hop stores nothing: a path
+//          constraint acknowledges the source (ok[s] = 1, nem_1.hpp:683-727,
+//          326-342), a cycle constraint additionally flags the edge the token
+//          came back on (nem_1.hpp:764-770) in bit 31 of the working adjacency.
+//          The reference never forwards a token to the parent it came from
+//          (nem_1.hpp:836-838); that parent is always rejected downstream when
+//          interior hop labels are pairwise distinct and P[h-1] != P[h+1]
+//          (SURVEY A.6 #7), which pm_pattern_load_dir verifies per constraint —
+//          otherwise the reference result is arrival-order dependent.
+//   TDS:   aggregation off (enable_vertex_token_source_cache = false,
+//          tds_batch_1.hpp:11); token = (index of parent token, vertex), the
+//          visited history (tds_batch_1.hpp:964) is recovered by walking parent
+//          links, and the enumeration-index rule (tds_batch_1.hpp:284-302,
+//          622-639, 808-886) is tested against it.  Completed walks are appended
+//          to a match list and materialised for the subgraph files on request.
+#pragma once
+
+#include "pm_common.cuh"
+#include "pm_lcc.cuh"
+
+namespace pm {
+
+__constant__ NlcConst c_nlc;
+
+#define PM_HSET_EMPTY 0xFFFFFFFFFFFFFFFFull
+
+struct NlcArgs {
+  const uint32_t* rowblk;
+  uint32_t* colw;
+  const uint16_t* S;
+  const uint32_t* adeg;
+  const uint8_t* cls;
+  uint8_t* ok;
+  uint32_t* src_list;
+  unsigned long long* hset;
+  uint64_t hset_mask;
+  uint2* pool;
+  uint64_t pool_cap;
+  uint2* matches;      // TDS: (token index at the penultimate level, final vertex)
+  uint64_t match_cap;
+  DevCounters* cnt;
+};
+
+__device__ __forceinline__ bool hop_ok(uint32_t su, uint32_t cu, int h) {
+  // active + label + template bit of hop h (nem_1.hpp:101,186-210; tds_batch_1.hpp:125,207-233)
+  return cu == c_nlc.cls[h] && ((su >> c_nlc.I[h]) & 1u);
+}
+
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+  return x;
+}
+
+// true iff (u, s) was not in the set before
+__device__ __forceinline__ bool hset_insert(const NlcArgs& a, uint32_t u, uint32_t s) {
+  const unsigned long long key = ((unsigned long long)u << 32) | s;
+  uint64_t h = mix64(key) & a.hset_mask;
+  for (int probe = 0; probe < 256; ++probe) {
+    const unsigned long long prev = atomicCAS(&a.hset[h], PM_HSET_EMPTY, key);
+    if (prev == PM_HSET_EMPTY) return true;
+    if (prev == key) return false;
+    h = (h + 1) & a.hset_mask;
+  }
+  a.cnt->overflow = 1u;
+  return false;
+}
+
+// ---------------------------------------------------------------------------
+// token sources (nem_1.hpp:387-527; tds_batch_1.hpp:1067-1135, 425-512)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_nlcc_sources(NlcArgs a, const uint32_t* __restrict__ l0,
+                                                          const uint32_t* __restrict__ l1,
+                                                          const uint32_t* __restrict__ l2, int cur, int tds) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t c0 = a.cnt->fr_n[cur][0], c1 = a.cnt->fr_n[cur][1], c2 = a.cnt->fr_n[cur][2];
+  const uint32_t total = c0 + c1 + c2;
+  uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u;
+  for (; i0 < total; i0 += gridDim.x * blockDim.x) {
+    const uint32_t i = i0 + lane;
+    bool is_src = false;
+    uint32_t v = 0;
+    if (i < total) {
+      v = i < c0 ? l0[i] : (i < c0 + c1 ? l1[i - c0] : l2[i - c0 - c1]);
+      const uint32_t T = a.S[v];
+      is_src = T != 0 && hop_ok(T, a.cls[v], 0);
+      // path checking starts only from vertices that match BOTH end points (nem_1.hpp:447-451)
+      if (is_src && !tds && !c_nlc.valid_cycle) is_src = (T >> c_nlc.I[c_nlc.n - 1]) & 1u;
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, is_src);
+    if (m) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(&a.cnt->n_src, (uint32_t)__popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (is_src) {
+        const uint32_t pos = base + __popc(m & lanemask_lt());
+        a.src_list[pos] = v;
+        a.ok[v] = 0;
+        // level 0 of the token pool; n_src never exceeds V <= pool_cap
+        a.pool[pos] = tds ? make_uint2(0xFFFFFFFFu, v) : make_uint2(v, v);
+      }
+    }
+  }
+}
+
+// flag the edge (s -> parent) a successful cycle token came back on (nem_1.hpp:764-770)
+__device__ __forceinline__ void mark_edge(const NlcArgs& a, uint32_t s, uint32_t parent) {
+  const uint64_t row = (uint64_t)a.rowblk[s] * 8;
+  uint32_t lo = 0, hi = a.adeg[s];
+  while (lo < hi) {  // rows stay ascending: compaction is stable
+    const uint32_t mid = (lo + hi) >> 1;
+    const uint32_t x = a.colw[row + mid] & PM_IDMASK;
+    if (x < parent) lo = mid + 1; else hi = mid;
+  }
+  if (lo < a.adeg[s] && (a.colw[row + lo] & PM_IDMASK) == parent) atomicOr(&a.colw[row + lo], 0x80000000u);
+}
+
+// ---------------------------------------------------------------------------
+// nem_1: advance tokens [lo, hi) (accepted at hop hn-1) to hop hn
+// ---------------------------------------------------------------------------
+template <bool FINAL>
+__global__ void __launch_bounds__(kBlock) k_nem1_expand(NlcArgs a, uint64_t lo, uint64_t hi, int hn) {
+  constexpr int GROUP = 8;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t gl = lane % GROUP, gw = lane / GROUP;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  unsigned long long fan = 0;
+  for (uint64_t base = lo + warp * 4; base < hi; base += nwarps * 4) {
+    const uint64_t t = base + gw;
+    const bool has = t < hi;
+    uint32_t v = 0, s = 0, d = 0;
+    if (has) {
+      const uint2 tk = a.pool[t];
+      v = tk.x;
+      s = tk.y;
+      d = a.adeg[v];
+    }
+    const uint64_t row = has ? (uint64_t)a.rowblk[v] * 8 : 0;
+    const uint32_t passes = (d + GROUP * 4 - 1) / (GROUP * 4);
+    const uint32_t maxp = __reduce_max_sync(0xffffffffu, passes);
+    for (uint32_t p = 0; p < maxp; ++p) {
+      const uint32_t j0 = p * GROUP * 4 + gl * 4;
+      uint4 q = make_uint4(0, 0, 0, 0);
+      if (j0 < d) q = *reinterpret_cast<const uint4*>(a.colw + row + j0);
+      const uint32_t u[4] = {q.x & PM_IDMASK, q.y & PM_IDMASK, q.z & PM_IDMASK, q.w & PM_IDMASK};
+      bool pass_static[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        pass_static[k] = false;
+        if (j0 + k < d) {
+          const uint32_t su = a.S[u[k]];
+          pass_static[k] = su != 0 && hop_ok(su, a.cls[u[k]], hn);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (FINAL) {
+          // max_itr_count == itr_count (nem_1.hpp:661-791)
+          const bool succ = pass_static[k] && (c_nlc.valid_cycle ? u[k] == s : u[k] != s);
+          if (succ) {
+            a.ok[s] = 1;
+            a.cnt->found = 1u;
+            if (c_nlc.valid_cycle) mark_edge(a, s, v);
+          }
+        } else {
+          // interior hop: the source cannot relay (nem_1.hpp:174-177), one token per
+          // (vertex, source) (nem_1.hpp:131-139, 270-285)
+          bool ins = pass_static[k] && u[k] != s;
+          if (ins) ins = hset_insert(a, u[k], s);
+          const uint32_t b = __ballot_sync(0xffffffffu, ins);
+          if (b) {
+            unsigned long long pbase = 0;
+            if (lane == 0) pbase = atomicAdd(&a.cnt->pool_n, (unsigned long long)__popc(b));
+            pbase = __shfl_sync(0xffffffffu, pbase, 0);
+            if (ins) {
+              const unsigned long long pos = pbase + __popc(b & lanemask_lt());
+              if (pos < a.pool_cap) a.pool[pos] = make_uint2(u[k], s); else a.cnt->overflow = 1u;
+            }
+          }
+        }
+      }
+    }
+    if (has && gl == 0) fan += d;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) fan += __shfl_xor_sync(0xffffffffu, fan, o);
+  if (lane == 0 && fan) atomicAdd(&a.cnt->fanout, fan);
+}
+
+// ---------------------------------------------------------------------------
+// TDS: advance tokens [lo, hi) of level h = hn-1 to hop hn.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ bool hist_rule(const uint32_t (&hist)[16], int hp, uint32_t x) {
+  const int e = c_nlc.e[hp];
+  bool dup = false, eq = false;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    if (i < hp && hist[i] == x) dup = true;
+    if (i == e && hist[i] == x) eq = true;
+  }
+  if (e == hp) return !dup;   // a new vertex must differ from everything visited
+  if (e < hp) return eq;      // a revisit must equal visited[e]
+  return false;               // "invalid value" branches drop the token
+}
+
+template <bool FINAL>
+__global__ void __launch_bounds__(kBlock) k_tds_expand(NlcArgs a, uint64_t lo, uint64_t hi, int hn) {
+  constexpr int GROUP = 8;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t gl = lane % GROUP, gw = lane / GROUP;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  const int h = hn - 1;
+  unsigned long long fan = 0;
+  for (uint64_t base = lo + warp * 4; base < hi; base += nwarps * 4) {
+    const uint64_t t = base + gw;
+    const bool has = t < hi;
+    uint32_t hist[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) hist[i] = 0xFFFFFFFFu;
+    uint32_t v = 0, d = 0;
+    if (has) {
+      uint2 tk = a.pool[t];
+      v = tk.y;
+      // walk the parent links: hist[h] = v, hist[h-1] = parent's vertex, ...
+#pragma unroll
+      for (int i = 15; i >= 0; --i) {
+        if (i == h) hist[i] = v;
+        if (i < h) {
+          tk = a.pool[tk.x];
+          hist[i] = tk.y;
+        }
+      }
+      d = a.adeg[v];
+    }
+    const uint32_t s = hist[0];
+    const uint64_t row = has ? (uint64_t)a.rowblk[v] * 8 : 0;
+    const uint32_t passes = (d + GROUP * 4 - 1) / (GROUP * 4);
+    const uint32_t maxp = __reduce_max_sync(0xffffffffu, passes);
+    for (uint32_t p = 0; p < maxp; ++p) {
+      const uint32_t j0 = p * GROUP * 4 + gl * 4;
+      uint4 q = make_uint4(0, 0, 0, 0);
+      if (j0 < d) q = *reinterpret_cast<const uint4*>(a.colw + row + j0);
+      const uint32_t u[4] = {q.x & PM_IDMASK, q.y & PM_IDMASK, q.z & PM_IDMASK, q.w & PM_IDMASK};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        bool acc = false;
+        if (j0 + k < d) {
+          const uint32_t su = a.S[u[k]];
+          acc = su != 0 && hop_ok(su, a.cls[u[k]], hn);
+          if (acc) {
+            if (FINAL)  // penultimate-hop filter of the sender (tds_batch_1.hpp:808-845)
+              acc = c_nlc.valid_cycle ? (u[k] == s) : (u[k] != s && hist_rule(hist, hn, u[k]));
+            else        // tds_batch_1.hpp:284-302 (receiver) == :846-886 (sender)
+              acc = hist_rule(hist, hn, u[k]);
+          }
+        }
+        const uint32_t b = __ballot_sync(0xffffffffu, acc);
+        if (b) {
+          unsigned long long pbase = 0;
+          if (lane == 0)
+            pbase = atomicAdd(FINAL ? &a.cnt->matches : &a.cnt->pool_n, (unsigned long long)__popc(b));
+          pbase = __shfl_sync(0xffffffffu, pbase, 0);
+          if (acc) {
+            const unsigned long long pos = pbase + __popc(b & lanemask_lt());
+            if (FINAL) {
+              // walk completed (tds_batch_1.hpp:664-694, 699-750)
+              a.ok[s] = 1;
+              a.cnt->found = 1u;
+              if (a.matches && pos < a.match_cap) a.matches[pos] = make_uint2((uint32_t)t, u[k]);
+            } else if (pos < a.pool_cap) {
+              a.pool[pos] = make_uint2((uint32_t)t, u[k]);
+            } else {
+              a.cnt->overflow = 1u;
+            }
+          }
+        }
+      }
+    }
+    if (has && gl == 0) fan += d;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) fan += __shfl_xor_sync(0xffffffffu, fan, o);
+  if (lane == 0 && fan) atomicAdd(&a.cnt->fanout, fan);
+}
+
+// rows_out[i * width + j] = j-th vertex of completed walk i (subgraph file rows, tds_batch_1.hpp:685-689)
+__global__ void k_tds_materialize(const uint2* __restrict__ pool, const uint2* __restrict__ matches,
+                                  uint64_t n, int width, uint32_t* __restrict__ rows_out) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const uint2 mt = matches[i];
+    uint32_t* r = rows_out + i * width;
+    r[width - 1] = mt.y;
+    uint32_t t = mt.x;
+    for (int j = width - 2; j >= 0; --j) {
+      const uint2 tk = pool[t];
+      r[j] = tk.y;
+      t = tk.x;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// post-processing of token_source_map (beta.cpp:964-1005, 1043-1062): a source
+// whose walk never completed loses bit pattern_indices[0] in template_vertices
+// (T_arr ONLY — vertex_state.template_vertices keeps it); with no
+// bit left it is deactivated and leaves the vertex_state_map (S == 0).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_nlcc_apply(uint16_t* __restrict__ S, const uint8_t* __restrict__ ok,
+                                                        const uint32_t* __restrict__ src_list,
+                                                        DevCounters* cnt) {
+  const uint32_t n = cnt->n_src;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t s = src_list[i];
+    if (ok[s]) continue;
+    const uint32_t T = S[s];
+    if (T == 0) continue;
+    S[s] = (uint16_t)(T & ~(1u << c_nlc.I[0]));
+    cnt->deleted = 1u;
+  }
+}
+
+}  // namespace pm

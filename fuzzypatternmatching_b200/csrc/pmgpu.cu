@@ -1,0 +1,729 @@
+// pmgpu.cu — C ABI of libpmgpu.so (see include/pmgpu.h) and the host-side driver
+// loop that mirrors /root/reference/src/run_pattern_matching_beta.cpp:544-1351.
+// Compiled for sm_100a only.  There is no CPU path: every entry point that
+// computes anything launches the kernels in pm_graph.cuh / pm_lcc.cuh / pm_nlcc.cuh.
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <map>
+
+#include "pm_common.cuh"
+#include "pm_graph.cuh"
+#include "pm_lcc.cuh"
+#include "pm_nlcc.cuh"
+#include "pm_rmat.cuh"
+
+using namespace pm;
+
+namespace {
+
+double wall_s() {
+  using namespace std::chrono;
+  return duration<double>(steady_clock::now().time_since_epoch()).count();
+}
+
+int sync_counters(pm_ctx* c) {
+  PM_CUDA(c, cudaMemcpyAsync(c->h_cnt, c->cnt, sizeof(DevCounters), cudaMemcpyDeviceToHost, c->stream));
+  PM_CUDA(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+LccArgs lcc_args(pm_ctx* c, int row) {
+  LccArgs a;
+  a.rowblk = c->rowblk; a.deg = c->deg; a.col0 = c->col0; a.colw = c->colw;
+  a.S = c->S; a.Tst = c->Tst; a.adeg = c->adeg; a.cls = c->cls; a.cnt = c->cnt;
+  a.row = c->rowstat + row;
+  return a;
+}
+
+NlcArgs nlc_args(pm_ctx* c, uint2* matches, uint64_t match_cap) {
+  NlcArgs a;
+  a.rowblk = c->rowblk; a.colw = c->colw; a.S = c->S; a.adeg = c->adeg; a.cls = c->cls;
+  a.ok = c->ok; a.src_list = c->src_list; a.hset = c->hset; a.hset_mask = c->hset_cap - 1;
+  a.pool = c->pool; a.pool_cap = c->pool_cap; a.matches = matches; a.match_cap = match_cap;
+  a.cnt = c->cnt;
+  return a;
+}
+
+void state_free(pm_ctx* c) {
+  dev_free(c->S); dev_free(c->Tst); dev_free(c->adeg); dev_free(c->cls);
+  for (int b = 0; b < 2; ++b) for (int k = 0; k < 3; ++k) dev_free(c->fr[b][k]);
+  dev_free(c->cnt); dev_free(c->rowstat); dev_free(c->ok); dev_free(c->src_list);
+  dev_free(c->hset); dev_free(c->pool);
+  if (c->h_cnt) cudaFreeHost(c->h_cnt);
+  if (c->h_rowstat) cudaFreeHost(c->h_rowstat);
+  c->h_cnt = nullptr; c->h_rowstat = nullptr;
+  c->hset_cap = c->pool_cap = 0;
+  c->state_ready = false;
+}
+
+// nem_1's result is independent of message arrival order iff interior hop labels
+// are pairwise distinct and P[h-1] != P[h+1].
+bool nem1_order_independent(const Constraint& k) {
+  const size_t n = k.P.size();
+  for (size_t a = 1; a + 1 < n; ++a)
+    for (size_t b = a + 1; b + 1 < n; ++b)
+      if (k.P[a] == k.P[b]) return false;
+  for (size_t h = 1; h + 1 < n; ++h)
+    if (k.P[h - 1] == k.P[h + 1]) return false;
+  return true;
+}
+
+int nlcc_reserve(pm_ctx* c, uint64_t pool_cap) {
+  if (pool_cap <= c->pool_cap) return 0;
+  dev_free(c->pool);
+  dev_free(c->hset);
+  uint64_t hc = 1;
+  while (hc < 2 * pool_cap) hc <<= 1;
+  int rc;
+  if ((rc = dev_alloc(c, &c->pool, pool_cap))) { c->pool_cap = c->hset_cap = 0; return rc; }
+  if ((rc = dev_alloc(c, &c->hset, hc))) { c->pool_cap = c->hset_cap = 0; return rc; }
+  c->pool_cap = pool_cap;
+  c->hset_cap = hc;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pm_create(pm_ctx** out, int device) {
+  if (!out) return PM_ERR_ARG;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return PM_ERR_CUDA;  // no CPU fallback
+  if (device < 0 || device >= n) return PM_ERR_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return PM_ERR_CUDA;
+  pm_ctx* c = new pm_ctx();
+  c->device = device;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete c;
+    return PM_ERR_CUDA;
+  }
+  *out = c;
+  return 0;
+}
+
+void pm_destroy(pm_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  state_free(c);
+  graph_free(c);
+  for (auto e : c->events) cudaEventDestroy(e);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+const char* pm_last_error(const pm_ctx* c) { return c ? c->err.c_str() : "null context"; }
+uint64_t pm_kernel_launches(const pm_ctx* c) { return c ? c->launches : 0; }
+
+int pm_comm_unique_id(char id_out[PM_COMM_ID_BYTES]) {
+  std::memset(id_out, 0, PM_COMM_ID_BYTES);
+  return PM_ERR_UNSUPPORTED;
+}
+int pm_comm_init(pm_ctx* c, int rank, int n_ranks, const char*) {
+  if (n_ranks == 1 && rank == 0) return 0;
+  return fail(c, PM_ERR_UNSUPPORTED, "multi-GPU partitioning is not built into this library yet");
+}
+
+// ------------------------------------------------------------------ graph
+int pm_graph_from_slots(pm_ctx* c, uint64_t n_vertices, uint64_t n_slots, const uint32_t* src,
+                        const uint32_t* dst) {
+  if (!c || (n_slots && (!src || !dst))) return fail(c, PM_ERR_ARG, "pm_graph_from_slots: null argument");
+  PM_CUDA(c, cudaSetDevice(c->device));
+  state_free(c);
+  uint32_t *d_src = nullptr, *d_dst = nullptr;
+  int rc;
+  if ((rc = dev_alloc(c, &d_src, n_slots))) return rc;
+  if ((rc = dev_alloc(c, &d_dst, n_slots))) { dev_free(d_src); return rc; }
+  cudaError_t e1 = cudaMemcpyAsync(d_src, src, n_slots * 4, cudaMemcpyHostToDevice, c->stream);
+  cudaError_t e2 = cudaMemcpyAsync(d_dst, dst, n_slots * 4, cudaMemcpyHostToDevice, c->stream);
+  if (e1 != cudaSuccess || e2 != cudaSuccess) {
+    dev_free(d_src); dev_free(d_dst);
+    return fail(c, PM_ERR_CUDA, "pm_graph_from_slots: host to device copy failed");
+  }
+  rc = graph_build_from_device_slots(c, n_vertices, n_slots, d_src, d_dst);
+  dev_free(d_src);
+  dev_free(d_dst);
+  return rc;
+}
+
+int pm_graph_rmat(pm_ctx* c, uint64_t scale, uint64_t gen_ranks) {
+  if (!c) return PM_ERR_ARG;
+  PM_CUDA(c, cudaSetDevice(c->device));
+  state_free(c);
+  return rmat_build(c, scale, gen_ranks);
+}
+
+int pm_graph_info(const pm_ctx* c, pm_graph_info_t* o) {
+  if (!c || !o || !c->has_graph) return PM_ERR_ARG;
+  o->n_vertices = c->V; o->n_local = c->nloc; o->n_slots_multi = c->E_multi; o->n_slots = c->E;
+  o->n_slots_padded = c->Epad; o->max_degree = c->max_deg; o->device_bytes = c->graph_bytes;
+  return 0;
+}
+
+int pm_graph_get_degree(const pm_ctx* cc, uint64_t* out) {
+  pm_ctx* c = const_cast<pm_ctx*>(cc);
+  if (!c || !c->has_graph || !out) return PM_ERR_ARG;
+  std::vector<uint32_t> h(c->V);
+  PM_CUDA(c, cudaMemcpy(h.data(), c->degm, c->V * 4, cudaMemcpyDeviceToHost));
+  for (uint64_t v = 0; v < c->V; ++v) out[v] = h[v];
+  return 0;
+}
+
+int pm_graph_get_csr(const pm_ctx* cc, uint64_t* rowptr_out, uint32_t* col_out) {
+  pm_ctx* c = const_cast<pm_ctx*>(cc);
+  if (!c || !c->has_graph || !rowptr_out || !col_out) return PM_ERR_ARG;
+  std::vector<uint32_t> deg(c->V), blk(c->V + 1), col(c->Epad);
+  PM_CUDA(c, cudaMemcpy(deg.data(), c->deg, c->V * 4, cudaMemcpyDeviceToHost));
+  PM_CUDA(c, cudaMemcpy(blk.data(), c->rowblk, (c->V + 1) * 4, cudaMemcpyDeviceToHost));
+  PM_CUDA(c, cudaMemcpy(col.data(), c->col0, c->Epad * 4, cudaMemcpyDeviceToHost));
+  uint64_t o = 0;
+  for (uint64_t v = 0; v < c->V; ++v) {
+    rowptr_out[v] = o;
+    std::memcpy(col_out + o, col.data() + (uint64_t)blk[v] * 8, (size_t)deg[v] * 4);
+    o += deg[v];
+  }
+  rowptr_out[c->V] = o;
+  return 0;
+}
+
+// ------------------------------------------------------------------ labels
+int pm_labels_degree_log2(pm_ctx* c) {
+  if (!c || !c->has_graph) return fail(c, PM_ERR_ARG, "pm_labels_degree_log2: no graph");
+  PM_CUDA(c, cudaSetDevice(c->device));
+  if (!c->label) { int rc = dev_alloc(c, &c->label, c->V, &c->graph_bytes); if (rc) return rc; }
+  k_labels_degree_log2<<<grid_for(), kBlock, 0, c->stream>>>(c->degm, c->V, c->label);
+  PM_LAUNCH_CHECK(c);
+  c->has_labels = true;
+  c->state_ready = false;
+  return 0;
+}
+
+int pm_labels_set(pm_ctx* c, const uint64_t* labels) {
+  if (!c || !c->has_graph || !labels) return fail(c, PM_ERR_ARG, "pm_labels_set: no graph or null labels");
+  PM_CUDA(c, cudaSetDevice(c->device));
+  if (!c->label) { int rc = dev_alloc(c, &c->label, c->V, &c->graph_bytes); if (rc) return rc; }
+  PM_CUDA(c, cudaMemcpyAsync(c->label, labels, c->V * 8, cudaMemcpyHostToDevice, c->stream));
+  PM_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->has_labels = true;
+  c->state_ready = false;
+  return 0;
+}
+
+int pm_labels_get(const pm_ctx* cc, uint64_t* out) {
+  pm_ctx* c = const_cast<pm_ctx*>(cc);
+  if (!c || !c->has_labels || !out) return PM_ERR_ARG;
+  PM_CUDA(c, cudaStreamSynchronize(c->stream));
+  PM_CUDA(c, cudaMemcpy(out, c->label, c->V * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// ----------------------------------------------------------------- pattern
+int pm_pattern_load_dir(pm_ctx* c, const char* dir) {
+  if (!c || !dir) return PM_ERR_ARG;
+  Pattern p;
+  std::string why = load_pattern_dir(dir, p);
+  if (!why.empty()) return fail(c, PM_ERR_PATTERN, why);
+  PatConst pc;
+  std::memset(&pc, 0, sizeof(pc));
+  for (int i = 0; i < 16; ++i) pc.N[i] = p.N[i];
+  // distinct template labels -> classes (ee.hpp:371-380 compares every template label)
+  for (size_t i = 0; i < p.vertex_label.size(); ++i) {
+    int k = 0;
+    while (k < pc.ncls && pc.clabel[k] != p.vertex_label[i]) ++k;
+    if (k == pc.ncls) pc.clabel[pc.ncls++] = p.vertex_label[i];
+    pc.LMc[k] |= (uint16_t)(1u << i);
+  }
+  c->pat = p;
+  c->pc = pc;
+  c->has_pattern = true;
+  c->state_ready = false;
+  c->subgraphs.assign(p.constraints.size(), {});
+  c->subgraph_width.assign(p.constraints.size(), 0);
+  c->subgraph_count.assign(p.constraints.size(), 0);
+  return 0;
+}
+
+int pm_pattern_info(const pm_ctx* c, pm_pattern_info_t* o) {
+  if (!c || !o || !c->has_pattern) return PM_ERR_ARG;
+  o->n_vertices = c->pat.n_vertices; o->n_edges = c->pat.n_edges; o->diameter = c->pat.diameter;
+  o->n_constraints = (int)c->pat.constraints.size();
+  return 0;
+}
+
+// ------------------------------------------------------------------- state
+int pm_state_reset(pm_ctx* c) {
+  if (!c || !c->has_graph || !c->has_labels || !c->has_pattern)
+    return fail(c, PM_ERR_ARG, "pm_state_reset needs a graph, labels and a pattern");
+  PM_CUDA(c, cudaSetDevice(c->device));
+  const uint64_t V = c->V;
+  int rc;
+  if (!c->S) {
+    if ((rc = dev_alloc(c, &c->S, V))) return rc;
+    if ((rc = dev_alloc(c, &c->Tst, V))) return rc;
+    if ((rc = dev_alloc(c, &c->adeg, V))) return rc;
+    if ((rc = dev_alloc(c, &c->cls, V))) return rc;
+    if ((rc = dev_alloc(c, &c->ok, V))) return rc;
+    if ((rc = dev_alloc(c, &c->src_list, V))) return rc;
+    for (int b = 0; b < 2; ++b)
+      for (int k = 0; k < 3; ++k)
+        if ((rc = dev_alloc(c, &c->fr[b][k], V))) return rc;
+    if ((rc = dev_alloc(c, &c->cnt, 1))) return rc;
+    PM_CUDA(c, cudaMallocHost((void**)&c->h_cnt, sizeof(DevCounters)));
+  }
+  dev_free(c->rowstat);
+  if (c->h_rowstat) cudaFreeHost(c->h_rowstat);
+  c->h_rowstat = nullptr;
+  const int nrow = c->pat.diameter + 1;
+  if ((rc = dev_alloc(c, &c->rowstat, nrow))) return rc;
+  PM_CUDA(c, cudaMallocHost((void**)&c->h_rowstat, nrow * sizeof(RowStat)));
+  while ((int)c->events.size() < nrow + 1) {
+    cudaEvent_t e;
+    PM_CUDA(c, cudaEventCreate(&e));
+    c->events.push_back(e);
+  }
+  PM_CUDA(c, cudaMemcpyToSymbolAsync(c_pat, &c->pc, sizeof(PatConst), 0, cudaMemcpyHostToDevice, c->stream));
+  PM_CUDA(c, cudaMemsetAsync(c->cnt, 0, sizeof(DevCounters), c->stream));
+  c->cur = 0;
+  k_init_state<<<grid_for(), kBlock, 0, c->stream>>>(c->label, c->deg, V, c->cls, c->S, c->Tst, c->adeg,
+                                                     c->fr[0][0], c->fr[0][1], c->fr[0][2], c->cnt, 0);
+  PM_LAUNCH_CHECK(c);
+  PM_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->rows.clear();
+  c->step_rows.clear();
+  c->iter_seconds.clear();
+  c->itr = 0;
+  c->summary = pm_run_summary_t{};
+  for (auto& s : c->subgraphs) s.clear();
+  std::fill(c->subgraph_count.begin(), c->subgraph_count.end(), 0);
+  c->state_ready = true;
+  return 0;
+}
+
+// --------------------------------------------------------------------- LCC
+int pm_lcc(pm_ctx* c, int init_step, int* not_finished, pm_counts_t* counts_out) {
+  if (!c || !c->state_ready) return fail(c, PM_ERR_ARG, "pm_lcc: call pm_state_reset first");
+  PM_CUDA(c, cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  const int D = c->pat.diameter;
+  const int grid = grid_for();
+  const double t0 = wall_s();
+  PM_CUDA(c, cudaMemsetAsync(c->rowstat, 0, D * sizeof(RowStat), st));
+  PM_CUDA(c, cudaMemsetAsync(&c->cnt->nf, 0, sizeof(uint32_t), st));
+  for (int k = 0; k < D; ++k) {  // fixed superstep count (ee.hpp:1069)
+    const bool first = init_step && k == 0;
+    const int cur = c->cur, nxt = cur ^ 1;
+    PM_CUDA(c, cudaEventRecord(c->events[k], st));
+    PM_CUDA(c, cudaMemsetAsync(&c->cnt->fr_n[nxt][0], 0, 4 * sizeof(uint32_t), st));
+    LccArgs a = lcc_args(c, k);
+    if (first) {
+      k_lcc_scan<8, true><<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], &c->cnt->fr_n[cur][0]);
+      PM_LAUNCH_CHECK(c);
+      k_lcc_scan<32, true><<<grid, kBlock, 0, st>>>(a, c->fr[cur][1], &c->cnt->fr_n[cur][1]);
+      PM_LAUNCH_CHECK(c);
+      k_lcc_scan_big<true><<<148, 1024, 0, st>>>(a, c->fr[cur][2], &c->cnt->fr_n[cur][2]);
+      PM_LAUNCH_CHECK(c);
+    } else {
+      k_lcc_scan<8, false><<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], &c->cnt->fr_n[cur][0]);
+      PM_LAUNCH_CHECK(c);
+      k_lcc_scan<32, false><<<grid, kBlock, 0, st>>>(a, c->fr[cur][1], &c->cnt->fr_n[cur][1]);
+      PM_LAUNCH_CHECK(c);
+      k_lcc_scan_big<false><<<148, 1024, 0, st>>>(a, c->fr[cur][2], &c->cnt->fr_n[cur][2]);
+      PM_LAUNCH_CHECK(c);
+    }
+    k_lcc_commit<<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], c->fr[cur][1], c->fr[cur][2], c->fr[nxt][0],
+                                          c->fr[nxt][1], c->fr[nxt][2], cur, nxt);
+    PM_LAUNCH_CHECK(c);
+    c->cur = nxt;
+  }
+  PM_CUDA(c, cudaEventRecord(c->events[D], st));
+  PM_CUDA(c, cudaMemcpyAsync(c->h_rowstat, c->rowstat, D * sizeof(RowStat), cudaMemcpyDeviceToHost, st));
+  int rc = sync_counters(c);
+  if (rc) return rc;
+  if (c->h_cnt->nf && not_finished) *not_finished = 1;
+  for (int k = 0; k < D; ++k) {
+    float ms = 0;
+    PM_CUDA(c, cudaEventElapsedTime(&ms, c->events[k], c->events[k + 1]));
+    pm_row_t r;
+    r.itr = c->itr; r.kind = 0; r.index = k;
+    r.n_vertices = c->h_rowstat[k].nv; r.n_edges = c->h_rowstat[k].ne; r.seconds = ms * 1e-3;
+    c->rows.push_back(r);
+    if (counts_out) { counts_out[k].n_vertices = r.n_vertices; counts_out[k].n_edges = r.n_edges; counts_out[k].seconds = r.seconds; }
+    c->summary.device_seconds += r.seconds;
+    const uint64_t sc = c->h_rowstat[k].scanned;
+    c->summary.edges_processed += sc;
+    // SURVEY §8(d) byte model: 4 B column + 2 B neighbour mask per scanned slot;
+    // 12 B per scanned vertex (row start, own masks read + written, |E_v|)
+    c->summary.algorithmic_bytes += sc * 6;
+  }
+  c->step_rows.push_back({c->itr, wall_s() - t0});
+  return 0;
+}
+
+// -------------------------------------------------------------------- NLCC
+int pm_nlcc(pm_ctx* c, int pl, int mode, int* pattern_found, int* token_source_deleted,
+            pm_counts_t* counts_out) {
+  if (!c || !c->state_ready) return fail(c, PM_ERR_ARG, "pm_nlcc: call pm_state_reset first");
+  if (pl < 0 || pl >= (int)c->pat.constraints.size()) return fail(c, PM_ERR_ARG, "pm_nlcc: bad constraint index");
+  PM_CUDA(c, cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  const Constraint& k = c->pat.constraints[pl];
+  const bool tds = mode == PM_NLCC_TDS;
+  if (!tds && !nem1_order_independent(k))
+    return fail(c, PM_ERR_UNSUPPORTED,
+                "constraint " + std::to_string(pl) +
+                    ": repeated interior labels make the reference's nem_1 result depend on message "
+                    "arrival order (SURVEY A.6 #7); use template driven search for this constraint");
+  const int n = (int)k.P.size();
+  if (tds && (int)k.enum_idx.size() < n)
+    return fail(c, PM_ERR_PATTERN, "pattern_non_local_constraint has no enumeration indices for this walk");
+  NlcConst nc;
+  std::memset(&nc, 0, sizeof(nc));
+  nc.n = n; nc.C = (int)k.C; nc.valid_cycle = k.valid_cycle ? 1 : 0;
+  for (int h = 0; h < n; ++h) {
+    int cl = PM_NOCLASS;
+    for (int q = 0; q < c->pc.ncls; ++q) if (c->pc.clabel[q] == k.P[h]) cl = q;
+    nc.cls[h] = (uint8_t)cl;
+    nc.I[h] = (uint8_t)k.I[h];
+    nc.e[h] = (uint8_t)(tds ? std::min<uint32_t>(k.enum_idx[h], 255u) : h);
+  }
+  const int grid = grid_for();
+  const int D = c->pat.diameter;  // rowstat[D] is the TP row accumulator
+  PM_CUDA(c, cudaEventRecord(c->events[0], st));
+  PM_CUDA(c, cudaMemcpyToSymbolAsync(c_nlc, &nc, sizeof(NlcConst), 0, cudaMemcpyHostToDevice, st));
+  int rc;
+  if ((rc = nlcc_reserve(c, std::max<uint64_t>(c->V, 1ull << 20)))) return rc;
+  uint2* d_matches = nullptr;
+  uint64_t match_cap = 0;
+  const int cur = c->cur;
+  uint64_t n_matches = 0, lo = 0, hi = 0;
+  for (int attempt = 0;; ++attempt) {
+    if (tds && c->keep_subgraphs) {
+      match_cap = c->pool_cap;
+      dev_free(d_matches);
+      if ((rc = dev_alloc(c, &d_matches, match_cap))) return rc;
+    }
+    // zero found .. hash_n, keep the frontier counters and nf
+    PM_CUDA(c, cudaMemsetAsync(&c->cnt->found, 0, sizeof(DevCounters) - offsetof(DevCounters, found), st));
+    if (!tds) PM_CUDA(c, cudaMemsetAsync(c->hset, 0xFF, c->hset_cap * sizeof(unsigned long long), st));
+    NlcArgs a = nlc_args(c, d_matches, match_cap);
+    k_nlcc_sources<<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], c->fr[cur][1], c->fr[cur][2], cur, tds ? 1 : 0);
+    PM_LAUNCH_CHECK(c);
+    if ((rc = sync_counters(c))) { dev_free(d_matches); return rc; }
+    lo = 0;
+    hi = c->h_cnt->n_src;
+    unsigned long long pn = hi;
+    PM_CUDA(c, cudaMemcpyAsync(&c->cnt->pool_n, &pn, sizeof(pn), cudaMemcpyHostToDevice, st));
+    bool overflow = false;
+    for (int hn = 1; hn <= (int)k.C + 1 && hi > lo; ++hn) {
+      const bool fin = hn == (int)k.C + 1;
+      if (tds) {
+        if (fin) k_tds_expand<true><<<grid, kBlock, 0, st>>>(a, lo, hi, hn);
+        else k_tds_expand<false><<<grid, kBlock, 0, st>>>(a, lo, hi, hn);
+      } else {
+        if (fin) k_nem1_expand<true><<<grid, kBlock, 0, st>>>(a, lo, hi, hn);
+        else k_nem1_expand<false><<<grid, kBlock, 0, st>>>(a, lo, hi, hn);
+      }
+      PM_LAUNCH_CHECK(c);
+      if ((rc = sync_counters(c))) { dev_free(d_matches); return rc; }
+      // the pool / hash set ran out, or more walks completed than the match list holds
+      if (c->h_cnt->overflow || (tds && fin && c->keep_subgraphs && c->h_cnt->matches > match_cap)) {
+        overflow = true;
+        break;
+      }
+      lo = hi;
+      hi = c->h_cnt->pool_n;
+    }
+    if (!overflow) { n_matches = c->h_cnt->matches; break; }
+    if (attempt >= 6) { dev_free(d_matches); return fail(c, PM_ERR_CAPACITY, "NLCC token pool exhausted"); }
+    const uint64_t want = std::max<uint64_t>(c->pool_cap * 4, (uint64_t)c->h_cnt->matches + 1);
+    if ((rc = nlcc_reserve(c, want))) { dev_free(d_matches); return rc; }
+  }
+  const uint64_t fanout = c->h_cnt->fanout;
+  const int found = c->h_cnt->found;
+  // post-processing of token_source_map (beta.cpp:956-1062) and the TP row (beta.cpp:1094-1120)
+  k_nlcc_apply<<<grid, kBlock, 0, st>>>(c->S, c->ok, c->src_list, c->cnt);
+  PM_LAUNCH_CHECK(c);
+  PM_CUDA(c, cudaMemsetAsync(c->rowstat + D, 0, sizeof(RowStat), st));
+  LccArgs la = lcc_args(c, D);
+  k_count_alive<<<grid, kBlock, 0, st>>>(la, c->fr[cur][0], c->fr[cur][1], c->fr[cur][2], cur);
+  PM_LAUNCH_CHECK(c);
+  // enumerated subgraphs (the file is truncated per outer iteration, beta.cpp:713-717)
+  if (tds) {
+    c->subgraph_width[pl] = n;
+    c->subgraph_count[pl] = n_matches;
+    c->subgraphs[pl].clear();
+    c->summary.path_count += n_matches;  // path_count is never reset (tds_batch_1.hpp:14,1243)
+    if (c->keep_subgraphs && n_matches) {
+      uint32_t* d_rows = nullptr;
+      if ((rc = dev_alloc(c, &d_rows, n_matches * n))) { dev_free(d_matches); return rc; }
+      k_tds_materialize<<<grid, kBlock, 0, st>>>(c->pool, d_matches, n_matches, n, d_rows);
+      c->launches++;
+      c->subgraphs[pl].resize(n_matches * n);
+      cudaError_t e = cudaMemcpyAsync(c->subgraphs[pl].data(), d_rows, n_matches * n * 4, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      dev_free(d_rows);
+      if (e != cudaSuccess) { dev_free(d_matches); return fail(c, PM_ERR_CUDA, cudaGetErrorString(e)); }
+    }
+  }
+  dev_free(d_matches);
+  PM_CUDA(c, cudaEventRecord(c->events[1], st));
+  PM_CUDA(c, cudaMemcpyAsync(c->h_rowstat + D, c->rowstat + D, sizeof(RowStat), cudaMemcpyDeviceToHost, st));
+  if ((rc = sync_counters(c))) return rc;
+  float ms = 0;
+  PM_CUDA(c, cudaEventElapsedTime(&ms, c->events[0], c->events[1]));
+  pm_row_t r;
+  r.itr = c->itr; r.kind = 1; r.index = pl;
+  r.n_vertices = c->h_rowstat[D].nv; r.n_edges = c->h_rowstat[D].ne; r.seconds = ms * 1e-3;
+  c->rows.push_back(r);
+  if (counts_out) { counts_out->n_vertices = r.n_vertices; counts_out->n_edges = r.n_edges; counts_out->seconds = r.seconds; }
+  if (pattern_found) *pattern_found = found;
+  if (token_source_deleted) *token_source_deleted = c->h_cnt->deleted ? 1 : 0;
+  c->summary.device_seconds += r.seconds;
+  c->summary.edges_processed += fanout;
+  c->summary.algorithmic_bytes += fanout * 6 + (hi) * 16;  // §8(d): 4+2 B per walked slot, 8 B in + 8 B out per token
+  return 0;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------ results
+namespace pm {
+
+// (vertex, T_arr) of every vertex still in the map (beta.cpp:1386-1394)
+__global__ void k_emit_vertices(LccArgs a, const uint32_t* __restrict__ l0, const uint32_t* __restrict__ l1,
+                                const uint32_t* __restrict__ l2, int cur, uint2* __restrict__ out,
+                                unsigned long long* __restrict__ n_out) {
+  const uint32_t c0 = a.cnt->fr_n[cur][0], c1 = a.cnt->fr_n[cur][1], c2 = a.cnt->fr_n[cur][2];
+  const uint32_t total = c0 + c1 + c2;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const uint32_t v = i < c0 ? l0[i] : (i < c0 + c1 ? l1[i - c0] : l2[i - c0 - c1]);
+    const uint32_t T = a.S[v];
+    if (T) out[atomicAdd(n_out, 1ull)] = make_uint2(v, T);
+  }
+}
+
+// (vertex, neighbour) for every key of vertex_active_edges_map[v], v in the map (beta.cpp:1397-1403)
+__global__ void k_emit_edges(LccArgs a, const uint32_t* __restrict__ l0, const uint32_t* __restrict__ l1,
+                             const uint32_t* __restrict__ l2, int cur, uint2* __restrict__ out,
+                             unsigned long long* __restrict__ n_out) {
+  const uint32_t c0 = a.cnt->fr_n[cur][0], c1 = a.cnt->fr_n[cur][1], c2 = a.cnt->fr_n[cur][2];
+  const uint32_t total = c0 + c1 + c2;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t i = warp; i < total; i += nwarps) {
+    const uint32_t v = i < c0 ? l0[i] : (i < c0 + c1 ? l1[i - c0] : l2[i - c0 - c1]);
+    if (!a.S[v]) continue;
+    const uint32_t d = a.adeg[v];
+    const uint64_t row = (uint64_t)a.rowblk[v] * 8;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(n_out, (unsigned long long)d);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for (uint32_t j = lane; j < d; j += 32) out[base + j] = make_uint2(v, a.colw[row + j] & PM_IDMASK);
+  }
+}
+
+}  // namespace pm
+
+namespace {
+
+int fetch_pairs(pm_ctx* c, bool edges, std::vector<uint2>& host) {
+  PM_CUDA(c, cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  // size from a fresh count
+  const int D = c->pat.diameter;
+  PM_CUDA(c, cudaMemsetAsync(c->rowstat + D, 0, sizeof(RowStat), st));
+  LccArgs la = lcc_args(c, D);
+  const int cur = c->cur;
+  k_count_alive<<<grid_for(), kBlock, 0, st>>>(la, c->fr[cur][0], c->fr[cur][1], c->fr[cur][2], cur);
+  PM_LAUNCH_CHECK(c);
+  PM_CUDA(c, cudaMemcpyAsync(c->h_rowstat + D, c->rowstat + D, sizeof(RowStat), cudaMemcpyDeviceToHost, st));
+  PM_CUDA(c, cudaStreamSynchronize(st));
+  const uint64_t n = edges ? c->h_rowstat[D].ne : c->h_rowstat[D].nv;
+  host.resize(n);
+  if (!n) return 0;
+  uint2* d_out = nullptr;
+  unsigned long long* d_n = nullptr;
+  int rc;
+  if ((rc = dev_alloc(c, &d_out, n))) return rc;
+  if ((rc = dev_alloc(c, &d_n, 1))) { dev_free(d_out); return rc; }
+  cudaMemsetAsync(d_n, 0, sizeof(unsigned long long), st);
+  if (edges) k_emit_edges<<<grid_for(), kBlock, 0, st>>>(la, c->fr[cur][0], c->fr[cur][1], c->fr[cur][2], cur, d_out, d_n);
+  else k_emit_vertices<<<grid_for(), kBlock, 0, st>>>(la, c->fr[cur][0], c->fr[cur][1], c->fr[cur][2], cur, d_out, d_n);
+  c->launches++;
+  cudaError_t e = cudaMemcpyAsync(host.data(), d_out, n * sizeof(uint2), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  dev_free(d_out);
+  dev_free(d_n);
+  if (e != cudaSuccess) return fail(c, PM_ERR_CUDA, cudaGetErrorString(e));
+  std::sort(host.begin(), host.end(), [](const uint2& x, const uint2& y) { return x.x != y.x ? x.x < y.x : x.y < y.y; });
+  return 0;
+}
+
+std::string bitset16(uint32_t x) {  // std::bitset<16> operator<<, most significant bit first
+  std::string s(16, '0');
+  for (int i = 0; i < 16; ++i) if ((x >> i) & 1u) s[15 - i] = '1';
+  return s;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---------------------------------------------------------------- the loop
+int pm_run(pm_ctx* c, const pm_run_options_t* opt_in, pm_run_summary_t* out) {
+  if (!c) return PM_ERR_ARG;
+  pm_run_options_t opt{4, 0, 0, 1};
+  if (opt_in) opt = *opt_in;
+  c->keep_subgraphs = opt.keep_subgraphs != 0;
+  int rc = pm_state_reset(c);  // beta.cpp:484-492
+  if (rc) return rc;
+  const int max_it = opt.max_iterations > 0 ? opt.max_iterations : 1000;
+  const size_t ncons = c->pat.constraints.size();
+  std::vector<pm_counts_t> counts(c->pat.diameter);
+  bool init_step = true;
+  int nf = 0;
+  const double t_begin = wall_s();
+  do {  // beta.cpp:544
+    const double it0 = wall_s();
+    nf = 0;                                                   // :546
+    if ((rc = pm_lcc(c, init_step, &nf, counts.data()))) return rc;  // :577-583
+    init_step = false;                                        // :602-604
+    if (!opt.lcc_only) {
+      if (c->itr == 0) nf = 1;                                // forced token passing, :686-688
+      if (nf) {                                               // :695
+        nf = 0;                                               // :697
+        for (size_t pl = 0; pl < ncons; ++pl) {               // :710
+          const int mode = (opt.tds_from_pl >= 0 && (int)pl >= opt.tds_from_pl) ? PM_NLCC_TDS : PM_NLCC_NEM1;  // :762-767
+          int found = 0, deleted = 0;
+          pm_counts_t tp;
+          if ((rc = pm_nlcc(c, (int)pl, mode, &found, &deleted, &tp))) return rc;
+          if (deleted) nf = 1;                                // :994-996
+          if (deleted && c->pat.constraints[pl].interleave)   // :1163-1184
+            if ((rc = pm_lcc(c, 0, &nf, counts.data()))) return rc;
+        }
+      }
+    }
+    c->iter_seconds.push_back(wall_s() - it0);                // :1337-1338
+    c->itr++;                                                 // :1341
+    if ((int)c->itr >= max_it && nf) { c->err = "iteration cap reached (SURVEY A.6 #4)"; break; }
+  } while (nf);                                               // :1351
+  c->summary.iterations = c->itr;
+  c->summary.search_seconds = wall_s() - t_begin;
+  c->summary.n_rows = c->rows.size();
+  if (!c->rows.empty()) {
+    c->summary.n_active_vertices = c->rows.back().n_vertices;
+    c->summary.n_active_edges = c->rows.back().n_edges;
+  }
+  if (out) *out = c->summary;
+  return 0;
+}
+
+int pm_get_rows(const pm_ctx* c, pm_row_t* rows_out) {
+  if (!c || !rows_out) return PM_ERR_ARG;
+  std::copy(c->rows.begin(), c->rows.end(), rows_out);
+  return 0;
+}
+
+int pm_get_active_vertices(const pm_ctx* cc, uint64_t* vertices_out, uint16_t* bits_out) {
+  pm_ctx* c = const_cast<pm_ctx*>(cc);
+  if (!c || !c->state_ready) return PM_ERR_ARG;
+  std::vector<uint2> h;
+  int rc = fetch_pairs(c, false, h);
+  if (rc) return rc;
+  for (size_t i = 0; i < h.size(); ++i) {
+    if (vertices_out) vertices_out[i] = h[i].x;
+    if (bits_out) bits_out[i] = (uint16_t)h[i].y;
+  }
+  c->summary.n_active_vertices = h.size();
+  return 0;
+}
+
+int pm_get_active_edges(const pm_ctx* cc, uint64_t* pairs_out) {
+  pm_ctx* c = const_cast<pm_ctx*>(cc);
+  if (!c || !c->state_ready || !pairs_out) return PM_ERR_ARG;
+  std::vector<uint2> h;
+  int rc = fetch_pairs(c, true, h);
+  if (rc) return rc;
+  for (size_t i = 0; i < h.size(); ++i) { pairs_out[2 * i] = h[i].x; pairs_out[2 * i + 1] = h[i].y; }
+  return 0;
+}
+
+int pm_get_subgraph_count(const pm_ctx* c, int pl, uint64_t* count_out, int* width_out) {
+  if (!c || pl < 0 || pl >= (int)c->subgraph_count.size()) return PM_ERR_ARG;
+  if (count_out) *count_out = c->subgraph_count[pl];
+  if (width_out) *width_out = c->subgraph_width[pl];
+  return 0;
+}
+
+int pm_get_subgraphs(const pm_ctx* c, int pl, uint32_t* rows_out) {
+  if (!c || pl < 0 || pl >= (int)c->subgraphs.size() || !rows_out) return PM_ERR_ARG;
+  if (c->subgraphs[pl].size() != c->subgraph_count[pl] * (uint64_t)c->subgraph_width[pl])
+    return fail(const_cast<pm_ctx*>(c), PM_ERR_ARG, "subgraphs were not kept (keep_subgraphs = 0)");
+  std::copy(c->subgraphs[pl].begin(), c->subgraphs[pl].end(), rows_out);
+  return 0;
+}
+
+// result tree of beta.cpp:504-535, 713-717, 1375-1425 (row grammar: SURVEY A.5)
+int pm_write_results(const pm_ctx* cc, const char* outdir) {
+  pm_ctx* c = const_cast<pm_ctx*>(cc);
+  if (!c || !outdir || !c->state_ready) return PM_ERR_ARG;
+  const std::string base(outdir), ps = base + "/0";
+  const std::string rk = std::to_string(c->rank);
+  auto open = [&](const std::string& p, std::ofstream& f) -> bool {
+    f.open(p, std::ofstream::out);
+    if (!f) c->err = "cannot open " + p + " (the result tree must pre-exist, like the reference's)";
+    return (bool)f;
+  };
+  if (c->rank == 0) {
+    std::ofstream f_set, f_itr, f_step, f_ss;
+    if (!open(base + "/result_pattern_set", f_set) || !open(ps + "/result_iteration", f_itr) ||
+        !open(ps + "/result_step", f_step) || !open(ps + "/result_superstep", f_ss))
+      return PM_ERR_IO;
+    for (size_t i = 0; i < c->iter_seconds.size(); ++i) f_itr << i << ", " << c->iter_seconds[i] << "\n";
+    for (auto& s : c->step_rows) f_step << s.first << ", LP, " << s.second << "\n";
+    for (auto& r : c->rows) f_ss << r.itr << (r.kind == 0 ? ", LP, " : ", TP, ") << r.index << ", " << r.seconds << "\n";
+    f_set << 0 << ", " << c->n_ranks << ", " << c->summary.iterations << ", " << c->summary.search_seconds << ", "
+          << c->pat.n_edges << ", " << c->pat.n_vertices << ", " << c->pat.constraints.size() << "\n";
+  }
+  std::ofstream fvc, fec, fv, fe, fm;
+  if (!open(ps + "/all_ranks_active_vertices_count/active_vertices_" + rk, fvc) ||
+      !open(ps + "/all_ranks_active_edges_count/active_edges_" + rk, fec) ||
+      !open(ps + "/all_ranks_active_vertices/active_vertices_" + rk, fv) ||
+      !open(ps + "/all_ranks_active_edges/active_edges_" + rk, fe) ||
+      !open(ps + "/all_ranks_messages/messages_" + rk, fm))
+    return PM_ERR_IO;
+  for (auto& r : c->rows) {
+    const char* kind = r.kind == 0 ? ", LP, " : ", TP, ";
+    fvc << r.itr << kind << r.index << ", " << r.n_vertices << "\n";
+    fec << r.itr << kind << r.index << ", " << r.n_edges << "\n";
+    fm << r.itr << kind << r.index << ", 0\n";  // message counts are transport specific
+  }
+  std::vector<uint2> hv, he;
+  int rc;
+  if ((rc = fetch_pairs(c, false, hv))) return rc;
+  if ((rc = fetch_pairs(c, true, he))) return rc;
+  std::vector<uint64_t> lab(c->V);
+  if ((rc = pm_labels_get(c, lab.data()))) return rc;
+  for (auto& p : hv) fv << c->rank << ", " << p.x << ", 0, " << lab[p.x] << ", " << bitset16(p.y) << "\n";
+  for (auto& p : he) fe << c->rank << ", " << p.x << ", " << p.y << "\n";
+  for (size_t pl = 0; pl < c->pat.constraints.size(); ++pl) {
+    std::ofstream fs;
+    if (!open(ps + "/all_ranks_subgraphs/subgraphs_" + std::to_string(pl) + "_" + rk, fs)) return PM_ERR_IO;
+    const int w = c->subgraph_width[pl];
+    const auto& sg = c->subgraphs[pl];
+    for (size_t i = 0; w && i + w <= sg.size(); i += w) {
+      fs << "[" << c->rank << "], ";
+      for (int x = 0; x < w; ++x) fs << sg[i + x] << ", ";
+      fs << "[" << sg[i + w - 1] << "]\n";
+    }
+  }
+  return 0;
+}
+
+}  // extern "C"

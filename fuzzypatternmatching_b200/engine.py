@@ -1,0 +1,193 @@
+"""Host-side mirror of the reference driver's interface for the pruning path.
+
+The names follow /root/reference/src/run_pattern_matching_beta.cpp: the driver
+loads a graph (-i/-b), builds degree labels unless -v is given, reads the
+pattern directory (-p) and then alternates
+`label_propagation_pattern_matching_bsp` (LCC, beta.cpp:577-583) with
+`token_passing_pattern_matching` (NLCC, beta.cpp:879-909) until nothing is
+removed, writing the result tree under -o.  Every method forwards to one entry
+point of the C ABI (include/pmgpu.h); nothing is computed in Python.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+class PmError(RuntimeError):
+    pass
+
+
+class Engine:
+    def __init__(self, device=0):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        rc = self._lib.pm_create(C.byref(h), device)
+        if rc != 0:
+            raise PmError("pm_create failed (%d): no usable CUDA device; this engine has no CPU fallback" % rc)
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.pm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise PmError("%s (status %d)" % (self._lib.pm_last_error(self._h).decode(), rc))
+
+    # ---- graph (-i / -b) ------------------------------------------------------
+    def graph_from_slots(self, n_vertices, src, dst):
+        src = np.ascontiguousarray(src, dtype=np.uint32)
+        dst = np.ascontiguousarray(dst, dtype=np.uint32)
+        assert src.shape == dst.shape
+        self._chk(self._lib.pm_graph_from_slots(self._h, n_vertices, src.size, src.ctypes.data, dst.ctypes.data))
+
+    def graph_from_undirected(self, n_vertices, edges):
+        e = np.asarray(edges, dtype=np.uint32).reshape(-1, 2)
+        src = np.empty(2 * len(e), dtype=np.uint32)
+        dst = np.empty(2 * len(e), dtype=np.uint32)
+        src[0::2], dst[0::2] = e[:, 0], e[:, 1]
+        src[1::2], dst[1::2] = e[:, 1], e[:, 0]
+        self.graph_from_slots(n_vertices, src, dst)
+
+    def graph_rmat(self, scale, gen_ranks):
+        """generate_rmat -s <scale> on <gen_ranks> ranks, on the GPU."""
+        self._chk(self._lib.pm_graph_rmat(self._h, scale, gen_ranks))
+
+    def graph_info(self):
+        gi = _lib.GraphInfo()
+        self._chk(self._lib.pm_graph_info(self._h, C.byref(gi)))
+        return {n: int(getattr(gi, n)) for n, _ in gi._fields_}
+
+    def graph_degree(self):
+        out = np.empty(self.graph_info()["n_local"], dtype=np.uint64)
+        self._chk(self._lib.pm_graph_get_degree(self._h, out.ctypes.data))
+        return out
+
+    def graph_csr(self):
+        gi = self.graph_info()
+        rowptr = np.empty(gi["n_local"] + 1, dtype=np.uint64)
+        col = np.empty(max(gi["n_slots"], 1), dtype=np.uint32)
+        self._chk(self._lib.pm_graph_get_csr(self._h, rowptr.ctypes.data, col.ctypes.data))
+        return rowptr, col[:gi["n_slots"]]
+
+    # ---- labels (-v) ------------------------------------------------------------
+    def labels_degree_log2(self):
+        self._chk(self._lib.pm_labels_degree_log2(self._h))
+
+    def labels_set(self, labels):
+        labels = np.ascontiguousarray(labels, dtype=np.uint64)
+        self._chk(self._lib.pm_labels_set(self._h, labels.ctypes.data))
+
+    def labels_get(self):
+        out = np.empty(self.graph_info()["n_vertices"], dtype=np.uint64)
+        self._chk(self._lib.pm_labels_get(self._h, out.ctypes.data))
+        return out
+
+    # ---- pattern (-p) -------------------------------------------------------------
+    def pattern_load_dir(self, directory):
+        self._chk(self._lib.pm_pattern_load_dir(self._h, directory.encode()))
+        pi = _lib.PatternInfo()
+        self._chk(self._lib.pm_pattern_info(self._h, C.byref(pi)))
+        self.pattern = {n: int(getattr(pi, n)) for n, _ in pi._fields_}
+        return self.pattern
+
+    # ---- the two operators of the path ------------------------------------------------
+    def state_reset(self):
+        self._chk(self._lib.pm_state_reset(self._h))
+
+    def label_propagation_pattern_matching_bsp(self, global_init_step, global_not_finished=False):
+        """One LCC call = `diameter` supersteps.  Returns (global_not_finished, [(n_vertices, n_edges, s)])."""
+        nf = C.c_int(int(global_not_finished))
+        counts = (_lib.Counts * self.pattern["diameter"])()
+        self._chk(self._lib.pm_lcc(self._h, int(global_init_step), C.byref(nf), counts))
+        return bool(nf.value), [(int(c.n_vertices), int(c.n_edges), float(c.seconds)) for c in counts]
+
+    def token_passing_pattern_matching(self, pl, tds=False):
+        """One NLCC constraint incl. the driver's token_source_map post-processing.
+        Returns (pattern_found, token_source_deleted, (n_vertices, n_edges, s))."""
+        found, deleted, cnt = C.c_int(0), C.c_int(0), _lib.Counts()
+        self._chk(self._lib.pm_nlcc(self._h, pl, _lib.PM_NLCC_TDS if tds else _lib.PM_NLCC_NEM1,
+                                    C.byref(found), C.byref(deleted), C.byref(cnt)))
+        return bool(found.value), bool(deleted.value), (int(cnt.n_vertices), int(cnt.n_edges), float(cnt.seconds))
+
+    # ---- the driver loop ----------------------------------------------------------------
+    def run(self, tds_from_pl=4, max_iterations=0, lcc_only=False, keep_subgraphs=True):
+        opt = _lib.RunOptions(tds_from_pl, max_iterations, int(lcc_only), int(keep_subgraphs))
+        s = _lib.RunSummary()
+        self._chk(self._lib.pm_run(self._h, C.byref(opt), C.byref(s)))
+        self.summary = {n: getattr(s, n) for n, _ in s._fields_}
+        return self.summary
+
+    def rows(self):
+        n = int(self.summary["n_rows"])
+        buf = (_lib.Row * max(n, 1))()
+        self._chk(self._lib.pm_get_rows(self._h, buf))
+        return [(int(r.itr), "LP" if r.kind == 0 else "TP", int(r.index), int(r.n_vertices), int(r.n_edges))
+                for r in buf[:n]]
+
+    def row_seconds(self):
+        n = int(self.summary["n_rows"])
+        buf = (_lib.Row * max(n, 1))()
+        self._chk(self._lib.pm_get_rows(self._h, buf))
+        return [float(r.seconds) for r in buf[:n]]
+
+    def active_vertices(self, n=None):
+        n = int(self.summary["n_active_vertices"]) if n is None else n
+        v = np.empty(max(n, 1), dtype=np.uint64)
+        b = np.empty(max(n, 1), dtype=np.uint16)
+        self._chk(self._lib.pm_get_active_vertices(self._h, v.ctypes.data, b.ctypes.data))
+        return v[:n], b[:n]
+
+    def active_edges(self, n=None):
+        n = int(self.summary["n_active_edges"]) if n is None else n
+        p = np.empty(2 * max(n, 1), dtype=np.uint64)
+        self._chk(self._lib.pm_get_active_edges(self._h, p.ctypes.data))
+        return p[:2 * n].reshape(-1, 2)
+
+    def subgraphs(self, pl):
+        cnt, w = C.c_uint64(0), C.c_int(0)
+        self._chk(self._lib.pm_get_subgraph_count(self._h, pl, C.byref(cnt), C.byref(w)))
+        if cnt.value == 0 or w.value == 0:
+            return np.zeros((0, max(w.value, 1)), dtype=np.uint32)
+        out = np.empty(cnt.value * w.value, dtype=np.uint32)
+        self._chk(self._lib.pm_get_subgraphs(self._h, pl, out.ctypes.data))
+        return out.reshape(-1, w.value)
+
+    def subgraph_count(self, pl):
+        cnt, w = C.c_uint64(0), C.c_int(0)
+        self._chk(self._lib.pm_get_subgraph_count(self._h, pl, C.byref(cnt), C.byref(w)))
+        return int(cnt.value)
+
+    def write_results(self, outdir):
+        self._chk(self._lib.pm_write_results(self._h, outdir.encode()))
+
+    def kernel_launches(self):
+        return int(self._lib.pm_kernel_launches(self._h))
+
+
+def run_pattern_matching_beta(graph, pattern_dir, output_dir=None, labels=None, device=0, **run_kw):
+    """The reference driver's flow (-i/-p/-o) in one call.
+    graph: ("rmat", scale, gen_ranks) or (n_vertices, src, dst) directed slots."""
+    eng = Engine(device)
+    if graph[0] == "rmat":
+        eng.graph_rmat(graph[1], graph[2])
+    else:
+        eng.graph_from_slots(*graph)
+    if labels is None:
+        eng.labels_degree_log2()
+    else:
+        eng.labels_set(labels)
+    eng.pattern_load_dir(pattern_dir)
+    eng.run(**run_kw)
+    if output_dir is not None:
+        eng.write_results(output_dir)
+    return eng

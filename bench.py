@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""bench.py — LCC+NLCC search throughput on synthetic R-MAT graphs (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W          # this repo's CUDA engine
+  python bench.py --impl reference --gpus N ...          # reference CPU path (oracle port) on host cores
+
+One "step" = one full search (per-pattern state reset, LCC supersteps, NLCC token
+walks, until the reference's loop terminates) of every template of the workload
+over one resident R-MAT graph.  `value` = directed edge slots of the graph
+(16 * 2^scale generated edges, both directions) * templates per step / step time:
+input edges searched per second.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from fuzzypatternmatching_b200 import patterns as PT  # noqa: E402
+
+# BASELINE.json configs[2]: R-MAT with cyclic templates (triangle, 4-cycle, 6-vertex
+# cycle + chords) exercising NLCC token walks; labels = degree classes ceil(log2(d+1)).
+# Interior hop labels are pairwise distinct, so the reference result is independent of
+# message order.  The README's tree template rides along as template 0.
+WORKLOADS = {
+    "cyclic": [("tree", PT.RMAT_LOG2_TREE), ("triangle_678", PT.triangle(6, 7, 8)),
+               ("cycle4_5678", PT.cycle4(5, 6, 7, 8)), ("cycle6_chords_456789", PT.cycle6_chords([4, 5, 6, 7, 8, 9]))],
+    "tree": [("tree", PT.RMAT_LOG2_TREE)],
+}
+
+
+def write_patterns(workload):
+    base = tempfile.mkdtemp(prefix="pm_bench_")
+    out = []
+    for name, spec in WORKLOADS[workload]:
+        d = PT.write_pattern_dir(os.path.join(base, name), spec)
+        out.append((name, d, PT.tds_from_pl(spec)))
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line)
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_reference(scale, gen_ranks, pats, steps, warmup, budget_s=150.0):
+    """The reference's CPU path for the same templates: the oracle port (the reference
+    binary needs MPI + Boost and cannot be built on this image), all host threads."""
+    from oracle import oracle as O
+    threads = host_threads()
+    g = O.Graph.rmat(scale, gen_ranks, threads)
+    labels = g.labels_degree_log2()
+    ps = [(O.Pattern(d), tds) for _, d, tds in pats]
+
+    def one_step():
+        t = 0.0
+        for p, tds in ps:
+            r = O.Run(g, labels, p, tds_from_pl=tds, threads=threads, keep_subgraphs=False)
+            t += r.search_seconds
+        return t
+
+    t_begin = time.time()
+    for _ in range(warmup):
+        one_step()
+        if time.time() - t_begin > budget_s / 3:
+            break
+    times = []
+    for _ in range(steps):
+        times.append(one_step())
+        if time.time() - t_begin > budget_s:
+            break
+    edges = g.n_slots_multi * len(ps)
+    return {"value": edges * len(times) / sum(times), "seconds_per_step": sum(times) / len(times),
+            "steps_done": len(times), "cores": threads, "scale": scale, "edges_per_step": edges}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scale", type=int, default=int(os.environ.get("PM_BENCH_SCALE", "26")))
+    ap.add_argument("--gen-ranks", type=int, default=1024, help="generating ranks of the R-MAT stream (part of the graph's identity)")
+    ap.add_argument("--workload", default="cyclic", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-scale", type=int, default=int(os.environ.get("PM_BENCH_CPU_SCALE", "20")))
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    pats = write_patterns(args.workload)
+    metric, unit = "lcc_nlcc_search_edges_per_second", "edges/s"
+    config = {"workload": "rmat_s%d_%s" % (args.scale, args.workload), "scale": args.scale,
+              "gen_ranks": args.gen_ranks, "templates": [n for n, _, _ in pats],
+              "labels": "ceil(log2(degree+1))", "parallelism": "1d_vertex_partition_x%d" % args.gpus}
+
+    # ---------------------------------------------------------------- reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        cpu_scale = min(args.scale, args.cpu_scale)
+        r = cpu_reference(cpu_scale, min(args.gen_ranks, 4) if cpu_scale != args.scale else args.gen_ranks,
+                          pats, args.steps, max(args.warmup, 1))
+        sample = ("oracle port of the reference CPU path, R-MAT scale %d (bounded sample of the scale-%d workload), "
+                  "same templates, %d host threads" % (cpu_scale, args.scale, r["cores"]))
+        line = {"impl": "reference", "metric": metric, "value": r["value"], "unit": unit, "n_gpus": args.gpus,
+                "steps": r["steps_done"], "warmup": args.warmup, "ms_per_step": r["seconds_per_step"] * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16",
+                "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": r["value"], "unit": unit, "cores": r["cores"], "kind": "port", "sample": sample},
+                "e2e": {"value": r["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ---------------------------------------------------------------------- our arm
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from fuzzypatternmatching_b200.engine import Engine
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    eng = Engine(local_rank)
+    t0 = time.time()
+    # N > 1: every rank searches its own R-MAT graph (weak scaling; distinct streams per rank)
+    eng.graph_rmat(args.scale, args.gen_ranks)
+    eng.labels_degree_log2()
+    gi = eng.graph_info()
+    build_s = time.time() - t0
+    n_edges = gi["n_slots_multi"] * len(pats)
+
+    def one_step(fetch=False):
+        got = 0
+        for _, d, tds in pats:
+            eng.pattern_load_dir(d)
+            s = eng.run(tds_from_pl=tds, keep_subgraphs=False)
+            if fetch:  # device -> host read of the step's result
+                v, b = eng.active_vertices()
+                e = eng.active_edges()
+                got += v.nbytes + b.nbytes + e.nbytes
+        return got
+
+    for _ in range(args.warmup):
+        one_step()
+    ks0 = [eng.kernel_stats(b) for b in range(3)]
+    l0 = eng.kernel_launches()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one_step()
+    barrier()
+    elapsed = time.perf_counter() - t0
+    clocks = sampler.stop()
+    launches = eng.kernel_launches() - l0
+    ks1 = [eng.kernel_stats(b) for b in range(3)]
+    if world > 1:
+        t = torch.tensor([elapsed], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed = float(t.item())
+    value = n_edges * args.steps * world / elapsed
+
+    # roofline of the dominant kernel: the first-superstep scan of the bin that walked most slots
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    dk = [dict((k, ks1[b][k] - ks0[b][k]) for k in ks1[b]) for b in range(3)]
+    top = max(range(3), key=lambda b: dk[b]["slots"])
+    names = ["k_lcc_scan<8,true>", "k_lcc_scan<32,true>", "k_lcc_scan_big<true>"]
+    roof = None
+    if dk[top]["launches"] and dk[top]["ms"] > 0:
+        alg_bytes = dk[top]["slots"] * 6.25 + dk[top]["vertices"] * 12.25
+        achieved = alg_bytes / dk[top]["launches"] / (dk[top]["ms"] / dk[top]["launches"] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": names[top], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None,
+                "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback",
+                "algorithmic_bytes_per_launch": alg_bytes / dk[top]["launches"],
+                "avg_launch_ms": dk[top]["ms"] / dk[top]["launches"],
+                "model": "6.25 B per scanned slot + 12.25 B per scanned vertex"}
+
+    # end to end through the C ABI with HOST buffers: upload the host CSR, search, read results back
+    e2e = None
+    if (rank == 0 or world > 1) and args.e2e_steps > 0:
+        rowptr, col = eng.graph_csr()
+        degm = eng.graph_degree()
+        pin = lambda a: torch.from_numpy(a).pin_memory().numpy()  # noqa: E731
+        rowptr, col, degm = pin(rowptr), pin(col), pin(degm)
+        h2d = rowptr.nbytes + col.nbytes + degm.nbytes
+        d2h = 0
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            eng.graph_from_csr(rowptr, col, degm)
+            eng.labels_degree_log2()
+            d2h = one_step(fetch=True)
+        barrier()
+        e2e_elapsed = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([e2e_elapsed], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_elapsed = float(t.item())
+        e2e = {"value": n_edges * args.e2e_steps * world / e2e_elapsed, "unit": unit,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_elapsed / args.e2e_steps * 1e3,
+               "steps": args.e2e_steps,
+               "what": "pm_graph_from_csr (pinned host CSR -> device store) + degree labels + search of every template + "
+                       "device->host read of the final active vertex and edge lists"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cs = min(args.scale, args.cpu_scale)
+        r = cpu_reference(cs, 4 if cs != args.scale else args.gen_ranks, pats, 2, 1, budget_s=60.0)
+        cpu = {"value": r["value"], "unit": unit, "cores": r["cores"], "kind": "port",
+               "sample": "oracle port (reference binary needs MPI+Boost, unbuildable here) on R-MAT scale %d, same "
+                         "templates, %d steps, %d host threads" % (cs, r["steps_done"], r["cores"])}
+
+    if rank == 0:
+        config.update({"inputs_exceed_l2": gi["n_slots_padded"] * 4 > 126e6, "graph_build_seconds": build_s,
+                       "directed_edge_slots": gi["n_slots_multi"], "distinct_slots": gi["n_slots"],
+                       "multi_gpu": "independent graph per rank (weak)" if world > 1 else "single gpu"})
+        line = {"metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u16", "data": "synthetic", "config": config,
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+                "search_ms_per_template": elapsed / args.steps / len(pats) * 1e3}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -37,6 +37,10 @@ class RunSummary(C.Structure):
                 ("path_count", C.c_uint64), ("edges_processed", C.c_uint64), ("algorithmic_bytes", C.c_uint64)]
 
 
+class KernelStats(C.Structure):
+    _fields_ = [("launches", C.c_uint64), ("ms", C.c_double), ("slots", C.c_uint64), ("vertices", C.c_uint64)]
+
+
 class Row(C.Structure):
     _fields_ = [("itr", C.c_uint64), ("kind", C.c_int32), ("index", C.c_int32), ("n_vertices", C.c_uint64),
                 ("n_edges", C.c_uint64), ("seconds", C.c_double)]
@@ -53,6 +57,8 @@ SYMBOLS = {
     "pm_comm_init": (_i, [_vp, _i, _i, C.c_char_p]),
     "pm_graph_from_slots": (_i, [_vp, _u64, _u64, _vp, _vp]),
     "pm_graph_rmat": (_i, [_vp, _u64, _u64]),
+    "pm_graph_from_csr": (_i, [_vp, _u64, _vp, _vp, _vp]),
+    "pm_get_kernel_stats": (_i, [_vp, _i, C.POINTER(KernelStats)]),
     "pm_graph_info": (_i, [_vp, C.POINTER(GraphInfo)]),
     "pm_graph_get_degree": (_i, [_vp, _vp]),
     "pm_graph_get_csr": (_i, [_vp, _vp, _vp]),

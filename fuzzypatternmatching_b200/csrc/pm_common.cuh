@@ -54,7 +54,9 @@ struct DevCounters {
 };
 
 struct RowStat {                // one result row, accumulated on the device
-  unsigned long long nv, ne, scanned;
+  unsigned long long nv, ne;
+  unsigned long long scanned[3];   // adjacency slots walked, per degree bin
+  unsigned long long verts[3];     // live vertices whose row was walked, per degree bin
 };
 
 }  // namespace pm
@@ -114,6 +116,9 @@ struct pm_ctx {
   uint64_t itr = 0;
   pm_run_summary_t summary{};
   std::vector<cudaEvent_t> events;
+  // CUDA-event timing of the first-superstep scan kernels (the dominant kernels), per bin
+  cudaEvent_t kev[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+  pm_kernel_stats_t kstat[3] = {};
 };
 
 namespace pm {

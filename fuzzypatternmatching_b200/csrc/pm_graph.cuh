@@ -64,6 +64,36 @@ __global__ void k_scatter_cols(const unsigned long long* __restrict__ ukeys, uin
   }
 }
 
+__global__ void k_csr_degrees(const unsigned long long* __restrict__ rowptr,
+                              const unsigned long long* __restrict__ degm64, uint64_t V,
+                              uint32_t* __restrict__ deg, uint32_t* __restrict__ degm,
+                              uint32_t* __restrict__ sectors) {
+  uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; v <= V; v += stride) {
+    uint32_t d = 0;
+    if (v < V) {
+      d = (uint32_t)(rowptr[v + 1] - rowptr[v]);
+      deg[v] = d;
+      degm[v] = (uint32_t)degm64[v];
+    }
+    sectors[v] = (d + 7u) >> 3;
+  }
+}
+
+// one warp copies one row of the compact CSR into its padded, sector aligned slot range
+__global__ void k_csr_place(const unsigned long long* __restrict__ rowptr, const uint32_t* __restrict__ col,
+                            uint64_t V, const uint32_t* __restrict__ rowblk, uint32_t* __restrict__ col0) {
+  const uint32_t lane = threadIdx.x & 31;
+  uint64_t v = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (; v < V; v += nwarps) {
+    const unsigned long long b = rowptr[v], e = rowptr[v + 1];
+    const uint64_t o = (uint64_t)rowblk[v] * 8;
+    for (unsigned long long j = b + lane; j < e; j += 32) col0[o + (j - b)] = col[j];
+  }
+}
+
 // label = ceil(log2(degree + 1)) == bit length of the degree
 // (include/havoqgt/vertex_data_db_degree.hpp:109; exact integer form)
 __global__ void k_labels_degree_log2(const uint32_t* __restrict__ degm, uint64_t V,
@@ -198,6 +228,74 @@ inline int graph_build_from_device_slots(pm_ctx* c, uint64_t V, uint64_t n, cons
   cleanup();
 #undef PM_G
 #undef PM_GC
+  c->graph_bytes = bytes;
+  c->has_graph = true;
+  c->state_ready = false;
+  return 0;
+}
+
+// Host CSR -> device store.  h_* are HOST pointers (copied here: this is the
+// host->device traffic an end-to-end run pays).
+inline int graph_build_from_host_csr(pm_ctx* c, uint64_t V, const uint64_t* h_rowptr, const uint32_t* h_col,
+                                     const uint64_t* h_degm) {
+  if (V == 0 || V > (1ull << 31)) return fail(c, PM_ERR_ARG, "n_vertices must be in [1, 2^31]");
+  graph_free(c);
+  cudaStream_t st = c->stream;
+  const uint64_t E = h_rowptr[V];
+  c->V = c->nloc = V;
+  c->E = E;
+  uint64_t bytes = 0;
+  int rc;
+  unsigned long long *d_rowptr = nullptr, *d_degm64 = nullptr;
+  uint32_t *d_col = nullptr, *sectors = nullptr;
+  void* tmp = nullptr;
+  auto cleanup = [&]() { dev_free(d_rowptr); dev_free(d_degm64); dev_free(d_col); dev_free(sectors); if (tmp) cudaFree(tmp); tmp = nullptr; };
+  if ((rc = dev_alloc(c, &c->degm, V, &bytes)) || (rc = dev_alloc(c, &c->deg, V, &bytes)) ||
+      (rc = dev_alloc(c, &c->rowblk, V + 1, &bytes)) || (rc = dev_alloc(c, &d_rowptr, V + 1)) ||
+      (rc = dev_alloc(c, &d_degm64, V)) || (rc = dev_alloc(c, &d_col, E)) || (rc = dev_alloc(c, &sectors, V + 1))) {
+    cleanup();
+    return rc;
+  }
+#define PM_GC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); \
+    return fail(c, PM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
+  PM_GC(cudaMemcpyAsync(d_rowptr, h_rowptr, (V + 1) * 8, cudaMemcpyHostToDevice, st));
+  PM_GC(cudaMemcpyAsync(d_degm64, h_degm, V * 8, cudaMemcpyHostToDevice, st));
+  if (E) PM_GC(cudaMemcpyAsync(d_col, h_col, E * 4, cudaMemcpyHostToDevice, st));
+  const int grid = grid_for();
+  k_csr_degrees<<<grid, kBlock, 0, st>>>(d_rowptr, d_degm64, V, c->deg, c->degm, sectors);
+  c->launches++;
+  size_t tb = 0, tb2 = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tb, sectors, c->rowblk, (int64_t)(V + 1), st);
+  uint32_t* d_max = nullptr;
+  cub::DeviceReduce::Max(nullptr, tb2, c->degm, d_max, (int64_t)V, st);
+  tb = std::max(tb, tb2);
+  PM_GC(cudaMalloc(&tmp, std::max<size_t>(tb, 16) + 16));
+  PM_GC(cub::DeviceScan::ExclusiveSum(tmp, tb, sectors, c->rowblk, (int64_t)(V + 1), st));
+  uint32_t h_total = 0, h_max = 0;
+  PM_GC(cudaMemcpyAsync(&h_total, c->rowblk + V, 4, cudaMemcpyDeviceToHost, st));
+  d_max = sectors;  // reuse: sectors are consumed
+  PM_GC(cub::DeviceReduce::Max(tmp, tb, c->degm, d_max, (int64_t)V, st));
+  PM_GC(cudaMemcpyAsync(&h_max, d_max, 4, cudaMemcpyDeviceToHost, st));
+  PM_GC(cudaStreamSynchronize(st));
+  c->max_deg = h_max;
+  c->Epad = (uint64_t)h_total * 8;
+  const uint64_t alloc_slots = c->Epad + 64;
+  if ((rc = dev_alloc(c, &c->col0, alloc_slots, &bytes)) || (rc = dev_alloc(c, &c->colw, alloc_slots, &bytes))) {
+    cleanup();
+    return rc;
+  }
+  PM_GC(cudaMemsetAsync(c->col0, 0xFF, alloc_slots * 4, st));
+  PM_GC(cudaMemsetAsync(c->colw, 0xFF, alloc_slots * 4, st));
+  k_csr_place<<<grid, kBlock, 0, st>>>(d_rowptr, d_col, V, c->rowblk, c->col0);
+  c->launches++;
+  PM_GC(cudaGetLastError());
+  PM_GC(cudaStreamSynchronize(st));
+#undef PM_GC
+  cleanup();
+  // multigraph slot count = sum of multigraph degrees
+  uint64_t em = 0;
+  for (uint64_t v = 0; v < V; ++v) em += h_degm[v];
+  c->E_multi = em;
   c->graph_bytes = bytes;
   c->has_graph = true;
   c->state_ready = false;

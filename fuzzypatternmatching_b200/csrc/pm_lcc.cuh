@@ -66,6 +66,7 @@ struct LccArgs {
   const uint8_t* cls;
   DevCounters* cnt;
   RowStat* row;   // accumulator of this superstep
+  int bin;        // degree bin this launch serves (row statistics)
 };
 
 // ---------------------------------------------------------------------------
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(kBlock) k_lcc_scan(LccArgs a, const uint32_t* 
   const uint32_t n = *n_ptr;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-  unsigned long long scanned = 0;
+  unsigned long long scanned = 0, verts = 0;
   for (uint32_t base = warp * GPW; base < n; base += nwarps * GPW) {
     const uint32_t idx = base + gw;
     const bool has = idx < n;
@@ -202,12 +203,19 @@ __global__ void __launch_bounds__(kBlock) k_lcc_scan(LccArgs a, const uint32_t* 
       // superstep only vertices that heard a valid neighbour ever entered the map (:841-852).
       if (ts == 0 && (FIRST ? heard != 0u : Tv != 0u)) a.cnt->nf = 1u;
       scanned += d;
+      verts += Tv != 0u;
     }
   }
   // one atomic per warp
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) scanned += __shfl_xor_sync(0xffffffffu, scanned, o);
-  if (lane == 0 && scanned) atomicAdd(&a.row->scanned, scanned);
+  for (int o = 16; o > 0; o >>= 1) {
+    scanned += __shfl_xor_sync(0xffffffffu, scanned, o);
+    verts += __shfl_xor_sync(0xffffffffu, verts, o);
+  }
+  if (lane == 0 && verts) {
+    atomicAdd(&a.row->scanned[a.bin], scanned);
+    atomicAdd(&a.row->verts[a.bin], verts);
+  }
 }
 
 // one CTA per high-degree vertex ("delegates across warps and CTAs")
@@ -287,7 +295,10 @@ __global__ void __launch_bounds__(1024) k_lcc_scan_big(LccArgs a, const uint32_t
       a.Tst[v] = (uint16_t)ts;
       a.adeg[v] = s_out;
       if (ts == 0 && (FIRST ? h != 0u : Tv != 0u)) a.cnt->nf = 1u;
-      atomicAdd(&a.row->scanned, (unsigned long long)d);
+      if (Tv) {
+        atomicAdd(&a.row->scanned[2], (unsigned long long)d);
+        atomicAdd(&a.row->verts[2], 1ull);
+      }
     }
   }
 }

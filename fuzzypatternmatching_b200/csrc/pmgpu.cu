@@ -36,6 +36,7 @@ LccArgs lcc_args(pm_ctx* c, int row) {
   a.rowblk = c->rowblk; a.deg = c->deg; a.col0 = c->col0; a.colw = c->colw;
   a.S = c->S; a.Tst = c->Tst; a.adeg = c->adeg; a.cls = c->cls; a.cnt = c->cnt;
   a.row = c->rowstat + row;
+  a.bin = 0;
   return a;
 }
 
@@ -103,6 +104,9 @@ int pm_create(pm_ctx** out, int device) {
     delete c;
     return PM_ERR_CUDA;
   }
+  for (int b = 0; b < 3; ++b)
+    for (int k = 0; k < 2; ++k)
+      if (cudaEventCreate(&c->kev[b][k]) != cudaSuccess) { delete c; return PM_ERR_CUDA; }
   *out = c;
   return 0;
 }
@@ -114,6 +118,7 @@ void pm_destroy(pm_ctx* c) {
   state_free(c);
   graph_free(c);
   for (auto e : c->events) cudaEventDestroy(e);
+  for (int b = 0; b < 3; ++b) for (int k = 0; k < 2; ++k) if (c->kev[b][k]) cudaEventDestroy(c->kev[b][k]);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -150,6 +155,21 @@ int pm_graph_from_slots(pm_ctx* c, uint64_t n_vertices, uint64_t n_slots, const 
   dev_free(d_src);
   dev_free(d_dst);
   return rc;
+}
+
+int pm_graph_from_csr(pm_ctx* c, uint64_t n_vertices, const uint64_t* rowptr, const uint32_t* col,
+                      const uint64_t* degree_multi) {
+  if (!c || !rowptr || !degree_multi || (rowptr[n_vertices] && !col))
+    return fail(c, PM_ERR_ARG, "pm_graph_from_csr: null argument");
+  PM_CUDA(c, cudaSetDevice(c->device));
+  state_free(c);
+  return graph_build_from_host_csr(c, n_vertices, rowptr, col, degree_multi);
+}
+
+int pm_get_kernel_stats(const pm_ctx* c, int bin, pm_kernel_stats_t* out) {
+  if (!c || !out || bin < 0 || bin > 2) return PM_ERR_ARG;
+  *out = c->kstat[bin];
+  return 0;
 }
 
 int pm_graph_rmat(pm_ctx* c, uint64_t scale, uint64_t gen_ranks) {
@@ -320,20 +340,29 @@ int pm_lcc(pm_ctx* c, int init_step, int* not_finished, pm_counts_t* counts_out)
     const int cur = c->cur, nxt = cur ^ 1;
     PM_CUDA(c, cudaEventRecord(c->events[k], st));
     PM_CUDA(c, cudaMemsetAsync(&c->cnt->fr_n[nxt][0], 0, 4 * sizeof(uint32_t), st));
-    LccArgs a = lcc_args(c, k);
+    LccArgs a = lcc_args(c, k), a1 = a, a2 = a;
+    a1.bin = 1;
+    a2.bin = 2;
     if (first) {
+      // the kernels that walk the pristine adjacency are timed with CUDA events on this stream
+      PM_CUDA(c, cudaEventRecord(c->kev[0][0], st));
       k_lcc_scan<8, true><<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], &c->cnt->fr_n[cur][0]);
       PM_LAUNCH_CHECK(c);
-      k_lcc_scan<32, true><<<grid, kBlock, 0, st>>>(a, c->fr[cur][1], &c->cnt->fr_n[cur][1]);
+      PM_CUDA(c, cudaEventRecord(c->kev[0][1], st));
+      PM_CUDA(c, cudaEventRecord(c->kev[1][0], st));
+      k_lcc_scan<32, true><<<grid, kBlock, 0, st>>>(a1, c->fr[cur][1], &c->cnt->fr_n[cur][1]);
       PM_LAUNCH_CHECK(c);
-      k_lcc_scan_big<true><<<148, 1024, 0, st>>>(a, c->fr[cur][2], &c->cnt->fr_n[cur][2]);
+      PM_CUDA(c, cudaEventRecord(c->kev[1][1], st));
+      PM_CUDA(c, cudaEventRecord(c->kev[2][0], st));
+      k_lcc_scan_big<true><<<148, 1024, 0, st>>>(a2, c->fr[cur][2], &c->cnt->fr_n[cur][2]);
       PM_LAUNCH_CHECK(c);
+      PM_CUDA(c, cudaEventRecord(c->kev[2][1], st));
     } else {
       k_lcc_scan<8, false><<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], &c->cnt->fr_n[cur][0]);
       PM_LAUNCH_CHECK(c);
-      k_lcc_scan<32, false><<<grid, kBlock, 0, st>>>(a, c->fr[cur][1], &c->cnt->fr_n[cur][1]);
+      k_lcc_scan<32, false><<<grid, kBlock, 0, st>>>(a1, c->fr[cur][1], &c->cnt->fr_n[cur][1]);
       PM_LAUNCH_CHECK(c);
-      k_lcc_scan_big<false><<<148, 1024, 0, st>>>(a, c->fr[cur][2], &c->cnt->fr_n[cur][2]);
+      k_lcc_scan_big<false><<<148, 1024, 0, st>>>(a2, c->fr[cur][2], &c->cnt->fr_n[cur][2]);
       PM_LAUNCH_CHECK(c);
     }
     k_lcc_commit<<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], c->fr[cur][1], c->fr[cur][2], c->fr[nxt][0],
@@ -355,11 +384,24 @@ int pm_lcc(pm_ctx* c, int init_step, int* not_finished, pm_counts_t* counts_out)
     c->rows.push_back(r);
     if (counts_out) { counts_out[k].n_vertices = r.n_vertices; counts_out[k].n_edges = r.n_edges; counts_out[k].seconds = r.seconds; }
     c->summary.device_seconds += r.seconds;
-    const uint64_t sc = c->h_rowstat[k].scanned;
+    const RowStat& rs = c->h_rowstat[k];
+    const uint64_t sc = rs.scanned[0] + rs.scanned[1] + rs.scanned[2];
+    const uint64_t vs = rs.verts[0] + rs.verts[1] + rs.verts[2];
     c->summary.edges_processed += sc;
+    if (k == 0 && init_step) {
+      for (int b = 0; b < 3; ++b) {
+        float kms = 0;
+        PM_CUDA(c, cudaEventElapsedTime(&kms, c->kev[b][0], c->kev[b][1]));
+        c->kstat[b].launches++;
+        c->kstat[b].ms += kms;
+        c->kstat[b].slots += rs.scanned[b];
+        c->kstat[b].vertices += rs.verts[b];
+      }
+    }
     // SURVEY §8(d) byte model: 4 B column + 2 B neighbour mask per scanned slot;
     // 12 B per scanned vertex (row start, own masks read + written, |E_v|)
-    c->summary.algorithmic_bytes += sc * 6;
+    // 6.25 B per scanned slot + 12.25 B per scanned vertex
+    c->summary.algorithmic_bytes += sc * 25 / 4 + vs * 49 / 4;
   }
   c->step_rows.push_back({c->itr, wall_s() - t0});
   return 0;

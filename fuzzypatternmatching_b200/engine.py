@@ -58,6 +58,14 @@ class Engine:
         src[1::2], dst[1::2] = e[:, 1], e[:, 0]
         self.graph_from_slots(n_vertices, src, dst)
 
+    def graph_from_csr(self, rowptr, col, degree_multi):
+        """Host CSR (distinct neighbours, ascending) + multigraph degrees -> device store."""
+        rowptr = np.ascontiguousarray(rowptr, dtype=np.uint64)
+        col = np.ascontiguousarray(col, dtype=np.uint32)
+        degree_multi = np.ascontiguousarray(degree_multi, dtype=np.uint64)
+        self._chk(self._lib.pm_graph_from_csr(self._h, len(rowptr) - 1, rowptr.ctypes.data, col.ctypes.data,
+                                              degree_multi.ctypes.data))
+
     def graph_rmat(self, scale, gen_ranks):
         """generate_rmat -s <scale> on <gen_ranks> ranks, on the GPU."""
         self._chk(self._lib.pm_graph_rmat(self._h, scale, gen_ranks))
@@ -169,6 +177,11 @@ class Engine:
 
     def write_results(self, outdir):
         self._chk(self._lib.pm_write_results(self._h, outdir.encode()))
+
+    def kernel_stats(self, bin=0):
+        ks = _lib.KernelStats()
+        self._chk(self._lib.pm_get_kernel_stats(self._h, bin, C.byref(ks)))
+        return dict(launches=int(ks.launches), ms=float(ks.ms), slots=int(ks.slots), vertices=int(ks.vertices))
 
     def kernel_launches(self):
         return int(self._lib.pm_kernel_launches(self._h))

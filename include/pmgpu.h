@@ -77,6 +77,13 @@ int pm_graph_from_slots(pm_ctx* ctx, uint64_t n_vertices, uint64_t n_slots,
  * (src/generate_rmat.cpp:197-213, include/havoqgt/rmat_edge_generator.hpp:218-259) */
 int pm_graph_rmat(pm_ctx* ctx, uint64_t scale, uint64_t gen_ranks);
 
+/* Distinct-neighbour CSR held in HOST memory (rows ascending, no duplicates)
+ * plus the multigraph out-degrees the labels derive from: the analogue of
+ * opening the reference's memory-mapped graph image (beta.cpp:213-223).  This is
+ * the entry point whose host->device copies an end-to-end measurement includes. */
+int pm_graph_from_csr(pm_ctx* ctx, uint64_t n_vertices, const uint64_t* rowptr /* n_vertices+1 */,
+                      const uint32_t* col, const uint64_t* degree_multi /* n_vertices */);
+
 typedef struct {
   uint64_t n_vertices;      /* global                                  */
   uint64_t n_local;         /* vertices owned by this rank             */
@@ -127,6 +134,17 @@ typedef struct {
  * With several ranks the flag and nothing else is reduced here; counts are
  * per rank like the reference's per-rank files.                               */
 int pm_lcc(pm_ctx* ctx, int global_init_step, int* not_finished, pm_counts_t* counts_out);
+
+/* CUDA-event timing of the first-superstep scan kernels (the kernels that walk
+ * the pristine adjacency; bin 0: <= 32 slots per row, 8-lane groups; bin 1: <=
+ * 4096, one warp per row; bin 2: one CTA per row), accumulated since pm_create. */
+typedef struct {
+  uint64_t launches;
+  double ms;         /* sum of launch durations                    */
+  uint64_t slots;    /* adjacency slots walked                     */
+  uint64_t vertices; /* rows walked                                */
+} pm_kernel_stats_t;
+int pm_get_kernel_stats(const pm_ctx* ctx, int bin, pm_kernel_stats_t* out);
 
 /* ---- NLCC ----------------------------------------------------------------
  * replaces token_passing_pattern_matching (both overloads) AND the driver's

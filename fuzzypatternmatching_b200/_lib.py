@@ -23,6 +23,10 @@ class PatternInfo(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("n_vertices", "n_edges", "diameter", "n_constraints")]
 
 
+class ConstraintInfo(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("walk_length", "valid_cycle", "interleave_lcc", "order_independent")]
+
+
 class Counts(C.Structure):
     _fields_ = [("n_vertices", C.c_uint64), ("n_edges", C.c_uint64), ("seconds", C.c_double)]
 
@@ -67,6 +71,8 @@ SYMBOLS = {
     "pm_labels_get": (_i, [_vp, _vp]),
     "pm_pattern_load_dir": (_i, [_vp, C.c_char_p]),
     "pm_pattern_info": (_i, [_vp, C.POINTER(PatternInfo)]),
+    "pm_pattern_constraint_info": (_i, [_vp, _i, C.POINTER(ConstraintInfo)]),
+    "pm_end_iteration": (_i, [_vp, C.c_double]),
     "pm_state_reset": (_i, [_vp]),
     "pm_lcc": (_i, [_vp, _i, C.POINTER(_i), C.POINTER(Counts)]),
     "pm_nlcc": (_i, [_vp, _i, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(Counts)]),

@@ -666,6 +666,30 @@ int pm_run(pm_ctx* c, const pm_run_options_t* opt_in, pm_run_summary_t* out) {
   return 0;
 }
 
+int pm_end_iteration(pm_ctx* c, double seconds) {
+  if (!c || !c->state_ready) return PM_ERR_ARG;
+  c->iter_seconds.push_back(seconds);
+  c->itr++;
+  c->summary.iterations = c->itr;
+  c->summary.search_seconds += seconds;
+  c->summary.n_rows = c->rows.size();
+  if (!c->rows.empty()) {
+    c->summary.n_active_vertices = c->rows.back().n_vertices;
+    c->summary.n_active_edges = c->rows.back().n_edges;
+  }
+  return 0;
+}
+
+int pm_pattern_constraint_info(const pm_ctx* c, int pl, pm_constraint_info_t* o) {
+  if (!c || !o || !c->has_pattern || pl < 0 || pl >= (int)c->pat.constraints.size()) return PM_ERR_ARG;
+  const Constraint& k = c->pat.constraints[pl];
+  o->walk_length = (int)k.P.size();
+  o->valid_cycle = k.valid_cycle;
+  o->interleave_lcc = k.interleave;
+  o->order_independent = nem1_order_independent(k);
+  return 0;
+}
+
 int pm_get_rows(const pm_ctx* c, pm_row_t* rows_out) {
   if (!c || !rows_out) return PM_ERR_ARG;
   std::copy(c->rows.begin(), c->rows.end(), rows_out);

@@ -114,6 +114,14 @@ typedef struct {
   int n_vertices, n_edges, diameter, n_constraints;
 } pm_pattern_info_t;
 int pm_pattern_info(const pm_ctx* ctx, pm_pattern_info_t* out);
+/* one line of pattern_nlc (pattern_util.hpp:172-210) */
+typedef struct {
+  int walk_length;         /* vertices on the walk = cycle_length + 2                     */
+  int valid_cycle;         /* 1: the walk must close at its source                        */
+  int interleave_lcc;      /* 1: the driver runs LCC after this constraint removed a source */
+  int order_independent;   /* 1: nem_1's result does not depend on message order (A.6 #7)  */
+} pm_constraint_info_t;
+int pm_pattern_constraint_info(const pm_ctx* ctx, int pl, pm_constraint_info_t* out);
 
 /* ---- per-pattern state ---------------------------------------------------
  * replaces the container reset of beta.cpp:484-492                            */
@@ -185,6 +193,10 @@ typedef struct {
 } pm_row_t;
 
 int pm_run(pm_ctx* ctx, const pm_run_options_t* opt, pm_run_summary_t* out);
+/* For a host driver that spells the loop out over pm_lcc / pm_nlcc itself (as the
+ * reference main does): closes outer iteration `global_itr_count` (beta.cpp:1327-1341)
+ * so that later rows carry the next iteration number and result_iteration gets its row. */
+int pm_end_iteration(pm_ctx* ctx, double iteration_seconds);
 int pm_get_rows(const pm_ctx* ctx, pm_row_t* rows_out /* n_rows */);
 
 /* ---- results -------------------------------------------------------------

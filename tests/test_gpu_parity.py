@@ -99,3 +99,108 @@ def test_rmat_tree_search(oracle, eng, scale, gen_ranks):
     got, want = cases.engine_summary(eng, pat.n_constraints), cases.run_summary(ref)
     for k in ("rows", "iterations", "vertices", "edges", "subgraphs"):
         assert got[k] == want[k], k
+
+
+def test_golden_fixtures_on_gpu(oracle, eng):
+    import json
+    import os
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "runs.json")))
+    specs = {s[0]: s for s in cases.SPECS}
+    for case in gold:
+        _, spec, labelset, tds_from = specs[case["spec"]]
+        edges = cases.random_multigraph(case["seed"], case["n"], case["m"])
+        labels = cases.random_labels(case["seed"], case["n"], labelset)
+        src, dst = cases.slots_of(edges)
+        eng.graph_from_slots(case["n"], src, dst)
+        eng.labels_set(labels)
+        eng.pattern_load_dir(cases.pattern_dir(spec))
+        eng.run(tds_from_pl=tds_from, max_iterations=50)
+        s = cases.engine_summary(eng, len(spec["constraints"]))
+        assert [list(x) for x in s["rows"]] == case["rows"]
+        assert [list(x) for x in s["vertices"]] == case["vertices"]
+        assert [list(x) for x in s["edges"]] == case["edges"]
+        assert [[list(w) for w in sg] for sg in s["subgraphs"]] == case["subgraphs"]
+
+
+def test_host_csr_upload_equals_slot_build(oracle, eng):
+    edges = cases.random_multigraph(8, 3000, 20000, dup=0.15, loops=0.05)
+    g = oracle.Graph.from_undirected(3000, edges)
+    eng.graph_from_csr(g.rowptr, g.col, g.degree)
+    assert np.array_equal(eng.graph_degree(), g.degree)
+    rowptr, col = eng.graph_csr()
+    assert np.array_equal(rowptr, g.rowptr) and np.array_equal(col, g.col)
+    assert eng.graph_info()["n_slots_multi"] == g.n_slots_multi
+
+
+def test_step_by_step_operators_match_the_driver_loop(oracle, eng):
+    """pm_lcc / pm_nlcc called one by one, the way the reference main does, give the rows pm_run gives."""
+    from fuzzypatternmatching_b200 import patterns as PT
+    spec = PT.RMAT_LOG2_TREE
+    edges = cases.random_multigraph(21, 400, 2400)
+    labels = cases.random_labels(21, 400, [2, 3, 4, 5, 7])
+    d = cases.pattern_dir(spec)
+    g = oracle.Graph.from_undirected(400, edges)
+    ref = oracle.Run(g, labels, oracle.Pattern(d), tds_from_pl=4)
+    src, dst = cases.slots_of(edges)
+    eng.graph_from_slots(400, src, dst)
+    eng.labels_set(labels)
+    eng.pattern_load_dir(d)
+    eng.state_reset()
+    rows, itr, init = [], 0, True
+    while True:
+        nf, counts = eng.label_propagation_pattern_matching_bsp(init)
+        rows += [(itr, "LP", k, c[0], c[1]) for k, c in enumerate(counts)]
+        init = False
+        if itr == 0:
+            nf = True
+        if nf:
+            nf = False
+            for pl in range(5):
+                found, deleted, c = eng.token_passing_pattern_matching(pl, tds=pl >= 4)
+                rows.append((itr, "TP", pl, c[0], c[1]))
+                if deleted:
+                    nf = True
+                    nf2, counts = eng.label_propagation_pattern_matching_bsp(False, nf)
+                    nf = nf or nf2
+                    rows += [(itr, "LP", k, c[0], c[1]) for k, c in enumerate(counts)]
+        eng._chk(eng._lib.pm_end_iteration(eng._h, 0.0))
+        itr += 1
+        if not nf:
+            break
+    assert rows == ref.rows and itr == ref.iterations
+
+
+def test_cli_writes_the_reference_result_tree(oracle, tmp_path):
+    """generate_rmat + run_pattern_matching_beta (the C++ host driver) against the oracle's result tree."""
+    import os
+    import subprocess
+    from fuzzypatternmatching_b200 import patterns as PT
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    bindir = os.path.join(root, "fuzzypatternmatching_b200", "bin")
+    gbase = str(tmp_path / "rmat")
+    subprocess.check_call([os.path.join(bindir, "generate_rmat"), "-s", "17", "-r", "4", "-o", gbase],
+                          stdout=subprocess.DEVNULL)
+    pdir = str(tmp_path / "pattern")
+    PT.write_pattern_dir(pdir, PT.RMAT_LOG2_TREE)
+    out_gpu, out_ref = str(tmp_path / "gpu"), str(tmp_path / "ref")
+    for o in (out_gpu, out_ref):
+        os.makedirs(o)
+        oracle.make_result_tree(o)
+    subprocess.check_call([os.path.join(bindir, "run_pattern_matching_beta"), "-i", gbase, "-p", pdir, "-o", out_gpu],
+                          stdout=subprocess.DEVNULL)
+    g = oracle.Graph.rmat(17, 4)
+    labels = g.labels_degree_log2()
+    ref = oracle.Run(g, labels, oracle.Pattern(os.path.join(pdir, "0")), n_ranks=1, tds_from_pl=4)
+    ref.write_results(out_ref)
+    for rel in ("0/all_ranks_active_vertices/active_vertices_0", "0/all_ranks_active_edges/active_edges_0",
+                "0/all_ranks_active_vertices_count/active_vertices_0", "0/all_ranks_active_edges_count/active_edges_0",
+                "0/all_ranks_subgraphs/subgraphs_4_0"):
+        a = sorted(open(os.path.join(out_gpu, rel)).read().splitlines())
+        b = sorted(open(os.path.join(out_ref, rel)).read().splitlines())
+        assert a == b and len(a) > 0, rel
+    # time carrying files: same row keys
+    key = lambda p: [",".join(l.split(",")[:3]) for l in open(p).read().splitlines()]  # noqa: E731
+    assert key(os.path.join(out_gpu, "0/result_superstep")) == key(os.path.join(out_ref, "0/result_superstep"))
+    a = open(os.path.join(out_gpu, "result_pattern_set")).read().split(",")
+    b = open(os.path.join(out_ref, "result_pattern_set")).read().split(",")
+    assert [x.strip() for x in a[:3] + a[4:]] == [x.strip() for x in b[:3] + b[4:]]

@@ -1,0 +1,216 @@
+"""CPU tests that PIN the oracle (the reference ships no golden vectors for this
+path, SURVEY §4/§8c, so the pins are independent restatements and hand-derived
+answers): Mersenne-Twister stream vs numpy's MT19937, R-MAT edges vs a pure-Python
+restatement, label formula, hand-computed LCC/NLCC outcomes, and the committed
+golden fixtures."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from fuzzypatternmatching_b200 import patterns as PT
+from tests import cases
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+# ---- independent pure-Python restatement of the R-MAT stream -----------------------
+def _h16(a):
+    a &= 0xFFFF
+    a = ((a + 0x5D16) + (a << 6)) & 0xFFFF
+    a = ((a ^ 0xC23C) ^ (a >> 9)) & 0xFFFF
+    a = ((a + 0x67B1) + (a << 5)) & 0xFFFF
+    a = ((a + 0x646C) ^ (a << 7)) & 0xFFFF
+    a = ((a + 0x46C5) + (a << 3)) & 0xFFFF
+    a = ((a ^ 0x4F09) ^ (a >> 8)) & 0xFFFF
+    return a
+
+
+def _hash_nbits_lt32(x, n):
+    k = n - 16
+    order = list(range(k + 1)) + list(range(k, -1, -1))
+    for i in order:
+        h = _h16((x >> i) & 0xFFFF)
+        x = (x & ~(0xFFFF << i)) | (h << i)
+    return x
+
+
+def _py_rmat(scale, rank, n_edges):
+    bg = np.random.MT19937()
+    bg._legacy_seeding(5489 + 3 * rank)  # init_genrand == std::mt19937(seed) == boost::mt19937(seed)
+    raw = bg.random_raw(n_edges * 5 * scale)
+    out, k = [], 0
+    for _ in range(n_edges):
+        a, b, c, d = 0.57, 0.19, 0.19, 0.05
+        u = v = 0
+        step = (1 << scale) >> 1
+        for _j in range(scale):
+            p = float(raw[k]) * 2.0 ** -32
+            if p < a:
+                pass
+            elif p < a + b:
+                v += step
+            elif p < a + b + c:
+                u += step
+            else:
+                u += step
+                v += step
+            step >>= 1
+            a *= 0.9 + 0.2 * (float(raw[k + 1]) * 2.0 ** -32)
+            b *= 0.9 + 0.2 * (float(raw[k + 2]) * 2.0 ** -32)
+            c *= 0.9 + 0.2 * (float(raw[k + 3]) * 2.0 ** -32)
+            d *= 0.9 + 0.2 * (float(raw[k + 4]) * 2.0 ** -32)
+            k += 5
+            s = a + b + c + d
+            a /= s
+            b /= s
+            c /= s
+            d = 1.0 - a - b - c
+        out.append((_hash_nbits_lt32(u, scale), _hash_nbits_lt32(v, scale)))
+    return out
+
+
+def test_mt19937_first_output_is_the_textbook_value():
+    bg = np.random.MT19937()
+    bg._legacy_seeding(5489)
+    assert int(bg.random_raw(1)[0]) == 3499211612  # mt19937 default-seed known answer
+
+
+@pytest.mark.parametrize("scale,rank", [(17, 0), (17, 3), (21, 0), (21, 2)])
+def test_rmat_stream_matches_independent_restatement(oracle, scale, rank):
+    got = oracle.rmat_stream(scale, rank, 64).tolist()
+    assert [tuple(x) for x in got] == _py_rmat(scale, rank, 64)
+
+
+def test_rmat_stream_golden(oracle):
+    gold = json.load(open(os.path.join(HERE, "golden", "rmat_kat.json")))
+    for key, edges in gold.items():
+        scale, rank = [int(x) for x in key.split("_")]
+        assert oracle.rmat_stream(scale, rank, len(edges)).tolist() == edges
+
+
+def test_hash_nbits_is_a_permutation_of_17_bits(oracle):
+    xs = {oracle.hash_nbits(x, 17) for x in range(0, 1 << 17, 7)}
+    assert len(xs) == len(range(0, 1 << 17, 7)) and max(xs) < (1 << 17)
+    assert oracle.hash_nbits(12345, 17) == _hash_nbits_lt32(12345, 17)
+
+
+def test_rmat_graph_chunked_generation_equals_stream(oracle):
+    g = oracle.Graph.rmat(17, 4, threads=3)
+    deg = np.zeros(1 << 17, dtype=np.uint64)
+    for r in range(4):
+        e = oracle.rmat_stream(17, r, (1 << 17) * 16 // 4)
+        np.add.at(deg, e[:, 0], 1)
+        np.add.at(deg, e[:, 1], 1)
+    assert np.array_equal(deg, g.degree)
+    assert g.n_slots_multi == 2 * 16 * (1 << 17)
+
+
+def test_degree_labels_are_bit_lengths(oracle):
+    # ceil(log2(d+1)) evaluated in double == bit length of d (vertex_data_db_degree.hpp:109)
+    n = 5000
+    edges = [(0, i) for i in range(1, 40)] + [(1, 2), (1, 2), (100, 100)]
+    g = oracle.Graph.from_undirected(n, edges)
+    lab = g.labels_degree_log2()
+    assert all(int(l) == int(d).bit_length() for l, d in zip(lab, g.degree))
+    assert g.degree[100] == 2 and g.degree[1] == 3 and g.degree[0] == 39  # self loop counts twice, duplicates count
+
+
+# ---- hand-derived LCC / NLCC answers -----------------------------------------------------
+def _run(oracle, n, edges, labels, spec, tds_from=None, **kw):
+    pat = oracle.Pattern(cases.pattern_dir(spec))
+    g = oracle.Graph.from_undirected(n, edges)
+    return oracle.Run(g, np.asarray(labels, dtype=np.uint64), pat,
+                      tds_from_pl=PT.tds_from_pl(spec) if tds_from is None else tds_from, **kw)
+
+
+def test_triangle_present_and_absent(oracle):
+    spec = PT.triangle(1, 2, 3)
+    # vertices 0,1,2 form a 1-2-3 triangle; 3,4,5 form an open path 1-2-3 (no closing edge)
+    edges = [(0, 1), (1, 2), (0, 2), (3, 4), (4, 5)]
+    r = _run(oracle, 6, edges, [1, 2, 3, 1, 2, 3], spec)
+    v, t = r.active_vertices()
+    assert v.tolist() == [0, 1, 2] and t.tolist() == [1, 2, 4]
+    assert sorted(map(tuple, r.active_edges.tolist())) == [(0, 1), (0, 2), (1, 0), (1, 2), (2, 0), (2, 1)]
+    # LCC alone removes the open path 3-4-5: in superstep 0 the end points 3 and 5 miss one
+    # required template neighbour each and leave; the middle vertex 4 heard both and stays,
+    # still holding its two edges (4 vertices, 6 + 2 edges); in superstep 1 it hears nobody.
+    assert r.rows[0] == (0, "LP", 0, 4, 8)
+    assert r.rows[1] == (0, "LP", 1, 3, 6)
+    assert sorted(map(tuple, r.subgraphs[1].tolist())) == [(0, 1, 2, 0)]
+
+
+def test_lcc_keeps_a_hexagon_that_only_nlcc_can_reject(oracle):
+    spec = PT.triangle(1, 2, 3)
+    # 6-cycle labelled 1,2,3,1,2,3: locally every vertex sees both other labels, but there is no triangle
+    edges = [(0, 1), (1, 2), (2, 3), (3, 4), (4, 5), (5, 0)]
+    r = _run(oracle, 6, edges, [1, 2, 3, 1, 2, 3], spec)
+    assert r.rows[0][3:] == (6, 12) and r.rows[1][3:] == (6, 12)       # LCC keeps everything
+    tp0 = [x for x in r.rows if x[1] == "TP" and x[2] == 0][0]
+    # both label-1 sources fail the cycle check and leave the map; the TP row counts the edge
+    # maps of the 4 vertices still in the map (their entries towards the dead sources included)
+    assert tp0[3:] == (4, 8)
+    assert r.in_map.sum() == 0 and len(r.active_edges) == 0             # and the rest unravels
+    assert r.iterations == 2
+
+
+def test_parallel_edges_and_self_loops(oracle):
+    spec = PT.triangle(1, 2, 3)
+    edges = [(0, 1), (0, 1), (0, 1), (1, 2), (0, 2), (2, 2), (0, 0)]
+    r = _run(oracle, 3, edges, [1, 2, 3], spec)
+    # edge maps are keyed by neighbour: duplicates collapse, self loops are dropped (labels differ)
+    assert r.rows[0][3:] == (3, 6)
+    assert len(r.active_edges) == 6
+
+
+def test_path_constraint_needs_a_second_end_point(oracle):
+    # template: path 1 - 2 - 1 (two template vertices share label 1); the path constraint
+    # 0 -> 1 -> 2 must end at a vertex different from its source
+    spec = {"labels": [1, 2, 1], "edges": [(0, 1), (1, 2)], "diameter": 2,
+            "constraints": [{"walk": [0, 1, 2]}, {"walk": [2, 1, 0]}]}
+    # star with ONE leaf: 0(label 1) - 1(label 2): the only length-2 walk returns to the source
+    r = _run(oracle, 2, [(0, 1)], [1, 2], spec, tds_from=-1)
+    assert r.in_map.sum() == 0
+    # star with TWO leaves: both leaves can be the two ends
+    r = _run(oracle, 3, [(0, 1), (1, 2)], [1, 2, 1], spec, tds_from=-1)
+    v, t = r.active_vertices()
+    assert v.tolist() == [0, 1, 2] and t.tolist() == [0b101, 0b010, 0b101]
+
+
+def test_planted_tree_is_found_exactly_once(oracle):
+    spec = PT.RMAT_LOG2_TREE
+    labels = spec["labels"] + [9, 9, 9]
+    edges = list(spec["edges"]) + [(7, 8), (8, 9), (0, 7)]
+    r = _run(oracle, 10, edges, labels, spec)
+    v, _ = r.active_vertices()
+    assert v.tolist() == list(range(7))
+    assert len(r.active_edges) == 12
+    # template vertices 0/4 (label 3) and 2/6 (label 7) are interchangeable only where the tree allows it
+    assert r.subgraphs[4].tolist() == [[0, 1, 2, 1, 3, 5, 4, 5, 6]]
+    assert r.hazards[:5].tolist() == [0, 0, 0, 0, 0]
+
+
+def test_lcc_only_runs_to_a_vertex_fixed_point(oracle):
+    spec = PT.RMAT_LOG2_TREE
+    edges = cases.random_multigraph(4, 80, 300)
+    labels = cases.random_labels(4, 80, [2, 3, 4, 5, 7])
+    r = _run(oracle, 80, edges, labels, spec, lcc_only=True)
+    assert all(k == "LP" for _, k, _, _, _ in r.rows)
+    d = spec["diameter"]
+    assert r.rows[-1][3] == r.rows[-1 - d][3] if len(r.rows) > d else True
+
+
+def test_golden_fixtures(oracle):
+    gold = json.load(open(os.path.join(HERE, "golden", "runs.json")))
+    specs = {s[0]: s for s in cases.SPECS}
+    for case in gold:
+        _, spec, labelset, tds_from = specs[case["spec"]]
+        edges = cases.random_multigraph(case["seed"], case["n"], case["m"])
+        labels = cases.random_labels(case["seed"], case["n"], labelset)
+        r = _run(oracle, case["n"], edges, labels, spec, tds_from=tds_from, max_iterations=50)
+        s = cases.run_summary(r)
+        assert [list(x) for x in s["rows"]] == case["rows"]
+        assert [list(x) for x in s["vertices"]] == case["vertices"]
+        assert [list(x) for x in s["edges"]] == case["edges"]
+        assert [[list(w) for w in sg] for sg in s["subgraphs"]] == case["subgraphs"]

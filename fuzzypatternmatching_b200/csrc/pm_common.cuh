@@ -28,12 +28,14 @@ struct PatConst {
   uint16_t LMc[17];    // class -> bitmask of template vertices carrying that label; [16] = 0
   uint64_t clabel[16]; // class -> label value
   int ncls;
+  uint8_t cls_of_label[64];  // small-label mode: label value -> class (PM_NOCLASS if none)
 };
 
 struct NlcConst {      // one non-local constraint (walk)
   uint8_t cls[16];     // class of P[h]  (PM_NOCLASS if the label is not in the template)
   uint8_t I[16];       // template vertex id at hop h
   uint8_t e[16];       // enumeration index (TDS history rule)
+  uint8_t lab[16];     // label value of P[h] when labels are bytes < 64, else 255
   int n;               // walk length = C + 2
   int C;               // max itr_count
   int valid_cycle;
@@ -51,12 +53,14 @@ struct DevCounters {
   unsigned long long matches;   // TDS: completed walks
   unsigned long long fanout;    // NLCC: adjacency slots walked by tokens
   unsigned long long hash_n;    // NLCC: keys in the (vertex, source) set
+  unsigned long long lvl[20];   // NLCC: token pool level bounds, level h = [lvl[h], lvl[h+1])
 };
 
 struct RowStat {                // one result row, accumulated on the device
   unsigned long long nv, ne;
   unsigned long long scanned[3];   // adjacency slots walked, per degree bin
   unsigned long long verts[3];     // live vertices whose row was walked, per degree bin
+  unsigned long long filtered;     // candidates settled or passed on by the signature filter
 };
 
 }  // namespace pm
@@ -76,6 +80,11 @@ struct pm_ctx {
   uint32_t* col0 = nullptr;    // [Epad] pristine adjacency: sorted, distinct, rows padded to 8 with PM_SENTINEL
   uint32_t* colw = nullptr;    // [Epad] working adjacency: first adeg[v] slots of a row = keys(E_v)
   uint64_t* label = nullptr;   // [V] vertex labels
+  uint8_t* lab8 = nullptr;     // [V] labels as bytes when every label is < 64 (degree labels always are)
+  unsigned long long* sig = nullptr;  // [V] bit l set iff some distinct neighbour carries label l (labels < 64)
+  uint8_t* lab0 = nullptr;     // [Epad] label of the neighbour stored in col0 (labels < 64)
+  uint8_t* labw = nullptr;     // [Epad] label of the neighbour stored in colw
+  bool labels_small = false;   // lab8 / sig are valid
   bool has_graph = false, has_labels = false;
 
   // ---- pattern ----------------------------------------------------------------
@@ -90,6 +99,7 @@ struct pm_ctx {
   uint8_t* cls = nullptr;   // [V] label class (index into the template's distinct labels, PM_NOCLASS = none)
   uint32_t* fr[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};  // frontier lists by bin
   int cur = 0;              // which frontier buffer is current
+  bool bin_live[3] = {true, true, true};  // bin b or a larger one was non-empty at the last host sync
   pm::DevCounters* cnt = nullptr;      // device
   pm::DevCounters* h_cnt = nullptr;    // pinned host mirror
   pm::RowStat* rowstat = nullptr;      // device, [diameter + 1]
@@ -117,8 +127,8 @@ struct pm_ctx {
   pm_run_summary_t summary{};
   std::vector<cudaEvent_t> events;
   // CUDA-event timing of the first-superstep scan kernels (the dominant kernels), per bin
-  cudaEvent_t kev[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
-  pm_kernel_stats_t kstat[3] = {};
+  cudaEvent_t kev[4][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+  pm_kernel_stats_t kstat[4] = {};  // [3]: the first-superstep signature filter
 };
 
 namespace pm {

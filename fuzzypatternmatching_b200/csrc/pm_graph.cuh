@@ -103,7 +103,124 @@ __global__ void k_labels_degree_log2(const uint32_t* __restrict__ degm, uint64_t
   for (; v < V; v += stride) label[v] = (uint64_t)(32 - __clz(degm[v]));
 }
 
+__global__ void k_labels_to_bytes(const uint64_t* __restrict__ label, uint64_t V, uint8_t* __restrict__ lab8) {
+  uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; v < V; v += stride) lab8[v] = (uint8_t)label[v];
+}
+
+// Neighbour-label signature: sig[v] = OR over the distinct neighbours u of v of (1 << label[u]).
+// It is a property of graph + labels (built once, next to the labels, outside any search) and
+// lets the first LCC superstep decide most candidates without walking their rows.
+// 8-lane groups take rows of up to kSigBig slots; longer rows are queued for k_build_sig_big.
+#define PM_SIG_BIG 2048u
+__global__ void __launch_bounds__(256) k_build_sig(const uint32_t* __restrict__ rowblk, const uint32_t* __restrict__ deg,
+                                                   const uint32_t* __restrict__ col0, const uint8_t* __restrict__ lab8,
+                                                   uint64_t V, unsigned long long* __restrict__ sig,
+                                                   uint32_t* __restrict__ big_list, uint32_t* __restrict__ big_n) {
+  const uint32_t lane = threadIdx.x & 31, gl = lane & 7, gw = lane >> 3;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t base = warp * 4; base < V; base += nwarps * 4) {
+    const uint64_t v = base + gw;
+    uint32_t d = v < V ? deg[v] : 0u;
+    if (d > PM_SIG_BIG) {
+      if (gl == 0) big_list[atomicAdd(big_n, 1u)] = (uint32_t)v;
+      d = 0;
+    }
+    const uint64_t row = v < V ? (uint64_t)rowblk[v] * 8 : 0;
+    const uint32_t passes = (d + 31) / 32;
+    const uint32_t maxp = __reduce_max_sync(0xffffffffu, passes);
+    unsigned long long m = 0;
+    for (uint32_t p = 0; p < maxp; ++p) {
+      const uint32_t j0 = p * 32 + gl * 4;
+      if (j0 < d) {
+        const uint4 q = *reinterpret_cast<const uint4*>(col0 + row + j0);
+        m |= 1ull << lab8[q.x];
+        if (j0 + 1 < d) m |= 1ull << lab8[q.y];
+        if (j0 + 2 < d) m |= 1ull << lab8[q.z];
+        if (j0 + 3 < d) m |= 1ull << lab8[q.w];
+      }
+    }
+    m |= __shfl_xor_sync(0xffffffffu, m, 1);
+    m |= __shfl_xor_sync(0xffffffffu, m, 2);
+    m |= __shfl_xor_sync(0xffffffffu, m, 4);
+    if (v < V && gl == 0 && deg[v] <= PM_SIG_BIG) sig[v] = m;
+  }
+}
+
+__global__ void __launch_bounds__(1024) k_build_sig_big(const uint32_t* __restrict__ rowblk, const uint32_t* __restrict__ deg,
+                                                        const uint32_t* __restrict__ col0, const uint8_t* __restrict__ lab8,
+                                                        unsigned long long* __restrict__ sig,
+                                                        const uint32_t* __restrict__ big_list, const uint32_t* __restrict__ big_n) {
+  __shared__ unsigned long long s_m[32];
+  const uint32_t n = *big_n;
+  for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+    const uint32_t v = big_list[i], d = deg[v];
+    const uint64_t row = (uint64_t)rowblk[v] * 8;
+    unsigned long long m = 0;
+    for (uint32_t j = threadIdx.x; j < d; j += blockDim.x) m |= 1ull << lab8[col0[row + j]];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m |= __shfl_xor_sync(0xffffffffu, m, o);
+    if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long t = 0;
+      for (uint32_t w = 0; w < (blockDim.x >> 5); ++w) t |= s_m[w];
+      sig[v] = t;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void k_build_lab0(const uint32_t* __restrict__ col0, const uint8_t* __restrict__ lab8, uint64_t n,
+                             uint8_t* __restrict__ lab0) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const uint32_t u = col0[i];
+    lab0[i] = u == PM_SENTINEL ? (uint8_t)0 : lab8[u];
+  }
+}
+
+// after the labels changed: byte labels + neighbour-label signatures (labels < 64 only)
+inline int labels_derive(pm_ctx* c, bool small) {
+  dev_free(c->lab8);
+  dev_free(c->sig);
+  dev_free(c->lab0);
+  dev_free(c->labw);
+  c->labels_small = false;
+  if (!small) return 0;
+  int rc;
+  uint32_t *big_list = nullptr, *big_n = nullptr;
+  if ((rc = dev_alloc(c, &c->lab8, c->V, &c->graph_bytes))) return rc;
+  if ((rc = dev_alloc(c, &c->sig, c->V, &c->graph_bytes))) return rc;
+  if ((rc = dev_alloc(c, &c->lab0, c->Epad + 64, &c->graph_bytes))) return rc;
+  if ((rc = dev_alloc(c, &c->labw, c->Epad + 64, &c->graph_bytes))) return rc;
+  if ((rc = dev_alloc(c, &big_list, c->Epad / PM_SIG_BIG + 1024))) return rc;
+  if ((rc = dev_alloc(c, &big_n, 1))) { dev_free(big_list); return rc; }
+  cudaStream_t st = c->stream;
+  cudaMemsetAsync(big_n, 0, 4, st);
+  k_labels_to_bytes<<<grid_for(), kBlock, 0, st>>>(c->label, c->V, c->lab8);
+  k_build_sig<<<grid_for(), 256, 0, st>>>(c->rowblk, c->deg, c->col0, c->lab8, c->V, c->sig, big_list, big_n);
+  k_build_sig_big<<<148, 1024, 0, st>>>(c->rowblk, c->deg, c->col0, c->lab8, c->sig, big_list, big_n);
+  k_build_lab0<<<grid_for(), kBlock, 0, st>>>(c->col0, c->lab8, c->Epad + 64, c->lab0);
+  c->launches += 4;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  dev_free(big_list);
+  dev_free(big_n);
+  if (e != cudaSuccess) return fail(c, PM_ERR_CUDA, std::string("labels_derive: ") + cudaGetErrorString(e));
+  c->labels_small = true;
+  return 0;
+}
+
 inline void graph_free(pm_ctx* c) {
+  dev_free(c->lab8);
+  dev_free(c->sig);
+  dev_free(c->lab0);
+  dev_free(c->labw);
+  c->labels_small = false;
   dev_free(c->rowblk);
   dev_free(c->deg);
   dev_free(c->degm);

@@ -55,6 +55,50 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
   return m;
 }
 
+// Appends up to ITEMS values per thread to one of three lists with ONE atomic per list
+// and block (a returning atomic on a single address retires ~1 per clock chip-wide, so
+// per-warp atomics would serialise the whole grid).  Must be called by every thread of
+// the block; order inside a block follows (item, thread).
+template <int ITEMS>
+__device__ __forceinline__ void block_bin_append(const bool (&flag)[ITEMS], const int (&bin)[ITEMS],
+                                                 const uint32_t (&val)[ITEMS], uint32_t* d0, uint32_t* d1,
+                                                 uint32_t* d2, uint32_t* counters) {
+  __shared__ uint32_t s_w[kBlock / 32][3];
+  __shared__ uint32_t s_base[3];
+  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t lt = lanemask_lt();
+  uint32_t off[ITEMS];
+  uint32_t tot[3] = {0, 0, 0};
+#pragma unroll
+  for (int k = 0; k < ITEMS; ++k) {
+    off[k] = 0;
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      const uint32_t m = __ballot_sync(0xffffffffu, flag[k] && bin[k] == b);
+      if (flag[k] && bin[k] == b) off[k] = tot[b] + __popc(m & lt);
+      tot[b] += __popc(m);
+    }
+  }
+  if (lane == 0) { s_w[w][0] = tot[0]; s_w[w][1] = tot[1]; s_w[w][2] = tot[2]; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    uint32_t t = 0;
+    for (uint32_t i = 0; i < blockDim.x / 32; ++i) t += s_w[i][threadIdx.x];
+    s_base[threadIdx.x] = t ? atomicAdd(&counters[threadIdx.x], t) : 0u;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < ITEMS; ++k)
+    if (flag[k]) {
+      const int b = bin[k];
+      uint32_t base = s_base[b];
+      for (uint32_t i = 0; i < w; ++i) base += s_w[i][b];
+      uint32_t* dst = b == 0 ? d0 : (b == 1 ? d1 : d2);
+      dst[base + off[k]] = val[k];
+    }
+  __syncthreads();
+}
+
 struct LccArgs {
   const uint32_t* rowblk;
   const uint32_t* deg;
@@ -64,6 +108,8 @@ struct LccArgs {
   uint16_t* Tst;
   uint32_t* adeg;
   const uint8_t* cls;
+  const uint8_t* lab0;  // [Epad] label of the neighbour in col0 (labels < 64 only)
+  uint8_t* labw;        // [Epad] same for colw, moved along by the row compaction
   DevCounters* cnt;
   RowStat* row;   // accumulator of this superstep
   int bin;        // degree bin this launch serves (row statistics)
@@ -72,49 +118,116 @@ struct LccArgs {
 // ---------------------------------------------------------------------------
 // per-pattern initialisation (beta.cpp:484-492 + the label test every vertex
 // performs in the first superstep, ee.hpp:371-380 / :523-546):
-//   cls[v]  = class of label[v];  S[v] = labelmask(label[v])  (0: v goes inactive)
-//   candidates are appended to the frontier bin of their degree
+//   cls[v] = class of label[v] for EVERY vertex (the first scan gathers it);
+//   candidates (label matches a template vertex, degree > 0) get S[v] =
+//   labelmask(label[v]) and are appended to the frontier bin of their degree.
+//   S of a non-candidate is never read: every later gather goes through an edge
+//   map, and edge maps only ever hold candidates.
+// SMALL = labels are bytes < 64 (lab8 + 64-entry class table), else u64 compare.
 // ---------------------------------------------------------------------------
-__global__ void k_init_state(const uint64_t* __restrict__ label, const uint32_t* __restrict__ deg,
-                             uint64_t V, uint8_t* __restrict__ cls, uint16_t* __restrict__ S,
-                             uint16_t* __restrict__ Tst, uint32_t* __restrict__ adeg,
-                             uint32_t* fr_small, uint32_t* fr_mid, uint32_t* fr_big, DevCounters* cnt,
-                             int buf) {
-  const uint32_t lane = threadIdx.x & 31;
-  uint64_t v0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31ull;
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (; v0 < V; v0 += stride) {
-    uint64_t v = v0 + lane;
-    uint32_t c = PM_NOCLASS, d = 0;
-    if (v < V) {
-      uint64_t lab = label[v];
-      d = deg[v];
+template <bool SMALL>
+__global__ void __launch_bounds__(kBlock) k_init_state(const uint64_t* __restrict__ label,
+                                                        const uint8_t* __restrict__ lab8,
+                                                        const uint32_t* __restrict__ deg, uint64_t V,
+                                                        uint8_t* __restrict__ cls, uint16_t* __restrict__ S,
+                                                        uint32_t* fr_small, uint32_t* fr_mid, uint32_t* fr_big,
+                                                        DevCounters* cnt, int buf) {
+  __shared__ uint8_t s_cl[64];
+  __shared__ uint16_t s_lm[17];
+  if (threadIdx.x < 64) s_cl[threadIdx.x] = c_pat.cls_of_label[threadIdx.x];
+  if (threadIdx.x < 17) s_lm[threadIdx.x] = c_pat.LMc[threadIdx.x];
+  __syncthreads();
+  constexpr int IT = 8;
+  const uint64_t tile = (uint64_t)blockDim.x * IT;
+  for (uint64_t base = (uint64_t)blockIdx.x * tile; base < V; base += (uint64_t)gridDim.x * tile) {
+    bool cand[IT];
+    int bin[IT];
+    uint32_t val[IT];
 #pragma unroll
-      for (int k = 0; k < 16; ++k)
-        if (k < c_pat.ncls && c_pat.clabel[k] == lab) c = k;
-      cls[v] = (uint8_t)c;
-      uint16_t lm = d ? c_pat.LMc[c] : (uint16_t)0;
-      S[v] = lm;
-      Tst[v] = lm;
-      adeg[v] = 0;
-      if (lm == 0) c = PM_NOCLASS;
-    }
-    const bool cand = (c != PM_NOCLASS);
-    const int bin = d <= PM_SMALL_MAX ? 0 : (d <= PM_MID_MAX ? 1 : 2);
+    for (int k = 0; k < IT; ++k) {
+      const uint64_t v = base + (uint64_t)k * blockDim.x + threadIdx.x;
+      uint32_t c = PM_NOCLASS, d = 0;
+      if (v < V) {
+        if (SMALL) {
+          c = s_cl[lab8[v] & 63];
+        } else {
+          const uint64_t lab = label[v];
 #pragma unroll
-    for (int b = 0; b < 3; ++b) {
-      uint32_t m = __ballot_sync(0xffffffffu, cand && bin == b);
-      if (m) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&cnt->fr_n[buf][b], (uint32_t)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (cand && bin == b) {
-          uint32_t* dst = b == 0 ? fr_small : (b == 1 ? fr_mid : fr_big);
-          dst[base + __popc(m & lanemask_lt())] = (uint32_t)v;
+          for (int q = 0; q < 16; ++q)
+            if (q < c_pat.ncls && c_pat.clabel[q] == lab) c = q;
+        }
+        cls[v] = (uint8_t)c;
+        if (c != PM_NOCLASS) {
+          d = deg[v];
+          if (d) S[v] = s_lm[c]; else c = PM_NOCLASS;
         }
       }
+      cand[k] = c != PM_NOCLASS;
+      bin[k] = d <= PM_SMALL_MAX ? 0 : (d <= PM_MID_MAX ? 1 : 2);
+      val[k] = (uint32_t)v;
     }
+    block_bin_append<IT>(cand, bin, val, fr_small, fr_mid, fr_big, &cnt->fr_n[buf][0]);
   }
+}
+
+// ---------------------------------------------------------------------------
+// first-superstep signature filter.  In the first superstep every neighbour u of
+// v sends labelmask(label[u]) (ee.hpp:519-561), so heard(v) depends only on WHICH
+// labels occur among v's neighbours: heard(v) = OR { LM(l) : l in sig[v],
+// LM(l) & NB(T_v) != 0 } — exactly what walking the row would compute.  A
+// candidate whose T_state comes out empty leaves (or never enters) the map; it is
+// settled here from 8 bytes of signature instead of its whole row.  Survivors go
+// to the next frontier buffer and are scanned normally (their edge maps must be
+// built from the row).  Writing S[v] = 0 here is safe: first-superstep scans
+// read neighbour classes from cls[], never S[].
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_lcc_first_filter(LccArgs a, const unsigned long long* __restrict__ sig,
+                                                              const uint32_t* __restrict__ l0,
+                                                              const uint32_t* __restrict__ l1,
+                                                              const uint32_t* __restrict__ l2, uint32_t* n0,
+                                                              uint32_t* n1, uint32_t* n2, int cur, int nxt) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t c0 = a.cnt->fr_n[cur][0], c1 = a.cnt->fr_n[cur][1], c2 = a.cnt->fr_n[cur][2];
+  const uint32_t total = c0 + c1 + c2;
+  unsigned long long verts = 0;
+  constexpr int IT = 4;
+  const uint32_t tile = blockDim.x * IT;
+  for (uint32_t base = blockIdx.x * tile; base < total; base += gridDim.x * tile) {
+    bool keep[IT];
+    int bin[IT];
+    uint32_t val[IT];
+#pragma unroll
+    for (int k = 0; k < IT; ++k) {
+      const uint32_t i = base + k * blockDim.x + threadIdx.x;
+      keep[k] = false;
+      bin[k] = 0;
+      val[k] = 0;
+      if (i < total) {
+        bin[k] = i < c0 ? 0 : (i < c0 + c1 ? 1 : 2);
+        const uint32_t v = bin[k] == 0 ? l0[i] : (bin[k] == 1 ? l1[i - c0] : l2[i - c0 - c1]);
+        val[k] = v;
+        const uint32_t Tv = a.S[v];
+        const unsigned long long sg = sig[v];
+        const uint32_t NBv = nb_of(Tv);
+        uint32_t heard = 0;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const uint32_t lm = c_pat.LMc[q];
+          if (q < c_pat.ncls && ((sg >> (c_pat.clabel[q] & 63)) & 1ull) && (lm & NBv)) heard |= lm;
+        }
+        keep[k] = cover_of(Tv, heard) != 0;
+        if (!keep[k]) {
+          a.S[v] = 0;
+          if (heard) a.cnt->nf = 1u;  // it entered the map and left it again (ee.hpp:941-946, 968-970)
+        }
+        verts++;
+      }
+    }
+    block_bin_append<IT>(keep, bin, val, n0, n1, n2, &a.cnt->fr_n[nxt][0]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) verts += __shfl_xor_sync(0xffffffffu, verts, o);
+  if (lane == 0 && verts) atomicAdd(&a.row->filtered, verts);
 }
 
 // ---------------------------------------------------------------------------
@@ -125,11 +238,16 @@ __global__ void k_init_state(const uint64_t* __restrict__ label, const uint32_t*
 //   col0 (all deg[v] slots), neighbour mask = labelmask via the class array
 //   (ee.hpp:519-561 sender, :368-404 receiver); otherwise walk keys(E_v) in colw.
 // ---------------------------------------------------------------------------
-template <int GROUP, bool FIRST>
+//   STREAM = the label of every neighbour travels next to its id (lab0 / labw,
+//   labels < 64): the first superstep then needs no gather at all — ids and labels
+//   are both streamed — and later compactions keep labw aligned with colw for NLCC.
+template <int GROUP, bool FIRST, bool STREAM>
 __global__ void __launch_bounds__(kBlock) k_lcc_scan(LccArgs a, const uint32_t* __restrict__ list,
                                                       const uint32_t* __restrict__ n_ptr) {
   __shared__ uint16_t s_lm[17];
+  __shared__ uint16_t s_lml[64];  // label value -> labelmask
   if (threadIdx.x < 17) s_lm[threadIdx.x] = c_pat.LMc[threadIdx.x];
+  if (threadIdx.x < 64) s_lml[threadIdx.x] = c_pat.LMc[c_pat.cls_of_label[threadIdx.x]];
   __syncthreads();
   constexpr int GPW = 32 / GROUP;  // groups per warp
   const uint32_t lane = threadIdx.x & 31;
@@ -160,7 +278,11 @@ __global__ void __launch_bounds__(kBlock) k_lcc_scan(LccArgs a, const uint32_t* 
     for (uint32_t p = 0; p < maxp; ++p) {
       const uint32_t j0 = p * GROUP * 4 + gl * 4;
       uint4 q = make_uint4(PM_SENTINEL, PM_SENTINEL, PM_SENTINEL, PM_SENTINEL);
-      if (j0 < d) q = *reinterpret_cast<const uint4*>(src + row + j0);
+      uint32_t l4 = 0;
+      if (j0 < d) {
+        q = *reinterpret_cast<const uint4*>(src + row + j0);
+        if (STREAM) l4 = *reinterpret_cast<const uint32_t*>((FIRST ? a.lab0 : a.labw) + row + j0);
+      }
       uint32_t u[4] = {q.x, q.y, q.z, q.w};
       uint32_t m[4];
       bool keep[4];
@@ -169,7 +291,10 @@ __global__ void __launch_bounds__(kBlock) k_lcc_scan(LccArgs a, const uint32_t* 
         const bool act = j0 + k < d;
         const uint32_t uu = u[k] & PM_IDMASK;
         m[k] = 0;
-        if (act) m[k] = FIRST ? (uint32_t)s_lm[a.cls[uu]] : (uint32_t)a.S[uu];
+        if (act) {
+          if (FIRST) m[k] = STREAM ? (uint32_t)s_lml[(l4 >> (8 * k)) & 63u] : (uint32_t)s_lm[a.cls[uu]];
+          else m[k] = (uint32_t)a.S[uu];
+        }
       }
       uint32_t cnt_lane = 0;
       uint32_t below = 0;
@@ -189,7 +314,11 @@ __global__ void __launch_bounds__(kBlock) k_lcc_scan(LccArgs a, const uint32_t* 
       uint32_t pos = out + below;
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        if (keep[k]) a.colw[row + pos++] = u[k] & PM_IDMASK;
+        if (keep[k]) {
+          a.colw[row + pos] = u[k] & PM_IDMASK;
+          if (STREAM) a.labw[row + pos] = (uint8_t)(l4 >> (8 * k));
+          ++pos;
+        }
       out += cnt_lane;
     }
 #pragma unroll
@@ -219,13 +348,14 @@ __global__ void __launch_bounds__(kBlock) k_lcc_scan(LccArgs a, const uint32_t* 
 }
 
 // one CTA per high-degree vertex ("delegates across warps and CTAs")
-template <bool FIRST>
+template <bool FIRST, bool STREAM>
 __global__ void __launch_bounds__(1024) k_lcc_scan_big(LccArgs a, const uint32_t* __restrict__ list,
                                                         const uint32_t* __restrict__ n_ptr) {
   __shared__ uint16_t s_lm[17];
+  __shared__ uint16_t s_lml[64];
+  if (threadIdx.x < 64) s_lml[threadIdx.x] = c_pat.LMc[c_pat.cls_of_label[threadIdx.x]];
   __shared__ uint32_t s_wcnt[32];
   __shared__ uint32_t s_heard[32];
-  __shared__ uint32_t s_out;
   if (threadIdx.x < 17) s_lm[threadIdx.x] = c_pat.LMc[threadIdx.x];
   const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const uint32_t lt = lanemask_lt();
@@ -239,13 +369,17 @@ __global__ void __launch_bounds__(1024) k_lcc_scan_big(LccArgs a, const uint32_t
     const uint32_t NBv = nb_of(Tv);
     const uint64_t row = (uint64_t)a.rowblk[v] * 8;
     const uint32_t* __restrict__ src = FIRST ? a.col0 : a.colw;
-    if (threadIdx.x == 0) s_out = 0;
+    uint32_t outp = 0;  // slots kept so far (every thread tracks the same value)
     uint32_t heard = 0;
     const uint32_t per_pass = blockDim.x * 4;
     for (uint32_t p0 = 0; p0 < d; p0 += per_pass) {
       const uint32_t j0 = p0 + threadIdx.x * 4;
       uint4 q = make_uint4(PM_SENTINEL, PM_SENTINEL, PM_SENTINEL, PM_SENTINEL);
-      if (j0 < d) q = *reinterpret_cast<const uint4*>(src + row + j0);
+      uint32_t l4 = 0;
+      if (j0 < d) {
+        q = *reinterpret_cast<const uint4*>(src + row + j0);
+        if (STREAM) l4 = *reinterpret_cast<const uint32_t*>((FIRST ? a.lab0 : a.labw) + row + j0);
+      }
       uint32_t u[4] = {q.x, q.y, q.z, q.w};
       uint32_t m[4];
       bool keep[4];
@@ -254,7 +388,10 @@ __global__ void __launch_bounds__(1024) k_lcc_scan_big(LccArgs a, const uint32_t
         const bool act = j0 + k < d;
         const uint32_t uu = u[k] & PM_IDMASK;
         m[k] = 0;
-        if (act) m[k] = FIRST ? (uint32_t)s_lm[a.cls[uu]] : (uint32_t)a.S[uu];
+        if (act) {
+          if (FIRST) m[k] = STREAM ? (uint32_t)s_lml[(l4 >> (8 * k)) & 63u] : (uint32_t)s_lm[a.cls[uu]];
+          else m[k] = (uint32_t)a.S[uu];
+        }
       }
       uint32_t below = 0, wtotal = 0;
 #pragma unroll
@@ -270,18 +407,22 @@ __global__ void __launch_bounds__(1024) k_lcc_scan_big(LccArgs a, const uint32_t
       }
       if (lane == 0) s_wcnt[wid] = wtotal;
       __syncthreads();  // every warp has read its slots of this pass
-      uint32_t wbase = s_out;
-      for (uint32_t w = 0; w < wid; ++w) wbase += s_wcnt[w];
+      uint32_t wbase = outp, ptotal = 0;
+      for (uint32_t w = 0; w < nw; ++w) {
+        const uint32_t cw = s_wcnt[w];
+        if (w < wid) wbase += cw;
+        ptotal += cw;
+      }
       uint32_t pos = wbase + below;
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        if (keep[k]) a.colw[row + pos++] = u[k] & PM_IDMASK;
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        uint32_t t = s_out;
-        for (uint32_t w = 0; w < nw; ++w) t += s_wcnt[w];
-        s_out = t;
-      }
+        if (keep[k]) {
+          a.colw[row + pos] = u[k] & PM_IDMASK;
+          if (STREAM) a.labw[row + pos] = (uint8_t)(l4 >> (8 * k));
+          ++pos;
+        }
+      outp += ptotal;
+      __syncthreads();  // s_wcnt may be overwritten by the next pass only after everyone has read it
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) heard |= __shfl_xor_sync(0xffffffffu, heard, o);
@@ -293,7 +434,7 @@ __global__ void __launch_bounds__(1024) k_lcc_scan_big(LccArgs a, const uint32_t
       const uint32_t T0 = FIRST ? Tv : (uint32_t)a.Tst[v];
       const uint32_t ts = Tv ? cover_of(T0, h) : 0u;
       a.Tst[v] = (uint16_t)ts;
-      a.adeg[v] = s_out;
+      a.adeg[v] = outp;
       if (ts == 0 && (FIRST ? h != 0u : Tv != 0u)) a.cnt->nf = 1u;
       if (Tv) {
         atomicAdd(&a.row->scanned[2], (unsigned long long)d);
@@ -316,34 +457,30 @@ __global__ void __launch_bounds__(kBlock) k_lcc_commit(LccArgs a, const uint32_t
   const uint32_t c0 = a.cnt->fr_n[cur][0], c1 = a.cnt->fr_n[cur][1], c2 = a.cnt->fr_n[cur][2];
   const uint32_t total = c0 + c1 + c2;
   unsigned long long nv = 0, ne = 0;
-  uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u;
-  const uint32_t stride = gridDim.x * blockDim.x;
-  for (; i0 < total; i0 += stride) {
-    const uint32_t i = i0 + lane;
-    bool alive = false;
-    uint32_t v = 0, d = 0;
-    if (i < total) {
-      v = i < c0 ? l0[i] : (i < c0 + c1 ? l1[i - c0] : l2[i - c0 - c1]);
-      const uint16_t ts = a.Tst[v];
-      a.S[v] = ts;
-      alive = ts != 0;
-      d = a.adeg[v];
-      if (alive) { nv++; ne += d; }
-    }
-    const int bin = d <= PM_SMALL_MAX ? 0 : (d <= PM_MID_MAX ? 1 : 2);
+  constexpr int IT = 4;
+  const uint32_t tile = blockDim.x * IT;
+  for (uint32_t base = blockIdx.x * tile; base < total; base += gridDim.x * tile) {
+    bool alive[IT];
+    int bin[IT];
+    uint32_t val[IT];
 #pragma unroll
-    for (int b = 0; b < 3; ++b) {
-      const uint32_t m = __ballot_sync(0xffffffffu, alive && bin == b);
-      if (m) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&a.cnt->fr_n[nxt][b], (uint32_t)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (alive && bin == b) {
-          uint32_t* dst = b == 0 ? n0 : (b == 1 ? n1 : n2);
-          dst[base + __popc(m & lanemask_lt())] = v;
-        }
+    for (int k = 0; k < IT; ++k) {
+      const uint32_t i = base + k * blockDim.x + threadIdx.x;
+      alive[k] = false;
+      bin[k] = 0;
+      val[k] = 0;
+      if (i < total) {
+        const uint32_t v = i < c0 ? l0[i] : (i < c0 + c1 ? l1[i - c0] : l2[i - c0 - c1]);
+        const uint16_t ts = a.Tst[v];
+        a.S[v] = ts;
+        alive[k] = ts != 0;
+        const uint32_t d = a.adeg[v];
+        if (alive[k]) { nv++; ne += d; }
+        bin[k] = d <= PM_SMALL_MAX ? 0 : (d <= PM_MID_MAX ? 1 : 2);
+        val[k] = v;
       }
     }
+    block_bin_append<IT>(alive, bin, val, n0, n1, n2, &a.cnt->fr_n[nxt][0]);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {

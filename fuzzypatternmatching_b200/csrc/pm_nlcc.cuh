@@ -46,6 +46,7 @@ struct NlcArgs {
   const uint16_t* S;
   const uint32_t* adeg;
   const uint8_t* cls;
+  const uint8_t* labw;  // label of the neighbour stored in colw (STREAM kernels)
   uint8_t* ok;
   uint32_t* src_list;
   unsigned long long* hset;
@@ -79,6 +80,25 @@ __device__ __forceinline__ bool hset_insert(const NlcArgs& a, uint32_t u, uint32
   }
   a.cnt->overflow = 1u;
   return false;
+}
+
+// Reserves `n` consecutive slots per lane behind *counter with one atomic per warp;
+// returns this lane's first slot.  All 32 lanes must call it.
+__device__ __forceinline__ unsigned long long warp_reserve(unsigned long long* counter, uint32_t n) {
+  const uint32_t lane = threadIdx.x & 31;
+  uint32_t incl = n;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= (uint32_t)o) incl += t;
+  }
+  const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+  unsigned long long base = 0;
+  if (total) {
+    if (lane == 31) base = atomicAdd(counter, (unsigned long long)total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+  }
+  return base + incl - n;
 }
 
 // ---------------------------------------------------------------------------
@@ -130,16 +150,65 @@ __device__ __forceinline__ void mark_edge(const NlcArgs& a, uint32_t s, uint32_t
   if (lo < a.adeg[s] && (a.colw[row + lo] & PM_IDMASK) == parent) atomicOr(&a.colw[row + lo], 0x80000000u);
 }
 
+// level bookkeeping on the device (no host round trip per hop): level 0 = the sources
+__global__ void k_nlcc_begin(DevCounters* cnt) {
+  cnt->lvl[0] = 0;
+  cnt->lvl[1] = cnt->n_src;
+  cnt->pool_n = cnt->n_src;
+}
+// after the expand kernel that produced level h
+__global__ void k_nlcc_close_level(DevCounters* cnt, int h, unsigned long long pool_cap) {
+  const unsigned long long n = cnt->pool_n;
+  cnt->lvl[h + 1] = n < pool_cap ? n : pool_cap;
+}
+
 // ---------------------------------------------------------------------------
-// nem_1: advance tokens [lo, hi) (accepted at hop hn-1) to hop hn
+// nem_1, final hop of a CYCLE constraint (max_itr_count == itr_count,
+// nem_1.hpp:661-773): the token at v (hop C) would be forwarded along E_v and only
+// the copy arriving at the source s can succeed, so instead of walking E_v the row
+// is binary-searched for s.  Success acknowledges the source and flags the edge
+// E_s[v] the token came back on (nem_1.hpp:764-770).
 // ---------------------------------------------------------------------------
-template <bool FINAL>
-__global__ void __launch_bounds__(kBlock) k_nem1_expand(NlcArgs a, uint64_t lo, uint64_t hi, int hn) {
+__global__ void __launch_bounds__(kBlock) k_nem1_final_cycle(NlcArgs a, int hlevel, int hn) {
+  const unsigned long long lo = a.cnt->lvl[hlevel], hi = a.cnt->lvl[hlevel + 1];
+  unsigned long long fan = 0;
+  for (unsigned long long t = lo + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < hi;
+       t += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint2 tk = a.pool[t];
+    const uint32_t v = tk.x, s = tk.y;
+    const uint32_t ss = a.S[s];
+    if (ss == 0 || !hop_ok(ss, a.cls[s], hn)) continue;  // receiver tests at the source (nem_1.hpp:557-581)
+    const uint64_t row = (uint64_t)a.rowblk[v] * 8;
+    uint32_t b = 0, e = a.adeg[v];
+    fan += e;
+    while (b < e) {  // rows stay ascending: compaction is stable
+      const uint32_t mid = (b + e) >> 1;
+      const uint32_t x = a.colw[row + mid] & PM_IDMASK;
+      if (x < s) b = mid + 1; else e = mid;
+    }
+    if (b < a.adeg[v] && (a.colw[row + b] & PM_IDMASK) == s) {
+      a.ok[s] = 1;
+      a.cnt->found = 1u;
+      mark_edge(a, s, v);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) fan += __shfl_xor_sync(0xffffffffu, fan, o);
+  if ((threadIdx.x & 31) == 0 && fan) atomicAdd(&a.cnt->fanout, fan);
+}
+
+// ---------------------------------------------------------------------------
+// nem_1: advance the tokens of level hlevel (accepted at hop hn-1) to hop hn
+// ---------------------------------------------------------------------------
+template <bool FINAL, bool STREAM>
+__global__ void __launch_bounds__(kBlock) k_nem1_expand(NlcArgs a, int hlevel, int hn) {
+  const uint64_t lo = a.cnt->lvl[hlevel], hi = a.cnt->lvl[hlevel + 1];
   constexpr int GROUP = 8;
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t gl = lane % GROUP, gw = lane / GROUP;
   const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  const uint32_t want_lab = c_nlc.lab[hn];
   unsigned long long fan = 0;
   for (uint64_t base = lo + warp * 4; base < hi; base += nwarps * 4) {
     const uint64_t t = base + gw;
@@ -150,6 +219,9 @@ __global__ void __launch_bounds__(kBlock) k_nem1_expand(NlcArgs a, uint64_t lo, 
       v = tk.x;
       s = tk.y;
       d = a.adeg[v];
+      // a path constraint needs ONE completed walk per source (ack_success just sets
+      // token_source_map[s] = 1, nem_1.hpp:326-342): later tokens of an acknowledged source are moot
+      if (FINAL && a.ok[s]) d = 0;
     }
     const uint64_t row = has ? (uint64_t)a.rowblk[v] * 8 : 0;
     const uint32_t passes = (d + GROUP * 4 - 1) / (GROUP * 4);
@@ -157,43 +229,53 @@ __global__ void __launch_bounds__(kBlock) k_nem1_expand(NlcArgs a, uint64_t lo, 
     for (uint32_t p = 0; p < maxp; ++p) {
       const uint32_t j0 = p * GROUP * 4 + gl * 4;
       uint4 q = make_uint4(0, 0, 0, 0);
-      if (j0 < d) q = *reinterpret_cast<const uint4*>(a.colw + row + j0);
+      uint32_t l4 = 0;
+      if (j0 < d) {
+        q = *reinterpret_cast<const uint4*>(a.colw + row + j0);
+        if (STREAM) l4 = *reinterpret_cast<const uint32_t*>(a.labw + row + j0);
+      }
       const uint32_t u[4] = {q.x & PM_IDMASK, q.y & PM_IDMASK, q.z & PM_IDMASK, q.w & PM_IDMASK};
       bool pass_static[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         pass_static[k] = false;
-        if (j0 + k < d) {
+        // the label test needs no gather when the neighbour's label travels with the edge
+        bool may = j0 + k < d;
+        if (STREAM) may = may && ((l4 >> (8 * k)) & 0xffu) == want_lab;
+        if (may) {
           const uint32_t su = a.S[u[k]];
-          pass_static[k] = su != 0 && hop_ok(su, a.cls[u[k]], hn);
+          pass_static[k] = su != 0 && ((su >> c_nlc.I[hn]) & 1u) && (STREAM || a.cls[u[k]] == c_nlc.cls[hn]);
         }
       }
+      if (FINAL) {
+        // max_itr_count == itr_count (nem_1.hpp:661-791)
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (FINAL) {
-          // max_itr_count == itr_count (nem_1.hpp:661-791)
+        for (int k = 0; k < 4; ++k) {
           const bool succ = pass_static[k] && (c_nlc.valid_cycle ? u[k] == s : u[k] != s);
           if (succ) {
             a.ok[s] = 1;
             a.cnt->found = 1u;
             if (c_nlc.valid_cycle) mark_edge(a, s, v);
           }
-        } else {
-          // interior hop: the source cannot relay (nem_1.hpp:174-177), one token per
-          // (vertex, source) (nem_1.hpp:131-139, 270-285)
-          bool ins = pass_static[k] && u[k] != s;
-          if (ins) ins = hset_insert(a, u[k], s);
-          const uint32_t b = __ballot_sync(0xffffffffu, ins);
-          if (b) {
-            unsigned long long pbase = 0;
-            if (lane == 0) pbase = atomicAdd(&a.cnt->pool_n, (unsigned long long)__popc(b));
-            pbase = __shfl_sync(0xffffffffu, pbase, 0);
-            if (ins) {
-              const unsigned long long pos = pbase + __popc(b & lanemask_lt());
-              if (pos < a.pool_cap) a.pool[pos] = make_uint2(u[k], s); else a.cnt->overflow = 1u;
-            }
-          }
         }
+      } else {
+        // interior hop: the source cannot relay (nem_1.hpp:174-177), one token per
+        // (vertex, source) (nem_1.hpp:131-139, 270-285)
+        bool ins[4];
+        uint32_t nins = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          ins[k] = pass_static[k] && u[k] != s;
+          if (ins[k]) ins[k] = hset_insert(a, u[k], s);
+          nins += ins[k];
+        }
+        unsigned long long pos = warp_reserve(&a.cnt->pool_n, nins);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (ins[k]) {
+            if (pos < a.pool_cap) a.pool[pos] = make_uint2(u[k], s); else a.cnt->overflow = 1u;
+            ++pos;
+          }
       }
     }
     if (has && gl == 0) fan += d;
@@ -219,8 +301,10 @@ __device__ __forceinline__ bool hist_rule(const uint32_t (&hist)[16], int hp, ui
   return false;               // "invalid value" branches drop the token
 }
 
-template <bool FINAL>
-__global__ void __launch_bounds__(kBlock) k_tds_expand(NlcArgs a, uint64_t lo, uint64_t hi, int hn) {
+template <bool FINAL, bool STREAM>
+__global__ void __launch_bounds__(kBlock) k_tds_expand(NlcArgs a, int hlevel, int hn) {
+  const uint32_t want_lab = c_nlc.lab[hn];
+  const uint64_t lo = a.cnt->lvl[hlevel], hi = a.cnt->lvl[hlevel + 1];
   constexpr int GROUP = 8;
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t gl = lane % GROUP, gw = lane / GROUP;
@@ -256,42 +340,47 @@ __global__ void __launch_bounds__(kBlock) k_tds_expand(NlcArgs a, uint64_t lo, u
     for (uint32_t p = 0; p < maxp; ++p) {
       const uint32_t j0 = p * GROUP * 4 + gl * 4;
       uint4 q = make_uint4(0, 0, 0, 0);
-      if (j0 < d) q = *reinterpret_cast<const uint4*>(a.colw + row + j0);
+      uint32_t l4 = 0;
+      if (j0 < d) {
+        q = *reinterpret_cast<const uint4*>(a.colw + row + j0);
+        if (STREAM) l4 = *reinterpret_cast<const uint32_t*>(a.labw + row + j0);
+      }
       const uint32_t u[4] = {q.x & PM_IDMASK, q.y & PM_IDMASK, q.z & PM_IDMASK, q.w & PM_IDMASK};
+      bool acc[4];
+      uint32_t nacc = 0;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        bool acc = false;
-        if (j0 + k < d) {
+        acc[k] = false;
+        bool may = j0 + k < d;
+        if (STREAM) may = may && ((l4 >> (8 * k)) & 0xffu) == want_lab;
+        if (may) {
           const uint32_t su = a.S[u[k]];
-          acc = su != 0 && hop_ok(su, a.cls[u[k]], hn);
-          if (acc) {
+          acc[k] = su != 0 && ((su >> c_nlc.I[hn]) & 1u) && (STREAM || a.cls[u[k]] == c_nlc.cls[hn]);
+          if (acc[k]) {
             if (FINAL)  // penultimate-hop filter of the sender (tds_batch_1.hpp:808-845)
-              acc = c_nlc.valid_cycle ? (u[k] == s) : (u[k] != s && hist_rule(hist, hn, u[k]));
+              acc[k] = c_nlc.valid_cycle ? (u[k] == s) : (u[k] != s && hist_rule(hist, hn, u[k]));
             else        // tds_batch_1.hpp:284-302 (receiver) == :846-886 (sender)
-              acc = hist_rule(hist, hn, u[k]);
+              acc[k] = hist_rule(hist, hn, u[k]);
           }
         }
-        const uint32_t b = __ballot_sync(0xffffffffu, acc);
-        if (b) {
-          unsigned long long pbase = 0;
-          if (lane == 0)
-            pbase = atomicAdd(FINAL ? &a.cnt->matches : &a.cnt->pool_n, (unsigned long long)__popc(b));
-          pbase = __shfl_sync(0xffffffffu, pbase, 0);
-          if (acc) {
-            const unsigned long long pos = pbase + __popc(b & lanemask_lt());
-            if (FINAL) {
-              // walk completed (tds_batch_1.hpp:664-694, 699-750)
-              a.ok[s] = 1;
-              a.cnt->found = 1u;
-              if (a.matches && pos < a.match_cap) a.matches[pos] = make_uint2((uint32_t)t, u[k]);
-            } else if (pos < a.pool_cap) {
-              a.pool[pos] = make_uint2((uint32_t)t, u[k]);
-            } else {
-              a.cnt->overflow = 1u;
-            }
-          }
-        }
+        nacc += acc[k];
       }
+      unsigned long long pos = warp_reserve(FINAL ? &a.cnt->matches : &a.cnt->pool_n, nacc);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (acc[k]) {
+          if (FINAL) {
+            // walk completed (tds_batch_1.hpp:664-694, 699-750)
+            a.ok[s] = 1;
+            a.cnt->found = 1u;
+            if (a.matches && pos < a.match_cap) a.matches[pos] = make_uint2((uint32_t)t, u[k]);
+          } else if (pos < a.pool_cap) {
+            a.pool[pos] = make_uint2((uint32_t)t, u[k]);
+          } else {
+            a.cnt->overflow = 1u;
+          }
+          ++pos;
+        }
     }
     if (has && gl == 0) fan += d;
   }

@@ -35,6 +35,7 @@ LccArgs lcc_args(pm_ctx* c, int row) {
   LccArgs a;
   a.rowblk = c->rowblk; a.deg = c->deg; a.col0 = c->col0; a.colw = c->colw;
   a.S = c->S; a.Tst = c->Tst; a.adeg = c->adeg; a.cls = c->cls; a.cnt = c->cnt;
+  a.lab0 = c->lab0; a.labw = c->labw;
   a.row = c->rowstat + row;
   a.bin = 0;
   return a;
@@ -42,7 +43,7 @@ LccArgs lcc_args(pm_ctx* c, int row) {
 
 NlcArgs nlc_args(pm_ctx* c, uint2* matches, uint64_t match_cap) {
   NlcArgs a;
-  a.rowblk = c->rowblk; a.colw = c->colw; a.S = c->S; a.adeg = c->adeg; a.cls = c->cls;
+  a.rowblk = c->rowblk; a.colw = c->colw; a.S = c->S; a.adeg = c->adeg; a.cls = c->cls; a.labw = c->labw;
   a.ok = c->ok; a.src_list = c->src_list; a.hset = c->hset; a.hset_mask = c->hset_cap - 1;
   a.pool = c->pool; a.pool_cap = c->pool_cap; a.matches = matches; a.match_cap = match_cap;
   a.cnt = c->cnt;
@@ -104,7 +105,7 @@ int pm_create(pm_ctx** out, int device) {
     delete c;
     return PM_ERR_CUDA;
   }
-  for (int b = 0; b < 3; ++b)
+  for (int b = 0; b < 4; ++b)
     for (int k = 0; k < 2; ++k)
       if (cudaEventCreate(&c->kev[b][k]) != cudaSuccess) { delete c; return PM_ERR_CUDA; }
   *out = c;
@@ -118,7 +119,7 @@ void pm_destroy(pm_ctx* c) {
   state_free(c);
   graph_free(c);
   for (auto e : c->events) cudaEventDestroy(e);
-  for (int b = 0; b < 3; ++b) for (int k = 0; k < 2; ++k) if (c->kev[b][k]) cudaEventDestroy(c->kev[b][k]);
+  for (int b = 0; b < 4; ++b) for (int k = 0; k < 2; ++k) if (c->kev[b][k]) cudaEventDestroy(c->kev[b][k]);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -167,7 +168,7 @@ int pm_graph_from_csr(pm_ctx* c, uint64_t n_vertices, const uint64_t* rowptr, co
 }
 
 int pm_get_kernel_stats(const pm_ctx* c, int bin, pm_kernel_stats_t* out) {
-  if (!c || !out || bin < 0 || bin > 2) return PM_ERR_ARG;
+  if (!c || !out || bin < 0 || bin > 3) return PM_ERR_ARG;
   *out = c->kstat[bin];
   return 0;
 }
@@ -221,7 +222,7 @@ int pm_labels_degree_log2(pm_ctx* c) {
   PM_LAUNCH_CHECK(c);
   c->has_labels = true;
   c->state_ready = false;
-  return 0;
+  return labels_derive(c, true);  // bit lengths of 32-bit degrees are <= 32
 }
 
 int pm_labels_set(pm_ctx* c, const uint64_t* labels) {
@@ -232,7 +233,9 @@ int pm_labels_set(pm_ctx* c, const uint64_t* labels) {
   PM_CUDA(c, cudaStreamSynchronize(c->stream));
   c->has_labels = true;
   c->state_ready = false;
-  return 0;
+  bool small = true;
+  for (uint64_t v = 0; v < c->V && small; ++v) small = labels[v] < 64;
+  return labels_derive(c, small);
 }
 
 int pm_labels_get(const pm_ctx* cc, uint64_t* out) {
@@ -259,6 +262,9 @@ int pm_pattern_load_dir(pm_ctx* c, const char* dir) {
     if (k == pc.ncls) pc.clabel[pc.ncls++] = p.vertex_label[i];
     pc.LMc[k] |= (uint16_t)(1u << i);
   }
+  for (int l = 0; l < 64; ++l) pc.cls_of_label[l] = PM_NOCLASS;
+  for (int k = 0; k < pc.ncls; ++k)
+    if (pc.clabel[k] < 64) pc.cls_of_label[pc.clabel[k]] = (uint8_t)k;
   c->pat = p;
   c->pc = pc;
   c->has_pattern = true;
@@ -310,10 +316,19 @@ int pm_state_reset(pm_ctx* c) {
   PM_CUDA(c, cudaMemcpyToSymbolAsync(c_pat, &c->pc, sizeof(PatConst), 0, cudaMemcpyHostToDevice, c->stream));
   PM_CUDA(c, cudaMemsetAsync(c->cnt, 0, sizeof(DevCounters), c->stream));
   c->cur = 0;
-  k_init_state<<<grid_for(), kBlock, 0, c->stream>>>(c->label, c->deg, V, c->cls, c->S, c->Tst, c->adeg,
-                                                     c->fr[0][0], c->fr[0][1], c->fr[0][2], c->cnt, 0);
+  if (c->labels_small)
+    k_init_state<true><<<grid_for(), kBlock, 0, c->stream>>>(c->label, c->lab8, c->deg, V, c->cls, c->S, c->fr[0][0],
+                                                            c->fr[0][1], c->fr[0][2], c->cnt, 0);
+  else
+    k_init_state<false><<<grid_for(), kBlock, 0, c->stream>>>(c->label, c->lab8, c->deg, V, c->cls, c->S, c->fr[0][0],
+                                                             c->fr[0][1], c->fr[0][2], c->cnt, 0);
   PM_LAUNCH_CHECK(c);
-  PM_CUDA(c, cudaStreamSynchronize(c->stream));
+  {
+    int rc2 = sync_counters(c);
+    if (rc2) return rc2;
+    bool any = false;
+    for (int b = 2; b >= 0; --b) { any = any || c->h_cnt->fr_n[0][b] != 0; c->bin_live[b] = any; }
+  }
   c->rows.clear();
   c->step_rows.clear();
   c->iter_seconds.clear();
@@ -332,49 +347,64 @@ int pm_lcc(pm_ctx* c, int init_step, int* not_finished, pm_counts_t* counts_out)
   cudaStream_t st = c->stream;
   const int D = c->pat.diameter;
   const int grid = grid_for();
+  const bool sm = c->labels_small;  // neighbour labels are streamed next to the ids
   const double t0 = wall_s();
   PM_CUDA(c, cudaMemsetAsync(c->rowstat, 0, D * sizeof(RowStat), st));
   PM_CUDA(c, cudaMemsetAsync(&c->cnt->nf, 0, sizeof(uint32_t), st));
   for (int k = 0; k < D; ++k) {  // fixed superstep count (ee.hpp:1069)
     const bool first = init_step && k == 0;
-    const int cur = c->cur, nxt = cur ^ 1;
     PM_CUDA(c, cudaEventRecord(c->events[k], st));
-    PM_CUDA(c, cudaMemsetAsync(&c->cnt->fr_n[nxt][0], 0, 4 * sizeof(uint32_t), st));
+    PM_CUDA(c, cudaMemsetAsync(&c->cnt->fr_n[c->cur ^ 1][0], 0, 4 * sizeof(uint32_t), st));
     LccArgs a = lcc_args(c, k), a1 = a, a2 = a;
     a1.bin = 1;
     a2.bin = 2;
     if (first) {
+      int cur = c->cur, nxt = cur ^ 1;
+      if (c->labels_small) {
+        // settle most candidates from their neighbour-label signature; survivors move to the other buffer
+        PM_CUDA(c, cudaEventRecord(c->kev[3][0], st));
+        k_lcc_first_filter<<<grid, kBlock, 0, st>>>(a, c->sig, c->fr[cur][0], c->fr[cur][1], c->fr[cur][2],
+                                                    c->fr[nxt][0], c->fr[nxt][1], c->fr[nxt][2], cur, nxt);
+        PM_LAUNCH_CHECK(c);
+        PM_CUDA(c, cudaEventRecord(c->kev[3][1], st));
+        c->cur = nxt;
+        cur = nxt;
+        nxt = cur ^ 1;
+        PM_CUDA(c, cudaMemsetAsync(&c->cnt->fr_n[nxt][0], 0, 4 * sizeof(uint32_t), st));
+      }
       // the kernels that walk the pristine adjacency are timed with CUDA events on this stream
       PM_CUDA(c, cudaEventRecord(c->kev[0][0], st));
-      k_lcc_scan<8, true><<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], &c->cnt->fr_n[cur][0]);
-      PM_LAUNCH_CHECK(c);
+      if (c->bin_live[0]) { (sm ? k_lcc_scan<8, true, true> : k_lcc_scan<8, true, false>)<<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], &c->cnt->fr_n[cur][0]); PM_LAUNCH_CHECK(c); }
       PM_CUDA(c, cudaEventRecord(c->kev[0][1], st));
       PM_CUDA(c, cudaEventRecord(c->kev[1][0], st));
-      k_lcc_scan<32, true><<<grid, kBlock, 0, st>>>(a1, c->fr[cur][1], &c->cnt->fr_n[cur][1]);
-      PM_LAUNCH_CHECK(c);
+      if (c->bin_live[1]) { (sm ? k_lcc_scan<32, true, true> : k_lcc_scan<32, true, false>)<<<grid, kBlock, 0, st>>>(a1, c->fr[cur][1], &c->cnt->fr_n[cur][1]); PM_LAUNCH_CHECK(c); }
       PM_CUDA(c, cudaEventRecord(c->kev[1][1], st));
       PM_CUDA(c, cudaEventRecord(c->kev[2][0], st));
-      k_lcc_scan_big<true><<<148, 1024, 0, st>>>(a2, c->fr[cur][2], &c->cnt->fr_n[cur][2]);
-      PM_LAUNCH_CHECK(c);
+      if (c->bin_live[2]) { (sm ? k_lcc_scan_big<true, true> : k_lcc_scan_big<true, false>)<<<148, 1024, 0, st>>>(a2, c->fr[cur][2], &c->cnt->fr_n[cur][2]); PM_LAUNCH_CHECK(c); }
       PM_CUDA(c, cudaEventRecord(c->kev[2][1], st));
     } else {
-      k_lcc_scan<8, false><<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], &c->cnt->fr_n[cur][0]);
-      PM_LAUNCH_CHECK(c);
-      k_lcc_scan<32, false><<<grid, kBlock, 0, st>>>(a1, c->fr[cur][1], &c->cnt->fr_n[cur][1]);
-      PM_LAUNCH_CHECK(c);
-      k_lcc_scan_big<false><<<148, 1024, 0, st>>>(a2, c->fr[cur][2], &c->cnt->fr_n[cur][2]);
-      PM_LAUNCH_CHECK(c);
+      const int cur = c->cur;
+      if (c->bin_live[0]) { (sm ? k_lcc_scan<8, false, true> : k_lcc_scan<8, false, false>)<<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], &c->cnt->fr_n[cur][0]); PM_LAUNCH_CHECK(c); }
+      if (c->bin_live[1]) { (sm ? k_lcc_scan<32, false, true> : k_lcc_scan<32, false, false>)<<<grid, kBlock, 0, st>>>(a1, c->fr[cur][1], &c->cnt->fr_n[cur][1]); PM_LAUNCH_CHECK(c); }
+      if (c->bin_live[2]) { (sm ? k_lcc_scan_big<false, true> : k_lcc_scan_big<false, false>)<<<148, 1024, 0, st>>>(a2, c->fr[cur][2], &c->cnt->fr_n[cur][2]); PM_LAUNCH_CHECK(c); }
     }
-    k_lcc_commit<<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], c->fr[cur][1], c->fr[cur][2], c->fr[nxt][0],
-                                          c->fr[nxt][1], c->fr[nxt][2], cur, nxt);
-    PM_LAUNCH_CHECK(c);
-    c->cur = nxt;
+    {
+      const int cur = c->cur, nxt = cur ^ 1;
+      k_lcc_commit<<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], c->fr[cur][1], c->fr[cur][2], c->fr[nxt][0],
+                                            c->fr[nxt][1], c->fr[nxt][2], cur, nxt);
+      PM_LAUNCH_CHECK(c);
+      c->cur = nxt;
+    }
   }
   PM_CUDA(c, cudaEventRecord(c->events[D], st));
   PM_CUDA(c, cudaMemcpyAsync(c->h_rowstat, c->rowstat, D * sizeof(RowStat), cudaMemcpyDeviceToHost, st));
   int rc = sync_counters(c);
   if (rc) return rc;
   if (c->h_cnt->nf && not_finished) *not_finished = 1;
+  {
+    bool any = false;
+    for (int b = 2; b >= 0; --b) { any = any || c->h_cnt->fr_n[c->cur][b] != 0; c->bin_live[b] = any; }
+  }
   for (int k = 0; k < D; ++k) {
     float ms = 0;
     PM_CUDA(c, cudaEventElapsedTime(&ms, c->events[k], c->events[k + 1]));
@@ -396,6 +426,15 @@ int pm_lcc(pm_ctx* c, int init_step, int* not_finished, pm_counts_t* counts_out)
         c->kstat[b].ms += kms;
         c->kstat[b].slots += rs.scanned[b];
         c->kstat[b].vertices += rs.verts[b];
+      }
+      if (c->labels_small) {
+        float kms = 0;
+        PM_CUDA(c, cudaEventElapsedTime(&kms, c->kev[3][0], c->kev[3][1]));
+        c->kstat[3].launches++;
+        c->kstat[3].ms += kms;
+        c->kstat[3].vertices += rs.filtered;
+        // signature filter: 8 B signature + 2 B mask + 4 B list entry per candidate
+        c->summary.algorithmic_bytes += rs.filtered * 14;
       }
     }
     // SURVEY §8(d) byte model: 4 B column + 2 B neighbour mask per scanned slot;
@@ -433,17 +472,23 @@ int pm_nlcc(pm_ctx* c, int pl, int mode, int* pattern_found, int* token_source_d
     nc.cls[h] = (uint8_t)cl;
     nc.I[h] = (uint8_t)k.I[h];
     nc.e[h] = (uint8_t)(tds ? std::min<uint32_t>(k.enum_idx[h], 255u) : h);
+    nc.lab[h] = (uint8_t)(k.P[h] < 64 ? k.P[h] : 255);
   }
   const int grid = grid_for();
   const int D = c->pat.diameter;  // rowstat[D] is the TP row accumulator
   PM_CUDA(c, cudaEventRecord(c->events[0], st));
   PM_CUDA(c, cudaMemcpyToSymbolAsync(c_nlc, &nc, sizeof(NlcConst), 0, cudaMemcpyHostToDevice, st));
   int rc;
-  if ((rc = nlcc_reserve(c, std::max<uint64_t>(c->V, 1ull << 20)))) return rc;
+  {
+    // tokens of one hop are bounded by the walked slots of the previous one; start from the
+    // size of the current edge maps and grow (retrying the constraint) if that is not enough
+    const uint64_t ne = c->rows.empty() ? c->E : c->rows.back().n_edges;
+    if ((rc = nlcc_reserve(c, std::max<uint64_t>(4 * ne + (1ull << 16), 1ull << 20)))) return rc;
+  }
   uint2* d_matches = nullptr;
   uint64_t match_cap = 0;
   const int cur = c->cur;
-  uint64_t n_matches = 0, lo = 0, hi = 0;
+  uint64_t n_matches = 0, hi = 0;
   for (int attempt = 0;; ++attempt) {
     if (tds && c->keep_subgraphs) {
       match_cap = c->pool_cap;
@@ -456,31 +501,32 @@ int pm_nlcc(pm_ctx* c, int pl, int mode, int* pattern_found, int* token_source_d
     NlcArgs a = nlc_args(c, d_matches, match_cap);
     k_nlcc_sources<<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], c->fr[cur][1], c->fr[cur][2], cur, tds ? 1 : 0);
     PM_LAUNCH_CHECK(c);
-    if ((rc = sync_counters(c))) { dev_free(d_matches); return rc; }
-    lo = 0;
-    hi = c->h_cnt->n_src;
-    unsigned long long pn = hi;
-    PM_CUDA(c, cudaMemcpyAsync(&c->cnt->pool_n, &pn, sizeof(pn), cudaMemcpyHostToDevice, st));
-    bool overflow = false;
-    for (int hn = 1; hn <= (int)k.C + 1 && hi > lo; ++hn) {
+    k_nlcc_begin<<<1, 1, 0, st>>>(c->cnt);
+    PM_LAUNCH_CHECK(c);
+    for (int hn = 1; hn <= (int)k.C + 1; ++hn) {
       const bool fin = hn == (int)k.C + 1;
+      const int lvl = hn - 1;
+      const bool sm = c->labels_small;
       if (tds) {
-        if (fin) k_tds_expand<true><<<grid, kBlock, 0, st>>>(a, lo, hi, hn);
-        else k_tds_expand<false><<<grid, kBlock, 0, st>>>(a, lo, hi, hn);
+        if (fin) (sm ? k_tds_expand<true, true> : k_tds_expand<true, false>)<<<grid, kBlock, 0, st>>>(a, lvl, hn);
+        else (sm ? k_tds_expand<false, true> : k_tds_expand<false, false>)<<<grid, kBlock, 0, st>>>(a, lvl, hn);
+      } else if (fin) {
+        if (k.valid_cycle) k_nem1_final_cycle<<<grid, kBlock, 0, st>>>(a, lvl, hn);
+        else (sm ? k_nem1_expand<true, true> : k_nem1_expand<true, false>)<<<grid, kBlock, 0, st>>>(a, lvl, hn);
       } else {
-        if (fin) k_nem1_expand<true><<<grid, kBlock, 0, st>>>(a, lo, hi, hn);
-        else k_nem1_expand<false><<<grid, kBlock, 0, st>>>(a, lo, hi, hn);
+        (sm ? k_nem1_expand<false, true> : k_nem1_expand<false, false>)<<<grid, kBlock, 0, st>>>(a, lvl, hn);
       }
       PM_LAUNCH_CHECK(c);
-      if ((rc = sync_counters(c))) { dev_free(d_matches); return rc; }
-      // the pool / hash set ran out, or more walks completed than the match list holds
-      if (c->h_cnt->overflow || (tds && fin && c->keep_subgraphs && c->h_cnt->matches > match_cap)) {
-        overflow = true;
-        break;
+      if (!fin) {
+        k_nlcc_close_level<<<1, 1, 0, st>>>(c->cnt, hn, c->pool_cap);
+        PM_LAUNCH_CHECK(c);
       }
-      lo = hi;
-      hi = c->h_cnt->pool_n;
     }
+    if ((rc = sync_counters(c))) { dev_free(d_matches); return rc; }
+    hi = c->h_cnt->pool_n;
+    // the pool / hash set ran out, or more walks completed than the match list holds
+    const bool overflow = c->h_cnt->overflow || c->h_cnt->pool_n > c->pool_cap ||
+                          (tds && c->keep_subgraphs && c->h_cnt->matches > match_cap);
     if (!overflow) { n_matches = c->h_cnt->matches; break; }
     if (attempt >= 6) { dev_free(d_matches); return fail(c, PM_ERR_CAPACITY, "NLCC token pool exhausted"); }
     const uint64_t want = std::max<uint64_t>(c->pool_cap * 4, (uint64_t)c->h_cnt->matches + 1);

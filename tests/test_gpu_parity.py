@@ -204,3 +204,19 @@ def test_cli_writes_the_reference_result_tree(oracle, tmp_path):
     a = open(os.path.join(out_gpu, "result_pattern_set")).read().split(",")
     b = open(os.path.join(out_ref, "result_pattern_set")).read().split(",")
     assert [x.strip() for x in a[:3] + a[4:]] == [x.strip() for x in b[:3] + b[4:]]
+
+
+def test_large_label_values_take_the_gather_path(oracle, eng):
+    """labels >= 64 (e.g. string hashes, VertexData = uint64_t in beta.cpp:263) disable the byte-label
+    streams and the signature filter; the class-gather kernels must give the same answers."""
+    import copy
+    from fuzzypatternmatching_b200 import patterns as PT
+    off = 1000003
+    for base_spec, labelset, tds_from in ((PT.RMAT_LOG2_TREE, [2, 3, 4, 5, 7], 4), (PT.cycle4(1, 2, 3, 4), [1, 2, 3, 4], 1)):
+        spec = copy.deepcopy(base_spec)
+        spec["labels"] = [l + off for l in spec["labels"]]
+        for seed in range(4):
+            n, m = 300, 1500
+            edges = cases.random_multigraph(seed + 40, n, m)
+            labels = cases.random_labels(seed + 40, n, labelset) + np.uint64(off)
+            _compare(oracle, eng, n, edges, labels, spec, tds_from)

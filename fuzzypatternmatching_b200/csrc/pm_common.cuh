@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <map>
 #include <string>
 #include <vector>
 
@@ -43,12 +44,13 @@ struct NlcConst {      // one non-local constraint (walk)
 
 struct DevCounters {
   uint32_t fr_n[2][4];          // frontier sizes [buffer][bin]; [.][3] unused
+  unsigned long long filtered_init;  // candidates tested by the fused init filter
   uint32_t nf;                  // a vertex left the vertex_state_map in this LCC call
   uint32_t found;               // NLCC: a walk completed
   uint32_t deleted;             // NLCC: a source failed
   uint32_t overflow;            // NLCC: token pool / hash set exhausted
   uint32_t n_src;               // NLCC: number of sources
-  uint32_t pad0;
+  uint32_t nf_init;             // the fused init filter removed a vertex that had entered the map
   unsigned long long pool_n;    // NLCC: tokens in the pool
   unsigned long long matches;   // TDS: completed walks
   unsigned long long fanout;    // NLCC: adjacency slots walked by tokens
@@ -99,7 +101,10 @@ struct pm_ctx {
   uint8_t* cls = nullptr;   // [V] label class (index into the template's distinct labels, PM_NOCLASS = none)
   uint32_t* fr[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};  // frontier lists by bin
   int cur = 0;              // which frontier buffer is current
-  bool bin_live[3] = {true, true, true};  // bin b or a larger one was non-empty at the last host sync
+  bool bin_live[3] = {true, true, true};
+  bool filter_done = false;     // the fused init filter ran: the first superstep skips its own filter
+  float init_ms = 0;            // its device time (accounted to LP superstep 0)
+  uint64_t init_candidates = 0;  // bin b or a larger one was non-empty at the last host sync
   pm::DevCounters* cnt = nullptr;      // device
   pm::DevCounters* h_cnt = nullptr;    // pinned host mirror
   pm::RowStat* rowstat = nullptr;      // device, [diameter + 1]
@@ -111,6 +116,10 @@ struct pm_ctx {
   uint32_t* src_list = nullptr;     // [V] sources of the current constraint
   unsigned long long* hset = nullptr;  // (vertex, source) set, open addressing
   uint64_t hset_cap = 0;
+  uint64_t hset_use = 0;            // power-of-two part of the table the current constraint uses
+  std::vector<uint64_t> pool_seen;  // per constraint: most tokens ever stored (sizes the next run's table)
+  std::string pat_key;              // pattern directory the sizes belong to
+  std::map<std::string, std::vector<uint64_t>> pool_cache;
   uint2* pool = nullptr;            // token pool: nem_1 (vertex, source); TDS (parent index, vertex)
   uint64_t pool_cap = 0;
   uint32_t* match_rows = nullptr;   // TDS: materialised walks of the last run of each constraint

@@ -171,6 +171,69 @@ __global__ void __launch_bounds__(kBlock) k_init_state(const uint64_t* __restric
 }
 
 // ---------------------------------------------------------------------------
+// fused per-pattern initialisation + first-superstep signature filter (labels < 64).
+// One streaming pass over all vertices: class from the byte label, candidate test,
+// then — for candidates — the signature test documented at k_lcc_first_filter below.
+// Writes cls[v] and S[v] for EVERY vertex with coalesced stores (S = 0 unless the
+// vertex survives the first superstep's cover test) and appends the survivors to the
+// frontier bin of their degree.  Their rows are walked by the first scan afterwards.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_init_filter(const uint8_t* __restrict__ lab8,
+                                                         const uint32_t* __restrict__ deg,
+                                                         const unsigned long long* __restrict__ sig, uint64_t V,
+                                                         uint8_t* __restrict__ cls, uint16_t* __restrict__ S,
+                                                         uint32_t* fr_small, uint32_t* fr_mid, uint32_t* fr_big,
+                                                         DevCounters* cnt, int buf) {
+  __shared__ uint8_t s_cl[64];
+  __shared__ uint16_t s_lm[17];
+  if (threadIdx.x < 64) s_cl[threadIdx.x] = c_pat.cls_of_label[threadIdx.x];
+  if (threadIdx.x < 17) s_lm[threadIdx.x] = c_pat.LMc[threadIdx.x];
+  __syncthreads();
+  constexpr int IT = 8;
+  const uint64_t tile = (uint64_t)blockDim.x * IT;
+  unsigned long long ncand = 0;
+  bool any_removed = false;
+  for (uint64_t base = (uint64_t)blockIdx.x * tile; base < V; base += (uint64_t)gridDim.x * tile) {
+    bool keep[IT];
+    int bin[IT];
+    uint32_t val[IT];
+#pragma unroll
+    for (int k = 0; k < IT; ++k) {
+      const uint64_t v = base + (uint64_t)k * blockDim.x + threadIdx.x;
+      keep[k] = false;
+      uint32_t d = 0;
+      if (v < V) {
+        const uint32_t c = s_cl[lab8[v] & 63];
+        d = deg[v];
+        const uint32_t lm = d ? (uint32_t)s_lm[c] : 0u;
+        if (lm) {
+          const unsigned long long sg = sig[v];
+          const uint32_t NBv = nb_of(lm);
+          uint32_t heard = 0;
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const uint32_t lq = c_pat.LMc[q];
+            if (q < c_pat.ncls && ((sg >> (c_pat.clabel[q] & 63)) & 1ull) && (lq & NBv)) heard |= lq;
+          }
+          keep[k] = cover_of(lm, heard) != 0;
+          any_removed = any_removed || (!keep[k] && heard != 0);  // entered the map and left it (ee.hpp:941-946)
+          ncand++;
+        }
+        cls[v] = (uint8_t)c;
+        S[v] = keep[k] ? (uint16_t)lm : (uint16_t)0;
+      }
+      bin[k] = d <= PM_SMALL_MAX ? 0 : (d <= PM_MID_MAX ? 1 : 2);
+      val[k] = (uint32_t)v;
+    }
+    block_bin_append<IT>(keep, bin, val, fr_small, fr_mid, fr_big, &cnt->fr_n[buf][0]);
+  }
+  if (any_removed) cnt->nf_init = 1u;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ncand += __shfl_xor_sync(0xffffffffu, ncand, o);
+  if ((threadIdx.x & 31) == 0 && ncand) atomicAdd(&cnt->filtered_init, ncand);
+}
+
+// ---------------------------------------------------------------------------
 // first-superstep signature filter.  In the first superstep every neighbour u of
 // v sends labelmask(label[u]) (ee.hpp:519-561), so heard(v) depends only on WHICH
 // labels occur among v's neighbours: heard(v) = OR { LM(l) : l in sig[v],

@@ -44,7 +44,7 @@ LccArgs lcc_args(pm_ctx* c, int row) {
 NlcArgs nlc_args(pm_ctx* c, uint2* matches, uint64_t match_cap) {
   NlcArgs a;
   a.rowblk = c->rowblk; a.colw = c->colw; a.S = c->S; a.adeg = c->adeg; a.cls = c->cls; a.labw = c->labw;
-  a.ok = c->ok; a.src_list = c->src_list; a.hset = c->hset; a.hset_mask = c->hset_cap - 1;
+  a.ok = c->ok; a.src_list = c->src_list; a.hset = c->hset; a.hset_mask = c->hset_use - 1;
   a.pool = c->pool; a.pool_cap = c->pool_cap; a.matches = matches; a.match_cap = match_cap;
   a.cnt = c->cnt;
   return a;
@@ -269,6 +269,12 @@ int pm_pattern_load_dir(pm_ctx* c, const char* dir) {
   c->pc = pc;
   c->has_pattern = true;
   c->state_ready = false;
+  c->pat_key = dir;
+  {
+    auto it = c->pool_cache.find(c->pat_key);
+    if (it != c->pool_cache.end() && it->second.size() == p.constraints.size()) c->pool_seen = it->second;
+    else c->pool_seen.assign(p.constraints.size(), 0);
+  }
   c->subgraphs.assign(p.constraints.size(), {});
   c->subgraph_width.assign(p.constraints.size(), 0);
   c->subgraph_count.assign(p.constraints.size(), 0);
@@ -316,10 +322,15 @@ int pm_state_reset(pm_ctx* c) {
   PM_CUDA(c, cudaMemcpyToSymbolAsync(c_pat, &c->pc, sizeof(PatConst), 0, cudaMemcpyHostToDevice, c->stream));
   PM_CUDA(c, cudaMemsetAsync(c->cnt, 0, sizeof(DevCounters), c->stream));
   c->cur = 0;
-  if (c->labels_small)
-    k_init_state<true><<<grid_for(), kBlock, 0, c->stream>>>(c->label, c->lab8, c->deg, V, c->cls, c->S, c->fr[0][0],
-                                                            c->fr[0][1], c->fr[0][2], c->cnt, 0);
-  else
+  c->filter_done = false;
+  if (c->labels_small) {
+    // init and the signature filter of the first superstep in one streaming pass
+    PM_CUDA(c, cudaEventRecord(c->kev[3][0], c->stream));
+    k_init_filter<<<grid_for(), kBlock, 0, c->stream>>>(c->lab8, c->deg, c->sig, V, c->cls, c->S, c->fr[0][0],
+                                                        c->fr[0][1], c->fr[0][2], c->cnt, 0);
+    PM_CUDA(c, cudaEventRecord(c->kev[3][1], c->stream));
+    c->filter_done = true;
+  } else
     k_init_state<false><<<grid_for(), kBlock, 0, c->stream>>>(c->label, c->lab8, c->deg, V, c->cls, c->S, c->fr[0][0],
                                                              c->fr[0][1], c->fr[0][2], c->cnt, 0);
   PM_LAUNCH_CHECK(c);
@@ -328,6 +339,9 @@ int pm_state_reset(pm_ctx* c) {
     if (rc2) return rc2;
     bool any = false;
     for (int b = 2; b >= 0; --b) { any = any || c->h_cnt->fr_n[0][b] != 0; c->bin_live[b] = any; }
+    c->init_ms = 0;
+    c->init_candidates = c->h_cnt->filtered_init;
+    if (c->filter_done) PM_CUDA(c, cudaEventElapsedTime(&c->init_ms, c->kev[3][0], c->kev[3][1]));
   }
   c->rows.clear();
   c->step_rows.clear();
@@ -360,7 +374,7 @@ int pm_lcc(pm_ctx* c, int init_step, int* not_finished, pm_counts_t* counts_out)
     a2.bin = 2;
     if (first) {
       int cur = c->cur, nxt = cur ^ 1;
-      if (c->labels_small) {
+      if (c->labels_small && !c->filter_done) {
         // settle most candidates from their neighbour-label signature; survivors move to the other buffer
         PM_CUDA(c, cudaEventRecord(c->kev[3][0], st));
         k_lcc_first_filter<<<grid, kBlock, 0, st>>>(a, c->sig, c->fr[cur][0], c->fr[cur][1], c->fr[cur][2],
@@ -400,7 +414,7 @@ int pm_lcc(pm_ctx* c, int init_step, int* not_finished, pm_counts_t* counts_out)
   PM_CUDA(c, cudaMemcpyAsync(c->h_rowstat, c->rowstat, D * sizeof(RowStat), cudaMemcpyDeviceToHost, st));
   int rc = sync_counters(c);
   if (rc) return rc;
-  if (c->h_cnt->nf && not_finished) *not_finished = 1;
+  if ((c->h_cnt->nf || (init_step && c->filter_done && c->h_cnt->nf_init)) && not_finished) *not_finished = 1;
   {
     bool any = false;
     for (int b = 2; b >= 0; --b) { any = any || c->h_cnt->fr_n[c->cur][b] != 0; c->bin_live[b] = any; }
@@ -428,13 +442,20 @@ int pm_lcc(pm_ctx* c, int init_step, int* not_finished, pm_counts_t* counts_out)
         c->kstat[b].vertices += rs.verts[b];
       }
       if (c->labels_small) {
-        float kms = 0;
-        PM_CUDA(c, cudaEventElapsedTime(&kms, c->kev[3][0], c->kev[3][1]));
+        float kms = c->init_ms;
+        uint64_t nfil = c->init_candidates;
+        if (!c->filter_done) {
+          PM_CUDA(c, cudaEventElapsedTime(&kms, c->kev[3][0], c->kev[3][1]));
+          nfil = rs.filtered;
+        } else {
+          c->rows[c->rows.size() - 1].seconds += kms * 1e-3;  // the fused filter is part of superstep 0
+          c->summary.device_seconds += kms * 1e-3;
+        }
         c->kstat[3].launches++;
         c->kstat[3].ms += kms;
-        c->kstat[3].vertices += rs.filtered;
+        c->kstat[3].vertices += nfil;
         // signature filter: 8 B signature + 2 B mask + 4 B list entry per candidate
-        c->summary.algorithmic_bytes += rs.filtered * 14;
+        c->summary.algorithmic_bytes += nfil * 14;
       }
     }
     // SURVEY §8(d) byte model: 4 B column + 2 B neighbour mask per scanned slot;
@@ -479,12 +500,19 @@ int pm_nlcc(pm_ctx* c, int pl, int mode, int* pattern_found, int* token_source_d
   PM_CUDA(c, cudaEventRecord(c->events[0], st));
   PM_CUDA(c, cudaMemcpyToSymbolAsync(c_nlc, &nc, sizeof(NlcConst), 0, cudaMemcpyHostToDevice, st));
   int rc;
-  {
-    // tokens of one hop are bounded by the walked slots of the previous one; start from the
-    // size of the current edge maps and grow (retrying the constraint) if that is not enough
-    const uint64_t ne = c->rows.empty() ? c->E : c->rows.back().n_edges;
-    if ((rc = nlcc_reserve(c, std::max<uint64_t>(4 * ne + (1ull << 16), 1ull << 20)))) return rc;
-  }
+  // Size the (vertex, source) set for what this constraint stored last time (or for the current
+  // edge maps on its first run); an undersized table is detected and the constraint retried.
+  if (c->pool_seen.size() != c->pat.constraints.size()) c->pool_seen.assign(c->pat.constraints.size(), 0);
+  const uint64_t ne_now = c->rows.empty() ? c->E : c->rows.back().n_edges;
+  uint64_t want_pool = c->pool_seen[pl] ? c->pool_seen[pl] + c->pool_seen[pl] / 2 + 4096 : 2 * ne_now + 65536;
+  want_pool = std::max<uint64_t>(want_pool, 1ull << 18);
+  if ((rc = nlcc_reserve(c, want_pool))) return rc;
+  auto pick_table = [&]() {
+    uint64_t use = 1;
+    while (use < 2 * want_pool) use <<= 1;
+    c->hset_use = std::min(use, c->hset_cap);
+  };
+  pick_table();
   uint2* d_matches = nullptr;
   uint64_t match_cap = 0;
   const int cur = c->cur;
@@ -497,7 +525,7 @@ int pm_nlcc(pm_ctx* c, int pl, int mode, int* pattern_found, int* token_source_d
     }
     // zero found .. hash_n, keep the frontier counters and nf
     PM_CUDA(c, cudaMemsetAsync(&c->cnt->found, 0, sizeof(DevCounters) - offsetof(DevCounters, found), st));
-    if (!tds) PM_CUDA(c, cudaMemsetAsync(c->hset, 0xFF, c->hset_cap * sizeof(unsigned long long), st));
+    if (!tds) PM_CUDA(c, cudaMemsetAsync(c->hset, 0xFF, c->hset_use * sizeof(unsigned long long), st));
     NlcArgs a = nlc_args(c, d_matches, match_cap);
     k_nlcc_sources<<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], c->fr[cur][1], c->fr[cur][2], cur, tds ? 1 : 0);
     PM_LAUNCH_CHECK(c);
@@ -527,10 +555,16 @@ int pm_nlcc(pm_ctx* c, int pl, int mode, int* pattern_found, int* token_source_d
     // the pool / hash set ran out, or more walks completed than the match list holds
     const bool overflow = c->h_cnt->overflow || c->h_cnt->pool_n > c->pool_cap ||
                           (tds && c->keep_subgraphs && c->h_cnt->matches > match_cap);
-    if (!overflow) { n_matches = c->h_cnt->matches; break; }
+    if (!overflow) {
+      n_matches = c->h_cnt->matches;
+      c->pool_seen[pl] = std::max<uint64_t>(c->pool_seen[pl], c->h_cnt->pool_n);
+      c->pool_cache[c->pat_key] = c->pool_seen;
+      break;
+    }
     if (attempt >= 6) { dev_free(d_matches); return fail(c, PM_ERR_CAPACITY, "NLCC token pool exhausted"); }
-    const uint64_t want = std::max<uint64_t>(c->pool_cap * 4, (uint64_t)c->h_cnt->matches + 1);
-    if ((rc = nlcc_reserve(c, want))) { dev_free(d_matches); return rc; }
+    want_pool = std::max<uint64_t>(want_pool * 4, (uint64_t)c->h_cnt->matches + 1);
+    if ((rc = nlcc_reserve(c, want_pool))) { dev_free(d_matches); return rc; }
+    pick_table();
   }
   const uint64_t fanout = c->h_cnt->fanout;
   const int found = c->h_cnt->found;

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <map>
@@ -568,6 +569,13 @@ int pm_nlcc(pm_ctx* c, int pl, int mode, int* pattern_found, int* token_source_d
   }
   const uint64_t fanout = c->h_cnt->fanout;
   const int found = c->h_cnt->found;
+  if (getenv("PM_DEBUG")) {
+    fprintf(stderr, "[pm] nlcc pl=%d %s n_src=%u fanout=%llu pool_n=%llu table=%llu levels:", pl, tds ? "tds" : "nem1",
+            c->h_cnt->n_src, (unsigned long long)fanout, (unsigned long long)c->h_cnt->pool_n,
+            (unsigned long long)c->hset_use);
+    for (int h = 0; h <= (int)k.C + 1; ++h) fprintf(stderr, " %llu", (unsigned long long)c->h_cnt->lvl[h]);
+    fprintf(stderr, "\n");
+  }
   // post-processing of token_source_map (beta.cpp:956-1062) and the TP row (beta.cpp:1094-1120)
   k_nlcc_apply<<<grid, kBlock, 0, st>>>(c->S, c->ok, c->src_list, c->cnt);
   PM_LAUNCH_CHECK(c);

@@ -142,6 +142,10 @@ class Engine:
         return [(int(r.itr), "LP" if r.kind == 0 else "TP", int(r.index), int(r.n_vertices), int(r.n_edges))
                 for r in buf[:n]]
 
+    def rows_timed(self):
+        """rows() with the device milliseconds of each row appended"""
+        return [r + (round(t * 1e3, 3),) for r, t in zip(self.rows(), self.row_seconds())]
+
     def row_seconds(self):
         n = int(self.summary["n_rows"])
         buf = (_lib.Row * max(n, 1))()

@@ -24,6 +24,9 @@ for s in scales:
             name, dt * 1e3, sm["device_seconds"] * 1e3, sm["iterations"], len(rows), rows[-1][3:], sm["path_count"],
             sm["edges_processed"], eng.kernel_launches()), flush=True)
         print("     first rows", [(r[1], r[2], r[3], r[4]) for r in rows[:4]], flush=True)
+        if os.environ.get("PM_ROWS"):
+            for r in eng.rows_timed():
+                print("       %s" % (r,), flush=True)
         if check:
             t = time.time(); ref = O.Run(g, lab, O.Pattern(d), tds_from_pl=tds, keep_subgraphs=False)
             print("     oracle %.2fs rows_equal %s hazards %s" % (time.time() - t, ref.rows == rows, ref.hazards[:5]), flush=True)

@@ -51,6 +51,8 @@ struct DevCounters {
   uint32_t overflow;            // NLCC: token pool / hash set exhausted
   uint32_t n_src;               // NLCC: number of sources
   uint32_t nf_init;             // the fused init filter removed a vertex that had entered the map
+  uint32_t match_drop;          // TDS: a completed walk did not fit the match list
+  uint32_t pad1;
   unsigned long long pool_n;    // NLCC: tokens in the pool
   unsigned long long matches;   // TDS: completed walks
   unsigned long long fanout;    // NLCC: adjacency slots walked by tokens

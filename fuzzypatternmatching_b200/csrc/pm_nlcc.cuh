@@ -101,6 +101,60 @@ __device__ __forceinline__ unsigned long long warp_reserve(unsigned long long* c
   return base + incl - n;
 }
 
+
+// ---------------------------------------------------------------------------
+// Work aggregation for token emission.  A returning atomic on ONE address retires
+// about one per clock chip-wide, so reserving pool slots per warp and pass would
+// serialise the expand kernels on the pool counter.  Each warp instead stages its
+// tokens in a private shared-memory buffer and reserves pool slots once per
+// PM_STAGE_FLUSH or more tokens (one atomic, then coalesced 8-byte stores).
+// ---------------------------------------------------------------------------
+#define PM_STAGE_FLUSH 64u
+#define PM_STAGE_CAP (PM_STAGE_FLUSH + 128u)  // a pass appends at most 32 lanes x 4 slots
+
+struct WarpStage {
+  uint2* buf;     // this warp's PM_STAGE_CAP entries
+  uint32_t fill;  // same value in every lane
+};
+
+__device__ __forceinline__ void stage_flush(WarpStage& w, uint2* __restrict__ dst, unsigned long long cap,
+                                            unsigned long long* counter, uint32_t* overflow) {
+  if (w.fill == 0) return;
+  const uint32_t lane = threadIdx.x & 31;
+  unsigned long long base = 0;
+  if (lane == 0) base = atomicAdd(counter, (unsigned long long)w.fill);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  __syncwarp();
+  for (uint32_t i = lane; i < w.fill; i += 32) {
+    if (dst && base + i < cap) dst[base + i] = w.buf[i];
+    else if (dst) *overflow = 1u;
+  }
+  __syncwarp();
+  w.fill = 0;
+}
+
+// all 32 lanes call; each lane appends its flagged values (order: lane, then k)
+__device__ __forceinline__ void stage_push(WarpStage& w, const bool (&flag)[4], const uint2 (&val)[4],
+                                           uint2* __restrict__ dst, unsigned long long cap,
+                                           unsigned long long* counter, uint32_t* overflow) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t n = (uint32_t)flag[0] + flag[1] + flag[2] + flag[3];
+  uint32_t incl = n;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= (uint32_t)o) incl += t;
+  }
+  const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+  if (total == 0) return;
+  uint32_t pos = w.fill + incl - n;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (flag[k]) w.buf[pos++] = val[k];
+  w.fill += total;
+  if (w.fill > PM_STAGE_FLUSH) stage_flush(w, dst, cap, counter, overflow);
+}
+
 // ---------------------------------------------------------------------------
 // token sources (nem_1.hpp:387-527; tds_batch_1.hpp:1067-1135, 425-512)
 // ---------------------------------------------------------------------------
@@ -202,6 +256,8 @@ __global__ void __launch_bounds__(kBlock) k_nem1_final_cycle(NlcArgs a, int hlev
 // ---------------------------------------------------------------------------
 template <bool FINAL, bool STREAM>
 __global__ void __launch_bounds__(kBlock) k_nem1_expand(NlcArgs a, int hlevel, int hn) {
+  __shared__ uint2 s_stage[FINAL ? 1 : (kBlock / 32) * PM_STAGE_CAP];
+  WarpStage stage{s_stage + (FINAL ? 0 : (threadIdx.x >> 5) * PM_STAGE_CAP), 0u};
   const uint64_t lo = a.cnt->lvl[hlevel], hi = a.cnt->lvl[hlevel + 1];
   constexpr int GROUP = 8;
   const uint32_t lane = threadIdx.x & 31;
@@ -262,20 +318,94 @@ __global__ void __launch_bounds__(kBlock) k_nem1_expand(NlcArgs a, int hlevel, i
         // interior hop: the source cannot relay (nem_1.hpp:174-177), one token per
         // (vertex, source) (nem_1.hpp:131-139, 270-285)
         bool ins[4];
-        uint32_t nins = 0;
+        uint2 tok[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           ins[k] = pass_static[k] && u[k] != s;
           if (ins[k]) ins[k] = hset_insert(a, u[k], s);
-          nins += ins[k];
+          tok[k] = make_uint2(u[k], s);
         }
-        unsigned long long pos = warp_reserve(&a.cnt->pool_n, nins);
+        stage_push(stage, ins, tok, a.pool, a.pool_cap, &a.cnt->pool_n, &a.cnt->overflow);
+      }
+    }
+    if (has && gl == 0) fan += d;
+  }
+  if (!FINAL) stage_flush(stage, a.pool, a.pool_cap, &a.cnt->pool_n, &a.cnt->overflow);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (ins[k]) {
-            if (pos < a.pool_cap) a.pool[pos] = make_uint2(u[k], s); else a.cnt->overflow = 1u;
-            ++pos;
-          }
+  for (int o = 16; o > 0; o >>= 1) fan += __shfl_xor_sync(0xffffffffu, fan, o);
+  if (lane == 0 && fan) atomicAdd(&a.cnt->fanout, fan);
+}
+
+// ---------------------------------------------------------------------------
+// nem_1, the last TWO hops of a CYCLE constraint in one kernel.  A token (v, s)
+// accepted at hop C-1 would be relayed to every u in E_v that passes the tests of
+// hop C (the last interior hop), and u would relay it along E_u where only the copy
+// arriving at the source can succeed (max_itr_count == itr_count, nem_1.hpp:661-773).
+// So the walk closes iff some u passes the hop-C tests and lies in E_v AND E_s
+// (edge maps are symmetric between live vertices once an LCC call of >= 2 supersteps
+// has run, see pm_lcc.cuh; pm_nlcc checks that precondition): the row of v is
+// streamed and each label-matching neighbour is looked up in the (short, cached) row
+// of s before its mask is gathered.  No level-C tokens are stored or deduplicated.
+// Success acknowledges the source and flags the edge E_s[u] the token would have
+// come back on (nem_1.hpp:764-770).
+// ---------------------------------------------------------------------------
+template <bool STREAM>
+__global__ void __launch_bounds__(kBlock) k_nem1_close_cycle(NlcArgs a, int hlevel, int hn) {
+  const uint64_t lo = a.cnt->lvl[hlevel], hi = a.cnt->lvl[hlevel + 1];
+  constexpr int GROUP = 8;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t gl = lane % GROUP, gw = lane / GROUP;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  const uint32_t want_lab = c_nlc.lab[hn];
+  unsigned long long fan = 0;
+  for (uint64_t base = lo + warp * 4; base < hi; base += nwarps * 4) {
+    const uint64_t t = base + gw;
+    const bool has = t < hi;
+    uint32_t v = 0, s = 0, d = 0, ds = 0;
+    uint64_t rs = 0;
+    if (has) {
+      const uint2 tk = a.pool[t];
+      v = tk.x;
+      s = tk.y;
+      const uint32_t ss = a.S[s];
+      // receiver tests of the closing hop at the source (nem_1.hpp:557-581)
+      if (ss != 0 && hop_ok(ss, a.cls[s], hn + 1)) {
+        d = a.adeg[v];
+        ds = a.adeg[s];
+        rs = (uint64_t)a.rowblk[s] * 8;
+      }
+    }
+    const uint64_t row = has ? (uint64_t)a.rowblk[v] * 8 : 0;
+    const uint32_t passes = (d + GROUP * 4 - 1) / (GROUP * 4);
+    const uint32_t maxp = __reduce_max_sync(0xffffffffu, passes);
+    for (uint32_t p = 0; p < maxp; ++p) {
+      const uint32_t j0 = p * GROUP * 4 + gl * 4;
+      uint4 q = make_uint4(0, 0, 0, 0);
+      uint32_t l4 = 0;
+      if (j0 < d) {
+        q = *reinterpret_cast<const uint4*>(a.colw + row + j0);
+        if (STREAM) l4 = *reinterpret_cast<const uint32_t*>(a.labw + row + j0);
+      }
+      const uint32_t u[4] = {q.x & PM_IDMASK, q.y & PM_IDMASK, q.z & PM_IDMASK, q.w & PM_IDMASK};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        bool may = j0 + k < d && u[k] != s;  // the source cannot relay (nem_1.hpp:174-177)
+        if (STREAM) may = may && ((l4 >> (8 * k)) & 0xffu) == want_lab;
+        if (!may) continue;
+        uint32_t b = 0, e = ds;
+        while (b < e) {  // rows stay ascending: compaction is stable
+          const uint32_t mid = (b + e) >> 1;
+          const uint32_t x = a.colw[rs + mid] & PM_IDMASK;
+          if (x < u[k]) b = mid + 1; else e = mid;
+        }
+        if (b >= ds || (a.colw[rs + b] & PM_IDMASK) != u[k]) continue;
+        const uint32_t su = a.S[u[k]];
+        if (su != 0 && ((su >> c_nlc.I[hn]) & 1u) && (STREAM || a.cls[u[k]] == c_nlc.cls[hn])) {
+          a.ok[s] = 1;
+          a.cnt->found = 1u;
+          atomicOr(&a.colw[rs + b], 0x80000000u);
+        }
       }
     }
     if (has && gl == 0) fan += d;
@@ -303,6 +433,8 @@ __device__ __forceinline__ bool hist_rule(const uint32_t (&hist)[16], int hp, ui
 
 template <bool FINAL, bool STREAM>
 __global__ void __launch_bounds__(kBlock) k_tds_expand(NlcArgs a, int hlevel, int hn) {
+  __shared__ uint2 s_stage[(kBlock / 32) * PM_STAGE_CAP];
+  WarpStage stage{s_stage + (threadIdx.x >> 5) * PM_STAGE_CAP, 0u};
   const uint32_t want_lab = c_nlc.lab[hn];
   const uint64_t lo = a.cnt->lvl[hlevel], hi = a.cnt->lvl[hlevel + 1];
   constexpr int GROUP = 8;
@@ -347,10 +479,11 @@ __global__ void __launch_bounds__(kBlock) k_tds_expand(NlcArgs a, int hlevel, in
       }
       const uint32_t u[4] = {q.x & PM_IDMASK, q.y & PM_IDMASK, q.z & PM_IDMASK, q.w & PM_IDMASK};
       bool acc[4];
-      uint32_t nacc = 0;
+      uint2 tok[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         acc[k] = false;
+        tok[k] = make_uint2((uint32_t)t, u[k]);
         bool may = j0 + k < d;
         if (STREAM) may = may && ((l4 >> (8 * k)) & 0xffu) == want_lab;
         if (may) {
@@ -363,27 +496,20 @@ __global__ void __launch_bounds__(kBlock) k_tds_expand(NlcArgs a, int hlevel, in
               acc[k] = hist_rule(hist, hn, u[k]);
           }
         }
-        nacc += acc[k];
-      }
-      unsigned long long pos = warp_reserve(FINAL ? &a.cnt->matches : &a.cnt->pool_n, nacc);
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (acc[k]) {
-          if (FINAL) {
-            // walk completed (tds_batch_1.hpp:664-694, 699-750)
-            a.ok[s] = 1;
-            a.cnt->found = 1u;
-            if (a.matches && pos < a.match_cap) a.matches[pos] = make_uint2((uint32_t)t, u[k]);
-          } else if (pos < a.pool_cap) {
-            a.pool[pos] = make_uint2((uint32_t)t, u[k]);
-          } else {
-            a.cnt->overflow = 1u;
-          }
-          ++pos;
+        if (FINAL && acc[k]) {  // walk completed (tds_batch_1.hpp:664-694, 699-750)
+          a.ok[s] = 1;
+          a.cnt->found = 1u;
         }
+      }
+      // completed walks go to the match list (a count only when it is not kept: the host
+      // compares `matches` with match_cap itself), relayed tokens to the next pool level
+      if (FINAL) stage_push(stage, acc, tok, a.matches, a.match_cap, &a.cnt->matches, &a.cnt->match_drop);
+      else stage_push(stage, acc, tok, a.pool, a.pool_cap, &a.cnt->pool_n, &a.cnt->overflow);
     }
     if (has && gl == 0) fan += d;
   }
+  if (FINAL) stage_flush(stage, a.matches, a.match_cap, &a.cnt->matches, &a.cnt->match_drop);
+  else stage_flush(stage, a.pool, a.pool_cap, &a.cnt->pool_n, &a.cnt->overflow);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) fan += __shfl_xor_sync(0xffffffffu, fan, o);
   if (lane == 0 && fan) atomicAdd(&a.cnt->fanout, fan);

@@ -532,10 +532,18 @@ int pm_nlcc(pm_ctx* c, int pl, int mode, int* pattern_found, int* token_source_d
     PM_LAUNCH_CHECK(c);
     k_nlcc_begin<<<1, 1, 0, st>>>(c->cnt);
     PM_LAUNCH_CHECK(c);
+    // cycle constraints close their last two hops by intersecting E_v with E_s (k_nem1_close_cycle);
+    // that needs symmetric edge maps, which flags set outside LCC can break only while diameter < 2
+    const bool close2 = !tds && k.valid_cycle && (int)k.C >= 2 && c->pat.diameter >= 2;
     for (int hn = 1; hn <= (int)k.C + 1; ++hn) {
       const bool fin = hn == (int)k.C + 1;
       const int lvl = hn - 1;
       const bool sm = c->labels_small;
+      if (close2 && hn == (int)k.C) {
+        (sm ? k_nem1_close_cycle<true> : k_nem1_close_cycle<false>)<<<grid, kBlock, 0, st>>>(a, lvl, hn);
+        PM_LAUNCH_CHECK(c);
+        break;
+      }
       if (tds) {
         if (fin) (sm ? k_tds_expand<true, true> : k_tds_expand<true, false>)<<<grid, kBlock, 0, st>>>(a, lvl, hn);
         else (sm ? k_tds_expand<false, true> : k_tds_expand<false, false>)<<<grid, kBlock, 0, st>>>(a, lvl, hn);
@@ -555,7 +563,7 @@ int pm_nlcc(pm_ctx* c, int pl, int mode, int* pattern_found, int* token_source_d
     hi = c->h_cnt->pool_n;
     // the pool / hash set ran out, or more walks completed than the match list holds
     const bool overflow = c->h_cnt->overflow || c->h_cnt->pool_n > c->pool_cap ||
-                          (tds && c->keep_subgraphs && c->h_cnt->matches > match_cap);
+                          (tds && c->keep_subgraphs && (c->h_cnt->matches > match_cap || c->h_cnt->match_drop));
     if (!overflow) {
       n_matches = c->h_cnt->matches;
       c->pool_seen[pl] = std::max<uint64_t>(c->pool_seen[pl], c->h_cnt->pool_n);

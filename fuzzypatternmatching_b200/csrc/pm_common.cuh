@@ -30,6 +30,9 @@ struct PatConst {
   uint64_t clabel[16]; // class -> label value
   int ncls;
   uint8_t cls_of_label[64];  // small-label mode: label value -> class (PM_NOCLASS if none)
+  // small-label mode, first superstep from the neighbour-label signature sig[v]:
+  unsigned long long req[16];  // template vertex p survives iff (sig & req[p]) == req[p]: req[p] = labels of N(p)
+  unsigned long long rl[17];   // class c heard a valid neighbour iff sig & rl[c] != 0
 };
 
 struct NlcConst {      // one non-local constraint (walk)

@@ -186,51 +186,115 @@ __global__ void __launch_bounds__(kBlock) k_init_filter(const uint8_t* __restric
                                                          DevCounters* cnt, int buf) {
   __shared__ uint8_t s_cl[64];
   __shared__ uint16_t s_lm[17];
+  __shared__ unsigned long long s_rl[17];
+  __shared__ uint32_t s_w[kBlock / 32][3];
+  __shared__ uint32_t s_base[3];
   if (threadIdx.x < 64) s_cl[threadIdx.x] = c_pat.cls_of_label[threadIdx.x];
-  if (threadIdx.x < 17) s_lm[threadIdx.x] = c_pat.LMc[threadIdx.x];
+  if (threadIdx.x < 17) { s_lm[threadIdx.x] = c_pat.LMc[threadIdx.x]; s_rl[threadIdx.x] = c_pat.rl[threadIdx.x]; }
   __syncthreads();
-  constexpr int IT = 8;
-  const uint64_t tile = (uint64_t)blockDim.x * IT;
+  constexpr int VPT = 16;  // vertices per thread: one uint4 of byte labels, four uint4 of degrees
+  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint64_t tile = (uint64_t)blockDim.x * VPT;
   unsigned long long ncand = 0;
   bool any_removed = false;
   for (uint64_t base = (uint64_t)blockIdx.x * tile; base < V; base += (uint64_t)gridDim.x * tile) {
-    bool keep[IT];
-    int bin[IT];
-    uint32_t val[IT];
+    const uint64_t v0 = base + (uint64_t)threadIdx.x * VPT;
+    uint32_t k0 = 0, k1 = 0, k2 = 0;  // bit j: vertex v0 + j survives the first superstep, by degree bin
+    if (v0 + VPT <= V) {
+      const uint4 l16 = *reinterpret_cast<const uint4*>(lab8 + v0);
+      const uint32_t lw[4] = {l16.x, l16.y, l16.z, l16.w};
+      uint32_t cw[4];
+      uint32_t sw[8];
 #pragma unroll
-    for (int k = 0; k < IT; ++k) {
-      const uint64_t v = base + (uint64_t)k * blockDim.x + threadIdx.x;
-      keep[k] = false;
-      uint32_t d = 0;
-      if (v < V) {
+      for (int g = 0; g < 4; ++g) {
+        const uint4 d4 = *reinterpret_cast<const uint4*>(deg + v0 + 4 * g);
+        const uint32_t dd[4] = {d4.x, d4.y, d4.z, d4.w};
+        cw[g] = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int j = 4 * g + k;
+          const uint32_t c = s_cl[(lw[g] >> (8 * k)) & 63u];
+          const uint32_t d = dd[k];
+          uint32_t lm = d ? (uint32_t)s_lm[c] : 0u;
+          if (lm) {
+            const unsigned long long sg = sig[v0 + j];
+            uint32_t surv = 0;
+            for (uint32_t rest = lm; rest; rest &= rest - 1) {
+              const int pp = __ffs(rest) - 1;
+              const unsigned long long rq = c_pat.req[pp];
+              if (rq != 0ull && (sg & rq) == rq) surv = 1;
+            }
+            any_removed = any_removed || (!surv && (sg & s_rl[c]) != 0ull);  // entered the map and left it (ee.hpp:941-946)
+            ncand++;
+            if (surv) {
+              if (d <= PM_SMALL_MAX) k0 |= 1u << j; else if (d <= PM_MID_MAX) k1 |= 1u << j; else k2 |= 1u << j;
+            } else {
+              lm = 0;
+            }
+          }
+          cw[g] |= c << (8 * k);
+          if (k & 1) sw[j >> 1] |= lm << 16; else sw[j >> 1] = lm;
+        }
+      }
+      *reinterpret_cast<uint4*>(cls + v0) = make_uint4(cw[0], cw[1], cw[2], cw[3]);
+      *reinterpret_cast<uint4*>(S + v0) = make_uint4(sw[0], sw[1], sw[2], sw[3]);
+      *reinterpret_cast<uint4*>(S + v0 + 8) = make_uint4(sw[4], sw[5], sw[6], sw[7]);
+    } else {
+      for (int j = 0; j < VPT && v0 + j < V; ++j) {  // ragged tail
+        const uint64_t v = v0 + j;
         const uint32_t c = s_cl[lab8[v] & 63];
-        d = deg[v];
-        const uint32_t lm = d ? (uint32_t)s_lm[c] : 0u;
+        const uint32_t d = deg[v];
+        uint32_t lm = d ? (uint32_t)s_lm[c] : 0u;
         if (lm) {
           const unsigned long long sg = sig[v];
-          const uint32_t NBv = nb_of(lm);
-          uint32_t heard = 0;
-#pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            const uint32_t lq = c_pat.LMc[q];
-            if (q < c_pat.ncls && ((sg >> (c_pat.clabel[q] & 63)) & 1ull) && (lq & NBv)) heard |= lq;
+          uint32_t surv = 0;
+          for (uint32_t rest = lm; rest; rest &= rest - 1) {
+            const unsigned long long rq = c_pat.req[__ffs(rest) - 1];
+            if (rq != 0ull && (sg & rq) == rq) surv = 1;
           }
-          keep[k] = cover_of(lm, heard) != 0;
-          any_removed = any_removed || (!keep[k] && heard != 0);  // entered the map and left it (ee.hpp:941-946)
+          any_removed = any_removed || (!surv && (sg & s_rl[c]) != 0ull);
           ncand++;
+          if (surv) {
+            if (d <= PM_SMALL_MAX) k0 |= 1u << j; else if (d <= PM_MID_MAX) k1 |= 1u << j; else k2 |= 1u << j;
+          } else {
+            lm = 0;
+          }
         }
         cls[v] = (uint8_t)c;
-        S[v] = keep[k] ? (uint16_t)lm : (uint16_t)0;
+        S[v] = (uint16_t)lm;
       }
-      bin[k] = d <= PM_SMALL_MAX ? 0 : (d <= PM_MID_MAX ? 1 : 2);
-      val[k] = (uint32_t)v;
     }
-    block_bin_append<IT>(keep, bin, val, fr_small, fr_mid, fr_big, &cnt->fr_n[buf][0]);
+    // block-aggregated append of the survivors: one atomic per bin and tile
+    const uint32_t n0 = __popc(k0), n1 = __popc(k1), n2 = __popc(k2);
+    uint32_t i0 = n0, i1 = n1, i2 = n2;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t0 = __shfl_up_sync(0xffffffffu, i0, o);
+      const uint32_t t1 = __shfl_up_sync(0xffffffffu, i1, o);
+      const uint32_t t2 = __shfl_up_sync(0xffffffffu, i2, o);
+      if (lane >= (uint32_t)o) { i0 += t0; i1 += t1; i2 += t2; }
+    }
+    if (lane == 31) { s_w[w][0] = i0; s_w[w][1] = i1; s_w[w][2] = i2; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+      uint32_t t = 0;
+      for (uint32_t i = 0; i < blockDim.x / 32; ++i) t += s_w[i][threadIdx.x];
+      s_base[threadIdx.x] = t ? atomicAdd(&cnt->fr_n[buf][threadIdx.x], t) : 0u;
+    }
+    __syncthreads();
+    if (k0 | k1 | k2) {
+      uint32_t o0 = s_base[0] + i0 - n0, o1 = s_base[1] + i1 - n1, o2 = s_base[2] + i2 - n2;
+      for (uint32_t i = 0; i < w; ++i) { o0 += s_w[i][0]; o1 += s_w[i][1]; o2 += s_w[i][2]; }
+      for (uint32_t rest = k0; rest; rest &= rest - 1) fr_small[o0++] = (uint32_t)(v0 + __ffs(rest) - 1);
+      for (uint32_t rest = k1; rest; rest &= rest - 1) fr_mid[o1++] = (uint32_t)(v0 + __ffs(rest) - 1);
+      for (uint32_t rest = k2; rest; rest &= rest - 1) fr_big[o2++] = (uint32_t)(v0 + __ffs(rest) - 1);
+    }
+    __syncthreads();
   }
   if (any_removed) cnt->nf_init = 1u;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) ncand += __shfl_xor_sync(0xffffffffu, ncand, o);
-  if ((threadIdx.x & 31) == 0 && ncand) atomicAdd(&cnt->filtered_init, ncand);
+  if (lane == 0 && ncand) atomicAdd(&cnt->filtered_init, ncand);
 }
 
 // ---------------------------------------------------------------------------

@@ -266,6 +266,19 @@ int pm_pattern_load_dir(pm_ctx* c, const char* dir) {
   for (int l = 0; l < 64; ++l) pc.cls_of_label[l] = PM_NOCLASS;
   for (int k = 0; k < pc.ncls; ++k)
     if (pc.clabel[k] < 64) pc.cls_of_label[pc.clabel[k]] = (uint8_t)k;
+  // first-superstep tables over the neighbour-label signature (labels < 64): every neighbour u sends
+  // labelmask(label[u]) (ee.hpp:519-561), a sender is valid iff its mask meets NB(T_v) (:673-722), and
+  // template vertex p survives iff N(p) is covered by what was heard (:901-939)
+  for (int i = 0; i < p.n_vertices && i < 16; ++i)
+    for (int b = 0; b < 16; ++b)
+      if (((pc.N[i] >> b) & 1u) && b < (int)p.vertex_label.size() && p.vertex_label[b] < 64)
+        pc.req[i] |= 1ull << p.vertex_label[b];
+  for (int k = 0; k < pc.ncls; ++k) {
+    uint32_t nb = 0;
+    for (int a = 0; a < 16; ++a) if ((pc.LMc[k] >> a) & 1u) nb |= pc.N[a];
+    for (int q = 0; q < pc.ncls; ++q)
+      if ((pc.LMc[q] & nb) && pc.clabel[q] < 64) pc.rl[k] |= 1ull << pc.clabel[q];
+  }
   c->pat = p;
   c->pc = pc;
   c->has_pattern = true;

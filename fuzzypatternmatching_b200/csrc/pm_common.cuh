@@ -15,6 +15,7 @@
 #define PM_SENTINEL 0xFFFFFFFFu  // padding slot in the adjacency arrays
 #define PM_IDMASK 0x7FFFFFFFu    // bit 31 of a working-adjacency slot = "flag set outside LCC" 
 #define PM_NOCLASS 16            // class id of a label no template vertex carries
+#define PM_MAX_RANKS 8           // GPUs of one NVSwitch box
 
 // degree bins (current active degree) -> kernel shape
 #define PM_SMALL_MAX 32u    // <= 32 slots: one 8-lane group, one pass of uint4 loads
@@ -61,6 +62,39 @@ struct DevCounters {
   unsigned long long fanout;    // NLCC: adjacency slots walked by tokens
   unsigned long long hash_n;    // NLCC: keys in the (vertex, source) set
   unsigned long long lvl[20];   // NLCC: token pool level bounds, level h = [lvl[h], lvl[h+1])
+  // multi-GPU (all zero with one rank)
+  unsigned long long out_n[PM_MAX_RANKS];  // tokens / walks this rank stored in the inbox region of rank g during the current hop
+  uint32_t ndelta;              // mask changes this rank published in the current step
+  uint32_t pad2;
+};
+
+// what every rank contributes to the per-step all-gather (= the barrier)
+struct StepMsg {
+  unsigned long long out_n[PM_MAX_RANKS];
+  uint32_t ndelta, nf, found, deleted, overflow, pad;
+  unsigned long long accepted;   // tokens accepted so far (pool_n)
+};
+
+// Multi-GPU: one process per GPU, 1-D vertex partition owner(v) = v mod G like the reference
+// (impl/delegate_partitioned_graph.ipp:1682-1697).  On the device every vertex is named by its
+// SLOT, slot(v) = (v mod G) * nlmax + v / G, so that rank r owns the contiguous slot range
+// [r * nlmax, (r + 1) * nlmax): adjacency arrays store slots, replicated per-vertex arrays (S, cls,
+// lab8, ok) are indexed by slot, rank-local arrays by slot - base.  With G = 1, slot(v) = v.
+// Peers exchange data by storing straight into each other's memory over NVLink (CUDA IPC mappings of
+// cudaMalloc'd buffers); NCCL carries only the bootstrap, bulk all-gathers at initialisation and the
+// small per-step all-gather that doubles as the barrier.
+struct PeerTab {
+  int G, rank;
+  uint32_t nlmax;       // slots per rank
+  uint32_t base;        // first slot of this rank
+  uint32_t dcap;        // delta inbox: entries per sender region
+  unsigned long long tcap;  // token inbox: tokens per sender region
+  const uint32_t* rowblk[PM_MAX_RANKS];  // rank-local arrays of every rank (index: slot - owner * nlmax)
+  const uint32_t* adeg[PM_MAX_RANKS];
+  uint32_t* colw[PM_MAX_RANKS];
+  uint8_t* ok[PM_MAX_RANKS];             // replicated-size array of every rank (index: slot); truth lives at the owner
+  uint2* din[2][PM_MAX_RANKS];           // delta inbox of rank g: G regions of dcap (slot, mask) pairs, double buffered
+  uint2* tin[2][PM_MAX_RANKS];           // token inbox of rank g: G regions of tcap tokens, double buffered
 };
 
 struct RowStat {                // one result row, accumulated on the device
@@ -78,6 +112,16 @@ struct pm_ctx {
   std::string err;
   uint64_t launches = 0;
   int rank = 0, n_ranks = 1;
+  void* comm = nullptr;            // ncclComm_t
+  uint64_t nlmax = 0;              // slots per rank (multiple of 16); slot base of this rank = rank * nlmax
+  pm::PeerTab peers{};             // host copy of c_peer
+  std::vector<void*> ipc_open;     // peer mappings currently open
+  pm::StepMsg* step_msg = nullptr; // device: [1 + G] (mine, then everyone's)
+  pm::StepMsg* h_step = nullptr;   // pinned: [G]
+  uint2* din[2] = {nullptr, nullptr};   // delta inboxes (G regions of dcap)
+  uint2* tin[2] = {nullptr, nullptr};   // token inboxes (G regions of tcap)
+  uint64_t dcap = 0, tcap = 0;
+  int step_parity = 0;             // which delta inbox the next publication uses
 
   // ---- graph store (device) -------------------------------------------------
   uint64_t V = 0, nloc = 0, E_multi = 0, E = 0, Epad = 0, max_deg = 0, graph_bytes = 0;

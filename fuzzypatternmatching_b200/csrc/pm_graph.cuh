@@ -17,26 +17,58 @@
 #include <cub/cub.cuh>
 
 #include "pm_common.cuh"
+#include "pm_comm.cuh"
 
 namespace pm {
 
-__global__ void k_degm_and_keys(const uint32_t* __restrict__ src, const uint32_t* __restrict__ dst,
-                                uint64_t n, uint32_t* __restrict__ degm,
-                                unsigned long long* __restrict__ keys) {
+// slot(v) = (v mod G) * nlmax + v / G (see PeerTab); G == 1: slot = v
+__device__ __forceinline__ uint32_t d_slot_of(uint32_t v, uint32_t G, uint32_t nlmax) {
+  return G == 1 ? v : (v % G) * nlmax + v / G;
+}
+
+// keys[i] = slot(src) << 32 | slot(dst).  drop_foreign: slots whose source another rank owns become
+// ~0 (sorted to the end and cut off) — the caller passed the whole edge list to every rank.
+__global__ void k_slot_keys(const uint32_t* __restrict__ src, const uint32_t* __restrict__ dst, uint64_t n,
+                            uint32_t G, uint32_t nlmax, uint32_t rank, int drop_foreign,
+                            unsigned long long* __restrict__ keys) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
-    uint32_t s = src[i], d = dst[i];
-    atomicAdd(&degm[s], 1u);
-    keys[i] = ((unsigned long long)s << 32) | d;
+    const uint32_t s = src[i], d = dst[i];
+    unsigned long long k = ((unsigned long long)d_slot_of(s, G, nlmax) << 32) | d_slot_of(d, G, nlmax);
+    if (drop_foreign && s % G != rank) k = ~0ull;
+    keys[i] = k;
   }
 }
 
-__global__ void k_distinct_degree(const unsigned long long* __restrict__ ukeys, uint64_t n,
+// multigraph out-degree of the local rows (duplicates and self loops counted, ipp:437-470)
+__global__ void k_degm_of_keys(const unsigned long long* __restrict__ keys, uint64_t n, uint32_t base,
+                               uint32_t* __restrict__ degm) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) atomicAdd(&degm[(uint32_t)(keys[i] >> 32) - base], 1u);
+}
+
+// first index whose key is >= bound[g] (keys ascending): the owner ranges of a sorted key array
+__global__ void k_lower_bounds(const unsigned long long* __restrict__ keys, uint64_t n,
+                               const unsigned long long* __restrict__ bound, int nb,
+                               unsigned long long* __restrict__ out) {
+  const int g = threadIdx.x;
+  if (g >= nb) return;
+  uint64_t lo = 0, hi = n;
+  const unsigned long long b = bound[g];
+  while (lo < hi) {
+    const uint64_t mid = (lo + hi) >> 1;
+    if (keys[mid] < b) lo = mid + 1; else hi = mid;
+  }
+  out[g] = lo;
+}
+
+__global__ void k_distinct_degree(const unsigned long long* __restrict__ ukeys, uint64_t n, uint32_t base,
                                   uint32_t* __restrict__ deg) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) atomicAdd(&deg[(uint32_t)(ukeys[i] >> 32)], 1u);
+  for (; i < n; i += stride) atomicAdd(&deg[(uint32_t)(ukeys[i] >> 32) - base], 1u);
 }
 
 __global__ void k_row_sectors(const uint32_t* __restrict__ deg, uint64_t V,
@@ -50,7 +82,7 @@ __global__ void k_row_sectors(const uint32_t* __restrict__ deg, uint64_t V,
   }
 }
 
-__global__ void k_scatter_cols(const unsigned long long* __restrict__ ukeys, uint64_t n,
+__global__ void k_scatter_cols(const unsigned long long* __restrict__ ukeys, uint64_t n, uint32_t base,
                                const uint32_t* __restrict__ rowblk,
                                const unsigned long long* __restrict__ ustart,
                                uint32_t* __restrict__ col0) {
@@ -58,7 +90,7 @@ __global__ void k_scatter_cols(const unsigned long long* __restrict__ ukeys, uin
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
     unsigned long long k = ukeys[i];
-    uint32_t v = (uint32_t)(k >> 32);
+    uint32_t v = (uint32_t)(k >> 32) - base;
     uint64_t pos = (uint64_t)rowblk[v] * 8 + (i - ustart[v]);
     col0[pos] = (uint32_t)k;
   }
@@ -183,7 +215,9 @@ __global__ void k_build_lab0(const uint32_t* __restrict__ col0, const uint8_t* _
   }
 }
 
-// after the labels changed: byte labels + neighbour-label signatures (labels < 64 only)
+// after the labels changed: byte labels + neighbour-label signatures (labels < 64 only).
+// c->label holds the labels of the LOCAL rows; lab8 is replicated (indexed by slot) because the
+// label of a neighbour owned by another rank is needed to build lab0 and the signatures.
 inline int labels_derive(pm_ctx* c, bool small) {
   dev_free(c->lab8);
   dev_free(c->sig);
@@ -193,16 +227,18 @@ inline int labels_derive(pm_ctx* c, bool small) {
   if (!small) return 0;
   int rc;
   uint32_t *big_list = nullptr, *big_n = nullptr;
-  if ((rc = dev_alloc(c, &c->lab8, c->V, &c->graph_bytes))) return rc;
-  if ((rc = dev_alloc(c, &c->sig, c->V, &c->graph_bytes))) return rc;
+  const uint64_t Vs = c->nlmax * c->n_ranks, base = c->nlmax * c->rank;
+  if ((rc = dev_alloc(c, &c->lab8, Vs, &c->graph_bytes))) return rc;
+  if ((rc = dev_alloc(c, &c->sig, c->nloc, &c->graph_bytes))) return rc;
   if ((rc = dev_alloc(c, &c->lab0, c->Epad + 64, &c->graph_bytes))) return rc;
   if ((rc = dev_alloc(c, &c->labw, c->Epad + 64, &c->graph_bytes))) return rc;
   if ((rc = dev_alloc(c, &big_list, c->Epad / PM_SIG_BIG + 1024))) return rc;
   if ((rc = dev_alloc(c, &big_n, 1))) { dev_free(big_list); return rc; }
   cudaStream_t st = c->stream;
   cudaMemsetAsync(big_n, 0, 4, st);
-  k_labels_to_bytes<<<grid_for(), kBlock, 0, st>>>(c->label, c->V, c->lab8);
-  k_build_sig<<<grid_for(), 256, 0, st>>>(c->rowblk, c->deg, c->col0, c->lab8, c->V, c->sig, big_list, big_n);
+  k_labels_to_bytes<<<grid_for(), kBlock, 0, st>>>(c->label, c->nloc, c->lab8 + base);
+  if ((rc = comm_allgather_slots(c, c->lab8))) { dev_free(big_list); dev_free(big_n); return rc; }
+  k_build_sig<<<grid_for(), 256, 0, st>>>(c->rowblk, c->deg, c->col0, c->lab8, c->nloc, c->sig, big_list, big_n);
   k_build_sig_big<<<148, 1024, 0, st>>>(c->rowblk, c->deg, c->col0, c->lab8, c->sig, big_list, big_n);
   k_build_lab0<<<grid_for(), kBlock, 0, st>>>(c->col0, c->lab8, c->Epad + 64, c->lab0);
   c->launches += 4;
@@ -216,6 +252,7 @@ inline int labels_derive(pm_ctx* c, bool small) {
 }
 
 inline void graph_free(pm_ctx* c) {
+  comm_close_all(c);  // peers' mappings of the previous store
   dev_free(c->lab8);
   dev_free(c->sig);
   dev_free(c->lab0);
@@ -231,117 +268,217 @@ inline void graph_free(pm_ctx* c) {
   c->graph_bytes = 0;
 }
 
-// d_src / d_dst: device arrays of n directed slots (consumed, freed by the caller).
-inline int graph_build_from_device_slots(pm_ctx* c, uint64_t V, uint64_t n, const uint32_t* d_src,
-                                         const uint32_t* d_dst) {
+// slots per rank: every rank's range starts 16-aligned so that the vectorised kernels can treat the
+// local part of a replicated array like a whole array
+inline void graph_set_partition(pm_ctx* c, uint64_t V) {
+  c->V = V;
+  if (c->n_ranks == 1) {
+    c->nlmax = V;
+  } else {
+    const uint64_t per = (V + c->n_ranks - 1) / c->n_ranks;
+    c->nlmax = (per + 15) / 16 * 16;
+  }
+  c->nloc = c->nlmax;
+}
+
+// Moves every key to the rank that owns its source slot.  keys: sorted ascending, n entries (device).
+// On return *out / *n_out hold this rank's keys (unsorted concatenation of G sorted runs).
+inline int graph_route_keys(pm_ctx* c, const unsigned long long* keys, uint64_t n, unsigned long long** out,
+                            uint64_t* n_out) {
+  const int G = c->n_ranks;
+  cudaStream_t st = c->stream;
+  unsigned long long *d_bound = nullptr, *d_lb = nullptr, *d_all = nullptr;
+  int rc;
+  if ((rc = dev_alloc(c, &d_bound, G + 1)) || (rc = dev_alloc(c, &d_lb, G + 1)) || (rc = dev_alloc(c, &d_all, (uint64_t)G * G))) {
+    dev_free(d_bound); dev_free(d_lb); dev_free(d_all);
+    return rc;
+  }
+  std::vector<unsigned long long> bound(G + 1), lb(G + 1);
+  for (int g = 0; g <= G; ++g) bound[g] = (unsigned long long)(c->nlmax * g) << 32;
+  cudaMemcpyAsync(d_bound, bound.data(), 8 * (G + 1), cudaMemcpyHostToDevice, st);
+  k_lower_bounds<<<1, 32, 0, st>>>(keys, n, d_bound, G + 1, d_lb);
+  c->launches++;
+  cudaMemcpyAsync(lb.data(), d_lb, 8 * (G + 1), cudaMemcpyDeviceToHost, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  std::vector<unsigned long long> cnt(G), all((size_t)G * G);
+  for (int g = 0; g < G; ++g) cnt[g] = lb[g + 1] - lb[g];
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_all + (size_t)c->rank * G, cnt.data(), 8 * G, cudaMemcpyHostToDevice, st);
+  ncclResult_t nr = ncclSuccess;
+  if (e == cudaSuccess) nr = ncclAllGather(d_all + (size_t)c->rank * G, d_all, G, ncclUint64, comm_of(c), st);
+  if (e == cudaSuccess && nr == ncclSuccess) e = cudaMemcpyAsync(all.data(), d_all, 8 * (size_t)G * G, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && nr == ncclSuccess) e = cudaStreamSynchronize(st);
+  dev_free(d_bound); dev_free(d_lb); dev_free(d_all);
+  if (e != cudaSuccess) return fail(c, PM_ERR_CUDA, std::string("graph_route_keys: ") + cudaGetErrorString(e));
+  if (nr != ncclSuccess) return fail(c, PM_ERR_COMM, std::string("graph_route_keys: ") + ncclGetErrorString(nr));
+  uint64_t total = 0;
+  std::vector<uint64_t> roff(G);
+  for (int g = 0; g < G; ++g) { roff[g] = total; total += all[(size_t)g * G + c->rank]; }
+  unsigned long long* recv = nullptr;
+  if ((rc = dev_alloc(c, &recv, total))) return rc;
+  // chunked so that no single message exceeds 2^30 keys
+  const uint64_t chunk = 1ull << 30;
+  nr = ncclGroupStart();
+  for (int g = 0; g < G && nr == ncclSuccess; ++g) {
+    for (uint64_t o = 0; o < cnt[g] && nr == ncclSuccess; o += chunk)
+      nr = ncclSend(keys + lb[g] + o, (size_t)std::min<uint64_t>(chunk, cnt[g] - o), ncclUint64, g, comm_of(c), st);
+    const uint64_t rn = all[(size_t)g * G + c->rank];
+    for (uint64_t o = 0; o < rn && nr == ncclSuccess; o += chunk)
+      nr = ncclRecv(recv + roff[g] + o, (size_t)std::min<uint64_t>(chunk, rn - o), ncclUint64, g, comm_of(c), st);
+  }
+  if (nr == ncclSuccess) nr = ncclGroupEnd();
+  if (nr == ncclSuccess && cudaStreamSynchronize(st) != cudaSuccess) nr = ncclUnhandledCudaError;
+  if (nr != ncclSuccess) { dev_free(recv); return fail(c, PM_ERR_COMM, std::string("edge exchange: ") + ncclGetErrorString(nr)); }
+  *out = recv;
+  *n_out = total;
+  return 0;
+}
+
+// d_src / d_dst: device arrays of n directed slots with GLOBAL vertex ids (consumed, freed by the caller).
+// route = true: the ranks hold disjoint parts of one edge list and every slot is sent to the owner of
+// its source (the reference's edge shuffle, ipp:401-520); route = false: slots with a foreign source
+// are dropped (every rank was handed the whole list).
+inline int graph_build_from_device_slots(pm_ctx* c, uint64_t V, uint64_t n_in, const uint32_t* d_src,
+                                         const uint32_t* d_dst, bool route) {
   if (V == 0 || V > (1ull << 31)) return fail(c, PM_ERR_ARG, "n_vertices must be in [1, 2^31]");
   graph_free(c);
+  graph_set_partition(c, V);
   cudaStream_t st = c->stream;
-  c->V = c->nloc = V;
-  c->E_multi = n;
+  const uint64_t NL = c->nloc;
+  const uint32_t base = (uint32_t)(c->nlmax * c->rank);
+  const int G = c->n_ranks;
   uint64_t bytes = 0;
   int rc;
-  if ((rc = dev_alloc(c, &c->degm, V, &bytes))) return rc;
-  if ((rc = dev_alloc(c, &c->deg, V, &bytes))) return rc;
-  if ((rc = dev_alloc(c, &c->rowblk, V + 1, &bytes))) return rc;
-  PM_CUDA(c, cudaMemsetAsync(c->degm, 0, V * sizeof(uint32_t), st));
-  PM_CUDA(c, cudaMemsetAsync(c->deg, 0, V * sizeof(uint32_t), st));
+  if ((rc = dev_alloc(c, &c->degm, NL, &bytes))) return rc;
+  if ((rc = dev_alloc(c, &c->deg, NL, &bytes))) return rc;
+  if ((rc = dev_alloc(c, &c->rowblk, NL + 1, &bytes))) return rc;
+  PM_CUDA(c, cudaMemsetAsync(c->degm, 0, NL * sizeof(uint32_t), st));
+  PM_CUDA(c, cudaMemsetAsync(c->deg, 0, NL * sizeof(uint32_t), st));
 
-  unsigned long long *keys = nullptr, *keys2 = nullptr, *ustart = nullptr, *d_nuniq = nullptr;
+  unsigned long long *keys = nullptr, *keys2 = nullptr, *ustart = nullptr, *d_nuniq = nullptr, *deg64 = nullptr;
   uint32_t* sectors = nullptr;
   void* tmp = nullptr;
+  size_t tmp_bytes = 0;
   auto cleanup = [&]() {
-    dev_free(keys); dev_free(keys2); dev_free(ustart); dev_free(d_nuniq); dev_free(sectors);
+    dev_free(keys); dev_free(keys2); dev_free(ustart); dev_free(d_nuniq); dev_free(sectors); dev_free(deg64);
     if (tmp) cudaFree(tmp);
     tmp = nullptr;
   };
 #define PM_G(call) do { int rc_ = (call); if (rc_) { cleanup(); return rc_; } } while (0)
 #define PM_GC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); \
     return fail(c, PM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
+  auto need_tmp = [&](size_t want) -> cudaError_t {
+    if (want <= tmp_bytes) return cudaSuccess;
+    if (tmp) cudaFree(tmp);
+    tmp = nullptr;
+    tmp_bytes = std::max<size_t>(want, 16);
+    return cudaMalloc(&tmp, tmp_bytes);
+  };
+  const int grid = grid_for();
+  // only the bits that can be set take part in the sorts
+  int bits = 32;
+  while (bits < 64 && ((c->nlmax * G - 1) >> (bits - 32))) ++bits;
+  uint64_t n = n_in;
   PM_G(dev_alloc(c, &keys, n));
   PM_G(dev_alloc(c, &keys2, n));
-  PM_G(dev_alloc(c, &d_nuniq, 1));
-  const int grid = grid_for();
+  PM_G(dev_alloc(c, &d_nuniq, 2));
   if (n) {
-    k_degm_and_keys<<<grid, kBlock, 0, st>>>(d_src, d_dst, n, c->degm, keys);
+    k_slot_keys<<<grid, kBlock, 0, st>>>(d_src, d_dst, n, (uint32_t)G, (uint32_t)c->nlmax, (uint32_t)c->rank,
+                                         (G > 1 && !route) ? 1 : 0, keys);
     c->launches++;
     PM_GC(cudaGetLastError());
   }
-  // sort (src,dst) keys; only the bits that can be set take part
-  int bits = 32;
-  while (bits < 64 && (V - 1) >> (bits - 32)) ++bits;
-  size_t tmp_bytes = 0, tb2 = 0;
+  if (G > 1) {
+    // sort once so that every owner's keys are one contiguous range (foreign keys, if dropped, sort last)
+    size_t tb = 0;
+    cub::DoubleBuffer<unsigned long long> db0(keys, keys2);
+    PM_GC(cub::DeviceRadixSort::SortKeys(nullptr, tb, db0, (int64_t)n, 0, 64, st));
+    PM_GC(need_tmp(tb));
+    PM_GC(cub::DeviceRadixSort::SortKeys(tmp, tb, db0, (int64_t)n, 0, 64, st));
+    if (db0.Current() != keys) std::swap(keys, keys2);
+    if (route) {
+      unsigned long long* mine = nullptr;
+      uint64_t n_mine = 0;
+      PM_G(graph_route_keys(c, keys, n, &mine, &n_mine));
+      dev_free(keys);
+      dev_free(keys2);
+      keys = mine;
+      n = n_mine;
+      PM_G(dev_alloc(c, &keys2, n));
+    } else {
+      // keep [lower_bound(base), lower_bound(base + nlmax))
+      unsigned long long h_b[2] = {(unsigned long long)base << 32, (unsigned long long)(base + c->nlmax) << 32}, h_lb[2];
+      unsigned long long* d_b = d_nuniq;  // scratch: 2 entries
+      unsigned long long* d_lb = nullptr;
+      PM_G(dev_alloc(c, &d_lb, 2));
+      cudaMemcpyAsync(d_b, h_b, 16, cudaMemcpyHostToDevice, st);
+      k_lower_bounds<<<1, 32, 0, st>>>(keys, n, d_b, 2, d_lb);
+      cudaMemcpyAsync(h_lb, d_lb, 16, cudaMemcpyDeviceToHost, st);
+      cudaError_t e = cudaStreamSynchronize(st);
+      dev_free(d_lb);
+      PM_GC(e);
+      const uint64_t n_mine = h_lb[1] - h_lb[0];
+      PM_GC(cudaMemcpyAsync(keys2, keys + h_lb[0], n_mine * 8, cudaMemcpyDeviceToDevice, st));
+      std::swap(keys, keys2);
+      n = n_mine;
+    }
+  }
+  c->E_multi = n;
+  if (n) {
+    k_degm_of_keys<<<grid, kBlock, 0, st>>>(keys, n, base, c->degm);
+    c->launches++;
+    PM_GC(cudaGetLastError());
+  }
+  size_t tb1 = 0, tb2 = 0;
   cub::DoubleBuffer<unsigned long long> db(keys, keys2);
-  PM_GC(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, db, (int64_t)n, 0, bits, st));
+  PM_GC(cub::DeviceRadixSort::SortKeys(nullptr, tb1, db, (int64_t)n, 0, bits, st));
   PM_GC(cub::DeviceSelect::Unique(nullptr, tb2, keys, keys2, d_nuniq, (int64_t)n, st));
-  tmp_bytes = std::max(tmp_bytes, tb2);
-  PM_GC(cudaMalloc(&tmp, std::max<size_t>(tmp_bytes, 16)));
-  PM_GC(cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, db, (int64_t)n, 0, bits, st));
+  PM_GC(need_tmp(std::max(tb1, tb2)));
+  PM_GC(cub::DeviceRadixSort::SortKeys(tmp, tb1, db, (int64_t)n, 0, bits, st));
   unsigned long long* sorted = db.Current();
   unsigned long long* ukeys = db.Alternate();
-  PM_GC(cub::DeviceSelect::Unique(tmp, tmp_bytes, sorted, ukeys, d_nuniq, (int64_t)n, st));
+  PM_GC(cub::DeviceSelect::Unique(tmp, tb2, sorted, ukeys, d_nuniq, (int64_t)n, st));
   unsigned long long h_nuniq = 0;
   PM_GC(cudaMemcpyAsync(&h_nuniq, d_nuniq, sizeof(h_nuniq), cudaMemcpyDeviceToHost, st));
   PM_GC(cudaStreamSynchronize(st));
   c->E = h_nuniq;
   if (h_nuniq) {
-    k_distinct_degree<<<grid, kBlock, 0, st>>>(ukeys, h_nuniq, c->deg);
+    k_distinct_degree<<<grid, kBlock, 0, st>>>(ukeys, h_nuniq, base, c->deg);
     c->launches++;
     PM_GC(cudaGetLastError());
   }
   // row starts (in sectors) and starts in the unique list
-  PM_G(dev_alloc(c, &sectors, V + 1));
-  PM_G(dev_alloc(c, &ustart, V + 1));
-  unsigned long long* deg64 = nullptr;
-  PM_G(dev_alloc(c, &deg64, V + 1));
-  k_row_sectors<<<grid, kBlock, 0, st>>>(c->deg, V, sectors, deg64);
+  PM_G(dev_alloc(c, &sectors, NL + 1));
+  PM_G(dev_alloc(c, &ustart, NL + 1));
+  PM_G(dev_alloc(c, &deg64, NL + 1));
+  k_row_sectors<<<grid, kBlock, 0, st>>>(c->deg, NL, sectors, deg64);
   c->launches++;
-  size_t tb3 = 0, tb4 = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, tb3, sectors, c->rowblk, (int64_t)(V + 1), st);
-  cub::DeviceScan::ExclusiveSum(nullptr, tb4, deg64, ustart, (int64_t)(V + 1), st);
-  if (std::max(tb3, tb4) > tmp_bytes) {
-    cudaFree(tmp);
-    tmp = nullptr;
-    tmp_bytes = std::max(tb3, tb4);
-    PM_GC(cudaMalloc(&tmp, tmp_bytes));
-  }
-  PM_GC(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, sectors, c->rowblk, (int64_t)(V + 1), st));
-  PM_GC(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, deg64, ustart, (int64_t)(V + 1), st));
-  uint32_t h_total_sectors = 0;
-  PM_GC(cudaMemcpyAsync(&h_total_sectors, c->rowblk + V, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-  // largest multigraph degree
+  size_t tb3 = 0, tb4 = 0, tb5 = 0;
   uint32_t* d_max = (uint32_t*)d_nuniq;
-  size_t tb5 = 0;
-  cub::DeviceReduce::Max(nullptr, tb5, c->degm, d_max, (int64_t)V, st);
-  if (tb5 > tmp_bytes) {
-    cudaFree(tmp);
-    tmp = nullptr;
-    tmp_bytes = tb5;
-    PM_GC(cudaMalloc(&tmp, tmp_bytes));
-  }
-  PM_GC(cub::DeviceReduce::Max(tmp, tmp_bytes, c->degm, d_max, (int64_t)V, st));
-  uint32_t h_max = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tb3, sectors, c->rowblk, (int64_t)(NL + 1), st);
+  cub::DeviceScan::ExclusiveSum(nullptr, tb4, deg64, ustart, (int64_t)(NL + 1), st);
+  cub::DeviceReduce::Max(nullptr, tb5, c->degm, d_max, (int64_t)NL, st);
+  PM_GC(need_tmp(std::max(tb3, std::max(tb4, tb5))));
+  PM_GC(cub::DeviceScan::ExclusiveSum(tmp, tb3, sectors, c->rowblk, (int64_t)(NL + 1), st));
+  PM_GC(cub::DeviceScan::ExclusiveSum(tmp, tb4, deg64, ustart, (int64_t)(NL + 1), st));
+  uint32_t h_total_sectors = 0, h_max = 0;
+  PM_GC(cudaMemcpyAsync(&h_total_sectors, c->rowblk + NL, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  PM_GC(cub::DeviceReduce::Max(tmp, tb5, c->degm, d_max, (int64_t)NL, st));
   PM_GC(cudaMemcpyAsync(&h_max, d_max, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   PM_GC(cudaStreamSynchronize(st));
   c->max_deg = h_max;
   // +64 slots of slack: the scan kernels read whole uint4 windows
   c->Epad = (uint64_t)h_total_sectors * 8;
   const uint64_t alloc_slots = c->Epad + 64;
-  {
-    int rc2 = dev_alloc(c, &c->col0, alloc_slots, &bytes);
-    if (rc2) { cleanup(); dev_free(deg64); return rc2; }
-    rc2 = dev_alloc(c, &c->colw, alloc_slots, &bytes);
-    if (rc2) { cleanup(); dev_free(deg64); return rc2; }
-  }
+  PM_G(dev_alloc(c, &c->col0, alloc_slots, &bytes));
+  PM_G(dev_alloc(c, &c->colw, alloc_slots, &bytes));
   PM_GC(cudaMemsetAsync(c->col0, 0xFF, alloc_slots * sizeof(uint32_t), st));
   PM_GC(cudaMemsetAsync(c->colw, 0xFF, alloc_slots * sizeof(uint32_t), st));
   if (h_nuniq) {
-    k_scatter_cols<<<grid, kBlock, 0, st>>>(ukeys, h_nuniq, c->rowblk, ustart, c->col0);
+    k_scatter_cols<<<grid, kBlock, 0, st>>>(ukeys, h_nuniq, base, c->rowblk, ustart, c->col0);
     c->launches++;
     PM_GC(cudaGetLastError());
   }
   PM_GC(cudaStreamSynchronize(st));
-  dev_free(deg64);
   cleanup();
 #undef PM_G
 #undef PM_GC
@@ -357,9 +494,9 @@ inline int graph_build_from_host_csr(pm_ctx* c, uint64_t V, const uint64_t* h_ro
                                      const uint64_t* h_degm) {
   if (V == 0 || V > (1ull << 31)) return fail(c, PM_ERR_ARG, "n_vertices must be in [1, 2^31]");
   graph_free(c);
+  graph_set_partition(c, V);  // single rank: slot = vertex id, the rows can be placed as they are
   cudaStream_t st = c->stream;
   const uint64_t E = h_rowptr[V];
-  c->V = c->nloc = V;
   c->E = E;
   uint64_t bytes = 0;
   int rc;

@@ -25,6 +25,7 @@
 #pragma once
 
 #include "pm_common.cuh"
+#include "pm_comm.cuh"
 
 namespace pm {
 
@@ -113,7 +114,42 @@ struct LccArgs {
   DevCounters* cnt;
   RowStat* row;   // accumulator of this superstep
   int bin;        // degree bin this launch serves (row statistics)
+  uint32_t base;  // first slot of this rank: frontier lists and rank-local arrays are indexed by slot - base
+  int par;        // delta inbox the commit of this superstep publishes into
 };
+
+// Publishes "the mask of my vertex `slot` is now `mask`" to every peer: the pair is stored straight
+// into the sender's region of each peer's delta inbox (NVLink stores, one position per change, reserved
+// with one atomic per warp).  This replaces the per-message mailbox traffic of the reference
+// (visitor_queue.hpp:395-434): peers only ever need the CHANGES of template_vertices.  All 32 lanes call.
+__device__ __forceinline__ void publish_mask(bool changed, uint32_t slot, uint32_t mask, DevCounters* cnt, int par) {
+  const uint32_t m = __ballot_sync(0xffffffffu, changed);
+  if (m == 0u) return;
+  const uint32_t lane = threadIdx.x & 31;
+  const int leader = __ffs(m) - 1;
+  uint32_t pos = 0;
+  if ((int)lane == leader) pos = atomicAdd(&cnt->ndelta, (uint32_t)__popc(m));
+  pos = __shfl_sync(0xffffffffu, pos, leader) + __popc(m & ((1u << lane) - 1u));
+  if (changed && pos < c_peer.dcap) {
+    const uint2 d = make_uint2(slot, mask);
+    for (int g = 0; g < c_peer.G; ++g)
+      if (g != c_peer.rank) c_peer.din[par][g][(uint64_t)c_peer.rank * c_peer.dcap + pos] = d;
+  }
+}
+
+// applies the mask changes the peers published in the step that just ended (after comm_step)
+__global__ void __launch_bounds__(kBlock) k_apply_deltas(uint16_t* __restrict__ S, const StepMsg* __restrict__ all, int par) {
+  const int G = c_peer.G, me = c_peer.rank;
+  for (int r = 0; r < G; ++r) {
+    if (r == me) continue;
+    const uint32_t n = min(all[r].ndelta, c_peer.dcap);
+    const uint2* __restrict__ in = c_peer.din[par][me] + (uint64_t)r * c_peer.dcap;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+      const uint2 d = in[i];
+      S[d.x] = (uint16_t)d.y;
+    }
+  }
+}
 
 // ---------------------------------------------------------------------------
 // per-pattern initialisation (beta.cpp:484-492 + the label test every vertex
@@ -172,8 +208,12 @@ __global__ void __launch_bounds__(kBlock) k_init_state(const uint64_t* __restric
 
 // ---------------------------------------------------------------------------
 // fused per-pattern initialisation + first-superstep signature filter (labels < 64).
-// One streaming pass over all vertices: class from the byte label, candidate test,
-// then — for candidates — the signature test documented at k_lcc_first_filter below.
+// One streaming pass over all vertices: class from the byte label, candidate test, then — for
+// candidates — the signature test.  In the first superstep every neighbour u of v sends
+// labelmask(label[u]) (ee.hpp:519-561), so heard(v) depends only on WHICH labels occur among v's
+// neighbours: heard(v) = OR { LM(l) : l in sig[v], LM(l) & NB(T_v) != 0 } — exactly what walking the
+// row would compute.  A candidate whose T_state comes out empty leaves (or never enters) the map; it
+// is settled here from 8 bytes of signature instead of its whole row (tables c_pat.req / c_pat.rl).
 // Writes cls[v] and S[v] for EVERY vertex with coalesced stores (S = 0 unless the
 // vertex survives the first superstep's cover test) and appends the survivors to the
 // frontier bin of their degree.  Their rows are walked by the first scan afterwards.
@@ -298,66 +338,6 @@ __global__ void __launch_bounds__(kBlock) k_init_filter(const uint8_t* __restric
 }
 
 // ---------------------------------------------------------------------------
-// first-superstep signature filter.  In the first superstep every neighbour u of
-// v sends labelmask(label[u]) (ee.hpp:519-561), so heard(v) depends only on WHICH
-// labels occur among v's neighbours: heard(v) = OR { LM(l) : l in sig[v],
-// LM(l) & NB(T_v) != 0 } — exactly what walking the row would compute.  A
-// candidate whose T_state comes out empty leaves (or never enters) the map; it is
-// settled here from 8 bytes of signature instead of its whole row.  Survivors go
-// to the next frontier buffer and are scanned normally (their edge maps must be
-// built from the row).  Writing S[v] = 0 here is safe: first-superstep scans
-// read neighbour classes from cls[], never S[].
-// ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) k_lcc_first_filter(LccArgs a, const unsigned long long* __restrict__ sig,
-                                                              const uint32_t* __restrict__ l0,
-                                                              const uint32_t* __restrict__ l1,
-                                                              const uint32_t* __restrict__ l2, uint32_t* n0,
-                                                              uint32_t* n1, uint32_t* n2, int cur, int nxt) {
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t c0 = a.cnt->fr_n[cur][0], c1 = a.cnt->fr_n[cur][1], c2 = a.cnt->fr_n[cur][2];
-  const uint32_t total = c0 + c1 + c2;
-  unsigned long long verts = 0;
-  constexpr int IT = 4;
-  const uint32_t tile = blockDim.x * IT;
-  for (uint32_t base = blockIdx.x * tile; base < total; base += gridDim.x * tile) {
-    bool keep[IT];
-    int bin[IT];
-    uint32_t val[IT];
-#pragma unroll
-    for (int k = 0; k < IT; ++k) {
-      const uint32_t i = base + k * blockDim.x + threadIdx.x;
-      keep[k] = false;
-      bin[k] = 0;
-      val[k] = 0;
-      if (i < total) {
-        bin[k] = i < c0 ? 0 : (i < c0 + c1 ? 1 : 2);
-        const uint32_t v = bin[k] == 0 ? l0[i] : (bin[k] == 1 ? l1[i - c0] : l2[i - c0 - c1]);
-        val[k] = v;
-        const uint32_t Tv = a.S[v];
-        const unsigned long long sg = sig[v];
-        const uint32_t NBv = nb_of(Tv);
-        uint32_t heard = 0;
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const uint32_t lm = c_pat.LMc[q];
-          if (q < c_pat.ncls && ((sg >> (c_pat.clabel[q] & 63)) & 1ull) && (lm & NBv)) heard |= lm;
-        }
-        keep[k] = cover_of(Tv, heard) != 0;
-        if (!keep[k]) {
-          a.S[v] = 0;
-          if (heard) a.cnt->nf = 1u;  // it entered the map and left it again (ee.hpp:941-946, 968-970)
-        }
-        verts++;
-      }
-    }
-    block_bin_append<IT>(keep, bin, val, n0, n1, n2, &a.cnt->fr_n[nxt][0]);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) verts += __shfl_xor_sync(0xffffffffu, verts, o);
-  if (lane == 0 && verts) atomicAdd(&a.row->filtered, verts);
-}
-
-// ---------------------------------------------------------------------------
 // scan: GROUP lanes walk the active adjacency of one vertex with uint4 loads
 // (4 slots per lane and pass), gather the neighbour masks, OR the heard masks and
 // compact the surviving neighbours to the front of the row.
@@ -392,7 +372,7 @@ __global__ void __launch_bounds__(kBlock) k_lcc_scan(LccArgs a, const uint32_t* 
     uint32_t v = 0, d = 0, Tv = 0;
     if (has) {
       v = list[idx];
-      Tv = a.S[v];
+      Tv = a.S[v + a.base];
       d = FIRST ? a.deg[v] : a.adeg[v];
       if (Tv == 0) d = 0;  // deactivated by NLCC since the last commit (beta.cpp:990-992)
     }
@@ -490,7 +470,7 @@ __global__ void __launch_bounds__(1024) k_lcc_scan_big(LccArgs a, const uint32_t
   for (uint32_t idx = blockIdx.x; idx < n; idx += gridDim.x) {
     __syncthreads();
     const uint32_t v = list[idx];
-    const uint32_t Tv = a.S[v];
+    const uint32_t Tv = a.S[v + a.base];
     uint32_t d = FIRST ? a.deg[v] : a.adeg[v];
     if (Tv == 0) d = 0;
     const uint32_t NBv = nb_of(Tv);
@@ -596,16 +576,22 @@ __global__ void __launch_bounds__(kBlock) k_lcc_commit(LccArgs a, const uint32_t
       alive[k] = false;
       bin[k] = 0;
       val[k] = 0;
+      bool changed = false;
+      uint32_t cslot = 0, cmask = 0;
       if (i < total) {
         const uint32_t v = i < c0 ? l0[i] : (i < c0 + c1 ? l1[i - c0] : l2[i - c0 - c1]);
         const uint16_t ts = a.Tst[v];
-        a.S[v] = ts;
+        if (c_peer.G > 1) changed = ts != a.S[v + a.base];  // peers only need the changes
+        a.S[v + a.base] = ts;
+        cslot = v + a.base;
+        cmask = ts;
         alive[k] = ts != 0;
         const uint32_t d = a.adeg[v];
         if (alive[k]) { nv++; ne += d; }
         bin[k] = d <= PM_SMALL_MAX ? 0 : (d <= PM_MID_MAX ? 1 : 2);
         val[k] = v;
       }
+      if (c_peer.G > 1) publish_mask(changed, cslot, cmask, a.cnt, a.par);
     }
     block_bin_append<IT>(alive, bin, val, n0, n1, n2, &a.cnt->fr_n[nxt][0]);
   }
@@ -632,7 +618,7 @@ __global__ void __launch_bounds__(kBlock) k_count_alive(LccArgs a, const uint32_
   unsigned long long nv = 0, ne = 0;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const uint32_t v = i < c0 ? l0[i] : (i < c0 + c1 ? l1[i - c0] : l2[i - c0 - c1]);
-    if (a.S[v]) { nv++; ne += a.adeg[v]; }
+    if (a.S[v + a.base]) { nv++; ne += a.adeg[v]; }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {

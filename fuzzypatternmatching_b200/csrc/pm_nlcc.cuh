@@ -56,6 +56,9 @@ struct NlcArgs {
   uint2* matches;      // TDS: (token index at the penultimate level, final vertex)
   uint64_t match_cap;
   DevCounters* cnt;
+  uint32_t base;       // first slot of this rank (rank-local arrays: index slot - base)
+  int par;             // multi-GPU: token inbox written in this hop (the previous hop's is par ^ 1)
+  const StepMsg* all;  // multi-GPU: everyone's StepMsg of the previous hop
 };
 
 __device__ __forceinline__ bool hop_ok(uint32_t su, uint32_t cu, int h) {
@@ -164,13 +167,14 @@ __global__ void __launch_bounds__(kBlock) k_nlcc_sources(NlcArgs a, const uint32
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t c0 = a.cnt->fr_n[cur][0], c1 = a.cnt->fr_n[cur][1], c2 = a.cnt->fr_n[cur][2];
   const uint32_t total = c0 + c1 + c2;
+  const bool multi = c_peer.G > 1;
   uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u;
   for (; i0 < total; i0 += gridDim.x * blockDim.x) {
     const uint32_t i = i0 + lane;
     bool is_src = false;
     uint32_t v = 0;
     if (i < total) {
-      v = i < c0 ? l0[i] : (i < c0 + c1 ? l1[i - c0] : l2[i - c0 - c1]);
+      v = (i < c0 ? l0[i] : (i < c0 + c1 ? l1[i - c0] : l2[i - c0 - c1])) + a.base;  // slot
       const uint32_t T = a.S[v];
       is_src = T != 0 && hop_ok(T, a.cls[v], 0);
       // path checking starts only from vertices that match BOTH end points (nem_1.hpp:447-451)
@@ -185,8 +189,19 @@ __global__ void __launch_bounds__(kBlock) k_nlcc_sources(NlcArgs a, const uint32
         const uint32_t pos = base + __popc(m & lanemask_lt());
         a.src_list[pos] = v;
         a.ok[v] = 0;
-        // level 0 of the token pool; n_src never exceeds V <= pool_cap
-        a.pool[pos] = tds ? make_uint2(0xFFFFFFFFu, v) : make_uint2(v, v);
+        if (!multi) {
+          // level 0 of the token pool; n_src never exceeds V <= pool_cap
+          a.pool[pos] = tds ? make_uint2(0xFFFFFFFFu, v) : make_uint2(v, v);
+        } else if (!tds) {
+          // level 0 = my own region of my token inbox
+          if (pos < c_peer.tcap) c_peer.tin[a.par][c_peer.rank][(unsigned long long)c_peer.rank * c_peer.tcap + pos] = make_uint2(v, v);
+          else a.cnt->overflow = 1u;
+        } else {
+          const unsigned long long n = (unsigned long long)c_nlc.n;
+          if (pos < c_peer.tcap * 2ull / n)
+            reinterpret_cast<uint32_t*>(c_peer.tin[a.par][c_peer.rank])[(unsigned long long)c_peer.rank * c_peer.tcap * 2ull + pos * n] = v;
+          else a.cnt->overflow = 1u;
+        }
       }
     }
   }
@@ -209,6 +224,10 @@ __global__ void k_nlcc_begin(DevCounters* cnt) {
   cnt->lvl[0] = 0;
   cnt->lvl[1] = cnt->n_src;
   cnt->pool_n = cnt->n_src;
+  if (c_peer.G > 1) {  // the sources are level 0 of my own inbox region
+    cnt->pool_n = 0;
+    cnt->out_n[c_peer.rank] = cnt->n_src;
+  }
 }
 // after the expand kernel that produced level h
 __global__ void k_nlcc_close_level(DevCounters* cnt, int h, unsigned long long pool_cap) {
@@ -541,15 +560,23 @@ __global__ void k_tds_materialize(const uint2* __restrict__ pool, const uint2* _
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock) k_nlcc_apply(uint16_t* __restrict__ S, const uint8_t* __restrict__ ok,
                                                         const uint32_t* __restrict__ src_list,
-                                                        DevCounters* cnt) {
+                                                        DevCounters* cnt, int par) {
   const uint32_t n = cnt->n_src;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const uint32_t s = src_list[i];
-    if (ok[s]) continue;
-    const uint32_t T = S[s];
-    if (T == 0) continue;
-    S[s] = (uint16_t)(T & ~(1u << c_nlc.I[0]));
-    cnt->deleted = 1u;
+  const uint32_t nr = (n + 31u) & ~31u;  // whole warps: publish_mask is warp collective
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nr; i += gridDim.x * blockDim.x) {
+    bool changed = false;
+    uint32_t s = 0, T2 = 0;
+    if (i < n) {
+      s = src_list[i];
+      const uint32_t T = S[s];
+      if (!ok[s] && T != 0) {
+        T2 = T & ~(1u << c_nlc.I[0]);
+        S[s] = (uint16_t)T2;
+        cnt->deleted = 1u;
+        changed = T2 != T;
+      }
+    }
+    if (c_peer.G > 1) publish_mask(changed, s, T2, cnt, par);
   }
 }
 

@@ -1,0 +1,337 @@
+// pm_nlcc_multi.cuh — NLCC token walks across GPUs (1-D partition, see PeerTab in pm_common.cuh).
+//
+// The reference routes every token visitor through the mailbox to the rank that owns the target
+// vertex, where pre_visit applies the acceptance tests and the work-aggregation set
+// (token_passing_pattern_matching_nonunique_nem_1.hpp:98-303; visitor_queue.hpp:395-434).  Here a hop
+// is one kernel per GPU: the sender applies every test that needs only replicated state (label stream,
+// template bit of the replicated mask array S) and stores the surviving token STRAIGHT into its region
+// of the owner's token inbox over NVLink; the owner applies the (vertex, source) aggregation when it
+// picks the token up at the start of the next hop — the order the reference uses.  Region fill counts
+// are local counters that travel in the per-hop StepMsg all-gather, so there are no remote atomics.
+// Acknowledgements (token_source_map[s] = 1, nem_1.hpp:326-342) are single-byte stores into the
+// owner's `ok` array; the edge flag of a successful cycle (nem_1.hpp:764-770) is a remote atomicOr.
+//   TDS (tds_batch_1.hpp): a token record carries its visited history (the reference's
+//   visited_vertices array, :964) — `n` words per record — because parent links cannot cross GPUs.
+#pragma once
+
+#include "pm_nlcc.cuh"
+
+namespace pm {
+
+struct TokSrc {  // the tokens that arrived for this rank in the previous hop: G regions of the inbox
+  unsigned long long n[PM_MAX_RANKS];
+  unsigned long long total;
+};
+
+__device__ __forceinline__ TokSrc tok_src(const NlcArgs& a) {
+  TokSrc t;
+  t.total = 0;
+#pragma unroll
+  for (int r = 0; r < PM_MAX_RANKS; ++r) {
+    unsigned long long n = r < c_peer.G ? a.all[r].out_n[c_peer.rank] : 0ull;
+    t.n[r] = n;
+    t.total += n;
+  }
+  return t;
+}
+
+// index within the concatenation of the regions -> element index in the inbox (in units of records)
+__device__ __forceinline__ unsigned long long tok_locate(const TokSrc& ts, unsigned long long t, unsigned long long region_cap) {
+  int r = 0;
+#pragma unroll
+  for (int q = 0; q < PM_MAX_RANKS - 1; ++q)
+    if (r == q && t >= ts.n[q]) { t -= ts.n[q]; r = q + 1; }
+  return (unsigned long long)r * region_cap + t;
+}
+
+__device__ __forceinline__ void ack_source(const NlcArgs& a, uint32_t s) {
+  if (a.ok[s]) return;  // own source, or already acknowledged from this GPU
+  a.ok[s] = 1;
+  const uint32_t o = s / c_peer.nlmax;
+  if ((int)o != c_peer.rank) c_peer.ok[o][s] = 1;
+}
+
+// flag E_s[parent] at the owner of s (nem_1.hpp:764-770)
+__device__ __forceinline__ void mark_edge_m(uint32_t s, uint32_t parent) {
+  const uint32_t o = s / c_peer.nlmax, li = s - o * c_peer.nlmax;
+  const uint64_t row = (uint64_t)c_peer.rowblk[o][li] * 8;
+  const uint32_t d = c_peer.adeg[o][li];
+  uint32_t* __restrict__ cw = c_peer.colw[o];
+  uint32_t lo = 0, hi = d;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    const uint32_t x = cw[row + mid] & PM_IDMASK;
+    if (x < parent) lo = mid + 1; else hi = mid;
+  }
+  if (lo < d && (cw[row + lo] & PM_IDMASK) == parent) atomicOr(&cw[row + lo], 0x80000000u);
+}
+
+// One warp appends its accepted tokens to the inbox regions of their owners.  All 32 lanes call.
+// Positions come from this rank's own counters (cnt->out_n[g]); the stores go over NVLink.
+__device__ __forceinline__ void route_tokens(const NlcArgs& a, const bool (&flag)[4], const uint32_t (&u)[4], uint32_t s) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t lt = (1u << lane) - 1u;
+  uint32_t dest[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) dest[k] = flag[k] ? u[k] / c_peer.nlmax : 0xFFFFFFFFu;
+  for (int g = 0; g < c_peer.G; ++g) {
+    uint32_t m[4], total = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      m[k] = __ballot_sync(0xffffffffu, dest[k] == (uint32_t)g);
+      total += __popc(m[k]);
+    }
+    if (total == 0) continue;
+    // order inside the warp: (k, lane)
+    unsigned long long basep = 0;
+    if (lane == 0) basep = atomicAdd(&a.cnt->out_n[g], (unsigned long long)total);
+    basep = __shfl_sync(0xffffffffu, basep, 0);
+    uint32_t before = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (dest[k] == (uint32_t)g) {
+        const unsigned long long pos = basep + before + __popc(m[k] & lt);
+        if (pos < c_peer.tcap) c_peer.tin[a.par][g][(unsigned long long)c_peer.rank * c_peer.tcap + pos] = make_uint2(u[k], s);
+        else a.cnt->overflow = 1u;
+      }
+      before += __popc(m[k]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// nem_1 across GPUs: tokens of the previous hop (inbox `par ^ 1`) -> hop hn (inbox `par` of the owners)
+//   MODE 0: interior hop, 1: final hop of a path or (generic) cycle constraint, 2: closing two hops of a cycle
+//   first: the tokens are the sources themselves (no aggregation test)
+// ---------------------------------------------------------------------------
+template <int MODE, bool STREAM>
+__global__ void __launch_bounds__(kBlock) k_nem1_hop_m(NlcArgs a, int hn, int first) {
+  const TokSrc src = tok_src(a);
+  const uint2* __restrict__ in = c_peer.tin[a.par ^ 1][c_peer.rank];
+  constexpr int GROUP = 8;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t gl = lane % GROUP, gw = lane / GROUP;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  const uint32_t want_lab = c_nlc.lab[hn];
+  const uint32_t nlmax = c_peer.nlmax;
+  unsigned long long fan = 0, accepted = 0;
+  for (uint64_t base = warp * 4; base < src.total; base += nwarps * 4) {
+    const uint64_t t = base + gw;
+    bool has = t < src.total;
+    uint32_t v = 0, s = 0, d = 0, ds = 0;
+    uint64_t rs = 0;
+    uint32_t os = 0;
+    uint32_t fresh = 1;
+    if (has) {
+      const uint2 tk = in[tok_locate(src, t, c_peer.tcap)];
+      v = tk.x;
+      s = tk.y;
+      // work aggregation at the receiver: one token per (vertex, source) (nem_1.hpp:131-139, 270-285)
+      if (!first && gl == 0) fresh = hset_insert(a, v, s) ? 1u : 0u;
+    }
+    fresh = __shfl_sync(0xffffffffu, fresh, gw * GROUP);
+    if (!fresh) has = false;
+    if (has) {
+      d = a.adeg[v - a.base];
+      if (gl == 0) accepted++;
+      if (MODE == 1 && !c_nlc.valid_cycle && a.ok[s]) d = 0;  // acknowledged path source: later tokens are moot
+      if (MODE == 2) {
+        const uint32_t ss = a.S[s];
+        if (ss != 0 && hop_ok(ss, a.cls[s], hn + 1)) {  // receiver tests of the closing hop at the source
+          os = s / nlmax;
+          const uint32_t li = s - os * nlmax;
+          ds = c_peer.adeg[os][li];
+          rs = (uint64_t)c_peer.rowblk[os][li] * 8;
+        } else {
+          d = 0;
+        }
+      }
+    }
+    const uint64_t row = has ? (uint64_t)a.rowblk[v - a.base] * 8 : 0;
+    const uint32_t passes = (d + GROUP * 4 - 1) / (GROUP * 4);
+    const uint32_t maxp = __reduce_max_sync(0xffffffffu, passes);
+    for (uint32_t p = 0; p < maxp; ++p) {
+      const uint32_t j0 = p * GROUP * 4 + gl * 4;
+      uint4 q = make_uint4(0, 0, 0, 0);
+      uint32_t l4 = 0;
+      if (j0 < d) {
+        q = *reinterpret_cast<const uint4*>(a.colw + row + j0);
+        if (STREAM) l4 = *reinterpret_cast<const uint32_t*>(a.labw + row + j0);
+      }
+      const uint32_t u[4] = {q.x & PM_IDMASK, q.y & PM_IDMASK, q.z & PM_IDMASK, q.w & PM_IDMASK};
+      bool pass[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        pass[k] = false;
+        bool may = j0 + k < d;
+        if (STREAM) may = may && ((l4 >> (8 * k)) & 0xffu) == want_lab;
+        if (MODE == 2) may = may && u[k] != s;
+        if (!may) continue;
+        uint32_t b = 0;
+        if (MODE == 2) {  // u must also be a neighbour of the source (row of s, possibly on a peer)
+          const uint32_t* __restrict__ cs = c_peer.colw[os];
+          uint32_t e = ds;
+          while (b < e) {
+            const uint32_t mid = (b + e) >> 1;
+            const uint32_t x = cs[rs + mid] & PM_IDMASK;
+            if (x < u[k]) b = mid + 1; else e = mid;
+          }
+          if (b >= ds || (cs[rs + b] & PM_IDMASK) != u[k]) continue;
+        }
+        const uint32_t su = a.S[u[k]];
+        pass[k] = su != 0 && ((su >> c_nlc.I[hn]) & 1u) && (STREAM || a.cls[u[k]] == c_nlc.cls[hn]);
+        if (MODE == 2 && pass[k]) {
+          ack_source(a, s);
+          a.cnt->found = 1u;
+          atomicOr(&c_peer.colw[os][rs + b], 0x80000000u);
+        }
+      }
+      if (MODE == 1) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const bool succ = pass[k] && (c_nlc.valid_cycle ? u[k] == s : u[k] != s);
+          if (succ) {
+            ack_source(a, s);
+            a.cnt->found = 1u;
+            if (c_nlc.valid_cycle) mark_edge_m(s, v);
+          }
+        }
+      } else if (MODE == 0) {
+        bool ins[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ins[k] = pass[k] && u[k] != s;  // the source cannot relay (nem_1.hpp:174-177)
+        // one source per group: lanes of a group share s, lanes of different groups do not
+        route_tokens(a, ins, u, s);
+      }
+    }
+    if (has && gl == 0) fan += d;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    fan += __shfl_xor_sync(0xffffffffu, fan, o);
+    accepted += __shfl_xor_sync(0xffffffffu, accepted, o);
+  }
+  if (lane == 0 && fan) atomicAdd(&a.cnt->fanout, fan);
+  if (lane == 0 && accepted) atomicAdd(&a.cnt->pool_n, accepted);
+}
+
+// ---------------------------------------------------------------------------
+// TDS across GPUs.  A record is `n` words: hist[0..h] = the walk so far (h = hn - 1).
+// Completed walks (FINAL) are records of n words routed to the owner of the last vertex, which is
+// where the reference writes the subgraph line (tds_batch_1.hpp:684-693).
+// ---------------------------------------------------------------------------
+template <bool FINAL, bool STREAM>
+__global__ void __launch_bounds__(kBlock) k_tds_hop_m(NlcArgs a, int hn) {
+  const TokSrc src = tok_src(a);
+  const int n = c_nlc.n;
+  const unsigned long long rcap = c_peer.tcap * 2ull / (unsigned long long)n;  // records per region
+  const uint32_t* __restrict__ in = reinterpret_cast<const uint32_t*>(c_peer.tin[a.par ^ 1][c_peer.rank]);
+  const uint32_t want_lab = c_nlc.lab[hn];
+  constexpr int GROUP = 8;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t gl = lane % GROUP, gw = lane / GROUP;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  const int h = hn - 1;
+  unsigned long long fan = 0, accepted = 0;
+  for (uint64_t base = warp * 4; base < src.total; base += nwarps * 4) {
+    const uint64_t t = base + gw;
+    const bool has = t < src.total;
+    uint32_t hist[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) hist[i] = 0xFFFFFFFFu;
+    uint32_t v = 0, d = 0;
+    if (has) {
+      // region r starts at byte offset r * tcap * 8 whatever the record width
+      TokSrc tmp = src;
+      unsigned long long tt = t;
+      int r = 0;
+#pragma unroll
+      for (int q = 0; q < PM_MAX_RANKS - 1; ++q)
+        if (r == q && tt >= tmp.n[q]) { tt -= tmp.n[q]; r = q + 1; }
+      const uint32_t* rec = in + (unsigned long long)r * c_peer.tcap * 2ull + tt * (unsigned long long)n;
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (i <= h) hist[i] = rec[i];
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (i == h) v = hist[i];
+      d = a.adeg[v - a.base];
+      if (gl == 0) accepted++;
+    }
+    const uint32_t s = hist[0];
+    const uint64_t row = has ? (uint64_t)a.rowblk[v - a.base] * 8 : 0;
+    const uint32_t passes = (d + GROUP * 4 - 1) / (GROUP * 4);
+    const uint32_t maxp = __reduce_max_sync(0xffffffffu, passes);
+    for (uint32_t p = 0; p < maxp; ++p) {
+      const uint32_t j0 = p * GROUP * 4 + gl * 4;
+      uint4 q = make_uint4(0, 0, 0, 0);
+      uint32_t l4 = 0;
+      if (j0 < d) {
+        q = *reinterpret_cast<const uint4*>(a.colw + row + j0);
+        if (STREAM) l4 = *reinterpret_cast<const uint32_t*>(a.labw + row + j0);
+      }
+      const uint32_t u[4] = {q.x & PM_IDMASK, q.y & PM_IDMASK, q.z & PM_IDMASK, q.w & PM_IDMASK};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        bool acc = false;
+        bool may = j0 + k < d;
+        if (STREAM) may = may && ((l4 >> (8 * k)) & 0xffu) == want_lab;
+        if (may) {
+          const uint32_t su = a.S[u[k]];
+          acc = su != 0 && ((su >> c_nlc.I[hn]) & 1u) && (STREAM || a.cls[u[k]] == c_nlc.cls[hn]);
+          if (acc) {
+            if (FINAL) acc = c_nlc.valid_cycle ? (u[k] == s) : (u[k] != s && hist_rule(hist, hn, u[k]));
+            else acc = hist_rule(hist, hn, u[k]);
+          }
+        }
+        // records are rare compared with nem_1 tokens: one reservation per record
+        if (acc) {
+          const uint32_t g = u[k] / c_peer.nlmax;
+          const unsigned long long pos = atomicAdd(&a.cnt->out_n[g], 1ull);
+          if (pos < rcap) {
+            uint32_t* out = reinterpret_cast<uint32_t*>(c_peer.tin[a.par][g]) +
+                            (unsigned long long)c_peer.rank * c_peer.tcap * 2ull + pos * (unsigned long long)n;
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (i <= h) out[i] = hist[i];
+            out[hn] = u[k];
+          } else {
+            a.cnt->overflow = 1u;
+          }
+          if (FINAL) {  // walk completed (tds_batch_1.hpp:664-694, 699-750)
+            ack_source(a, s);
+            a.cnt->found = 1u;
+          }
+        }
+      }
+    }
+    if (has && gl == 0) fan += d;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    fan += __shfl_xor_sync(0xffffffffu, fan, o);
+    accepted += __shfl_xor_sync(0xffffffffu, accepted, o);
+  }
+  if (lane == 0 && fan) atomicAdd(&a.cnt->fanout, fan);
+  if (lane == 0 && accepted) atomicAdd(&a.cnt->pool_n, accepted);
+}
+
+// gathers the completed walks that arrived for this rank into one dense row array
+__global__ void k_tds_collect_m(NlcArgs a, int n, uint32_t* __restrict__ rows_out) {
+  const TokSrc src = tok_src(a);
+  const uint32_t* __restrict__ in = reinterpret_cast<const uint32_t*>(c_peer.tin[a.par ^ 1][c_peer.rank]);
+  for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < src.total;
+       t += (unsigned long long)gridDim.x * blockDim.x) {
+    unsigned long long tt = t;
+    int r = 0;
+#pragma unroll
+    for (int q = 0; q < PM_MAX_RANKS - 1; ++q)
+      if (r == q && tt >= src.n[q]) { tt -= src.n[q]; r = q + 1; }
+    const uint32_t* rec = in + (unsigned long long)r * c_peer.tcap * 2ull + tt * (unsigned long long)n;
+    for (int i = 0; i < n; ++i) rows_out[t * n + i] = rec[i];
+  }
+}
+
+}  // namespace pm

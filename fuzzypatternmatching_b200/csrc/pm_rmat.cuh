@@ -106,13 +106,15 @@ __device__ __forceinline__ void d_rmat_edge(const uint32_t* __restrict__ draws, 
 #define PM_MT_M 397
 
 // one CTA per generating rank; scratch: gridDim.x slabs of 624 * 5 * scale words
-__global__ void __launch_bounds__(256) k_rmat_stream(int scale, uint64_t per_rank, uint32_t* __restrict__ scratch,
+// (with several GPUs, GPU g generates the streams of the generating ranks r = blockIdx.x * n_gpus + g)
+__global__ void __launch_bounds__(256) k_rmat_stream(int scale, uint64_t per_rank, uint32_t first_rank,
+                                                      uint32_t rank_stride, uint32_t* __restrict__ scratch,
                                                       uint32_t* __restrict__ src, uint32_t* __restrict__ dst) {
   __shared__ uint32_t xa[PM_MT_N], xb[PM_MT_N];
-  const uint32_t r = blockIdx.x;
+  const uint32_t r = first_rank + blockIdx.x * rank_stride;
   const int tid = threadIdx.x;
   const int dpe = 5 * scale;  // draws per edge
-  uint32_t* slab = scratch + (uint64_t)r * PM_MT_N * dpe;
+  uint32_t* slab = scratch + (uint64_t)blockIdx.x * PM_MT_N * dpe;
   if (tid == 0) {  // mt19937 seeding, seed = 5489 + 3 * rank (generate_rmat.cpp:202)
     uint32_t x = 5489u + 3u * r;
     xa[0] = x;
@@ -165,7 +167,7 @@ __global__ void __launch_bounds__(256) k_rmat_stream(int scale, uint64_t per_ran
       if (e < per_rank) {
         uint32_t u, v;
         d_rmat_edge(slab + (uint64_t)i * dpe, scale, u, v);
-        const uint64_t o = 2 * ((uint64_t)r * per_rank + e);
+        const uint64_t o = 2 * ((uint64_t)blockIdx.x * per_rank + e);
         src[o] = u; dst[o] = v;          // generated edge
         src[o + 1] = v; dst[o + 1] = u;  // reversed copy (rmat_edge_generator.hpp:126-139)
       }
@@ -180,14 +182,20 @@ inline int rmat_slots_device(pm_ctx* c, uint64_t scale, uint64_t gen_ranks, uint
   if (gen_ranks == 0 || gen_ranks > 65535) return fail(c, PM_ERR_ARG, "gen_ranks must be in 1..65535");
   const uint64_t V = 1ull << scale;
   const uint64_t per_rank = V * 16 / gen_ranks;  // generate_rmat.cpp:201
-  const uint64_t n = 2 * per_rank * gen_ranks;
+  // this GPU's share of the generating ranks
+  const uint64_t G = c->n_ranks;
+  const uint64_t mine = gen_ranks / G + ((uint64_t)c->rank < gen_ranks % G ? 1 : 0);
+  const uint64_t n = 2 * per_rank * mine;
   int rc;
   uint32_t* scratch = nullptr;
   if ((rc = dev_alloc(c, d_src, n))) return rc;
   if ((rc = dev_alloc(c, d_dst, n))) { dev_free(*d_src); return rc; }
-  if ((rc = dev_alloc(c, &scratch, gen_ranks * (uint64_t)PM_MT_N * 5 * scale))) { dev_free(*d_src); dev_free(*d_dst); return rc; }
-  k_rmat_stream<<<(unsigned)gen_ranks, 256, 0, c->stream>>>((int)scale, per_rank, scratch, *d_src, *d_dst);
-  c->launches++;
+  if ((rc = dev_alloc(c, &scratch, mine * (uint64_t)PM_MT_N * 5 * scale))) { dev_free(*d_src); dev_free(*d_dst); return rc; }
+  if (mine) {
+    k_rmat_stream<<<(unsigned)mine, 256, 0, c->stream>>>((int)scale, per_rank, (uint32_t)c->rank, (uint32_t)G, scratch,
+                                                         *d_src, *d_dst);
+    c->launches++;
+  }
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
   dev_free(scratch);
@@ -201,7 +209,7 @@ inline int rmat_build(pm_ctx* c, uint64_t scale, uint64_t gen_ranks) {
   uint64_t n = 0;
   int rc = rmat_slots_device(c, scale, gen_ranks, &d_src, &d_dst, &n);
   if (rc) return rc;
-  rc = graph_build_from_device_slots(c, 1ull << scale, n, d_src, d_dst);
+  rc = graph_build_from_device_slots(c, 1ull << scale, n, d_src, d_dst, /*route=*/true);
   dev_free(d_src);
   dev_free(d_dst);
   return rc;

@@ -12,9 +12,11 @@
 #include <map>
 
 #include "pm_common.cuh"
+#include "pm_comm.cuh"
 #include "pm_graph.cuh"
 #include "pm_lcc.cuh"
 #include "pm_nlcc.cuh"
+#include "pm_nlcc_multi.cuh"
 #include "pm_rmat.cuh"
 
 using namespace pm;
@@ -39,6 +41,8 @@ LccArgs lcc_args(pm_ctx* c, int row) {
   a.lab0 = c->lab0; a.labw = c->labw;
   a.row = c->rowstat + row;
   a.bin = 0;
+  a.base = (uint32_t)(c->nlmax * c->rank);
+  a.par = c->step_parity;
   return a;
 }
 
@@ -48,10 +52,49 @@ NlcArgs nlc_args(pm_ctx* c, uint2* matches, uint64_t match_cap) {
   a.ok = c->ok; a.src_list = c->src_list; a.hset = c->hset; a.hset_mask = c->hset_use - 1;
   a.pool = c->pool; a.pool_cap = c->pool_cap; a.matches = matches; a.match_cap = match_cap;
   a.cnt = c->cnt;
+  a.base = (uint32_t)(c->nlmax * c->rank);
+  a.par = c->step_parity;
+  a.all = c->step_msg ? c->step_msg + 1 : nullptr;
   return a;
 }
 
+// number of vertices this rank owns (owner(v) = v mod G)
+uint64_t n_owned(const pm_ctx* c) {
+  return c->n_ranks == 1 ? c->V : (c->V + c->n_ranks - 1 - c->rank) / c->n_ranks;
+}
+
+// (Re)publishes every buffer the peers address directly and uploads the peer table.  Collective.
+int comm_publish(pm_ctx* c) {
+  comm_close_all(c);
+  PeerTab& t = c->peers;
+  std::memset(&t, 0, sizeof(t));
+  t.G = c->n_ranks; t.rank = c->rank; t.nlmax = (uint32_t)c->nlmax; t.base = (uint32_t)(c->nlmax * c->rank);
+  t.dcap = (uint32_t)c->dcap; t.tcap = c->tcap;
+  void* out[PM_MAX_RANKS];
+  int rc;
+#define PM_SHARE(buf, field, T)                                              \
+  if (buf) {                                                                 \
+    if ((rc = comm_share(c, (void*)(buf), out))) return rc;                  \
+    for (int g = 0; g < c->n_ranks; ++g) t.field[g] = (T)out[g];             \
+  }
+  PM_SHARE(c->rowblk, rowblk, const uint32_t*)
+  PM_SHARE(c->adeg, adeg, const uint32_t*)
+  PM_SHARE(c->colw, colw, uint32_t*)
+  PM_SHARE(c->ok, ok, uint8_t*)
+  PM_SHARE(c->din[0], din[0], uint2*)
+  PM_SHARE(c->din[1], din[1], uint2*)
+  PM_SHARE(c->tin[0], tin[0], uint2*)
+  PM_SHARE(c->tin[1], tin[1], uint2*)
+#undef PM_SHARE
+  return comm_upload_peers(c);
+}
+
 void state_free(pm_ctx* c) {
+  comm_close_all(c);  // nobody may still map the buffers freed below
+  dev_free(c->din[0]); dev_free(c->din[1]); dev_free(c->tin[0]); dev_free(c->tin[1]); dev_free(c->step_msg);
+  if (c->h_step) cudaFreeHost(c->h_step);
+  c->h_step = nullptr;
+  c->dcap = c->tcap = 0;
   dev_free(c->S); dev_free(c->Tst); dev_free(c->adeg); dev_free(c->cls);
   for (int b = 0; b < 2; ++b) for (int k = 0; k < 3; ++k) dev_free(c->fr[b][k]);
   dev_free(c->cnt); dev_free(c->rowstat); dev_free(c->ok); dev_free(c->src_list);
@@ -75,17 +118,34 @@ bool nem1_order_independent(const Constraint& k) {
   return true;
 }
 
+// Token storage for one constraint.  One rank: the token pool.  Several ranks: the two token inboxes
+// (G sender regions of pool_cap tokens each), which every peer must map — growing them is collective,
+// so the callers agree on pool_cap first.
 int nlcc_reserve(pm_ctx* c, uint64_t pool_cap) {
   if (pool_cap <= c->pool_cap) return 0;
+  const bool multi = c->n_ranks > 1;
+  if (multi) comm_close_all(c);
   dev_free(c->pool);
   dev_free(c->hset);
+  dev_free(c->tin[0]);
+  dev_free(c->tin[1]);
+  c->pool_cap = c->hset_cap = c->tcap = 0;
   uint64_t hc = 1;
   while (hc < 2 * pool_cap) hc <<= 1;
   int rc;
-  if ((rc = dev_alloc(c, &c->pool, pool_cap))) { c->pool_cap = c->hset_cap = 0; return rc; }
-  if ((rc = dev_alloc(c, &c->hset, hc))) { c->pool_cap = c->hset_cap = 0; return rc; }
+  if (!multi) {
+    if ((rc = dev_alloc(c, &c->pool, pool_cap))) return rc;
+  } else {
+    if ((rc = dev_alloc(c, &c->tin[0], pool_cap * c->n_ranks))) return rc;
+    if ((rc = dev_alloc(c, &c->tin[1], pool_cap * c->n_ranks))) return rc;
+  }
+  if ((rc = dev_alloc(c, &c->hset, hc))) return rc;
   c->pool_cap = pool_cap;
   c->hset_cap = hc;
+  if (multi) {
+    c->tcap = pool_cap;
+    if ((rc = comm_publish(c))) return rc;
+  }
   return 0;
 }
 
@@ -117,8 +177,14 @@ void pm_destroy(pm_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  // ranks may be destroyed at different times: unmap without the collective barrier
+  for (void* p : c->ipc_open) cudaIpcCloseMemHandle(p);
+  c->ipc_open.clear();
+  ncclComm_t comm = comm_of(c);
+  c->comm = nullptr;
   state_free(c);
   graph_free(c);
+  if (comm) ncclCommDestroy(comm);
   for (auto e : c->events) cudaEventDestroy(e);
   for (int b = 0; b < 4; ++b) for (int k = 0; k < 2; ++k) if (c->kev[b][k]) cudaEventDestroy(c->kev[b][k]);
   cudaStreamDestroy(c->stream);
@@ -129,12 +195,31 @@ const char* pm_last_error(const pm_ctx* c) { return c ? c->err.c_str() : "null c
 uint64_t pm_kernel_launches(const pm_ctx* c) { return c ? c->launches : 0; }
 
 int pm_comm_unique_id(char id_out[PM_COMM_ID_BYTES]) {
+  static_assert(sizeof(ncclUniqueId) <= PM_COMM_ID_BYTES, "PM_COMM_ID_BYTES too small");
   std::memset(id_out, 0, PM_COMM_ID_BYTES);
-  return PM_ERR_UNSUPPORTED;
+  if (!pm::dyn::api().ok) return PM_ERR_COMM;  // libnccl.so.2 not found
+  ncclUniqueId id;
+  if (ncclGetUniqueId(&id) != ncclSuccess) return PM_ERR_COMM;
+  std::memcpy(id_out, &id, sizeof(id));
+  return 0;
 }
-int pm_comm_init(pm_ctx* c, int rank, int n_ranks, const char*) {
-  if (n_ranks == 1 && rank == 0) return 0;
-  return fail(c, PM_ERR_UNSUPPORTED, "multi-GPU partitioning is not built into this library yet");
+
+int pm_comm_init(pm_ctx* c, int rank, int n_ranks, const char* id_bytes) {
+  if (!c || rank < 0 || n_ranks < 1 || rank >= n_ranks) return fail(c, PM_ERR_ARG, "pm_comm_init: bad rank");
+  if (c->has_graph) return fail(c, PM_ERR_ARG, "pm_comm_init must precede the graph");
+  if (n_ranks > PM_MAX_RANKS) return fail(c, PM_ERR_UNSUPPORTED, "at most 8 ranks (the GPUs of one NVSwitch box)");
+  if (n_ranks == 1) { c->rank = 0; c->n_ranks = 1; return 0; }
+  if (!id_bytes) return fail(c, PM_ERR_ARG, "pm_comm_init: null id");
+  if (!pm::dyn::api().ok) return fail(c, PM_ERR_COMM, "libnccl.so.2 could not be loaded");
+  PM_CUDA(c, cudaSetDevice(c->device));
+  ncclUniqueId id;
+  std::memcpy(&id, id_bytes, sizeof(id));
+  ncclComm_t comm = nullptr;
+  PM_NCCL(c, ncclCommInitRank(&comm, n_ranks, id, rank));
+  c->comm = comm;
+  c->rank = rank;
+  c->n_ranks = n_ranks;
+  return 0;
 }
 
 // ------------------------------------------------------------------ graph
@@ -153,7 +238,7 @@ int pm_graph_from_slots(pm_ctx* c, uint64_t n_vertices, uint64_t n_slots, const 
     dev_free(d_src); dev_free(d_dst);
     return fail(c, PM_ERR_CUDA, "pm_graph_from_slots: host to device copy failed");
   }
-  rc = graph_build_from_device_slots(c, n_vertices, n_slots, d_src, d_dst);
+  rc = graph_build_from_device_slots(c, n_vertices, n_slots, d_src, d_dst, /*route=*/false);
   dev_free(d_src);
   dev_free(d_dst);
   return rc;
@@ -161,11 +246,28 @@ int pm_graph_from_slots(pm_ctx* c, uint64_t n_vertices, uint64_t n_slots, const 
 
 int pm_graph_from_csr(pm_ctx* c, uint64_t n_vertices, const uint64_t* rowptr, const uint32_t* col,
                       const uint64_t* degree_multi) {
-  if (!c || !rowptr || !degree_multi || (rowptr[n_vertices] && !col))
-    return fail(c, PM_ERR_ARG, "pm_graph_from_csr: null argument");
+  if (!c || !rowptr || !degree_multi) return fail(c, PM_ERR_ARG, "pm_graph_from_csr: null argument");
   PM_CUDA(c, cudaSetDevice(c->device));
   state_free(c);
-  return graph_build_from_host_csr(c, n_vertices, rowptr, col, degree_multi);
+  if (c->n_ranks == 1) {
+    if (rowptr[n_vertices] && !col) return fail(c, PM_ERR_ARG, "pm_graph_from_csr: null argument");
+    return graph_build_from_host_csr(c, n_vertices, rowptr, col, degree_multi);
+  }
+  // several ranks: rowptr / col / degree_multi describe the rows of the vertices THIS rank owns
+  // (local row i = vertex i * n_ranks + rank); the rows are re-keyed by slot through the sort based build
+  c->V = n_vertices;
+  const uint64_t own = n_owned(c), E = rowptr[own];
+  std::vector<uint32_t> src(E), dst(E);
+  for (uint64_t i = 0; i < own; ++i)
+    for (uint64_t j = rowptr[i]; j < rowptr[i + 1]; ++j) { src[j] = (uint32_t)(i * c->n_ranks + c->rank); dst[j] = col[j]; }
+  int rc = pm_graph_from_slots(c, n_vertices, E, src.data(), dst.data());
+  if (rc) return rc;
+  std::vector<uint32_t> dm(c->nloc, 0u);
+  uint64_t em = 0;
+  for (uint64_t i = 0; i < own; ++i) { dm[i] = (uint32_t)degree_multi[i]; em += degree_multi[i]; }
+  PM_CUDA(c, cudaMemcpy(c->degm, dm.data(), c->nloc * 4, cudaMemcpyHostToDevice));
+  c->E_multi = em;
+  return 0;
 }
 
 int pm_get_kernel_stats(const pm_ctx* c, int bin, pm_kernel_stats_t* out) {
@@ -183,7 +285,7 @@ int pm_graph_rmat(pm_ctx* c, uint64_t scale, uint64_t gen_ranks) {
 
 int pm_graph_info(const pm_ctx* c, pm_graph_info_t* o) {
   if (!c || !o || !c->has_graph) return PM_ERR_ARG;
-  o->n_vertices = c->V; o->n_local = c->nloc; o->n_slots_multi = c->E_multi; o->n_slots = c->E;
+  o->n_vertices = c->V; o->n_local = n_owned(c); o->n_slots_multi = c->E_multi; o->n_slots = c->E;
   o->n_slots_padded = c->Epad; o->max_degree = c->max_deg; o->device_bytes = c->graph_bytes;
   return 0;
 }
@@ -191,26 +293,32 @@ int pm_graph_info(const pm_ctx* c, pm_graph_info_t* o) {
 int pm_graph_get_degree(const pm_ctx* cc, uint64_t* out) {
   pm_ctx* c = const_cast<pm_ctx*>(cc);
   if (!c || !c->has_graph || !out) return PM_ERR_ARG;
-  std::vector<uint32_t> h(c->V);
-  PM_CUDA(c, cudaMemcpy(h.data(), c->degm, c->V * 4, cudaMemcpyDeviceToHost));
-  for (uint64_t v = 0; v < c->V; ++v) out[v] = h[v];
+  const uint64_t own = n_owned(c);
+  std::vector<uint32_t> h(own);
+  PM_CUDA(c, cudaMemcpy(h.data(), c->degm, own * 4, cudaMemcpyDeviceToHost));
+  for (uint64_t v = 0; v < own; ++v) out[v] = h[v];
   return 0;
 }
 
 int pm_graph_get_csr(const pm_ctx* cc, uint64_t* rowptr_out, uint32_t* col_out) {
   pm_ctx* c = const_cast<pm_ctx*>(cc);
   if (!c || !c->has_graph || !rowptr_out || !col_out) return PM_ERR_ARG;
-  std::vector<uint32_t> deg(c->V), blk(c->V + 1), col(c->Epad);
-  PM_CUDA(c, cudaMemcpy(deg.data(), c->deg, c->V * 4, cudaMemcpyDeviceToHost));
-  PM_CUDA(c, cudaMemcpy(blk.data(), c->rowblk, (c->V + 1) * 4, cudaMemcpyDeviceToHost));
+  const uint64_t own = n_owned(c);
+  std::vector<uint32_t> deg(own), blk(own + 1), col(c->Epad);
+  PM_CUDA(c, cudaMemcpy(deg.data(), c->deg, own * 4, cudaMemcpyDeviceToHost));
+  PM_CUDA(c, cudaMemcpy(blk.data(), c->rowblk, (own + 1) * 4, cudaMemcpyDeviceToHost));
   PM_CUDA(c, cudaMemcpy(col.data(), c->col0, c->Epad * 4, cudaMemcpyDeviceToHost));
   uint64_t o = 0;
-  for (uint64_t v = 0; v < c->V; ++v) {
+  for (uint64_t v = 0; v < own; ++v) {
     rowptr_out[v] = o;
     std::memcpy(col_out + o, col.data() + (uint64_t)blk[v] * 8, (size_t)deg[v] * 4);
+    if (c->n_ranks > 1) {  // slots -> vertex ids, ascending
+      for (uint32_t j = 0; j < deg[v]; ++j) col_out[o + j] = (uint32_t)vertex_of(c, col_out[o + j]);
+      std::sort(col_out + o, col_out + o + deg[v]);
+    }
     o += deg[v];
   }
-  rowptr_out[c->V] = o;
+  rowptr_out[own] = o;
   return 0;
 }
 
@@ -218,8 +326,9 @@ int pm_graph_get_csr(const pm_ctx* cc, uint64_t* rowptr_out, uint32_t* col_out) 
 int pm_labels_degree_log2(pm_ctx* c) {
   if (!c || !c->has_graph) return fail(c, PM_ERR_ARG, "pm_labels_degree_log2: no graph");
   PM_CUDA(c, cudaSetDevice(c->device));
-  if (!c->label) { int rc = dev_alloc(c, &c->label, c->V, &c->graph_bytes); if (rc) return rc; }
-  k_labels_degree_log2<<<grid_for(), kBlock, 0, c->stream>>>(c->degm, c->V, c->label);
+  if (!c->label) { int rc = dev_alloc(c, &c->label, c->nloc, &c->graph_bytes); if (rc) return rc; }
+  // the owner of v holds all of v's slots, so its degree (and label) is local (no delegate reduce needed)
+  k_labels_degree_log2<<<grid_for(), kBlock, 0, c->stream>>>(c->degm, c->nloc, c->label);
   PM_LAUNCH_CHECK(c);
   c->has_labels = true;
   c->state_ready = false;
@@ -229,8 +338,16 @@ int pm_labels_degree_log2(pm_ctx* c) {
 int pm_labels_set(pm_ctx* c, const uint64_t* labels) {
   if (!c || !c->has_graph || !labels) return fail(c, PM_ERR_ARG, "pm_labels_set: no graph or null labels");
   PM_CUDA(c, cudaSetDevice(c->device));
-  if (!c->label) { int rc = dev_alloc(c, &c->label, c->V, &c->graph_bytes); if (rc) return rc; }
-  PM_CUDA(c, cudaMemcpyAsync(c->label, labels, c->V * 8, cudaMemcpyHostToDevice, c->stream));
+  if (!c->label) { int rc = dev_alloc(c, &c->label, c->nloc, &c->graph_bytes); if (rc) return rc; }
+  const uint64_t* src = labels;
+  std::vector<uint64_t> mine;
+  if (c->n_ranks > 1) {  // the labels of the rows this rank owns, in local order
+    mine.assign(c->nloc, 0);
+    const uint64_t own = n_owned(c);
+    for (uint64_t i = 0; i < own; ++i) mine[i] = labels[i * c->n_ranks + c->rank];
+    src = mine.data();
+  }
+  PM_CUDA(c, cudaMemcpyAsync(c->label, src, c->nloc * 8, cudaMemcpyHostToDevice, c->stream));
   PM_CUDA(c, cudaStreamSynchronize(c->stream));
   c->has_labels = true;
   c->state_ready = false;
@@ -243,7 +360,23 @@ int pm_labels_get(const pm_ctx* cc, uint64_t* out) {
   pm_ctx* c = const_cast<pm_ctx*>(cc);
   if (!c || !c->has_labels || !out) return PM_ERR_ARG;
   PM_CUDA(c, cudaStreamSynchronize(c->stream));
-  PM_CUDA(c, cudaMemcpy(out, c->label, c->V * 8, cudaMemcpyDeviceToHost));
+  if (c->n_ranks == 1) {
+    PM_CUDA(c, cudaMemcpy(out, c->label, c->V * 8, cudaMemcpyDeviceToHost));
+    return 0;
+  }
+  // collective: gather every rank's local labels, then slot order -> vertex order
+  const uint64_t Vs = c->nlmax * c->n_ranks;
+  unsigned long long* d = nullptr;
+  int rc = dev_alloc(c, &d, Vs);
+  if (rc) return rc;
+  ncclResult_t nr = ncclAllGather(c->label, d, c->nlmax, ncclUint64, comm_of(c), c->stream);
+  std::vector<uint64_t> h(Vs);
+  cudaError_t e = cudaMemcpyAsync(h.data(), d, Vs * 8, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  dev_free(d);
+  if (nr != ncclSuccess) return fail(c, PM_ERR_COMM, ncclGetErrorString(nr));
+  if (e != cudaSuccess) return fail(c, PM_ERR_CUDA, cudaGetErrorString(e));
+  for (uint64_t v = 0; v < c->V; ++v) out[v] = h[slot_of(c, v)];
   return 0;
 }
 
@@ -307,20 +440,34 @@ int pm_state_reset(pm_ctx* c) {
   if (!c || !c->has_graph || !c->has_labels || !c->has_pattern)
     return fail(c, PM_ERR_ARG, "pm_state_reset needs a graph, labels and a pattern");
   PM_CUDA(c, cudaSetDevice(c->device));
-  const uint64_t V = c->V;
+  const uint64_t NL = c->nloc;                      // rank-local arrays
+  const uint64_t Vs = c->nlmax * c->n_ranks;        // replicated arrays (indexed by slot)
+  const uint64_t base = c->nlmax * c->rank;
+  const bool multi = c->n_ranks > 1;
   int rc;
   if (!c->S) {
-    if ((rc = dev_alloc(c, &c->S, V))) return rc;
-    if ((rc = dev_alloc(c, &c->Tst, V))) return rc;
-    if ((rc = dev_alloc(c, &c->adeg, V))) return rc;
-    if ((rc = dev_alloc(c, &c->cls, V))) return rc;
-    if ((rc = dev_alloc(c, &c->ok, V))) return rc;
-    if ((rc = dev_alloc(c, &c->src_list, V))) return rc;
+    if ((rc = dev_alloc(c, &c->S, Vs))) return rc;
+    if ((rc = dev_alloc(c, &c->Tst, NL))) return rc;
+    if ((rc = dev_alloc(c, &c->adeg, NL))) return rc;
+    if ((rc = dev_alloc(c, &c->cls, Vs))) return rc;
+    if ((rc = dev_alloc(c, &c->ok, Vs))) return rc;
+    if ((rc = dev_alloc(c, &c->src_list, NL))) return rc;
     for (int b = 0; b < 2; ++b)
       for (int k = 0; k < 3; ++k)
-        if ((rc = dev_alloc(c, &c->fr[b][k], V))) return rc;
+        if ((rc = dev_alloc(c, &c->fr[b][k], NL))) return rc;
     if ((rc = dev_alloc(c, &c->cnt, 1))) return rc;
     PM_CUDA(c, cudaMallocHost((void**)&c->h_cnt, sizeof(DevCounters)));
+    PM_CUDA(c, cudaMemsetAsync(c->adeg, 0, NL * sizeof(uint32_t), c->stream));
+    if (multi) {
+      c->dcap = c->nlmax;  // a rank publishes at most one change per owned vertex and step
+      if ((rc = dev_alloc(c, &c->din[0], c->dcap * c->n_ranks))) return rc;
+      if ((rc = dev_alloc(c, &c->din[1], c->dcap * c->n_ranks))) return rc;
+      if ((rc = dev_alloc(c, &c->step_msg, 1 + c->n_ranks))) return rc;
+      PM_CUDA(c, cudaMemsetAsync(c->step_msg, 0, (1 + c->n_ranks) * sizeof(StepMsg), c->stream));
+      PM_CUDA(c, cudaMallocHost((void**)&c->h_step, sizeof(StepMsg) * c->n_ranks));
+    }
+    // the peer table (G = 1: everything points at this GPU)
+    if ((rc = comm_publish(c))) return rc;
   }
   dev_free(c->rowstat);
   if (c->h_rowstat) cudaFreeHost(c->h_rowstat);
@@ -337,17 +484,24 @@ int pm_state_reset(pm_ctx* c) {
   PM_CUDA(c, cudaMemsetAsync(c->cnt, 0, sizeof(DevCounters), c->stream));
   c->cur = 0;
   c->filter_done = false;
+  PM_CUDA(c, cudaEventRecord(c->kev[3][0], c->stream));
   if (c->labels_small) {
-    // init and the signature filter of the first superstep in one streaming pass
-    PM_CUDA(c, cudaEventRecord(c->kev[3][0], c->stream));
-    k_init_filter<<<grid_for(), kBlock, 0, c->stream>>>(c->lab8, c->deg, c->sig, V, c->cls, c->S, c->fr[0][0],
-                                                        c->fr[0][1], c->fr[0][2], c->cnt, 0);
-    PM_CUDA(c, cudaEventRecord(c->kev[3][1], c->stream));
+    // init and the signature filter of the first superstep in one streaming pass over the local rows
+    k_init_filter<<<grid_for(), kBlock, 0, c->stream>>>(c->lab8 + base, c->deg, c->sig, NL, c->cls + base, c->S + base,
+                                                        c->fr[0][0], c->fr[0][1], c->fr[0][2], c->cnt, 0);
     c->filter_done = true;
-  } else
-    k_init_state<false><<<grid_for(), kBlock, 0, c->stream>>>(c->label, c->lab8, c->deg, V, c->cls, c->S, c->fr[0][0],
-                                                             c->fr[0][1], c->fr[0][2], c->cnt, 0);
+  } else {
+    if (multi) PM_CUDA(c, cudaMemsetAsync(c->S, 0, Vs * sizeof(uint16_t), c->stream));
+    k_init_state<false><<<grid_for(), kBlock, 0, c->stream>>>(c->label, c->lab8, c->deg, NL, c->cls + base, c->S + base,
+                                                             c->fr[0][0], c->fr[0][1], c->fr[0][2], c->cnt, 0);
+  }
   PM_LAUNCH_CHECK(c);
+  if (multi) {
+    // every rank needs the class and the first mask of every vertex (they are gathered from neighbours)
+    if ((rc = comm_allgather_slots(c, c->cls))) return rc;
+    if ((rc = comm_allgather_slots(c, c->S))) return rc;
+  }
+  PM_CUDA(c, cudaEventRecord(c->kev[3][1], c->stream));
   {
     int rc2 = sync_counters(c);
     if (rc2) return rc2;
@@ -387,19 +541,7 @@ int pm_lcc(pm_ctx* c, int init_step, int* not_finished, pm_counts_t* counts_out)
     a1.bin = 1;
     a2.bin = 2;
     if (first) {
-      int cur = c->cur, nxt = cur ^ 1;
-      if (c->labels_small && !c->filter_done) {
-        // settle most candidates from their neighbour-label signature; survivors move to the other buffer
-        PM_CUDA(c, cudaEventRecord(c->kev[3][0], st));
-        k_lcc_first_filter<<<grid, kBlock, 0, st>>>(a, c->sig, c->fr[cur][0], c->fr[cur][1], c->fr[cur][2],
-                                                    c->fr[nxt][0], c->fr[nxt][1], c->fr[nxt][2], cur, nxt);
-        PM_LAUNCH_CHECK(c);
-        PM_CUDA(c, cudaEventRecord(c->kev[3][1], st));
-        c->cur = nxt;
-        cur = nxt;
-        nxt = cur ^ 1;
-        PM_CUDA(c, cudaMemsetAsync(&c->cnt->fr_n[nxt][0], 0, 4 * sizeof(uint32_t), st));
-      }
+      const int cur = c->cur;
       // the kernels that walk the pristine adjacency are timed with CUDA events on this stream
       PM_CUDA(c, cudaEventRecord(c->kev[0][0], st));
       if (c->bin_live[0]) { (sm ? k_lcc_scan<8, true, true> : k_lcc_scan<8, true, false>)<<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], &c->cnt->fr_n[cur][0]); PM_LAUNCH_CHECK(c); }
@@ -423,12 +565,27 @@ int pm_lcc(pm_ctx* c, int init_step, int* not_finished, pm_counts_t* counts_out)
       PM_LAUNCH_CHECK(c);
       c->cur = nxt;
     }
+    if (c->n_ranks > 1) {
+      // the commit stored this rank's mask changes into every peer's delta inbox; the StepMsg
+      // all-gather is the barrier after which the peers' changes can be applied to the local replica
+      int rc2 = comm_step(c);
+      if (rc2) return rc2;
+      k_apply_deltas<<<grid, kBlock, 0, st>>>(c->S, c->step_msg + 1, c->step_parity);
+      PM_LAUNCH_CHECK(c);
+      c->step_parity ^= 1;
+    }
   }
   PM_CUDA(c, cudaEventRecord(c->events[D], st));
   PM_CUDA(c, cudaMemcpyAsync(c->h_rowstat, c->rowstat, D * sizeof(RowStat), cudaMemcpyDeviceToHost, st));
   int rc = sync_counters(c);
   if (rc) return rc;
-  if ((c->h_cnt->nf || (init_step && c->filter_done && c->h_cnt->nf_init)) && not_finished) *not_finished = 1;
+  bool removed = c->h_cnt->nf || (init_step && c->filter_done && c->h_cnt->nf_init);
+  if (c->n_ranks > 1) {  // global_not_finished is reduced over the ranks (beta.cpp:609)
+    if ((rc = comm_step_fetch(c))) return rc;
+    for (int g = 0; g < c->n_ranks; ++g)
+      removed = removed || c->h_step[g].nf || (init_step && c->filter_done && c->h_step[g].pad);
+  }
+  if (removed && not_finished) *not_finished = 1;
   {
     bool any = false;
     for (int b = 2; b >= 0; --b) { any = any || c->h_cnt->fr_n[c->cur][b] != 0; c->bin_live[b] = any; }
@@ -514,12 +671,14 @@ int pm_nlcc(pm_ctx* c, int pl, int mode, int* pattern_found, int* token_source_d
   PM_CUDA(c, cudaEventRecord(c->events[0], st));
   PM_CUDA(c, cudaMemcpyToSymbolAsync(c_nlc, &nc, sizeof(NlcConst), 0, cudaMemcpyHostToDevice, st));
   int rc;
+  const bool multi = c->n_ranks > 1;
   // Size the (vertex, source) set for what this constraint stored last time (or for the current
   // edge maps on its first run); an undersized table is detected and the constraint retried.
   if (c->pool_seen.size() != c->pat.constraints.size()) c->pool_seen.assign(c->pat.constraints.size(), 0);
   const uint64_t ne_now = c->rows.empty() ? c->E : c->rows.back().n_edges;
   uint64_t want_pool = c->pool_seen[pl] ? c->pool_seen[pl] + c->pool_seen[pl] / 2 + 4096 : 2 * ne_now + 65536;
   want_pool = std::max<uint64_t>(want_pool, 1ull << 18);
+  if (multi && (rc = comm_allreduce_max_u64(c, &want_pool))) return rc;  // growing the inboxes is collective
   if ((rc = nlcc_reserve(c, want_pool))) return rc;
   auto pick_table = [&]() {
     uint64_t use = 1;
@@ -530,55 +689,96 @@ int pm_nlcc(pm_ctx* c, int pl, int mode, int* pattern_found, int* token_source_d
   uint2* d_matches = nullptr;
   uint64_t match_cap = 0;
   const int cur = c->cur;
-  uint64_t n_matches = 0, hi = 0;
+  const bool sm = c->labels_small;
+  uint64_t n_matches = 0, hi = 0, fanout = 0;
+  int found = 0;
+  // cycle constraints close their last two hops by intersecting E_v with E_s (k_nem1_close_cycle);
+  // that needs symmetric edge maps, which flags set outside LCC can break only while diameter < 2
+  const bool close2 = !tds && k.valid_cycle && (int)k.C >= 2 && c->pat.diameter >= 2;
   for (int attempt = 0;; ++attempt) {
-    if (tds && c->keep_subgraphs) {
+    if (tds && c->keep_subgraphs && !multi) {
       match_cap = c->pool_cap;
       dev_free(d_matches);
       if ((rc = dev_alloc(c, &d_matches, match_cap))) return rc;
     }
-    // zero found .. hash_n, keep the frontier counters and nf
+    // zero found .. the end, keep the frontier counters and nf
     PM_CUDA(c, cudaMemsetAsync(&c->cnt->found, 0, sizeof(DevCounters) - offsetof(DevCounters, found), st));
     if (!tds) PM_CUDA(c, cudaMemsetAsync(c->hset, 0xFF, c->hset_use * sizeof(unsigned long long), st));
+    // several ranks: `ok` doubles as this GPU's "already acknowledged" cache for foreign sources
+    if (multi) PM_CUDA(c, cudaMemsetAsync(c->ok, 0, c->nlmax * c->n_ranks, st));
     NlcArgs a = nlc_args(c, d_matches, match_cap);
     k_nlcc_sources<<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], c->fr[cur][1], c->fr[cur][2], cur, tds ? 1 : 0);
     PM_LAUNCH_CHECK(c);
     k_nlcc_begin<<<1, 1, 0, st>>>(c->cnt);
     PM_LAUNCH_CHECK(c);
-    // cycle constraints close their last two hops by intersecting E_v with E_s (k_nem1_close_cycle);
-    // that needs symmetric edge maps, which flags set outside LCC can break only while diameter < 2
-    const bool close2 = !tds && k.valid_cycle && (int)k.C >= 2 && c->pat.diameter >= 2;
-    for (int hn = 1; hn <= (int)k.C + 1; ++hn) {
-      const bool fin = hn == (int)k.C + 1;
-      const int lvl = hn - 1;
-      const bool sm = c->labels_small;
-      if (close2 && hn == (int)k.C) {
-        (sm ? k_nem1_close_cycle<true> : k_nem1_close_cycle<false>)<<<grid, kBlock, 0, st>>>(a, lvl, hn);
+    if (!multi) {
+      for (int hn = 1; hn <= (int)k.C + 1; ++hn) {
+        const bool fin = hn == (int)k.C + 1;
+        const int lvl = hn - 1;
+        if (close2 && hn == (int)k.C) {
+          (sm ? k_nem1_close_cycle<true> : k_nem1_close_cycle<false>)<<<grid, kBlock, 0, st>>>(a, lvl, hn);
+          PM_LAUNCH_CHECK(c);
+          break;
+        }
+        if (tds) {
+          if (fin) (sm ? k_tds_expand<true, true> : k_tds_expand<true, false>)<<<grid, kBlock, 0, st>>>(a, lvl, hn);
+          else (sm ? k_tds_expand<false, true> : k_tds_expand<false, false>)<<<grid, kBlock, 0, st>>>(a, lvl, hn);
+        } else if (fin) {
+          if (k.valid_cycle) k_nem1_final_cycle<<<grid, kBlock, 0, st>>>(a, lvl, hn);
+          else (sm ? k_nem1_expand<true, true> : k_nem1_expand<true, false>)<<<grid, kBlock, 0, st>>>(a, lvl, hn);
+        } else {
+          (sm ? k_nem1_expand<false, true> : k_nem1_expand<false, false>)<<<grid, kBlock, 0, st>>>(a, lvl, hn);
+        }
         PM_LAUNCH_CHECK(c);
-        break;
+        if (!fin) {
+          k_nlcc_close_level<<<1, 1, 0, st>>>(c->cnt, hn, c->pool_cap);
+          PM_LAUNCH_CHECK(c);
+        }
       }
-      if (tds) {
-        if (fin) (sm ? k_tds_expand<true, true> : k_tds_expand<true, false>)<<<grid, kBlock, 0, st>>>(a, lvl, hn);
-        else (sm ? k_tds_expand<false, true> : k_tds_expand<false, false>)<<<grid, kBlock, 0, st>>>(a, lvl, hn);
-      } else if (fin) {
-        if (k.valid_cycle) k_nem1_final_cycle<<<grid, kBlock, 0, st>>>(a, lvl, hn);
-        else (sm ? k_nem1_expand<true, true> : k_nem1_expand<true, false>)<<<grid, kBlock, 0, st>>>(a, lvl, hn);
-      } else {
-        (sm ? k_nem1_expand<false, true> : k_nem1_expand<false, false>)<<<grid, kBlock, 0, st>>>(a, lvl, hn);
-      }
-      PM_LAUNCH_CHECK(c);
-      if (!fin) {
-        k_nlcc_close_level<<<1, 1, 0, st>>>(c->cnt, hn, c->pool_cap);
+      if ((rc = sync_counters(c))) { dev_free(d_matches); return rc; }
+    } else {
+      // one kernel + one StepMsg all-gather per hop: tokens are stored into the owners' inboxes
+      // (parity a.par), the all-gather publishes the region fill counts and is the barrier
+      if ((rc = comm_step(c))) return rc;  // level 0 (the sources) is in inbox `par`
+      c->step_parity ^= 1;
+      for (int hn = 1; hn <= (int)k.C + 1; ++hn) {
+        const bool fin = hn == (int)k.C + 1;
+        const int first = hn == 1 ? 1 : 0;
+        a = nlc_args(c, nullptr, 0);
+        bool last = fin;
+        if (tds) {
+          if (fin) (sm ? k_tds_hop_m<true, true> : k_tds_hop_m<true, false>)<<<grid, kBlock, 0, st>>>(a, hn);
+          else (sm ? k_tds_hop_m<false, true> : k_tds_hop_m<false, false>)<<<grid, kBlock, 0, st>>>(a, hn);
+        } else if (close2 && hn == (int)k.C) {
+          (sm ? k_nem1_hop_m<2, true> : k_nem1_hop_m<2, false>)<<<grid, kBlock, 0, st>>>(a, hn, first);
+          last = true;
+        } else if (fin) {
+          (sm ? k_nem1_hop_m<1, true> : k_nem1_hop_m<1, false>)<<<grid, kBlock, 0, st>>>(a, hn, first);
+        } else {
+          (sm ? k_nem1_hop_m<0, true> : k_nem1_hop_m<0, false>)<<<grid, kBlock, 0, st>>>(a, hn, first);
+        }
         PM_LAUNCH_CHECK(c);
+        if ((rc = comm_step(c))) return rc;  // after the last hop: the acknowledgements have landed
+        c->step_parity ^= 1;
+        if (last) break;
+      }
+      if ((rc = sync_counters(c))) return rc;
+      if ((rc = comm_step_fetch(c))) return rc;
+    }
+    hi = c->h_cnt->pool_n;
+    // the pool / hash set / an inbox region ran out, or more walks completed than the match list holds
+    bool overflow = c->h_cnt->overflow || (!multi && c->h_cnt->pool_n > c->pool_cap) ||
+                    (!multi && tds && c->keep_subgraphs && (c->h_cnt->matches > match_cap || c->h_cnt->match_drop));
+    uint64_t matches_here = c->h_cnt->matches;
+    if (multi) {
+      matches_here = 0;
+      for (int g = 0; g < c->n_ranks; ++g) {
+        overflow = overflow || c->h_step[g].overflow;
+        if (tds) matches_here += c->h_step[g].out_n[c->rank];  // completed walks routed to this rank
       }
     }
-    if ((rc = sync_counters(c))) { dev_free(d_matches); return rc; }
-    hi = c->h_cnt->pool_n;
-    // the pool / hash set ran out, or more walks completed than the match list holds
-    const bool overflow = c->h_cnt->overflow || c->h_cnt->pool_n > c->pool_cap ||
-                          (tds && c->keep_subgraphs && (c->h_cnt->matches > match_cap || c->h_cnt->match_drop));
     if (!overflow) {
-      n_matches = c->h_cnt->matches;
+      n_matches = matches_here;
       c->pool_seen[pl] = std::max<uint64_t>(c->pool_seen[pl], c->h_cnt->pool_n);
       c->pool_cache[c->pat_key] = c->pool_seen;
       break;
@@ -588,44 +788,61 @@ int pm_nlcc(pm_ctx* c, int pl, int mode, int* pattern_found, int* token_source_d
     if ((rc = nlcc_reserve(c, want_pool))) { dev_free(d_matches); return rc; }
     pick_table();
   }
-  const uint64_t fanout = c->h_cnt->fanout;
-  const int found = c->h_cnt->found;
+  fanout = c->h_cnt->fanout;
+  found = c->h_cnt->found;
+  if (multi)
+    for (int g = 0; g < c->n_ranks; ++g) found = found || c->h_step[g].found;  // beta.cpp:1136
   if (getenv("PM_DEBUG")) {
-    fprintf(stderr, "[pm] nlcc pl=%d %s n_src=%u fanout=%llu pool_n=%llu table=%llu levels:", pl, tds ? "tds" : "nem1",
-            c->h_cnt->n_src, (unsigned long long)fanout, (unsigned long long)c->h_cnt->pool_n,
+    fprintf(stderr, "[pm] rank %d nlcc pl=%d %s n_src=%u fanout=%llu pool_n=%llu table=%llu levels:", c->rank, pl,
+            tds ? "tds" : "nem1", c->h_cnt->n_src, (unsigned long long)fanout, (unsigned long long)c->h_cnt->pool_n,
             (unsigned long long)c->hset_use);
     for (int h = 0; h <= (int)k.C + 1; ++h) fprintf(stderr, " %llu", (unsigned long long)c->h_cnt->lvl[h]);
     fprintf(stderr, "\n");
   }
-  // post-processing of token_source_map (beta.cpp:956-1062) and the TP row (beta.cpp:1094-1120)
-  k_nlcc_apply<<<grid, kBlock, 0, st>>>(c->S, c->ok, c->src_list, c->cnt);
-  PM_LAUNCH_CHECK(c);
-  PM_CUDA(c, cudaMemsetAsync(c->rowstat + D, 0, sizeof(RowStat), st));
-  LccArgs la = lcc_args(c, D);
-  k_count_alive<<<grid, kBlock, 0, st>>>(la, c->fr[cur][0], c->fr[cur][1], c->fr[cur][2], cur);
-  PM_LAUNCH_CHECK(c);
-  // enumerated subgraphs (the file is truncated per outer iteration, beta.cpp:713-717)
+  // enumerated subgraphs (the file is truncated per outer iteration, beta.cpp:713-717); several ranks:
+  // the completed walks are in the inbox the last hop wrote (now `step_parity ^ 1`)
   if (tds) {
     c->subgraph_width[pl] = n;
     c->subgraph_count[pl] = n_matches;
     c->subgraphs[pl].clear();
     c->summary.path_count += n_matches;  // path_count is never reset (tds_batch_1.hpp:14,1243)
-    if (c->keep_subgraphs && n_matches) {
+    if (n_matches && (c->keep_subgraphs || multi)) {
       uint32_t* d_rows = nullptr;
       if ((rc = dev_alloc(c, &d_rows, n_matches * n))) { dev_free(d_matches); return rc; }
-      k_tds_materialize<<<grid, kBlock, 0, st>>>(c->pool, d_matches, n_matches, n, d_rows);
+      if (multi) k_tds_collect_m<<<grid, kBlock, 0, st>>>(nlc_args(c, nullptr, 0), n, d_rows);
+      else k_tds_materialize<<<grid, kBlock, 0, st>>>(c->pool, d_matches, n_matches, n, d_rows);
       c->launches++;
       c->subgraphs[pl].resize(n_matches * n);
       cudaError_t e = cudaMemcpyAsync(c->subgraphs[pl].data(), d_rows, n_matches * n * 4, cudaMemcpyDeviceToHost, st);
       if (e == cudaSuccess) e = cudaStreamSynchronize(st);
       dev_free(d_rows);
       if (e != cudaSuccess) { dev_free(d_matches); return fail(c, PM_ERR_CUDA, cudaGetErrorString(e)); }
+      if (multi)
+        for (auto& x : c->subgraphs[pl]) x = (uint32_t)vertex_of(c, x);  // slots -> vertex ids
     }
   }
   dev_free(d_matches);
+  // post-processing of token_source_map (beta.cpp:956-1062) and the TP row (beta.cpp:1094-1120)
+  k_nlcc_apply<<<grid, kBlock, 0, st>>>(c->S, c->ok, c->src_list, c->cnt, c->step_parity);
+  PM_LAUNCH_CHECK(c);
+  if (multi) {  // the deactivations reach the peers' replicas (vertex_data all_min/max_reduce, beta.cpp:1020-1039)
+    if ((rc = comm_step(c))) return rc;
+    k_apply_deltas<<<grid, kBlock, 0, st>>>(c->S, c->step_msg + 1, c->step_parity);
+    PM_LAUNCH_CHECK(c);
+    c->step_parity ^= 1;
+  }
+  PM_CUDA(c, cudaMemsetAsync(c->rowstat + D, 0, sizeof(RowStat), st));
+  LccArgs la = lcc_args(c, D);
+  k_count_alive<<<grid, kBlock, 0, st>>>(la, c->fr[cur][0], c->fr[cur][1], c->fr[cur][2], cur);
+  PM_LAUNCH_CHECK(c);
   PM_CUDA(c, cudaEventRecord(c->events[1], st));
   PM_CUDA(c, cudaMemcpyAsync(c->h_rowstat + D, c->rowstat + D, sizeof(RowStat), cudaMemcpyDeviceToHost, st));
   if ((rc = sync_counters(c))) return rc;
+  int deleted = c->h_cnt->deleted ? 1 : 0;
+  if (multi) {  // token_source_deleted is reduced over the ranks (beta.cpp:1149)
+    if ((rc = comm_step_fetch(c))) return rc;
+    for (int g = 0; g < c->n_ranks; ++g) deleted = deleted || c->h_step[g].deleted;
+  }
   float ms = 0;
   PM_CUDA(c, cudaEventElapsedTime(&ms, c->events[0], c->events[1]));
   pm_row_t r;
@@ -634,7 +851,7 @@ int pm_nlcc(pm_ctx* c, int pl, int mode, int* pattern_found, int* token_source_d
   c->rows.push_back(r);
   if (counts_out) { counts_out->n_vertices = r.n_vertices; counts_out->n_edges = r.n_edges; counts_out->seconds = r.seconds; }
   if (pattern_found) *pattern_found = found;
-  if (token_source_deleted) *token_source_deleted = c->h_cnt->deleted ? 1 : 0;
+  if (token_source_deleted) *token_source_deleted = deleted;
   c->summary.device_seconds += r.seconds;
   c->summary.edges_processed += fanout;
   c->summary.algorithmic_bytes += fanout * 6 + (hi) * 16;  // §8(d): 4+2 B per walked slot, 8 B in + 8 B out per token
@@ -654,8 +871,8 @@ __global__ void k_emit_vertices(LccArgs a, const uint32_t* __restrict__ l0, cons
   const uint32_t total = c0 + c1 + c2;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const uint32_t v = i < c0 ? l0[i] : (i < c0 + c1 ? l1[i - c0] : l2[i - c0 - c1]);
-    const uint32_t T = a.S[v];
-    if (T) out[atomicAdd(n_out, 1ull)] = make_uint2(v, T);
+    const uint32_t T = a.S[v + a.base];
+    if (T) out[atomicAdd(n_out, 1ull)] = make_uint2(v + a.base, T);
   }
 }
 
@@ -669,13 +886,13 @@ __global__ void k_emit_edges(LccArgs a, const uint32_t* __restrict__ l0, const u
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t i = warp; i < total; i += nwarps) {
     const uint32_t v = i < c0 ? l0[i] : (i < c0 + c1 ? l1[i - c0] : l2[i - c0 - c1]);
-    if (!a.S[v]) continue;
+    if (!a.S[v + a.base]) continue;
     const uint32_t d = a.adeg[v];
     const uint64_t row = (uint64_t)a.rowblk[v] * 8;
     unsigned long long base = 0;
     if (lane == 0) base = atomicAdd(n_out, (unsigned long long)d);
     base = __shfl_sync(0xffffffffu, base, 0);
-    for (uint32_t j = lane; j < d; j += 32) out[base + j] = make_uint2(v, a.colw[row + j] & PM_IDMASK);
+    for (uint32_t j = lane; j < d; j += 32) out[base + j] = make_uint2(v + a.base, a.colw[row + j] & PM_IDMASK);
   }
 }
 
@@ -712,6 +929,11 @@ int fetch_pairs(pm_ctx* c, bool edges, std::vector<uint2>& host) {
   dev_free(d_out);
   dev_free(d_n);
   if (e != cudaSuccess) return fail(c, PM_ERR_CUDA, cudaGetErrorString(e));
+  if (c->n_ranks > 1)  // slots -> vertex ids
+    for (auto& p : host) {
+      p.x = (uint32_t)vertex_of(c, p.x);
+      if (edges) p.y = (uint32_t)vertex_of(c, p.y);
+    }
   std::sort(host.begin(), host.end(), [](const uint2& x, const uint2& y) { return x.x != y.x ? x.x < y.x : x.y < y.y; });
   return 0;
 }
@@ -883,9 +1105,10 @@ int pm_write_results(const pm_ctx* cc, const char* outdir) {
   int rc;
   if ((rc = fetch_pairs(c, false, hv))) return rc;
   if ((rc = fetch_pairs(c, true, he))) return rc;
-  std::vector<uint64_t> lab(c->V);
-  if ((rc = pm_labels_get(c, lab.data()))) return rc;
-  for (auto& p : hv) fv << c->rank << ", " << p.x << ", 0, " << lab[p.x] << ", " << bitset16(p.y) << "\n";
+  // labels of the vertices this rank owns (local row of v = v / n_ranks)
+  std::vector<uint64_t> lab(c->nloc);
+  PM_CUDA(c, cudaMemcpy(lab.data(), c->label, c->nloc * 8, cudaMemcpyDeviceToHost));
+  for (auto& p : hv) fv << c->rank << ", " << p.x << ", 0, " << lab[p.x / c->n_ranks] << ", " << bitset16(p.y) << "\n";
   for (auto& p : he) fe << c->rank << ", " << p.x << ", " << p.y << "\n";
   for (size_t pl = 0; pl < c->pat.constraints.size(); ++pl) {
     std::ofstream fs;

@@ -43,6 +43,20 @@ class Engine:
         if rc != 0:
             raise PmError("%s (status %d)" % (self._lib.pm_last_error(self._h).decode(), rc))
 
+    # ---- several GPUs: one Engine (process) per GPU, owner(v) = v mod n_ranks ----------
+    @staticmethod
+    def comm_unique_id():
+        """128 opaque bytes; rank 0 creates them and every rank passes the same bytes to comm_init."""
+        buf = C.create_string_buffer(_lib.PM_COMM_ID_BYTES)
+        rc = _lib.load().pm_comm_unique_id(buf)
+        if rc != 0:
+            raise PmError("pm_comm_unique_id failed (%d)" % rc)
+        return buf.raw
+
+    def comm_init(self, rank, n_ranks, unique_id):
+        self.rank, self.n_ranks = rank, n_ranks
+        self._chk(self._lib.pm_comm_init(self._h, rank, n_ranks, unique_id))
+
     # ---- graph (-i / -b) ------------------------------------------------------
     def graph_from_slots(self, n_vertices, src, dst):
         src = np.ascontiguousarray(src, dtype=np.uint32)

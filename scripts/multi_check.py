@@ -1,0 +1,113 @@
+"""Multi-GPU parity check: run under torchrun with one rank per GPU.
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+      scripts/multi_check.py [scale] [gen_ranks]
+
+Every rank searches its partition (owner(v) = v mod G); rank 0 gathers the per-rank rows, vertex /
+edge lists and enumerated subgraphs and compares them with the CPU oracle run with n_ranks = G.
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from fuzzypatternmatching_b200.engine import Engine  # noqa: E402
+from fuzzypatternmatching_b200 import patterns as PT  # noqa: E402
+from tests import cases  # noqa: E402
+
+
+def main():
+    scale = int(sys.argv[1]) if len(sys.argv) > 1 else 17
+    gen_ranks = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("gloo")
+    eng = Engine(local)
+    ids = [Engine.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    eng.comm_init(rank, world, ids[0])
+    failures = []
+
+    def check(name, build_graph, oracle_graph, labels, spec, tds_from):
+        d = cases.pattern_dir(spec) if rank == 0 else None
+        box = [d]
+        dist.broadcast_object_list(box, src=0)
+        d = box[0]
+        build_graph()
+        if labels is None:
+            eng.labels_degree_log2()
+        else:
+            eng.labels_set(labels)
+        eng.pattern_load_dir(d)
+        eng.run(tds_from_pl=tds_from, max_iterations=50)
+        ncons = len(spec["constraints"])
+        mine = dict(rows=eng.rows(), iterations=int(eng.summary["iterations"]),
+                    vertices=[tuple(map(int, x)) for x in zip(*eng.active_vertices())],
+                    edges=[tuple(map(int, x)) for x in eng.active_edges().tolist()],
+                    subgraphs=[sorted(map(tuple, eng.subgraphs(pl).tolist())) for pl in range(ncons)],
+                    labels=eng.labels_get().tolist() if labels is None else None)
+        got = [None] * world
+        dist.gather_object(mine, got if rank == 0 else None, dst=0)
+        if rank != 0:
+            return
+        from oracle import oracle as O
+        g = oracle_graph()
+        lab = g.labels_degree_log2() if labels is None else labels
+        ref = O.Run(g, lab, O.Pattern(d), n_ranks=world, tds_from_pl=tds_from, max_iterations=50)
+        want = cases.run_summary(ref)
+        ok = True
+        if labels is None:
+            ok &= all(gr["labels"] == lab.tolist() for gr in got)
+        # rows: per-rank counts sum to the oracle's totals
+        rows = [(r[0], r[1], r[2], sum(gr["rows"][i][3] for gr in got), sum(gr["rows"][i][4] for gr in got))
+                for i, r in enumerate(got[0]["rows"])]
+        ok &= rows == want["rows"]
+        ok &= all(gr["iterations"] == want["iterations"] for gr in got)
+        for r, gr in enumerate(got):
+            ok &= gr["vertices"] == [x for x in want["vertices"] if x[0] % world == r]
+            ok &= gr["edges"] == [x for x in want["edges"] if x[0] % world == r]
+            for pl in range(ncons):
+                ok &= gr["subgraphs"][pl] == [w for w in want["subgraphs"][pl] if w[-1] % world == r]
+        print("%-28s %s  rows %d final (%d, %d) subgraphs %s" % (
+            name, "ok" if ok else "MISMATCH", len(rows), rows[-1][3] if rows else -1, rows[-1][4] if rows else -1,
+            [len(x) for x in want["subgraphs"]]), flush=True)
+        if not ok:
+            failures.append(name)
+            if rows != want["rows"]:
+                for a, b in zip(rows, want["rows"]):
+                    if a != b:
+                        print("   first differing row: got", a, "want", b)
+                        break
+
+    from oracle import oracle as O
+    # small random graphs, every template family
+    for name, spec, labelset, tds_from in cases.SPECS:
+        for seed in range(4):
+            n, m = 60 + 10 * (seed % 4), 220 + 60 * (seed % 5)
+            edges = cases.random_multigraph(seed, n, m)
+            labels = cases.random_labels(seed, n, labelset)
+            src, dst = cases.slots_of(edges)
+            check("%s/seed%d" % (name, seed), lambda: eng.graph_from_slots(n, src, dst),
+                  lambda: O.Graph.from_undirected(n, edges), labels, spec, tds_from)
+    # R-MAT, generated across the GPUs and shuffled to the owners
+    check("rmat%d/tree" % scale, lambda: eng.graph_rmat(scale, gen_ranks), lambda: O.Graph.rmat(scale, gen_ranks),
+          None, PT.RMAT_LOG2_TREE, 4)
+    for nm, spec, tds in (("triangle", PT.triangle(6, 7, 8), 1), ("cycle4", PT.cycle4(5, 6, 7, 8), 1)):
+        check("rmat%d/%s" % (scale, nm), lambda: eng.graph_rmat(scale, gen_ranks), lambda: O.Graph.rmat(scale, gen_ranks),
+              None, spec, tds)
+    flag = [len(failures)]
+    dist.broadcast_object_list(flag, src=0)
+    eng.close()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("MULTI-GPU PARITY", "FAILED: %s" % failures if failures else "OK (%d ranks)" % world, flush=True)
+    sys.exit(1 if flag[0] else 0)
+
+
+if __name__ == "__main__":
+    main()

@@ -147,7 +147,12 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     pats = write_patterns(args.workload)
     metric, unit = "lcc_nlcc_search_edges_per_second", "edges/s"
-    config = {"workload": "rmat_s%d_%s" % (args.scale, args.workload), "scale": args.scale,
+    # Weak scaling: the per-GPU share of the graph stays that of R-MAT scale `--scale` on one GPU, so N GPUs
+    # search ONE R-MAT graph of scale + log2(N) partitioned 1-D (owner(v) = v mod N); N = 4 is BASELINE
+    # configs[4] (scale 28).  PM_BENCH_STRONG=1 keeps the scale fixed instead.
+    strong = os.environ.get("PM_BENCH_STRONG", "0") == "1"
+    scale = args.scale if (strong or world == 1) else args.scale + max(0, (world - 1).bit_length())
+    config = {"workload": "rmat_s%d_%s" % (scale, args.workload), "scale": scale,
               "gen_ranks": args.gen_ranks, "templates": [n for n, _, _ in pats],
               "labels": "ceil(log2(degree+1))", "parallelism": "1d_vertex_partition_x%d" % args.gpus}
 
@@ -155,11 +160,11 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        cpu_scale = min(args.scale, args.cpu_scale)
-        r = cpu_reference(cpu_scale, min(args.gen_ranks, 4) if cpu_scale != args.scale else args.gen_ranks,
+        cpu_scale = min(scale, args.cpu_scale)
+        r = cpu_reference(cpu_scale, min(args.gen_ranks, 4) if cpu_scale != scale else args.gen_ranks,
                           pats, args.steps, max(args.warmup, 1))
         sample = ("oracle port of the reference CPU path, R-MAT scale %d (bounded sample of the scale-%d workload), "
-                  "same templates, %d host threads" % (cpu_scale, args.scale, r["cores"]))
+                  "same templates, %d host threads" % (cpu_scale, scale, r["cores"]))
         line = {"impl": "reference", "metric": metric, "value": r["value"], "unit": unit, "n_gpus": args.gpus,
                 "steps": r["steps_done"], "warmup": args.warmup, "ms_per_step": r["seconds_per_step"] * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16",
@@ -185,13 +190,25 @@ def main():
         torch.cuda.synchronize()
 
     eng = Engine(local_rank)
+    if world > 1:
+        # one engine context per GPU; the NCCL id of the engine's own communicator travels through torch.distributed
+        ids = [Engine.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0, device=torch.device("cuda", local_rank))
+        eng.comm_init(rank, world, ids[0])
     t0 = time.time()
-    # N > 1: every rank searches its own R-MAT graph (weak scaling; distinct streams per rank)
-    eng.graph_rmat(args.scale, args.gen_ranks)
+    # every rank generates its share of the generating ranks' streams; the slots are shuffled to their owners
+    eng.graph_rmat(scale, args.gen_ranks)
     eng.labels_degree_log2()
     gi = eng.graph_info()
     build_s = time.time() - t0
-    n_edges = gi["n_slots_multi"] * len(pats)
+    n_local_edges = gi["n_slots_multi"]
+    if world > 1:
+        t = torch.tensor([n_local_edges], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t)
+        n_global_edges = int(t.item())
+    else:
+        n_global_edges = n_local_edges
+    n_edges = n_global_edges * len(pats)      # whole-job edges searched per step
 
     def one_step(fetch=False):
         got = 0
@@ -223,7 +240,7 @@ def main():
         t = torch.tensor([elapsed], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed = float(t.item())
-    value = n_edges * args.steps * world / elapsed
+    value = n_edges * args.steps / elapsed
 
     # roofline of the dominant kernel: the first-superstep scan of the bin that walked most slots
     peaks = {}
@@ -248,17 +265,23 @@ def main():
 
     # end to end through the C ABI with HOST buffers: upload the host CSR, search, read results back
     e2e = None
+    if world > 1:
+        args.e2e_steps = min(args.e2e_steps, 1)  # the partitioned upload re-keys every row on the host: one step is enough
     if (rank == 0 or world > 1) and args.e2e_steps > 0:
         rowptr, col = eng.graph_csr()
         degm = eng.graph_degree()
         pin = lambda a: torch.from_numpy(a).pin_memory().numpy()  # noqa: E731
         rowptr, col, degm = pin(rowptr), pin(col), pin(degm)
         h2d = rowptr.nbytes + col.nbytes + degm.nbytes
+        if world > 1:
+            t = torch.tensor([h2d], dtype=torch.int64, device="cuda")
+            dist.all_reduce(t)
+            h2d = int(t.item())
         d2h = 0
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
-            eng.graph_from_csr(rowptr, col, degm)
+            eng.graph_from_csr(rowptr, col, degm, n_vertices=gi["n_vertices"])
             eng.labels_degree_log2()
             d2h = one_step(fetch=True)
         barrier()
@@ -267,7 +290,7 @@ def main():
             t = torch.tensor([e2e_elapsed], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_elapsed = float(t.item())
-        e2e = {"value": n_edges * args.e2e_steps * world / e2e_elapsed, "unit": unit,
+        e2e = {"value": n_edges * args.e2e_steps / e2e_elapsed, "unit": unit,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_elapsed / args.e2e_steps * 1e3,
                "steps": args.e2e_steps,
                "what": "pm_graph_from_csr (pinned host CSR -> device store) + degree labels + search of every template + "
@@ -275,19 +298,20 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cs = min(args.scale, args.cpu_scale)
-        r = cpu_reference(cs, 4 if cs != args.scale else args.gen_ranks, pats, 2, 1, budget_s=60.0)
+        cs = min(scale, args.cpu_scale)
+        r = cpu_reference(cs, 4 if cs != scale else args.gen_ranks, pats, 2, 1, budget_s=60.0)
         cpu = {"value": r["value"], "unit": unit, "cores": r["cores"], "kind": "port",
                "sample": "oracle port (reference binary needs MPI+Boost, unbuildable here) on R-MAT scale %d, same "
                          "templates, %d steps, %d host threads" % (cs, r["steps_done"], r["cores"])}
 
     if rank == 0:
         config.update({"inputs_exceed_l2": gi["n_slots_padded"] * 4 > 126e6, "graph_build_seconds": build_s,
-                       "directed_edge_slots": gi["n_slots_multi"], "distinct_slots": gi["n_slots"],
-                       "multi_gpu": "independent graph per rank (weak)" if world > 1 else "single gpu"})
+                       "directed_edge_slots": n_global_edges, "distinct_slots_rank0": gi["n_slots"],
+                       "multi_gpu": ("one graph, 1-D partition owner(v) = v mod %d, per-GPU share = scale %d" % (world, args.scale))
+                       if world > 1 else "single gpu"})
         line = {"metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "u16", "data": "synthetic", "config": config,
+                "scaling": "strong" if (strong and world > 1) else "weak", "vs_baseline": None, "dtype": "u16", "data": "synthetic", "config": config,
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
                 "search_ms_per_template": elapsed / args.steps / len(pats) * 1e3}
         print(json.dumps(line))

@@ -136,8 +136,10 @@ inline void comm_close_all(pm_ctx* c) {
 // (and re-arms the per-step counters)
 __global__ void k_step_msg(DevCounters* cnt, StepMsg* msg) {
   if (threadIdx.x < PM_MAX_RANKS) {
-    msg->out_n[threadIdx.x] = cnt->out_n[threadIdx.x];
+    const unsigned long long n = cnt->out_n[threadIdx.x];
+    msg->out_n[threadIdx.x] = n;
     cnt->out_n[threadIdx.x] = 0;
+    atomicMax(&cnt->peak_out, n);
   }
   if (threadIdx.x == 0) {
     msg->ndelta = cnt->ndelta;
@@ -177,28 +179,17 @@ inline int comm_allgather_slots(pm_ctx* c, T* replicated) {
   return 0;
 }
 
-inline int comm_allreduce_max_u64(pm_ctx* c, uint64_t* host_value) {
+inline int comm_allreduce_u64(pm_ctx* c, uint64_t* host_values, int n, ncclRedOp_t op) {
   if (c->n_ranks == 1) return 0;
-  unsigned long long* d = nullptr;
-  PM_CUDA(c, cudaMalloc((void**)&d, 8));
-  PM_CUDA(c, cudaMemcpyAsync(d, host_value, 8, cudaMemcpyHostToDevice, c->stream));
-  PM_NCCL(c, ncclAllReduce(d, d, 1, ncclUint64, ncclMax, comm_of(c), c->stream));
-  PM_CUDA(c, cudaMemcpyAsync(host_value, d, 8, cudaMemcpyDeviceToHost, c->stream));
-  PM_CUDA(c, cudaStreamSynchronize(c->stream));
-  cudaFree(d);
-  return 0;
-}
-
-inline int comm_allreduce_sum_u64(pm_ctx* c, uint64_t* host_values, int n) {
-  if (c->n_ranks == 1) return 0;
-  unsigned long long* d = nullptr;
-  PM_CUDA(c, cudaMalloc((void**)&d, 8 * n));
+  if (n > 8 || !c->d_scratch) return fail(c, PM_ERR_ARG, "comm_allreduce_u64: bad size");
+  unsigned long long* d = c->d_scratch;
   PM_CUDA(c, cudaMemcpyAsync(d, host_values, 8 * n, cudaMemcpyHostToDevice, c->stream));
-  PM_NCCL(c, ncclAllReduce(d, d, n, ncclUint64, ncclSum, comm_of(c), c->stream));
+  PM_NCCL(c, ncclAllReduce(d, d, n, ncclUint64, op, comm_of(c), c->stream));
   PM_CUDA(c, cudaMemcpyAsync(host_values, d, 8 * n, cudaMemcpyDeviceToHost, c->stream));
   PM_CUDA(c, cudaStreamSynchronize(c->stream));
-  cudaFree(d);
   return 0;
 }
+inline int comm_allreduce_max_u64(pm_ctx* c, uint64_t* host_value) { return comm_allreduce_u64(c, host_value, 1, ncclMax); }
+inline int comm_allreduce_sum_u64(pm_ctx* c, uint64_t* host_values, int n) { return comm_allreduce_u64(c, host_values, n, ncclSum); }
 
 }  // namespace pm

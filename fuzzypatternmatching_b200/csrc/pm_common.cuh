@@ -66,6 +66,8 @@ struct DevCounters {
   unsigned long long out_n[PM_MAX_RANKS];  // tokens / walks this rank stored in the inbox region of rank g during the current hop
   uint32_t ndelta;              // mask changes this rank published in the current step
   uint32_t pad2;
+  unsigned long long peak_out;  // largest inbox region fill of any hop (sizes the next run's inboxes)
+  unsigned long long ce_n;      // closing-edge keys filed in the hash set
 };
 
 // what every rank contributes to the per-step all-gather (= the barrier)
@@ -117,6 +119,7 @@ struct pm_ctx {
   pm::PeerTab peers{};             // host copy of c_peer
   std::vector<void*> ipc_open;     // peer mappings currently open
   pm::StepMsg* step_msg = nullptr; // device: [1 + G] (mine, then everyone's)
+  unsigned long long* d_scratch = nullptr;  // device: 8 words for small all-reduces
   pm::StepMsg* h_step = nullptr;   // pinned: [G]
   uint2* din[2] = {nullptr, nullptr};   // delta inboxes (G regions of dcap)
   uint2* tin[2] = {nullptr, nullptr};   // token inboxes (G regions of tcap)
@@ -166,7 +169,9 @@ struct pm_ctx {
   unsigned long long* hset = nullptr;  // (vertex, source) set, open addressing
   uint64_t hset_cap = 0;
   uint64_t hset_use = 0;            // power-of-two part of the table the current constraint uses
-  std::vector<uint64_t> pool_seen;  // per constraint: most tokens ever stored (sizes the next run's table)
+  std::vector<uint64_t> pool_seen;  // per constraint: most tokens ever stored (sizes the next run's pool / inbox regions)
+  std::vector<uint64_t> keys_seen;  // per constraint: most keys ever held by the hash set (sizes the next run's table)
+  std::map<std::string, std::vector<uint64_t>> keys_cache;
   std::string pat_key;              // pattern directory the sizes belong to
   std::map<std::string, std::vector<uint64_t>> pool_cache;
   uint2* pool = nullptr;            // token pool: nem_1 (vertex, source); TDS (parent index, vertex)

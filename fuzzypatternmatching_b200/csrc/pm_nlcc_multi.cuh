@@ -100,6 +100,133 @@ __device__ __forceinline__ void route_tokens(const NlcArgs& a, const bool (&flag
 }
 
 // ---------------------------------------------------------------------------
+// Closing-edge set of a cycle constraint.  The closing two hops (see k_nem1_close_cycle) need
+// "is u a neighbour of the source s that passes the tests of the last interior hop C?" at the GPU that
+// owns the token's vertex, but E_s lives at the owner of s, and peer loads (about 2 us each, never cached
+// in L2) make a remote binary search per candidate far too slow.  Every rank therefore publishes the
+// qualifying (s, u) pairs of its own sources to ALL ranks once per constraint — a broadcast through the
+// token inboxes, a few MB — and every rank files them in its hash set under a tag bit.  The closing
+// kernel then does one local probe per candidate.
+// ---------------------------------------------------------------------------
+#define PM_CE_TAG 0x8000000000000000ull  // vertex slots are < 2^31, so (vertex, source) keys never carry bit 63
+
+template <bool STREAM>
+__global__ void __launch_bounds__(kBlock) k_close_keys_m(NlcArgs a, const uint32_t* __restrict__ l0,
+                                                          const uint32_t* __restrict__ l1,
+                                                          const uint32_t* __restrict__ l2, int cur, int hn) {
+  const uint32_t c0 = a.cnt->fr_n[cur][0], c1 = a.cnt->fr_n[cur][1], c2 = a.cnt->fr_n[cur][2];
+  const uint32_t total = c0 + c1 + c2;
+  const uint32_t want_lab = c_nlc.lab[hn];
+  constexpr int GROUP = 8;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t gl = lane % GROUP, gw = lane / GROUP;
+  const uint32_t lt = (1u << lane) - 1u;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t base = warp * 4; base < total; base += nwarps * 4) {
+    const uint32_t i = base + gw;
+    uint32_t s = 0, d = 0;
+    uint64_t row = 0;
+    if (i < total) {
+      const uint32_t li = i < c0 ? l0[i] : (i < c0 + c1 ? l1[i - c0] : l2[i - c0 - c1]);
+      s = li + a.base;
+      const uint32_t T = a.S[s];
+      // a source of the constraint that can also receive the closing hop (nem_1.hpp:428-451, 557-581)
+      if (T != 0 && hop_ok(T, a.cls[s], 0) && hop_ok(T, a.cls[s], hn + 1)) {
+        d = a.adeg[li];
+        row = (uint64_t)a.rowblk[li] * 8;
+      }
+    }
+    const uint32_t passes = (d + GROUP * 4 - 1) / (GROUP * 4);
+    const uint32_t maxp = __reduce_max_sync(0xffffffffu, passes);
+    for (uint32_t p = 0; p < maxp; ++p) {
+      const uint32_t j0 = p * GROUP * 4 + gl * 4;
+      uint4 q = make_uint4(0, 0, 0, 0);
+      uint32_t l4 = 0;
+      if (j0 < d) {
+        q = *reinterpret_cast<const uint4*>(a.colw + row + j0);
+        if (STREAM) l4 = *reinterpret_cast<const uint32_t*>(a.labw + row + j0);
+      }
+      const uint32_t u[4] = {q.x & PM_IDMASK, q.y & PM_IDMASK, q.z & PM_IDMASK, q.w & PM_IDMASK};
+      bool ok[4];
+      uint32_t n = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        bool may = j0 + k < d && u[k] != s;
+        if (STREAM) may = may && ((l4 >> (8 * k)) & 0xffu) == want_lab;
+        ok[k] = false;
+        if (may) {
+          const uint32_t su = a.S[u[k]];
+          ok[k] = su != 0 && ((su >> c_nlc.I[hn]) & 1u) && (STREAM || a.cls[u[k]] == c_nlc.cls[hn]);
+        }
+        n += ok[k];
+      }
+      // one reservation per warp and pass
+      uint32_t incl = n;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o) incl += t;
+      }
+      const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+      if (tot == 0) continue;
+      unsigned long long pos = 0;
+      if (lane == 31) pos = atomicAdd(&a.cnt->out_n[0], (unsigned long long)tot);
+      pos = __shfl_sync(0xffffffffu, pos, 31) + incl - n;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (ok[k]) {
+          if (pos < c_peer.tcap) {
+            const uint2 key = make_uint2(u[k], s);
+            for (int g = 0; g < c_peer.G; ++g) c_peer.tin[a.par][g][(unsigned long long)c_peer.rank * c_peer.tcap + pos] = key;
+          } else {
+            a.cnt->overflow = 1u;
+          }
+          ++pos;
+        }
+    }
+  }
+  (void)lt;
+}
+
+// the same count goes to every rank
+__global__ void k_close_keys_count_m(DevCounters* cnt) {
+  const unsigned long long n = cnt->out_n[0];
+  for (int g = 1; g < c_peer.G; ++g) cnt->out_n[g] = n;
+}
+
+__global__ void __launch_bounds__(kBlock) k_close_ingest_m(NlcArgs a) {
+  const TokSrc src = tok_src(a);
+  const uint2* __restrict__ in = c_peer.tin[a.par ^ 1][c_peer.rank];
+  for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < src.total;
+       t += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint2 k = in[tok_locate(src, t, c_peer.tcap)];
+    const unsigned long long key = PM_CE_TAG | ((unsigned long long)k.y << 32) | k.x;  // (source, neighbour)
+    uint64_t h = mix64(key) & a.hset_mask;
+    int probe = 0;
+    for (; probe < 256; ++probe) {
+      const unsigned long long prev = atomicCAS(&a.hset[h], PM_HSET_EMPTY, key);
+      if (prev == PM_HSET_EMPTY || prev == key) break;
+      h = (h + 1) & a.hset_mask;
+    }
+    if (probe == 256) a.cnt->overflow = 1u;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.cnt->ce_n = src.total;
+}
+
+__device__ __forceinline__ bool close_edge_known(const NlcArgs& a, uint32_t s, uint32_t u) {
+  const unsigned long long key = PM_CE_TAG | ((unsigned long long)s << 32) | u;
+  uint64_t h = mix64(key) & a.hset_mask;
+  for (int probe = 0; probe < 256; ++probe) {
+    const unsigned long long x = a.hset[h];
+    if (x == key) return true;
+    if (x == PM_HSET_EMPTY) return false;
+    h = (h + 1) & a.hset_mask;
+  }
+  return false;
+}
+
+// ---------------------------------------------------------------------------
 // nem_1 across GPUs: tokens of the previous hop (inbox `par ^ 1`) -> hop hn (inbox `par` of the owners)
 //   MODE 0: interior hop, 1: final hop of a path or (generic) cycle constraint, 2: closing two hops of a cycle
 //   first: the tokens are the sources themselves (no aggregation test)
@@ -114,14 +241,11 @@ __global__ void __launch_bounds__(kBlock) k_nem1_hop_m(NlcArgs a, int hn, int fi
   const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
   const uint32_t want_lab = c_nlc.lab[hn];
-  const uint32_t nlmax = c_peer.nlmax;
   unsigned long long fan = 0, accepted = 0;
   for (uint64_t base = warp * 4; base < src.total; base += nwarps * 4) {
     const uint64_t t = base + gw;
     bool has = t < src.total;
-    uint32_t v = 0, s = 0, d = 0, ds = 0;
-    uint64_t rs = 0;
-    uint32_t os = 0;
+    uint32_t v = 0, s = 0, d = 0;
     uint32_t fresh = 1;
     if (has) {
       const uint2 tk = in[tok_locate(src, t, c_peer.tcap)];
@@ -138,14 +262,7 @@ __global__ void __launch_bounds__(kBlock) k_nem1_hop_m(NlcArgs a, int hn, int fi
       if (MODE == 1 && !c_nlc.valid_cycle && a.ok[s]) d = 0;  // acknowledged path source: later tokens are moot
       if (MODE == 2) {
         const uint32_t ss = a.S[s];
-        if (ss != 0 && hop_ok(ss, a.cls[s], hn + 1)) {  // receiver tests of the closing hop at the source
-          os = s / nlmax;
-          const uint32_t li = s - os * nlmax;
-          ds = c_peer.adeg[os][li];
-          rs = (uint64_t)c_peer.rowblk[os][li] * 8;
-        } else {
-          d = 0;
-        }
+        if (ss == 0 || !hop_ok(ss, a.cls[s], hn + 1)) d = 0;  // receiver tests of the closing hop at the source
       }
     }
     const uint64_t row = has ? (uint64_t)a.rowblk[v - a.base] * 8 : 0;
@@ -168,24 +285,19 @@ __global__ void __launch_bounds__(kBlock) k_nem1_hop_m(NlcArgs a, int hn, int fi
         if (STREAM) may = may && ((l4 >> (8 * k)) & 0xffu) == want_lab;
         if (MODE == 2) may = may && u[k] != s;
         if (!may) continue;
-        uint32_t b = 0;
-        if (MODE == 2) {  // u must also be a neighbour of the source (row of s, possibly on a peer)
-          const uint32_t* __restrict__ cs = c_peer.colw[os];
-          uint32_t e = ds;
-          while (b < e) {
-            const uint32_t mid = (b + e) >> 1;
-            const uint32_t x = cs[rs + mid] & PM_IDMASK;
-            if (x < u[k]) b = mid + 1; else e = mid;
+        if (MODE == 2) {
+          // u must be a qualifying neighbour of the source: one probe of the closing-edge set (which
+          // already holds the label / template-bit tests of hop C, evaluated by the owner of s)
+          pass[k] = close_edge_known(a, s, u[k]);
+          if (pass[k]) {
+            ack_source(a, s);
+            a.cnt->found = 1u;
+            mark_edge_m(s, u[k]);  // rare: only completed cycles get here
           }
-          if (b >= ds || (cs[rs + b] & PM_IDMASK) != u[k]) continue;
+          continue;
         }
         const uint32_t su = a.S[u[k]];
         pass[k] = su != 0 && ((su >> c_nlc.I[hn]) & 1u) && (STREAM || a.cls[u[k]] == c_nlc.cls[hn]);
-        if (MODE == 2 && pass[k]) {
-          ack_source(a, s);
-          a.cnt->found = 1u;
-          atomicOr(&c_peer.colw[os][rs + b], 0x80000000u);
-        }
       }
       if (MODE == 1) {
 #pragma unroll

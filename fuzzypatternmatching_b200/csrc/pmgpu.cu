@@ -121,8 +121,11 @@ bool nem1_order_independent(const Constraint& k) {
 // Token storage for one constraint.  One rank: the token pool.  Several ranks: the two token inboxes
 // (G sender regions of pool_cap tokens each), which every peer must map — growing them is collective,
 // so the callers agree on pool_cap first.
-int nlcc_reserve(pm_ctx* c, uint64_t pool_cap) {
-  if (pool_cap <= c->pool_cap) return 0;
+int nlcc_reserve(pm_ctx* c, uint64_t pool_cap, uint64_t key_cap) {
+  uint64_t hc_want = 1;
+  while (hc_want < 2 * key_cap) hc_want <<= 1;
+  if (pool_cap <= c->pool_cap && hc_want <= c->hset_cap) return 0;
+  pool_cap = std::max(pool_cap, c->pool_cap);
   const bool multi = c->n_ranks > 1;
   if (multi) comm_close_all(c);
   dev_free(c->pool);
@@ -130,8 +133,7 @@ int nlcc_reserve(pm_ctx* c, uint64_t pool_cap) {
   dev_free(c->tin[0]);
   dev_free(c->tin[1]);
   c->pool_cap = c->hset_cap = c->tcap = 0;
-  uint64_t hc = 1;
-  while (hc < 2 * pool_cap) hc <<= 1;
+  const uint64_t hc = hc_want;
   int rc;
   if (!multi) {
     if ((rc = dev_alloc(c, &c->pool, pool_cap))) return rc;
@@ -185,6 +187,7 @@ void pm_destroy(pm_ctx* c) {
   state_free(c);
   graph_free(c);
   if (comm) ncclCommDestroy(comm);
+  if (c->d_scratch) cudaFree(c->d_scratch);
   for (auto e : c->events) cudaEventDestroy(e);
   for (int b = 0; b < 4; ++b) for (int k = 0; k < 2; ++k) if (c->kev[b][k]) cudaEventDestroy(c->kev[b][k]);
   cudaStreamDestroy(c->stream);
@@ -219,6 +222,7 @@ int pm_comm_init(pm_ctx* c, int rank, int n_ranks, const char* id_bytes) {
   c->comm = comm;
   c->rank = rank;
   c->n_ranks = n_ranks;
+  PM_CUDA(c, cudaMalloc((void**)&c->d_scratch, 64));
   return 0;
 }
 
@@ -421,6 +425,9 @@ int pm_pattern_load_dir(pm_ctx* c, const char* dir) {
     auto it = c->pool_cache.find(c->pat_key);
     if (it != c->pool_cache.end() && it->second.size() == p.constraints.size()) c->pool_seen = it->second;
     else c->pool_seen.assign(p.constraints.size(), 0);
+    auto it2 = c->keys_cache.find(c->pat_key);
+    if (it2 != c->keys_cache.end() && it2->second.size() == p.constraints.size()) c->keys_seen = it2->second;
+    else c->keys_seen.assign(p.constraints.size(), 0);
   }
   c->subgraphs.assign(p.constraints.size(), {});
   c->subgraph_width.assign(p.constraints.size(), 0);
@@ -675,14 +682,21 @@ int pm_nlcc(pm_ctx* c, int pl, int mode, int* pattern_found, int* token_source_d
   // Size the (vertex, source) set for what this constraint stored last time (or for the current
   // edge maps on its first run); an undersized table is detected and the constraint retried.
   if (c->pool_seen.size() != c->pat.constraints.size()) c->pool_seen.assign(c->pat.constraints.size(), 0);
+  if (c->keys_seen.size() != c->pat.constraints.size()) c->keys_seen.assign(c->pat.constraints.size(), 0);
   const uint64_t ne_now = c->rows.empty() ? c->E : c->rows.back().n_edges;
   uint64_t want_pool = c->pool_seen[pl] ? c->pool_seen[pl] + c->pool_seen[pl] / 2 + 4096 : 2 * ne_now + 65536;
   want_pool = std::max<uint64_t>(want_pool, 1ull << 18);
-  if (multi && (rc = comm_allreduce_max_u64(c, &want_pool))) return rc;  // growing the inboxes is collective
-  if ((rc = nlcc_reserve(c, want_pool))) return rc;
+  uint64_t want_keys = c->keys_seen[pl] ? c->keys_seen[pl] + c->keys_seen[pl] / 2 + 4096 : want_pool;
+  if (multi) {  // growing the inboxes is collective
+    uint64_t w[2] = {want_pool, want_keys};
+    if ((rc = comm_allreduce_u64(c, w, 2, ncclMax))) return rc;
+    want_pool = w[0];
+    want_keys = w[1];
+  }
+  if ((rc = nlcc_reserve(c, want_pool, want_keys))) return rc;
   auto pick_table = [&]() {
     uint64_t use = 1;
-    while (use < 2 * want_pool) use <<= 1;
+    while (use < 2 * want_keys) use <<= 1;
     c->hset_use = std::min(use, c->hset_cap);
   };
   pick_table();
@@ -706,6 +720,25 @@ int pm_nlcc(pm_ctx* c, int pl, int mode, int* pattern_found, int* token_source_d
     if (!tds) PM_CUDA(c, cudaMemsetAsync(c->hset, 0xFF, c->hset_use * sizeof(unsigned long long), st));
     // several ranks: `ok` doubles as this GPU's "already acknowledged" cache for foreign sources
     if (multi) PM_CUDA(c, cudaMemsetAsync(c->ok, 0, c->nlmax * c->n_ranks, st));
+    const bool dbg = getenv("PM_DEBUG_HOPS") != nullptr;
+    std::vector<cudaEvent_t> dev;
+    auto mark = [&]() { if (dbg) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); dev.push_back(e); } };
+    mark();
+    if (multi && close2) {
+      // every rank learns the qualifying (source, neighbour) pairs of the closing hop (k_close_keys_m)
+      NlcArgs ka = nlc_args(c, nullptr, 0);
+      (sm ? k_close_keys_m<true> : k_close_keys_m<false>)<<<grid, kBlock, 0, st>>>(ka, c->fr[cur][0], c->fr[cur][1],
+                                                                                 c->fr[cur][2], cur, (int)k.C);
+      PM_LAUNCH_CHECK(c);
+      k_close_keys_count_m<<<1, 1, 0, st>>>(c->cnt);
+      PM_LAUNCH_CHECK(c);
+      if ((rc = comm_step(c))) return rc;
+      c->step_parity ^= 1;
+      mark();
+      k_close_ingest_m<<<grid, kBlock, 0, st>>>(nlc_args(c, nullptr, 0));
+      PM_LAUNCH_CHECK(c);
+      mark();
+    }
     NlcArgs a = nlc_args(c, d_matches, match_cap);
     k_nlcc_sources<<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], c->fr[cur][1], c->fr[cur][2], cur, tds ? 1 : 0);
     PM_LAUNCH_CHECK(c);
@@ -741,6 +774,7 @@ int pm_nlcc(pm_ctx* c, int pl, int mode, int* pattern_found, int* token_source_d
       // (parity a.par), the all-gather publishes the region fill counts and is the barrier
       if ((rc = comm_step(c))) return rc;  // level 0 (the sources) is in inbox `par`
       c->step_parity ^= 1;
+      mark();
       for (int hn = 1; hn <= (int)k.C + 1; ++hn) {
         const bool fin = hn == (int)k.C + 1;
         const int first = hn == 1 ? 1 : 0;
@@ -758,11 +792,19 @@ int pm_nlcc(pm_ctx* c, int pl, int mode, int* pattern_found, int* token_source_d
           (sm ? k_nem1_hop_m<0, true> : k_nem1_hop_m<0, false>)<<<grid, kBlock, 0, st>>>(a, hn, first);
         }
         PM_LAUNCH_CHECK(c);
+        mark();
         if ((rc = comm_step(c))) return rc;  // after the last hop: the acknowledgements have landed
+        mark();
         c->step_parity ^= 1;
         if (last) break;
       }
       if ((rc = sync_counters(c))) return rc;
+      if (dbg) {
+        fprintf(stderr, "[pm] rank %d pl=%d attempt %d tcap %llu hop kernel/barrier ms:", c->rank, pl, attempt, (unsigned long long)c->tcap);
+        for (size_t i = 0; i + 1 < dev.size(); ++i) { float ms = 0; cudaEventElapsedTime(&ms, dev[i], dev[i + 1]); fprintf(stderr, " %.3f", ms); }
+        fprintf(stderr, "\n");
+        for (auto e : dev) cudaEventDestroy(e);
+      }
       if ((rc = comm_step_fetch(c))) return rc;
     }
     hi = c->h_cnt->pool_n;
@@ -779,13 +821,17 @@ int pm_nlcc(pm_ctx* c, int pl, int mode, int* pattern_found, int* token_source_d
     }
     if (!overflow) {
       n_matches = matches_here;
-      c->pool_seen[pl] = std::max<uint64_t>(c->pool_seen[pl], c->h_cnt->pool_n);
+      // several ranks: what must fit is the fullest inbox region of any hop (tokens arrive undeduplicated)
+      c->pool_seen[pl] = std::max<uint64_t>(c->pool_seen[pl], multi ? (uint64_t)c->h_cnt->peak_out : (uint64_t)c->h_cnt->pool_n);
+      c->keys_seen[pl] = std::max<uint64_t>(c->keys_seen[pl], (uint64_t)c->h_cnt->pool_n + c->h_cnt->ce_n);
       c->pool_cache[c->pat_key] = c->pool_seen;
+      c->keys_cache[c->pat_key] = c->keys_seen;
       break;
     }
     if (attempt >= 6) { dev_free(d_matches); return fail(c, PM_ERR_CAPACITY, "NLCC token pool exhausted"); }
     want_pool = std::max<uint64_t>(want_pool * 4, (uint64_t)c->h_cnt->matches + 1);
-    if ((rc = nlcc_reserve(c, want_pool))) { dev_free(d_matches); return rc; }
+    want_keys *= 4;
+    if ((rc = nlcc_reserve(c, want_pool, want_keys))) { dev_free(d_matches); return rc; }
     pick_table();
   }
   fanout = c->h_cnt->fanout;

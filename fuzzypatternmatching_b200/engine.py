@@ -72,12 +72,15 @@ class Engine:
         src[1::2], dst[1::2] = e[:, 1], e[:, 0]
         self.graph_from_slots(n_vertices, src, dst)
 
-    def graph_from_csr(self, rowptr, col, degree_multi):
-        """Host CSR (distinct neighbours, ascending) + multigraph degrees -> device store."""
+    def graph_from_csr(self, rowptr, col, degree_multi, n_vertices=None):
+        """Host CSR (distinct neighbours, ascending) + multigraph degrees -> device store.
+        Several ranks: the rows of the vertices this rank owns (local row i = vertex i * n_ranks + rank)
+        and the global vertex count."""
         rowptr = np.ascontiguousarray(rowptr, dtype=np.uint64)
         col = np.ascontiguousarray(col, dtype=np.uint32)
         degree_multi = np.ascontiguousarray(degree_multi, dtype=np.uint64)
-        self._chk(self._lib.pm_graph_from_csr(self._h, len(rowptr) - 1, rowptr.ctypes.data, col.ctypes.data,
+        n = len(rowptr) - 1 if n_vertices is None else int(n_vertices)
+        self._chk(self._lib.pm_graph_from_csr(self._h, n, rowptr.ctypes.data, col.ctypes.data,
                                               degree_multi.ctypes.data))
 
     def graph_rmat(self, scale, gen_ranks):

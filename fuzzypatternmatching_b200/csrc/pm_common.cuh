@@ -18,7 +18,7 @@
 #define PM_MAX_RANKS 8           // GPUs of one NVSwitch box
 
 // degree bins (current active degree) -> kernel shape
-#define PM_SMALL_MAX 32u    // <= 32 slots: one 8-lane group, one pass of uint4 loads
+#define PM_TINY_MAX 16       // <= 16 slots: one THREAD per vertex (four uint4 loads)
 #define PM_MID_MAX 4096u    // <= 4096 slots: one warp per vertex
                             // larger: one CTA per vertex
 
@@ -148,12 +148,12 @@ struct pm_ctx {
 
   // ---- per-pattern state (device) -----------------------------------------------
   uint16_t* S = nullptr;    // [V] template_vertices[v] (T_arr) while v is active and in the map, else 0
-  uint16_t* Tst = nullptr;  // [V] vertex_state.template_vertices (T_state)
+                            // (vertex_state.template_vertices, T_state, lives in the frontier entries)
   uint32_t* adeg = nullptr; // [V] |E_v|
   uint8_t* cls = nullptr;   // [V] label class (index into the template's distinct labels, PM_NOCLASS = none)
-  uint32_t* fr[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};  // frontier lists by bin
+  uint4* fr[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // frontier entry lists [buffer][main, big rows]
   int cur = 0;              // which frontier buffer is current
-  bool bin_live[3] = {true, true, true};
+  bool bin_live[2] = {true, true};  // main list / big-row list non-empty at the last host sync
   bool filter_done = false;     // the fused init filter ran: the first superstep skips its own filter
   float init_ms = 0;            // its device time (accounted to LP superstep 0)
   uint64_t init_candidates = 0;  // bin b or a larger one was non-empty at the last host sync
@@ -190,6 +190,8 @@ struct pm_ctx {
   pm_run_summary_t summary{};
   std::vector<cudaEvent_t> events;
   // CUDA-event timing of the first-superstep scan kernels (the dominant kernels), per bin
+  std::vector<cudaEvent_t> kev2;   // per superstep: before main scan, after it, after the big-row scan
+  std::vector<int> kev2_cls;       // per superstep: kernel class of the main scan (0 first, 1 later)
   cudaEvent_t kev[4][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
   pm_kernel_stats_t kstat[4] = {};  // [3]: the first-superstep signature filter
 };

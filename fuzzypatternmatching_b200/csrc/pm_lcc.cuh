@@ -22,6 +22,14 @@
 // delivers (the one exception, SURVEY A.6 #11 combined with #4, is detected by
 // the oracle's hazard counters).  k_lcc_commit then publishes S and builds the
 // next frontier, so S is single-buffered yet the sweep stays Jacobi.
+//
+// Frontier.  The vertices still in the vertex_state_map are kept as a list of
+// 16-byte ENTRIES {local row, row start (sectors), |E_v|, T_state}: a scan streams
+// its entries (coalesced), needs no dependent gather before it can fetch the row,
+// and writes its result (new |E_v|, new T_state) back into the entry.  Rows of up to
+// PM_TINY_MAX slots are handled by ONE thread each (32 independent rows in flight per
+// warp: these scans are latency bound, not bandwidth bound), longer rows by the whole
+// warp with the next row's first pass prefetched, rows above PM_MID_MAX by a CTA.
 #pragma once
 
 #include "pm_common.cuh"
@@ -56,33 +64,32 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
   return m;
 }
 
-// Appends up to ITEMS values per thread to one of three lists with ONE atomic per list
+// Appends up to ITEMS entries per thread to one of two lists with ONE atomic per list
 // and block (a returning atomic on a single address retires ~1 per clock chip-wide, so
 // per-warp atomics would serialise the whole grid).  Must be called by every thread of
 // the block; order inside a block follows (item, thread).
 template <int ITEMS>
-__device__ __forceinline__ void block_bin_append(const bool (&flag)[ITEMS], const int (&bin)[ITEMS],
-                                                 const uint32_t (&val)[ITEMS], uint32_t* d0, uint32_t* d1,
-                                                 uint32_t* d2, uint32_t* counters) {
-  __shared__ uint32_t s_w[kBlock / 32][3];
-  __shared__ uint32_t s_base[3];
+__device__ __forceinline__ void block_append2(const bool (&flag)[ITEMS], const int (&bin)[ITEMS],
+                                              const uint4 (&val)[ITEMS], uint4* d0, uint4* d1, uint32_t* counters) {
+  __shared__ uint32_t s_w[kBlock / 32][2];
+  __shared__ uint32_t s_base[2];
   const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const uint32_t lt = lanemask_lt();
   uint32_t off[ITEMS];
-  uint32_t tot[3] = {0, 0, 0};
+  uint32_t tot[2] = {0, 0};
 #pragma unroll
   for (int k = 0; k < ITEMS; ++k) {
     off[k] = 0;
 #pragma unroll
-    for (int b = 0; b < 3; ++b) {
+    for (int b = 0; b < 2; ++b) {
       const uint32_t m = __ballot_sync(0xffffffffu, flag[k] && bin[k] == b);
       if (flag[k] && bin[k] == b) off[k] = tot[b] + __popc(m & lt);
       tot[b] += __popc(m);
     }
   }
-  if (lane == 0) { s_w[w][0] = tot[0]; s_w[w][1] = tot[1]; s_w[w][2] = tot[2]; }
+  if (lane == 0) { s_w[w][0] = tot[0]; s_w[w][1] = tot[1]; }
   __syncthreads();
-  if (threadIdx.x < 3) {
+  if (threadIdx.x < 2) {
     uint32_t t = 0;
     for (uint32_t i = 0; i < blockDim.x / 32; ++i) t += s_w[i][threadIdx.x];
     s_base[threadIdx.x] = t ? atomicAdd(&counters[threadIdx.x], t) : 0u;
@@ -94,29 +101,28 @@ __device__ __forceinline__ void block_bin_append(const bool (&flag)[ITEMS], cons
       const int b = bin[k];
       uint32_t base = s_base[b];
       for (uint32_t i = 0; i < w; ++i) base += s_w[i][b];
-      uint32_t* dst = b == 0 ? d0 : (b == 1 ? d1 : d2);
-      dst[base + off[k]] = val[k];
+      (b == 0 ? d0 : d1)[base + off[k]] = val[k];
     }
   __syncthreads();
 }
 
 struct LccArgs {
-  const uint32_t* rowblk;
-  const uint32_t* deg;
   const uint32_t* col0;
   uint32_t* colw;
   uint16_t* S;
-  uint16_t* Tst;
   uint32_t* adeg;
   const uint8_t* cls;
   const uint8_t* lab0;  // [Epad] label of the neighbour in col0 (labels < 64 only)
   uint8_t* labw;        // [Epad] same for colw, moved along by the row compaction
   DevCounters* cnt;
   RowStat* row;   // accumulator of this superstep
-  int bin;        // degree bin this launch serves (row statistics)
-  uint32_t base;  // first slot of this rank: frontier lists and rank-local arrays are indexed by slot - base
+  uint32_t base;  // first slot of this rank: entries and rank-local arrays are indexed by slot - base
   int par;        // delta inbox the commit of this superstep publishes into
 };
+
+// frontier entry: x = local row (slot - base), y = row start in sectors, z = |E_v| (deg(v) before the
+// first scan), w = T_state (vertex_state.template_vertices)
+__device__ __forceinline__ int bin_of(uint32_t d) { return d <= PM_MID_MAX ? 0 : 1; }
 
 // Publishes "the mask of my vertex `slot` is now `mask`" to every peer: the pair is stored straight
 // into the sender's region of each peer's delta inbox (NVLink stores, one position per change, reserved
@@ -153,56 +159,48 @@ __global__ void __launch_bounds__(kBlock) k_apply_deltas(uint16_t* __restrict__ 
 
 // ---------------------------------------------------------------------------
 // per-pattern initialisation (beta.cpp:484-492 + the label test every vertex
-// performs in the first superstep, ee.hpp:371-380 / :523-546):
-//   cls[v] = class of label[v] for EVERY vertex (the first scan gathers it);
+// performs in the first superstep, ee.hpp:371-380 / :523-546), labels >= 64:
+//   cls[v] = class of label[v] for EVERY local vertex (the first scan gathers it);
 //   candidates (label matches a template vertex, degree > 0) get S[v] =
-//   labelmask(label[v]) and are appended to the frontier bin of their degree.
+//   labelmask(label[v]) and an entry in the frontier.
 //   S of a non-candidate is never read: every later gather goes through an edge
 //   map, and edge maps only ever hold candidates.
-// SMALL = labels are bytes < 64 (lab8 + 64-entry class table), else u64 compare.
 // ---------------------------------------------------------------------------
-template <bool SMALL>
 __global__ void __launch_bounds__(kBlock) k_init_state(const uint64_t* __restrict__ label,
-                                                        const uint8_t* __restrict__ lab8,
-                                                        const uint32_t* __restrict__ deg, uint64_t V,
+                                                        const uint32_t* __restrict__ deg,
+                                                        const uint32_t* __restrict__ rowblk, uint64_t V,
                                                         uint8_t* __restrict__ cls, uint16_t* __restrict__ S,
-                                                        uint32_t* fr_small, uint32_t* fr_mid, uint32_t* fr_big,
-                                                        DevCounters* cnt, int buf) {
-  __shared__ uint8_t s_cl[64];
+                                                        uint4* fr_main, uint4* fr_big, DevCounters* cnt, int buf) {
   __shared__ uint16_t s_lm[17];
-  if (threadIdx.x < 64) s_cl[threadIdx.x] = c_pat.cls_of_label[threadIdx.x];
   if (threadIdx.x < 17) s_lm[threadIdx.x] = c_pat.LMc[threadIdx.x];
   __syncthreads();
-  constexpr int IT = 8;
+  constexpr int IT = 4;
   const uint64_t tile = (uint64_t)blockDim.x * IT;
   for (uint64_t base = (uint64_t)blockIdx.x * tile; base < V; base += (uint64_t)gridDim.x * tile) {
     bool cand[IT];
     int bin[IT];
-    uint32_t val[IT];
+    uint4 val[IT];
 #pragma unroll
     for (int k = 0; k < IT; ++k) {
       const uint64_t v = base + (uint64_t)k * blockDim.x + threadIdx.x;
-      uint32_t c = PM_NOCLASS, d = 0;
+      uint32_t c = PM_NOCLASS, d = 0, lm = 0;
       if (v < V) {
-        if (SMALL) {
-          c = s_cl[lab8[v] & 63];
-        } else {
-          const uint64_t lab = label[v];
+        const uint64_t lab = label[v];
 #pragma unroll
-          for (int q = 0; q < 16; ++q)
-            if (q < c_pat.ncls && c_pat.clabel[q] == lab) c = q;
-        }
+        for (int q = 0; q < 16; ++q)
+          if (q < c_pat.ncls && c_pat.clabel[q] == lab) c = q;
         cls[v] = (uint8_t)c;
         if (c != PM_NOCLASS) {
           d = deg[v];
-          if (d) S[v] = s_lm[c]; else c = PM_NOCLASS;
+          lm = s_lm[c];
+          if (d) S[v] = (uint16_t)lm; else c = PM_NOCLASS;
         }
       }
       cand[k] = c != PM_NOCLASS;
-      bin[k] = d <= PM_SMALL_MAX ? 0 : (d <= PM_MID_MAX ? 1 : 2);
-      val[k] = (uint32_t)v;
+      bin[k] = bin_of(d);
+      val[k] = make_uint4((uint32_t)v, cand[k] ? rowblk[v] : 0u, d, lm);
     }
-    block_bin_append<IT>(cand, bin, val, fr_small, fr_mid, fr_big, &cnt->fr_n[buf][0]);
+    block_append2<IT>(cand, bin, val, fr_main, fr_big, &cnt->fr_n[buf][0]);
   }
 }
 
@@ -216,19 +214,19 @@ __global__ void __launch_bounds__(kBlock) k_init_state(const uint64_t* __restric
 // is settled here from 8 bytes of signature instead of its whole row (tables c_pat.req / c_pat.rl).
 // Writes cls[v] and S[v] for EVERY vertex with coalesced stores (S = 0 unless the
 // vertex survives the first superstep's cover test) and appends the survivors to the
-// frontier bin of their degree.  Their rows are walked by the first scan afterwards.
+// frontier.  Their rows are walked by the first scan afterwards.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock) k_init_filter(const uint8_t* __restrict__ lab8,
                                                          const uint32_t* __restrict__ deg,
+                                                         const uint32_t* __restrict__ rowblk,
                                                          const unsigned long long* __restrict__ sig, uint64_t V,
                                                          uint8_t* __restrict__ cls, uint16_t* __restrict__ S,
-                                                         uint32_t* fr_small, uint32_t* fr_mid, uint32_t* fr_big,
-                                                         DevCounters* cnt, int buf) {
+                                                         uint4* fr_main, uint4* fr_big, DevCounters* cnt, int buf) {
   __shared__ uint8_t s_cl[64];
   __shared__ uint16_t s_lm[17];
   __shared__ unsigned long long s_rl[17];
-  __shared__ uint32_t s_w[kBlock / 32][3];
-  __shared__ uint32_t s_base[3];
+  __shared__ uint32_t s_w[kBlock / 32][2];
+  __shared__ uint32_t s_base[2];
   if (threadIdx.x < 64) s_cl[threadIdx.x] = c_pat.cls_of_label[threadIdx.x];
   if (threadIdx.x < 17) { s_lm[threadIdx.x] = c_pat.LMc[threadIdx.x]; s_rl[threadIdx.x] = c_pat.rl[threadIdx.x]; }
   __syncthreads();
@@ -239,7 +237,7 @@ __global__ void __launch_bounds__(kBlock) k_init_filter(const uint8_t* __restric
   bool any_removed = false;
   for (uint64_t base = (uint64_t)blockIdx.x * tile; base < V; base += (uint64_t)gridDim.x * tile) {
     const uint64_t v0 = base + (uint64_t)threadIdx.x * VPT;
-    uint32_t k0 = 0, k1 = 0, k2 = 0;  // bit j: vertex v0 + j survives the first superstep, by degree bin
+    uint32_t k0 = 0, k1 = 0;  // bit j: vertex v0 + j survives the first superstep (main / big list)
     if (v0 + VPT <= V) {
       const uint4 l16 = *reinterpret_cast<const uint4*>(lab8 + v0);
       const uint32_t lw[4] = {l16.x, l16.y, l16.z, l16.w};
@@ -267,7 +265,7 @@ __global__ void __launch_bounds__(kBlock) k_init_filter(const uint8_t* __restric
             any_removed = any_removed || (!surv && (sg & s_rl[c]) != 0ull);  // entered the map and left it (ee.hpp:941-946)
             ncand++;
             if (surv) {
-              if (d <= PM_SMALL_MAX) k0 |= 1u << j; else if (d <= PM_MID_MAX) k1 |= 1u << j; else k2 |= 1u << j;
+              if (d <= PM_MID_MAX) k0 |= 1u << j; else k1 |= 1u << j;
             } else {
               lm = 0;
             }
@@ -295,7 +293,7 @@ __global__ void __launch_bounds__(kBlock) k_init_filter(const uint8_t* __restric
           any_removed = any_removed || (!surv && (sg & s_rl[c]) != 0ull);
           ncand++;
           if (surv) {
-            if (d <= PM_SMALL_MAX) k0 |= 1u << j; else if (d <= PM_MID_MAX) k1 |= 1u << j; else k2 |= 1u << j;
+            if (d <= PM_MID_MAX) k0 |= 1u << j; else k1 |= 1u << j;
           } else {
             lm = 0;
           }
@@ -304,30 +302,32 @@ __global__ void __launch_bounds__(kBlock) k_init_filter(const uint8_t* __restric
         S[v] = (uint16_t)lm;
       }
     }
-    // block-aggregated append of the survivors: one atomic per bin and tile
-    const uint32_t n0 = __popc(k0), n1 = __popc(k1), n2 = __popc(k2);
-    uint32_t i0 = n0, i1 = n1, i2 = n2;
+    // block-aggregated append of the survivors' entries: one atomic per list and tile
+    const uint32_t n0 = __popc(k0), n1 = __popc(k1);
+    uint32_t i0 = n0, i1 = n1;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const uint32_t t0 = __shfl_up_sync(0xffffffffu, i0, o);
       const uint32_t t1 = __shfl_up_sync(0xffffffffu, i1, o);
-      const uint32_t t2 = __shfl_up_sync(0xffffffffu, i2, o);
-      if (lane >= (uint32_t)o) { i0 += t0; i1 += t1; i2 += t2; }
+      if (lane >= (uint32_t)o) { i0 += t0; i1 += t1; }
     }
-    if (lane == 31) { s_w[w][0] = i0; s_w[w][1] = i1; s_w[w][2] = i2; }
+    if (lane == 31) { s_w[w][0] = i0; s_w[w][1] = i1; }
     __syncthreads();
-    if (threadIdx.x < 3) {
+    if (threadIdx.x < 2) {
       uint32_t t = 0;
       for (uint32_t i = 0; i < blockDim.x / 32; ++i) t += s_w[i][threadIdx.x];
       s_base[threadIdx.x] = t ? atomicAdd(&cnt->fr_n[buf][threadIdx.x], t) : 0u;
     }
     __syncthreads();
-    if (k0 | k1 | k2) {
-      uint32_t o0 = s_base[0] + i0 - n0, o1 = s_base[1] + i1 - n1, o2 = s_base[2] + i2 - n2;
-      for (uint32_t i = 0; i < w; ++i) { o0 += s_w[i][0]; o1 += s_w[i][1]; o2 += s_w[i][2]; }
-      for (uint32_t rest = k0; rest; rest &= rest - 1) fr_small[o0++] = (uint32_t)(v0 + __ffs(rest) - 1);
-      for (uint32_t rest = k1; rest; rest &= rest - 1) fr_mid[o1++] = (uint32_t)(v0 + __ffs(rest) - 1);
-      for (uint32_t rest = k2; rest; rest &= rest - 1) fr_big[o2++] = (uint32_t)(v0 + __ffs(rest) - 1);
+    if (k0 | k1) {
+      uint32_t o0 = s_base[0] + i0 - n0, o1 = s_base[1] + i1 - n1;
+      for (uint32_t i = 0; i < w; ++i) { o0 += s_w[i][0]; o1 += s_w[i][1]; }
+      for (uint32_t rest = k0 | k1; rest; rest &= rest - 1) {
+        const int j = __ffs(rest) - 1;
+        const uint64_t v = v0 + j;
+        const uint4 e = make_uint4((uint32_t)v, rowblk[v], deg[v], (uint32_t)S[v]);
+        if ((k0 >> j) & 1u) fr_main[o0++] = e; else fr_big[o1++] = e;
+      }
     }
     __syncthreads();
   }
@@ -338,108 +338,206 @@ __global__ void __launch_bounds__(kBlock) k_init_filter(const uint8_t* __restric
 }
 
 // ---------------------------------------------------------------------------
-// scan: GROUP lanes walk the active adjacency of one vertex with uint4 loads
-// (4 slots per lane and pass), gather the neighbour masks, OR the heard masks and
-// compact the surviving neighbours to the front of the row.
+// scan of the main list: every warp takes 32 consecutive entries.
 //   FIRST = first superstep of the first iteration: walk the pristine adjacency
-//   col0 (all deg[v] slots), neighbour mask = labelmask via the class array
-//   (ee.hpp:519-561 sender, :368-404 receiver); otherwise walk keys(E_v) in colw.
-// ---------------------------------------------------------------------------
+//   col0 (all deg[v] slots), neighbour mask = labelmask via the label stream / class
+//   array (ee.hpp:519-561 sender, :368-404 receiver) and COPY the survivors into the
+//   working adjacency; otherwise walk keys(E_v) in colw and compact in place.
 //   STREAM = the label of every neighbour travels next to its id (lab0 / labw,
-//   labels < 64): the first superstep then needs no gather at all — ids and labels
-//   are both streamed — and later compactions keep labw aligned with colw for NLCC.
-template <int GROUP, bool FIRST, bool STREAM>
-__global__ void __launch_bounds__(kBlock) k_lcc_scan(LccArgs a, const uint32_t* __restrict__ list,
+//   labels < 64): the first superstep then needs no gather at all, and later
+//   compactions keep labw aligned with colw for NLCC.
+// ---------------------------------------------------------------------------
+template <bool FIRST, bool STREAM>
+__global__ void __launch_bounds__(kBlock) k_lcc_scan(LccArgs a, uint4* __restrict__ list,
                                                       const uint32_t* __restrict__ n_ptr) {
   __shared__ uint16_t s_lm[17];
   __shared__ uint16_t s_lml[64];  // label value -> labelmask
   if (threadIdx.x < 17) s_lm[threadIdx.x] = c_pat.LMc[threadIdx.x];
   if (threadIdx.x < 64) s_lml[threadIdx.x] = c_pat.LMc[c_pat.cls_of_label[threadIdx.x]];
   __syncthreads();
-  constexpr int GPW = 32 / GROUP;  // groups per warp
   const uint32_t lane = threadIdx.x & 31;
-  const uint32_t gl = lane % GROUP;
-  const uint32_t gw = lane / GROUP;
-  const uint32_t gmask = GROUP == 32 ? 0xffffffffu : (((1u << GROUP) - 1u) << (gw * GROUP));
-  const uint32_t lt = lanemask_lt() & gmask;
+  const uint32_t lt = lanemask_lt();
   const uint32_t n = *n_ptr;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t* __restrict__ src = FIRST ? a.col0 : a.colw;
+  const uint8_t* __restrict__ lsrc = FIRST ? a.lab0 : a.labw;
   unsigned long long scanned = 0, verts = 0;
-  for (uint32_t base = warp * GPW; base < n; base += nwarps * GPW) {
-    const uint32_t idx = base + gw;
+  for (uint32_t base = warp * 32; base < n; base += nwarps * 32) {
+    const uint32_t idx = base + lane;
     const bool has = idx < n;
-    uint32_t v = 0, d = 0, Tv = 0;
+    uint4 e = make_uint4(0, 0, 0, 0);
+    uint32_t Tv = 0;
     if (has) {
-      v = list[idx];
-      Tv = a.S[v + a.base];
-      d = FIRST ? a.deg[v] : a.adeg[v];
-      if (Tv == 0) d = 0;  // deactivated by NLCC since the last commit (beta.cpp:990-992)
+      e = list[idx];
+      Tv = a.S[e.x + a.base];
     }
+    uint32_t d = Tv ? e.z : 0u;  // Tv == 0: deactivated by NLCC since the last commit (beta.cpp:990-992)
     const uint32_t NBv = nb_of(Tv);
-    const uint64_t row = has ? (uint64_t)a.rowblk[v] * 8 : 0;
-    const uint32_t* __restrict__ src = FIRST ? a.col0 : a.colw;
-    const uint32_t passes = (d + GROUP * 4 - 1) / (GROUP * 4);
-    const uint32_t maxp = GROUP == 32 ? passes : __reduce_max_sync(0xffffffffu, passes);
+    const uint64_t row = (uint64_t)e.y * 8;
     uint32_t heard = 0, out = 0;
-    for (uint32_t p = 0; p < maxp; ++p) {
-      const uint32_t j0 = p * GROUP * 4 + gl * 4;
-      uint4 q = make_uint4(PM_SENTINEL, PM_SENTINEL, PM_SENTINEL, PM_SENTINEL);
-      uint32_t l4 = 0;
-      if (j0 < d) {
-        q = *reinterpret_cast<const uint4*>(src + row + j0);
-        if (STREAM) l4 = *reinterpret_cast<const uint32_t*>((FIRST ? a.lab0 : a.labw) + row + j0);
-      }
-      uint32_t u[4] = {q.x, q.y, q.z, q.w};
-      uint32_t m[4];
-      bool keep[4];
+
+    // ---- rows of up to PM_TINY_MAX slots: one thread each --------------------------------
+    if (d != 0u && d <= PM_TINY_MAX) {
+      uint4 q[PM_TINY_MAX / 4];
+      uint32_t l4[PM_TINY_MAX / 4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const bool act = j0 + k < d;
-        const uint32_t uu = u[k] & PM_IDMASK;
-        m[k] = 0;
-        if (act) {
-          if (FIRST) m[k] = STREAM ? (uint32_t)s_lml[(l4 >> (8 * k)) & 63u] : (uint32_t)s_lm[a.cls[uu]];
-          else m[k] = (uint32_t)a.S[uu];
+      for (int c = 0; c < PM_TINY_MAX / 4; ++c) {
+        q[c] = make_uint4(PM_SENTINEL, PM_SENTINEL, PM_SENTINEL, PM_SENTINEL);
+        l4[c] = 0;
+        if ((uint32_t)(4 * c) < d) {
+          q[c] = *reinterpret_cast<const uint4*>(src + row + 4 * c);
+          if (STREAM) l4[c] = *reinterpret_cast<const uint32_t*>(lsrc + row + 4 * c);
         }
       }
-      uint32_t cnt_lane = 0;
-      uint32_t below = 0;
+      uint32_t m[PM_TINY_MAX];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const bool act = j0 + k < d;
-        const bool valid = (m[k] & NBv) != 0u;
-        const bool pre = !FIRST && act && (u[k] >> 31);
-        keep[k] = valid || pre;
-        if (valid) heard |= m[k];
-        const uint32_t b = __ballot_sync(0xffffffffu, keep[k]);
-        below += __popc(b & lt);
-        cnt_lane += __popc(b & gmask);
-      }
-      // all loads of this pass are complete (ballots synchronise the group) and
-      // every write lands at or before a slot read in this or an earlier pass
-      uint32_t pos = out + below;
+      for (int c = 0; c < PM_TINY_MAX / 4; ++c) {
+        const uint32_t u[4] = {q[c].x, q[c].y, q[c].z, q[c].w};
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (keep[k]) {
-          a.colw[row + pos] = u[k] & PM_IDMASK;
-          if (STREAM) a.labw[row + pos] = (uint8_t)(l4 >> (8 * k));
-          ++pos;
+        for (int k = 0; k < 4; ++k) {
+          const int j = 4 * c + k;
+          m[j] = 0;
+          if ((uint32_t)j < d) {
+            const uint32_t uu = u[k] & PM_IDMASK;
+            if (FIRST) m[j] = STREAM ? (uint32_t)s_lml[(l4[c] >> (8 * k)) & 63u] : (uint32_t)s_lm[a.cls[uu]];
+            else m[j] = (uint32_t)a.S[uu];
+          }
         }
-      out += cnt_lane;
+      }
+      // which slots stay (bit j), and whether the row has to be rewritten at all
+      uint32_t keepm = 0, flagged = 0;
+#pragma unroll
+      for (int c = 0; c < PM_TINY_MAX / 4; ++c) {
+        const uint32_t u[4] = {q[c].x, q[c].y, q[c].z, q[c].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int j = 4 * c + k;
+          const bool act = (uint32_t)j < d;
+          const bool valid = (m[j] & NBv) != 0u;
+          const bool pre = !FIRST && act && (u[k] >> 31);
+          if (valid) heard |= m[j];
+          if (valid || pre) keepm |= 1u << j;
+          if (pre) flagged = 1;
+        }
+      }
+      out = __popc(keepm);
+      if (FIRST || out != d || flagged) {
+        uint32_t pos = 0;
+#pragma unroll
+        for (int c = 0; c < PM_TINY_MAX / 4; ++c) {
+          const uint32_t u[4] = {q[c].x, q[c].y, q[c].z, q[c].w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int j = 4 * c + k;
+            if ((keepm >> j) & 1u) {
+              a.colw[row + pos] = u[k] & PM_IDMASK;
+              if (STREAM) a.labw[row + pos] = (uint8_t)(l4[c] >> (8 * k));
+              ++pos;
+            }
+          }
+        }
+      }
     }
+
+    // ---- longer rows: the whole warp walks one row at a time -------------------------------
+    uint32_t todo = __ballot_sync(0xffffffffu, d > PM_TINY_MAX);
+    // first pass of the first row is fetched ahead, like every following row's
+    uint4 qn = make_uint4(PM_SENTINEL, PM_SENTINEL, PM_SENTINEL, PM_SENTINEL);
+    uint32_t ln = 0;
+    if (todo) {
+      const int sl = __ffs(todo) - 1;
+      const uint32_t rd = __shfl_sync(0xffffffffu, d, sl);
+      const uint64_t rrow = (uint64_t)__shfl_sync(0xffffffffu, e.y, sl) * 8;
+      if (lane * 4 < rd) {
+        qn = *reinterpret_cast<const uint4*>(src + rrow + lane * 4);
+        if (STREAM) ln = *reinterpret_cast<const uint32_t*>(lsrc + rrow + lane * 4);
+      }
+    }
+    while (todo) {
+      const int sl = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const uint32_t rd = __shfl_sync(0xffffffffu, d, sl);
+      const uint32_t rNB = __shfl_sync(0xffffffffu, NBv, sl);
+      const uint64_t rrow = (uint64_t)__shfl_sync(0xffffffffu, e.y, sl) * 8;
+      uint4 q = qn;
+      uint32_t l4 = ln;
+      // prefetch the first pass of the next long row of this warp
+      if (todo) {
+        const int nl = __ffs(todo) - 1;
+        const uint32_t nd = __shfl_sync(0xffffffffu, d, nl);
+        const uint64_t nrow = (uint64_t)__shfl_sync(0xffffffffu, e.y, nl) * 8;
+        qn = make_uint4(PM_SENTINEL, PM_SENTINEL, PM_SENTINEL, PM_SENTINEL);
+        ln = 0;
+        if (lane * 4 < nd) {
+          qn = *reinterpret_cast<const uint4*>(src + nrow + lane * 4);
+          if (STREAM) ln = *reinterpret_cast<const uint32_t*>(lsrc + nrow + lane * 4);
+        }
+      }
+      uint32_t rheard = 0, rout = 0;
+      for (uint32_t p0 = 0; p0 < rd; p0 += 128) {
+        const uint32_t j0 = p0 + lane * 4;
+        // next pass of this row, fetched before the current one is consumed
+        uint4 q2 = make_uint4(PM_SENTINEL, PM_SENTINEL, PM_SENTINEL, PM_SENTINEL);
+        uint32_t l2 = 0;
+        if (j0 + 128 < rd) {
+          q2 = *reinterpret_cast<const uint4*>(src + rrow + j0 + 128);
+          if (STREAM) l2 = *reinterpret_cast<const uint32_t*>(lsrc + rrow + j0 + 128);
+        }
+        const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+        uint32_t m[4];
 #pragma unroll
-    for (int o = GROUP / 2; o > 0; o >>= 1) heard |= __shfl_xor_sync(0xffffffffu, heard, o);
-    if (has && gl == 0) {
-      const uint32_t T0 = FIRST ? Tv : (uint32_t)a.Tst[v];
+        for (int k = 0; k < 4; ++k) {
+          m[k] = 0;
+          if (j0 + k < rd) {
+            const uint32_t uu = u[k] & PM_IDMASK;
+            if (FIRST) m[k] = STREAM ? (uint32_t)s_lml[(l4 >> (8 * k)) & 63u] : (uint32_t)s_lm[a.cls[uu]];
+            else m[k] = (uint32_t)a.S[uu];
+          }
+        }
+        bool keep[4];
+        uint32_t below = 0, cnt_pass = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const bool act = j0 + k < rd;
+          const bool valid = (m[k] & rNB) != 0u;
+          const bool pre = !FIRST && act && (u[k] >> 31);
+          keep[k] = valid || pre;
+          if (valid) rheard |= m[k];
+          const uint32_t b = __ballot_sync(0xffffffffu, keep[k]);
+          below += __popc(b & lt);
+          cnt_pass += __popc(b);
+        }
+        // all loads of this pass (and of the prefetched next pass, which lies strictly behind every
+        // slot written now: writes land at or before slots already read) are complete
+        uint32_t pos = rout + below;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (keep[k]) {
+            a.colw[rrow + pos] = u[k] & PM_IDMASK;
+            if (STREAM) a.labw[rrow + pos] = (uint8_t)(l4 >> (8 * k));
+            ++pos;
+          }
+        rout += cnt_pass;
+        q = q2;
+        l4 = l2;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) rheard |= __shfl_xor_sync(0xffffffffu, rheard, o);
+      if ((int)lane == sl) { heard = rheard; out = rout; }
+    }
+
+    if (has) {
+      const uint32_t T0 = FIRST ? Tv : e.w;
       const uint32_t ts = Tv ? cover_of(T0, heard) : 0u;
-      a.Tst[v] = (uint16_t)ts;
-      a.adeg[v] = out;
       // a vertex leaves the vertex_state_map (ee.hpp:941-946, :968-970).  In the first
       // superstep only vertices that heard a valid neighbour ever entered the map (:841-852).
       if (ts == 0 && (FIRST ? heard != 0u : Tv != 0u)) a.cnt->nf = 1u;
       scanned += d;
       verts += Tv != 0u;
+      e.z = out;
+      e.w = ts;
+      list[idx] = e;
     }
   }
   // one atomic per warp
@@ -449,14 +547,14 @@ __global__ void __launch_bounds__(kBlock) k_lcc_scan(LccArgs a, const uint32_t* 
     verts += __shfl_xor_sync(0xffffffffu, verts, o);
   }
   if (lane == 0 && verts) {
-    atomicAdd(&a.row->scanned[a.bin], scanned);
-    atomicAdd(&a.row->verts[a.bin], verts);
+    atomicAdd(&a.row->scanned[0], scanned);
+    atomicAdd(&a.row->verts[0], verts);
   }
 }
 
 // one CTA per high-degree vertex ("delegates across warps and CTAs")
 template <bool FIRST, bool STREAM>
-__global__ void __launch_bounds__(1024) k_lcc_scan_big(LccArgs a, const uint32_t* __restrict__ list,
+__global__ void __launch_bounds__(1024) k_lcc_scan_big(LccArgs a, uint4* __restrict__ list,
                                                         const uint32_t* __restrict__ n_ptr) {
   __shared__ uint16_t s_lm[17];
   __shared__ uint16_t s_lml[64];
@@ -469,12 +567,11 @@ __global__ void __launch_bounds__(1024) k_lcc_scan_big(LccArgs a, const uint32_t
   const uint32_t n = *n_ptr;
   for (uint32_t idx = blockIdx.x; idx < n; idx += gridDim.x) {
     __syncthreads();
-    const uint32_t v = list[idx];
-    const uint32_t Tv = a.S[v + a.base];
-    uint32_t d = FIRST ? a.deg[v] : a.adeg[v];
-    if (Tv == 0) d = 0;
+    const uint4 e = list[idx];
+    const uint32_t Tv = a.S[e.x + a.base];
+    const uint32_t d = Tv ? e.z : 0u;
     const uint32_t NBv = nb_of(Tv);
-    const uint64_t row = (uint64_t)a.rowblk[v] * 8;
+    const uint64_t row = (uint64_t)e.y * 8;
     const uint32_t* __restrict__ src = FIRST ? a.col0 : a.colw;
     uint32_t outp = 0;  // slots kept so far (every thread tracks the same value)
     uint32_t heard = 0;
@@ -538,11 +635,13 @@ __global__ void __launch_bounds__(1024) k_lcc_scan_big(LccArgs a, const uint32_t
     if (threadIdx.x == 0) {
       uint32_t h = 0;
       for (uint32_t w = 0; w < nw; ++w) h |= s_heard[w];
-      const uint32_t T0 = FIRST ? Tv : (uint32_t)a.Tst[v];
+      const uint32_t T0 = FIRST ? Tv : e.w;
       const uint32_t ts = Tv ? cover_of(T0, h) : 0u;
-      a.Tst[v] = (uint16_t)ts;
-      a.adeg[v] = outp;
       if (ts == 0 && (FIRST ? h != 0u : Tv != 0u)) a.cnt->nf = 1u;
+      uint4 e2 = e;
+      e2.z = outp;
+      e2.w = ts;
+      list[idx] = e2;
       if (Tv) {
         atomicAdd(&a.row->scanned[2], (unsigned long long)d);
         atomicAdd(&a.row->verts[2], 1ull);
@@ -552,48 +651,47 @@ __global__ void __launch_bounds__(1024) k_lcc_scan_big(LccArgs a, const uint32_t
 }
 
 // ---------------------------------------------------------------------------
-// commit: publish T_arr (ee.hpp:948), drop removed vertices (:941-946), bin the
+// commit: publish T_arr (ee.hpp:948) and |E_v|, drop removed vertices (:941-946), bin the
 // survivors by their new |E_v| into the next frontier and accumulate the row
 // counts the reference writes after every superstep (:1112-1138).
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) k_lcc_commit(LccArgs a, const uint32_t* __restrict__ l0,
-                                                        const uint32_t* __restrict__ l1,
-                                                        const uint32_t* __restrict__ l2, uint32_t* n0,
-                                                        uint32_t* n1, uint32_t* n2, int cur, int nxt) {
+__global__ void __launch_bounds__(kBlock) k_lcc_commit(LccArgs a, const uint4* __restrict__ l0,
+                                                        const uint4* __restrict__ l1, uint4* n0, uint4* n1,
+                                                        int cur, int nxt) {
   const uint32_t lane = threadIdx.x & 31;
-  const uint32_t c0 = a.cnt->fr_n[cur][0], c1 = a.cnt->fr_n[cur][1], c2 = a.cnt->fr_n[cur][2];
-  const uint32_t total = c0 + c1 + c2;
+  const uint32_t c0 = a.cnt->fr_n[cur][0], c1 = a.cnt->fr_n[cur][1];
+  const uint32_t total = c0 + c1;
   unsigned long long nv = 0, ne = 0;
   constexpr int IT = 4;
   const uint32_t tile = blockDim.x * IT;
   for (uint32_t base = blockIdx.x * tile; base < total; base += gridDim.x * tile) {
     bool alive[IT];
     int bin[IT];
-    uint32_t val[IT];
+    uint4 val[IT];
 #pragma unroll
     for (int k = 0; k < IT; ++k) {
       const uint32_t i = base + k * blockDim.x + threadIdx.x;
       alive[k] = false;
       bin[k] = 0;
-      val[k] = 0;
+      val[k] = make_uint4(0, 0, 0, 0);
       bool changed = false;
       uint32_t cslot = 0, cmask = 0;
       if (i < total) {
-        const uint32_t v = i < c0 ? l0[i] : (i < c0 + c1 ? l1[i - c0] : l2[i - c0 - c1]);
-        const uint16_t ts = a.Tst[v];
-        if (c_peer.G > 1) changed = ts != a.S[v + a.base];  // peers only need the changes
-        a.S[v + a.base] = ts;
-        cslot = v + a.base;
+        const uint4 e = i < c0 ? l0[i] : l1[i - c0];
+        const uint32_t ts = e.w, d = e.z;
+        cslot = e.x + a.base;
         cmask = ts;
+        if (c_peer.G > 1) changed = ts != a.S[cslot];  // peers only need the changes
+        a.S[cslot] = (uint16_t)ts;
+        a.adeg[e.x] = d;
         alive[k] = ts != 0;
-        const uint32_t d = a.adeg[v];
         if (alive[k]) { nv++; ne += d; }
-        bin[k] = d <= PM_SMALL_MAX ? 0 : (d <= PM_MID_MAX ? 1 : 2);
-        val[k] = v;
+        bin[k] = bin_of(d);
+        val[k] = e;
       }
       if (c_peer.G > 1) publish_mask(changed, cslot, cmask, a.cnt, a.par);
     }
-    block_bin_append<IT>(alive, bin, val, n0, n1, n2, &a.cnt->fr_n[nxt][0]);
+    block_append2<IT>(alive, bin, val, n0, n1, &a.cnt->fr_n[nxt][0]);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -609,16 +707,15 @@ __global__ void __launch_bounds__(kBlock) k_lcc_commit(LccArgs a, const uint32_t
 // counts after an NLCC constraint (beta.cpp:1094-1120): vertices still in the map
 // and the sizes of their edge maps.  Frontier lists are left untouched; entries
 // deactivated by NLCC are skipped by the next scan and dropped by its commit.
-__global__ void __launch_bounds__(kBlock) k_count_alive(LccArgs a, const uint32_t* __restrict__ l0,
-                                                         const uint32_t* __restrict__ l1,
-                                                         const uint32_t* __restrict__ l2, int cur) {
+__global__ void __launch_bounds__(kBlock) k_count_alive(LccArgs a, const uint4* __restrict__ l0,
+                                                         const uint4* __restrict__ l1, int cur) {
   const uint32_t lane = threadIdx.x & 31;
-  const uint32_t c0 = a.cnt->fr_n[cur][0], c1 = a.cnt->fr_n[cur][1], c2 = a.cnt->fr_n[cur][2];
-  const uint32_t total = c0 + c1 + c2;
+  const uint32_t c0 = a.cnt->fr_n[cur][0], c1 = a.cnt->fr_n[cur][1];
+  const uint32_t total = c0 + c1;
   unsigned long long nv = 0, ne = 0;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const uint32_t v = i < c0 ? l0[i] : (i < c0 + c1 ? l1[i - c0] : l2[i - c0 - c1]);
-    if (a.S[v + a.base]) { nv++; ne += a.adeg[v]; }
+    const uint4 e = i < c0 ? l0[i] : l1[i - c0];
+    if (a.S[e.x + a.base]) { nv++; ne += e.z; }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {

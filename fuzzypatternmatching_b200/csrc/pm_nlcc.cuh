@@ -161,12 +161,11 @@ __device__ __forceinline__ void stage_push(WarpStage& w, const bool (&flag)[4], 
 // ---------------------------------------------------------------------------
 // token sources (nem_1.hpp:387-527; tds_batch_1.hpp:1067-1135, 425-512)
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) k_nlcc_sources(NlcArgs a, const uint32_t* __restrict__ l0,
-                                                          const uint32_t* __restrict__ l1,
-                                                          const uint32_t* __restrict__ l2, int cur, int tds) {
+__global__ void __launch_bounds__(kBlock) k_nlcc_sources(NlcArgs a, const uint4* __restrict__ l0,
+                                                          const uint4* __restrict__ l1, int cur, int tds) {
   const uint32_t lane = threadIdx.x & 31;
-  const uint32_t c0 = a.cnt->fr_n[cur][0], c1 = a.cnt->fr_n[cur][1], c2 = a.cnt->fr_n[cur][2];
-  const uint32_t total = c0 + c1 + c2;
+  const uint32_t c0 = a.cnt->fr_n[cur][0], c1 = a.cnt->fr_n[cur][1];
+  const uint32_t total = c0 + c1;
   const bool multi = c_peer.G > 1;
   uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u;
   for (; i0 < total; i0 += gridDim.x * blockDim.x) {
@@ -174,7 +173,7 @@ __global__ void __launch_bounds__(kBlock) k_nlcc_sources(NlcArgs a, const uint32
     bool is_src = false;
     uint32_t v = 0;
     if (i < total) {
-      v = (i < c0 ? l0[i] : (i < c0 + c1 ? l1[i - c0] : l2[i - c0 - c1])) + a.base;  // slot
+      v = (i < c0 ? l0[i].x : l1[i - c0].x) + a.base;  // slot
       const uint32_t T = a.S[v];
       is_src = T != 0 && hop_ok(T, a.cls[v], 0);
       // path checking starts only from vertices that match BOTH end points (nem_1.hpp:447-451)

@@ -111,11 +111,10 @@ __device__ __forceinline__ void route_tokens(const NlcArgs& a, const bool (&flag
 #define PM_CE_TAG 0x8000000000000000ull  // vertex slots are < 2^31, so (vertex, source) keys never carry bit 63
 
 template <bool STREAM>
-__global__ void __launch_bounds__(kBlock) k_close_keys_m(NlcArgs a, const uint32_t* __restrict__ l0,
-                                                          const uint32_t* __restrict__ l1,
-                                                          const uint32_t* __restrict__ l2, int cur, int hn) {
-  const uint32_t c0 = a.cnt->fr_n[cur][0], c1 = a.cnt->fr_n[cur][1], c2 = a.cnt->fr_n[cur][2];
-  const uint32_t total = c0 + c1 + c2;
+__global__ void __launch_bounds__(kBlock) k_close_keys_m(NlcArgs a, const uint4* __restrict__ l0,
+                                                          const uint4* __restrict__ l1, int cur, int hn) {
+  const uint32_t c0 = a.cnt->fr_n[cur][0], c1 = a.cnt->fr_n[cur][1];
+  const uint32_t total = c0 + c1;
   const uint32_t want_lab = c_nlc.lab[hn];
   constexpr int GROUP = 8;
   const uint32_t lane = threadIdx.x & 31;
@@ -128,7 +127,7 @@ __global__ void __launch_bounds__(kBlock) k_close_keys_m(NlcArgs a, const uint32
     uint32_t s = 0, d = 0;
     uint64_t row = 0;
     if (i < total) {
-      const uint32_t li = i < c0 ? l0[i] : (i < c0 + c1 ? l1[i - c0] : l2[i - c0 - c1]);
+      const uint32_t li = i < c0 ? l0[i].x : l1[i - c0].x;
       s = li + a.base;
       const uint32_t T = a.S[s];
       // a source of the constraint that can also receive the closing hop (nem_1.hpp:428-451, 557-581)

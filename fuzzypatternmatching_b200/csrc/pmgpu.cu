@@ -36,11 +36,10 @@ int sync_counters(pm_ctx* c) {
 
 LccArgs lcc_args(pm_ctx* c, int row) {
   LccArgs a;
-  a.rowblk = c->rowblk; a.deg = c->deg; a.col0 = c->col0; a.colw = c->colw;
-  a.S = c->S; a.Tst = c->Tst; a.adeg = c->adeg; a.cls = c->cls; a.cnt = c->cnt;
+  a.col0 = c->col0; a.colw = c->colw;
+  a.S = c->S; a.adeg = c->adeg; a.cls = c->cls; a.cnt = c->cnt;
   a.lab0 = c->lab0; a.labw = c->labw;
   a.row = c->rowstat + row;
-  a.bin = 0;
   a.base = (uint32_t)(c->nlmax * c->rank);
   a.par = c->step_parity;
   return a;
@@ -95,8 +94,8 @@ void state_free(pm_ctx* c) {
   if (c->h_step) cudaFreeHost(c->h_step);
   c->h_step = nullptr;
   c->dcap = c->tcap = 0;
-  dev_free(c->S); dev_free(c->Tst); dev_free(c->adeg); dev_free(c->cls);
-  for (int b = 0; b < 2; ++b) for (int k = 0; k < 3; ++k) dev_free(c->fr[b][k]);
+  dev_free(c->S); dev_free(c->adeg); dev_free(c->cls);
+  for (int b = 0; b < 2; ++b) for (int k = 0; k < 2; ++k) dev_free(c->fr[b][k]);
   dev_free(c->cnt); dev_free(c->rowstat); dev_free(c->ok); dev_free(c->src_list);
   dev_free(c->hset); dev_free(c->pool);
   if (c->h_cnt) cudaFreeHost(c->h_cnt);
@@ -189,6 +188,7 @@ void pm_destroy(pm_ctx* c) {
   if (comm) ncclCommDestroy(comm);
   if (c->d_scratch) cudaFree(c->d_scratch);
   for (auto e : c->events) cudaEventDestroy(e);
+  for (auto e : c->kev2) cudaEventDestroy(e);
   for (int b = 0; b < 4; ++b) for (int k = 0; k < 2; ++k) if (c->kev[b][k]) cudaEventDestroy(c->kev[b][k]);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -454,14 +454,15 @@ int pm_state_reset(pm_ctx* c) {
   int rc;
   if (!c->S) {
     if ((rc = dev_alloc(c, &c->S, Vs))) return rc;
-    if ((rc = dev_alloc(c, &c->Tst, NL))) return rc;
     if ((rc = dev_alloc(c, &c->adeg, NL))) return rc;
     if ((rc = dev_alloc(c, &c->cls, Vs))) return rc;
     if ((rc = dev_alloc(c, &c->ok, Vs))) return rc;
     if ((rc = dev_alloc(c, &c->src_list, NL))) return rc;
-    for (int b = 0; b < 2; ++b)
-      for (int k = 0; k < 3; ++k)
-        if ((rc = dev_alloc(c, &c->fr[b][k], NL))) return rc;
+    // frontier entry lists: main rows, and rows above PM_MID_MAX slots (at most E / PM_MID_MAX of those)
+    for (int b = 0; b < 2; ++b) {
+      if ((rc = dev_alloc(c, &c->fr[b][0], NL))) return rc;
+      if ((rc = dev_alloc(c, &c->fr[b][1], std::min<uint64_t>(NL, c->E / PM_MID_MAX + 1024)))) return rc;
+    }
     if ((rc = dev_alloc(c, &c->cnt, 1))) return rc;
     PM_CUDA(c, cudaMallocHost((void**)&c->h_cnt, sizeof(DevCounters)));
     PM_CUDA(c, cudaMemsetAsync(c->adeg, 0, NL * sizeof(uint32_t), c->stream));
@@ -487,6 +488,12 @@ int pm_state_reset(pm_ctx* c) {
     PM_CUDA(c, cudaEventCreate(&e));
     c->events.push_back(e);
   }
+  while (c->kev2.size() < (size_t)nrow * 4) {
+    cudaEvent_t e;
+    PM_CUDA(c, cudaEventCreate(&e));
+    c->kev2.push_back(e);
+  }
+  c->kev2_cls.assign(nrow, 1);
   PM_CUDA(c, cudaMemcpyToSymbolAsync(c_pat, &c->pc, sizeof(PatConst), 0, cudaMemcpyHostToDevice, c->stream));
   PM_CUDA(c, cudaMemsetAsync(c->cnt, 0, sizeof(DevCounters), c->stream));
   c->cur = 0;
@@ -494,13 +501,13 @@ int pm_state_reset(pm_ctx* c) {
   PM_CUDA(c, cudaEventRecord(c->kev[3][0], c->stream));
   if (c->labels_small) {
     // init and the signature filter of the first superstep in one streaming pass over the local rows
-    k_init_filter<<<grid_for(), kBlock, 0, c->stream>>>(c->lab8 + base, c->deg, c->sig, NL, c->cls + base, c->S + base,
-                                                        c->fr[0][0], c->fr[0][1], c->fr[0][2], c->cnt, 0);
+    k_init_filter<<<grid_for(), kBlock, 0, c->stream>>>(c->lab8 + base, c->deg, c->rowblk, c->sig, NL, c->cls + base,
+                                                        c->S + base, c->fr[0][0], c->fr[0][1], c->cnt, 0);
     c->filter_done = true;
   } else {
     if (multi) PM_CUDA(c, cudaMemsetAsync(c->S, 0, Vs * sizeof(uint16_t), c->stream));
-    k_init_state<false><<<grid_for(), kBlock, 0, c->stream>>>(c->label, c->lab8, c->deg, NL, c->cls + base, c->S + base,
-                                                             c->fr[0][0], c->fr[0][1], c->fr[0][2], c->cnt, 0);
+    k_init_state<<<grid_for(), kBlock, 0, c->stream>>>(c->label, c->deg, c->rowblk, NL, c->cls + base, c->S + base,
+                                                       c->fr[0][0], c->fr[0][1], c->cnt, 0);
   }
   PM_LAUNCH_CHECK(c);
   if (multi) {
@@ -512,8 +519,7 @@ int pm_state_reset(pm_ctx* c) {
   {
     int rc2 = sync_counters(c);
     if (rc2) return rc2;
-    bool any = false;
-    for (int b = 2; b >= 0; --b) { any = any || c->h_cnt->fr_n[0][b] != 0; c->bin_live[b] = any; }
+    for (int b = 0; b < 2; ++b) c->bin_live[b] = c->h_cnt->fr_n[0][b] != 0;
     c->init_ms = 0;
     c->init_candidates = c->h_cnt->filtered_init;
     if (c->filter_done) PM_CUDA(c, cudaEventElapsedTime(&c->init_ms, c->kev[3][0], c->kev[3][1]));
@@ -544,34 +550,29 @@ int pm_lcc(pm_ctx* c, int init_step, int* not_finished, pm_counts_t* counts_out)
     const bool first = init_step && k == 0;
     PM_CUDA(c, cudaEventRecord(c->events[k], st));
     PM_CUDA(c, cudaMemsetAsync(&c->cnt->fr_n[c->cur ^ 1][0], 0, 4 * sizeof(uint32_t), st));
-    LccArgs a = lcc_args(c, k), a1 = a, a2 = a;
-    a1.bin = 1;
-    a2.bin = 2;
-    if (first) {
-      const int cur = c->cur;
-      // the kernels that walk the pristine adjacency are timed with CUDA events on this stream
-      PM_CUDA(c, cudaEventRecord(c->kev[0][0], st));
-      if (c->bin_live[0]) { (sm ? k_lcc_scan<8, true, true> : k_lcc_scan<8, true, false>)<<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], &c->cnt->fr_n[cur][0]); PM_LAUNCH_CHECK(c); }
-      PM_CUDA(c, cudaEventRecord(c->kev[0][1], st));
-      PM_CUDA(c, cudaEventRecord(c->kev[1][0], st));
-      if (c->bin_live[1]) { (sm ? k_lcc_scan<32, true, true> : k_lcc_scan<32, true, false>)<<<grid, kBlock, 0, st>>>(a1, c->fr[cur][1], &c->cnt->fr_n[cur][1]); PM_LAUNCH_CHECK(c); }
-      PM_CUDA(c, cudaEventRecord(c->kev[1][1], st));
-      PM_CUDA(c, cudaEventRecord(c->kev[2][0], st));
-      if (c->bin_live[2]) { (sm ? k_lcc_scan_big<true, true> : k_lcc_scan_big<true, false>)<<<148, 1024, 0, st>>>(a2, c->fr[cur][2], &c->cnt->fr_n[cur][2]); PM_LAUNCH_CHECK(c); }
-      PM_CUDA(c, cudaEventRecord(c->kev[2][1], st));
-    } else {
-      const int cur = c->cur;
-      if (c->bin_live[0]) { (sm ? k_lcc_scan<8, false, true> : k_lcc_scan<8, false, false>)<<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], &c->cnt->fr_n[cur][0]); PM_LAUNCH_CHECK(c); }
-      if (c->bin_live[1]) { (sm ? k_lcc_scan<32, false, true> : k_lcc_scan<32, false, false>)<<<grid, kBlock, 0, st>>>(a1, c->fr[cur][1], &c->cnt->fr_n[cur][1]); PM_LAUNCH_CHECK(c); }
-      if (c->bin_live[2]) { (sm ? k_lcc_scan_big<false, true> : k_lcc_scan_big<false, false>)<<<148, 1024, 0, st>>>(a2, c->fr[cur][2], &c->cnt->fr_n[cur][2]); PM_LAUNCH_CHECK(c); }
-    }
-    {
-      const int cur = c->cur, nxt = cur ^ 1;
-      k_lcc_commit<<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], c->fr[cur][1], c->fr[cur][2], c->fr[nxt][0],
-                                            c->fr[nxt][1], c->fr[nxt][2], cur, nxt);
+    LccArgs a = lcc_args(c, k);
+    const int cur = c->cur, nxt = cur ^ 1;
+    // kernel classes timed with CUDA events on this stream: 0 = first-superstep scan of the main list,
+    // 1 = later scans of the main list, 2 = CTA-per-row scans
+    const int cls_main = first ? 0 : 1;
+    cudaEvent_t* ev = &c->kev2[(size_t)k * 4];
+    PM_CUDA(c, cudaEventRecord(ev[0], st));
+    if (c->bin_live[0]) {
+      if (first) (sm ? k_lcc_scan<true, true> : k_lcc_scan<true, false>)<<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], &c->cnt->fr_n[cur][0]);
+      else (sm ? k_lcc_scan<false, true> : k_lcc_scan<false, false>)<<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], &c->cnt->fr_n[cur][0]);
       PM_LAUNCH_CHECK(c);
-      c->cur = nxt;
     }
+    PM_CUDA(c, cudaEventRecord(ev[1], st));
+    if (c->bin_live[1]) {
+      if (first) (sm ? k_lcc_scan_big<true, true> : k_lcc_scan_big<true, false>)<<<148, 1024, 0, st>>>(a, c->fr[cur][1], &c->cnt->fr_n[cur][1]);
+      else (sm ? k_lcc_scan_big<false, true> : k_lcc_scan_big<false, false>)<<<148, 1024, 0, st>>>(a, c->fr[cur][1], &c->cnt->fr_n[cur][1]);
+      PM_LAUNCH_CHECK(c);
+    }
+    PM_CUDA(c, cudaEventRecord(ev[2], st));
+    c->kev2_cls[k] = cls_main;
+    k_lcc_commit<<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], c->fr[cur][1], c->fr[nxt][0], c->fr[nxt][1], cur, nxt);
+    PM_LAUNCH_CHECK(c);
+    c->cur = nxt;
     if (c->n_ranks > 1) {
       // the commit stored this rank's mask changes into every peer's delta inbox; the StepMsg
       // all-gather is the barrier after which the peers' changes can be applied to the local replica
@@ -594,8 +595,7 @@ int pm_lcc(pm_ctx* c, int init_step, int* not_finished, pm_counts_t* counts_out)
   }
   if (removed && not_finished) *not_finished = 1;
   {
-    bool any = false;
-    for (int b = 2; b >= 0; --b) { any = any || c->h_cnt->fr_n[c->cur][b] != 0; c->bin_live[b] = any; }
+    for (int b = 0; b < 2; ++b) c->bin_live[b] = c->h_cnt->fr_n[c->cur][b] != 0;
   }
   for (int k = 0; k < D; ++k) {
     float ms = 0;
@@ -610,31 +610,25 @@ int pm_lcc(pm_ctx* c, int init_step, int* not_finished, pm_counts_t* counts_out)
     const uint64_t sc = rs.scanned[0] + rs.scanned[1] + rs.scanned[2];
     const uint64_t vs = rs.verts[0] + rs.verts[1] + rs.verts[2];
     c->summary.edges_processed += sc;
-    if (k == 0 && init_step) {
-      for (int b = 0; b < 3; ++b) {
-        float kms = 0;
-        PM_CUDA(c, cudaEventElapsedTime(&kms, c->kev[b][0], c->kev[b][1]));
-        c->kstat[b].launches++;
-        c->kstat[b].ms += kms;
-        c->kstat[b].slots += rs.scanned[b];
-        c->kstat[b].vertices += rs.verts[b];
-      }
-      if (c->labels_small) {
-        float kms = c->init_ms;
-        uint64_t nfil = c->init_candidates;
-        if (!c->filter_done) {
-          PM_CUDA(c, cudaEventElapsedTime(&kms, c->kev[3][0], c->kev[3][1]));
-          nfil = rs.filtered;
-        } else {
-          c->rows[c->rows.size() - 1].seconds += kms * 1e-3;  // the fused filter is part of superstep 0
-          c->summary.device_seconds += kms * 1e-3;
-        }
-        c->kstat[3].launches++;
-        c->kstat[3].ms += kms;
-        c->kstat[3].vertices += nfil;
-        // signature filter: 8 B signature + 2 B mask + 4 B list entry per candidate
-        c->summary.algorithmic_bytes += nfil * 14;
-      }
+    {
+      float kms = 0;
+      const cudaEvent_t* ev = &c->kev2[(size_t)k * 4];
+      PM_CUDA(c, cudaEventElapsedTime(&kms, ev[0], ev[1]));
+      pm_kernel_stats_t& ks = c->kstat[c->kev2_cls[k]];
+      if (rs.verts[0]) { ks.launches++; ks.ms += kms; ks.slots += rs.scanned[0]; ks.vertices += rs.verts[0]; }
+      PM_CUDA(c, cudaEventElapsedTime(&kms, ev[1], ev[2]));
+      if (rs.verts[2]) { c->kstat[2].launches++; c->kstat[2].ms += kms; c->kstat[2].slots += rs.scanned[2]; c->kstat[2].vertices += rs.verts[2]; }
+    }
+    if (k == 0 && init_step && c->labels_small) {
+      // the fused init + signature filter is part of superstep 0
+      const float kms = c->init_ms;
+      c->rows[c->rows.size() - 1].seconds += kms * 1e-3;
+      c->summary.device_seconds += kms * 1e-3;
+      c->kstat[3].launches++;
+      c->kstat[3].ms += kms;
+      c->kstat[3].vertices += c->init_candidates;
+      // signature filter: 8 B signature + 2 B mask + 4 B list entry per candidate
+      c->summary.algorithmic_bytes += c->init_candidates * 14;
     }
     // SURVEY §8(d) byte model: 4 B column + 2 B neighbour mask per scanned slot;
     // 12 B per scanned vertex (row start, own masks read + written, |E_v|)
@@ -727,8 +721,7 @@ int pm_nlcc(pm_ctx* c, int pl, int mode, int* pattern_found, int* token_source_d
     if (multi && close2) {
       // every rank learns the qualifying (source, neighbour) pairs of the closing hop (k_close_keys_m)
       NlcArgs ka = nlc_args(c, nullptr, 0);
-      (sm ? k_close_keys_m<true> : k_close_keys_m<false>)<<<grid, kBlock, 0, st>>>(ka, c->fr[cur][0], c->fr[cur][1],
-                                                                                 c->fr[cur][2], cur, (int)k.C);
+      (sm ? k_close_keys_m<true> : k_close_keys_m<false>)<<<grid, kBlock, 0, st>>>(ka, c->fr[cur][0], c->fr[cur][1], cur, (int)k.C);
       PM_LAUNCH_CHECK(c);
       k_close_keys_count_m<<<1, 1, 0, st>>>(c->cnt);
       PM_LAUNCH_CHECK(c);
@@ -740,7 +733,7 @@ int pm_nlcc(pm_ctx* c, int pl, int mode, int* pattern_found, int* token_source_d
       mark();
     }
     NlcArgs a = nlc_args(c, d_matches, match_cap);
-    k_nlcc_sources<<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], c->fr[cur][1], c->fr[cur][2], cur, tds ? 1 : 0);
+    k_nlcc_sources<<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], c->fr[cur][1], cur, tds ? 1 : 0);
     PM_LAUNCH_CHECK(c);
     k_nlcc_begin<<<1, 1, 0, st>>>(c->cnt);
     PM_LAUNCH_CHECK(c);
@@ -879,7 +872,7 @@ int pm_nlcc(pm_ctx* c, int pl, int mode, int* pattern_found, int* token_source_d
   }
   PM_CUDA(c, cudaMemsetAsync(c->rowstat + D, 0, sizeof(RowStat), st));
   LccArgs la = lcc_args(c, D);
-  k_count_alive<<<grid, kBlock, 0, st>>>(la, c->fr[cur][0], c->fr[cur][1], c->fr[cur][2], cur);
+  k_count_alive<<<grid, kBlock, 0, st>>>(la, c->fr[cur][0], c->fr[cur][1], cur);
   PM_LAUNCH_CHECK(c);
   PM_CUDA(c, cudaEventRecord(c->events[1], st));
   PM_CUDA(c, cudaMemcpyAsync(c->h_rowstat + D, c->rowstat + D, sizeof(RowStat), cudaMemcpyDeviceToHost, st));
@@ -910,36 +903,36 @@ int pm_nlcc(pm_ctx* c, int pl, int mode, int* pattern_found, int* token_source_d
 namespace pm {
 
 // (vertex, T_arr) of every vertex still in the map (beta.cpp:1386-1394)
-__global__ void k_emit_vertices(LccArgs a, const uint32_t* __restrict__ l0, const uint32_t* __restrict__ l1,
-                                const uint32_t* __restrict__ l2, int cur, uint2* __restrict__ out,
-                                unsigned long long* __restrict__ n_out) {
-  const uint32_t c0 = a.cnt->fr_n[cur][0], c1 = a.cnt->fr_n[cur][1], c2 = a.cnt->fr_n[cur][2];
-  const uint32_t total = c0 + c1 + c2;
+__global__ void k_emit_vertices(LccArgs a, const uint4* __restrict__ l0, const uint4* __restrict__ l1, int cur,
+                                uint2* __restrict__ out, unsigned long long* __restrict__ n_out) {
+  const uint32_t c0 = a.cnt->fr_n[cur][0], c1 = a.cnt->fr_n[cur][1];
+  const uint32_t total = c0 + c1;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const uint32_t v = i < c0 ? l0[i] : (i < c0 + c1 ? l1[i - c0] : l2[i - c0 - c1]);
-    const uint32_t T = a.S[v + a.base];
-    if (T) out[atomicAdd(n_out, 1ull)] = make_uint2(v + a.base, T);
+    const uint4 e = i < c0 ? l0[i] : l1[i - c0];
+    const uint32_t T = a.S[e.x + a.base];
+    if (T) out[atomicAdd(n_out, 1ull)] = make_uint2(e.x + a.base, T);
   }
 }
 
 // (vertex, neighbour) for every key of vertex_active_edges_map[v], v in the map (beta.cpp:1397-1403)
-__global__ void k_emit_edges(LccArgs a, const uint32_t* __restrict__ l0, const uint32_t* __restrict__ l1,
-                             const uint32_t* __restrict__ l2, int cur, uint2* __restrict__ out,
+__global__ void k_emit_edges(LccArgs a, const uint32_t* __restrict__ rowblk, const uint4* __restrict__ l0,
+                             const uint4* __restrict__ l1, int cur, uint2* __restrict__ out,
                              unsigned long long* __restrict__ n_out) {
-  const uint32_t c0 = a.cnt->fr_n[cur][0], c1 = a.cnt->fr_n[cur][1], c2 = a.cnt->fr_n[cur][2];
-  const uint32_t total = c0 + c1 + c2;
+  const uint32_t c0 = a.cnt->fr_n[cur][0], c1 = a.cnt->fr_n[cur][1];
+  const uint32_t total = c0 + c1;
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t i = warp; i < total; i += nwarps) {
-    const uint32_t v = i < c0 ? l0[i] : (i < c0 + c1 ? l1[i - c0] : l2[i - c0 - c1]);
-    if (!a.S[v + a.base]) continue;
-    const uint32_t d = a.adeg[v];
-    const uint64_t row = (uint64_t)a.rowblk[v] * 8;
+    const uint4 e = i < c0 ? l0[i] : l1[i - c0];
+    if (!a.S[e.x + a.base]) continue;
+    const uint32_t d = e.z;
+    const uint64_t row = (uint64_t)e.y * 8;
     unsigned long long base = 0;
     if (lane == 0) base = atomicAdd(n_out, (unsigned long long)d);
     base = __shfl_sync(0xffffffffu, base, 0);
-    for (uint32_t j = lane; j < d; j += 32) out[base + j] = make_uint2(v + a.base, a.colw[row + j] & PM_IDMASK);
+    for (uint32_t j = lane; j < d; j += 32) out[base + j] = make_uint2(e.x + a.base, a.colw[row + j] & PM_IDMASK);
   }
+  (void)rowblk;
 }
 
 }  // namespace pm
@@ -954,7 +947,7 @@ int fetch_pairs(pm_ctx* c, bool edges, std::vector<uint2>& host) {
   PM_CUDA(c, cudaMemsetAsync(c->rowstat + D, 0, sizeof(RowStat), st));
   LccArgs la = lcc_args(c, D);
   const int cur = c->cur;
-  k_count_alive<<<grid_for(), kBlock, 0, st>>>(la, c->fr[cur][0], c->fr[cur][1], c->fr[cur][2], cur);
+  k_count_alive<<<grid_for(), kBlock, 0, st>>>(la, c->fr[cur][0], c->fr[cur][1], cur);
   PM_LAUNCH_CHECK(c);
   PM_CUDA(c, cudaMemcpyAsync(c->h_rowstat + D, c->rowstat + D, sizeof(RowStat), cudaMemcpyDeviceToHost, st));
   PM_CUDA(c, cudaStreamSynchronize(st));
@@ -967,8 +960,8 @@ int fetch_pairs(pm_ctx* c, bool edges, std::vector<uint2>& host) {
   if ((rc = dev_alloc(c, &d_out, n))) return rc;
   if ((rc = dev_alloc(c, &d_n, 1))) { dev_free(d_out); return rc; }
   cudaMemsetAsync(d_n, 0, sizeof(unsigned long long), st);
-  if (edges) k_emit_edges<<<grid_for(), kBlock, 0, st>>>(la, c->fr[cur][0], c->fr[cur][1], c->fr[cur][2], cur, d_out, d_n);
-  else k_emit_vertices<<<grid_for(), kBlock, 0, st>>>(la, c->fr[cur][0], c->fr[cur][1], c->fr[cur][2], cur, d_out, d_n);
+  if (edges) k_emit_edges<<<grid_for(), kBlock, 0, st>>>(la, c->rowblk, c->fr[cur][0], c->fr[cur][1], cur, d_out, d_n);
+  else k_emit_vertices<<<grid_for(), kBlock, 0, st>>>(la, c->fr[cur][0], c->fr[cur][1], cur, d_out, d_n);
   c->launches++;
   cudaError_t e = cudaMemcpyAsync(host.data(), d_out, n * sizeof(uint2), cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);

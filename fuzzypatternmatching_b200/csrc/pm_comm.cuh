@@ -150,6 +150,67 @@ __global__ void k_step_msg(DevCounters* cnt, StepMsg* msg) {
     msg->deleted = cnt->deleted;
     msg->overflow = cnt->overflow;
     msg->accepted = cnt->pool_n;
+    msg->seq = 0;
+    msg->timeout = 0;
+  }
+}
+
+// The step barrier over peer memory, one tiny kernel: every rank stores its StepMsg straight into the
+// step mailbox of every peer (NVLink stores, sequence number last behind a system fence) and then polls
+// its own mailbox until all peers' messages of this step have arrived.  Stores a rank issued before the
+// barrier (mask deltas, tokens) are ordered before its sequence number, so they are visible afterwards.
+// Mailbox slots alternate with the step parity: a rank is never more than one step ahead of a peer
+// that has not yet read the previous message.  A peer that never arrives trips a time-out instead of a hang.
+__global__ void k_step_sync(DevCounters* cnt, StepMsg* msg, StepMsg* all_out, uint32_t seq) {
+  const int G = c_peer.G, me = c_peer.rank;
+  const int lane = threadIdx.x;
+  // 1. my message (and re-arm the per-step counters)
+  if (lane < PM_MAX_RANKS) {
+    const unsigned long long n = cnt->out_n[lane];
+    msg->out_n[lane] = n;
+    cnt->out_n[lane] = 0;
+    atomicMax(&cnt->peak_out, n);
+  }
+  if (lane == 0) {
+    msg->ndelta = cnt->ndelta;
+    cnt->ndelta = 0;
+    msg->nf = cnt->nf;
+    msg->pad = cnt->nf_init;
+    msg->found = cnt->found;
+    msg->deleted = cnt->deleted;
+    msg->overflow = cnt->overflow;
+    msg->accepted = cnt->pool_n;
+    msg->seq = seq;
+    msg->timeout = 0;
+  }
+  __syncwarp();
+  __threadfence_system();  // everything this GPU stored into peers' inboxes before this step is out
+  // 2. lane g delivers it to rank g
+  const uint32_t slot = (seq & 1u) * (uint32_t)G + (uint32_t)me;
+  if (lane < G) {
+    volatile unsigned long long* dst = reinterpret_cast<volatile unsigned long long*>(c_peer.sync_in[lane] + slot);
+    const unsigned long long* srcw = reinterpret_cast<const unsigned long long*>(msg);
+    constexpr int W = sizeof(StepMsg) / 8;
+    for (int i = 0; i < W - 1; ++i) dst[i] = srcw[i];
+    __threadfence_system();
+    dst[W - 1] = srcw[W - 1];  // {seq, timeout}: the arrival flag
+  }
+  // 3. lane g waits for rank g's message of this step
+  bool late = false;
+  if (lane < G) {
+    const volatile StepMsg* in = c_peer.sync_in[me] + (seq & 1u) * (uint32_t)G + lane;
+    unsigned long long t0 = 0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (in->seq != seq) {
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 20000000000ull) { late = true; break; }  // 20 s
+    }
+    __threadfence_system();
+    const unsigned long long* srcw = reinterpret_cast<const unsigned long long*>(const_cast<const StepMsg*>(in));
+    unsigned long long* dstw = reinterpret_cast<unsigned long long*>(all_out + lane);
+    for (int i = 0; i < (int)(sizeof(StepMsg) / 8); ++i) dstw[i] = srcw[i];
+    if (late) { all_out[lane].timeout = 1; cnt->overflow = 1u; }
   }
 }
 
@@ -157,6 +218,12 @@ __global__ void k_step_msg(DevCounters* cnt, StepMsg* msg) {
 // g's on every rank, and all stores rank g issued before the call are visible here.
 inline int comm_step(pm_ctx* c) {
   if (c->n_ranks == 1) return 0;
+  if (!c->step_nccl) {
+    c->step_seq++;
+    k_step_sync<<<1, 32, 0, c->stream>>>(c->cnt, c->step_msg, c->step_msg + 1, c->step_seq);
+    PM_LAUNCH_CHECK(c);
+    return 0;
+  }
   k_step_msg<<<1, 32, 0, c->stream>>>(c->cnt, c->step_msg);
   PM_LAUNCH_CHECK(c);
   PM_NCCL(c, ncclAllGather(c->step_msg, c->step_msg + 1, sizeof(StepMsg), ncclChar, comm_of(c), c->stream));
@@ -167,6 +234,8 @@ inline int comm_step(pm_ctx* c) {
 inline int comm_step_fetch(pm_ctx* c) {
   PM_CUDA(c, cudaMemcpyAsync(c->h_step, c->step_msg + 1, sizeof(StepMsg) * c->n_ranks, cudaMemcpyDeviceToHost, c->stream));
   PM_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (int g = 0; g < c->n_ranks; ++g)
+    if (c->h_step[g].timeout) return fail(c, PM_ERR_COMM, "step barrier timed out waiting for rank " + std::to_string(g));
   return 0;
 }
 

@@ -73,8 +73,10 @@ struct DevCounters {
 // what every rank contributes to the per-step all-gather (= the barrier)
 struct StepMsg {
   unsigned long long out_n[PM_MAX_RANKS];
-  uint32_t ndelta, nf, found, deleted, overflow, pad;
+  uint32_t ndelta, nf, found, deleted, overflow, pad;  // pad: nf_init
   unsigned long long accepted;   // tokens accepted so far (pool_n)
+  uint32_t seq;                  // step number: written LAST, polled by the receiver
+  uint32_t timeout;              // a peer never arrived (the step barrier gave up)
 };
 
 // Multi-GPU: one process per GPU, 1-D vertex partition owner(v) = v mod G like the reference
@@ -97,6 +99,7 @@ struct PeerTab {
   uint8_t* ok[PM_MAX_RANKS];             // replicated-size array of every rank (index: slot); truth lives at the owner
   uint2* din[2][PM_MAX_RANKS];           // delta inbox of rank g: G regions of dcap (slot, mask) pairs, double buffered
   uint2* tin[2][PM_MAX_RANKS];           // token inbox of rank g: G regions of tcap tokens, double buffered
+  StepMsg* sync_in[PM_MAX_RANKS];        // step mailbox of rank g: [2][G] StepMsg, slot [seq & 1][sender]
 };
 
 struct RowStat {                // one result row, accumulated on the device
@@ -119,6 +122,9 @@ struct pm_ctx {
   pm::PeerTab peers{};             // host copy of c_peer
   std::vector<void*> ipc_open;     // peer mappings currently open
   pm::StepMsg* step_msg = nullptr; // device: [1 + G] (mine, then everyone's)
+  pm::StepMsg* sync_in = nullptr;  // device: [2][G] step mailbox the peers store into
+  uint32_t step_seq = 0;           // steps taken so far (same on every rank)
+  bool step_nccl = false;          // PM_COMM_NCCL=1: use an NCCL all-gather for the step barrier instead
   unsigned long long* d_scratch = nullptr;  // device: 8 words for small all-reduces
   pm::StepMsg* h_step = nullptr;   // pinned: [G]
   uint2* din[2] = {nullptr, nullptr};   // delta inboxes (G regions of dcap)

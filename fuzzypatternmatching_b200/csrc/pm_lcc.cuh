@@ -204,6 +204,26 @@ __global__ void __launch_bounds__(kBlock) k_init_state(const uint64_t* __restric
   }
 }
 
+// class of EVERY slot from the replicated byte labels (several GPUs: neighbours owned by peers)
+__global__ void __launch_bounds__(kBlock) k_cls_all(const uint8_t* __restrict__ lab8, uint64_t n, uint8_t* __restrict__ cls) {
+  __shared__ uint8_t s_cl[64];
+  if (threadIdx.x < 64) s_cl[threadIdx.x] = c_pat.cls_of_label[threadIdx.x];
+  __syncthreads();
+  const uint64_t n16 = n / 16;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint4 l = reinterpret_cast<const uint4*>(lab8)[i];
+    const uint32_t in[4] = {l.x, l.y, l.z, l.w};
+    uint32_t out[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      out[g] = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) out[g] |= (uint32_t)s_cl[(in[g] >> (8 * k)) & 63u] << (8 * k);
+    }
+    reinterpret_cast<uint4*>(cls)[i] = make_uint4(out[0], out[1], out[2], out[3]);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // fused per-pattern initialisation + first-superstep signature filter (labels < 64).
 // One streaming pass over all vertices: class from the byte label, candidate test, then — for
@@ -221,7 +241,8 @@ __global__ void __launch_bounds__(kBlock) k_init_filter(const uint8_t* __restric
                                                          const uint32_t* __restrict__ rowblk,
                                                          const unsigned long long* __restrict__ sig, uint64_t V,
                                                          uint8_t* __restrict__ cls, uint16_t* __restrict__ S,
-                                                         uint4* fr_main, uint4* fr_big, DevCounters* cnt, int buf) {
+                                                         uint4* fr_main, uint4* fr_big, DevCounters* cnt, int buf,
+                                                         uint32_t slot_base, int par) {
   __shared__ uint8_t s_cl[64];
   __shared__ uint16_t s_lm[17];
   __shared__ unsigned long long s_rl[17];
@@ -329,6 +350,32 @@ __global__ void __launch_bounds__(kBlock) k_init_filter(const uint8_t* __restric
         if ((k0 >> j) & 1u) fr_main[o0++] = e; else fr_big[o1++] = e;
       }
     }
+    if (c_peer.G > 1) {
+      // the peers' replicas of S start from zero: they only need the survivors' masks
+      // (one reservation in the delta inboxes per warp and tile)
+      const uint32_t ks = k0 | k1;
+      const uint32_t ns = __popc(ks);
+      uint32_t incl = ns;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o) incl += t;
+      }
+      const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+      if (tot) {
+        uint32_t pos = 0;
+        if (lane == 31) pos = atomicAdd(&cnt->ndelta, tot);
+        pos = __shfl_sync(0xffffffffu, pos, 31) + incl - ns;
+        for (uint32_t rest = ks; rest; rest &= rest - 1) {
+          const int j = __ffs(rest) - 1;
+          const uint2 d = make_uint2((uint32_t)(v0 + j) + slot_base, (uint32_t)S[v0 + j]);
+          if (pos < c_peer.dcap)
+            for (int g = 0; g < c_peer.G; ++g)
+              if (g != c_peer.rank) c_peer.din[par][g][(uint64_t)c_peer.rank * c_peer.dcap + pos] = d;
+          ++pos;
+        }
+      }
+    }
     __syncthreads();
   }
   if (any_removed) cnt->nf_init = 1u;
@@ -348,7 +395,7 @@ __global__ void __launch_bounds__(kBlock) k_init_filter(const uint8_t* __restric
 //   compactions keep labw aligned with colw for NLCC.
 // ---------------------------------------------------------------------------
 template <bool FIRST, bool STREAM>
-__global__ void __launch_bounds__(kBlock) k_lcc_scan(LccArgs a, uint4* __restrict__ list,
+__global__ void __launch_bounds__(kBlock, 4) k_lcc_scan(LccArgs a, uint4* __restrict__ list,
                                                       const uint32_t* __restrict__ n_ptr) {
   __shared__ uint16_t s_lm[17];
   __shared__ uint16_t s_lml[64];  // label value -> labelmask

@@ -84,6 +84,7 @@ int comm_publish(pm_ctx* c) {
   PM_SHARE(c->din[1], din[1], uint2*)
   PM_SHARE(c->tin[0], tin[0], uint2*)
   PM_SHARE(c->tin[1], tin[1], uint2*)
+  PM_SHARE(c->sync_in, sync_in, StepMsg*)
 #undef PM_SHARE
   return comm_upload_peers(c);
 }
@@ -91,6 +92,7 @@ int comm_publish(pm_ctx* c) {
 void state_free(pm_ctx* c) {
   comm_close_all(c);  // nobody may still map the buffers freed below
   dev_free(c->din[0]); dev_free(c->din[1]); dev_free(c->tin[0]); dev_free(c->tin[1]); dev_free(c->step_msg);
+  dev_free(c->sync_in);
   if (c->h_step) cudaFreeHost(c->h_step);
   c->h_step = nullptr;
   c->dcap = c->tcap = 0;
@@ -472,6 +474,12 @@ int pm_state_reset(pm_ctx* c) {
       if ((rc = dev_alloc(c, &c->din[1], c->dcap * c->n_ranks))) return rc;
       if ((rc = dev_alloc(c, &c->step_msg, 1 + c->n_ranks))) return rc;
       PM_CUDA(c, cudaMemsetAsync(c->step_msg, 0, (1 + c->n_ranks) * sizeof(StepMsg), c->stream));
+      // step mailbox; sequence numbers start at 1, and every rank restarts from 0 together here
+      if ((rc = dev_alloc(c, &c->sync_in, 2 * c->n_ranks))) return rc;
+      PM_CUDA(c, cudaMemsetAsync(c->sync_in, 0, 2 * c->n_ranks * sizeof(StepMsg), c->stream));
+      PM_CUDA(c, cudaStreamSynchronize(c->stream));
+      c->step_seq = 0;
+      c->step_nccl = getenv("PM_COMM_NCCL") != nullptr;
       PM_CUDA(c, cudaMallocHost((void**)&c->h_step, sizeof(StepMsg) * c->n_ranks));
     }
     // the peer table (G = 1: everything points at this GPU)
@@ -500,20 +508,34 @@ int pm_state_reset(pm_ctx* c) {
   c->filter_done = false;
   PM_CUDA(c, cudaEventRecord(c->kev[3][0], c->stream));
   if (c->labels_small) {
+    if (multi) {
+      // peers' parts of the replicas: classes follow from the replicated labels, masks start at zero and
+      // receive the survivors of the first superstep as deltas (a few % of the vertices) — no bulk all-gather
+      PM_CUDA(c, cudaMemsetAsync(c->S, 0, Vs * sizeof(uint16_t), c->stream));
+      k_cls_all<<<grid_for(), kBlock, 0, c->stream>>>(c->lab8, Vs, c->cls);
+      PM_LAUNCH_CHECK(c);
+    }
     // init and the signature filter of the first superstep in one streaming pass over the local rows
     k_init_filter<<<grid_for(), kBlock, 0, c->stream>>>(c->lab8 + base, c->deg, c->rowblk, c->sig, NL, c->cls + base,
-                                                        c->S + base, c->fr[0][0], c->fr[0][1], c->cnt, 0);
+                                                        c->S + base, c->fr[0][0], c->fr[0][1], c->cnt, 0, (uint32_t)base, c->step_parity);
     c->filter_done = true;
+    PM_LAUNCH_CHECK(c);
+    if (multi) {
+      if ((rc = comm_step(c))) return rc;
+      k_apply_deltas<<<grid_for(), kBlock, 0, c->stream>>>(c->S, c->step_msg + 1, c->step_parity);
+      PM_LAUNCH_CHECK(c);
+      c->step_parity ^= 1;
+    }
   } else {
     if (multi) PM_CUDA(c, cudaMemsetAsync(c->S, 0, Vs * sizeof(uint16_t), c->stream));
     k_init_state<<<grid_for(), kBlock, 0, c->stream>>>(c->label, c->deg, c->rowblk, NL, c->cls + base, c->S + base,
                                                        c->fr[0][0], c->fr[0][1], c->cnt, 0);
-  }
-  PM_LAUNCH_CHECK(c);
-  if (multi) {
-    // every rank needs the class and the first mask of every vertex (they are gathered from neighbours)
-    if ((rc = comm_allgather_slots(c, c->cls))) return rc;
-    if ((rc = comm_allgather_slots(c, c->S))) return rc;
+    PM_LAUNCH_CHECK(c);
+    if (multi) {
+      // every rank needs the class and the first mask of every vertex (they are gathered from neighbours)
+      if ((rc = comm_allgather_slots(c, c->cls))) return rc;
+      if ((rc = comm_allgather_slots(c, c->S))) return rc;
+    }
   }
   PM_CUDA(c, cudaEventRecord(c->kev[3][1], c->stream));
   {
@@ -767,8 +789,13 @@ int pm_nlcc(pm_ctx* c, int pl, int mode, int* pattern_found, int* token_source_d
       // (parity a.par), the all-gather publishes the region fill counts and is the barrier
       if ((rc = comm_step(c))) return rc;  // level 0 (the sources) is in inbox `par`
       c->step_parity ^= 1;
+      // no rank has a source: nothing to walk (every rank sees the same counts and skips together)
+      if ((rc = comm_step_fetch(c))) return rc;
+      uint64_t n_src_all = 0;
+      for (int g = 0; g < c->n_ranks; ++g) n_src_all += c->h_step[g].out_n[g];
+      const bool walk = n_src_all != 0;
       mark();
-      for (int hn = 1; hn <= (int)k.C + 1; ++hn) {
+      for (int hn = 1; walk && hn <= (int)k.C + 1; ++hn) {
         const bool fin = hn == (int)k.C + 1;
         const int first = hn == 1 ? 1 : 0;
         a = nlc_args(c, nullptr, 0);

@@ -64,6 +64,8 @@ def lib():
             getattr(L, f).restype = i32
         L.orc_run_pattern.argtypes = [vp, vp, vp, C.POINTER(OrcOptions)]
         L.orc_run_pattern.restype = vp
+        L.orc_run_fuzzy.argtypes = [vp, vp, vp, C.POINTER(OrcOptions)]
+        L.orc_run_fuzzy.restype = vp
         L.orc_run_free.argtypes = [vp]
         L.orc_run_error.argtypes = [vp]
         L.orc_run_error.restype = C.c_char_p
@@ -185,13 +187,15 @@ class Run:
     """Result of the reference outer loop (beta.cpp:544-1351) on the CPU oracle."""
 
     def __init__(self, graph, labels, pattern, n_ranks=1, tds_from_pl=4, max_iterations=0,
-                 lcc_only=False, threads=0, keep_subgraphs=True, delegate_threshold=0):
+                 lcc_only=False, threads=0, keep_subgraphs=True, delegate_threshold=0, fuzzy=False):
+        """fuzzy=True: the run_fuzzy_pattern_matching path (unique-label LCC + cycle token passing over
+        the unpruned adjacency) instead of run_pattern_matching_beta's."""
         L = lib()
         self.graph, self.pattern = graph, pattern
         self.labels = np.ascontiguousarray(labels, dtype=np.uint64)
         opt = OrcOptions(n_ranks, tds_from_pl, max_iterations, int(lcc_only), threads,
                          int(keep_subgraphs), delegate_threshold)
-        self.h = L.orc_run_pattern(graph.h, self.labels.ctypes.data, pattern.h, C.byref(opt))
+        self.h = (L.orc_run_fuzzy if fuzzy else L.orc_run_pattern)(graph.h, self.labels.ctypes.data, pattern.h, C.byref(opt))
         err = L.orc_run_error(self.h)
         if err:
             raise ValueError(err.decode())

@@ -46,6 +46,9 @@
 #include <string>
 #include <unordered_set>
 #include <vector>
+#include <unordered_map>
+#include <map>
+#include <deque>
 
 #ifdef _OPENMP
 #include <omp.h>
@@ -955,4 +958,191 @@ extern "C" int orc_run_write_results(const orc_run* r, const orc_graph* g, const
     }
   }
   return 0;
+}
+
+// ---------------------------------------------------------------------------
+// run_fuzzy path: unique-label LCC + cycle token passing over the UNPRUNED adjacency.
+//   LCC    include/havoqgt/label_propagation_pattern_matching_bsp.hpp:66-310 (visitor), :317-520
+//          (per-message state), :527-593 (post step), :598-699 (superstep loop)
+//   NLCC   include/havoqgt/token_passing_pattern_matching.hpp:51-508
+//   loop   src/run_pattern_matching.cpp:340-722 (the compiling twin of the stale
+//          src/run_fuzzy_pattern_matching.cpp:287-557; TP_ORIG is defined at :31)
+// Restated literally, message by message, with the reference's containers:
+//   vertex_state {is_active, vertex_pattern_index, pattern_vertex_itr_count_map}  (bsp.hpp:9-26)
+//   vertex_active, vertex_state_map, token_source_map, vertex_token_source_set.
+// ---------------------------------------------------------------------------
+namespace {
+
+struct FzState {
+  bool is_active = false;
+  uint32_t vpi = 0;
+  std::map<uint32_t, uint8_t> count;  // pattern_vertex_itr_count_map
+};
+
+struct FzCtx {
+  const orc_graph* g;
+  const uint64_t* label;
+  const orc_pattern* pat;
+  std::vector<uint8_t> active;                 // vertex_active
+  std::unordered_map<uint32_t, FzState> map;   // vertex_state_map
+};
+
+// lppm_visitor::verify_and_update_vertex_state_map (bsp.hpp:317-520) for itr_count == 1
+int fz_verify_update(FzCtx& c, uint32_t v, uint32_t q, uint32_t parent_idx) {
+  const orc_pattern& P = *c.pat;
+  if (!((P.N[q] >> parent_idx) & 1u)) return 0;                        // :330-339
+  auto it = c.map.find(v);
+  if (it == c.map.end()) {                                             // :360-370
+    it = c.map.insert({v, FzState()}).first;
+    it->second.vpi = q;
+  }
+  FzState& st = it->second;
+  if (st.is_active) return 1;                                          // :379-381
+  if (st.count.empty())                                                // :385-414
+    for (uint32_t b = 0; b < 16; ++b)
+      if ((P.N[q] >> b) & 1u) st.count.insert({b, 0});
+  if (st.count.empty()) return 0;                                      // :416-418
+  auto f = st.count.find(parent_idx);
+  if (f == st.count.end()) return 0;                                   // :420-430 ("did not find the expected item")
+  if (f->second < 1) f->second = 1;                                    // :433-435
+  bool all = true;                                                     // :438-466
+  for (auto& kv : st.count)
+    if (kv.second == 0) { all = false; break; }
+  st.is_active = all;
+  if (all)                                                             // :513-517
+    for (auto& kv : st.count) kv.second = 0;
+  return 1;
+}
+
+// one message of superstep `superstep` from u (as template index p) to v: pre_visit (:91-155) + visit (:163-310)
+void fz_deliver(FzCtx& c, uint32_t v, uint32_t p, bool map_required) {
+  const orc_pattern& P = *c.pat;
+  if (!c.active[v]) return;                                            // :93-95
+  // pre_visit: the FIRST template vertex carrying v's label decides (:113-141)
+  bool match = false;
+  for (uint32_t q = 0; q < (uint32_t)P.nv; ++q) {
+    if (P.vlabel[q] != c.label[v]) continue;
+    match = true;
+    if (!((P.N[q] >> p) & 1u)) return;                                 // :133-135
+    break;                                                             // :139-141
+  }
+  if (!match) return;
+  // visit (:163-...)
+  if (map_required && c.map.find(v) == c.map.end()) return;            // :173-178
+  for (uint32_t q = 0; q < (uint32_t)P.nv; ++q)
+    if (P.vlabel[q] == c.label[v]) fz_verify_update(c, v, q, p);       // :253-262
+}
+
+}  // namespace
+
+extern "C" orc_run* orc_run_fuzzy(const orc_graph* g, const uint64_t* labels, const orc_pattern* pat,
+                                   const orc_options* opt_in) {
+  orc_run* r = new orc_run();
+  r->g = g;
+  r->V = g->V;
+  orc_options opt{1, -1, 0, 0, 0, 0, 0};
+  if (opt_in) opt = *opt_in;
+  r->n_ranks = opt.n_ranks > 0 ? opt.n_ranks : 1;
+  const uint64_t V = g->V;
+  const orc_pattern& P = *pat;
+  FzCtx c{g, labels, pat, std::vector<uint8_t>(V, 1), {}};
+  // walks whose interior hops repeat a template vertex make the (source-keyed) aggregation set of
+  // token_passing_pattern_matching.hpp:104-109 depend on message order: not restated
+  for (auto& k : P.cons) {
+    for (size_t a = 1; a <= k.C && a < k.I.size(); ++a)
+      for (size_t b = a + 1; b <= k.C && b < k.I.size(); ++b)
+        if (k.I[a] == k.I[b]) { r->err = "token walk repeats a template vertex at interior hops (order dependent)"; return r; }
+  }
+  const int max_it = opt.max_iterations > 0 ? opt.max_iterations : 1000;
+  bool initstep = true, nf = false;
+  const double t_begin = now_s();
+  uint64_t itr = 0;
+  do {
+    nf = false;
+    // ---- label_propagation_pattern_matching_bsp (bsp.hpp:598-699) ----
+    for (int ss = 0; ss < P.diameter; ++ss) {
+      const double t0 = now_s();
+      const bool map_required = ss > 0 || !initstep;                   // :173
+      // senders are fixed at the start of the superstep: membership only changes by insertion
+      // during the very first superstep (where it is not consulted) and in the post step
+      std::vector<uint32_t> senders;
+      for (uint64_t u = 0; u < V; ++u) {
+        if (!c.active[u]) continue;                                    // :165-167
+        if (map_required && c.map.find((uint32_t)u) == c.map.end()) continue;
+        bool match = false;
+        for (int q = 0; q < P.nv; ++q) match = match || P.vlabel[q] == labels[u];
+        if (!match) { c.active[u] = 0; continue; }                     // :199-203
+        senders.push_back((uint32_t)u);
+      }
+      for (uint32_t u : senders)                                       // :207-225: all neighbours, all matching indices
+        for (uint64_t e = g->rowptr[u]; e < g->rowptr[u + 1]; ++e) {
+          r->edges_processed++;
+          for (int p = 0; p < P.nv; ++p)
+            if (P.vlabel[p] == labels[u]) fz_deliver(c, g->col[e], (uint32_t)p, map_required);
+        }
+      // post step (:527-593)
+      std::vector<uint32_t> gone;
+      for (auto& kv : c.map) {
+        if (!kv.second.is_active) { gone.push_back(kv.first); c.active[kv.first] = 0; }
+        else kv.second.is_active = false;
+      }
+      if (!gone.empty()) nf = true;
+      for (uint32_t v : gone) c.map.erase(v);
+      orc_row row{itr, 0, ss, c.map.size(), 0, now_s() - t0};
+      r->rows.push_back(row);
+    }
+    initstep = false;
+    // ---- token passing (run_pattern_matching.cpp:511-640), only if something was removed ----
+    if (nf) {
+      nf = false;
+      for (size_t pl = 0; pl < P.cons.size(); ++pl) {
+        const orc_constraint& k = P.cons[pl];
+        std::unordered_map<uint32_t, bool> token_source_map;           // cleared per constraint (:523)
+        std::unordered_map<uint32_t, std::unordered_set<uint32_t>> forwarded;  // vertex_token_source_set
+        struct Tok { uint32_t v, target, itr, parent_idx; };
+        std::deque<Tok> q;
+        for (auto& kv : c.map)                                          // init visit (tp.hpp:208-228)
+          if (kv.second.vpi == k.I[0] && labels[kv.first] == k.P[0]) {
+            token_source_map.insert({kv.first, false});
+            for (uint64_t e = g->rowptr[kv.first]; e < g->rowptr[kv.first + 1]; ++e)
+              q.push_back({g->col[e], kv.first, 0, k.I[0]});
+          }
+        while (!q.empty()) {
+          const Tok t = q.front();
+          q.pop_front();
+          r->edges_processed++;
+          const bool interior = k.C > t.itr;
+          if (interior && forwarded[t.v].count(t.target)) continue;     // pre_visit :104-109
+          auto f = c.map.find(t.v);
+          if (f == c.map.end()) continue;                               // :111-114
+          const uint32_t ni = t.itr + 1;
+          if (ni >= k.P.size()) continue;
+          if (!(labels[t.v] == k.P[ni] && f->second.vpi == k.I[ni] && t.parent_idx == k.I[ni - 1])) continue;  // :127-131, 157-164
+          if (interior) {
+            forwarded[t.v].insert(t.target);                            // :137-149
+            for (uint64_t e = g->rowptr[t.v]; e < g->rowptr[t.v + 1]; ++e)   // visit :289-295
+              q.push_back({g->col[e], t.target, ni, f->second.vpi});
+          } else if (t.v == t.target && k.valid_cycle) {                // :250-262
+            token_source_map[t.v] = true;
+          }
+        }
+        for (auto& kv : token_source_map)                               // TP_ORIG post-processing (:583-629)
+          if (!kv.second) { c.active[kv.first] = 0; c.map.erase(kv.first); nf = true; }
+      }
+      orc_row row{itr, 1, 0, c.map.size(), 0, 0.0};                     // "itr, TP, 0, count" (:664-666)
+      r->rows.push_back(row);
+    }
+    ++itr;
+    if ((int)itr >= max_it && nf) { r->hazards[4]++; break; }
+  } while (nf);
+  r->iterations = itr;
+  r->search_seconds = now_s() - t_begin;
+  r->inmap.assign(V, 0);
+  r->T_arr.assign(V, 0);
+  for (auto& kv : c.map) { r->inmap[kv.first] = 1; r->T_arr[kv.first] = (uint16_t)(1u << kv.second.vpi); }
+  r->active = c.active;
+  r->estate.assign(g->col.size(), 0);  // this path keeps no edge maps
+  r->subgraphs.resize(P.cons.size());
+  r->subgraph_width.assign(P.cons.size(), 0);
+  return r;
 }

@@ -119,6 +119,12 @@ const uint64_t* orc_run_hazards(const orc_run*);
 int orc_run_write_results(const orc_run*, const orc_graph*, const uint64_t* labels,
                           const orc_pattern*, const char* outdir);
 
+/* ---- run_fuzzy path: unique-label LCC (label_propagation_pattern_matching_bsp.hpp) + cycle
+ * token passing over the unpruned adjacency (token_passing_pattern_matching.hpp), loop of
+ * src/run_pattern_matching.cpp:340-722.  Rows: (itr, LP, k, |map|, 0) per superstep and (itr, TP, 0, |map|, 0)
+ * once per iteration that ran token passing; template_vertices[v] = 1 << vertex_pattern_index.  ---- */
+orc_run* orc_run_fuzzy(const orc_graph*, const uint64_t* labels, const orc_pattern*, const orc_options*);
+
 #ifdef __cplusplus
 }
 #endif

@@ -77,6 +77,7 @@ SYMBOLS = {
     "pm_lcc": (_i, [_vp, _i, C.POINTER(_i), C.POINTER(Counts)]),
     "pm_nlcc": (_i, [_vp, _i, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(Counts)]),
     "pm_run": (_i, [_vp, C.POINTER(RunOptions), C.POINTER(RunSummary)]),
+    "pm_run_fuzzy": (_i, [_vp, C.POINTER(RunOptions), C.POINTER(RunSummary)]),
     "pm_get_rows": (_i, [_vp, C.POINTER(Row)]),
     "pm_get_active_vertices": (_i, [_vp, _vp, _vp]),
     "pm_get_active_edges": (_i, [_vp, _vp]),

@@ -18,6 +18,7 @@
 #include "pm_nlcc.cuh"
 #include "pm_nlcc_multi.cuh"
 #include "pm_rmat.cuh"
+#include "pm_fuzzy.cuh"
 
 using namespace pm;
 
@@ -1059,6 +1060,155 @@ int pm_run(pm_ctx* c, const pm_run_options_t* opt_in, pm_run_summary_t* out) {
     c->summary.n_active_vertices = c->rows.back().n_vertices;
     c->summary.n_active_edges = c->rows.back().n_edges;
   }
+  if (out) *out = c->summary;
+  return 0;
+}
+
+// ------------------------------------------------------ the run_fuzzy loop
+int pm_run_fuzzy(pm_ctx* c, const pm_run_options_t* opt_in, pm_run_summary_t* out) {
+  if (!c) return PM_ERR_ARG;
+  if (c->n_ranks > 1) return fail(c, PM_ERR_UNSUPPORTED, "pm_run_fuzzy: one rank only");
+  if (!c->has_graph || !c->has_labels || !c->has_pattern) return fail(c, PM_ERR_ARG, "pm_run_fuzzy needs a graph, labels and a pattern");
+  if (!c->labels_small) return fail(c, PM_ERR_UNSUPPORTED, "pm_run_fuzzy: labels must be < 64");
+  // a walk that repeats a template vertex at interior hops makes the source-keyed aggregation set of
+  // token_passing_pattern_matching.hpp:104-109 depend on message order
+  for (const Constraint& k : c->pat.constraints)
+    for (size_t x = 1; x <= k.C && x < k.I.size(); ++x)
+      for (size_t y = x + 1; y <= k.C && y < k.I.size(); ++y)
+        if (k.I[x] == k.I[y]) return fail(c, PM_ERR_UNSUPPORTED, "token walk repeats a template vertex at interior hops (order dependent)");
+  pm_run_options_t opt{-1, 0, 0, 0};
+  if (opt_in) opt = *opt_in;
+  int rc = pm_state_reset(c);  // allocations, pattern constants, bookkeeping (beta.cpp:484-492 analogue)
+  if (rc) return rc;
+  cudaStream_t st = c->stream;
+  const int D = c->pat.diameter, grid = grid_for();
+  const int max_it = opt.max_iterations > 0 ? opt.max_iterations : 1000;
+  FzArgs a;
+  a.rowblk = c->rowblk; a.deg = c->deg; a.col0 = c->col0; a.lab0 = c->lab0; a.lab8 = c->lab8; a.S = c->S; a.cnt = c->cnt;
+  a.row = c->rowstat;
+  PM_CUDA(c, cudaMemsetAsync(c->cnt, 0, sizeof(DevCounters), st));
+  c->cur = 0;
+  bool init = true;
+  int nf = 0;
+  const double t_begin = wall_s();
+  do {
+    const double it0 = wall_s();
+    // ---- label_propagation_pattern_matching_bsp (bsp.hpp:598-699): `diameter` supersteps
+    PM_CUDA(c, cudaMemsetAsync(c->rowstat, 0, D * sizeof(RowStat), st));
+    PM_CUDA(c, cudaMemsetAsync(&c->cnt->nf, 0, sizeof(uint32_t), st));
+    for (int k = 0; k < D; ++k) {
+      PM_CUDA(c, cudaEventRecord(c->events[k], st));
+      a.row = c->rowstat + k;
+      if (init && k == 0) {
+        PM_CUDA(c, cudaMemsetAsync(&c->cnt->fr_n[0][0], 0, 8 * sizeof(uint32_t), st));
+        k_fz_init<<<grid, kBlock, 0, st>>>(a, c->sig, c->nloc, c->fr[0][0], 0);
+        PM_LAUNCH_CHECK(c);
+        c->cur = 0;
+      } else {
+        const int cur = c->cur, nxt = cur ^ 1;
+        PM_CUDA(c, cudaMemsetAsync(&c->cnt->fr_n[nxt][0], 0, 4 * sizeof(uint32_t), st));
+        k_fz_scan<<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], &c->cnt->fr_n[cur][0]);
+        PM_LAUNCH_CHECK(c);
+        k_fz_commit<<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], c->fr[nxt][0], cur, nxt);
+        PM_LAUNCH_CHECK(c);
+        c->cur = nxt;
+      }
+    }
+    PM_CUDA(c, cudaEventRecord(c->events[D], st));
+    PM_CUDA(c, cudaMemcpyAsync(c->h_rowstat, c->rowstat, D * sizeof(RowStat), cudaMemcpyDeviceToHost, st));
+    if ((rc = sync_counters(c))) return rc;
+    nf = c->h_cnt->nf ? 1 : 0;
+    for (int k = 0; k < D; ++k) {
+      float ms = 0;
+      PM_CUDA(c, cudaEventElapsedTime(&ms, c->events[k], c->events[k + 1]));
+      pm_row_t r;
+      r.itr = c->itr; r.kind = 0; r.index = k; r.n_vertices = c->h_rowstat[k].nv; r.n_edges = 0; r.seconds = ms * 1e-3;
+      c->rows.push_back(r);
+      c->summary.device_seconds += r.seconds;
+      c->summary.edges_processed += c->h_rowstat[k].scanned[0];
+      // 4 B id + 1 B label per walked slot, 2 B mask gathers for the label-matching ones are not counted
+      c->summary.algorithmic_bytes += c->h_rowstat[k].scanned[0] * 5 + c->h_rowstat[k].verts[0] * 16;
+    }
+    c->step_rows.push_back({c->itr, wall_s() - it0});
+    init = false;
+    // ---- token passing only after an LCC call that removed something (run_pattern_matching.cpp:511)
+    if (nf) {
+      nf = 0;
+      PM_CUDA(c, cudaEventRecord(c->events[0], st));
+      const int cur = c->cur;
+      for (size_t pl = 0; pl < c->pat.constraints.size(); ++pl) {
+        const Constraint& k = c->pat.constraints[pl];
+        FzTok ft;
+        std::memset(&ft, 0, sizeof(ft));
+        ft.C = (int)k.C;
+        ft.valid_cycle = k.valid_cycle ? 1 : 0;
+        if (k.P.size() > 18) return fail(c, PM_ERR_UNSUPPORTED, "token walk longer than 18 vertices");
+        for (size_t h = 0; h < k.P.size(); ++h) { ft.lab[h] = (uint8_t)(k.P[h] < 64 ? k.P[h] : 255); ft.I[h] = (uint8_t)k.I[h]; }
+        PM_CUDA(c, cudaMemcpyToSymbolAsync(c_fz, &ft, sizeof(ft), 0, cudaMemcpyHostToDevice, st));
+        if (c->pool_seen.size() != c->pat.constraints.size()) c->pool_seen.assign(c->pat.constraints.size(), 0);
+        uint64_t want = c->pool_seen[pl] ? c->pool_seen[pl] + c->pool_seen[pl] / 2 + 4096 : std::max<uint64_t>(1ull << 20, 16 * c->rows.back().n_vertices);
+        for (int attempt = 0;; ++attempt) {
+          if ((rc = nlcc_reserve(c, want, want))) return rc;
+          c->hset_use = c->hset_cap;
+          uint64_t use = 1;
+          while (use < 2 * want) use <<= 1;
+          c->hset_use = std::min(use, c->hset_cap);
+          PM_CUDA(c, cudaMemsetAsync(&c->cnt->found, 0, sizeof(DevCounters) - offsetof(DevCounters, found), st));
+          PM_CUDA(c, cudaMemsetAsync(c->hset, 0xFF, c->hset_use * sizeof(unsigned long long), st));
+          NlcArgs t = nlc_args(c, nullptr, 0);
+          k_fz_sources<<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], cur, c->ok, c->src_list, c->pool);
+          PM_LAUNCH_CHECK(c);
+          k_nlcc_begin<<<1, 1, 0, st>>>(c->cnt);
+          PM_LAUNCH_CHECK(c);
+          for (int hn = 1; hn <= (int)k.C; ++hn) {  // interior hops
+            k_fz_expand<<<grid, kBlock, 0, st>>>(a, t, hn - 1, hn);
+            PM_LAUNCH_CHECK(c);
+            k_nlcc_close_level<<<1, 1, 0, st>>>(c->cnt, hn, c->pool_cap);
+            PM_LAUNCH_CHECK(c);
+          }
+          if (k.valid_cycle) {  // a path never marks its source in this path (tp.hpp:263-268)
+            k_fz_final<<<grid, kBlock, 0, st>>>(a, t, (int)k.C, (int)k.C + 1);
+            PM_LAUNCH_CHECK(c);
+          }
+          if ((rc = sync_counters(c))) return rc;
+          if (!(c->h_cnt->overflow || c->h_cnt->pool_n > c->pool_cap)) {
+            c->pool_seen[pl] = std::max<uint64_t>(c->pool_seen[pl], c->h_cnt->pool_n);
+            break;
+          }
+          if (attempt >= 6) return fail(c, PM_ERR_CAPACITY, "token pool exhausted");
+          want *= 4;
+        }
+        c->summary.edges_processed += c->h_cnt->fanout;
+        c->summary.algorithmic_bytes += c->h_cnt->fanout * 5 + c->h_cnt->pool_n * 16;
+        k_fz_apply<<<grid, kBlock, 0, st>>>(c->S, c->ok, c->src_list, c->cnt);
+        PM_LAUNCH_CHECK(c);
+        if ((rc = sync_counters(c))) return rc;
+        if (c->h_cnt->deleted) nf = 1;
+      }
+      // "itr, TP, 0, |map|" (run_pattern_matching.cpp:664-666)
+      PM_CUDA(c, cudaMemsetAsync(c->rowstat + D, 0, sizeof(RowStat), st));
+      a.row = c->rowstat + D;
+      k_fz_count<<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], cur);
+      PM_LAUNCH_CHECK(c);
+      PM_CUDA(c, cudaEventRecord(c->events[1], st));
+      PM_CUDA(c, cudaMemcpyAsync(c->h_rowstat + D, c->rowstat + D, sizeof(RowStat), cudaMemcpyDeviceToHost, st));
+      if ((rc = sync_counters(c))) return rc;
+      float ms = 0;
+      PM_CUDA(c, cudaEventElapsedTime(&ms, c->events[0], c->events[1]));
+      pm_row_t r;
+      r.itr = c->itr; r.kind = 1; r.index = 0; r.n_vertices = c->h_rowstat[D].nv; r.n_edges = 0; r.seconds = ms * 1e-3;
+      c->rows.push_back(r);
+      c->summary.device_seconds += r.seconds;
+    }
+    c->iter_seconds.push_back(wall_s() - it0);
+    c->itr++;
+    if ((int)c->itr >= max_it && nf) { c->err = "iteration cap reached"; break; }
+  } while (nf);
+  c->summary.iterations = c->itr;
+  c->summary.search_seconds = wall_s() - t_begin;
+  c->summary.n_rows = c->rows.size();
+  c->summary.n_active_vertices = c->rows.empty() ? 0 : c->rows.back().n_vertices;
+  c->summary.n_active_edges = 0;
   if (out) *out = c->summary;
   return 0;
 }

@@ -152,6 +152,15 @@ class Engine:
         self.summary = {n: getattr(s, n) for n, _ in s._fields_}
         return self.summary
 
+    def run_fuzzy(self, max_iterations=0):
+        """The run_fuzzy_pattern_matching path (run_fuzzy_pattern_matching.cpp / run_pattern_matching.cpp):
+        unique-label LCC + cycle token passing over the unpruned adjacency."""
+        opt = _lib.RunOptions(-1, max_iterations, 0, 0)
+        s = _lib.RunSummary()
+        self._chk(self._lib.pm_run_fuzzy(self._h, C.byref(opt), C.byref(s)))
+        self.summary = {n: getattr(s, n) for n, _ in s._fields_}
+        return self.summary
+
     def rows(self):
         n = int(self.summary["n_rows"])
         buf = (_lib.Row * max(n, 1))()

@@ -193,6 +193,16 @@ typedef struct {
 } pm_row_t;
 
 int pm_run(pm_ctx* ctx, const pm_run_options_t* opt, pm_run_summary_t* out);
+/* The run_fuzzy_pattern_matching path (src/run_fuzzy_pattern_matching.cpp:287-557; the driver is stale at this
+ * revision, its compiling twin is src/run_pattern_matching.cpp:340-722): unique-label LCC
+ * (include/havoqgt/label_propagation_pattern_matching_bsp.hpp:598-699) — every vertex stands for the FIRST template
+ * vertex carrying its label and must hear all of that vertex's template neighbours among ALL its graph neighbours
+ * each superstep, no edge elimination — followed, when LCC removed something, by cycle token passing over the
+ * unpruned adjacency (include/havoqgt/token_passing_pattern_matching.hpp:514-530) whose failed sources leave the
+ * vertex_state_map.  Rows: (itr, LP, k, |map|, 0) and one (itr, TP, 0, |map|, 0) per iteration that passed
+ * tokens; pm_get_active_vertices returns (vertex, 1 << vertex_pattern_index).  Only opt->max_iterations is used.
+ * One rank, labels < 64. */
+int pm_run_fuzzy(pm_ctx* ctx, const pm_run_options_t* opt, pm_run_summary_t* out);
 /* For a host driver that spells the loop out over pm_lcc / pm_nlcc itself (as the
  * reference main does): closes outer iteration `global_itr_count` (beta.cpp:1327-1341)
  * so that later rows carry the next iteration number and result_iteration gets its row. */

@@ -220,3 +220,42 @@ def test_large_label_values_take_the_gather_path(oracle, eng):
             edges = cases.random_multigraph(seed + 40, n, m)
             labels = cases.random_labels(seed + 40, n, labelset) + np.uint64(off)
             _compare(oracle, eng, n, edges, labels, spec, tds_from)
+
+
+def test_run_fuzzy_path_matches_oracle(oracle, eng):
+    """unique-label LCC + cycle token passing over the unpruned adjacency (pm_run_fuzzy)."""
+    from fuzzypatternmatching_b200 import patterns as PT
+    nontrivial = 0
+    for spec, labelset in ((PT.triangle(1, 2, 3), [1, 2, 3]), (PT.cycle4(1, 2, 3, 4), [1, 2, 3, 4])):
+        d = cases.pattern_dir(spec)
+        for seed in range(10):
+            n, m = 60 + 10 * (seed % 4), 220 + 60 * (seed % 5)
+            edges = cases.random_multigraph(seed, n, m)
+            labels = cases.random_labels(seed, n, labelset)
+            g = oracle.Graph.from_undirected(n, edges)
+            ref = oracle.Run(g, labels, oracle.Pattern(d), fuzzy=True, max_iterations=50)
+            src, dst = cases.slots_of(edges)
+            eng.graph_from_slots(n, src, dst)
+            eng.labels_set(labels)
+            eng.pattern_load_dir(d)
+            eng.run_fuzzy(max_iterations=50)
+            assert eng.rows() == ref.rows and int(eng.summary["iterations"]) == ref.iterations
+            v, t = eng.active_vertices()
+            rv, rt = ref.active_vertices()
+            assert np.array_equal(v, rv) and np.array_equal(t, rt)
+            nontrivial += len(rv) > 0
+    assert nontrivial >= 5
+    # R-MAT with degree labels
+    spec = PT.cycle4(5, 6, 7, 8)
+    d = cases.pattern_dir(spec)
+    g = oracle.Graph.rmat(17, 4)
+    labels = g.labels_degree_log2()
+    ref = oracle.Run(g, labels, oracle.Pattern(d), fuzzy=True)
+    eng.graph_rmat(17, 4)
+    eng.labels_degree_log2()
+    eng.pattern_load_dir(d)
+    eng.run_fuzzy()
+    assert eng.rows() == ref.rows
+    v, t = eng.active_vertices()
+    rv, rt = ref.active_vertices()
+    assert np.array_equal(v, rv) and np.array_equal(t, rt) and len(rv) > 0

@@ -125,3 +125,72 @@ def cycle6_chords(labels):
                         # one walk that covers every template edge
                         {"walk": [0, 1, 2, 3, 4, 5, 0, 3, 4, 1], "tds": True}],
     }
+
+
+# ---------------------------------------------------------------------------
+# BASELINE configs[3]: "edit-distance-k prototype set (k = 1, 2)".  The reference holds no
+# prototype logic (grep -i "edit.?dist|prototype" over src/ and include/ finds nothing; its drivers
+# only ever read pattern directory 0, run_fuzzy_pattern_matching.cpp:208), so the SET is ours: the
+# connected templates obtained from a base template by deleting up to k edges.  Each prototype is an
+# ordinary pattern directory <base>/<i>/ and is searched independently.
+# ---------------------------------------------------------------------------
+def _connected(n, edges):
+    adj = {i: set() for i in range(n)}
+    for a, b in edges:
+        adj[a].add(b)
+        adj[b].add(a)
+    seen, todo = {0}, [0]
+    while todo:
+        x = todo.pop()
+        for y in adj[x]:
+            if y not in seen:
+                seen.add(y)
+                todo.append(y)
+    return len(seen) == n
+
+
+def _diameter(n, edges):
+    adj = {i: set() for i in range(n)}
+    for a, b in edges:
+        adj[a].add(b)
+        adj[b].add(a)
+    best = 0
+    for s in range(n):
+        dist, todo = {s: 0}, [s]
+        for x in todo:
+            for y in adj[x]:
+                if y not in dist:
+                    dist[y] = dist[x] + 1
+                    todo.append(y)
+        best = max(best, max(dist.values()))
+    return best
+
+
+def edit_distance_prototypes(spec, k):
+    """[(deleted_edges, prototype_spec)] for every connected template within edit distance k of `spec`
+    (edge deletions only; distance 0 = the base template itself comes first).  A constraint is kept iff
+    every edge of its walk is still present; the superstep count follows the prototype's diameter."""
+    import itertools
+    n = len(spec["labels"])
+    base = [tuple(sorted(e)) for e in spec["edges"]]
+    out = []
+    for dist in range(0, k + 1):
+        for gone in itertools.combinations(base, dist):
+            edges = [e for e in base if e not in gone]
+            if not edges or not _connected(n, edges):
+                continue
+            es = set(edges)
+            cons = [c for c in spec.get("constraints", [])
+                    if all(tuple(sorted((a, b))) in es for a, b in zip(c["walk"], c["walk"][1:]))]
+            out.append((list(gone), {"labels": list(spec["labels"]), "edges": edges,
+                                     "diameter": max(spec.get("diameter", 1) if dist == 0 else 1, _diameter(n, edges)),
+                                     "constraints": cons}))
+    return out
+
+
+def write_prototype_set(base_dir, spec, k):
+    """Writes <base_dir>/<i>/pattern_* for every prototype; returns [(i, deleted_edges, dir)]."""
+    out = []
+    for i, (gone, proto) in enumerate(edit_distance_prototypes(spec, k)):
+        out.append((i, gone, write_pattern_dir(base_dir, proto, ps=i)))
+    return out

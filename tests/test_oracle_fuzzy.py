@@ -71,3 +71,18 @@ def test_fuzzy_known_answers(oracle):
     ref4 = oracle.Run(g4, np.array([1, 2, 3, 1, 2, 3, 1], dtype=np.uint64), oracle.Pattern(d), fuzzy=True)
     assert ref4.active_vertices()[0].size == 0 and ref4.iterations >= 2
     assert ("TP" in [r[1] for r in ref4.rows])
+
+
+def test_prototype_set_generation(tmp_path):
+    """BASELINE configs[3]: connected edge-deleted variants within edit distance k, as pattern directories."""
+    import os
+    protos = PT.edit_distance_prototypes(PT.cycle4(5, 6, 7, 8), 2)
+    assert [len(g) for g, _ in protos] == [0, 1, 1, 1, 1]  # two deletions disconnect a 4-cycle
+    assert len(protos[0][1]["constraints"]) == 2 and all(not p["constraints"] for _, p in protos[1:])
+    assert [p["diameter"] for _, p in protos] == [3, 3, 3, 3, 3]
+    six = PT.edit_distance_prototypes(PT.cycle6_chords([4, 5, 6, 7, 8, 9]), 2)
+    assert len(six) == 1 + 8 + 26 and all(len(p["edges"]) == 8 - len(g) for g, p in six)
+    dirs = PT.write_prototype_set(str(tmp_path), PT.cycle4(5, 6, 7, 8), 1)
+    assert [os.path.basename(d) for _, _, d in dirs] == ["0", "1", "2", "3", "4"]
+    assert open(os.path.join(dirs[1][2], "pattern_stat")).read().strip() == "diameter : 3"
+    assert open(os.path.join(dirs[1][2], "pattern_nlc")).read().strip() == ""

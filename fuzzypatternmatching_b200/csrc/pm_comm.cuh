@@ -65,6 +65,13 @@ inline Api& api() {
 
 __constant__ PeerTab c_peer;
 
+// owner of a compact id: rank g owns [off[g], off[g+1])
+__device__ __forceinline__ uint32_t cid_owner(uint32_t c) {
+  uint32_t o = 0;
+  for (int g = 1; g < c_peer.G; ++g) o += c >= c_peer.off[g] ? 1u : 0u;
+  return o;
+}
+
 #define PM_NCCL(ctx, call)                                                                          \
   do {                                                                                              \
     ncclResult_t r_ = (call);                                                                       \
@@ -150,6 +157,8 @@ __global__ void k_step_msg(DevCounters* cnt, StepMsg* msg) {
     msg->deleted = cnt->deleted;
     msg->overflow = cnt->overflow;
     msg->accepted = cnt->pool_n;
+    msg->n_c = cnt->n_c;
+    msg->pad1 = 0;
     msg->seq = 0;
     msg->timeout = 0;
   }
@@ -180,6 +189,8 @@ __global__ void k_step_sync(DevCounters* cnt, StepMsg* msg, StepMsg* all_out, ui
     msg->deleted = cnt->deleted;
     msg->overflow = cnt->overflow;
     msg->accepted = cnt->pool_n;
+    msg->n_c = cnt->n_c;
+    msg->pad1 = 0;
     msg->seq = seq;
     msg->timeout = 0;
   }
@@ -245,6 +256,14 @@ inline int comm_allgather_slots(pm_ctx* c, T* replicated) {
   if (c->n_ranks == 1) return 0;
   PM_NCCL(c, ncclAllGather(replicated + (uint64_t)c->rank * c->nlmax, replicated, c->nlmax * sizeof(T), ncclChar,
                            comm_of(c), c->stream));
+  return 0;
+}
+
+// all-gathers equally sized per-rank segments of an array in place (segment g = [g * n, (g + 1) * n))
+template <class T>
+inline int comm_allgather_seg(pm_ctx* c, T* array, uint64_t n) {
+  if (c->n_ranks == 1 || n == 0) return 0;
+  PM_NCCL(c, ncclAllGather(array + (uint64_t)c->rank * n, array, n * sizeof(T), ncclChar, comm_of(c), c->stream));
   return 0;
 }
 

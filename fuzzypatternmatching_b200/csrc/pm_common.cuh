@@ -68,6 +68,8 @@ struct DevCounters {
   uint32_t pad2;
   unsigned long long peak_out;  // largest inbox region fill of any hop (sizes the next run's inboxes)
   unsigned long long ce_n;      // closing-edge keys filed in the hash set
+  uint32_t n_c;                 // survivors of the first-superstep filter on this rank = compact ids it owns
+  uint32_t pad3;
 };
 
 // what every rank contributes to the per-step all-gather (= the barrier)
@@ -75,6 +77,7 @@ struct StepMsg {
   unsigned long long out_n[PM_MAX_RANKS];
   uint32_t ndelta, nf, found, deleted, overflow, pad;  // pad: nf_init
   unsigned long long accepted;   // tokens accepted so far (pool_n)
+  uint32_t n_c, pad1;            // compact ids this rank owns (published once per pattern)
   uint32_t seq;                  // step number: written LAST, polled by the receiver
   uint32_t timeout;              // a peer never arrived (the step barrier gave up)
 };
@@ -100,6 +103,8 @@ struct PeerTab {
   uint2* din[2][PM_MAX_RANKS];           // delta inbox of rank g: G regions of dcap (slot, mask) pairs, double buffered
   uint2* tin[2][PM_MAX_RANKS];           // token inbox of rank g: G regions of tcap tokens, double buffered
   StepMsg* sync_in[PM_MAX_RANKS];        // step mailbox of rank g: [2][G] StepMsg, slot [seq & 1][sender]
+  // compact ids of the current pattern (see "Compact ids" in pm_lcc.cuh): rank g owns [off[g], off[g+1])
+  uint32_t off[PM_MAX_RANKS + 1];
 };
 
 struct RowStat {                // one result row, accumulated on the device
@@ -155,7 +160,13 @@ struct pm_ctx {
   // ---- per-pattern state (device) -----------------------------------------------
   uint16_t* S = nullptr;    // [V] template_vertices[v] (T_arr) while v is active and in the map, else 0
                             // (vertex_state.template_vertices, T_state, lives in the frontier entries)
-  uint32_t* adeg = nullptr; // [V] |E_v|
+  uint32_t* adeg = nullptr; // [nloc] |E_v|, by LOCAL compact id (cid - off[rank])
+  uint32_t* rowc = nullptr; // [nloc] row start (sectors), by local compact id
+  uint32_t* vid = nullptr;  // [Vs] compact id -> slot (replicated)
+  uint8_t* clsc = nullptr;  // [Vs] label class by compact id (replicated)
+  uint32_t* fw = nullptr;   // [Vs / 16] per 16 slots: survivors before them in their tile << 16 | survivor bits (replicated)
+  uint32_t* tb = nullptr;   // [tiles] compact id of every 4096-slot tile's first survivor (replicated)
+  uint32_t cid_off[PM_MAX_RANKS + 1] = {0};  // host copy of the compact id ranges
   uint8_t* cls = nullptr;   // [V] label class (index into the template's distinct labels, PM_NOCLASS = none)
   uint4* fr[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // frontier entry lists [buffer][main, big rows]
   int cur = 0;              // which frontier buffer is current
@@ -168,6 +179,7 @@ struct pm_ctx {
   pm::RowStat* rowstat = nullptr;      // device, [diameter + 1]
   pm::RowStat* h_rowstat = nullptr;    // pinned
   bool state_ready = false;
+  bool fuzzy_ids = false;   // the frontier entries of the last run name vertices, not compact ids (pm_run_fuzzy)
 
   // ---- NLCC scratch -----------------------------------------------------------------
   uint8_t* ok = nullptr;            // [V] token_source_map value of source s

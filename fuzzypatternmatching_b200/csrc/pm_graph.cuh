@@ -275,8 +275,9 @@ inline void graph_set_partition(pm_ctx* c, uint64_t V) {
   if (c->n_ranks == 1) {
     c->nlmax = V;
   } else {
+    // 4096-aligned: the compact id tables (pm_lcc.cuh) work on tiles of 4096 slots that must not straddle ranks
     const uint64_t per = (V + c->n_ranks - 1) / c->n_ranks;
-    c->nlmax = (per + 15) / 16 * 16;
+    c->nlmax = (per + 4095) / 4096 * 4096;
   }
   c->nloc = c->nlmax;
 }

@@ -116,12 +116,14 @@ struct LccArgs {
   uint8_t* labw;        // [Epad] same for colw, moved along by the row compaction
   DevCounters* cnt;
   RowStat* row;   // accumulator of this superstep
-  uint32_t base;  // first slot of this rank: entries and rank-local arrays are indexed by slot - base
+  uint32_t base;  // first compact id of this rank: rank-local arrays (adeg, rowc) are indexed by cid - base
   int par;        // delta inbox the commit of this superstep publishes into
+  const uint32_t* fw;      // slot -> compact id (first scan): survivor bits + in-tile prefix per 16 slots
+  const uint32_t* tb;      // cid of every tile's first survivor
 };
 
-// frontier entry: x = local row (slot - base), y = row start in sectors, z = |E_v| (deg(v) before the
-// first scan), w = T_state (vertex_state.template_vertices)
+// frontier entry: x = compact id, y = row start in sectors (PM_TOMB: the row is in the big-row list),
+// z = |E_v| (deg(v) before the first scan), w = T_state (vertex_state.template_vertices)
 __device__ __forceinline__ int bin_of(uint32_t d) { return d <= PM_MID_MAX ? 0 : 1; }
 
 // Publishes "the mask of my vertex `slot` is now `mask`" to every peer: the pair is stored straight
@@ -158,230 +160,221 @@ __global__ void __launch_bounds__(kBlock) k_apply_deltas(uint16_t* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------
-// per-pattern initialisation (beta.cpp:484-492 + the label test every vertex
-// performs in the first superstep, ee.hpp:371-380 / :523-546), labels >= 64:
-//   cls[v] = class of label[v] for EVERY local vertex (the first scan gathers it);
-//   candidates (label matches a template vertex, degree > 0) get S[v] =
-//   labelmask(label[v]) and an entry in the frontier.
-//   S of a non-candidate is never read: every later gather goes through an edge
-//   map, and edge maps only ever hold candidates.
+// Compact ids.  After the first-superstep filter only a few % of the vertices are left, but their
+// masks would stay scattered over a V-sized array: every later gather S[u] would pull a 32-byte
+// sector from HBM for 2 useful bytes.  The survivors are therefore renumbered densely, in vertex
+// order, and EVERYTHING after the filter — masks, classes, |E_v|, row starts, the working adjacency,
+// tokens, hash keys — is indexed by that compact id (cid).  The whole mask array then fits in L2.
+//   vid[cid] = slot of the vertex.  slot -> cid needs no table of its own: survivors are numbered in slot
+//   order, so cid(s) = tb[s / 4096] + prefix(s / 16) + popc(bits of word s / 16 below s), read from
+//   fw[s / 16] = (survivors before this word inside its tile) << 16 | (survivor bits of 16 vertices)
+//   and tb[tile] = cid of the tile's first survivor — 4 bytes per 16 vertices, L2 resident.
+// With several GPUs rank g owns the cids [off[g], off[g+1]) (c_peer.off), numbered by (rank, slot);
+// fw and tb are all-gathered (slot ranges are rank-contiguous and tile aligned).
+// The first scan copies the neighbours it keeps as SLOTS (a kept neighbour that did not survive the
+// filter is in E_v for the first superstep's edge count, ee.hpp:791-813); the second scan of the call
+// (XLATE) renames them to cids while it walks the by then short rows and drops the non-survivors, whose
+// masks are zero.  A pattern with a single superstep per LCC call (pattern_stat diameter 1) has no second
+// scan: its filter is switched off (every label-matching vertex is numbered) and a rename-only pass follows.
+//
+// per-pattern initialisation (beta.cpp:484-492) + the label test every vertex performs in the first
+// superstep (ee.hpp:371-380 / :523-546) + (labels < 64) the signature filter, in three passes:
+//   k_init_flags   one streaming pass over the local vertices: survivor bits + in-tile prefixes (fw), count per tile
+//   k_init_scan    exclusive prefix of the tile counts (one block)
+//   k_init_assign  per-cid state (mask, class, slot) for EVERY survivor, frontier entries for the local ones
+// Signature filter: in the first superstep every neighbour u of v sends labelmask(label[u])
+// (ee.hpp:519-561), so heard(v) depends only on WHICH labels occur among v's neighbours:
+// heard(v) = OR { LM(l) : l in sig[v], LM(l) & NB(T_v) != 0 } — exactly what walking the row would
+// compute.  A candidate whose T_state comes out empty leaves (or never enters) the map; it is settled
+// from 8 bytes of signature instead of its whole row (tables c_pat.req / c_pat.rl).
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) k_init_state(const uint64_t* __restrict__ label,
+#define PM_TILE (kBlock * 16)     // vertices per tile: 16 per thread
+#define PM_TOMB 0xFFFFFFFFu       // entry.y of a main-list slot whose row lives in the big-row list
+
+// SMALL: labels are bytes < 64 (lab8, signature filter); else u64 labels, every label-matching
+// vertex of degree > 0 is a "survivor" and cls[] (by slot) is filled for the first scan's gathers
+template <bool SMALL>
+__global__ void __launch_bounds__(kBlock) k_init_flags(const uint8_t* __restrict__ lab8, const uint64_t* __restrict__ label,
                                                         const uint32_t* __restrict__ deg,
-                                                        const uint32_t* __restrict__ rowblk, uint64_t V,
-                                                        uint8_t* __restrict__ cls, uint16_t* __restrict__ S,
-                                                        uint4* fr_main, uint4* fr_big, DevCounters* cnt, int buf) {
-  __shared__ uint16_t s_lm[17];
-  if (threadIdx.x < 17) s_lm[threadIdx.x] = c_pat.LMc[threadIdx.x];
-  __syncthreads();
-  constexpr int IT = 4;
-  const uint64_t tile = (uint64_t)blockDim.x * IT;
-  for (uint64_t base = (uint64_t)blockIdx.x * tile; base < V; base += (uint64_t)gridDim.x * tile) {
-    bool cand[IT];
-    int bin[IT];
-    uint4 val[IT];
-#pragma unroll
-    for (int k = 0; k < IT; ++k) {
-      const uint64_t v = base + (uint64_t)k * blockDim.x + threadIdx.x;
-      uint32_t c = PM_NOCLASS, d = 0, lm = 0;
-      if (v < V) {
-        const uint64_t lab = label[v];
-#pragma unroll
-        for (int q = 0; q < 16; ++q)
-          if (q < c_pat.ncls && c_pat.clabel[q] == lab) c = q;
-        cls[v] = (uint8_t)c;
-        if (c != PM_NOCLASS) {
-          d = deg[v];
-          lm = s_lm[c];
-          if (d) S[v] = (uint16_t)lm; else c = PM_NOCLASS;
-        }
-      }
-      cand[k] = c != PM_NOCLASS;
-      bin[k] = bin_of(d);
-      val[k] = make_uint4((uint32_t)v, cand[k] ? rowblk[v] : 0u, d, lm);
-    }
-    block_append2<IT>(cand, bin, val, fr_main, fr_big, &cnt->fr_n[buf][0]);
-  }
-}
-
-// class of EVERY slot from the replicated byte labels (several GPUs: neighbours owned by peers)
-__global__ void __launch_bounds__(kBlock) k_cls_all(const uint8_t* __restrict__ lab8, uint64_t n, uint8_t* __restrict__ cls) {
-  __shared__ uint8_t s_cl[64];
-  if (threadIdx.x < 64) s_cl[threadIdx.x] = c_pat.cls_of_label[threadIdx.x];
-  __syncthreads();
-  const uint64_t n16 = n / 16;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (uint64_t)gridDim.x * blockDim.x) {
-    const uint4 l = reinterpret_cast<const uint4*>(lab8)[i];
-    const uint32_t in[4] = {l.x, l.y, l.z, l.w};
-    uint32_t out[4];
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      out[g] = 0;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) out[g] |= (uint32_t)s_cl[(in[g] >> (8 * k)) & 63u] << (8 * k);
-    }
-    reinterpret_cast<uint4*>(cls)[i] = make_uint4(out[0], out[1], out[2], out[3]);
-  }
-}
-
-// ---------------------------------------------------------------------------
-// fused per-pattern initialisation + first-superstep signature filter (labels < 64).
-// One streaming pass over all vertices: class from the byte label, candidate test, then — for
-// candidates — the signature test.  In the first superstep every neighbour u of v sends
-// labelmask(label[u]) (ee.hpp:519-561), so heard(v) depends only on WHICH labels occur among v's
-// neighbours: heard(v) = OR { LM(l) : l in sig[v], LM(l) & NB(T_v) != 0 } — exactly what walking the
-// row would compute.  A candidate whose T_state comes out empty leaves (or never enters) the map; it
-// is settled here from 8 bytes of signature instead of its whole row (tables c_pat.req / c_pat.rl).
-// Writes cls[v] and S[v] for EVERY vertex with coalesced stores (S = 0 unless the
-// vertex survives the first superstep's cover test) and appends the survivors to the
-// frontier.  Their rows are walked by the first scan afterwards.
-// ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) k_init_filter(const uint8_t* __restrict__ lab8,
-                                                         const uint32_t* __restrict__ deg,
-                                                         const uint32_t* __restrict__ rowblk,
-                                                         const unsigned long long* __restrict__ sig, uint64_t V,
-                                                         uint8_t* __restrict__ cls, uint16_t* __restrict__ S,
-                                                         uint4* fr_main, uint4* fr_big, DevCounters* cnt, int buf,
-                                                         uint32_t slot_base, int par) {
+                                                        const unsigned long long* __restrict__ sig, uint64_t V,
+                                                        uint8_t* __restrict__ cls, uint32_t* __restrict__ fw,
+                                                        uint32_t* __restrict__ tile_cnt, DevCounters* cnt, int use_sig) {
   __shared__ uint8_t s_cl[64];
   __shared__ uint16_t s_lm[17];
   __shared__ unsigned long long s_rl[17];
-  __shared__ uint32_t s_w[kBlock / 32][2];
-  __shared__ uint32_t s_base[2];
+  __shared__ uint32_t s_w[kBlock / 32];
   if (threadIdx.x < 64) s_cl[threadIdx.x] = c_pat.cls_of_label[threadIdx.x];
   if (threadIdx.x < 17) { s_lm[threadIdx.x] = c_pat.LMc[threadIdx.x]; s_rl[threadIdx.x] = c_pat.rl[threadIdx.x]; }
   __syncthreads();
-  constexpr int VPT = 16;  // vertices per thread: one uint4 of byte labels, four uint4 of degrees
   const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const uint64_t tile = (uint64_t)blockDim.x * VPT;
+  const uint64_t n_tiles = (V + PM_TILE - 1) / PM_TILE;
   unsigned long long ncand = 0;
   bool any_removed = false;
-  for (uint64_t base = (uint64_t)blockIdx.x * tile; base < V; base += (uint64_t)gridDim.x * tile) {
-    const uint64_t v0 = base + (uint64_t)threadIdx.x * VPT;
-    uint32_t k0 = 0, k1 = 0;  // bit j: vertex v0 + j survives the first superstep (main / big list)
-    if (v0 + VPT <= V) {
+  for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint64_t v0 = tile * PM_TILE + (uint64_t)threadIdx.x * 16;
+    uint32_t bits = 0;
+    if (SMALL && v0 + 16 <= V) {
       const uint4 l16 = *reinterpret_cast<const uint4*>(lab8 + v0);
       const uint32_t lw[4] = {l16.x, l16.y, l16.z, l16.w};
-      uint32_t cw[4];
-      uint32_t sw[8];
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const uint4 d4 = *reinterpret_cast<const uint4*>(deg + v0 + 4 * g);
         const uint32_t dd[4] = {d4.x, d4.y, d4.z, d4.w};
-        cw[g] = 0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const int j = 4 * g + k;
           const uint32_t c = s_cl[(lw[g] >> (8 * k)) & 63u];
-          const uint32_t d = dd[k];
-          uint32_t lm = d ? (uint32_t)s_lm[c] : 0u;
+          const uint32_t lm = dd[k] ? (uint32_t)s_lm[c] : 0u;
           if (lm) {
-            const unsigned long long sg = sig[v0 + j];
-            uint32_t surv = 0;
+            const unsigned long long sg = sig[v0 + 4 * g + k];
+            uint32_t surv = use_sig ? 0u : 1u;
             for (uint32_t rest = lm; rest; rest &= rest - 1) {
-              const int pp = __ffs(rest) - 1;
-              const unsigned long long rq = c_pat.req[pp];
+              const unsigned long long rq = c_pat.req[__ffs(rest) - 1];
               if (rq != 0ull && (sg & rq) == rq) surv = 1;
             }
             any_removed = any_removed || (!surv && (sg & s_rl[c]) != 0ull);  // entered the map and left it (ee.hpp:941-946)
             ncand++;
-            if (surv) {
-              if (d <= PM_MID_MAX) k0 |= 1u << j; else k1 |= 1u << j;
-            } else {
-              lm = 0;
-            }
+            bits |= surv << (4 * g + k);
           }
-          cw[g] |= c << (8 * k);
-          if (k & 1) sw[j >> 1] |= lm << 16; else sw[j >> 1] = lm;
         }
       }
-      *reinterpret_cast<uint4*>(cls + v0) = make_uint4(cw[0], cw[1], cw[2], cw[3]);
-      *reinterpret_cast<uint4*>(S + v0) = make_uint4(sw[0], sw[1], sw[2], sw[3]);
-      *reinterpret_cast<uint4*>(S + v0 + 8) = make_uint4(sw[4], sw[5], sw[6], sw[7]);
     } else {
-      for (int j = 0; j < VPT && v0 + j < V; ++j) {  // ragged tail
+      for (int j = 0; j < 16 && v0 + j < V; ++j) {
         const uint64_t v = v0 + j;
-        const uint32_t c = s_cl[lab8[v] & 63];
         const uint32_t d = deg[v];
-        uint32_t lm = d ? (uint32_t)s_lm[c] : 0u;
-        if (lm) {
-          const unsigned long long sg = sig[v];
-          uint32_t surv = 0;
-          for (uint32_t rest = lm; rest; rest &= rest - 1) {
-            const unsigned long long rq = c_pat.req[__ffs(rest) - 1];
-            if (rq != 0ull && (sg & rq) == rq) surv = 1;
+        if (SMALL) {
+          const uint32_t c = s_cl[lab8[v] & 63];
+          const uint32_t lm = d ? (uint32_t)s_lm[c] : 0u;
+          if (lm) {
+            const unsigned long long sg = sig[v];
+            uint32_t surv = use_sig ? 0u : 1u;
+            for (uint32_t rest = lm; rest; rest &= rest - 1) {
+              const unsigned long long rq = c_pat.req[__ffs(rest) - 1];
+              if (rq != 0ull && (sg & rq) == rq) surv = 1;
+            }
+            any_removed = any_removed || (!surv && (sg & s_rl[c]) != 0ull);
+            ncand++;
+            bits |= surv << j;
           }
-          any_removed = any_removed || (!surv && (sg & s_rl[c]) != 0ull);
-          ncand++;
-          if (surv) {
-            if (d <= PM_MID_MAX) k0 |= 1u << j; else k1 |= 1u << j;
-          } else {
-            lm = 0;
-          }
+        } else {
+          const uint64_t lab = label[v];
+          uint32_t c = PM_NOCLASS;
+#pragma unroll
+          for (int q = 0; q < 16; ++q)
+            if (q < c_pat.ncls && c_pat.clabel[q] == lab) c = q;
+          cls[v] = (uint8_t)c;
+          if (c != PM_NOCLASS && d) bits |= 1u << j;
         }
-        cls[v] = (uint8_t)c;
-        S[v] = (uint16_t)lm;
       }
     }
-    // block-aggregated append of the survivors' entries: one atomic per list and tile
-    const uint32_t n0 = __popc(k0), n1 = __popc(k1);
-    uint32_t i0 = n0, i1 = n1;
+    // survivors before this thread's 16 vertices inside the tile
+    const uint32_t n = __popc(bits);
+    uint32_t incl = n;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t t0 = __shfl_up_sync(0xffffffffu, i0, o);
-      const uint32_t t1 = __shfl_up_sync(0xffffffffu, i1, o);
-      if (lane >= (uint32_t)o) { i0 += t0; i1 += t1; }
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= (uint32_t)o) incl += t;
     }
-    if (lane == 31) { s_w[w][0] = i0; s_w[w][1] = i1; }
+    if (lane == 31) s_w[w] = incl;
     __syncthreads();
-    if (threadIdx.x < 2) {
-      uint32_t t = 0;
-      for (uint32_t i = 0; i < blockDim.x / 32; ++i) t += s_w[i][threadIdx.x];
-      s_base[threadIdx.x] = t ? atomicAdd(&cnt->fr_n[buf][threadIdx.x], t) : 0u;
-    }
-    __syncthreads();
-    if (k0 | k1) {
-      uint32_t o0 = s_base[0] + i0 - n0, o1 = s_base[1] + i1 - n1;
-      for (uint32_t i = 0; i < w; ++i) { o0 += s_w[i][0]; o1 += s_w[i][1]; }
-      for (uint32_t rest = k0 | k1; rest; rest &= rest - 1) {
-        const int j = __ffs(rest) - 1;
-        const uint64_t v = v0 + j;
-        const uint4 e = make_uint4((uint32_t)v, rowblk[v], deg[v], (uint32_t)S[v]);
-        if ((k0 >> j) & 1u) fr_main[o0++] = e; else fr_big[o1++] = e;
-      }
-    }
-    if (c_peer.G > 1) {
-      // the peers' replicas of S start from zero: they only need the survivors' masks
-      // (one reservation in the delta inboxes per warp and tile)
-      const uint32_t ks = k0 | k1;
-      const uint32_t ns = __popc(ks);
-      uint32_t incl = ns;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= (uint32_t)o) incl += t;
-      }
-      const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
-      if (tot) {
-        uint32_t pos = 0;
-        if (lane == 31) pos = atomicAdd(&cnt->ndelta, tot);
-        pos = __shfl_sync(0xffffffffu, pos, 31) + incl - ns;
-        for (uint32_t rest = ks; rest; rest &= rest - 1) {
-          const int j = __ffs(rest) - 1;
-          const uint2 d = make_uint2((uint32_t)(v0 + j) + slot_base, (uint32_t)S[v0 + j]);
-          if (pos < c_peer.dcap)
-            for (int g = 0; g < c_peer.G; ++g)
-              if (g != c_peer.rank) c_peer.din[par][g][(uint64_t)c_peer.rank * c_peer.dcap + pos] = d;
-          ++pos;
-        }
-      }
-    }
+    uint32_t before = incl - n;
+    for (uint32_t k = 0; k < w; ++k) before += s_w[k];
+    if (v0 < V) fw[v0 / 16] = (before << 16) | bits;
+    if (threadIdx.x == kBlock - 1) tile_cnt[tile] = before + n;
     __syncthreads();
   }
   if (any_removed) cnt->nf_init = 1u;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) ncand += __shfl_xor_sync(0xffffffffu, ncand, o);
   if (lane == 0 && ncand) atomicAdd(&cnt->filtered_init, ncand);
+}
+
+// exclusive prefix of the tile counts (in place) with one block; publishes the number of survivors
+__global__ void __launch_bounds__(1024) k_init_scan(uint32_t* __restrict__ tile_cnt, uint64_t n_tiles, DevCounters* cnt, int buf) {
+  __shared__ uint32_t s_w[32];
+  __shared__ uint32_t s_carry;
+  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (uint64_t base = 0; base < n_tiles; base += blockDim.x) {
+    const uint64_t i = base + threadIdx.x;
+    const uint32_t x = i < n_tiles ? tile_cnt[i] : 0u;
+    uint32_t incl = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= (uint32_t)o) incl += t;
+    }
+    if (lane == 31) s_w[w] = incl;
+    __syncthreads();
+    uint32_t wbase = 0;
+    for (uint32_t k = 0; k < w; ++k) wbase += s_w[k];
+    const uint32_t carry = s_carry;
+    if (i < n_tiles) tile_cnt[i] = carry + wbase + incl - x;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) s_carry = carry + wbase + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    cnt->n_c = s_carry;
+    cnt->fr_n[buf][0] = s_carry;  // the main list holds one entry per survivor, in cid order
+  }
+}
+
+// several GPUs: tb of every rank's tiles = that rank's first cid + its local tile prefix
+__global__ void k_tile_offsets(uint32_t* __restrict__ tb, uint32_t tiles_per_rank) {
+  const uint32_t n = tiles_per_rank * (uint32_t)c_peer.G;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) tb[i] += c_peer.off[i / tiles_per_rank];
+}
+
+// compact id of slot u if it survived the filter, else PM_SENTINEL
+__device__ __forceinline__ uint32_t cid_of_slot(const uint32_t* __restrict__ fw, const uint32_t* __restrict__ tb, uint32_t u) {
+  const uint32_t w = fw[u >> 4];
+  const uint32_t b = u & 15u;
+  if (!((w >> b) & 1u)) return PM_SENTINEL;
+  return tb[u >> 12] + (w >> 16) + __popc(w & ((1u << b) - 1u));
+}
+
+// n_slots: every slot of every rank (replicated per-cid state); [own_lo, own_hi): this rank's slots, which also
+// get their row start and frontier entry.  deg / rowblk are indexed by slot - own_lo.
+template <bool SMALL>
+__global__ void __launch_bounds__(kBlock) k_init_assign(const uint8_t* __restrict__ lab8, const uint8_t* __restrict__ cls,
+                                                         const uint32_t* __restrict__ deg, const uint32_t* __restrict__ rowblk,
+                                                         const uint32_t* __restrict__ fw, const uint32_t* __restrict__ tb,
+                                                         uint64_t n_slots, uint32_t own_lo, uint32_t own_hi,
+                                                         uint16_t* __restrict__ S, uint8_t* __restrict__ clsc,
+                                                         uint32_t* __restrict__ vid, uint32_t* __restrict__ rowc,
+                                                         uint4* fr_main, uint4* fr_big, DevCounters* cnt, int buf) {
+  __shared__ uint8_t s_cl[64];
+  __shared__ uint16_t s_lm[17];
+  if (threadIdx.x < 64) s_cl[threadIdx.x] = c_pat.cls_of_label[threadIdx.x];
+  if (threadIdx.x < 17) s_lm[threadIdx.x] = c_pat.LMc[threadIdx.x];
+  __syncthreads();
+  const uint32_t off_me = c_peer.off[c_peer.rank];
+  const uint64_t n_words = (n_slots + 15) / 16;
+  for (uint64_t wi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; wi < n_words; wi += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t w = fw[wi];
+    uint32_t bits = w & 0xFFFFu;
+    if (!bits) continue;
+    uint32_t cid = tb[wi >> 8] + (w >> 16);
+    for (; bits; bits &= bits - 1, ++cid) {
+      const uint32_t slot = (uint32_t)(wi * 16) + (__ffs(bits) - 1);
+      const uint32_t c = SMALL ? (uint32_t)s_cl[lab8[slot] & 63] : (uint32_t)cls[slot];
+      const uint32_t lm = s_lm[c];
+      vid[cid] = slot;
+      S[cid] = (uint16_t)lm;
+      clsc[cid] = (uint8_t)c;
+      if (slot >= own_lo && slot < own_hi) {
+        const uint32_t lcid = cid - off_me, d = deg[slot - own_lo], rb = rowblk[slot - own_lo];
+        rowc[lcid] = rb;
+        if (d <= PM_MID_MAX) {
+          fr_main[lcid] = make_uint4(cid, rb, d, lm);
+        } else {
+          fr_main[lcid] = make_uint4(cid, PM_TOMB, 0u, 0u);
+          fr_big[atomicAdd(&cnt->fr_n[buf][1], 1u)] = make_uint4(cid, rb, d, lm);
+        }
+      }
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -394,9 +387,14 @@ __global__ void __launch_bounds__(kBlock) k_init_filter(const uint8_t* __restric
 //   labels < 64): the first superstep then needs no gather at all, and later
 //   compactions keep labw aligned with colw for NLCC.
 // ---------------------------------------------------------------------------
-template <bool FIRST, bool STREAM>
+//   XLATE (with !FIRST) = the first scan after the first superstep: the rows still hold SLOTS (the first scan
+//   copies them as they are, so that its latency-bound row walks carry no extra dependent loads); this scan
+//   renames every neighbour to its compact id while it walks the — by now short — rows, dropping neighbours
+//   that did not survive the filter (their masks are zero: they would be dropped here anyway).
+//   xlate_only: rename and nothing else (a pattern whose LCC call has a single superstep).
+template <bool FIRST, bool STREAM, bool XLATE>
 __global__ void __launch_bounds__(kBlock, 4) k_lcc_scan(LccArgs a, uint4* __restrict__ list,
-                                                      const uint32_t* __restrict__ n_ptr) {
+                                                      const uint32_t* __restrict__ n_ptr, int xlate_only) {
   __shared__ uint16_t s_lm[17];
   __shared__ uint16_t s_lml[64];  // label value -> labelmask
   if (threadIdx.x < 17) s_lm[threadIdx.x] = c_pat.LMc[threadIdx.x];
@@ -415,9 +413,11 @@ __global__ void __launch_bounds__(kBlock, 4) k_lcc_scan(LccArgs a, uint4* __rest
     const bool has = idx < n;
     uint4 e = make_uint4(0, 0, 0, 0);
     uint32_t Tv = 0;
+    bool live = false;
     if (has) {
       e = list[idx];
-      Tv = a.S[e.x + a.base];
+      live = e.y != PM_TOMB;
+      if (live) Tv = a.S[e.x];
     }
     uint32_t d = Tv ? e.z : 0u;  // Tv == 0: deactivated by NLCC since the last commit (beta.cpp:990-992)
     const uint32_t NBv = nb_of(Tv);
@@ -438,6 +438,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_lcc_scan(LccArgs a, uint4* __rest
         }
       }
       uint32_t m[PM_TINY_MAX];
+      uint32_t xl[XLATE ? PM_TINY_MAX : 1];  // XLATE: the neighbours' compact ids
 #pragma unroll
       for (int c = 0; c < PM_TINY_MAX / 4; ++c) {
         const uint32_t u[4] = {q[c].x, q[c].y, q[c].z, q[c].w};
@@ -446,9 +447,13 @@ __global__ void __launch_bounds__(kBlock, 4) k_lcc_scan(LccArgs a, uint4* __rest
           const int j = 4 * c + k;
           m[j] = 0;
           if ((uint32_t)j < d) {
-            const uint32_t uu = u[k] & PM_IDMASK;
+            uint32_t uu = u[k] & PM_IDMASK;
+            if (XLATE) {
+              uu = cid_of_slot(a.fw, a.tb, uu);
+              xl[j] = uu;
+            }
             if (FIRST) m[j] = STREAM ? (uint32_t)s_lml[(l4[c] >> (8 * k)) & 63u] : (uint32_t)s_lm[a.cls[uu]];
-            else m[j] = (uint32_t)a.S[uu];
+            else if (!XLATE || uu != PM_SENTINEL) m[j] = xlate_only ? 0xFFFFu : (uint32_t)a.S[uu];
           }
         }
       }
@@ -461,15 +466,15 @@ __global__ void __launch_bounds__(kBlock, 4) k_lcc_scan(LccArgs a, uint4* __rest
         for (int k = 0; k < 4; ++k) {
           const int j = 4 * c + k;
           const bool act = (uint32_t)j < d;
-          const bool valid = (m[j] & NBv) != 0u;
-          const bool pre = !FIRST && act && (u[k] >> 31);
+          const bool valid = xlate_only ? m[j] != 0u : (m[j] & NBv) != 0u;
+          const bool pre = !FIRST && !XLATE && act && (u[k] >> 31);
           if (valid) heard |= m[j];
           if (valid || pre) keepm |= 1u << j;
           if (pre) flagged = 1;
         }
       }
       out = __popc(keepm);
-      if (FIRST || out != d || flagged) {
+      if (FIRST || XLATE || out != d || flagged) {
         uint32_t pos = 0;
 #pragma unroll
         for (int c = 0; c < PM_TINY_MAX / 4; ++c) {
@@ -478,7 +483,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_lcc_scan(LccArgs a, uint4* __rest
           for (int k = 0; k < 4; ++k) {
             const int j = 4 * c + k;
             if ((keepm >> j) & 1u) {
-              a.colw[row + pos] = u[k] & PM_IDMASK;
+              a.colw[row + pos] = XLATE ? xl[j] : (u[k] & PM_IDMASK);
               if (STREAM) a.labw[row + pos] = (uint8_t)(l4[c] >> (8 * k));
               ++pos;
             }
@@ -533,24 +538,29 @@ __global__ void __launch_bounds__(kBlock, 4) k_lcc_scan(LccArgs a, uint4* __rest
         }
         const uint32_t u[4] = {q.x, q.y, q.z, q.w};
         uint32_t m[4];
+        uint32_t wr[4];  // what is stored back: the id as it stands, or (XLATE) the neighbour's compact id
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           m[k] = 0;
+          wr[k] = u[k] & PM_IDMASK;
           if (j0 + k < rd) {
-            const uint32_t uu = u[k] & PM_IDMASK;
-            if (FIRST) m[k] = STREAM ? (uint32_t)s_lml[(l4 >> (8 * k)) & 63u] : (uint32_t)s_lm[a.cls[uu]];
-            else m[k] = (uint32_t)a.S[uu];
+            if (XLATE) wr[k] = cid_of_slot(a.fw, a.tb, wr[k]);
+            if (FIRST) m[k] = STREAM ? (uint32_t)s_lml[(l4 >> (8 * k)) & 63u] : (uint32_t)s_lm[a.cls[wr[k]]];
+            else if (!XLATE || wr[k] != PM_SENTINEL) m[k] = xlate_only ? 0xFFFFu : (uint32_t)a.S[wr[k]];
           }
         }
         bool keep[4];
-        uint32_t below = 0, cnt_pass = 0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const bool act = j0 + k < rd;
-          const bool valid = (m[k] & rNB) != 0u;
-          const bool pre = !FIRST && act && (u[k] >> 31);
+          const bool valid = xlate_only ? m[k] != 0u : (m[k] & rNB) != 0u;
+          const bool pre = !FIRST && !XLATE && act && (u[k] >> 31);
           keep[k] = valid || pre;
           if (valid) rheard |= m[k];
+        }
+        uint32_t below = 0, cnt_pass = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
           const uint32_t b = __ballot_sync(0xffffffffu, keep[k]);
           below += __popc(b & lt);
           cnt_pass += __popc(b);
@@ -561,7 +571,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_lcc_scan(LccArgs a, uint4* __rest
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           if (keep[k]) {
-            a.colw[rrow + pos] = u[k] & PM_IDMASK;
+            a.colw[rrow + pos] = wr[k];
             if (STREAM) a.labw[rrow + pos] = (uint8_t)(l4 >> (8 * k));
             ++pos;
           }
@@ -574,9 +584,10 @@ __global__ void __launch_bounds__(kBlock, 4) k_lcc_scan(LccArgs a, uint4* __rest
       if ((int)lane == sl) { heard = rheard; out = rout; }
     }
 
-    if (has) {
+    if (has && live) {
       const uint32_t T0 = FIRST ? Tv : e.w;
-      const uint32_t ts = Tv ? cover_of(T0, heard) : 0u;
+      uint32_t ts = Tv ? cover_of(T0, heard) : 0u;
+      if (xlate_only) ts = Tv ? e.w : 0u;  // renaming only: T_state stays as it is
       // a vertex leaves the vertex_state_map (ee.hpp:941-946, :968-970).  In the first
       // superstep only vertices that heard a valid neighbour ever entered the map (:841-852).
       if (ts == 0 && (FIRST ? heard != 0u : Tv != 0u)) a.cnt->nf = 1u;
@@ -600,9 +611,9 @@ __global__ void __launch_bounds__(kBlock, 4) k_lcc_scan(LccArgs a, uint4* __rest
 }
 
 // one CTA per high-degree vertex ("delegates across warps and CTAs")
-template <bool FIRST, bool STREAM>
+template <bool FIRST, bool STREAM, bool XLATE>
 __global__ void __launch_bounds__(1024) k_lcc_scan_big(LccArgs a, uint4* __restrict__ list,
-                                                        const uint32_t* __restrict__ n_ptr) {
+                                                        const uint32_t* __restrict__ n_ptr, int xlate_only) {
   __shared__ uint16_t s_lm[17];
   __shared__ uint16_t s_lml[64];
   if (threadIdx.x < 64) s_lml[threadIdx.x] = c_pat.LMc[c_pat.cls_of_label[threadIdx.x]];
@@ -615,7 +626,7 @@ __global__ void __launch_bounds__(1024) k_lcc_scan_big(LccArgs a, uint4* __restr
   for (uint32_t idx = blockIdx.x; idx < n; idx += gridDim.x) {
     __syncthreads();
     const uint4 e = list[idx];
-    const uint32_t Tv = a.S[e.x + a.base];
+    const uint32_t Tv = a.S[e.x];
     const uint32_t d = Tv ? e.z : 0u;
     const uint32_t NBv = nb_of(Tv);
     const uint64_t row = (uint64_t)e.y * 8;
@@ -633,25 +644,30 @@ __global__ void __launch_bounds__(1024) k_lcc_scan_big(LccArgs a, uint4* __restr
       }
       uint32_t u[4] = {q.x, q.y, q.z, q.w};
       uint32_t m[4];
+      uint32_t wr[4];  // what is stored back: the id as it stands, or (XLATE) the neighbour's compact id
       bool keep[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const bool act = j0 + k < d;
-        const uint32_t uu = u[k] & PM_IDMASK;
         m[k] = 0;
+        wr[k] = u[k] & PM_IDMASK;
         if (act) {
-          if (FIRST) m[k] = STREAM ? (uint32_t)s_lml[(l4 >> (8 * k)) & 63u] : (uint32_t)s_lm[a.cls[uu]];
-          else m[k] = (uint32_t)a.S[uu];
+          if (XLATE) wr[k] = cid_of_slot(a.fw, a.tb, wr[k]);
+          if (FIRST) m[k] = STREAM ? (uint32_t)s_lml[(l4 >> (8 * k)) & 63u] : (uint32_t)s_lm[a.cls[wr[k]]];
+          else if (!XLATE || wr[k] != PM_SENTINEL) m[k] = xlate_only ? 0xFFFFu : (uint32_t)a.S[wr[k]];
         }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const bool act = j0 + k < d;
+        const bool valid = xlate_only ? m[k] != 0u : (m[k] & NBv) != 0u;
+        const bool pre = !FIRST && !XLATE && act && (u[k] >> 31);
+        keep[k] = valid || pre;
+        if (valid) heard |= m[k];
       }
       uint32_t below = 0, wtotal = 0;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const bool act = j0 + k < d;
-        const bool valid = (m[k] & NBv) != 0u;
-        const bool pre = !FIRST && act && (u[k] >> 31);
-        keep[k] = valid || pre;
-        if (valid) heard |= m[k];
         const uint32_t b = __ballot_sync(0xffffffffu, keep[k]);
         below += __popc(b & lt);
         wtotal += __popc(b);
@@ -668,7 +684,7 @@ __global__ void __launch_bounds__(1024) k_lcc_scan_big(LccArgs a, uint4* __restr
 #pragma unroll
       for (int k = 0; k < 4; ++k)
         if (keep[k]) {
-          a.colw[row + pos] = u[k] & PM_IDMASK;
+          a.colw[row + pos] = wr[k];
           if (STREAM) a.labw[row + pos] = (uint8_t)(l4 >> (8 * k));
           ++pos;
         }
@@ -683,7 +699,8 @@ __global__ void __launch_bounds__(1024) k_lcc_scan_big(LccArgs a, uint4* __restr
       uint32_t h = 0;
       for (uint32_t w = 0; w < nw; ++w) h |= s_heard[w];
       const uint32_t T0 = FIRST ? Tv : e.w;
-      const uint32_t ts = Tv ? cover_of(T0, h) : 0u;
+      uint32_t ts = Tv ? cover_of(T0, h) : 0u;
+      if (xlate_only) ts = Tv ? e.w : 0u;  // renaming only: T_state stays as it is
       if (ts == 0 && (FIRST ? h != 0u : Tv != 0u)) a.cnt->nf = 1u;
       uint4 e2 = e;
       e2.z = outp;
@@ -725,16 +742,18 @@ __global__ void __launch_bounds__(kBlock) k_lcc_commit(LccArgs a, const uint4* _
       uint32_t cslot = 0, cmask = 0;
       if (i < total) {
         const uint4 e = i < c0 ? l0[i] : l1[i - c0];
-        const uint32_t ts = e.w, d = e.z;
-        cslot = e.x + a.base;
-        cmask = ts;
-        if (c_peer.G > 1) changed = ts != a.S[cslot];  // peers only need the changes
-        a.S[cslot] = (uint16_t)ts;
-        a.adeg[e.x] = d;
-        alive[k] = ts != 0;
-        if (alive[k]) { nv++; ne += d; }
-        bin[k] = bin_of(d);
-        val[k] = e;
+        if (e.y != PM_TOMB) {
+          const uint32_t ts = e.w, d = e.z;
+          cslot = e.x;
+          cmask = ts;
+          if (c_peer.G > 1) changed = ts != a.S[cslot];  // peers only need the changes
+          a.S[cslot] = (uint16_t)ts;
+          a.adeg[e.x - a.base] = d;
+          alive[k] = ts != 0;
+          if (alive[k]) { nv++; ne += d; }
+          bin[k] = bin_of(d);
+          val[k] = e;
+        }
       }
       if (c_peer.G > 1) publish_mask(changed, cslot, cmask, a.cnt, a.par);
     }
@@ -762,7 +781,7 @@ __global__ void __launch_bounds__(kBlock) k_count_alive(LccArgs a, const uint4* 
   unsigned long long nv = 0, ne = 0;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const uint4 e = i < c0 ? l0[i] : l1[i - c0];
-    if (a.S[e.x + a.base]) { nv++; ne += e.z; }
+    if (e.y != PM_TOMB && a.S[e.x]) { nv++; ne += e.z; }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {

@@ -40,6 +40,7 @@ __constant__ NlcConst c_nlc;
 
 #define PM_HSET_EMPTY 0xFFFFFFFFFFFFFFFFull
 
+// every vertex below is named by its COMPACT ID (see pm_lcc.cuh); `rowblk` is the row start by local compact id
 struct NlcArgs {
   const uint32_t* rowblk;
   uint32_t* colw;
@@ -56,7 +57,8 @@ struct NlcArgs {
   uint2* matches;      // TDS: (token index at the penultimate level, final vertex)
   uint64_t match_cap;
   DevCounters* cnt;
-  uint32_t base;       // first slot of this rank (rank-local arrays: index slot - base)
+  uint32_t base;       // first compact id of this rank (rank-local arrays rowblk / adeg: index cid - base)
+  const uint32_t* vid; // compact id -> slot
   int par;             // multi-GPU: token inbox written in this hop (the previous hop's is par ^ 1)
   const StepMsg* all;  // multi-GPU: everyone's StepMsg of the previous hop
 };
@@ -173,8 +175,9 @@ __global__ void __launch_bounds__(kBlock) k_nlcc_sources(NlcArgs a, const uint4*
     bool is_src = false;
     uint32_t v = 0;
     if (i < total) {
-      v = (i < c0 ? l0[i].x : l1[i - c0].x) + a.base;  // slot
-      const uint32_t T = a.S[v];
+      const uint4 e = i < c0 ? l0[i] : l1[i - c0];
+      v = e.x;  // compact id
+      const uint32_t T = e.y != PM_TOMB ? (uint32_t)a.S[v] : 0u;
       is_src = T != 0 && hop_ok(T, a.cls[v], 0);
       // path checking starts only from vertices that match BOTH end points (nem_1.hpp:447-451)
       if (is_src && !tds && !c_nlc.valid_cycle) is_src = (T >> c_nlc.I[c_nlc.n - 1]) & 1u;
@@ -535,17 +538,18 @@ __global__ void __launch_bounds__(kBlock) k_tds_expand(NlcArgs a, int hlevel, in
 
 // rows_out[i * width + j] = j-th vertex of completed walk i (subgraph file rows, tds_batch_1.hpp:685-689)
 __global__ void k_tds_materialize(const uint2* __restrict__ pool, const uint2* __restrict__ matches,
-                                  uint64_t n, int width, uint32_t* __restrict__ rows_out) {
+                                  uint64_t n, int width, const uint32_t* __restrict__ vid,
+                                  uint32_t* __restrict__ rows_out) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
     const uint2 mt = matches[i];
     uint32_t* r = rows_out + i * width;
-    r[width - 1] = mt.y;
+    r[width - 1] = vid[mt.y];
     uint32_t t = mt.x;
     for (int j = width - 2; j >= 0; --j) {
       const uint2 tk = pool[t];
-      r[j] = tk.y;
+      r[j] = vid[tk.y];
       t = tk.x;
     }
   }

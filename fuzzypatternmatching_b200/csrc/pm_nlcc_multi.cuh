@@ -47,13 +47,13 @@ __device__ __forceinline__ unsigned long long tok_locate(const TokSrc& ts, unsig
 __device__ __forceinline__ void ack_source(const NlcArgs& a, uint32_t s) {
   if (a.ok[s]) return;  // own source, or already acknowledged from this GPU
   a.ok[s] = 1;
-  const uint32_t o = s / c_peer.nlmax;
+  const uint32_t o = cid_owner(s);
   if ((int)o != c_peer.rank) c_peer.ok[o][s] = 1;
 }
 
 // flag E_s[parent] at the owner of s (nem_1.hpp:764-770)
 __device__ __forceinline__ void mark_edge_m(uint32_t s, uint32_t parent) {
-  const uint32_t o = s / c_peer.nlmax, li = s - o * c_peer.nlmax;
+  const uint32_t o = cid_owner(s), li = s - c_peer.off[o];
   const uint64_t row = (uint64_t)c_peer.rowblk[o][li] * 8;
   const uint32_t d = c_peer.adeg[o][li];
   uint32_t* __restrict__ cw = c_peer.colw[o];
@@ -73,7 +73,7 @@ __device__ __forceinline__ void route_tokens(const NlcArgs& a, const bool (&flag
   const uint32_t lt = (1u << lane) - 1u;
   uint32_t dest[4];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) dest[k] = flag[k] ? u[k] / c_peer.nlmax : 0xFFFFFFFFu;
+  for (int k = 0; k < 4; ++k) dest[k] = flag[k] ? cid_owner(u[k]) : 0xFFFFFFFFu;
   for (int g = 0; g < c_peer.G; ++g) {
     uint32_t m[4], total = 0;
 #pragma unroll
@@ -127,9 +127,10 @@ __global__ void __launch_bounds__(kBlock) k_close_keys_m(NlcArgs a, const uint4*
     uint32_t s = 0, d = 0;
     uint64_t row = 0;
     if (i < total) {
-      const uint32_t li = i < c0 ? l0[i].x : l1[i - c0].x;
-      s = li + a.base;
-      const uint32_t T = a.S[s];
+      const uint4 e = i < c0 ? l0[i] : l1[i - c0];
+      s = e.x;  // compact id
+      const uint32_t li = s - a.base;
+      const uint32_t T = e.y != PM_TOMB ? (uint32_t)a.S[s] : 0u;
       // a source of the constraint that can also receive the closing hop (nem_1.hpp:428-451, 557-581)
       if (T != 0 && hop_ok(T, a.cls[s], 0) && hop_ok(T, a.cls[s], hn + 1)) {
         d = a.adeg[li];
@@ -399,7 +400,7 @@ __global__ void __launch_bounds__(kBlock) k_tds_hop_m(NlcArgs a, int hn) {
         }
         // records are rare compared with nem_1 tokens: one reservation per record
         if (acc) {
-          const uint32_t g = u[k] / c_peer.nlmax;
+          const uint32_t g = cid_owner(u[k]);
           const unsigned long long pos = atomicAdd(&a.cnt->out_n[g], 1ull);
           if (pos < rcap) {
             uint32_t* out = reinterpret_cast<uint32_t*>(c_peer.tin[a.par][g]) +
@@ -441,7 +442,7 @@ __global__ void k_tds_collect_m(NlcArgs a, int n, uint32_t* __restrict__ rows_ou
     for (int q = 0; q < PM_MAX_RANKS - 1; ++q)
       if (r == q && tt >= src.n[q]) { tt -= src.n[q]; r = q + 1; }
     const uint32_t* rec = in + (unsigned long long)r * c_peer.tcap * 2ull + tt * (unsigned long long)n;
-    for (int i = 0; i < n; ++i) rows_out[t * n + i] = rec[i];
+    for (int i = 0; i < n; ++i) rows_out[t * n + i] = a.vid[rec[i]];
   }
 }
 

@@ -41,18 +41,20 @@ LccArgs lcc_args(pm_ctx* c, int row) {
   a.S = c->S; a.adeg = c->adeg; a.cls = c->cls; a.cnt = c->cnt;
   a.lab0 = c->lab0; a.labw = c->labw;
   a.row = c->rowstat + row;
-  a.base = (uint32_t)(c->nlmax * c->rank);
+  a.base = c->cid_off[c->rank];
   a.par = c->step_parity;
+  a.fw = c->fw; a.tb = c->tb;
   return a;
 }
 
 NlcArgs nlc_args(pm_ctx* c, uint2* matches, uint64_t match_cap) {
   NlcArgs a;
-  a.rowblk = c->rowblk; a.colw = c->colw; a.S = c->S; a.adeg = c->adeg; a.cls = c->cls; a.labw = c->labw;
+  a.rowblk = c->rowc; a.colw = c->colw; a.S = c->S; a.adeg = c->adeg; a.cls = c->clsc; a.labw = c->labw;
   a.ok = c->ok; a.src_list = c->src_list; a.hset = c->hset; a.hset_mask = c->hset_use - 1;
   a.pool = c->pool; a.pool_cap = c->pool_cap; a.matches = matches; a.match_cap = match_cap;
   a.cnt = c->cnt;
-  a.base = (uint32_t)(c->nlmax * c->rank);
+  a.base = c->cid_off[c->rank];
+  a.vid = c->vid;
   a.par = c->step_parity;
   a.all = c->step_msg ? c->step_msg + 1 : nullptr;
   return a;
@@ -70,6 +72,7 @@ int comm_publish(pm_ctx* c) {
   std::memset(&t, 0, sizeof(t));
   t.G = c->n_ranks; t.rank = c->rank; t.nlmax = (uint32_t)c->nlmax; t.base = (uint32_t)(c->nlmax * c->rank);
   t.dcap = (uint32_t)c->dcap; t.tcap = c->tcap;
+  for (int g = 0; g <= PM_MAX_RANKS; ++g) t.off[g] = c->cid_off[g];
   void* out[PM_MAX_RANKS];
   int rc;
 #define PM_SHARE(buf, field, T)                                              \
@@ -77,7 +80,7 @@ int comm_publish(pm_ctx* c) {
     if ((rc = comm_share(c, (void*)(buf), out))) return rc;                  \
     for (int g = 0; g < c->n_ranks; ++g) t.field[g] = (T)out[g];             \
   }
-  PM_SHARE(c->rowblk, rowblk, const uint32_t*)
+  PM_SHARE(c->rowc, rowblk, const uint32_t*)
   PM_SHARE(c->adeg, adeg, const uint32_t*)
   PM_SHARE(c->colw, colw, uint32_t*)
   PM_SHARE(c->ok, ok, uint8_t*)
@@ -98,6 +101,7 @@ void state_free(pm_ctx* c) {
   c->h_step = nullptr;
   c->dcap = c->tcap = 0;
   dev_free(c->S); dev_free(c->adeg); dev_free(c->cls);
+  dev_free(c->rowc); dev_free(c->vid); dev_free(c->clsc); dev_free(c->fw); dev_free(c->tb);
   for (int b = 0; b < 2; ++b) for (int k = 0; k < 2; ++k) dev_free(c->fr[b][k]);
   dev_free(c->cnt); dev_free(c->rowstat); dev_free(c->ok); dev_free(c->src_list);
   dev_free(c->hset); dev_free(c->pool);
@@ -458,6 +462,11 @@ int pm_state_reset(pm_ctx* c) {
   if (!c->S) {
     if ((rc = dev_alloc(c, &c->S, Vs))) return rc;
     if ((rc = dev_alloc(c, &c->adeg, NL))) return rc;
+    if ((rc = dev_alloc(c, &c->rowc, NL))) return rc;
+    if ((rc = dev_alloc(c, &c->vid, Vs))) return rc;
+    if ((rc = dev_alloc(c, &c->clsc, Vs))) return rc;
+    if ((rc = dev_alloc(c, &c->fw, Vs / 16 + 2))) return rc;
+    if ((rc = dev_alloc(c, &c->tb, Vs / PM_TILE + 2))) return rc;
     if ((rc = dev_alloc(c, &c->cls, Vs))) return rc;
     if ((rc = dev_alloc(c, &c->ok, Vs))) return rc;
     if ((rc = dev_alloc(c, &c->src_list, NL))) return rc;
@@ -508,35 +517,57 @@ int pm_state_reset(pm_ctx* c) {
   c->cur = 0;
   c->filter_done = false;
   PM_CUDA(c, cudaEventRecord(c->kev[3][0], c->stream));
-  if (c->labels_small) {
-    if (multi) {
-      // peers' parts of the replicas: classes follow from the replicated labels, masks start at zero and
-      // receive the survivors of the first superstep as deltas (a few % of the vertices) — no bulk all-gather
-      PM_CUDA(c, cudaMemsetAsync(c->S, 0, Vs * sizeof(uint16_t), c->stream));
-      k_cls_all<<<grid_for(), kBlock, 0, c->stream>>>(c->lab8, Vs, c->cls);
-      PM_LAUNCH_CHECK(c);
-    }
-    // init and the signature filter of the first superstep in one streaming pass over the local rows
-    k_init_filter<<<grid_for(), kBlock, 0, c->stream>>>(c->lab8 + base, c->deg, c->rowblk, c->sig, NL, c->cls + base,
-                                                        c->S + base, c->fr[0][0], c->fr[0][1], c->cnt, 0, (uint32_t)base, c->step_parity);
-    c->filter_done = true;
+  {
+    const bool small = c->labels_small;
+    const uint64_t tpr = (NL + PM_TILE - 1) / PM_TILE;  // tiles per rank (several ranks: NL is a multiple of the tile)
+    const int grid = grid_for();
+    uint32_t* fw_me = c->fw + base / 16;
+    uint32_t* tb_me = c->tb + (uint64_t)c->rank * tpr;
+    // pass 1: survivor bits + in-tile prefixes of the local vertices (labels < 64: candidates that pass the
+    // signature filter of the first superstep; else every label-matching vertex), survivors per tile
+    // a single superstep per LCC call: no second scan could drop the neighbours the filter removed, so
+    // the filter stays off and every label-matching vertex gets a compact id
+    const bool use_sig = small && c->pat.diameter >= 2;
+    if (small)
+      k_init_flags<true><<<grid, kBlock, 0, c->stream>>>(c->lab8 + base, nullptr, c->deg, c->sig, NL, nullptr, fw_me, tb_me, c->cnt, use_sig ? 1 : 0);
+    else
+      k_init_flags<false><<<grid, kBlock, 0, c->stream>>>(nullptr, c->label, c->deg, nullptr, NL, c->cls + base, fw_me, tb_me, c->cnt, 0);
     PM_LAUNCH_CHECK(c);
+    c->filter_done = use_sig;
+    // pass 2: tile prefix, number of survivors
+    k_init_scan<<<1, 1024, 0, c->stream>>>(tb_me, tpr, c->cnt, 0);
+    PM_LAUNCH_CHECK(c);
+    // the compact id ranges of the ranks; every rank needs every rank's slot -> cid tables
+    for (int g = 0; g <= PM_MAX_RANKS; ++g) c->cid_off[g] = 0;
     if (multi) {
+      if (!small && (rc = comm_allgather_slots(c, c->cls))) return rc;  // classes of foreign neighbours (first scan)
+      if ((rc = comm_allgather_seg(c, c->fw, c->nlmax / 16))) return rc;
+      if ((rc = comm_allgather_seg(c, c->tb, tpr))) return rc;
       if ((rc = comm_step(c))) return rc;
-      k_apply_deltas<<<grid_for(), kBlock, 0, c->stream>>>(c->S, c->step_msg + 1, c->step_parity);
-      PM_LAUNCH_CHECK(c);
+      if ((rc = comm_step_fetch(c))) return rc;
       c->step_parity ^= 1;
+      for (int g = 0; g < c->n_ranks; ++g) c->cid_off[g + 1] = c->cid_off[g] + c->h_step[g].n_c;
+    } else {
+      if ((rc = sync_counters(c))) return rc;
+      c->cid_off[1] = c->h_cnt->n_c;
     }
-  } else {
-    if (multi) PM_CUDA(c, cudaMemsetAsync(c->S, 0, Vs * sizeof(uint16_t), c->stream));
-    k_init_state<<<grid_for(), kBlock, 0, c->stream>>>(c->label, c->deg, c->rowblk, NL, c->cls + base, c->S + base,
-                                                       c->fr[0][0], c->fr[0][1], c->cnt, 0);
-    PM_LAUNCH_CHECK(c);
+    for (int g = c->n_ranks + 1; g <= PM_MAX_RANKS; ++g) c->cid_off[g] = c->cid_off[c->n_ranks];
+    for (int g = 0; g <= PM_MAX_RANKS; ++g) c->peers.off[g] = c->cid_off[g];
+    if ((rc = comm_upload_peers(c))) return rc;
     if (multi) {
-      // every rank needs the class and the first mask of every vertex (they are gathered from neighbours)
-      if ((rc = comm_allgather_slots(c, c->cls))) return rc;
-      if ((rc = comm_allgather_slots(c, c->S))) return rc;
+      k_tile_offsets<<<grid, kBlock, 0, c->stream>>>(c->tb, (uint32_t)tpr);
+      PM_LAUNCH_CHECK(c);
     }
+    // pass 3: per-cid state of every survivor (all ranks), row starts and frontier entries of the local ones
+    if (small)
+      k_init_assign<true><<<grid, kBlock, 0, c->stream>>>(c->lab8, nullptr, c->deg, c->rowblk, c->fw, c->tb, multi ? Vs : NL,
+                                                          (uint32_t)base, (uint32_t)(base + NL), c->S, c->clsc, c->vid, c->rowc,
+                                                          c->fr[0][0], c->fr[0][1], c->cnt, 0);
+    else
+      k_init_assign<false><<<grid, kBlock, 0, c->stream>>>(nullptr, c->cls, c->deg, c->rowblk, c->fw, c->tb, multi ? Vs : NL,
+                                                           (uint32_t)base, (uint32_t)(base + NL), c->S, c->clsc, c->vid, c->rowc,
+                                                           c->fr[0][0], c->fr[0][1], c->cnt, 0);
+    PM_LAUNCH_CHECK(c);
   }
   PM_CUDA(c, cudaEventRecord(c->kev[3][1], c->stream));
   {
@@ -547,6 +578,7 @@ int pm_state_reset(pm_ctx* c) {
     c->init_candidates = c->h_cnt->filtered_init;
     if (c->filter_done) PM_CUDA(c, cudaEventElapsedTime(&c->init_ms, c->kev[3][0], c->kev[3][1]));
   }
+  c->fuzzy_ids = false;
   c->rows.clear();
   c->step_rows.clear();
   c->iter_seconds.clear();
@@ -571,6 +603,7 @@ int pm_lcc(pm_ctx* c, int init_step, int* not_finished, pm_counts_t* counts_out)
   PM_CUDA(c, cudaMemsetAsync(&c->cnt->nf, 0, sizeof(uint32_t), st));
   for (int k = 0; k < D; ++k) {  // fixed superstep count (ee.hpp:1069)
     const bool first = init_step && k == 0;
+    const bool xlate = init_step && k == 1;  // rows still hold slots: this scan renames them to compact ids
     PM_CUDA(c, cudaEventRecord(c->events[k], st));
     PM_CUDA(c, cudaMemsetAsync(&c->cnt->fr_n[c->cur ^ 1][0], 0, 4 * sizeof(uint32_t), st));
     LccArgs a = lcc_args(c, k);
@@ -581,14 +614,16 @@ int pm_lcc(pm_ctx* c, int init_step, int* not_finished, pm_counts_t* counts_out)
     cudaEvent_t* ev = &c->kev2[(size_t)k * 4];
     PM_CUDA(c, cudaEventRecord(ev[0], st));
     if (c->bin_live[0]) {
-      if (first) (sm ? k_lcc_scan<true, true> : k_lcc_scan<true, false>)<<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], &c->cnt->fr_n[cur][0]);
-      else (sm ? k_lcc_scan<false, true> : k_lcc_scan<false, false>)<<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], &c->cnt->fr_n[cur][0]);
+      if (first) (sm ? k_lcc_scan<true, true, false> : k_lcc_scan<true, false, false>)<<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], &c->cnt->fr_n[cur][0], 0);
+      else if (xlate) (sm ? k_lcc_scan<false, true, true> : k_lcc_scan<false, false, true>)<<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], &c->cnt->fr_n[cur][0], 0);
+      else (sm ? k_lcc_scan<false, true, false> : k_lcc_scan<false, false, false>)<<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], &c->cnt->fr_n[cur][0], 0);
       PM_LAUNCH_CHECK(c);
     }
     PM_CUDA(c, cudaEventRecord(ev[1], st));
     if (c->bin_live[1]) {
-      if (first) (sm ? k_lcc_scan_big<true, true> : k_lcc_scan_big<true, false>)<<<148, 1024, 0, st>>>(a, c->fr[cur][1], &c->cnt->fr_n[cur][1]);
-      else (sm ? k_lcc_scan_big<false, true> : k_lcc_scan_big<false, false>)<<<148, 1024, 0, st>>>(a, c->fr[cur][1], &c->cnt->fr_n[cur][1]);
+      if (first) (sm ? k_lcc_scan_big<true, true, false> : k_lcc_scan_big<true, false, false>)<<<148, 1024, 0, st>>>(a, c->fr[cur][1], &c->cnt->fr_n[cur][1], 0);
+      else if (xlate) (sm ? k_lcc_scan_big<false, true, true> : k_lcc_scan_big<false, false, true>)<<<148, 1024, 0, st>>>(a, c->fr[cur][1], &c->cnt->fr_n[cur][1], 0);
+      else (sm ? k_lcc_scan_big<false, true, false> : k_lcc_scan_big<false, false, false>)<<<148, 1024, 0, st>>>(a, c->fr[cur][1], &c->cnt->fr_n[cur][1], 0);
       PM_LAUNCH_CHECK(c);
     }
     PM_CUDA(c, cudaEventRecord(ev[2], st));
@@ -605,6 +640,15 @@ int pm_lcc(pm_ctx* c, int init_step, int* not_finished, pm_counts_t* counts_out)
       PM_LAUNCH_CHECK(c);
       c->step_parity ^= 1;
     }
+  }
+  if (init_step && D == 1) {
+    // no second scan in this call: rename the rows of the vertices still in the map to compact ids now
+    LccArgs a = lcc_args(c, 0);
+    const int cur = c->cur;
+    (sm ? k_lcc_scan<false, true, true> : k_lcc_scan<false, false, true>)<<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], &c->cnt->fr_n[cur][0], 1);
+    PM_LAUNCH_CHECK(c);
+    (sm ? k_lcc_scan_big<false, true, true> : k_lcc_scan_big<false, false, true>)<<<148, 1024, 0, st>>>(a, c->fr[cur][1], &c->cnt->fr_n[cur][1], 1);
+    PM_LAUNCH_CHECK(c);
   }
   PM_CUDA(c, cudaEventRecord(c->events[D], st));
   PM_CUDA(c, cudaMemcpyAsync(c->h_rowstat, c->rowstat, D * sizeof(RowStat), cudaMemcpyDeviceToHost, st));
@@ -736,7 +780,7 @@ int pm_nlcc(pm_ctx* c, int pl, int mode, int* pattern_found, int* token_source_d
     PM_CUDA(c, cudaMemsetAsync(&c->cnt->found, 0, sizeof(DevCounters) - offsetof(DevCounters, found), st));
     if (!tds) PM_CUDA(c, cudaMemsetAsync(c->hset, 0xFF, c->hset_use * sizeof(unsigned long long), st));
     // several ranks: `ok` doubles as this GPU's "already acknowledged" cache for foreign sources
-    if (multi) PM_CUDA(c, cudaMemsetAsync(c->ok, 0, c->nlmax * c->n_ranks, st));
+    if (multi) PM_CUDA(c, cudaMemsetAsync(c->ok, 0, std::max<uint64_t>(1, c->cid_off[c->n_ranks]), st));
     const bool dbg = getenv("PM_DEBUG_HOPS") != nullptr;
     std::vector<cudaEvent_t> dev;
     auto mark = [&]() { if (dbg) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); dev.push_back(e); } };
@@ -877,7 +921,7 @@ int pm_nlcc(pm_ctx* c, int pl, int mode, int* pattern_found, int* token_source_d
       uint32_t* d_rows = nullptr;
       if ((rc = dev_alloc(c, &d_rows, n_matches * n))) { dev_free(d_matches); return rc; }
       if (multi) k_tds_collect_m<<<grid, kBlock, 0, st>>>(nlc_args(c, nullptr, 0), n, d_rows);
-      else k_tds_materialize<<<grid, kBlock, 0, st>>>(c->pool, d_matches, n_matches, n, d_rows);
+      else k_tds_materialize<<<grid, kBlock, 0, st>>>(c->pool, d_matches, n_matches, n, c->vid, d_rows);
       c->launches++;
       c->subgraphs[pl].resize(n_matches * n);
       cudaError_t e = cudaMemcpyAsync(c->subgraphs[pl].data(), d_rows, n_matches * n * 4, cudaMemcpyDeviceToHost, st);
@@ -930,20 +974,23 @@ int pm_nlcc(pm_ctx* c, int pl, int mode, int* pattern_found, int* token_source_d
 // ------------------------------------------------------------------ results
 namespace pm {
 
-// (vertex, T_arr) of every vertex still in the map (beta.cpp:1386-1394)
-__global__ void k_emit_vertices(LccArgs a, const uint4* __restrict__ l0, const uint4* __restrict__ l1, int cur,
-                                uint2* __restrict__ out, unsigned long long* __restrict__ n_out) {
+// (vertex, T_arr) of every vertex still in the map (beta.cpp:1386-1394); vid: compact id -> slot
+// (null on the run_fuzzy path, whose entries name vertices directly)
+__global__ void k_emit_vertices(LccArgs a, const uint32_t* __restrict__ vid, const uint4* __restrict__ l0,
+                                const uint4* __restrict__ l1, int cur, uint2* __restrict__ out,
+                                unsigned long long* __restrict__ n_out) {
   const uint32_t c0 = a.cnt->fr_n[cur][0], c1 = a.cnt->fr_n[cur][1];
   const uint32_t total = c0 + c1;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const uint4 e = i < c0 ? l0[i] : l1[i - c0];
-    const uint32_t T = a.S[e.x + a.base];
-    if (T) out[atomicAdd(n_out, 1ull)] = make_uint2(e.x + a.base, T);
+    if (e.y == PM_TOMB) continue;
+    const uint32_t T = a.S[e.x];
+    if (T) out[atomicAdd(n_out, 1ull)] = make_uint2(vid ? vid[e.x] : e.x, T);
   }
 }
 
 // (vertex, neighbour) for every key of vertex_active_edges_map[v], v in the map (beta.cpp:1397-1403)
-__global__ void k_emit_edges(LccArgs a, const uint32_t* __restrict__ rowblk, const uint4* __restrict__ l0,
+__global__ void k_emit_edges(LccArgs a, const uint32_t* __restrict__ vid, const uint4* __restrict__ l0,
                              const uint4* __restrict__ l1, int cur, uint2* __restrict__ out,
                              unsigned long long* __restrict__ n_out) {
   const uint32_t c0 = a.cnt->fr_n[cur][0], c1 = a.cnt->fr_n[cur][1];
@@ -952,15 +999,17 @@ __global__ void k_emit_edges(LccArgs a, const uint32_t* __restrict__ rowblk, con
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t i = warp; i < total; i += nwarps) {
     const uint4 e = i < c0 ? l0[i] : l1[i - c0];
-    if (!a.S[e.x + a.base]) continue;
+    if (e.y == PM_TOMB || !a.S[e.x]) continue;
     const uint32_t d = e.z;
     const uint64_t row = (uint64_t)e.y * 8;
     unsigned long long base = 0;
     if (lane == 0) base = atomicAdd(n_out, (unsigned long long)d);
     base = __shfl_sync(0xffffffffu, base, 0);
-    for (uint32_t j = lane; j < d; j += 32) out[base + j] = make_uint2(e.x + a.base, a.colw[row + j] & PM_IDMASK);
+    for (uint32_t j = lane; j < d; j += 32) {
+      const uint32_t u = a.colw[row + j] & PM_IDMASK;
+      out[base + j] = make_uint2(vid ? vid[e.x] : e.x, vid ? vid[u] : u);
+    }
   }
-  (void)rowblk;
 }
 
 }  // namespace pm
@@ -988,8 +1037,9 @@ int fetch_pairs(pm_ctx* c, bool edges, std::vector<uint2>& host) {
   if ((rc = dev_alloc(c, &d_out, n))) return rc;
   if ((rc = dev_alloc(c, &d_n, 1))) { dev_free(d_out); return rc; }
   cudaMemsetAsync(d_n, 0, sizeof(unsigned long long), st);
-  if (edges) k_emit_edges<<<grid_for(), kBlock, 0, st>>>(la, c->rowblk, c->fr[cur][0], c->fr[cur][1], cur, d_out, d_n);
-  else k_emit_vertices<<<grid_for(), kBlock, 0, st>>>(la, c->fr[cur][0], c->fr[cur][1], cur, d_out, d_n);
+  const uint32_t* vid = c->fuzzy_ids ? nullptr : c->vid;
+  if (edges) k_emit_edges<<<grid_for(), kBlock, 0, st>>>(la, vid, c->fr[cur][0], c->fr[cur][1], cur, d_out, d_n);
+  else k_emit_vertices<<<grid_for(), kBlock, 0, st>>>(la, vid, c->fr[cur][0], c->fr[cur][1], cur, d_out, d_n);
   c->launches++;
   cudaError_t e = cudaMemcpyAsync(host.data(), d_out, n * sizeof(uint2), cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -1080,6 +1130,7 @@ int pm_run_fuzzy(pm_ctx* c, const pm_run_options_t* opt_in, pm_run_summary_t* ou
   if (opt_in) opt = *opt_in;
   int rc = pm_state_reset(c);  // allocations, pattern constants, bookkeeping (beta.cpp:484-492 analogue)
   if (rc) return rc;
+  c->fuzzy_ids = true;         // this path names vertices directly (no compact ids)
   cudaStream_t st = c->stream;
   const int D = c->pat.diameter, grid = grid_for();
   const int max_it = opt.max_iterations > 0 ? opt.max_iterations : 1000;

@@ -41,6 +41,9 @@ SPECS = [
     ("triangle", PT.triangle(1, 2, 3), [1, 2, 3], 1),
     ("cycle4", PT.cycle4(1, 2, 3, 4), [1, 2, 3, 4], 1),
     ("cycle6", PT.cycle6_chords([1, 2, 3, 4, 5, 6]), [1, 2, 3, 4, 5, 6], 3),
+    # a single LCC superstep per call (pattern_stat "diameter : 1"): edge maps keep neighbours that left the
+    # vertex map until the next call
+    ("triangle_d1", dict(PT.triangle(1, 2, 3), diameter=1), [1, 2, 3], 1),
 ]
 
 

@@ -223,7 +223,7 @@ def main():
 
     for _ in range(args.warmup):
         one_step()
-    ks0 = [eng.kernel_stats(b) for b in range(3)]
+    ks0 = [eng.kernel_stats(b) for b in range(5)]
     l0 = eng.kernel_launches()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -235,7 +235,7 @@ def main():
     elapsed = time.perf_counter() - t0
     clocks = sampler.stop()
     launches = eng.kernel_launches() - l0
-    ks1 = [eng.kernel_stats(b) for b in range(3)]
+    ks1 = [eng.kernel_stats(b) for b in range(5)]
     if world > 1:
         t = torch.tensor([elapsed], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -250,14 +250,17 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    dk = [dict((k, ks1[b][k] - ks0[b][k]) for k in ks1[b]) for b in range(3)]
-    top = max(range(3), key=lambda b: dk[b]["ms"])
-    names = ["k_lcc_scan<FIRST=true> (first superstep: pristine adjacency + label stream)",
-             "k_lcc_scan<FIRST=false> (later supersteps: active edge maps + mask gathers)", "k_lcc_scan_big"]
+    dk = [dict((k, ks1[b][k] - ks0[b][k]) for k in ks1[b]) for b in range(5)]
+    scan_classes = [0, 1, 2, 4]                       # 3 is the init filter (no adjacency walked)
+    top = max(scan_classes, key=lambda b: dk[b]["ms"])
+    names = {0: "k_lcc_scan<FIRST=true> (first superstep: pristine adjacency + label stream)",
+             1: "k_lcc_scan<FIRST=false> (later supersteps: active edge maps + mask gathers)",
+             2: "k_lcc_scan_big (CTA per row)",
+             4: "k_lcc_scan<XLATE=true> (second superstep: mask gathers + renaming slots to compact ids)"}
     traffic = None
     try:  # DRAM bytes per launch of the same kernel class from the committed ncu --set full capture
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = tr.get(["scan_first", "scan_later", "scan_big"][top], {}).get("dram_bytes_per_launch")
+        traffic = tr.get({0: "scan_first", 1: "scan_later", 2: "scan_big", 4: "scan_xlate"}[top], {}).get("dram_bytes_per_launch")
     except Exception:
         pass
     roof = None
@@ -270,7 +273,7 @@ def main():
                 "algorithmic_bytes_per_launch": alg_bytes / dk[top]["launches"],
                 "avg_launch_ms": dk[top]["ms"] / dk[top]["launches"], "launches": dk[top]["launches"],
                 "share_of_step": dk[top]["ms"] * 1e-3 / elapsed,
-                "other_classes": {names[b].split(" ")[0]: {"ms": dk[b]["ms"], "launches": dk[b]["launches"]} for b in range(3) if b != top},
+                "other_classes": {names[b].split(" ")[0]: {"ms": dk[b]["ms"], "launches": dk[b]["launches"]} for b in scan_classes if b != top},
                 "model": "6.25 B per scanned slot + 12.25 B per scanned vertex"}
 
     # end to end through the C ABI with HOST buffers: upload the host CSR, search, read results back

@@ -1,6 +1,10 @@
 // pm_common.cuh — context, device-side constants and small helpers shared by the
 // kernels of libpmgpu.so (sm_100a only; no CPU fallback, no multi-backend dispatch).
 #pragma once
+#include <chrono>
+#include <unordered_map>
+#include <mutex>
+#include <list>
 
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -178,7 +182,12 @@ struct pm_ctx {
   pm::DevCounters* h_cnt = nullptr;    // pinned host mirror
   pm::RowStat* rowstat = nullptr;      // device, [diameter + 1]
   pm::RowStat* h_rowstat = nullptr;    // pinned
+  int rowstat_cap = 0;                 // rows rowstat / h_rowstat can hold
   bool state_ready = false;
+  // maintain labw (the label stream of the working adjacency) through the scans so that NLCC hops can test the
+  // label without gathering S.  Off by default: with compact ids S is L2 resident and the gather is cheaper than
+  // moving a second stream along with every row compaction (PM_KEEP_LABW=1 switches it back on).
+  bool keep_labw = false;
   bool fuzzy_ids = false;   // the frontier entries of the last run name vertices, not compact ids (pm_run_fuzzy)
 
   // ---- NLCC scratch -----------------------------------------------------------------
@@ -211,7 +220,7 @@ struct pm_ctx {
   std::vector<cudaEvent_t> kev2;   // per superstep: before main scan, after it, after the big-row scan
   std::vector<int> kev2_cls;       // per superstep: kernel class of the main scan (0 first, 1 later)
   cudaEvent_t kev[4][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
-  pm_kernel_stats_t kstat[4] = {};  // [3]: the first-superstep signature filter
+  pm_kernel_stats_t kstat[5] = {};  // [3]: the first-superstep signature filter, [4]: the renaming scan
 };
 
 namespace pm {
@@ -236,17 +245,90 @@ inline int fail(pm_ctx* c, int code, const std::string& msg) {
     PM_CUDA((ctx), cudaGetLastError());                     \
   } while (0)
 
+// Device blocks are recycled by exact size: re-opening a graph or loading the next pattern asks for the
+// same array sizes again, and cudaMalloc / cudaFree of multi-GB blocks (a device-wide synchronisation each)
+// would otherwise cost tens of milliseconds per call.  Freed blocks wait in a per-process list, oldest
+// evicted first above kCacheCap bytes; everything is released when an allocation fails or a context dies.
+struct DevBlockCache {
+  static constexpr size_t kCacheCap = 64ull << 30;
+  struct Block { void* p; int dev; size_t bytes; };
+  std::mutex mu;
+  std::unordered_map<void*, std::pair<int, size_t>> live;  // blocks handed out: device, size
+  std::list<Block> idle;                                    // freed blocks, oldest first
+  size_t idle_bytes = 0;
+
+  void* take(int dev, size_t bytes) {
+    std::lock_guard<std::mutex> g(mu);
+    for (auto it = idle.begin(); it != idle.end(); ++it)
+      if (it->dev == dev && it->bytes == bytes) {
+        void* p = it->p;
+        idle_bytes -= bytes;
+        idle.erase(it);
+        live[p] = {dev, bytes};
+        return p;
+      }
+    return nullptr;
+  }
+  void adopt(void* p, int dev, size_t bytes) {
+    std::lock_guard<std::mutex> g(mu);
+    live[p] = {dev, bytes};
+  }
+  void give_back(void* p) {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = live.find(p);
+    if (it == live.end()) { cudaFree(p); return; }
+    const Block b{p, it->second.first, it->second.second};
+    live.erase(it);
+    if (b.bytes > kCacheCap) { cudaFree(p); return; }
+    while (!idle.empty() && idle_bytes + b.bytes > kCacheCap) {
+      cudaFree(idle.front().p);
+      idle_bytes -= idle.front().bytes;
+      idle.pop_front();
+    }
+    idle.push_back(b);
+    idle_bytes += b.bytes;
+  }
+  void flush(int dev) {  // dev < 0: every device
+    std::lock_guard<std::mutex> g(mu);
+    for (auto it = idle.begin(); it != idle.end();) {
+      if (dev < 0 || it->dev == dev) {
+        cudaFree(it->p);
+        idle_bytes -= it->bytes;
+        it = idle.erase(it);
+      } else {
+        ++it;
+      }
+    }
+  }
+};
+inline DevBlockCache& dev_cache() {
+  static DevBlockCache* cache = new DevBlockCache();  // never destroyed: the driver may be gone at exit
+  return *cache;
+}
+
 template <class T>
 inline int dev_alloc(pm_ctx* c, T** p, uint64_t n, uint64_t* tally = nullptr) {
   *p = nullptr;
   if (n == 0) n = 1;
-  PM_CUDA(c, cudaMalloc((void**)p, n * sizeof(T)));
+  const size_t bytes = (n * sizeof(T) + 255) / 256 * 256;
+  void* q = dev_cache().take(c->device, bytes);
+  if (!q) {
+    cudaError_t e = cudaMalloc(&q, bytes);
+    if (e != cudaSuccess) {  // make room: drop everything that is only cached
+      (void)cudaGetLastError();
+      dev_cache().flush(c->device);
+      q = nullptr;
+      PM_CUDA(c, cudaMalloc(&q, bytes));
+    }
+    dev_cache().adopt(q, c->device, bytes);
+  }
+  *p = (T*)q;
   if (tally) *tally += n * sizeof(T);
   return 0;
 }
 template <class T>
 inline void dev_free(T*& p) {
-  if (p) cudaFree(p);
+  if (p) dev_cache().give_back((void*)p);
   p = nullptr;
 }
 
@@ -256,6 +338,11 @@ static const int kGridPerSM = 8;
 inline int grid_for(uint64_t work_items_per_thread_hint = 0) {
   (void)work_items_per_thread_hint;
   return 148 * kGridPerSM;
+}
+
+inline double wall_s() {
+  using namespace std::chrono;
+  return duration<double>(steady_clock::now().time_since_epoch()).count();
 }
 
 }  // namespace pm

@@ -99,30 +99,51 @@ __global__ void k_scatter_cols(const unsigned long long* __restrict__ ukeys, uin
 __global__ void k_csr_degrees(const unsigned long long* __restrict__ rowptr,
                               const unsigned long long* __restrict__ degm64, uint64_t V,
                               uint32_t* __restrict__ deg, uint32_t* __restrict__ degm,
-                              uint32_t* __restrict__ sectors) {
+                              uint32_t* __restrict__ sectors, unsigned long long* __restrict__ degm_total) {
   uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  unsigned long long sum = 0;
   for (; v <= V; v += stride) {
     uint32_t d = 0;
     if (v < V) {
       d = (uint32_t)(rowptr[v + 1] - rowptr[v]);
       deg[v] = d;
-      degm[v] = (uint32_t)degm64[v];
+      const unsigned long long dm = degm64[v];
+      degm[v] = (uint32_t)dm;
+      sum += dm;
     }
     sectors[v] = (d + 7u) >> 3;
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0 && sum) atomicAdd(degm_total, sum);
 }
 
-// one warp copies one row of the compact CSR into its padded, sector aligned slot range
+// one warp copies one row of the compact CSR into its padded, sector aligned slot range (rows [v0, v1);
+// the padding slots are written too, so the destination needs no memset)
 __global__ void k_csr_place(const unsigned long long* __restrict__ rowptr, const uint32_t* __restrict__ col,
-                            uint64_t V, const uint32_t* __restrict__ rowblk, uint32_t* __restrict__ col0) {
+                            uint64_t v0, uint64_t v1, const uint32_t* __restrict__ rowblk, uint32_t* __restrict__ col0) {
   const uint32_t lane = threadIdx.x & 31;
-  uint64_t v = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  uint64_t v = v0 + (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-  for (; v < V; v += nwarps) {
+  for (; v < v1; v += nwarps) {
     const unsigned long long b = rowptr[v], e = rowptr[v + 1];
     const uint64_t o = (uint64_t)rowblk[v] * 8;
-    for (unsigned long long j = b + lane; j < e; j += 32) col0[o + (j - b)] = col[j];
+    const unsigned long long d = e - b, padded = (d + 7ull) & ~7ull;
+    for (unsigned long long j = lane; j < padded; j += 32) col0[o + j] = j < d ? col[b + j] : PM_SENTINEL;
+  }
+}
+
+// src[j] = global id of the vertex whose local row holds slot j (local row i = vertex i * G + rank)
+__global__ void k_csr_expand_sources(const unsigned long long* __restrict__ rowptr, uint64_t n_rows, uint32_t G,
+                                     uint32_t rank, uint32_t* __restrict__ src) {
+  const uint32_t lane = threadIdx.x & 31;
+  uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (; i < n_rows; i += nwarps) {
+    const unsigned long long b = rowptr[i], e = rowptr[i + 1];
+    const uint32_t v = (uint32_t)(i * G + rank);
+    for (unsigned long long j = b + lane; j < e; j += 32) src[j] = v;
   }
 }
 
@@ -149,6 +170,7 @@ __global__ void k_labels_to_bytes(const uint64_t* __restrict__ label, uint64_t V
 __global__ void __launch_bounds__(256) k_build_sig(const uint32_t* __restrict__ rowblk, const uint32_t* __restrict__ deg,
                                                    const uint32_t* __restrict__ col0, const uint8_t* __restrict__ lab8,
                                                    uint64_t V, unsigned long long* __restrict__ sig,
+                                                   uint8_t* __restrict__ lab0,
                                                    uint32_t* __restrict__ big_list, uint32_t* __restrict__ big_n) {
   const uint32_t lane = threadIdx.x & 31, gl = lane & 7, gw = lane >> 3;
   const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -168,10 +190,18 @@ __global__ void __launch_bounds__(256) k_build_sig(const uint32_t* __restrict__ 
       const uint32_t j0 = p * 32 + gl * 4;
       if (j0 < d) {
         const uint4 q = *reinterpret_cast<const uint4*>(col0 + row + j0);
-        m |= 1ull << lab8[q.x];
-        if (j0 + 1 < d) m |= 1ull << lab8[q.y];
-        if (j0 + 2 < d) m |= 1ull << lab8[q.z];
-        if (j0 + 3 < d) m |= 1ull << lab8[q.w];
+        const uint32_t l0 = lab8[q.x];
+        const uint32_t l1 = j0 + 1 < d ? (uint32_t)lab8[q.y] : 0u;
+        const uint32_t l2 = j0 + 2 < d ? (uint32_t)lab8[q.z] : 0u;
+        const uint32_t l3 = j0 + 3 < d ? (uint32_t)lab8[q.w] : 0u;
+        m |= 1ull << l0;
+        if (j0 + 1 < d) m |= 1ull << l1;
+        if (j0 + 2 < d) m |= 1ull << l2;
+        if (j0 + 3 < d) m |= 1ull << l3;
+        // the label stream of the row (padding slots carry label 0); rows start sector aligned
+        *reinterpret_cast<uint32_t*>(lab0 + row + j0) = l0 | (l1 << 8) | (l2 << 16) | (l3 << 24);
+      } else if (j0 < ((d + 7u) & ~7u)) {
+        *reinterpret_cast<uint32_t*>(lab0 + row + j0) = 0u;
       }
     }
     m |= __shfl_xor_sync(0xffffffffu, m, 1);
@@ -183,7 +213,7 @@ __global__ void __launch_bounds__(256) k_build_sig(const uint32_t* __restrict__ 
 
 __global__ void __launch_bounds__(1024) k_build_sig_big(const uint32_t* __restrict__ rowblk, const uint32_t* __restrict__ deg,
                                                         const uint32_t* __restrict__ col0, const uint8_t* __restrict__ lab8,
-                                                        unsigned long long* __restrict__ sig,
+                                                        unsigned long long* __restrict__ sig, uint8_t* __restrict__ lab0,
                                                         const uint32_t* __restrict__ big_list, const uint32_t* __restrict__ big_n) {
   __shared__ unsigned long long s_m[32];
   const uint32_t n = *big_n;
@@ -191,7 +221,12 @@ __global__ void __launch_bounds__(1024) k_build_sig_big(const uint32_t* __restri
     const uint32_t v = big_list[i], d = deg[v];
     const uint64_t row = (uint64_t)rowblk[v] * 8;
     unsigned long long m = 0;
-    for (uint32_t j = threadIdx.x; j < d; j += blockDim.x) m |= 1ull << lab8[col0[row + j]];
+    const uint32_t padded = (d + 7u) & ~7u;
+    for (uint32_t j = threadIdx.x; j < padded; j += blockDim.x) {
+      const uint8_t l = j < d ? lab8[col0[row + j]] : (uint8_t)0;
+      if (j < d) m |= 1ull << l;
+      lab0[row + j] = l;
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m |= __shfl_xor_sync(0xffffffffu, m, o);
     if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = m;
@@ -202,16 +237,6 @@ __global__ void __launch_bounds__(1024) k_build_sig_big(const uint32_t* __restri
       sig[v] = t;
     }
     __syncthreads();
-  }
-}
-
-__global__ void k_build_lab0(const uint32_t* __restrict__ col0, const uint8_t* __restrict__ lab8, uint64_t n,
-                             uint8_t* __restrict__ lab0) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) {
-    const uint32_t u = col0[i];
-    lab0[i] = u == PM_SENTINEL ? (uint8_t)0 : lab8[u];
   }
 }
 
@@ -238,10 +263,11 @@ inline int labels_derive(pm_ctx* c, bool small) {
   cudaMemsetAsync(big_n, 0, 4, st);
   k_labels_to_bytes<<<grid_for(), kBlock, 0, st>>>(c->label, c->nloc, c->lab8 + base);
   if ((rc = comm_allgather_slots(c, c->lab8))) { dev_free(big_list); dev_free(big_n); return rc; }
-  k_build_sig<<<grid_for(), 256, 0, st>>>(c->rowblk, c->deg, c->col0, c->lab8, c->nloc, c->sig, big_list, big_n);
-  k_build_sig_big<<<148, 1024, 0, st>>>(c->rowblk, c->deg, c->col0, c->lab8, c->sig, big_list, big_n);
-  k_build_lab0<<<grid_for(), kBlock, 0, st>>>(c->col0, c->lab8, c->Epad + 64, c->lab0);
-  c->launches += 4;
+  // signatures and the label stream lab0 come out of the same pass over the adjacency (one gather per slot)
+  cudaMemsetAsync(c->lab0 + c->Epad, 0, 64, st);
+  k_build_sig<<<grid_for(), 256, 0, st>>>(c->rowblk, c->deg, c->col0, c->lab8, c->nloc, c->sig, c->lab0, big_list, big_n);
+  k_build_sig_big<<<148, 1024, 0, st>>>(c->rowblk, c->deg, c->col0, c->lab8, c->sig, c->lab0, big_list, big_n);
+  c->launches += 3;
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   dev_free(big_list);
@@ -481,6 +507,7 @@ inline int graph_build_from_device_slots(pm_ctx* c, uint64_t V, uint64_t n_in, c
   }
   PM_GC(cudaStreamSynchronize(st));
   cleanup();
+  dev_cache().flush(c->device);  // the sort buffers of a build are never asked for again
 #undef PM_G
 #undef PM_GC
   c->graph_bytes = bytes;
@@ -489,35 +516,58 @@ inline int graph_build_from_device_slots(pm_ctx* c, uint64_t V, uint64_t n_in, c
   return 0;
 }
 
-// Host CSR -> device store.  h_* are HOST pointers (copied here: this is the
-// host->device traffic an end-to-end run pays).
+// Host CSR -> device store.  h_* are HOST pointers (copied here: this is the host->device traffic an
+// end-to-end run pays).  The adjacency travels in chunks on a copy stream straight into the (still unused)
+// working adjacency `colw`; each chunk's rows are placed into their padded positions of `col0` while the
+// next chunk is still on the bus, so the PCIe copy is the only thing on the critical path.
 inline int graph_build_from_host_csr(pm_ctx* c, uint64_t V, const uint64_t* h_rowptr, const uint32_t* h_col,
                                      const uint64_t* h_degm) {
   if (V == 0 || V > (1ull << 31)) return fail(c, PM_ERR_ARG, "n_vertices must be in [1, 2^31]");
+  const bool dbg = getenv("PM_DEBUG_BUILD") != nullptr;
+  double t_prev = wall_s();
+  auto lap = [&](const char* what) {
+    if (!dbg) return;
+    cudaStreamSynchronize(c->stream);
+    const double t = wall_s();
+    fprintf(stderr, "[pm build] %-28s %.2f ms\n", what, (t - t_prev) * 1e3);
+    t_prev = t;
+  };
   graph_free(c);
+  lap("graph_free");
   graph_set_partition(c, V);  // single rank: slot = vertex id, the rows can be placed as they are
   cudaStream_t st = c->stream;
   const uint64_t E = h_rowptr[V];
   c->E = E;
   uint64_t bytes = 0;
   int rc;
-  unsigned long long *d_rowptr = nullptr, *d_degm64 = nullptr;
-  uint32_t *d_col = nullptr, *sectors = nullptr;
+  unsigned long long *d_rowptr = nullptr, *d_degm64 = nullptr, *d_total = nullptr;
+  uint32_t* sectors = nullptr;
   void* tmp = nullptr;
-  auto cleanup = [&]() { dev_free(d_rowptr); dev_free(d_degm64); dev_free(d_col); dev_free(sectors); if (tmp) cudaFree(tmp); tmp = nullptr; };
+  cudaStream_t cs = nullptr;
+  std::vector<cudaEvent_t> evs;
+  auto cleanup = [&]() {
+    dev_free(d_rowptr); dev_free(d_degm64); dev_free(d_total); dev_free(sectors);
+    if (tmp) cudaFree(tmp);
+    tmp = nullptr;
+    for (auto e : evs) cudaEventDestroy(e);
+    evs.clear();
+    if (cs) cudaStreamDestroy(cs);
+    cs = nullptr;
+  };
   if ((rc = dev_alloc(c, &c->degm, V, &bytes)) || (rc = dev_alloc(c, &c->deg, V, &bytes)) ||
       (rc = dev_alloc(c, &c->rowblk, V + 1, &bytes)) || (rc = dev_alloc(c, &d_rowptr, V + 1)) ||
-      (rc = dev_alloc(c, &d_degm64, V)) || (rc = dev_alloc(c, &d_col, E)) || (rc = dev_alloc(c, &sectors, V + 1))) {
+      (rc = dev_alloc(c, &d_degm64, V)) || (rc = dev_alloc(c, &d_total, 1)) || (rc = dev_alloc(c, &sectors, V + 1))) {
     cleanup();
     return rc;
   }
 #define PM_GC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); \
     return fail(c, PM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
+  lap("alloc 1");
   PM_GC(cudaMemcpyAsync(d_rowptr, h_rowptr, (V + 1) * 8, cudaMemcpyHostToDevice, st));
   PM_GC(cudaMemcpyAsync(d_degm64, h_degm, V * 8, cudaMemcpyHostToDevice, st));
-  if (E) PM_GC(cudaMemcpyAsync(d_col, h_col, E * 4, cudaMemcpyHostToDevice, st));
+  PM_GC(cudaMemsetAsync(d_total, 0, 8, st));
   const int grid = grid_for();
-  k_csr_degrees<<<grid, kBlock, 0, st>>>(d_rowptr, d_degm64, V, c->deg, c->degm, sectors);
+  k_csr_degrees<<<grid, kBlock, 0, st>>>(d_rowptr, d_degm64, V, c->deg, c->degm, sectors, d_total);
   c->launches++;
   size_t tb = 0, tb2 = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, tb, sectors, c->rowblk, (int64_t)(V + 1), st);
@@ -527,30 +577,52 @@ inline int graph_build_from_host_csr(pm_ctx* c, uint64_t V, const uint64_t* h_ro
   PM_GC(cudaMalloc(&tmp, std::max<size_t>(tb, 16) + 16));
   PM_GC(cub::DeviceScan::ExclusiveSum(tmp, tb, sectors, c->rowblk, (int64_t)(V + 1), st));
   uint32_t h_total = 0, h_max = 0;
+  unsigned long long h_em = 0;
   PM_GC(cudaMemcpyAsync(&h_total, c->rowblk + V, 4, cudaMemcpyDeviceToHost, st));
   d_max = sectors;  // reuse: sectors are consumed
   PM_GC(cub::DeviceReduce::Max(tmp, tb, c->degm, d_max, (int64_t)V, st));
   PM_GC(cudaMemcpyAsync(&h_max, d_max, 4, cudaMemcpyDeviceToHost, st));
+  PM_GC(cudaMemcpyAsync(&h_em, d_total, 8, cudaMemcpyDeviceToHost, st));
   PM_GC(cudaStreamSynchronize(st));
   c->max_deg = h_max;
+  c->E_multi = h_em;  // multigraph slot count = sum of multigraph degrees
   c->Epad = (uint64_t)h_total * 8;
+  lap("row pointers, degrees, scan");
   const uint64_t alloc_slots = c->Epad + 64;
   if ((rc = dev_alloc(c, &c->col0, alloc_slots, &bytes)) || (rc = dev_alloc(c, &c->colw, alloc_slots, &bytes))) {
     cleanup();
     return rc;
   }
-  PM_GC(cudaMemsetAsync(c->col0, 0xFF, alloc_slots * 4, st));
-  PM_GC(cudaMemsetAsync(c->colw, 0xFF, alloc_slots * 4, st));
-  k_csr_place<<<grid, kBlock, 0, st>>>(d_rowptr, d_col, V, c->rowblk, c->col0);
-  c->launches++;
-  PM_GC(cudaGetLastError());
+  lap("alloc col0/colw");
+  PM_GC(cudaMemsetAsync(c->col0 + c->Epad, 0xFF, 64 * 4, st));
+  if (E) {
+    PM_GC(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    const uint64_t n_chunks = std::max<uint64_t>(1, std::min<uint64_t>(32, E >> 24));  // >= 64 MiB per chunk
+    uint64_t v0 = 0;
+    for (uint64_t k = 1; k <= n_chunks && v0 < V; ++k) {
+      // rows [v0, v1): v1 = first row that starts at or after the k-th share of the slots
+      uint64_t v1 = V;
+      if (k < n_chunks) v1 = (uint64_t)(std::lower_bound(h_rowptr + v0, h_rowptr + V, E / n_chunks * k) - h_rowptr);
+      if (v1 <= v0) continue;
+      const uint64_t b = h_rowptr[v0], e = h_rowptr[v1];
+      cudaEvent_t ev;
+      PM_GC(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      evs.push_back(ev);
+      if (e > b) PM_GC(cudaMemcpyAsync(c->colw + b, h_col + b, (e - b) * 4, cudaMemcpyHostToDevice, cs));
+      PM_GC(cudaEventRecord(ev, cs));
+      PM_GC(cudaStreamWaitEvent(st, ev, 0));
+      k_csr_place<<<grid, kBlock, 0, st>>>(d_rowptr, c->colw, v0, v1, c->rowblk, c->col0);
+      c->launches++;
+      v0 = v1;
+    }
+    PM_GC(cudaGetLastError());
+  }
+  PM_GC(cudaMemsetAsync(c->colw, 0xFF, alloc_slots * 4, st));  // the staging copy is spent
   PM_GC(cudaStreamSynchronize(st));
 #undef PM_GC
+  lap("adjacency copy + placement");
   cleanup();
-  // multigraph slot count = sum of multigraph degrees
-  uint64_t em = 0;
-  for (uint64_t v = 0; v < V; ++v) em += h_degm[v];
-  c->E_multi = em;
+  lap("free temporaries");
   c->graph_bytes = bytes;
   c->has_graph = true;
   c->state_ready = false;

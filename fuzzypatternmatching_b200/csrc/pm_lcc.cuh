@@ -484,7 +484,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_lcc_scan(LccArgs a, uint4* __rest
             const int j = 4 * c + k;
             if ((keepm >> j) & 1u) {
               a.colw[row + pos] = XLATE ? xl[j] : (u[k] & PM_IDMASK);
-              if (STREAM) a.labw[row + pos] = (uint8_t)(l4[c] >> (8 * k));
+              if (STREAM && a.labw) a.labw[row + pos] = (uint8_t)(l4[c] >> (8 * k));
               ++pos;
             }
           }
@@ -572,7 +572,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_lcc_scan(LccArgs a, uint4* __rest
         for (int k = 0; k < 4; ++k)
           if (keep[k]) {
             a.colw[rrow + pos] = wr[k];
-            if (STREAM) a.labw[rrow + pos] = (uint8_t)(l4 >> (8 * k));
+            if (STREAM && a.labw) a.labw[rrow + pos] = (uint8_t)(l4 >> (8 * k));
             ++pos;
           }
         rout += cnt_pass;
@@ -685,7 +685,7 @@ __global__ void __launch_bounds__(1024) k_lcc_scan_big(LccArgs a, uint4* __restr
       for (int k = 0; k < 4; ++k)
         if (keep[k]) {
           a.colw[row + pos] = wr[k];
-          if (STREAM) a.labw[row + pos] = (uint8_t)(l4 >> (8 * k));
+          if (STREAM && a.labw) a.labw[row + pos] = (uint8_t)(l4 >> (8 * k));
           ++pos;
         }
       outp += ptotal;

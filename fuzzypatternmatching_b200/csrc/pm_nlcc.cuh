@@ -41,6 +41,9 @@ __constant__ NlcConst c_nlc;
 #define PM_HSET_EMPTY 0xFFFFFFFFFFFFFFFFull
 
 // every vertex below is named by its COMPACT ID (see pm_lcc.cuh); `rowblk` is the row start by local compact id
+// A neighbour u can take hop h iff bit I[h] of S[u] is set: S[u] is always a subset of labelmask(label[u]),
+// so the bit test implies the label test of the reference (nem_1.hpp:557-581) and no class gather is needed.
+// STREAM kernels additionally skip the S gather of neighbours whose label (labw) rules the hop out.
 struct NlcArgs {
   const uint32_t* rowblk;
   uint32_t* colw;
@@ -321,7 +324,7 @@ __global__ void __launch_bounds__(kBlock) k_nem1_expand(NlcArgs a, int hlevel, i
         if (STREAM) may = may && ((l4 >> (8 * k)) & 0xffu) == want_lab;
         if (may) {
           const uint32_t su = a.S[u[k]];
-          pass_static[k] = su != 0 && ((su >> c_nlc.I[hn]) & 1u) && (STREAM || a.cls[u[k]] == c_nlc.cls[hn]);
+          pass_static[k] = su != 0 && ((su >> c_nlc.I[hn]) & 1u);
         }
       }
       if (FINAL) {
@@ -422,7 +425,7 @@ __global__ void __launch_bounds__(kBlock) k_nem1_close_cycle(NlcArgs a, int hlev
         }
         if (b >= ds || (a.colw[rs + b] & PM_IDMASK) != u[k]) continue;
         const uint32_t su = a.S[u[k]];
-        if (su != 0 && ((su >> c_nlc.I[hn]) & 1u) && (STREAM || a.cls[u[k]] == c_nlc.cls[hn])) {
+        if (su != 0 && ((su >> c_nlc.I[hn]) & 1u)) {
           a.ok[s] = 1;
           a.cnt->found = 1u;
           atomicOr(&a.colw[rs + b], 0x80000000u);
@@ -509,7 +512,7 @@ __global__ void __launch_bounds__(kBlock) k_tds_expand(NlcArgs a, int hlevel, in
         if (STREAM) may = may && ((l4 >> (8 * k)) & 0xffu) == want_lab;
         if (may) {
           const uint32_t su = a.S[u[k]];
-          acc[k] = su != 0 && ((su >> c_nlc.I[hn]) & 1u) && (STREAM || a.cls[u[k]] == c_nlc.cls[hn]);
+          acc[k] = su != 0 && ((su >> c_nlc.I[hn]) & 1u);
           if (acc[k]) {
             if (FINAL)  // penultimate-hop filter of the sender (tds_batch_1.hpp:808-845)
               acc[k] = c_nlc.valid_cycle ? (u[k] == s) : (u[k] != s && hist_rule(hist, hn, u[k]));

@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(kBlock) k_close_keys_m(NlcArgs a, const uint4*
         ok[k] = false;
         if (may) {
           const uint32_t su = a.S[u[k]];
-          ok[k] = su != 0 && ((su >> c_nlc.I[hn]) & 1u) && (STREAM || a.cls[u[k]] == c_nlc.cls[hn]);
+          ok[k] = su != 0 && ((su >> c_nlc.I[hn]) & 1u);
         }
         n += ok[k];
       }
@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(kBlock) k_nem1_hop_m(NlcArgs a, int hn, int fi
           continue;
         }
         const uint32_t su = a.S[u[k]];
-        pass[k] = su != 0 && ((su >> c_nlc.I[hn]) & 1u) && (STREAM || a.cls[u[k]] == c_nlc.cls[hn]);
+        pass[k] = su != 0 && ((su >> c_nlc.I[hn]) & 1u);
       }
       if (MODE == 1) {
 #pragma unroll
@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(kBlock) k_tds_hop_m(NlcArgs a, int hn) {
         if (STREAM) may = may && ((l4 >> (8 * k)) & 0xffu) == want_lab;
         if (may) {
           const uint32_t su = a.S[u[k]];
-          acc = su != 0 && ((su >> c_nlc.I[hn]) & 1u) && (STREAM || a.cls[u[k]] == c_nlc.cls[hn]);
+          acc = su != 0 && ((su >> c_nlc.I[hn]) & 1u);
           if (acc) {
             if (FINAL) acc = c_nlc.valid_cycle ? (u[k] == s) : (u[k] != s && hist_rule(hist, hn, u[k]));
             else acc = hist_rule(hist, hn, u[k]);

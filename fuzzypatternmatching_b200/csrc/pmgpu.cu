@@ -24,11 +24,6 @@ using namespace pm;
 
 namespace {
 
-double wall_s() {
-  using namespace std::chrono;
-  return duration<double>(steady_clock::now().time_since_epoch()).count();
-}
-
 int sync_counters(pm_ctx* c) {
   PM_CUDA(c, cudaMemcpyAsync(c->h_cnt, c->cnt, sizeof(DevCounters), cudaMemcpyDeviceToHost, c->stream));
   PM_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -39,7 +34,7 @@ LccArgs lcc_args(pm_ctx* c, int row) {
   LccArgs a;
   a.col0 = c->col0; a.colw = c->colw;
   a.S = c->S; a.adeg = c->adeg; a.cls = c->cls; a.cnt = c->cnt;
-  a.lab0 = c->lab0; a.labw = c->labw;
+  a.lab0 = c->lab0; a.labw = c->keep_labw ? c->labw : nullptr;
   a.row = c->rowstat + row;
   a.base = c->cid_off[c->rank];
   a.par = c->step_parity;
@@ -93,8 +88,13 @@ int comm_publish(pm_ctx* c) {
   return comm_upload_peers(c);
 }
 
-void state_free(pm_ctx* c) {
+// keep_scratch: a new graph is about to be opened by the same context.  The NLCC token pool and key table
+// are sized by what the searches needed, not by the graph, so a single rank keeps them (growing them again
+// would cost one multi-GB cudaMalloc per step of the growth); several ranks release everything because the
+// peers' mappings of the old buffers must go.
+void state_free(pm_ctx* c, bool keep_scratch = false) {
   comm_close_all(c);  // nobody may still map the buffers freed below
+  const bool keep = keep_scratch && c->n_ranks == 1;
   dev_free(c->din[0]); dev_free(c->din[1]); dev_free(c->tin[0]); dev_free(c->tin[1]); dev_free(c->step_msg);
   dev_free(c->sync_in);
   if (c->h_step) cudaFreeHost(c->h_step);
@@ -103,12 +103,13 @@ void state_free(pm_ctx* c) {
   dev_free(c->S); dev_free(c->adeg); dev_free(c->cls);
   dev_free(c->rowc); dev_free(c->vid); dev_free(c->clsc); dev_free(c->fw); dev_free(c->tb);
   for (int b = 0; b < 2; ++b) for (int k = 0; k < 2; ++k) dev_free(c->fr[b][k]);
-  dev_free(c->cnt); dev_free(c->rowstat); dev_free(c->ok); dev_free(c->src_list);
-  dev_free(c->hset); dev_free(c->pool);
-  if (c->h_cnt) cudaFreeHost(c->h_cnt);
-  if (c->h_rowstat) cudaFreeHost(c->h_rowstat);
-  c->h_cnt = nullptr; c->h_rowstat = nullptr;
-  c->hset_cap = c->pool_cap = 0;
+  dev_free(c->cnt); dev_free(c->ok); dev_free(c->src_list);
+  if (!keep) {
+    dev_free(c->hset); dev_free(c->pool);
+    c->hset_cap = c->pool_cap = 0;
+  }
+  // the small pinned read-back buffers (h_cnt, h_rowstat) live as long as the context: pinned allocation
+  // calls synchronise the device
   c->state_ready = false;
 }
 
@@ -170,6 +171,7 @@ int pm_create(pm_ctx** out, int device) {
   if (cudaSetDevice(device) != cudaSuccess) return PM_ERR_CUDA;
   pm_ctx* c = new pm_ctx();
   c->device = device;
+  if (const char* e = getenv("PM_KEEP_LABW")) c->keep_labw = e[0] == '1';
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete c;
     return PM_ERR_CUDA;
@@ -192,6 +194,10 @@ void pm_destroy(pm_ctx* c) {
   c->comm = nullptr;
   state_free(c);
   graph_free(c);
+  dev_free(c->rowstat);
+  if (c->h_cnt) cudaFreeHost(c->h_cnt);
+  if (c->h_rowstat) cudaFreeHost(c->h_rowstat);
+  dev_cache().flush(c->device);
   if (comm) ncclCommDestroy(comm);
   if (c->d_scratch) cudaFree(c->d_scratch);
   for (auto e : c->events) cudaEventDestroy(e);
@@ -238,7 +244,7 @@ int pm_graph_from_slots(pm_ctx* c, uint64_t n_vertices, uint64_t n_slots, const 
                         const uint32_t* dst) {
   if (!c || (n_slots && (!src || !dst))) return fail(c, PM_ERR_ARG, "pm_graph_from_slots: null argument");
   PM_CUDA(c, cudaSetDevice(c->device));
-  state_free(c);
+  state_free(c, /*keep_scratch=*/true);
   uint32_t *d_src = nullptr, *d_dst = nullptr;
   int rc;
   if ((rc = dev_alloc(c, &d_src, n_slots))) return rc;
@@ -259,19 +265,37 @@ int pm_graph_from_csr(pm_ctx* c, uint64_t n_vertices, const uint64_t* rowptr, co
                       const uint64_t* degree_multi) {
   if (!c || !rowptr || !degree_multi) return fail(c, PM_ERR_ARG, "pm_graph_from_csr: null argument");
   PM_CUDA(c, cudaSetDevice(c->device));
-  state_free(c);
+  state_free(c, /*keep_scratch=*/true);
   if (c->n_ranks == 1) {
     if (rowptr[n_vertices] && !col) return fail(c, PM_ERR_ARG, "pm_graph_from_csr: null argument");
     return graph_build_from_host_csr(c, n_vertices, rowptr, col, degree_multi);
   }
   // several ranks: rowptr / col / degree_multi describe the rows of the vertices THIS rank owns
-  // (local row i = vertex i * n_ranks + rank); the rows are re-keyed by slot through the sort based build
+  // (local row i = vertex i * n_ranks + rank).  The adjacency is uploaded as it is, the source of every
+  // slot is expanded on the device and the rows are re-keyed by slot through the sort based build.
   c->V = n_vertices;
   const uint64_t own = n_owned(c), E = rowptr[own];
-  std::vector<uint32_t> src(E), dst(E);
-  for (uint64_t i = 0; i < own; ++i)
-    for (uint64_t j = rowptr[i]; j < rowptr[i + 1]; ++j) { src[j] = (uint32_t)(i * c->n_ranks + c->rank); dst[j] = col[j]; }
-  int rc = pm_graph_from_slots(c, n_vertices, E, src.data(), dst.data());
+  if (E && !col) return fail(c, PM_ERR_ARG, "pm_graph_from_csr: null argument");
+  uint32_t *d_src = nullptr, *d_dst = nullptr;
+  unsigned long long* d_rowptr = nullptr;
+  int rc;
+  if ((rc = dev_alloc(c, &d_src, E)) || (rc = dev_alloc(c, &d_dst, E)) || (rc = dev_alloc(c, &d_rowptr, own + 1))) {
+    dev_free(d_src); dev_free(d_dst); dev_free(d_rowptr);
+    return rc;
+  }
+  cudaError_t e1 = cudaMemcpyAsync(d_rowptr, rowptr, (own + 1) * 8, cudaMemcpyHostToDevice, c->stream);
+  cudaError_t e2 = E ? cudaMemcpyAsync(d_dst, col, E * 4, cudaMemcpyHostToDevice, c->stream) : cudaSuccess;
+  if (e1 == cudaSuccess && e2 == cudaSuccess) {
+    k_csr_expand_sources<<<grid_for(), kBlock, 0, c->stream>>>(d_rowptr, own, (uint32_t)c->n_ranks, (uint32_t)c->rank, d_src);
+    c->launches++;
+    e1 = cudaGetLastError();
+  }
+  if (e1 != cudaSuccess || e2 != cudaSuccess) {
+    dev_free(d_src); dev_free(d_dst); dev_free(d_rowptr);
+    return fail(c, PM_ERR_CUDA, "pm_graph_from_csr: host to device copy failed");
+  }
+  rc = graph_build_from_device_slots(c, n_vertices, E, d_src, d_dst, /*route=*/false);
+  dev_free(d_src); dev_free(d_dst); dev_free(d_rowptr);
   if (rc) return rc;
   std::vector<uint32_t> dm(c->nloc, 0u);
   uint64_t em = 0;
@@ -282,7 +306,7 @@ int pm_graph_from_csr(pm_ctx* c, uint64_t n_vertices, const uint64_t* rowptr, co
 }
 
 int pm_get_kernel_stats(const pm_ctx* c, int bin, pm_kernel_stats_t* out) {
-  if (!c || !out || bin < 0 || bin > 3) return PM_ERR_ARG;
+  if (!c || !out || bin < 0 || bin > 4) return PM_ERR_ARG;
   *out = c->kstat[bin];
   return 0;
 }
@@ -290,7 +314,7 @@ int pm_get_kernel_stats(const pm_ctx* c, int bin, pm_kernel_stats_t* out) {
 int pm_graph_rmat(pm_ctx* c, uint64_t scale, uint64_t gen_ranks) {
   if (!c) return PM_ERR_ARG;
   PM_CUDA(c, cudaSetDevice(c->device));
-  state_free(c);
+  state_free(c, /*keep_scratch=*/true);
   return rmat_build(c, scale, gen_ranks);
 }
 
@@ -476,7 +500,7 @@ int pm_state_reset(pm_ctx* c) {
       if ((rc = dev_alloc(c, &c->fr[b][1], std::min<uint64_t>(NL, c->E / PM_MID_MAX + 1024)))) return rc;
     }
     if ((rc = dev_alloc(c, &c->cnt, 1))) return rc;
-    PM_CUDA(c, cudaMallocHost((void**)&c->h_cnt, sizeof(DevCounters)));
+    if (!c->h_cnt) PM_CUDA(c, cudaMallocHost((void**)&c->h_cnt, sizeof(DevCounters)));
     PM_CUDA(c, cudaMemsetAsync(c->adeg, 0, NL * sizeof(uint32_t), c->stream));
     if (multi) {
       c->dcap = c->nlmax;  // a rank publishes at most one change per owned vertex and step
@@ -495,12 +519,15 @@ int pm_state_reset(pm_ctx* c) {
     // the peer table (G = 1: everything points at this GPU)
     if ((rc = comm_publish(c))) return rc;
   }
-  dev_free(c->rowstat);
-  if (c->h_rowstat) cudaFreeHost(c->h_rowstat);
-  c->h_rowstat = nullptr;
   const int nrow = c->pat.diameter + 1;
-  if ((rc = dev_alloc(c, &c->rowstat, nrow))) return rc;
-  PM_CUDA(c, cudaMallocHost((void**)&c->h_rowstat, nrow * sizeof(RowStat)));
+  if (!c->rowstat || nrow > c->rowstat_cap) {
+    dev_free(c->rowstat);
+    if (c->h_rowstat) cudaFreeHost(c->h_rowstat);
+    c->h_rowstat = nullptr;
+    c->rowstat_cap = std::max(nrow, 64);
+    if ((rc = dev_alloc(c, &c->rowstat, c->rowstat_cap))) return rc;
+    PM_CUDA(c, cudaMallocHost((void**)&c->h_rowstat, c->rowstat_cap * sizeof(RowStat)));
+  }
   while ((int)c->events.size() < nrow + 1) {
     cudaEvent_t e;
     PM_CUDA(c, cudaEventCreate(&e));
@@ -597,7 +624,8 @@ int pm_lcc(pm_ctx* c, int init_step, int* not_finished, pm_counts_t* counts_out)
   cudaStream_t st = c->stream;
   const int D = c->pat.diameter;
   const int grid = grid_for();
-  const bool sm = c->labels_small;  // neighbour labels are streamed next to the ids
+  const bool sm0 = c->labels_small;                 // first scan: neighbour labels are streamed next to the ids (lab0)
+  const bool sm = c->labels_small && c->keep_labw;  // later scans keep the label stream of the working adjacency aligned
   const double t0 = wall_s();
   PM_CUDA(c, cudaMemsetAsync(c->rowstat, 0, D * sizeof(RowStat), st));
   PM_CUDA(c, cudaMemsetAsync(&c->cnt->nf, 0, sizeof(uint32_t), st));
@@ -609,19 +637,19 @@ int pm_lcc(pm_ctx* c, int init_step, int* not_finished, pm_counts_t* counts_out)
     LccArgs a = lcc_args(c, k);
     const int cur = c->cur, nxt = cur ^ 1;
     // kernel classes timed with CUDA events on this stream: 0 = first-superstep scan of the main list,
-    // 1 = later scans of the main list, 2 = CTA-per-row scans
-    const int cls_main = first ? 0 : 1;
+    // 1 = later scans of the main list, 2 = CTA-per-row scans, 4 = the renaming (XLATE) scan
+    const int cls_main = first ? 0 : xlate ? 4 : 1;
     cudaEvent_t* ev = &c->kev2[(size_t)k * 4];
     PM_CUDA(c, cudaEventRecord(ev[0], st));
     if (c->bin_live[0]) {
-      if (first) (sm ? k_lcc_scan<true, true, false> : k_lcc_scan<true, false, false>)<<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], &c->cnt->fr_n[cur][0], 0);
+      if (first) (sm0 ? k_lcc_scan<true, true, false> : k_lcc_scan<true, false, false>)<<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], &c->cnt->fr_n[cur][0], 0);
       else if (xlate) (sm ? k_lcc_scan<false, true, true> : k_lcc_scan<false, false, true>)<<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], &c->cnt->fr_n[cur][0], 0);
       else (sm ? k_lcc_scan<false, true, false> : k_lcc_scan<false, false, false>)<<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], &c->cnt->fr_n[cur][0], 0);
       PM_LAUNCH_CHECK(c);
     }
     PM_CUDA(c, cudaEventRecord(ev[1], st));
     if (c->bin_live[1]) {
-      if (first) (sm ? k_lcc_scan_big<true, true, false> : k_lcc_scan_big<true, false, false>)<<<148, 1024, 0, st>>>(a, c->fr[cur][1], &c->cnt->fr_n[cur][1], 0);
+      if (first) (sm0 ? k_lcc_scan_big<true, true, false> : k_lcc_scan_big<true, false, false>)<<<148, 1024, 0, st>>>(a, c->fr[cur][1], &c->cnt->fr_n[cur][1], 0);
       else if (xlate) (sm ? k_lcc_scan_big<false, true, true> : k_lcc_scan_big<false, false, true>)<<<148, 1024, 0, st>>>(a, c->fr[cur][1], &c->cnt->fr_n[cur][1], 0);
       else (sm ? k_lcc_scan_big<false, true, false> : k_lcc_scan_big<false, false, false>)<<<148, 1024, 0, st>>>(a, c->fr[cur][1], &c->cnt->fr_n[cur][1], 0);
       PM_LAUNCH_CHECK(c);
@@ -764,7 +792,7 @@ int pm_nlcc(pm_ctx* c, int pl, int mode, int* pattern_found, int* token_source_d
   uint2* d_matches = nullptr;
   uint64_t match_cap = 0;
   const int cur = c->cur;
-  const bool sm = c->labels_small;
+  const bool sm = c->labels_small && c->keep_labw;
   uint64_t n_matches = 0, hi = 0, fanout = 0;
   int found = 0;
   // cycle constraints close their last two hops by intersecting E_v with E_s (k_nem1_close_cycle);

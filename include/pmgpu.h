@@ -143,9 +143,11 @@ typedef struct {
  * per rank like the reference's per-rank files.                               */
 int pm_lcc(pm_ctx* ctx, int global_init_step, int* not_finished, pm_counts_t* counts_out);
 
-/* CUDA-event timing of the first-superstep scan kernels (the kernels that walk
- * the pristine adjacency; bin 0: <= 32 slots per row, 8-lane groups; bin 1: <=
- * 4096, one warp per row; bin 2: one CTA per row), accumulated since pm_create. */
+/* CUDA-event timing of the LCC scan kernels on the context's stream, by kernel class, accumulated since
+ * pm_create.  bin 0: first-superstep scan of the main row list (walks the pristine adjacency + label stream);
+ * bin 1: later scans (active edge maps + mask gathers); bin 2: CTA-per-row scans (rows above 4096 slots);
+ * bin 3: the per-pattern initialisation + signature filter; bin 4: the renaming scan (second superstep of the
+ * first call: slots -> compact ids).                                                                       */
 typedef struct {
   uint64_t launches;
   double ms;         /* sum of launch durations                    */

@@ -30,5 +30,5 @@ for s in scales:
         if check:
             t = time.time(); ref = O.Run(g, lab, O.Pattern(d), tds_from_pl=tds, keep_subgraphs=False)
             print("     oracle %.2fs rows_equal %s hazards %s" % (time.time() - t, ref.rows == rows, ref.hazards[:5]), flush=True)
-    for b in range(3):
+    for b in range(5):
         print("  kstat", b, eng.kernel_stats(b))

@@ -100,6 +100,15 @@ def main():
     for nm, spec, tds in (("triangle", PT.triangle(6, 7, 8), 1), ("cycle4", PT.cycle4(5, 6, 7, 8), 1)):
         check("rmat%d/%s" % (scale, nm), lambda: eng.graph_rmat(scale, gen_ranks), lambda: O.Graph.rmat(scale, gen_ranks),
               None, spec, tds)
+    # host CSR round trip: every rank reads its rows back and re-opens the graph from them (pm_graph_from_csr)
+    def reopen_from_host_csr():
+        eng.graph_rmat(scale, gen_ranks)
+        rowptr, col = eng.graph_csr()
+        degm = eng.graph_degree()
+        nv = eng.graph_info()["n_vertices"]
+        eng.graph_from_csr(rowptr, col, degm, n_vertices=nv)
+    check("rmat%d/host_csr/triangle" % scale, reopen_from_host_csr, lambda: O.Graph.rmat(scale, gen_ranks),
+          None, PT.triangle(6, 7, 8), 1)
     flag = [len(failures)]
     dist.broadcast_object_list(flag, src=0)
     eng.close()

@@ -152,7 +152,6 @@ struct pm_ctx {
   uint8_t* lab8 = nullptr;     // [V] labels as bytes when every label is < 64 (degree labels always are)
   unsigned long long* sig = nullptr;  // [V] bit l set iff some distinct neighbour carries label l (labels < 64)
   uint8_t* lab0 = nullptr;     // [Epad] label of the neighbour stored in col0 (labels < 64)
-  uint8_t* labw = nullptr;     // [Epad] label of the neighbour stored in colw
   bool labels_small = false;   // lab8 / sig are valid
   bool has_graph = false, has_labels = false;
 
@@ -170,6 +169,7 @@ struct pm_ctx {
   uint8_t* clsc = nullptr;  // [Vs] label class by compact id (replicated)
   uint32_t* fw = nullptr;   // [Vs / 16] per 16 slots: survivors before them in their tile << 16 | survivor bits (replicated)
   uint32_t* tb = nullptr;   // [tiles] compact id of every 4096-slot tile's first survivor (replicated)
+  uint2* fwx = nullptr;     // [Vs / 16] {compact id of the word's first survivor, survivor bits}: what cid_of_slot reads
   uint32_t cid_off[PM_MAX_RANKS + 1] = {0};  // host copy of the compact id ranges
   uint8_t* cls = nullptr;   // [V] label class (index into the template's distinct labels, PM_NOCLASS = none)
   uint4* fr[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // frontier entry lists [buffer][main, big rows]
@@ -184,10 +184,6 @@ struct pm_ctx {
   pm::RowStat* h_rowstat = nullptr;    // pinned
   int rowstat_cap = 0;                 // rows rowstat / h_rowstat can hold
   bool state_ready = false;
-  // maintain labw (the label stream of the working adjacency) through the scans so that NLCC hops can test the
-  // label without gathering S.  Off by default: with compact ids S is L2 resident and the gather is cheaper than
-  // moving a second stream along with every row compaction (PM_KEEP_LABW=1 switches it back on).
-  bool keep_labw = false;
   bool fuzzy_ids = false;   // the frontier entries of the last run name vertices, not compact ids (pm_run_fuzzy)
 
   // ---- NLCC scratch -----------------------------------------------------------------

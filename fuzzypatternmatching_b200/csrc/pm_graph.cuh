@@ -247,7 +247,6 @@ inline int labels_derive(pm_ctx* c, bool small) {
   dev_free(c->lab8);
   dev_free(c->sig);
   dev_free(c->lab0);
-  dev_free(c->labw);
   c->labels_small = false;
   if (!small) return 0;
   int rc;
@@ -256,7 +255,6 @@ inline int labels_derive(pm_ctx* c, bool small) {
   if ((rc = dev_alloc(c, &c->lab8, Vs, &c->graph_bytes))) return rc;
   if ((rc = dev_alloc(c, &c->sig, c->nloc, &c->graph_bytes))) return rc;
   if ((rc = dev_alloc(c, &c->lab0, c->Epad + 64, &c->graph_bytes))) return rc;
-  if ((rc = dev_alloc(c, &c->labw, c->Epad + 64, &c->graph_bytes))) return rc;
   if ((rc = dev_alloc(c, &big_list, c->Epad / PM_SIG_BIG + 1024))) return rc;
   if ((rc = dev_alloc(c, &big_n, 1))) { dev_free(big_list); return rc; }
   cudaStream_t st = c->stream;
@@ -282,7 +280,6 @@ inline void graph_free(pm_ctx* c) {
   dev_free(c->lab8);
   dev_free(c->sig);
   dev_free(c->lab0);
-  dev_free(c->labw);
   c->labels_small = false;
   dev_free(c->rowblk);
   dev_free(c->deg);

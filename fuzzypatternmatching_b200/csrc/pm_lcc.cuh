@@ -113,13 +113,11 @@ struct LccArgs {
   uint32_t* adeg;
   const uint8_t* cls;
   const uint8_t* lab0;  // [Epad] label of the neighbour in col0 (labels < 64 only)
-  uint8_t* labw;        // [Epad] same for colw, moved along by the row compaction
   DevCounters* cnt;
   RowStat* row;   // accumulator of this superstep
   uint32_t base;  // first compact id of this rank: rank-local arrays (adeg, rowc) are indexed by cid - base
   int par;        // delta inbox the commit of this superstep publishes into
-  const uint32_t* fw;      // slot -> compact id (first scan): survivor bits + in-tile prefix per 16 slots
-  const uint32_t* tb;      // cid of every tile's first survivor
+  const uint2* fwx;        // slot -> compact id, per 16 slots: {cid of the word's first survivor, survivor bits}
 };
 
 // frontier entry: x = compact id, y = row start in sectors (PM_TOMB: the row is in the big-row list),
@@ -165,10 +163,11 @@ __global__ void __launch_bounds__(kBlock) k_apply_deltas(uint16_t* __restrict__ 
 // sector from HBM for 2 useful bytes.  The survivors are therefore renumbered densely, in vertex
 // order, and EVERYTHING after the filter — masks, classes, |E_v|, row starts, the working adjacency,
 // tokens, hash keys — is indexed by that compact id (cid).  The whole mask array then fits in L2.
-//   vid[cid] = slot of the vertex.  slot -> cid needs no table of its own: survivors are numbered in slot
-//   order, so cid(s) = tb[s / 4096] + prefix(s / 16) + popc(bits of word s / 16 below s), read from
-//   fw[s / 16] = (survivors before this word inside its tile) << 16 | (survivor bits of 16 vertices)
-//   and tb[tile] = cid of the tile's first survivor — 4 bytes per 16 vertices, L2 resident.
+//   vid[cid] = slot of the vertex.  slot -> cid: survivors are numbered in slot order, so
+//   cid(s) = fwx[s / 16].x + popc(fwx[s / 16].y & bits below s), fwx[w] = {cid of the word's first survivor,
+//   survivor bits of its 16 vertices} — 8 bytes per 16 vertices, L2 resident, one load per lookup.  It is
+//   assembled from fw[w] = (survivors before the word inside its 4096-slot tile) << 16 | bits (pass 1) and
+//   tb[tile] = cid of the tile's first survivor (pass 2).
 // With several GPUs rank g owns the cids [off[g], off[g+1]) (c_peer.off), numbered by (rank, slot);
 // fw and tb are all-gathered (slot ranges are rank-contiguous and tile aligned).
 // The first scan copies the neighbours it keeps as SLOTS (a kept neighbour that did not survive the
@@ -218,7 +217,9 @@ __global__ void __launch_bounds__(kBlock) k_init_flags(const uint8_t* __restrict
       const uint32_t lw[4] = {l16.x, l16.y, l16.z, l16.w};
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        const uint4 d4 = *reinterpret_cast<const uint4*>(deg + v0 + 4 * g);
+        // with the signature filter on the degrees need not be read: an isolated vertex has an empty signature
+        uint4 d4 = make_uint4(1u, 1u, 1u, 1u);
+        if (!use_sig) d4 = *reinterpret_cast<const uint4*>(deg + v0 + 4 * g);
         const uint32_t dd[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -326,12 +327,12 @@ __global__ void k_tile_offsets(uint32_t* __restrict__ tb, uint32_t tiles_per_ran
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) tb[i] += c_peer.off[i / tiles_per_rank];
 }
 
-// compact id of slot u if it survived the filter, else PM_SENTINEL
-__device__ __forceinline__ uint32_t cid_of_slot(const uint32_t* __restrict__ fw, const uint32_t* __restrict__ tb, uint32_t u) {
-  const uint32_t w = fw[u >> 4];
+// compact id of slot u if it survived the filter, else PM_SENTINEL: one 8-byte load from an L2 resident table
+__device__ __forceinline__ uint32_t cid_of_slot(const uint2* __restrict__ fwx, uint32_t u) {
+  const uint2 w = fwx[u >> 4];
   const uint32_t b = u & 15u;
-  if (!((w >> b) & 1u)) return PM_SENTINEL;
-  return tb[u >> 12] + (w >> 16) + __popc(w & ((1u << b) - 1u));
+  if (!((w.y >> b) & 1u)) return PM_SENTINEL;
+  return w.x + __popc(w.y & ((1u << b) - 1u));
 }
 
 // n_slots: every slot of every rank (replicated per-cid state); [own_lo, own_hi): this rank's slots, which also
@@ -343,6 +344,8 @@ __global__ void __launch_bounds__(kBlock) k_init_assign(const uint8_t* __restric
                                                          uint64_t n_slots, uint32_t own_lo, uint32_t own_hi,
                                                          uint16_t* __restrict__ S, uint8_t* __restrict__ clsc,
                                                          uint32_t* __restrict__ vid, uint32_t* __restrict__ rowc,
+                                                         uint2* __restrict__ fwx,
+                                                         const unsigned long long* __restrict__ sig,
                                                          uint4* fr_main, uint4* fr_big, DevCounters* cnt, int buf) {
   __shared__ uint8_t s_cl[64];
   __shared__ uint16_t s_lm[17];
@@ -354,8 +357,9 @@ __global__ void __launch_bounds__(kBlock) k_init_assign(const uint8_t* __restric
   for (uint64_t wi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; wi < n_words; wi += (uint64_t)gridDim.x * blockDim.x) {
     const uint32_t w = fw[wi];
     uint32_t bits = w & 0xFFFFu;
-    if (!bits) continue;
     uint32_t cid = tb[wi >> 8] + (w >> 16);
+    fwx[wi] = make_uint2(cid, bits);  // the table the renaming scan reads (cid_of_slot)
+    if (!bits) continue;
     for (; bits; bits &= bits - 1, ++cid) {
       const uint32_t slot = (uint32_t)(wi * 16) + (__ffs(bits) - 1);
       const uint32_t c = SMALL ? (uint32_t)s_cl[lab8[slot] & 63] : (uint32_t)cls[slot];
@@ -366,11 +370,25 @@ __global__ void __launch_bounds__(kBlock) k_init_assign(const uint8_t* __restric
       if (slot >= own_lo && slot < own_hi) {
         const uint32_t lcid = cid - off_me, d = deg[slot - own_lo], rb = rowblk[slot - own_lo];
         rowc[lcid] = rb;
+        // behind the signature filter (sig != null) the T_state the first superstep ends with is known here:
+        // heard(v) = OR of the labelmasks of the valid labels in v's signature (see the header above), so the
+        // first scan only has to build the edge map
+        uint32_t tw = lm;
+        if (sig) {
+          const unsigned long long sg = sig[slot - own_lo];
+          const uint32_t NBv = nb_of(lm);
+          uint32_t heard = 0;
+#pragma unroll
+          for (int q = 0; q < 16; ++q)
+            if (q < c_pat.ncls && ((uint32_t)c_pat.LMc[q] & NBv) && ((sg >> (c_pat.clabel[q] & 63ull)) & 1ull))
+              heard |= c_pat.LMc[q];
+          tw = cover_of(lm, heard);
+        }
         if (d <= PM_MID_MAX) {
-          fr_main[lcid] = make_uint4(cid, rb, d, lm);
+          fr_main[lcid] = make_uint4(cid, rb, d, tw);
         } else {
           fr_main[lcid] = make_uint4(cid, PM_TOMB, 0u, 0u);
-          fr_big[atomicAdd(&cnt->fr_n[buf][1], 1u)] = make_uint4(cid, rb, d, lm);
+          fr_big[atomicAdd(&cnt->fr_n[buf][1], 1u)] = make_uint4(cid, rb, d, tw);
         }
       }
     }
@@ -379,22 +397,52 @@ __global__ void __launch_bounds__(kBlock) k_init_assign(const uint8_t* __restric
 
 // ---------------------------------------------------------------------------
 // scan of the main list: every warp takes 32 consecutive entries.
-//   FIRST = first superstep of the first iteration: walk the pristine adjacency
-//   col0 (all deg[v] slots), neighbour mask = labelmask via the label stream / class
-//   array (ee.hpp:519-561 sender, :368-404 receiver) and COPY the survivors into the
-//   working adjacency; otherwise walk keys(E_v) in colw and compact in place.
-//   STREAM = the label of every neighbour travels next to its id (lab0 / labw,
-//   labels < 64): the first superstep then needs no gather at all, and later
-//   compactions keep labw aligned with colw for NLCC.
-// ---------------------------------------------------------------------------
+//   FIRST = first superstep of the first iteration: walk the pristine adjacency col0 (all deg[v] slots); a
+//   neighbour's mask is the labelmask of its label (ee.hpp:519-561 sender, :368-404 receiver) and the kept
+//   neighbours are COPIED into the working adjacency; otherwise walk keys(E_v) in colw and compact in place.
+//   STREAM (FIRST only) = labels are bytes < 64 and the label of every neighbour travels next to its id
+//   (lab0): validity is one bit test against the row's valid-label set and the scan needs no gather at all.
+//   HEARD = accumulate heard(v) and derive T_state from it.  Off only for the first scan behind the signature
+//   filter, whose entries already carry the T_state the first superstep ends with (k_init_assign).
 //   XLATE (with !FIRST) = the first scan after the first superstep: the rows still hold SLOTS (the first scan
-//   copies them as they are, so that its latency-bound row walks carry no extra dependent loads); this scan
-//   renames every neighbour to its compact id while it walks the — by now short — rows, dropping neighbours
-//   that did not survive the filter (their masks are zero: they would be dropped here anyway).
+//   copies them as they are, so that its row walks carry no dependent loads); this scan renames every
+//   neighbour to its compact id while it walks the — by now short — rows, dropping neighbours that did not
+//   survive the filter (their masks are zero: they would be dropped here anyway).
 //   xlate_only: rename and nothing else (a pattern whose LCC call has a single superstep).
-template <bool FIRST, bool STREAM, bool XLATE>
+// ---------------------------------------------------------------------------
+
+// labels a neighbour may carry to be valid for a vertex with template neighbourhood NBv (labels < 64)
+__device__ __forceinline__ unsigned long long valid_labels(uint32_t NBv) {
+  unsigned long long r = 0;
+#pragma unroll
+  for (int q = 0; q < 16; ++q)
+    if (q < c_pat.ncls && ((uint32_t)c_pat.LMc[q] & NBv)) r |= 1ull << (c_pat.clabel[q] & 63ull);
+  return r;
+}
+
+// stable compaction of a lane's four slots: out[0 .. n) = the kept values in order; returns n
+__device__ __forceinline__ uint32_t compact4(const bool (&keep)[4], const uint32_t (&v)[4], uint32_t (&out)[4]) {
+  const uint32_t k0 = keep[0], k1 = keep[1], k2 = keep[2], k3 = keep[3];
+  const uint32_t p2 = k0 + k1;
+  out[0] = k0 ? v[0] : k1 ? v[1] : k2 ? v[2] : v[3];
+  out[1] = (k1 && k0) ? v[1] : (k2 && p2 == 1u) ? v[2] : v[3];
+  out[2] = (k2 && p2 == 2u) ? v[2] : v[3];
+  out[3] = v[3];
+  return p2 + k2 + k3;
+}
+
+// exclusive prefix and total over the warp of a per-lane count in [0, 4]
+__device__ __forceinline__ void warp_prefix4(uint32_t n, uint32_t lt, uint32_t& below, uint32_t& total) {
+  const uint32_t b0 = __ballot_sync(0xffffffffu, n & 1u), b1 = __ballot_sync(0xffffffffu, n & 2u),
+                 b2 = __ballot_sync(0xffffffffu, n & 4u);
+  below = __popc(b0 & lt) + 2u * __popc(b1 & lt) + 4u * __popc(b2 & lt);
+  total = __popc(b0) + 2u * __popc(b1) + 4u * __popc(b2);
+}
+
+template <bool FIRST, bool STREAM, bool XLATE, bool HEARD>
 __global__ void __launch_bounds__(kBlock, 4) k_lcc_scan(LccArgs a, uint4* __restrict__ list,
                                                       const uint32_t* __restrict__ n_ptr, int xlate_only) {
+  static_assert(!(FIRST && XLATE) && (FIRST || !STREAM) && (HEARD || FIRST), "unsupported combination");
   __shared__ uint16_t s_lm[17];
   __shared__ uint16_t s_lml[64];  // label value -> labelmask
   if (threadIdx.x < 17) s_lm[threadIdx.x] = c_pat.LMc[threadIdx.x];
@@ -406,7 +454,6 @@ __global__ void __launch_bounds__(kBlock, 4) k_lcc_scan(LccArgs a, uint4* __rest
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
   const uint32_t* __restrict__ src = FIRST ? a.col0 : a.colw;
-  const uint8_t* __restrict__ lsrc = FIRST ? a.lab0 : a.labw;
   unsigned long long scanned = 0, verts = 0;
   for (uint32_t base = warp * 32; base < n; base += nwarps * 32) {
     const uint32_t idx = base + lane;
@@ -421,6 +468,8 @@ __global__ void __launch_bounds__(kBlock, 4) k_lcc_scan(LccArgs a, uint4* __rest
     }
     uint32_t d = Tv ? e.z : 0u;  // Tv == 0: deactivated by NLCC since the last commit (beta.cpp:990-992)
     const uint32_t NBv = nb_of(Tv);
+    unsigned long long VL = 0;   // FIRST && STREAM: the labels a valid neighbour can carry
+    if (FIRST && STREAM) VL = valid_labels(NBv);
     const uint64_t row = (uint64_t)e.y * 8;
     uint32_t heard = 0, out = 0;
 
@@ -434,43 +483,39 @@ __global__ void __launch_bounds__(kBlock, 4) k_lcc_scan(LccArgs a, uint4* __rest
         l4[c] = 0;
         if ((uint32_t)(4 * c) < d) {
           q[c] = *reinterpret_cast<const uint4*>(src + row + 4 * c);
-          if (STREAM) l4[c] = *reinterpret_cast<const uint32_t*>(lsrc + row + 4 * c);
+          if (STREAM) l4[c] = *reinterpret_cast<const uint32_t*>(a.lab0 + row + 4 * c);
         }
       }
-      uint32_t m[PM_TINY_MAX];
-      uint32_t xl[XLATE ? PM_TINY_MAX : 1];  // XLATE: the neighbours' compact ids
+      uint32_t keepm = 0, flagged = 0;         // slots that stay (bit j); some slot carries an outside flag
+      uint32_t xl[XLATE ? PM_TINY_MAX : 1];    // XLATE: the neighbours' compact ids
 #pragma unroll
       for (int c = 0; c < PM_TINY_MAX / 4; ++c) {
         const uint32_t u[4] = {q[c].x, q[c].y, q[c].z, q[c].w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const int j = 4 * c + k;
-          m[j] = 0;
           if ((uint32_t)j < d) {
             uint32_t uu = u[k] & PM_IDMASK;
-            if (XLATE) {
-              uu = cid_of_slot(a.fw, a.tb, uu);
-              xl[j] = uu;
+            bool valid;
+            uint32_t m = 0;
+            if (FIRST && STREAM) {
+              const uint32_t lab = (l4[c] >> (8 * k)) & 63u;
+              valid = (VL >> lab) & 1ull;
+              if (HEARD) m = s_lml[lab];
+            } else {
+              if (XLATE) {
+                uu = cid_of_slot(a.fwx, uu);
+                xl[j] = uu;
+              }
+              if (FIRST) m = s_lm[a.cls[uu]];
+              else if (!XLATE || uu != PM_SENTINEL) m = xlate_only ? 0xFFFFu : (uint32_t)a.S[uu];
+              valid = xlate_only ? m != 0u : (m & NBv) != 0u;
             }
-            if (FIRST) m[j] = STREAM ? (uint32_t)s_lml[(l4[c] >> (8 * k)) & 63u] : (uint32_t)s_lm[a.cls[uu]];
-            else if (!XLATE || uu != PM_SENTINEL) m[j] = xlate_only ? 0xFFFFu : (uint32_t)a.S[uu];
+            const bool pre = !FIRST && !XLATE && (u[k] >> 31);
+            if (HEARD && valid) heard |= m;
+            if (valid || pre) keepm |= 1u << j;
+            if (pre) flagged = 1;
           }
-        }
-      }
-      // which slots stay (bit j), and whether the row has to be rewritten at all
-      uint32_t keepm = 0, flagged = 0;
-#pragma unroll
-      for (int c = 0; c < PM_TINY_MAX / 4; ++c) {
-        const uint32_t u[4] = {q[c].x, q[c].y, q[c].z, q[c].w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int j = 4 * c + k;
-          const bool act = (uint32_t)j < d;
-          const bool valid = xlate_only ? m[j] != 0u : (m[j] & NBv) != 0u;
-          const bool pre = !FIRST && !XLATE && act && (u[k] >> 31);
-          if (valid) heard |= m[j];
-          if (valid || pre) keepm |= 1u << j;
-          if (pre) flagged = 1;
         }
       }
       out = __popc(keepm);
@@ -484,7 +529,6 @@ __global__ void __launch_bounds__(kBlock, 4) k_lcc_scan(LccArgs a, uint4* __rest
             const int j = 4 * c + k;
             if ((keepm >> j) & 1u) {
               a.colw[row + pos] = XLATE ? xl[j] : (u[k] & PM_IDMASK);
-              if (STREAM && a.labw) a.labw[row + pos] = (uint8_t)(l4[c] >> (8 * k));
               ++pos;
             }
           }
@@ -503,7 +547,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_lcc_scan(LccArgs a, uint4* __rest
       const uint64_t rrow = (uint64_t)__shfl_sync(0xffffffffu, e.y, sl) * 8;
       if (lane * 4 < rd) {
         qn = *reinterpret_cast<const uint4*>(src + rrow + lane * 4);
-        if (STREAM) ln = *reinterpret_cast<const uint32_t*>(lsrc + rrow + lane * 4);
+        if (STREAM) ln = *reinterpret_cast<const uint32_t*>(a.lab0 + rrow + lane * 4);
       }
     }
     while (todo) {
@@ -511,6 +555,8 @@ __global__ void __launch_bounds__(kBlock, 4) k_lcc_scan(LccArgs a, uint4* __rest
       todo &= todo - 1;
       const uint32_t rd = __shfl_sync(0xffffffffu, d, sl);
       const uint32_t rNB = __shfl_sync(0xffffffffu, NBv, sl);
+      unsigned long long rVL = 0;
+      if (FIRST && STREAM) rVL = __shfl_sync(0xffffffffu, VL, sl);
       const uint64_t rrow = (uint64_t)__shfl_sync(0xffffffffu, e.y, sl) * 8;
       uint4 q = qn;
       uint32_t l4 = ln;
@@ -523,10 +569,11 @@ __global__ void __launch_bounds__(kBlock, 4) k_lcc_scan(LccArgs a, uint4* __rest
         ln = 0;
         if (lane * 4 < nd) {
           qn = *reinterpret_cast<const uint4*>(src + nrow + lane * 4);
-          if (STREAM) ln = *reinterpret_cast<const uint32_t*>(lsrc + nrow + lane * 4);
+          if (STREAM) ln = *reinterpret_cast<const uint32_t*>(a.lab0 + nrow + lane * 4);
         }
       }
       uint32_t rheard = 0, rout = 0;
+      uint32_t* __restrict__ dst = a.colw + rrow;
       for (uint32_t p0 = 0; p0 < rd; p0 += 128) {
         const uint32_t j0 = p0 + lane * 4;
         // next pass of this row, fetched before the current one is consumed
@@ -534,63 +581,64 @@ __global__ void __launch_bounds__(kBlock, 4) k_lcc_scan(LccArgs a, uint4* __rest
         uint32_t l2 = 0;
         if (j0 + 128 < rd) {
           q2 = *reinterpret_cast<const uint4*>(src + rrow + j0 + 128);
-          if (STREAM) l2 = *reinterpret_cast<const uint32_t*>(lsrc + rrow + j0 + 128);
+          if (STREAM) l2 = *reinterpret_cast<const uint32_t*>(a.lab0 + rrow + j0 + 128);
         }
         const uint32_t u[4] = {q.x, q.y, q.z, q.w};
-        uint32_t m[4];
         uint32_t wr[4];  // what is stored back: the id as it stands, or (XLATE) the neighbour's compact id
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          m[k] = 0;
-          wr[k] = u[k] & PM_IDMASK;
-          if (j0 + k < rd) {
-            if (XLATE) wr[k] = cid_of_slot(a.fw, a.tb, wr[k]);
-            if (FIRST) m[k] = STREAM ? (uint32_t)s_lml[(l4 >> (8 * k)) & 63u] : (uint32_t)s_lm[a.cls[wr[k]]];
-            else if (!XLATE || wr[k] != PM_SENTINEL) m[k] = xlate_only ? 0xFFFFu : (uint32_t)a.S[wr[k]];
-          }
-        }
         bool keep[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const bool act = j0 + k < rd;
-          const bool valid = xlate_only ? m[k] != 0u : (m[k] & rNB) != 0u;
+          wr[k] = u[k] & PM_IDMASK;
+          uint32_t m = 0;
+          bool valid = false;
+          if (FIRST && STREAM) {
+            const uint32_t lab = (l4 >> (8 * k)) & 63u;
+            valid = act && ((rVL >> lab) & 1ull);
+            if (HEARD) m = s_lml[lab];
+          } else if (act) {
+            if (XLATE) wr[k] = cid_of_slot(a.fwx, wr[k]);
+            if (FIRST) m = s_lm[a.cls[wr[k]]];
+            else if (!XLATE || wr[k] != PM_SENTINEL) m = xlate_only ? 0xFFFFu : (uint32_t)a.S[wr[k]];
+            valid = xlate_only ? m != 0u : (m & rNB) != 0u;
+          }
           const bool pre = !FIRST && !XLATE && act && (u[k] >> 31);
           keep[k] = valid || pre;
-          if (valid) rheard |= m[k];
+          if (HEARD && valid) rheard |= m;
         }
-        uint32_t below = 0, cnt_pass = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint32_t b = __ballot_sync(0xffffffffu, keep[k]);
-          below += __popc(b & lt);
-          cnt_pass += __popc(b);
-        }
+        uint32_t outv[4], below, cnt_pass;
+        const uint32_t nk = compact4(keep, wr, outv);
+        warp_prefix4(nk, lt, below, cnt_pass);
         // all loads of this pass (and of the prefetched next pass, which lies strictly behind every
         // slot written now: writes land at or before slots already read) are complete
-        uint32_t pos = rout + below;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (keep[k]) {
-            a.colw[rrow + pos] = wr[k];
-            if (STREAM && a.labw) a.labw[rrow + pos] = (uint8_t)(l4 >> (8 * k));
-            ++pos;
-          }
+        uint32_t* __restrict__ p = dst + rout + below;
+        if (nk > 0u) p[0] = outv[0];
+        if (nk > 1u) p[1] = outv[1];
+        if (nk > 2u) p[2] = outv[2];
+        if (nk > 3u) p[3] = outv[3];
         rout += cnt_pass;
         q = q2;
         l4 = l2;
       }
+      if (HEARD) {
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) rheard |= __shfl_xor_sync(0xffffffffu, rheard, o);
+        for (int o = 16; o > 0; o >>= 1) rheard |= __shfl_xor_sync(0xffffffffu, rheard, o);
+      }
       if ((int)lane == sl) { heard = rheard; out = rout; }
     }
 
     if (has && live) {
-      const uint32_t T0 = FIRST ? Tv : e.w;
-      uint32_t ts = Tv ? cover_of(T0, heard) : 0u;
-      if (xlate_only) ts = Tv ? e.w : 0u;  // renaming only: T_state stays as it is
-      // a vertex leaves the vertex_state_map (ee.hpp:941-946, :968-970).  In the first
-      // superstep only vertices that heard a valid neighbour ever entered the map (:841-852).
-      if (ts == 0 && (FIRST ? heard != 0u : Tv != 0u)) a.cnt->nf = 1u;
+      uint32_t ts;
+      if (!HEARD) {
+        ts = Tv ? e.w : 0u;  // decided by the signature filter (k_init_assign): never empty
+      } else {
+        const uint32_t T0 = FIRST ? Tv : e.w;
+        ts = Tv ? cover_of(T0, heard) : 0u;
+        if (xlate_only) ts = Tv ? e.w : 0u;  // renaming only: T_state stays as it is
+        // a vertex leaves the vertex_state_map (ee.hpp:941-946, :968-970).  In the first
+        // superstep only vertices that heard a valid neighbour ever entered the map (:841-852).
+        if (ts == 0 && (FIRST ? heard != 0u : Tv != 0u)) a.cnt->nf = 1u;
+      }
       scanned += d;
       verts += Tv != 0u;
       e.z = out;
@@ -611,7 +659,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_lcc_scan(LccArgs a, uint4* __rest
 }
 
 // one CTA per high-degree vertex ("delegates across warps and CTAs")
-template <bool FIRST, bool STREAM, bool XLATE>
+template <bool FIRST, bool STREAM, bool XLATE, bool HEARD>
 __global__ void __launch_bounds__(1024) k_lcc_scan_big(LccArgs a, uint4* __restrict__ list,
                                                         const uint32_t* __restrict__ n_ptr, int xlate_only) {
   __shared__ uint16_t s_lm[17];
@@ -629,6 +677,8 @@ __global__ void __launch_bounds__(1024) k_lcc_scan_big(LccArgs a, uint4* __restr
     const uint32_t Tv = a.S[e.x];
     const uint32_t d = Tv ? e.z : 0u;
     const uint32_t NBv = nb_of(Tv);
+    unsigned long long VL = 0;
+    if (FIRST && STREAM) VL = valid_labels(NBv);
     const uint64_t row = (uint64_t)e.y * 8;
     const uint32_t* __restrict__ src = FIRST ? a.col0 : a.colw;
     uint32_t outp = 0;  // slots kept so far (every thread tracks the same value)
@@ -640,38 +690,34 @@ __global__ void __launch_bounds__(1024) k_lcc_scan_big(LccArgs a, uint4* __restr
       uint32_t l4 = 0;
       if (j0 < d) {
         q = *reinterpret_cast<const uint4*>(src + row + j0);
-        if (STREAM) l4 = *reinterpret_cast<const uint32_t*>((FIRST ? a.lab0 : a.labw) + row + j0);
+        if (STREAM) l4 = *reinterpret_cast<const uint32_t*>(a.lab0 + row + j0);
       }
-      uint32_t u[4] = {q.x, q.y, q.z, q.w};
-      uint32_t m[4];
+      const uint32_t u[4] = {q.x, q.y, q.z, q.w};
       uint32_t wr[4];  // what is stored back: the id as it stands, or (XLATE) the neighbour's compact id
       bool keep[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const bool act = j0 + k < d;
-        m[k] = 0;
         wr[k] = u[k] & PM_IDMASK;
-        if (act) {
-          if (XLATE) wr[k] = cid_of_slot(a.fw, a.tb, wr[k]);
-          if (FIRST) m[k] = STREAM ? (uint32_t)s_lml[(l4 >> (8 * k)) & 63u] : (uint32_t)s_lm[a.cls[wr[k]]];
-          else if (!XLATE || wr[k] != PM_SENTINEL) m[k] = xlate_only ? 0xFFFFu : (uint32_t)a.S[wr[k]];
+        uint32_t m = 0;
+        bool valid = false;
+        if (FIRST && STREAM) {
+          const uint32_t lab = (l4 >> (8 * k)) & 63u;
+          valid = act && ((VL >> lab) & 1ull);
+          if (HEARD) m = s_lml[lab];
+        } else if (act) {
+          if (XLATE) wr[k] = cid_of_slot(a.fwx, wr[k]);
+          if (FIRST) m = s_lm[a.cls[wr[k]]];
+          else if (!XLATE || wr[k] != PM_SENTINEL) m = xlate_only ? 0xFFFFu : (uint32_t)a.S[wr[k]];
+          valid = xlate_only ? m != 0u : (m & NBv) != 0u;
         }
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const bool act = j0 + k < d;
-        const bool valid = xlate_only ? m[k] != 0u : (m[k] & NBv) != 0u;
         const bool pre = !FIRST && !XLATE && act && (u[k] >> 31);
         keep[k] = valid || pre;
-        if (valid) heard |= m[k];
+        if (HEARD && valid) heard |= m;
       }
-      uint32_t below = 0, wtotal = 0;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const uint32_t b = __ballot_sync(0xffffffffu, keep[k]);
-        below += __popc(b & lt);
-        wtotal += __popc(b);
-      }
+      uint32_t outv[4], below, wtotal;
+      const uint32_t nk = compact4(keep, wr, outv);
+      warp_prefix4(nk, lt, below, wtotal);
       if (lane == 0) s_wcnt[wid] = wtotal;
       __syncthreads();  // every warp has read its slots of this pass
       uint32_t wbase = outp, ptotal = 0;
@@ -680,14 +726,11 @@ __global__ void __launch_bounds__(1024) k_lcc_scan_big(LccArgs a, uint4* __restr
         if (w < wid) wbase += cw;
         ptotal += cw;
       }
-      uint32_t pos = wbase + below;
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (keep[k]) {
-          a.colw[row + pos] = wr[k];
-          if (STREAM && a.labw) a.labw[row + pos] = (uint8_t)(l4 >> (8 * k));
-          ++pos;
-        }
+      uint32_t* __restrict__ p = a.colw + row + wbase + below;
+      if (nk > 0u) p[0] = outv[0];
+      if (nk > 1u) p[1] = outv[1];
+      if (nk > 2u) p[2] = outv[2];
+      if (nk > 3u) p[3] = outv[3];
       outp += ptotal;
       __syncthreads();  // s_wcnt may be overwritten by the next pass only after everyone has read it
     }
@@ -698,10 +741,15 @@ __global__ void __launch_bounds__(1024) k_lcc_scan_big(LccArgs a, uint4* __restr
     if (threadIdx.x == 0) {
       uint32_t h = 0;
       for (uint32_t w = 0; w < nw; ++w) h |= s_heard[w];
-      const uint32_t T0 = FIRST ? Tv : e.w;
-      uint32_t ts = Tv ? cover_of(T0, h) : 0u;
-      if (xlate_only) ts = Tv ? e.w : 0u;  // renaming only: T_state stays as it is
-      if (ts == 0 && (FIRST ? h != 0u : Tv != 0u)) a.cnt->nf = 1u;
+      uint32_t ts;
+      if (!HEARD) {
+        ts = Tv ? e.w : 0u;
+      } else {
+        const uint32_t T0 = FIRST ? Tv : e.w;
+        ts = Tv ? cover_of(T0, h) : 0u;
+        if (xlate_only) ts = Tv ? e.w : 0u;  // renaming only: T_state stays as it is
+        if (ts == 0 && (FIRST ? h != 0u : Tv != 0u)) a.cnt->nf = 1u;
+      }
       uint4 e2 = e;
       e2.z = outp;
       e2.w = ts;

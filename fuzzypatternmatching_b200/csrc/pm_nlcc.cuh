@@ -43,14 +43,12 @@ __constant__ NlcConst c_nlc;
 // every vertex below is named by its COMPACT ID (see pm_lcc.cuh); `rowblk` is the row start by local compact id
 // A neighbour u can take hop h iff bit I[h] of S[u] is set: S[u] is always a subset of labelmask(label[u]),
 // so the bit test implies the label test of the reference (nem_1.hpp:557-581) and no class gather is needed.
-// STREAM kernels additionally skip the S gather of neighbours whose label (labw) rules the hop out.
 struct NlcArgs {
   const uint32_t* rowblk;
   uint32_t* colw;
   const uint16_t* S;
   const uint32_t* adeg;
   const uint8_t* cls;
-  const uint8_t* labw;  // label of the neighbour stored in colw (STREAM kernels)
   uint8_t* ok;
   uint32_t* src_list;
   unsigned long long* hset;
@@ -278,7 +276,7 @@ __global__ void __launch_bounds__(kBlock) k_nem1_final_cycle(NlcArgs a, int hlev
 // ---------------------------------------------------------------------------
 // nem_1: advance the tokens of level hlevel (accepted at hop hn-1) to hop hn
 // ---------------------------------------------------------------------------
-template <bool FINAL, bool STREAM>
+template <bool FINAL>
 __global__ void __launch_bounds__(kBlock) k_nem1_expand(NlcArgs a, int hlevel, int hn) {
   __shared__ uint2 s_stage[FINAL ? 1 : (kBlock / 32) * PM_STAGE_CAP];
   WarpStage stage{s_stage + (FINAL ? 0 : (threadIdx.x >> 5) * PM_STAGE_CAP), 0u};
@@ -288,7 +286,6 @@ __global__ void __launch_bounds__(kBlock) k_nem1_expand(NlcArgs a, int hlevel, i
   const uint32_t gl = lane % GROUP, gw = lane / GROUP;
   const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-  const uint32_t want_lab = c_nlc.lab[hn];
   unsigned long long fan = 0;
   for (uint64_t base = lo + warp * 4; base < hi; base += nwarps * 4) {
     const uint64_t t = base + gw;
@@ -309,19 +306,15 @@ __global__ void __launch_bounds__(kBlock) k_nem1_expand(NlcArgs a, int hlevel, i
     for (uint32_t p = 0; p < maxp; ++p) {
       const uint32_t j0 = p * GROUP * 4 + gl * 4;
       uint4 q = make_uint4(0, 0, 0, 0);
-      uint32_t l4 = 0;
       if (j0 < d) {
         q = *reinterpret_cast<const uint4*>(a.colw + row + j0);
-        if (STREAM) l4 = *reinterpret_cast<const uint32_t*>(a.labw + row + j0);
       }
       const uint32_t u[4] = {q.x & PM_IDMASK, q.y & PM_IDMASK, q.z & PM_IDMASK, q.w & PM_IDMASK};
       bool pass_static[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         pass_static[k] = false;
-        // the label test needs no gather when the neighbour's label travels with the edge
         bool may = j0 + k < d;
-        if (STREAM) may = may && ((l4 >> (8 * k)) & 0xffu) == want_lab;
         if (may) {
           const uint32_t su = a.S[u[k]];
           pass_static[k] = su != 0 && ((su >> c_nlc.I[hn]) & 1u);
@@ -373,7 +366,6 @@ __global__ void __launch_bounds__(kBlock) k_nem1_expand(NlcArgs a, int hlevel, i
 // Success acknowledges the source and flags the edge E_s[u] the token would have
 // come back on (nem_1.hpp:764-770).
 // ---------------------------------------------------------------------------
-template <bool STREAM>
 __global__ void __launch_bounds__(kBlock) k_nem1_close_cycle(NlcArgs a, int hlevel, int hn) {
   const uint64_t lo = a.cnt->lvl[hlevel], hi = a.cnt->lvl[hlevel + 1];
   constexpr int GROUP = 8;
@@ -381,7 +373,6 @@ __global__ void __launch_bounds__(kBlock) k_nem1_close_cycle(NlcArgs a, int hlev
   const uint32_t gl = lane % GROUP, gw = lane / GROUP;
   const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-  const uint32_t want_lab = c_nlc.lab[hn];
   unsigned long long fan = 0;
   for (uint64_t base = lo + warp * 4; base < hi; base += nwarps * 4) {
     const uint64_t t = base + gw;
@@ -406,16 +397,13 @@ __global__ void __launch_bounds__(kBlock) k_nem1_close_cycle(NlcArgs a, int hlev
     for (uint32_t p = 0; p < maxp; ++p) {
       const uint32_t j0 = p * GROUP * 4 + gl * 4;
       uint4 q = make_uint4(0, 0, 0, 0);
-      uint32_t l4 = 0;
       if (j0 < d) {
         q = *reinterpret_cast<const uint4*>(a.colw + row + j0);
-        if (STREAM) l4 = *reinterpret_cast<const uint32_t*>(a.labw + row + j0);
       }
       const uint32_t u[4] = {q.x & PM_IDMASK, q.y & PM_IDMASK, q.z & PM_IDMASK, q.w & PM_IDMASK};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         bool may = j0 + k < d && u[k] != s;  // the source cannot relay (nem_1.hpp:174-177)
-        if (STREAM) may = may && ((l4 >> (8 * k)) & 0xffu) == want_lab;
         if (!may) continue;
         uint32_t b = 0, e = ds;
         while (b < e) {  // rows stay ascending: compaction is stable
@@ -455,11 +443,10 @@ __device__ __forceinline__ bool hist_rule(const uint32_t (&hist)[16], int hp, ui
   return false;               // "invalid value" branches drop the token
 }
 
-template <bool FINAL, bool STREAM>
+template <bool FINAL>
 __global__ void __launch_bounds__(kBlock) k_tds_expand(NlcArgs a, int hlevel, int hn) {
   __shared__ uint2 s_stage[(kBlock / 32) * PM_STAGE_CAP];
   WarpStage stage{s_stage + (threadIdx.x >> 5) * PM_STAGE_CAP, 0u};
-  const uint32_t want_lab = c_nlc.lab[hn];
   const uint64_t lo = a.cnt->lvl[hlevel], hi = a.cnt->lvl[hlevel + 1];
   constexpr int GROUP = 8;
   const uint32_t lane = threadIdx.x & 31;
@@ -496,10 +483,8 @@ __global__ void __launch_bounds__(kBlock) k_tds_expand(NlcArgs a, int hlevel, in
     for (uint32_t p = 0; p < maxp; ++p) {
       const uint32_t j0 = p * GROUP * 4 + gl * 4;
       uint4 q = make_uint4(0, 0, 0, 0);
-      uint32_t l4 = 0;
       if (j0 < d) {
         q = *reinterpret_cast<const uint4*>(a.colw + row + j0);
-        if (STREAM) l4 = *reinterpret_cast<const uint32_t*>(a.labw + row + j0);
       }
       const uint32_t u[4] = {q.x & PM_IDMASK, q.y & PM_IDMASK, q.z & PM_IDMASK, q.w & PM_IDMASK};
       bool acc[4];
@@ -509,7 +494,6 @@ __global__ void __launch_bounds__(kBlock) k_tds_expand(NlcArgs a, int hlevel, in
         acc[k] = false;
         tok[k] = make_uint2((uint32_t)t, u[k]);
         bool may = j0 + k < d;
-        if (STREAM) may = may && ((l4 >> (8 * k)) & 0xffu) == want_lab;
         if (may) {
           const uint32_t su = a.S[u[k]];
           acc[k] = su != 0 && ((su >> c_nlc.I[hn]) & 1u);

@@ -110,12 +110,10 @@ __device__ __forceinline__ void route_tokens(const NlcArgs& a, const bool (&flag
 // ---------------------------------------------------------------------------
 #define PM_CE_TAG 0x8000000000000000ull  // vertex slots are < 2^31, so (vertex, source) keys never carry bit 63
 
-template <bool STREAM>
 __global__ void __launch_bounds__(kBlock) k_close_keys_m(NlcArgs a, const uint4* __restrict__ l0,
                                                           const uint4* __restrict__ l1, int cur, int hn) {
   const uint32_t c0 = a.cnt->fr_n[cur][0], c1 = a.cnt->fr_n[cur][1];
   const uint32_t total = c0 + c1;
-  const uint32_t want_lab = c_nlc.lab[hn];
   constexpr int GROUP = 8;
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t gl = lane % GROUP, gw = lane / GROUP;
@@ -142,10 +140,8 @@ __global__ void __launch_bounds__(kBlock) k_close_keys_m(NlcArgs a, const uint4*
     for (uint32_t p = 0; p < maxp; ++p) {
       const uint32_t j0 = p * GROUP * 4 + gl * 4;
       uint4 q = make_uint4(0, 0, 0, 0);
-      uint32_t l4 = 0;
       if (j0 < d) {
         q = *reinterpret_cast<const uint4*>(a.colw + row + j0);
-        if (STREAM) l4 = *reinterpret_cast<const uint32_t*>(a.labw + row + j0);
       }
       const uint32_t u[4] = {q.x & PM_IDMASK, q.y & PM_IDMASK, q.z & PM_IDMASK, q.w & PM_IDMASK};
       bool ok[4];
@@ -153,7 +149,6 @@ __global__ void __launch_bounds__(kBlock) k_close_keys_m(NlcArgs a, const uint4*
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         bool may = j0 + k < d && u[k] != s;
-        if (STREAM) may = may && ((l4 >> (8 * k)) & 0xffu) == want_lab;
         ok[k] = false;
         if (may) {
           const uint32_t su = a.S[u[k]];
@@ -231,7 +226,7 @@ __device__ __forceinline__ bool close_edge_known(const NlcArgs& a, uint32_t s, u
 //   MODE 0: interior hop, 1: final hop of a path or (generic) cycle constraint, 2: closing two hops of a cycle
 //   first: the tokens are the sources themselves (no aggregation test)
 // ---------------------------------------------------------------------------
-template <int MODE, bool STREAM>
+template <int MODE>
 __global__ void __launch_bounds__(kBlock) k_nem1_hop_m(NlcArgs a, int hn, int first) {
   const TokSrc src = tok_src(a);
   const uint2* __restrict__ in = c_peer.tin[a.par ^ 1][c_peer.rank];
@@ -240,7 +235,6 @@ __global__ void __launch_bounds__(kBlock) k_nem1_hop_m(NlcArgs a, int hn, int fi
   const uint32_t gl = lane % GROUP, gw = lane / GROUP;
   const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-  const uint32_t want_lab = c_nlc.lab[hn];
   unsigned long long fan = 0, accepted = 0;
   for (uint64_t base = warp * 4; base < src.total; base += nwarps * 4) {
     const uint64_t t = base + gw;
@@ -271,10 +265,8 @@ __global__ void __launch_bounds__(kBlock) k_nem1_hop_m(NlcArgs a, int hn, int fi
     for (uint32_t p = 0; p < maxp; ++p) {
       const uint32_t j0 = p * GROUP * 4 + gl * 4;
       uint4 q = make_uint4(0, 0, 0, 0);
-      uint32_t l4 = 0;
       if (j0 < d) {
         q = *reinterpret_cast<const uint4*>(a.colw + row + j0);
-        if (STREAM) l4 = *reinterpret_cast<const uint32_t*>(a.labw + row + j0);
       }
       const uint32_t u[4] = {q.x & PM_IDMASK, q.y & PM_IDMASK, q.z & PM_IDMASK, q.w & PM_IDMASK};
       bool pass[4];
@@ -282,7 +274,6 @@ __global__ void __launch_bounds__(kBlock) k_nem1_hop_m(NlcArgs a, int hn, int fi
       for (int k = 0; k < 4; ++k) {
         pass[k] = false;
         bool may = j0 + k < d;
-        if (STREAM) may = may && ((l4 >> (8 * k)) & 0xffu) == want_lab;
         if (MODE == 2) may = may && u[k] != s;
         if (!may) continue;
         if (MODE == 2) {
@@ -333,13 +324,12 @@ __global__ void __launch_bounds__(kBlock) k_nem1_hop_m(NlcArgs a, int hn, int fi
 // Completed walks (FINAL) are records of n words routed to the owner of the last vertex, which is
 // where the reference writes the subgraph line (tds_batch_1.hpp:684-693).
 // ---------------------------------------------------------------------------
-template <bool FINAL, bool STREAM>
+template <bool FINAL>
 __global__ void __launch_bounds__(kBlock) k_tds_hop_m(NlcArgs a, int hn) {
   const TokSrc src = tok_src(a);
   const int n = c_nlc.n;
   const unsigned long long rcap = c_peer.tcap * 2ull / (unsigned long long)n;  // records per region
   const uint32_t* __restrict__ in = reinterpret_cast<const uint32_t*>(c_peer.tin[a.par ^ 1][c_peer.rank]);
-  const uint32_t want_lab = c_nlc.lab[hn];
   constexpr int GROUP = 8;
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t gl = lane % GROUP, gw = lane / GROUP;
@@ -379,17 +369,14 @@ __global__ void __launch_bounds__(kBlock) k_tds_hop_m(NlcArgs a, int hn) {
     for (uint32_t p = 0; p < maxp; ++p) {
       const uint32_t j0 = p * GROUP * 4 + gl * 4;
       uint4 q = make_uint4(0, 0, 0, 0);
-      uint32_t l4 = 0;
       if (j0 < d) {
         q = *reinterpret_cast<const uint4*>(a.colw + row + j0);
-        if (STREAM) l4 = *reinterpret_cast<const uint32_t*>(a.labw + row + j0);
       }
       const uint32_t u[4] = {q.x & PM_IDMASK, q.y & PM_IDMASK, q.z & PM_IDMASK, q.w & PM_IDMASK};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         bool acc = false;
         bool may = j0 + k < d;
-        if (STREAM) may = may && ((l4 >> (8 * k)) & 0xffu) == want_lab;
         if (may) {
           const uint32_t su = a.S[u[k]];
           acc = su != 0 && ((su >> c_nlc.I[hn]) & 1u);

@@ -34,17 +34,17 @@ LccArgs lcc_args(pm_ctx* c, int row) {
   LccArgs a;
   a.col0 = c->col0; a.colw = c->colw;
   a.S = c->S; a.adeg = c->adeg; a.cls = c->cls; a.cnt = c->cnt;
-  a.lab0 = c->lab0; a.labw = c->keep_labw ? c->labw : nullptr;
+  a.lab0 = c->lab0;
   a.row = c->rowstat + row;
   a.base = c->cid_off[c->rank];
   a.par = c->step_parity;
-  a.fw = c->fw; a.tb = c->tb;
+  a.fwx = c->fwx;
   return a;
 }
 
 NlcArgs nlc_args(pm_ctx* c, uint2* matches, uint64_t match_cap) {
   NlcArgs a;
-  a.rowblk = c->rowc; a.colw = c->colw; a.S = c->S; a.adeg = c->adeg; a.cls = c->clsc; a.labw = c->labw;
+  a.rowblk = c->rowc; a.colw = c->colw; a.S = c->S; a.adeg = c->adeg; a.cls = c->clsc;
   a.ok = c->ok; a.src_list = c->src_list; a.hset = c->hset; a.hset_mask = c->hset_use - 1;
   a.pool = c->pool; a.pool_cap = c->pool_cap; a.matches = matches; a.match_cap = match_cap;
   a.cnt = c->cnt;
@@ -101,7 +101,7 @@ void state_free(pm_ctx* c, bool keep_scratch = false) {
   c->h_step = nullptr;
   c->dcap = c->tcap = 0;
   dev_free(c->S); dev_free(c->adeg); dev_free(c->cls);
-  dev_free(c->rowc); dev_free(c->vid); dev_free(c->clsc); dev_free(c->fw); dev_free(c->tb);
+  dev_free(c->rowc); dev_free(c->vid); dev_free(c->clsc); dev_free(c->fw); dev_free(c->tb); dev_free(c->fwx);
   for (int b = 0; b < 2; ++b) for (int k = 0; k < 2; ++k) dev_free(c->fr[b][k]);
   dev_free(c->cnt); dev_free(c->ok); dev_free(c->src_list);
   if (!keep) {
@@ -171,7 +171,6 @@ int pm_create(pm_ctx** out, int device) {
   if (cudaSetDevice(device) != cudaSuccess) return PM_ERR_CUDA;
   pm_ctx* c = new pm_ctx();
   c->device = device;
-  if (const char* e = getenv("PM_KEEP_LABW")) c->keep_labw = e[0] == '1';
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete c;
     return PM_ERR_CUDA;
@@ -491,6 +490,7 @@ int pm_state_reset(pm_ctx* c) {
     if ((rc = dev_alloc(c, &c->clsc, Vs))) return rc;
     if ((rc = dev_alloc(c, &c->fw, Vs / 16 + 2))) return rc;
     if ((rc = dev_alloc(c, &c->tb, Vs / PM_TILE + 2))) return rc;
+    if ((rc = dev_alloc(c, &c->fwx, Vs / 16 + 2))) return rc;
     if ((rc = dev_alloc(c, &c->cls, Vs))) return rc;
     if ((rc = dev_alloc(c, &c->ok, Vs))) return rc;
     if ((rc = dev_alloc(c, &c->src_list, NL))) return rc;
@@ -588,12 +588,12 @@ int pm_state_reset(pm_ctx* c) {
     // pass 3: per-cid state of every survivor (all ranks), row starts and frontier entries of the local ones
     if (small)
       k_init_assign<true><<<grid, kBlock, 0, c->stream>>>(c->lab8, nullptr, c->deg, c->rowblk, c->fw, c->tb, multi ? Vs : NL,
-                                                          (uint32_t)base, (uint32_t)(base + NL), c->S, c->clsc, c->vid, c->rowc,
-                                                          c->fr[0][0], c->fr[0][1], c->cnt, 0);
+                                                          (uint32_t)base, (uint32_t)(base + NL), c->S, c->clsc, c->vid, c->rowc, c->fwx,
+                                                          use_sig ? c->sig : nullptr, c->fr[0][0], c->fr[0][1], c->cnt, 0);
     else
       k_init_assign<false><<<grid, kBlock, 0, c->stream>>>(nullptr, c->cls, c->deg, c->rowblk, c->fw, c->tb, multi ? Vs : NL,
-                                                           (uint32_t)base, (uint32_t)(base + NL), c->S, c->clsc, c->vid, c->rowc,
-                                                           c->fr[0][0], c->fr[0][1], c->cnt, 0);
+                                                           (uint32_t)base, (uint32_t)(base + NL), c->S, c->clsc, c->vid, c->rowc, c->fwx,
+                                                           nullptr, c->fr[0][0], c->fr[0][1], c->cnt, 0);
     PM_LAUNCH_CHECK(c);
   }
   PM_CUDA(c, cudaEventRecord(c->kev[3][1], c->stream));
@@ -624,8 +624,8 @@ int pm_lcc(pm_ctx* c, int init_step, int* not_finished, pm_counts_t* counts_out)
   cudaStream_t st = c->stream;
   const int D = c->pat.diameter;
   const int grid = grid_for();
-  const bool sm0 = c->labels_small;                 // first scan: neighbour labels are streamed next to the ids (lab0)
-  const bool sm = c->labels_small && c->keep_labw;  // later scans keep the label stream of the working adjacency aligned
+  const bool sm0 = c->labels_small;      // first scan: neighbour labels are streamed next to the ids (lab0)
+  const bool ts_known = c->filter_done;  // ... and the signature filter already settled every entry's T_state
   const double t0 = wall_s();
   PM_CUDA(c, cudaMemsetAsync(c->rowstat, 0, D * sizeof(RowStat), st));
   PM_CUDA(c, cudaMemsetAsync(&c->cnt->nf, 0, sizeof(uint32_t), st));
@@ -642,16 +642,24 @@ int pm_lcc(pm_ctx* c, int init_step, int* not_finished, pm_counts_t* counts_out)
     cudaEvent_t* ev = &c->kev2[(size_t)k * 4];
     PM_CUDA(c, cudaEventRecord(ev[0], st));
     if (c->bin_live[0]) {
-      if (first) (sm0 ? k_lcc_scan<true, true, false> : k_lcc_scan<true, false, false>)<<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], &c->cnt->fr_n[cur][0], 0);
-      else if (xlate) (sm ? k_lcc_scan<false, true, true> : k_lcc_scan<false, false, true>)<<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], &c->cnt->fr_n[cur][0], 0);
-      else (sm ? k_lcc_scan<false, true, false> : k_lcc_scan<false, false, false>)<<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], &c->cnt->fr_n[cur][0], 0);
+      uint4* l = c->fr[cur][0];
+      const uint32_t* np = &c->cnt->fr_n[cur][0];
+      if (first && ts_known) k_lcc_scan<true, true, false, false><<<grid, kBlock, 0, st>>>(a, l, np, 0);
+      else if (first && sm0) k_lcc_scan<true, true, false, true><<<grid, kBlock, 0, st>>>(a, l, np, 0);
+      else if (first) k_lcc_scan<true, false, false, true><<<grid, kBlock, 0, st>>>(a, l, np, 0);
+      else if (xlate) k_lcc_scan<false, false, true, true><<<grid, kBlock, 0, st>>>(a, l, np, 0);
+      else k_lcc_scan<false, false, false, true><<<grid, kBlock, 0, st>>>(a, l, np, 0);
       PM_LAUNCH_CHECK(c);
     }
     PM_CUDA(c, cudaEventRecord(ev[1], st));
     if (c->bin_live[1]) {
-      if (first) (sm0 ? k_lcc_scan_big<true, true, false> : k_lcc_scan_big<true, false, false>)<<<148, 1024, 0, st>>>(a, c->fr[cur][1], &c->cnt->fr_n[cur][1], 0);
-      else if (xlate) (sm ? k_lcc_scan_big<false, true, true> : k_lcc_scan_big<false, false, true>)<<<148, 1024, 0, st>>>(a, c->fr[cur][1], &c->cnt->fr_n[cur][1], 0);
-      else (sm ? k_lcc_scan_big<false, true, false> : k_lcc_scan_big<false, false, false>)<<<148, 1024, 0, st>>>(a, c->fr[cur][1], &c->cnt->fr_n[cur][1], 0);
+      uint4* l = c->fr[cur][1];
+      const uint32_t* np = &c->cnt->fr_n[cur][1];
+      if (first && ts_known) k_lcc_scan_big<true, true, false, false><<<148, 1024, 0, st>>>(a, l, np, 0);
+      else if (first && sm0) k_lcc_scan_big<true, true, false, true><<<148, 1024, 0, st>>>(a, l, np, 0);
+      else if (first) k_lcc_scan_big<true, false, false, true><<<148, 1024, 0, st>>>(a, l, np, 0);
+      else if (xlate) k_lcc_scan_big<false, false, true, true><<<148, 1024, 0, st>>>(a, l, np, 0);
+      else k_lcc_scan_big<false, false, false, true><<<148, 1024, 0, st>>>(a, l, np, 0);
       PM_LAUNCH_CHECK(c);
     }
     PM_CUDA(c, cudaEventRecord(ev[2], st));
@@ -673,9 +681,9 @@ int pm_lcc(pm_ctx* c, int init_step, int* not_finished, pm_counts_t* counts_out)
     // no second scan in this call: rename the rows of the vertices still in the map to compact ids now
     LccArgs a = lcc_args(c, 0);
     const int cur = c->cur;
-    (sm ? k_lcc_scan<false, true, true> : k_lcc_scan<false, false, true>)<<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], &c->cnt->fr_n[cur][0], 1);
+    k_lcc_scan<false, false, true, true><<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], &c->cnt->fr_n[cur][0], 1);
     PM_LAUNCH_CHECK(c);
-    (sm ? k_lcc_scan_big<false, true, true> : k_lcc_scan_big<false, false, true>)<<<148, 1024, 0, st>>>(a, c->fr[cur][1], &c->cnt->fr_n[cur][1], 1);
+    k_lcc_scan_big<false, false, true, true><<<148, 1024, 0, st>>>(a, c->fr[cur][1], &c->cnt->fr_n[cur][1], 1);
     PM_LAUNCH_CHECK(c);
   }
   PM_CUDA(c, cudaEventRecord(c->events[D], st));
@@ -792,7 +800,6 @@ int pm_nlcc(pm_ctx* c, int pl, int mode, int* pattern_found, int* token_source_d
   uint2* d_matches = nullptr;
   uint64_t match_cap = 0;
   const int cur = c->cur;
-  const bool sm = c->labels_small && c->keep_labw;
   uint64_t n_matches = 0, hi = 0, fanout = 0;
   int found = 0;
   // cycle constraints close their last two hops by intersecting E_v with E_s (k_nem1_close_cycle);
@@ -816,7 +823,7 @@ int pm_nlcc(pm_ctx* c, int pl, int mode, int* pattern_found, int* token_source_d
     if (multi && close2) {
       // every rank learns the qualifying (source, neighbour) pairs of the closing hop (k_close_keys_m)
       NlcArgs ka = nlc_args(c, nullptr, 0);
-      (sm ? k_close_keys_m<true> : k_close_keys_m<false>)<<<grid, kBlock, 0, st>>>(ka, c->fr[cur][0], c->fr[cur][1], cur, (int)k.C);
+      k_close_keys_m<<<grid, kBlock, 0, st>>>(ka, c->fr[cur][0], c->fr[cur][1], cur, (int)k.C);
       PM_LAUNCH_CHECK(c);
       k_close_keys_count_m<<<1, 1, 0, st>>>(c->cnt);
       PM_LAUNCH_CHECK(c);
@@ -837,18 +844,18 @@ int pm_nlcc(pm_ctx* c, int pl, int mode, int* pattern_found, int* token_source_d
         const bool fin = hn == (int)k.C + 1;
         const int lvl = hn - 1;
         if (close2 && hn == (int)k.C) {
-          (sm ? k_nem1_close_cycle<true> : k_nem1_close_cycle<false>)<<<grid, kBlock, 0, st>>>(a, lvl, hn);
+          k_nem1_close_cycle<<<grid, kBlock, 0, st>>>(a, lvl, hn);
           PM_LAUNCH_CHECK(c);
           break;
         }
         if (tds) {
-          if (fin) (sm ? k_tds_expand<true, true> : k_tds_expand<true, false>)<<<grid, kBlock, 0, st>>>(a, lvl, hn);
-          else (sm ? k_tds_expand<false, true> : k_tds_expand<false, false>)<<<grid, kBlock, 0, st>>>(a, lvl, hn);
+          if (fin) k_tds_expand<true><<<grid, kBlock, 0, st>>>(a, lvl, hn);
+          else k_tds_expand<false><<<grid, kBlock, 0, st>>>(a, lvl, hn);
         } else if (fin) {
           if (k.valid_cycle) k_nem1_final_cycle<<<grid, kBlock, 0, st>>>(a, lvl, hn);
-          else (sm ? k_nem1_expand<true, true> : k_nem1_expand<true, false>)<<<grid, kBlock, 0, st>>>(a, lvl, hn);
+          else k_nem1_expand<true><<<grid, kBlock, 0, st>>>(a, lvl, hn);
         } else {
-          (sm ? k_nem1_expand<false, true> : k_nem1_expand<false, false>)<<<grid, kBlock, 0, st>>>(a, lvl, hn);
+          k_nem1_expand<false><<<grid, kBlock, 0, st>>>(a, lvl, hn);
         }
         PM_LAUNCH_CHECK(c);
         if (!fin) {
@@ -874,15 +881,15 @@ int pm_nlcc(pm_ctx* c, int pl, int mode, int* pattern_found, int* token_source_d
         a = nlc_args(c, nullptr, 0);
         bool last = fin;
         if (tds) {
-          if (fin) (sm ? k_tds_hop_m<true, true> : k_tds_hop_m<true, false>)<<<grid, kBlock, 0, st>>>(a, hn);
-          else (sm ? k_tds_hop_m<false, true> : k_tds_hop_m<false, false>)<<<grid, kBlock, 0, st>>>(a, hn);
+          if (fin) k_tds_hop_m<true><<<grid, kBlock, 0, st>>>(a, hn);
+          else k_tds_hop_m<false><<<grid, kBlock, 0, st>>>(a, hn);
         } else if (close2 && hn == (int)k.C) {
-          (sm ? k_nem1_hop_m<2, true> : k_nem1_hop_m<2, false>)<<<grid, kBlock, 0, st>>>(a, hn, first);
+          k_nem1_hop_m<2><<<grid, kBlock, 0, st>>>(a, hn, first);
           last = true;
         } else if (fin) {
-          (sm ? k_nem1_hop_m<1, true> : k_nem1_hop_m<1, false>)<<<grid, kBlock, 0, st>>>(a, hn, first);
+          k_nem1_hop_m<1><<<grid, kBlock, 0, st>>>(a, hn, first);
         } else {
-          (sm ? k_nem1_hop_m<0, true> : k_nem1_hop_m<0, false>)<<<grid, kBlock, 0, st>>>(a, hn, first);
+          k_nem1_hop_m<0><<<grid, kBlock, 0, st>>>(a, hn, first);
         }
         PM_LAUNCH_CHECK(c);
         mark();

@@ -259,3 +259,97 @@ def test_run_fuzzy_path_matches_oracle(oracle, eng):
     v, t = eng.active_vertices()
     rv, rt = ref.active_vertices()
     assert np.array_equal(v, rv) and np.array_equal(t, rt) and len(rv) > 0
+
+
+def test_edge_cases_match_oracle(oracle, eng):
+    """Degenerate and ragged inputs: nothing matches, a single edge, only self loops, isolated vertices,
+    vertex counts that straddle the 16-slot words and 4096-slot tiles of the compact id tables, a template
+    without non-local constraints."""
+    from fuzzypatternmatching_b200 import patterns as PT
+    tri = PT.triangle(1, 2, 3)
+    lcc_only_spec = {"labels": [1, 2, 1], "edges": [(0, 1), (1, 2)], "diameter": 2, "constraints": []}
+    # no vertex carries a template label
+    edges = cases.random_multigraph(1, 50, 200)
+    _compare(oracle, eng, 50, edges, np.full(50, 9, dtype=np.uint64), tri, 1)
+    # labels match but the structure never does (a path, no triangle)
+    path = [(i, i + 1) for i in range(29)]
+    _compare(oracle, eng, 30, path, np.array([1 + i % 3 for i in range(30)], dtype=np.uint64), tri, 1)
+    # a single edge, and a graph of self loops only
+    _compare(oracle, eng, 2, [(0, 1)], np.array([1, 2], dtype=np.uint64), lcc_only_spec, 0)
+    _compare(oracle, eng, 5, [(i, i) for i in range(5)], np.array([1, 2, 1, 2, 1], dtype=np.uint64), lcc_only_spec, 0)
+    # one real triangle among isolated vertices; n just above a word / a tile of the slot -> compact id tables
+    for n in (17, 4097, 8193):
+        labels = np.full(n, 7, dtype=np.uint64)
+        a, b, c = n - 1, n // 2, 0
+        labels[[a, b, c]] = [1, 2, 3]
+        ref = _compare(oracle, eng, n, [(a, b), (b, c), (a, c)], labels, tri, 1)
+        assert ref.rows[-1][3] == 3 and ref.rows[-1][4] == 6
+    # LCC only (no pattern_non_local_constraint rows) on a random graph
+    for seed in range(4):
+        edges = cases.random_multigraph(seed + 70, 200, 900)
+        _compare(oracle, eng, 200, edges, cases.random_labels(seed + 70, 200, [1, 2]), lcc_only_spec, 0)
+
+
+@pytest.mark.parametrize("which", ["tree", "cycle4"])
+def test_full_size_properties(eng, which):
+    """BASELINE configs[1] / [2] sizes (R-MAT scale 25), where the oracle is out of reach: size-independent
+    properties of the reference's fixed point — determinism, symmetry of the active edge set, every edge
+    joins two active vertices, the local constraint holds at every active vertex, one more LCC call removes
+    nothing, and every enumerated walk runs over active edges."""
+    from fuzzypatternmatching_b200 import patterns as PT
+    spec, tds_from = (PT.RMAT_LOG2_TREE, 4) if which == "tree" else (PT.cycle4(5, 6, 7, 8), 1)
+    d = cases.pattern_dir(spec)
+    eng.graph_rmat(25, 1024)
+    eng.labels_degree_log2()
+    labels = eng.labels_get()
+    eng.pattern_load_dir(d)
+    eng.run(tds_from_pl=tds_from)
+    rows = eng.rows()
+    v, t = eng.active_vertices()
+    e = eng.active_edges()
+    sub = [eng.subgraphs(pl) for pl in range(len(spec["constraints"]))]
+    assert rows[-1][3] == len(v) and rows[-1][4] == len(e)
+    # vertex and edge counts never grow along the rows
+    assert all(rows[i + 1][3] <= rows[i][3] and rows[i + 1][4] <= rows[i][4] for i in range(len(rows) - 1))
+    # determinism: a second search gives the same rows and sets
+    eng.run(tds_from_pl=tds_from)
+    v2, t2 = eng.active_vertices()
+    assert eng.rows() == rows and np.array_equal(v, v2) and np.array_equal(t, t2) and np.array_equal(e, eng.active_edges())
+    # the fixed point: one more LCC call neither removes a vertex nor an edge
+    nf, counts = eng.label_propagation_pattern_matching_bsp(False)
+    assert not nf and all(c[0] == len(v) and c[1] == len(e) for c in counts)
+    if len(v) == 0:
+        return
+    assert np.all(t != 0) and np.all(np.diff(v.astype(np.int64)) > 0)
+    mask = dict(zip(v.tolist(), t.tolist()))
+    es = set(map(tuple, e.tolist()))
+    assert len(es) == len(e)
+    nbrs = {}
+    for a, b in es:
+        assert (b, a) in es and a in mask and b in mask
+        nbrs.setdefault(a, []).append(b)
+    # template side
+    n_t = len(spec["labels"])
+    tn = [[] for _ in range(n_t)]
+    for a, b in spec["edges"]:
+        tn[a].append(b)
+        tn[b].append(a)
+    for x, m in mask.items():
+        heard = 0
+        for y in nbrs.get(x, []):
+            heard |= mask[y]
+        for p in range(n_t):
+            if (m >> p) & 1:
+                assert int(labels[x]) == spec["labels"][p]
+                assert all((heard >> q) & 1 for q in tn[p]), "local constraint violated"
+    # enumerated walks (TDS constraints) run over active edges and carry the walk's labels
+    for pl, k in enumerate(spec["constraints"]):
+        if not k.get("tds") or pl < tds_from:
+            continue
+        w = k["walk"]
+        for r in sub[pl].tolist():
+            assert len(r) == len(w)
+            for i, x in enumerate(r):
+                assert int(labels[x]) == spec["labels"][w[i]]
+            for i in range(len(r) - 1):
+                assert (r[i], r[i + 1]) in es

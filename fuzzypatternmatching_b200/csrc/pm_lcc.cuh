@@ -445,10 +445,17 @@ __global__ void __launch_bounds__(kBlock, 4) k_lcc_scan(LccArgs a, uint4* __rest
   static_assert(!(FIRST && XLATE) && (FIRST || !STREAM) && (HEARD || FIRST), "unsupported combination");
   __shared__ uint16_t s_lm[17];
   __shared__ uint16_t s_lml[64];  // label value -> labelmask
+  // per warp, the 32 rows of the batch in flight: {row start (sectors), |E_v|, first chunk, NB(T_v)}, valid-label
+  // set, slots kept so far, masks heard so far, and the lanes that own the long rows in order
+  __shared__ uint4 s_rowp[kBlock / 32][32];
+  __shared__ unsigned long long s_vl[(FIRST && STREAM) ? kBlock / 32 : 1][32];
+  __shared__ uint32_t s_rout[kBlock / 32][32];
+  __shared__ uint32_t s_hrd[HEARD ? kBlock / 32 : 1][32];
+  __shared__ uint8_t s_nz[kBlock / 32][32];
   if (threadIdx.x < 17) s_lm[threadIdx.x] = c_pat.LMc[threadIdx.x];
   if (threadIdx.x < 64) s_lml[threadIdx.x] = c_pat.LMc[c_pat.cls_of_label[threadIdx.x]];
   __syncthreads();
-  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const uint32_t lt = lanemask_lt();
   const uint32_t n = *n_ptr;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -536,56 +543,66 @@ __global__ void __launch_bounds__(kBlock, 4) k_lcc_scan(LccArgs a, uint4* __rest
       }
     }
 
-    // ---- longer rows: the whole warp walks one row at a time -------------------------------
-    uint32_t todo = __ballot_sync(0xffffffffu, d > PM_TINY_MAX);
-    // first pass of the first row is fetched ahead, like every following row's
-    uint4 qn = make_uint4(PM_SENTINEL, PM_SENTINEL, PM_SENTINEL, PM_SENTINEL);
-    uint32_t ln = 0;
-    if (todo) {
-      const int sl = __ffs(todo) - 1;
-      const uint32_t rd = __shfl_sync(0xffffffffu, d, sl);
-      const uint64_t rrow = (uint64_t)__shfl_sync(0xffffffffu, e.y, sl) * 8;
-      if (lane * 4 < rd) {
-        qn = *reinterpret_cast<const uint4*>(src + rrow + lane * 4);
-        if (STREAM) ln = *reinterpret_cast<const uint32_t*>(a.lab0 + rrow + lane * 4);
-      }
+    // ---- longer rows: their 4-slot chunks are laid end to end and dealt to the lanes, 32 chunks per pass, so
+    // a pass is full whatever the row lengths are (candidate rows of 32..255 slots would leave a warp-per-row
+    // pass half empty).  Row parameters travel through shared memory; the store offset inside a row is a
+    // segmented prefix over the lanes plus the row's running count.
+    const uint32_t nch = d > PM_TINY_MAX ? (d + 3u) >> 2 : 0u;
+    uint32_t cum = nch;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, cum, o);
+      if (lane >= (uint32_t)o) cum += t;
     }
-    while (todo) {
-      const int sl = __ffs(todo) - 1;
-      todo &= todo - 1;
-      const uint32_t rd = __shfl_sync(0xffffffffu, d, sl);
-      const uint32_t rNB = __shfl_sync(0xffffffffu, NBv, sl);
-      unsigned long long rVL = 0;
-      if (FIRST && STREAM) rVL = __shfl_sync(0xffffffffu, VL, sl);
-      const uint64_t rrow = (uint64_t)__shfl_sync(0xffffffffu, e.y, sl) * 8;
-      uint4 q = qn;
-      uint32_t l4 = ln;
-      // prefetch the first pass of the next long row of this warp
-      if (todo) {
-        const int nl = __ffs(todo) - 1;
-        const uint32_t nd = __shfl_sync(0xffffffffu, d, nl);
-        const uint64_t nrow = (uint64_t)__shfl_sync(0xffffffffu, e.y, nl) * 8;
-        qn = make_uint4(PM_SENTINEL, PM_SENTINEL, PM_SENTINEL, PM_SENTINEL);
-        ln = 0;
-        if (lane * 4 < nd) {
-          qn = *reinterpret_cast<const uint4*>(src + nrow + lane * 4);
-          if (STREAM) ln = *reinterpret_cast<const uint32_t*>(a.lab0 + nrow + lane * 4);
+    const uint32_t C = __shfl_sync(0xffffffffu, cum, 31);  // chunks of this batch
+    if (C) {
+      const uint32_t first = cum - nch;                    // my row's first chunk
+      const uint32_t longrows = __ballot_sync(0xffffffffu, nch != 0u);
+      __syncwarp();
+      s_rowp[wid][lane] = make_uint4(e.y, d, first, NBv);
+      if (FIRST && STREAM) s_vl[wid][lane] = VL;
+      s_rout[wid][lane] = 0u;
+      if (HEARD) s_hrd[wid][lane] = 0u;
+      if (nch) s_nz[wid][__popc(longrows & lt)] = (uint8_t)lane;
+      __syncwarp();
+      const uint32_t le = lt | (1u << lane);
+      // one pass ahead: which row a lane's chunk belongs to, and the chunk itself
+      uint32_t rN = 0, hN = 0, jN = 0, dN = 0, lN = 0;
+      uint64_t rowN = 0;
+      uint4 qN = make_uint4(PM_SENTINEL, PM_SENTINEL, PM_SENTINEL, PM_SENTINEL);
+      auto fetch = [&](uint32_t g0) {
+        // rows whose first chunk lies in this pass (bit = lane that gets it), long rows that started before it
+        const uint32_t hb = (nch && first >= g0 && first < g0 + 32u) ? 1u << (first - g0) : 0u;
+        hN = __reduce_or_sync(0xffffffffu, hb);
+        const uint32_t before = __popc(__ballot_sync(0xffffffffu, nch && first < g0));
+        const uint32_t k = before + __popc(hN & le);  // my chunk's row is the k-th long row of the batch (k >= 1)
+        rN = s_nz[wid][k - 1u];
+        const uint4 rp = s_rowp[wid][rN];
+        const uint32_t g = g0 + lane;
+        dN = g < C ? rp.y : 0u;
+        jN = (g - rp.z) * 4u;
+        rowN = (uint64_t)rp.x * 8;
+        qN = make_uint4(PM_SENTINEL, PM_SENTINEL, PM_SENTINEL, PM_SENTINEL);
+        lN = 0u;
+        if (jN < dN) {
+          qN = *reinterpret_cast<const uint4*>(src + rowN + jN);
+          if (STREAM) lN = *reinterpret_cast<const uint32_t*>(a.lab0 + rowN + jN);
         }
-      }
-      uint32_t rheard = 0, rout = 0;
-      uint32_t* __restrict__ dst = a.colw + rrow;
-      for (uint32_t p0 = 0; p0 < rd; p0 += 128) {
-        const uint32_t j0 = p0 + lane * 4;
-        // next pass of this row, fetched before the current one is consumed
-        uint4 q2 = make_uint4(PM_SENTINEL, PM_SENTINEL, PM_SENTINEL, PM_SENTINEL);
-        uint32_t l2 = 0;
-        if (j0 + 128 < rd) {
-          q2 = *reinterpret_cast<const uint4*>(src + rrow + j0 + 128);
-          if (STREAM) l2 = *reinterpret_cast<const uint32_t*>(a.lab0 + rrow + j0 + 128);
-        }
+      };
+      fetch(0u);
+      for (uint32_t g0 = 0; g0 < C; g0 += 32u) {
+        const uint32_t r = rN, H = hN, j0 = jN, rd = dN, l4 = lN;
+        const uint64_t rrow = rowN;
+        const uint4 q = qN;
+        if (g0 + 32u < C) fetch(g0 + 32u);  // the next pass is on its way while this one is worked on
+        uint32_t rNB = 0;
+        unsigned long long rVL = 0;
+        if (FIRST && STREAM) rVL = s_vl[wid][r];
+        else rNB = s_rowp[wid][r].w;
         const uint32_t u[4] = {q.x, q.y, q.z, q.w};
         uint32_t wr[4];  // what is stored back: the id as it stands, or (XLATE) the neighbour's compact id
         bool keep[4];
+        uint32_t hv = 0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const bool act = j0 + k < rd;
@@ -604,27 +621,40 @@ __global__ void __launch_bounds__(kBlock, 4) k_lcc_scan(LccArgs a, uint4* __rest
           }
           const bool pre = !FIRST && !XLATE && act && (u[k] >> 31);
           keep[k] = valid || pre;
-          if (HEARD && valid) rheard |= m;
+          if (HEARD && valid) hv |= m;
         }
-        uint32_t outv[4], below, cnt_pass;
+        uint32_t outv[4], below, total;
         const uint32_t nk = compact4(keep, wr, outv);
-        warp_prefix4(nk, lt, below, cnt_pass);
-        // all loads of this pass (and of the prefetched next pass, which lies strictly behind every
-        // slot written now: writes land at or before slots already read) are complete
-        uint32_t* __restrict__ p = dst + rout + below;
+        warp_prefix4(nk, lt, below, total);
+        // every load of this pass is complete (the counts depend on them); the prefetched pass lies strictly
+        // behind every slot written now: a row's writes land at or before slots of it already read
+        const uint32_t hl = 31u - __clz((H | 1u) & le);  // first lane of my row's segment in this pass
+        const uint32_t off = below - __shfl_sync(0xffffffffu, below, hl);
+        const uint32_t rout = s_rout[wid][r];
+        uint32_t* __restrict__ p = a.colw + rrow + rout + off;
         if (nk > 0u) p[0] = outv[0];
         if (nk > 1u) p[1] = outv[1];
         if (nk > 2u) p[2] = outv[2];
         if (nk > 3u) p[3] = outv[3];
-        rout += cnt_pass;
-        q = q2;
-        l4 = l2;
-      }
-      if (HEARD) {
+        const bool last = rd != 0u && (lane == 31u || ((H >> (lane + 1u)) & 1u) || g0 + lane + 1u == C);
+        if (HEARD) {  // OR over the lanes of my segment
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) rheard |= __shfl_xor_sync(0xffffffffu, rheard, o);
+          for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, hv, o);
+            if (lane >= (uint32_t)o + hl) hv |= t;
+          }
+        }
+        __syncwarp();  // every lane has read its row's running count
+        if (last) {
+          s_rout[wid][r] = rout + off + nk;
+          if (HEARD) s_hrd[wid][r] |= hv;
+        }
+        __syncwarp();
       }
-      if ((int)lane == sl) { heard = rheard; out = rout; }
+      if (nch) {
+        out = s_rout[wid][lane];
+        if (HEARD) heard = s_hrd[wid][lane];
+      }
     }
 
     if (has && live) {

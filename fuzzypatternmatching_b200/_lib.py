@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpmgpu.so")
+# PMGPU_LIB: another build of the same library (kernel tuning experiments); the default is the in-tree build
+LIB_PATH = os.environ.get("PMGPU_LIB") or os.path.join(_HERE, "libpmgpu.so")
 
 PM_NLCC_NEM1, PM_NLCC_TDS = 0, 1
 PM_COMM_ID_BYTES = 128

@@ -22,7 +22,6 @@
 #define PM_MAX_RANKS 8           // GPUs of one NVSwitch box
 
 // degree bins (current active degree) -> kernel shape
-#define PM_TINY_MAX 16       // <= 16 slots: one THREAD per vertex (four uint4 loads)
 #define PM_MID_MAX 4096u    // <= 4096 slots: one warp per vertex
                             // larger: one CTA per vertex
 

@@ -26,10 +26,9 @@
 // Frontier.  The vertices still in the vertex_state_map are kept as a list of
 // 16-byte ENTRIES {local row, row start (sectors), |E_v|, T_state}: a scan streams
 // its entries (coalesced), needs no dependent gather before it can fetch the row,
-// and writes its result (new |E_v|, new T_state) back into the entry.  Rows of up to
-// PM_TINY_MAX slots are handled by ONE thread each (32 independent rows in flight per
-// warp: these scans are latency bound, not bandwidth bound), longer rows by the whole
-// warp with the next row's first pass prefetched, rows above PM_MID_MAX by a CTA.
+// and writes its result (new |E_v|, new T_state) back into the entry.  A warp takes 32
+// consecutive entries and deals the 4-slot chunks of their rows to its lanes, 32 chunks
+// per pass with the next pass prefetched; rows above PM_MID_MAX slots get a CTA each.
 #pragma once
 
 #include "pm_common.cuh"
@@ -477,77 +476,13 @@ __global__ void __launch_bounds__(kBlock, 4) k_lcc_scan(LccArgs a, uint4* __rest
     const uint32_t NBv = nb_of(Tv);
     unsigned long long VL = 0;   // FIRST && STREAM: the labels a valid neighbour can carry
     if (FIRST && STREAM) VL = valid_labels(NBv);
-    const uint64_t row = (uint64_t)e.y * 8;
     uint32_t heard = 0, out = 0;
 
-    // ---- rows of up to PM_TINY_MAX slots: one thread each --------------------------------
-    if (d != 0u && d <= PM_TINY_MAX) {
-      uint4 q[PM_TINY_MAX / 4];
-      uint32_t l4[PM_TINY_MAX / 4];
-#pragma unroll
-      for (int c = 0; c < PM_TINY_MAX / 4; ++c) {
-        q[c] = make_uint4(PM_SENTINEL, PM_SENTINEL, PM_SENTINEL, PM_SENTINEL);
-        l4[c] = 0;
-        if ((uint32_t)(4 * c) < d) {
-          q[c] = *reinterpret_cast<const uint4*>(src + row + 4 * c);
-          if (STREAM) l4[c] = *reinterpret_cast<const uint32_t*>(a.lab0 + row + 4 * c);
-        }
-      }
-      uint32_t keepm = 0, flagged = 0;         // slots that stay (bit j); some slot carries an outside flag
-      uint32_t xl[XLATE ? PM_TINY_MAX : 1];    // XLATE: the neighbours' compact ids
-#pragma unroll
-      for (int c = 0; c < PM_TINY_MAX / 4; ++c) {
-        const uint32_t u[4] = {q[c].x, q[c].y, q[c].z, q[c].w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int j = 4 * c + k;
-          if ((uint32_t)j < d) {
-            uint32_t uu = u[k] & PM_IDMASK;
-            bool valid;
-            uint32_t m = 0;
-            if (FIRST && STREAM) {
-              const uint32_t lab = (l4[c] >> (8 * k)) & 63u;
-              valid = (VL >> lab) & 1ull;
-              if (HEARD) m = s_lml[lab];
-            } else {
-              if (XLATE) {
-                uu = cid_of_slot(a.fwx, uu);
-                xl[j] = uu;
-              }
-              if (FIRST) m = s_lm[a.cls[uu]];
-              else if (!XLATE || uu != PM_SENTINEL) m = xlate_only ? 0xFFFFu : (uint32_t)a.S[uu];
-              valid = xlate_only ? m != 0u : (m & NBv) != 0u;
-            }
-            const bool pre = !FIRST && !XLATE && (u[k] >> 31);
-            if (HEARD && valid) heard |= m;
-            if (valid || pre) keepm |= 1u << j;
-            if (pre) flagged = 1;
-          }
-        }
-      }
-      out = __popc(keepm);
-      if (FIRST || XLATE || out != d || flagged) {
-        uint32_t pos = 0;
-#pragma unroll
-        for (int c = 0; c < PM_TINY_MAX / 4; ++c) {
-          const uint32_t u[4] = {q[c].x, q[c].y, q[c].z, q[c].w};
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int j = 4 * c + k;
-            if ((keepm >> j) & 1u) {
-              a.colw[row + pos] = XLATE ? xl[j] : (u[k] & PM_IDMASK);
-              ++pos;
-            }
-          }
-        }
-      }
-    }
-
-    // ---- longer rows: their 4-slot chunks are laid end to end and dealt to the lanes, 32 chunks per pass, so
-    // a pass is full whatever the row lengths are (candidate rows of 32..255 slots would leave a warp-per-row
-    // pass half empty).  Row parameters travel through shared memory; the store offset inside a row is a
-    // segmented prefix over the lanes plus the row's running count.
-    const uint32_t nch = d > PM_TINY_MAX ? (d + 3u) >> 2 : 0u;
+    // The 4-slot chunks of the batch's 32 rows are laid end to end and dealt to the lanes, 32 chunks per pass, so
+    // a pass is full whatever the row lengths are (a thread per short row wastes sectors, a warp per row of
+    // 32..255 slots leaves the pass half empty).  Row parameters travel through shared memory; the store offset
+    // inside a row is a segmented prefix over the lanes plus the row's running count.
+    const uint32_t nch = (d + 3u) >> 2;
     uint32_t cum = nch;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {

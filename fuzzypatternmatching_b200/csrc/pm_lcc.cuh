@@ -351,16 +351,41 @@ __global__ void __launch_bounds__(kBlock) k_init_assign(const uint8_t* __restric
   if (threadIdx.x < 64) s_cl[threadIdx.x] = c_pat.cls_of_label[threadIdx.x];
   if (threadIdx.x < 17) s_lm[threadIdx.x] = c_pat.LMc[threadIdx.x];
   __syncthreads();
+  // A warp takes 32 words = 512 consecutive slots (never across a tile).  Their survivors have CONSECUTIVE compact
+  // ids, so after the lanes have listed the survivors' slots in shared memory, lane j handles survivor j: the
+  // per-cid stores (masks, classes, slots, row starts, frontier entries) are coalesced and the lanes stay busy
+  // however the survivors are spread over the words.
+  __shared__ uint32_t s_slot[kBlock / 32][512];
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const uint32_t off_me = c_peer.off[c_peer.rank];
   const uint64_t n_words = (n_slots + 15) / 16;
-  for (uint64_t wi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; wi < n_words; wi += (uint64_t)gridDim.x * blockDim.x) {
-    const uint32_t w = fw[wi];
-    uint32_t bits = w & 0xFFFFu;
-    uint32_t cid = tb[wi >> 8] + (w >> 16);
-    fwx[wi] = make_uint2(cid, bits);  // the table the renaming scan reads (cid_of_slot)
-    if (!bits) continue;
-    for (; bits; bits &= bits - 1, ++cid) {
-      const uint32_t slot = (uint32_t)(wi * 16) + (__ffs(bits) - 1);
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t w0 = warp * 32; w0 < n_words; w0 += nwarps * 32) {
+    const uint64_t wi = w0 + lane;
+    uint32_t bits = 0, cid0 = 0;
+    if (wi < n_words) {
+      const uint32_t w = fw[wi];
+      bits = w & 0xFFFFu;
+      cid0 = tb[wi >> 8] + (w >> 16);
+      fwx[wi] = make_uint2(cid0, bits);  // the table the renaming scan reads (cid_of_slot)
+    }
+    const uint32_t cnt_w = __popc(bits);
+    uint32_t incl = cnt_w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= (uint32_t)o) incl += t;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    const uint32_t cid_first = __shfl_sync(0xffffffffu, cid0, 0);  // cid of the window's first survivor
+    if (total == 0u) continue;
+    __syncwarp();
+    uint32_t at = incl - cnt_w;
+    for (uint32_t rest = bits; rest; rest &= rest - 1, ++at) s_slot[wid][at] = (uint32_t)(wi * 16) + (__ffs(rest) - 1);
+    __syncwarp();
+    for (uint32_t j = lane; j < total; j += 32) {
+      const uint32_t slot = s_slot[wid][j], cid = cid_first + j;
       const uint32_t c = SMALL ? (uint32_t)s_cl[lab8[slot] & 63] : (uint32_t)cls[slot];
       const uint32_t lm = s_lm[c];
       vid[cid] = slot;

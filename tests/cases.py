@@ -67,3 +67,27 @@ def engine_summary(eng, n_constraints):
                 vertices=list(zip(v.tolist(), t.tolist())),
                 edges=[tuple(x) for x in eng.active_edges().tolist()],
                 subgraphs=[sorted(map(tuple, eng.subgraphs(pl).tolist())) for pl in range(n_constraints)])
+
+
+def edge_cases():
+    """(name, n, undirected edges, labels, spec, tds_from_pl): degenerate and ragged inputs — nothing matches, a single
+    edge, only self loops, isolated vertices, vertex counts that straddle the 16-slot words and 4096-slot tiles of the
+    compact id tables, a template without non-local constraints."""
+    tri = PT.triangle(1, 2, 3)
+    lcc_only = {"labels": [1, 2, 1], "edges": [(0, 1), (1, 2)], "diameter": 2, "constraints": []}
+    out = [
+        ("no_template_label", 50, random_multigraph(1, 50, 200), np.full(50, 9, dtype=np.uint64), tri, 1),
+        ("labels_match_structure_never", 30, [(i, i + 1) for i in range(29)],
+         np.array([1 + i % 3 for i in range(30)], dtype=np.uint64), tri, 1),
+        ("single_edge", 2, [(0, 1)], np.array([1, 2], dtype=np.uint64), lcc_only, 0),
+        ("self_loops_only", 5, [(i, i) for i in range(5)], np.array([1, 2, 1, 2, 1], dtype=np.uint64), lcc_only, 0),
+    ]
+    for n in (17, 4097, 8193):
+        labels = np.full(n, 7, dtype=np.uint64)
+        a, b, c = n - 1, n // 2, 0
+        labels[[a, b, c]] = [1, 2, 3]
+        out.append(("one_triangle_among_%d_isolated" % n, n, [(a, b), (b, c), (a, c)], labels, tri, 1))
+    for seed in range(4):
+        out.append(("lcc_only_seed%d" % seed, 200, random_multigraph(seed + 70, 200, 900),
+                    random_labels(seed + 70, 200, [1, 2]), lcc_only, 0))
+    return out

@@ -262,32 +262,11 @@ def test_run_fuzzy_path_matches_oracle(oracle, eng):
 
 
 def test_edge_cases_match_oracle(oracle, eng):
-    """Degenerate and ragged inputs: nothing matches, a single edge, only self loops, isolated vertices,
-    vertex counts that straddle the 16-slot words and 4096-slot tiles of the compact id tables, a template
-    without non-local constraints."""
-    from fuzzypatternmatching_b200 import patterns as PT
-    tri = PT.triangle(1, 2, 3)
-    lcc_only_spec = {"labels": [1, 2, 1], "edges": [(0, 1), (1, 2)], "diameter": 2, "constraints": []}
-    # no vertex carries a template label
-    edges = cases.random_multigraph(1, 50, 200)
-    _compare(oracle, eng, 50, edges, np.full(50, 9, dtype=np.uint64), tri, 1)
-    # labels match but the structure never does (a path, no triangle)
-    path = [(i, i + 1) for i in range(29)]
-    _compare(oracle, eng, 30, path, np.array([1 + i % 3 for i in range(30)], dtype=np.uint64), tri, 1)
-    # a single edge, and a graph of self loops only
-    _compare(oracle, eng, 2, [(0, 1)], np.array([1, 2], dtype=np.uint64), lcc_only_spec, 0)
-    _compare(oracle, eng, 5, [(i, i) for i in range(5)], np.array([1, 2, 1, 2, 1], dtype=np.uint64), lcc_only_spec, 0)
-    # one real triangle among isolated vertices; n just above a word / a tile of the slot -> compact id tables
-    for n in (17, 4097, 8193):
-        labels = np.full(n, 7, dtype=np.uint64)
-        a, b, c = n - 1, n // 2, 0
-        labels[[a, b, c]] = [1, 2, 3]
-        ref = _compare(oracle, eng, n, [(a, b), (b, c), (a, c)], labels, tri, 1)
-        assert ref.rows[-1][3] == 3 and ref.rows[-1][4] == 6
-    # LCC only (no pattern_non_local_constraint rows) on a random graph
-    for seed in range(4):
-        edges = cases.random_multigraph(seed + 70, 200, 900)
-        _compare(oracle, eng, 200, edges, cases.random_labels(seed + 70, 200, [1, 2]), lcc_only_spec, 0)
+    """Degenerate and ragged inputs (tests/cases.py: edge_cases)."""
+    for name, n, edges, labels, spec, tds_from in cases.edge_cases():
+        ref = _compare(oracle, eng, n, edges, labels, spec, tds_from)
+        if name.startswith("one_triangle"):
+            assert ref.rows[-1][3] == 3 and ref.rows[-1][4] == 6, name
 
 
 @pytest.mark.parametrize("which", ["tree", "cycle4"])

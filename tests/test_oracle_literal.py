@@ -54,3 +54,26 @@ def test_hazard_counters_fire_on_order_dependent_template(oracle):
         r, _ = _both(oracle, spec, [1, 2], -1, seed, 40, 200, sched_seeds=())
         fired += int(r.hazards[0] + r.hazards[1] > 0)
     assert fired > 0
+
+
+def test_edge_cases_equal_literal_execution(oracle):
+    """The degenerate inputs of the GPU parity suite, oracle against the literal asynchronous execution."""
+    for name, n, edges, labels, spec, tds_from in cases.edge_cases():
+        if n > 5000:
+            continue  # the literal executor is pure Python
+        d = cases.pattern_dir(spec)
+        g = oracle.Graph.from_undirected(n, edges)
+        r = oracle.Run(g, labels, oracle.Pattern(d), tds_from_pl=tds_from, max_iterations=50)
+        want = cases.run_summary(r)
+        assert not r.hazards[:5].any(), name
+        slots = []
+        for a, b in edges:
+            slots += [(a, b), (b, a)]
+        for s in (0, 1):
+            L = LiteralRun(n, slots, labels.tolist(), PatternFiles(d), seed=17 + s, tds_from_pl=tds_from)
+            assert not L.errors, name
+            assert L.rows == want["rows"], name
+            assert L.iterations == want["iterations"], name
+            assert L.final_vertices() == want["vertices"], name
+            assert L.final_edges() == want["edges"], name
+            assert [sorted(x) for x in L.subgraphs] == want["subgraphs"], name

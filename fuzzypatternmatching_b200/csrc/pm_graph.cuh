@@ -134,17 +134,58 @@ __global__ void k_csr_place(const unsigned long long* __restrict__ rowptr, const
   }
 }
 
-// src[j] = global id of the vertex whose local row holds slot j (local row i = vertex i * G + rank)
-__global__ void k_csr_expand_sources(const unsigned long long* __restrict__ rowptr, uint64_t n_rows, uint32_t G,
-                                     uint32_t rank, uint32_t* __restrict__ src) {
+// Several ranks: the neighbours of a row arrive ascending by VERTEX id and must leave ascending by SLOT,
+// slot(v) = (v mod G) * nlmax + v / G.  Inside a row the G residue classes keep their order and follow one
+// another, so every neighbour's position is (neighbours of smaller residue) + (its rank inside its class):
+// two passes of ballots over the row, no sort.  One warp per row; rows [v0, v1); padding written too.
+__global__ void k_csr_place_slots(const unsigned long long* __restrict__ rowptr, const uint32_t* __restrict__ col,
+                                  uint64_t v0, uint64_t v1, const uint32_t* __restrict__ rowblk,
+                                  uint32_t* __restrict__ col0, uint32_t G, uint32_t nlmax) {
   const uint32_t lane = threadIdx.x & 31;
-  uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lt = (1u << lane) - 1u;
+  uint64_t v = v0 + (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-  for (; i < n_rows; i += nwarps) {
-    const unsigned long long b = rowptr[i], e = rowptr[i + 1];
-    const uint32_t v = (uint32_t)(i * G + rank);
-    for (unsigned long long j = b + lane; j < e; j += 32) src[j] = v;
+  for (; v < v1; v += nwarps) {
+    const unsigned long long b = rowptr[v], e = rowptr[v + 1];
+    const uint64_t o = (uint64_t)rowblk[v] * 8;
+    const unsigned long long d = e - b, padded = (d + 7ull) & ~7ull;
+    uint32_t start[PM_MAX_RANKS];
+#pragma unroll
+    for (int g = 0; g < PM_MAX_RANKS; ++g) start[g] = 0u;
+    for (unsigned long long j0 = 0; j0 < d; j0 += 32) {  // neighbours per residue class
+      const bool act = j0 + lane < d;
+      const uint32_t r = act ? col[b + j0 + lane] % G : 0u;
+#pragma unroll
+      for (int g = 0; g < PM_MAX_RANKS; ++g)
+        if ((uint32_t)g < G) start[g] += __popc(__ballot_sync(0xffffffffu, act && r == (uint32_t)g));
+    }
+    uint32_t run = 0;
+#pragma unroll
+    for (int g = 0; g < PM_MAX_RANKS; ++g) {  // counts -> first position of every class
+      const uint32_t n = start[g];
+      start[g] = run;
+      run += n;
+    }
+    for (unsigned long long j0 = 0; j0 < d; j0 += 32) {
+      const bool act = j0 + lane < d;
+      const uint32_t u = act ? col[b + j0 + lane] : 0u;
+      const uint32_t r = u % G;
+#pragma unroll
+      for (int g = 0; g < PM_MAX_RANKS; ++g)
+        if ((uint32_t)g < G) {
+          const uint32_t m = __ballot_sync(0xffffffffu, act && r == (uint32_t)g);
+          if (act && r == (uint32_t)g) col0[o + start[g] + __popc(m & lt)] = r * nlmax + u / G;
+          start[g] += __popc(m);
+        }
+    }
+    for (unsigned long long j = d + lane; j < padded; j += 32) col0[o + j] = PM_SENTINEL;
   }
+}
+
+__global__ void k_fill_u64(unsigned long long* __restrict__ p, uint64_t n, unsigned long long value) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) p[i] = value;
 }
 
 // label = ceil(log2(degree + 1)) == bit length of the degree
@@ -517,8 +558,10 @@ inline int graph_build_from_device_slots(pm_ctx* c, uint64_t V, uint64_t n_in, c
 // end-to-end run pays).  The adjacency travels in chunks on a copy stream straight into the (still unused)
 // working adjacency `colw`; each chunk's rows are placed into their padded positions of `col0` while the
 // next chunk is still on the bus, so the PCIe copy is the only thing on the critical path.
-inline int graph_build_from_host_csr(pm_ctx* c, uint64_t V, const uint64_t* h_rowptr, const uint32_t* h_col,
-                                     const uint64_t* h_degm) {
+// Several ranks: V is the global vertex count and the host arrays describe the n_rows vertices THIS rank owns
+// (local row i = vertex i * n_ranks + rank, neighbours as global vertex ids ascending); one rank: n_rows = V.
+inline int graph_build_from_host_csr(pm_ctx* c, uint64_t V, uint64_t n_rows, const uint64_t* h_rowptr,
+                                     const uint32_t* h_col, const uint64_t* h_degm) {
   if (V == 0 || V > (1ull << 31)) return fail(c, PM_ERR_ARG, "n_vertices must be in [1, 2^31]");
   const bool dbg = getenv("PM_DEBUG_BUILD") != nullptr;
   double t_prev = wall_s();
@@ -533,7 +576,8 @@ inline int graph_build_from_host_csr(pm_ctx* c, uint64_t V, const uint64_t* h_ro
   lap("graph_free");
   graph_set_partition(c, V);  // single rank: slot = vertex id, the rows can be placed as they are
   cudaStream_t st = c->stream;
-  const uint64_t E = h_rowptr[V];
+  const uint64_t NL = c->nloc;  // local rows of the store (rows past n_rows are alignment padding: empty)
+  const uint64_t E = h_rowptr[n_rows];
   c->E = E;
   uint64_t bytes = 0;
   int rc;
@@ -551,33 +595,37 @@ inline int graph_build_from_host_csr(pm_ctx* c, uint64_t V, const uint64_t* h_ro
     if (cs) cudaStreamDestroy(cs);
     cs = nullptr;
   };
-  if ((rc = dev_alloc(c, &c->degm, V, &bytes)) || (rc = dev_alloc(c, &c->deg, V, &bytes)) ||
-      (rc = dev_alloc(c, &c->rowblk, V + 1, &bytes)) || (rc = dev_alloc(c, &d_rowptr, V + 1)) ||
-      (rc = dev_alloc(c, &d_degm64, V)) || (rc = dev_alloc(c, &d_total, 1)) || (rc = dev_alloc(c, &sectors, V + 1))) {
+  if ((rc = dev_alloc(c, &c->degm, NL, &bytes)) || (rc = dev_alloc(c, &c->deg, NL, &bytes)) ||
+      (rc = dev_alloc(c, &c->rowblk, NL + 1, &bytes)) || (rc = dev_alloc(c, &d_rowptr, NL + 1)) ||
+      (rc = dev_alloc(c, &d_degm64, NL)) || (rc = dev_alloc(c, &d_total, 1)) || (rc = dev_alloc(c, &sectors, NL + 1))) {
     cleanup();
     return rc;
   }
 #define PM_GC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); \
     return fail(c, PM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
   lap("alloc 1");
-  PM_GC(cudaMemcpyAsync(d_rowptr, h_rowptr, (V + 1) * 8, cudaMemcpyHostToDevice, st));
-  PM_GC(cudaMemcpyAsync(d_degm64, h_degm, V * 8, cudaMemcpyHostToDevice, st));
+  PM_GC(cudaMemcpyAsync(d_rowptr, h_rowptr, (n_rows + 1) * 8, cudaMemcpyHostToDevice, st));
+  PM_GC(cudaMemcpyAsync(d_degm64, h_degm, n_rows * 8, cudaMemcpyHostToDevice, st));
   PM_GC(cudaMemsetAsync(d_total, 0, 8, st));
   const int grid = grid_for();
-  k_csr_degrees<<<grid, kBlock, 0, st>>>(d_rowptr, d_degm64, V, c->deg, c->degm, sectors, d_total);
+  if (NL > n_rows) {
+    k_fill_u64<<<grid, kBlock, 0, st>>>(d_rowptr + n_rows + 1, NL - n_rows, (unsigned long long)E);
+    PM_GC(cudaMemsetAsync(d_degm64 + n_rows, 0, (NL - n_rows) * 8, st));
+  }
+  k_csr_degrees<<<grid, kBlock, 0, st>>>(d_rowptr, d_degm64, NL, c->deg, c->degm, sectors, d_total);
   c->launches++;
   size_t tb = 0, tb2 = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, tb, sectors, c->rowblk, (int64_t)(V + 1), st);
+  cub::DeviceScan::ExclusiveSum(nullptr, tb, sectors, c->rowblk, (int64_t)(NL + 1), st);
   uint32_t* d_max = nullptr;
-  cub::DeviceReduce::Max(nullptr, tb2, c->degm, d_max, (int64_t)V, st);
+  cub::DeviceReduce::Max(nullptr, tb2, c->degm, d_max, (int64_t)NL, st);
   tb = std::max(tb, tb2);
   PM_GC(cudaMalloc(&tmp, std::max<size_t>(tb, 16) + 16));
-  PM_GC(cub::DeviceScan::ExclusiveSum(tmp, tb, sectors, c->rowblk, (int64_t)(V + 1), st));
+  PM_GC(cub::DeviceScan::ExclusiveSum(tmp, tb, sectors, c->rowblk, (int64_t)(NL + 1), st));
   uint32_t h_total = 0, h_max = 0;
   unsigned long long h_em = 0;
-  PM_GC(cudaMemcpyAsync(&h_total, c->rowblk + V, 4, cudaMemcpyDeviceToHost, st));
+  PM_GC(cudaMemcpyAsync(&h_total, c->rowblk + NL, 4, cudaMemcpyDeviceToHost, st));
   d_max = sectors;  // reuse: sectors are consumed
-  PM_GC(cub::DeviceReduce::Max(tmp, tb, c->degm, d_max, (int64_t)V, st));
+  PM_GC(cub::DeviceReduce::Max(tmp, tb, c->degm, d_max, (int64_t)NL, st));
   PM_GC(cudaMemcpyAsync(&h_max, d_max, 4, cudaMemcpyDeviceToHost, st));
   PM_GC(cudaMemcpyAsync(&h_em, d_total, 8, cudaMemcpyDeviceToHost, st));
   PM_GC(cudaStreamSynchronize(st));
@@ -596,10 +644,10 @@ inline int graph_build_from_host_csr(pm_ctx* c, uint64_t V, const uint64_t* h_ro
     PM_GC(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
     const uint64_t n_chunks = std::max<uint64_t>(1, std::min<uint64_t>(32, E >> 24));  // >= 64 MiB per chunk
     uint64_t v0 = 0;
-    for (uint64_t k = 1; k <= n_chunks && v0 < V; ++k) {
+    for (uint64_t k = 1; k <= n_chunks && v0 < n_rows; ++k) {
       // rows [v0, v1): v1 = first row that starts at or after the k-th share of the slots
-      uint64_t v1 = V;
-      if (k < n_chunks) v1 = (uint64_t)(std::lower_bound(h_rowptr + v0, h_rowptr + V, E / n_chunks * k) - h_rowptr);
+      uint64_t v1 = n_rows;
+      if (k < n_chunks) v1 = (uint64_t)(std::lower_bound(h_rowptr + v0, h_rowptr + n_rows, E / n_chunks * k) - h_rowptr);
       if (v1 <= v0) continue;
       const uint64_t b = h_rowptr[v0], e = h_rowptr[v1];
       cudaEvent_t ev;
@@ -608,7 +656,11 @@ inline int graph_build_from_host_csr(pm_ctx* c, uint64_t V, const uint64_t* h_ro
       if (e > b) PM_GC(cudaMemcpyAsync(c->colw + b, h_col + b, (e - b) * 4, cudaMemcpyHostToDevice, cs));
       PM_GC(cudaEventRecord(ev, cs));
       PM_GC(cudaStreamWaitEvent(st, ev, 0));
-      k_csr_place<<<grid, kBlock, 0, st>>>(d_rowptr, c->colw, v0, v1, c->rowblk, c->col0);
+      if (c->n_ranks == 1)
+        k_csr_place<<<grid, kBlock, 0, st>>>(d_rowptr, c->colw, v0, v1, c->rowblk, c->col0);
+      else  // vertex ids -> slots, rows re-ordered by slot
+        k_csr_place_slots<<<grid, kBlock, 0, st>>>(d_rowptr, c->colw, v0, v1, c->rowblk, c->col0, (uint32_t)c->n_ranks,
+                                                   (uint32_t)c->nlmax);
       c->launches++;
       v0 = v1;
     }

@@ -265,43 +265,12 @@ int pm_graph_from_csr(pm_ctx* c, uint64_t n_vertices, const uint64_t* rowptr, co
   if (!c || !rowptr || !degree_multi) return fail(c, PM_ERR_ARG, "pm_graph_from_csr: null argument");
   PM_CUDA(c, cudaSetDevice(c->device));
   state_free(c, /*keep_scratch=*/true);
-  if (c->n_ranks == 1) {
-    if (rowptr[n_vertices] && !col) return fail(c, PM_ERR_ARG, "pm_graph_from_csr: null argument");
-    return graph_build_from_host_csr(c, n_vertices, rowptr, col, degree_multi);
-  }
   // several ranks: rowptr / col / degree_multi describe the rows of the vertices THIS rank owns
-  // (local row i = vertex i * n_ranks + rank).  The adjacency is uploaded as it is, the source of every
-  // slot is expanded on the device and the rows are re-keyed by slot through the sort based build.
+  // (local row i = vertex i * n_ranks + rank, neighbours as global vertex ids)
   c->V = n_vertices;
-  const uint64_t own = n_owned(c), E = rowptr[own];
-  if (E && !col) return fail(c, PM_ERR_ARG, "pm_graph_from_csr: null argument");
-  uint32_t *d_src = nullptr, *d_dst = nullptr;
-  unsigned long long* d_rowptr = nullptr;
-  int rc;
-  if ((rc = dev_alloc(c, &d_src, E)) || (rc = dev_alloc(c, &d_dst, E)) || (rc = dev_alloc(c, &d_rowptr, own + 1))) {
-    dev_free(d_src); dev_free(d_dst); dev_free(d_rowptr);
-    return rc;
-  }
-  cudaError_t e1 = cudaMemcpyAsync(d_rowptr, rowptr, (own + 1) * 8, cudaMemcpyHostToDevice, c->stream);
-  cudaError_t e2 = E ? cudaMemcpyAsync(d_dst, col, E * 4, cudaMemcpyHostToDevice, c->stream) : cudaSuccess;
-  if (e1 == cudaSuccess && e2 == cudaSuccess) {
-    k_csr_expand_sources<<<grid_for(), kBlock, 0, c->stream>>>(d_rowptr, own, (uint32_t)c->n_ranks, (uint32_t)c->rank, d_src);
-    c->launches++;
-    e1 = cudaGetLastError();
-  }
-  if (e1 != cudaSuccess || e2 != cudaSuccess) {
-    dev_free(d_src); dev_free(d_dst); dev_free(d_rowptr);
-    return fail(c, PM_ERR_CUDA, "pm_graph_from_csr: host to device copy failed");
-  }
-  rc = graph_build_from_device_slots(c, n_vertices, E, d_src, d_dst, /*route=*/false);
-  dev_free(d_src); dev_free(d_dst); dev_free(d_rowptr);
-  if (rc) return rc;
-  std::vector<uint32_t> dm(c->nloc, 0u);
-  uint64_t em = 0;
-  for (uint64_t i = 0; i < own; ++i) { dm[i] = (uint32_t)degree_multi[i]; em += degree_multi[i]; }
-  PM_CUDA(c, cudaMemcpy(c->degm, dm.data(), c->nloc * 4, cudaMemcpyHostToDevice));
-  c->E_multi = em;
-  return 0;
+  const uint64_t own = n_owned(c);
+  if (rowptr[own] && !col) return fail(c, PM_ERR_ARG, "pm_graph_from_csr: null argument");
+  return graph_build_from_host_csr(c, n_vertices, own, rowptr, col, degree_multi);
 }
 
 int pm_get_kernel_stats(const pm_ctx* c, int bin, pm_kernel_stats_t* out) {

@@ -279,7 +279,7 @@ def main():
     # end to end through the C ABI with HOST buffers: upload the host CSR, search, read results back
     e2e = None
     if world > 1:
-        args.e2e_steps = min(args.e2e_steps, 1)  # the partitioned upload re-keys every row on the host: one step is enough
+        args.e2e_steps = min(args.e2e_steps, 1)  # reading the rows back for the upload is a host loop per rank: keep the run short
     if (rank == 0 or world > 1) and args.e2e_steps > 0:
         rowptr, col = eng.graph_csr()
         degm = eng.graph_degree()

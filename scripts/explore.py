@@ -1,4 +1,5 @@
-"""GPU exploration: graph build and per-template search times at several scales."""
+"""GPU exploration: graph build and per-template search times at several scales.
+Development tooling, not product: the optional `check` argument uses the CPU oracle as a checker, like the tests do."""
 import sys, time, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench

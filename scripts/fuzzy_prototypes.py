@@ -4,7 +4,8 @@
 
 For every connected template within k edge deletions of the base template (4-cycle with degree
 labels 5,6,7,8 and the 6-cycle with chords 4..9) the run_fuzzy path prunes the graph and the
-surviving vertices are counted.  `check` compares every run with the CPU oracle (small scales)."""
+surviving vertices are counted.  `check` compares every run with the CPU oracle (small scales): that mode is test
+tooling (the oracle as the checker); without it the script only drives the GPU path."""
 import os
 import sys
 import tempfile

@@ -1,7 +1,7 @@
 """Multi-GPU parity check: run under torchrun with one rank per GPU.
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
-      scripts/multi_check.py [scale] [gen_ranks]
+      tests/multi_gpu_check.py [scale] [gen_ranks]
 
 Every rank searches its partition (owner(v) = v mod G); rank 0 gathers the per-rank rows, vertex /
 edge lists and enumerated subgraphs and compares them with the CPU oracle run with n_ranks = G.

@@ -18,7 +18,7 @@ def _worker(rank, world, port, tmp):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from oracle import oracle as O
     from fuzzypatternmatching_b200 import patterns as PT
-    # rank 0 fixes the inputs, everybody gets the same ones (what bench.py / multi_check.py do with the NCCL id)
+    # rank 0 fixes the inputs, everybody gets the same ones (what bench.py / tests/multi_gpu_check.py do with the NCCL id)
     box = [None]
     if rank == 0:
         edges = cases.random_multigraph(5, 300, 1800)

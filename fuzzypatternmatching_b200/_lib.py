@@ -73,6 +73,7 @@ SYMBOLS = {
     "pm_pattern_load_dir": (_i, [_vp, C.c_char_p]),
     "pm_pattern_info": (_i, [_vp, C.POINTER(PatternInfo)]),
     "pm_pattern_constraint_info": (_i, [_vp, _i, C.POINTER(ConstraintInfo)]),
+    "pm_pattern_check_dir": (_i, [C.c_char_p, C.POINTER(PatternInfo), C.POINTER(ConstraintInfo), _i, C.c_char_p, C.c_size_t]),
     "pm_end_iteration": (_i, [_vp, C.c_double]),
     "pm_state_reset": (_i, [_vp]),
     "pm_lcc": (_i, [_vp, _i, C.POINTER(_i), C.POINTER(Counts)]),

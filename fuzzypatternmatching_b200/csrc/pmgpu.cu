@@ -1292,6 +1292,31 @@ int pm_pattern_constraint_info(const pm_ctx* c, int pl, pm_constraint_info_t* o)
   return 0;
 }
 
+int pm_pattern_check_dir(const char* dir, pm_pattern_info_t* info_out, pm_constraint_info_t* constraints_out,
+                         int constraints_cap, char* err_out, size_t err_cap) {
+  if (err_out && err_cap) err_out[0] = 0;
+  if (!dir || !info_out) return PM_ERR_ARG;
+  Pattern p;
+  const std::string why = load_pattern_dir(dir, p);
+  if (!why.empty()) {
+    if (err_out && err_cap) {
+      std::strncpy(err_out, why.c_str(), err_cap - 1);
+      err_out[err_cap - 1] = 0;
+    }
+    return PM_ERR_PATTERN;
+  }
+  info_out->n_vertices = p.n_vertices; info_out->n_edges = p.n_edges; info_out->diameter = p.diameter;
+  info_out->n_constraints = (int)p.constraints.size();
+  for (int pl = 0; constraints_out && pl < constraints_cap && pl < (int)p.constraints.size(); ++pl) {
+    const Constraint& k = p.constraints[pl];
+    constraints_out[pl].walk_length = (int)k.P.size();
+    constraints_out[pl].valid_cycle = k.valid_cycle;
+    constraints_out[pl].interleave_lcc = k.interleave;
+    constraints_out[pl].order_independent = nem1_order_independent(k);
+  }
+  return 0;
+}
+
 int pm_get_rows(const pm_ctx* c, pm_row_t* rows_out) {
   if (!c || !rows_out) return PM_ERR_ARG;
   std::copy(c->rows.begin(), c->rows.end(), rows_out);

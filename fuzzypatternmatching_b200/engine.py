@@ -217,6 +217,22 @@ class Engine:
         return int(self._lib.pm_kernel_launches(self._h))
 
 
+def pattern_check_dir(directory, max_constraints=64):
+    """Host-only check of a pattern directory (pm_pattern_check_dir: no context, no GPU).  Returns the pattern's
+    sizes and its constraints, raises ValueError with the reader's reason if the directory is rejected."""
+    lib = _lib.load()
+    info = _lib.PatternInfo()
+    cons = (_lib.ConstraintInfo * max_constraints)()
+    err = C.create_string_buffer(512)
+    rc = lib.pm_pattern_check_dir(directory.encode(), C.byref(info), cons, max_constraints, err, len(err))
+    if rc != 0:
+        raise ValueError(err.value.decode() or "pm_pattern_check_dir failed (%d)" % rc)
+    out = {n: int(getattr(info, n)) for n, _ in info._fields_}
+    out["constraints"] = [{n: int(getattr(cons[i], n)) for n, _ in cons[i]._fields_}
+                          for i in range(min(out["n_constraints"], max_constraints))]
+    return out
+
+
 def run_pattern_matching_beta(graph, pattern_dir, output_dir=None, labels=None, device=0, **run_kw):
     """The reference driver's flow (-i/-p/-o) in one call.
     graph: ("rmat", scale, gen_ranks) or (n_vertices, src, dst) directed slots."""

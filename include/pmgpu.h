@@ -21,6 +21,7 @@
 #ifndef PMGPU_H
 #define PMGPU_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -122,6 +123,12 @@ typedef struct {
   int order_independent;   /* 1: nem_1's result does not depend on message order (A.6 #7)  */
 } pm_constraint_info_t;
 int pm_pattern_constraint_info(const pm_ctx* ctx, int pl, pm_constraint_info_t* out);
+/* Host-only check of a pattern directory with the reader pm_pattern_load_dir uses: no context, no device.
+ * Returns PM_OK and fills *info_out (and up to constraints_cap entries of constraints_out, which may be null),
+ * or PM_ERR_PATTERN with the reason in err_out (the message the reference's ::graph / pattern_util would
+ * have failed on later, graph.hpp:195-270, pattern_util.hpp:172-278).                                      */
+int pm_pattern_check_dir(const char* dir, pm_pattern_info_t* info_out, pm_constraint_info_t* constraints_out,
+                         int constraints_cap, char* err_out, size_t err_cap);
 
 /* ---- per-pattern state ---------------------------------------------------
  * replaces the container reset of beta.cpp:484-492                            */

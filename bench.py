@@ -161,10 +161,14 @@ def main():
         if rank != 0:
             return 0
         cpu_scale = min(scale, args.cpu_scale)
-        r = cpu_reference(cpu_scale, min(args.gen_ranks, 4) if cpu_scale != scale else args.gen_ranks,
-                          pats, args.steps, max(args.warmup, 1))
-        sample = ("oracle port of the reference CPU path, R-MAT scale %d (bounded sample of the scale-%d workload), "
-                  "same templates, %d host threads" % (cpu_scale, scale, r["cores"]))
+        cpu_gen = min(args.gen_ranks, 4) if cpu_scale != scale else args.gen_ranks
+        r = cpu_reference(cpu_scale, cpu_gen, pats, args.steps, max(args.warmup, 1))
+        sample = ("oracle port of the reference CPU path, R-MAT scale %d with %d generating ranks (bounded sample of the "
+                  "scale-%d workload), same templates, %d host threads" % (cpu_scale, cpu_gen, scale, r["cores"]))
+        # the config states what RAN; the workload it samples stays named beside it
+        config.update({"scale": cpu_scale, "gen_ranks": cpu_gen, "directed_edge_slots": r["edges_per_step"] // len(pats),
+                       "sample_of": {"workload": config["workload"], "scale": scale, "gen_ranks": args.gen_ranks},
+                       "parallelism": "openmp_x%d" % r["cores"]})
         line = {"impl": "reference", "metric": metric, "value": r["value"], "unit": unit, "n_gpus": args.gpus,
                 "steps": r["steps_done"], "warmup": args.warmup, "ms_per_step": r["seconds_per_step"] * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16",
@@ -180,8 +184,10 @@ def main():
     import torch
     import torch.distributed as dist
     from fuzzypatternmatching_b200.engine import Engine
+    gloo = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        gloo = dist.new_group(backend="gloo")  # object collectives of the parity check
     torch.cuda.set_device(local_rank)
 
     def barrier():
@@ -198,7 +204,11 @@ def main():
     t0 = time.time()
     # every rank generates its share of the generating ranks' streams; the slots are shuffled to their owners
     eng.graph_rmat(scale, args.gen_ranks)
-    eng.labels_degree_log2()
+    torch.cuda.synchronize()
+    t_lab = time.perf_counter()
+    eng.labels_degree_log2()   # degree labels + the per-graph index the search reads (byte labels, label stream, signatures)
+    torch.cuda.synchronize()
+    index_ms = (time.perf_counter() - t_lab) * 1e3
     gi = eng.graph_info()
     build_s = time.time() - t0
     n_local_edges = gi["n_slots_multi"]
@@ -210,11 +220,17 @@ def main():
         n_global_edges = n_local_edges
     n_edges = n_global_edges * len(pats)      # whole-job edges searched per step
 
+    step_acc = {"edges_scanned": 0, "algorithmic_bytes": 0, "device_seconds": 0.0}
+
     def one_step(fetch=False):
         got = 0
+        step_acc.update(edges_scanned=0, algorithmic_bytes=0, device_seconds=0.0)
         for _, d, tds in pats:
             eng.pattern_load_dir(d)
             s = eng.run(tds_from_pl=tds, keep_subgraphs=False)
+            step_acc["edges_scanned"] += int(s["edges_processed"])
+            step_acc["algorithmic_bytes"] += int(s["algorithmic_bytes"])
+            step_acc["device_seconds"] += float(s["device_seconds"])
             if fetch:  # device -> host read of the step's result
                 v, b = eng.active_vertices()
                 e = eng.active_edges()
@@ -241,6 +257,14 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed = float(t.item())
     value = n_edges * args.steps / elapsed
+    # what the kernels themselves counted over one step (pm_run_summary_t): adjacency slots walked by the LCC scans +
+    # token fan-out of the NLCC walks, and the SURVEY section 8(d) byte model over them; several ranks: summed
+    acc = [step_acc["edges_scanned"], step_acc["algorithmic_bytes"]]
+    if world > 1:
+        t = torch.tensor(acc, dtype=torch.int64, device="cuda")
+        dist.all_reduce(t)
+        acc = [int(x) for x in t.tolist()]
+    ms_step = elapsed / args.steps * 1e3
 
     # roofline of the dominant kernel: the LCC scan class (first superstep / later supersteps / CTA-per-row)
     # with the largest share of the timed region, timed with CUDA events on the engine's stream
@@ -260,6 +284,8 @@ def main():
     traffic = None
     try:  # DRAM bytes per launch of the same kernel class from the committed ncu --set full capture
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        # only a capture of THIS workload on this many GPUs describes this run
+        tr = tr.get("%s_n%d" % (config["workload"], world), {})
         traffic = tr.get({0: "scan_first", 1: "scan_later", 2: "scan_big", 4: "scan_xlate"}[top], {}).get("dram_bytes_per_launch")
     except Exception:
         pass
@@ -275,6 +301,57 @@ def main():
                 "share_of_step": dk[top]["ms"] * 1e-3 / elapsed,
                 "other_classes": {names[b].split(" ")[0]: {"ms": dk[b]["ms"], "launches": dk[b]["launches"]} for b in scan_classes if b != top},
                 "model": "6.25 B per scanned slot + 12.25 B per scanned vertex"}
+
+    # ---- several GPUs: correctness of THIS build on THIS many ranks, outside the timed region.  R-MAT scale 18 is
+    # searched by the partitioned engine and by the CPU oracle with n_ranks = N (the checker, tests/multi_gpu_check.py);
+    # per-rank rows, vertex / edge lists and enumerated subgraphs must be equal.
+    parity = None
+    strong_rec = None
+    if world > 1:
+        from tests.multi_gpu_check import partition_parity
+
+        class _Gloo:
+            @staticmethod
+            def broadcast_object_list(box, src=0):
+                dist.broadcast_object_list(box, src=src, group=gloo)
+
+            @staticmethod
+            def gather_object(obj, lst, dst=0):
+                dist.gather_object(obj, lst, dst=dst, group=gloo)
+
+        from oracle import oracle as O  # the checker, rank 0 only uses it
+        oks, names = [], []
+        for nm, spec in WORKLOADS[args.workload]:
+            tds = PT.tds_from_pl(spec)
+            ok = partition_parity(eng, _Gloo, rank, world, "rmat18/" + nm, lambda: eng.graph_rmat(18, 4),
+                                  lambda: O.Graph.rmat(18, 4), None, spec, tds, log=lambda m: sys.stderr.write(m + "\n"))
+            oks.append(ok)
+            names.append(nm)
+        if rank == 0:
+            parity = {"ranks": world, "ok": bool(all(oks)), "graph": "rmat scale 18, 4 generating ranks",
+                      "templates": names, "checker": "CPU oracle with n_ranks = %d" % world}
+        # ---- strong scaling beside the weak-scaling value: the N=1 graph (scale `--scale`) over N GPUs
+        if not strong:
+            eng.graph_rmat(args.scale, args.gen_ranks)
+            eng.labels_degree_log2()
+            for _ in range(args.warmup):
+                one_step()
+            barrier()
+            t0s = time.perf_counter()
+            for _ in range(args.steps):
+                one_step()
+            barrier()
+            el = time.perf_counter() - t0s
+            t = torch.tensor([el], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            el = float(t.item())
+            ne = 2 ** (args.scale + 5) * len(pats)
+            strong_rec = {"scale": args.scale, "n_gpus": world, "ms_per_step": el / args.steps * 1e3,
+                          "value": ne * args.steps / el, "unit": unit,
+                          "what": "the N=1 graph (scale %d) partitioned over %d GPUs" % (args.scale, world)}
+            # back to the weak-scaling graph for the end-to-end leg
+            eng.graph_rmat(scale, args.gen_ranks)
+            eng.labels_degree_log2()
 
     # end to end through the C ABI with HOST buffers: upload the host CSR, search, read results back
     e2e = None
@@ -331,7 +408,21 @@ def main():
                 "warmup": args.warmup, "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True,
                 "scaling": "strong" if (strong and world > 1) else "weak", "vs_baseline": None, "dtype": "u16", "data": "synthetic", "config": config,
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
-                "search_ms_per_template": elapsed / args.steps / len(pats) * 1e3}
+                "search_ms_per_template": elapsed / args.steps / len(pats) * 1e3,
+                # the kernels' own counters for one step, and the whole step against the HBM roofline
+                "edges_scanned_per_step": acc[0], "algorithmic_bytes_per_step": acc[1],
+                "edges_scanned_per_second": acc[0] / (ms_step * 1e-3),
+                "step_roofline_frac": acc[1] / (ms_step * 1e-3) / 1e9 / (peak * world),
+                "launches_per_step": launches / args.steps,
+                # the per-graph index (byte labels, label stream, neighbour-label signatures) is built with the labels,
+                # outside the timed search like the reference's label pass; `value_incl_index` charges one build per step
+                "index_build_ms": index_ms,
+                "value_incl_index": n_edges / ((ms_step + index_ms) * 1e-3),
+                "value_definition": "directed edge slots of the graph x templates / step time (input edges searched per second)"}
+        if parity is not None:
+            line["parity_check"] = parity
+        if strong_rec is not None:
+            line["strong_s%d" % args.scale] = strong_rec
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -194,7 +194,10 @@ struct pm_ctx {
   std::vector<uint64_t> pool_seen;  // per constraint: most tokens ever stored (sizes the next run's pool / inbox regions)
   std::vector<uint64_t> keys_seen;  // per constraint: most keys ever held by the hash set (sizes the next run's table)
   std::map<std::string, std::vector<uint64_t>> keys_cache;
-  std::string pat_key;              // pattern directory the sizes belong to
+  std::string pat_dir;              // pattern directory of the loaded pattern
+  std::string pat_key;              // (pattern directory, graph, labels, path) the sizes belong to
+  uint64_t labels_version = 0;      // 0: degree labels (a function of the graph); else the pm_labels_set call they came from
+  uint64_t labels_counter = 0;
   std::map<std::string, std::vector<uint64_t>> pool_cache;
   uint2* pool = nullptr;            // token pool: nem_1 (vertex, source); TDS (parent index, vertex)
   uint64_t pool_cap = 0;

@@ -202,7 +202,7 @@ __constant__ FzTok c_fz;
 
 // sources: vertices in the map whose vertex_pattern_index is I[0] (tp.hpp:208-228)
 __global__ void __launch_bounds__(kBlock) k_fz_sources(FzArgs a, const uint4* __restrict__ l0, int cur, uint8_t* ok,
-                                                        uint32_t* src_list, uint2* pool) {
+                                                        uint32_t* src_list, uint2* pool, unsigned long long pool_cap) {
   const uint32_t total = a.cnt->fr_n[cur][0];
   const uint32_t lane = threadIdx.x & 31;
   uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u;
@@ -224,7 +224,8 @@ __global__ void __launch_bounds__(kBlock) k_fz_sources(FzArgs a, const uint4* __
         const uint32_t pos = base + __popc(m & lanemask_lt());
         src_list[pos] = v;
         ok[v] = 0;
-        pool[pos] = make_uint2(v, v);
+        if (pos < pool_cap) pool[pos] = make_uint2(v, v);
+        else a.cnt->overflow = 1u;
       }
     }
   }

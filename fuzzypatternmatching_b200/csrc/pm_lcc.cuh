@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(kBlock) k_init_assign(const uint8_t* __restric
           uint32_t heard = 0;
 #pragma unroll
           for (int q = 0; q < 16; ++q)
-            if (q < c_pat.ncls && ((uint32_t)c_pat.LMc[q] & NBv) && ((sg >> (c_pat.clabel[q] & 63ull)) & 1ull))
+            if (q < c_pat.ncls && c_pat.clabel[q] < 64ull && ((uint32_t)c_pat.LMc[q] & NBv) && ((sg >> c_pat.clabel[q]) & 1ull))
               heard |= c_pat.LMc[q];
           tw = cover_of(lm, heard);
         }
@@ -440,7 +440,7 @@ __device__ __forceinline__ unsigned long long valid_labels(uint32_t NBv) {
   unsigned long long r = 0;
 #pragma unroll
   for (int q = 0; q < 16; ++q)
-    if (q < c_pat.ncls && ((uint32_t)c_pat.LMc[q] & NBv)) r |= 1ull << (c_pat.clabel[q] & 63ull);
+    if (q < c_pat.ncls && c_pat.clabel[q] < 64ull && ((uint32_t)c_pat.LMc[q] & NBv)) r |= 1ull << c_pat.clabel[q];
   return r;
 }
 

@@ -193,8 +193,10 @@ __global__ void __launch_bounds__(kBlock) k_nlcc_sources(NlcArgs a, const uint4*
         a.src_list[pos] = v;
         a.ok[v] = 0;
         if (!multi) {
-          // level 0 of the token pool; n_src never exceeds V <= pool_cap
-          a.pool[pos] = tds ? make_uint2(0xFFFFFFFFu, v) : make_uint2(v, v);
+          // level 0 of the token pool (pm_nlcc sizes the pool for at least the vertices still in the map; the
+          // guard covers a pool sized by an earlier, smaller search)
+          if (pos < a.pool_cap) a.pool[pos] = tds ? make_uint2(0xFFFFFFFFu, v) : make_uint2(v, v);
+          else a.cnt->overflow = 1u;
         } else if (!tds) {
           // level 0 = my own region of my token inbox
           if (pos < c_peer.tcap) c_peer.tin[a.par][c_peer.rank][(unsigned long long)c_peer.rank * c_peer.tcap + pos] = make_uint2(v, v);

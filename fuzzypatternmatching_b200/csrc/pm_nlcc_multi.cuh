@@ -23,12 +23,15 @@ struct TokSrc {  // the tokens that arrived for this rank in the previous hop: G
   unsigned long long total;
 };
 
-__device__ __forceinline__ TokSrc tok_src(const NlcArgs& a) {
+// region_cap: records a region holds.  A sender that ran out of room kept counting (and raised `overflow`, which
+// makes the host retry the constraint with larger inboxes) but stored nothing past the region: never read there.
+__device__ __forceinline__ TokSrc tok_src(const NlcArgs& a, unsigned long long region_cap) {
   TokSrc t;
   t.total = 0;
 #pragma unroll
   for (int r = 0; r < PM_MAX_RANKS; ++r) {
     unsigned long long n = r < c_peer.G ? a.all[r].out_n[c_peer.rank] : 0ull;
+    if (n > region_cap) n = region_cap;
     t.n[r] = n;
     t.total += n;
   }
@@ -191,7 +194,7 @@ __global__ void k_close_keys_count_m(DevCounters* cnt) {
 }
 
 __global__ void __launch_bounds__(kBlock) k_close_ingest_m(NlcArgs a) {
-  const TokSrc src = tok_src(a);
+  const TokSrc src = tok_src(a, c_peer.tcap);
   const uint2* __restrict__ in = c_peer.tin[a.par ^ 1][c_peer.rank];
   for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < src.total;
        t += (unsigned long long)gridDim.x * blockDim.x) {
@@ -228,7 +231,7 @@ __device__ __forceinline__ bool close_edge_known(const NlcArgs& a, uint32_t s, u
 // ---------------------------------------------------------------------------
 template <int MODE>
 __global__ void __launch_bounds__(kBlock) k_nem1_hop_m(NlcArgs a, int hn, int first) {
-  const TokSrc src = tok_src(a);
+  const TokSrc src = tok_src(a, c_peer.tcap);
   const uint2* __restrict__ in = c_peer.tin[a.par ^ 1][c_peer.rank];
   constexpr int GROUP = 8;
   const uint32_t lane = threadIdx.x & 31;
@@ -326,9 +329,9 @@ __global__ void __launch_bounds__(kBlock) k_nem1_hop_m(NlcArgs a, int hn, int fi
 // ---------------------------------------------------------------------------
 template <bool FINAL>
 __global__ void __launch_bounds__(kBlock) k_tds_hop_m(NlcArgs a, int hn) {
-  const TokSrc src = tok_src(a);
   const int n = c_nlc.n;
   const unsigned long long rcap = c_peer.tcap * 2ull / (unsigned long long)n;  // records per region
+  const TokSrc src = tok_src(a, rcap);
   const uint32_t* __restrict__ in = reinterpret_cast<const uint32_t*>(c_peer.tin[a.par ^ 1][c_peer.rank]);
   constexpr int GROUP = 8;
   const uint32_t lane = threadIdx.x & 31;
@@ -419,7 +422,7 @@ __global__ void __launch_bounds__(kBlock) k_tds_hop_m(NlcArgs a, int hn) {
 
 // gathers the completed walks that arrived for this rank into one dense row array
 __global__ void k_tds_collect_m(NlcArgs a, int n, uint32_t* __restrict__ rows_out) {
-  const TokSrc src = tok_src(a);
+  const TokSrc src = tok_src(a, c_peer.tcap * 2ull / (unsigned long long)n);
   const uint32_t* __restrict__ in = reinterpret_cast<const uint32_t*>(c_peer.tin[a.par ^ 1][c_peer.rank]);
   for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < src.total;
        t += (unsigned long long)gridDim.x * blockDim.x) {

@@ -17,6 +17,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <fstream>
 #include <sstream>
 #include <string>
@@ -64,7 +65,8 @@ inline bool numbers(const std::string& s, std::vector<T>& out) {
   std::string tok;
   while (ss >> tok) {
     if (tok.find_first_not_of("0123456789") != std::string::npos) return false;
-    out.push_back((T)std::stoull(tok));
+    if (tok.size() > 19) return false;  // does not fit 64 bits: rejected like any other malformed token
+    out.push_back((T)std::strtoull(tok.c_str(), nullptr, 10));
   }
   return true;
 }
@@ -105,6 +107,9 @@ inline std::string load_pattern_dir(const std::string& dir, Pattern& pat) {
     }
     if (pat.vertex_label.empty() || pat.vertex_label.size() > 16)
       return "pattern_vertex_data: need 1..16 template vertices";
+    if ((int)pat.vertex_label.size() != pat.n_vertices)
+      return "pattern_vertex_data lists " + std::to_string(pat.vertex_label.size()) + " template vertices, pattern_edge " +
+             std::to_string(pat.n_vertices);
   }
   {
     std::ifstream f(base + "_stat");

@@ -24,6 +24,22 @@ using namespace pm;
 
 namespace {
 
+// c_pat / c_peer are __constant__ symbols shared by every context of a device.  The context that uploaded them last
+// owns them; another live context on the same device re-uploads its own tables before it launches anything
+// (after a device-wide synchronisation: the other context's kernels may still be reading the old ones).
+pm_ctx* g_const_owner[64] = {nullptr};
+
+int claim_constants(pm_ctx* c) {
+  pm_ctx*& owner = g_const_owner[c->device & 63];
+  if (owner == c) return 0;
+  const bool contested = owner != nullptr;
+  owner = c;
+  if (!contested || !c->state_ready) return 0;  // pm_state_reset uploads both tables itself
+  PM_CUDA(c, cudaDeviceSynchronize());
+  PM_CUDA(c, cudaMemcpyToSymbolAsync(c_pat, &c->pc, sizeof(PatConst), 0, cudaMemcpyHostToDevice, c->stream));
+  return comm_upload_peers(c);
+}
+
 int sync_counters(pm_ctx* c) {
   PM_CUDA(c, cudaMemcpyAsync(c->h_cnt, c->cnt, sizeof(DevCounters), cudaMemcpyDeviceToHost, c->stream));
   PM_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -113,6 +129,22 @@ void state_free(pm_ctx* c, bool keep_scratch = false) {
   c->state_ready = false;
 }
 
+// NLCC scratch sizes (token pool, key table) remembered from earlier searches of the same pattern directory over
+// the same graph through the same path; anything else starts from the defaults again
+void load_nlcc_sizes(pm_ctx* c, const char* path) {
+  const std::string key = c->pat_dir + "|" + std::to_string(c->V) + "|" + std::to_string(c->E_multi) + "|" +
+                          std::to_string(c->labels_version) + "|" + path;
+  if (key == c->pat_key) return;
+  c->pat_key = key;
+  const size_t n = c->pat.constraints.size();
+  auto it = c->pool_cache.find(key);
+  if (it != c->pool_cache.end() && it->second.size() == n) c->pool_seen = it->second;
+  else c->pool_seen.assign(n, 0);
+  auto it2 = c->keys_cache.find(key);
+  if (it2 != c->keys_cache.end() && it2->second.size() == n) c->keys_seen = it2->second;
+  else c->keys_seen.assign(n, 0);
+}
+
 // nem_1's result is independent of message arrival order iff interior hop labels
 // are pairwise distinct and P[h-1] != P[h+1].
 bool nem1_order_independent(const Constraint& k) {
@@ -189,6 +221,7 @@ void pm_destroy(pm_ctx* c) {
   // ranks may be destroyed at different times: unmap without the collective barrier
   for (void* p : c->ipc_open) cudaIpcCloseMemHandle(p);
   c->ipc_open.clear();
+  if (g_const_owner[c->device & 63] == c) g_const_owner[c->device & 63] = nullptr;
   ncclComm_t comm = comm_of(c);
   c->comm = nullptr;
   state_free(c);
@@ -335,6 +368,7 @@ int pm_labels_degree_log2(pm_ctx* c) {
   PM_LAUNCH_CHECK(c);
   c->has_labels = true;
   c->state_ready = false;
+  c->labels_version = 0;  // a function of the graph alone
   return labels_derive(c, true);  // bit lengths of 32-bit degrees are <= 32
 }
 
@@ -354,6 +388,7 @@ int pm_labels_set(pm_ctx* c, const uint64_t* labels) {
   PM_CUDA(c, cudaStreamSynchronize(c->stream));
   c->has_labels = true;
   c->state_ready = false;
+  c->labels_version = ++c->labels_counter;
   bool small = true;
   for (uint64_t v = 0; v < c->V && small; ++v) small = labels[v] < 64;
   return labels_derive(c, small);
@@ -419,15 +454,10 @@ int pm_pattern_load_dir(pm_ctx* c, const char* dir) {
   c->pc = pc;
   c->has_pattern = true;
   c->state_ready = false;
-  c->pat_key = dir;
-  {
-    auto it = c->pool_cache.find(c->pat_key);
-    if (it != c->pool_cache.end() && it->second.size() == p.constraints.size()) c->pool_seen = it->second;
-    else c->pool_seen.assign(p.constraints.size(), 0);
-    auto it2 = c->keys_cache.find(c->pat_key);
-    if (it2 != c->keys_cache.end() && it2->second.size() == p.constraints.size()) c->keys_seen = it2->second;
-    else c->keys_seen.assign(p.constraints.size(), 0);
-  }
+  c->pat_dir = dir;
+  c->pat_key.clear();  // the remembered NLCC sizes are looked up per (pattern, graph, path) when a search starts
+  c->pool_seen.assign(p.constraints.size(), 0);
+  c->keys_seen.assign(p.constraints.size(), 0);
   c->subgraphs.assign(p.constraints.size(), {});
   c->subgraph_width.assign(p.constraints.size(), 0);
   c->subgraph_count.assign(p.constraints.size(), 0);
@@ -508,6 +538,11 @@ int pm_state_reset(pm_ctx* c) {
     c->kev2.push_back(e);
   }
   c->kev2_cls.assign(nrow, 1);
+  if (g_const_owner[c->device & 63] && g_const_owner[c->device & 63] != c) {
+    PM_CUDA(c, cudaDeviceSynchronize());  // another context of this device may still be running on the old tables
+    if ((rc = comm_upload_peers(c))) return rc;
+  }
+  g_const_owner[c->device & 63] = c;
   PM_CUDA(c, cudaMemcpyToSymbolAsync(c_pat, &c->pc, sizeof(PatConst), 0, cudaMemcpyHostToDevice, c->stream));
   PM_CUDA(c, cudaMemsetAsync(c->cnt, 0, sizeof(DevCounters), c->stream));
   c->cur = 0;
@@ -575,6 +610,7 @@ int pm_state_reset(pm_ctx* c) {
     if (c->filter_done) PM_CUDA(c, cudaEventElapsedTime(&c->init_ms, c->kev[3][0], c->kev[3][1]));
   }
   c->fuzzy_ids = false;
+  load_nlcc_sizes(c, "beta");
   c->rows.clear();
   c->step_rows.clear();
   c->iter_seconds.clear();
@@ -590,6 +626,7 @@ int pm_state_reset(pm_ctx* c) {
 int pm_lcc(pm_ctx* c, int init_step, int* not_finished, pm_counts_t* counts_out) {
   if (!c || !c->state_ready) return fail(c, PM_ERR_ARG, "pm_lcc: call pm_state_reset first");
   PM_CUDA(c, cudaSetDevice(c->device));
+  { int rc0 = claim_constants(c); if (rc0) return rc0; }
   cudaStream_t st = c->stream;
   const int D = c->pat.diameter;
   const int grid = grid_for();
@@ -717,6 +754,7 @@ int pm_nlcc(pm_ctx* c, int pl, int mode, int* pattern_found, int* token_source_d
   if (!c || !c->state_ready) return fail(c, PM_ERR_ARG, "pm_nlcc: call pm_state_reset first");
   if (pl < 0 || pl >= (int)c->pat.constraints.size()) return fail(c, PM_ERR_ARG, "pm_nlcc: bad constraint index");
   PM_CUDA(c, cudaSetDevice(c->device));
+  { int rc0 = claim_constants(c); if (rc0) return rc0; }
   cudaStream_t st = c->stream;
   const Constraint& k = c->pat.constraints[pl];
   const bool tds = mode == PM_NLCC_TDS;
@@ -752,6 +790,9 @@ int pm_nlcc(pm_ctx* c, int pl, int mode, int* pattern_found, int* token_source_d
   const uint64_t ne_now = c->rows.empty() ? c->E : c->rows.back().n_edges;
   uint64_t want_pool = c->pool_seen[pl] ? c->pool_seen[pl] + c->pool_seen[pl] / 2 + 4096 : 2 * ne_now + 65536;
   want_pool = std::max<uint64_t>(want_pool, 1ull << 18);
+  // level 0 holds one token per source: never smaller than the vertices still in the map (the sizes remembered
+  // per pattern directory may come from a smaller graph)
+  want_pool = std::max<uint64_t>(want_pool, (c->rows.empty() ? c->nloc : c->rows.back().n_vertices) + 4096);
   uint64_t want_keys = c->keys_seen[pl] ? c->keys_seen[pl] + c->keys_seen[pl] / 2 + 4096 : want_pool;
   if (multi) {  // growing the inboxes is collective
     uint64_t w[2] = {want_pool, want_keys};
@@ -1022,6 +1063,7 @@ namespace {
 
 int fetch_pairs(pm_ctx* c, bool edges, std::vector<uint2>& host) {
   PM_CUDA(c, cudaSetDevice(c->device));
+  { int rc0 = claim_constants(c); if (rc0) return rc0; }
   cudaStream_t st = c->stream;
   // size from a fresh count
   const int D = c->pat.diameter;
@@ -1135,6 +1177,7 @@ int pm_run_fuzzy(pm_ctx* c, const pm_run_options_t* opt_in, pm_run_summary_t* ou
   int rc = pm_state_reset(c);  // allocations, pattern constants, bookkeeping (beta.cpp:484-492 analogue)
   if (rc) return rc;
   c->fuzzy_ids = true;         // this path names vertices directly (no compact ids)
+  load_nlcc_sizes(c, "fuzzy");
   cudaStream_t st = c->stream;
   const int D = c->pat.diameter, grid = grid_for();
   const int max_it = opt.max_iterations > 0 ? opt.max_iterations : 1000;
@@ -1202,6 +1245,7 @@ int pm_run_fuzzy(pm_ctx* c, const pm_run_options_t* opt_in, pm_run_summary_t* ou
         PM_CUDA(c, cudaMemcpyToSymbolAsync(c_fz, &ft, sizeof(ft), 0, cudaMemcpyHostToDevice, st));
         if (c->pool_seen.size() != c->pat.constraints.size()) c->pool_seen.assign(c->pat.constraints.size(), 0);
         uint64_t want = c->pool_seen[pl] ? c->pool_seen[pl] + c->pool_seen[pl] / 2 + 4096 : std::max<uint64_t>(1ull << 20, 16 * c->rows.back().n_vertices);
+        want = std::max<uint64_t>(want, c->rows.back().n_vertices + 4096);  // level 0: one token per source
         for (int attempt = 0;; ++attempt) {
           if ((rc = nlcc_reserve(c, want, want))) return rc;
           c->hset_use = c->hset_cap;
@@ -1211,7 +1255,7 @@ int pm_run_fuzzy(pm_ctx* c, const pm_run_options_t* opt_in, pm_run_summary_t* ou
           PM_CUDA(c, cudaMemsetAsync(&c->cnt->found, 0, sizeof(DevCounters) - offsetof(DevCounters, found), st));
           PM_CUDA(c, cudaMemsetAsync(c->hset, 0xFF, c->hset_use * sizeof(unsigned long long), st));
           NlcArgs t = nlc_args(c, nullptr, 0);
-          k_fz_sources<<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], cur, c->ok, c->src_list, c->pool);
+          k_fz_sources<<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], cur, c->ok, c->src_list, c->pool, c->pool_cap);
           PM_LAUNCH_CHECK(c);
           k_nlcc_begin<<<1, 1, 0, st>>>(c->cnt);
           PM_LAUNCH_CHECK(c);
@@ -1228,6 +1272,7 @@ int pm_run_fuzzy(pm_ctx* c, const pm_run_options_t* opt_in, pm_run_summary_t* ou
           if ((rc = sync_counters(c))) return rc;
           if (!(c->h_cnt->overflow || c->h_cnt->pool_n > c->pool_cap)) {
             c->pool_seen[pl] = std::max<uint64_t>(c->pool_seen[pl], c->h_cnt->pool_n);
+            c->pool_cache[c->pat_key] = c->pool_seen;
             break;
           }
           if (attempt >= 6) return fail(c, PM_ERR_CAPACITY, "token pool exhausted");

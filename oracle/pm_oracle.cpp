@@ -436,7 +436,7 @@ struct orc_run {
   std::vector<uint8_t> inmap;     // v in vertex_state_map   (beta.cpp:307)
   std::vector<uint16_t> T_state;  // vertex_state.template_vertices
   std::vector<uint16_t> heard;    // vertex_state.template_neighbors
-  std::vector<uint8_t> estate;    // per distinct slot: 0 absent, 1 in E_v flag 0, 2 in E_v flag 1
+  std::vector<uint8_t> estate;    // per distinct slot: 0 absent, 1 in E_v flag 0, 2 in E_v flag 1 (heard this superstep), 3 flag 1 set by nem_1
   std::vector<orc_row> rows;
   uint64_t iterations = 0;
   double search_seconds = 0;
@@ -573,8 +573,8 @@ struct Ctx {
       R.edges_processed += msgs;
       R.hazards[2] += asym;
       // ---- post step, ee.hpp:827-1027
-      uint64_t removed = 0, grew = 0;
-#pragma omp parallel for reduction(+ : removed, grew) schedule(dynamic, 2048)
+      uint64_t removed = 0, grew = 0, flagged = 0;
+#pragma omp parallel for reduction(+ : removed, grew, flagged) schedule(dynamic, 2048)
       for (uint64_t v = 0; v < V; ++v) {
         if (first && R.active[v] && !R.inmap[v]) {  // :841-852
           R.active[v] = 0;
@@ -593,12 +593,15 @@ struct Ctx {
           R.T_state[v] = ts;
           R.T_arr[v] = ts;
           R.heard[v] = 0;
-          for (uint64_t j = g->rowptr[v]; j < g->rowptr[v + 1]; ++j)
-            R.estate[j] = (R.estate[j] == 2) ? 1 : 0;
+          for (uint64_t j = g->rowptr[v]; j < g->rowptr[v + 1]; ++j) {
+            flagged += R.estate[j] == 3;  // survives this post step on the flag alone, :954-962
+            R.estate[j] = (R.estate[j] >= 2) ? 1 : 0;
+          }
         }
       }
       if (removed) not_finished = true;             // :968-970
       R.hazards[3] += grew;
+      R.hazards[5] += flagged;
       double t1 = now_s();
       orc_row row;
       row.itr = itr; row.kind = 0; row.index = k; row.seconds = t1 - t0;
@@ -687,7 +690,7 @@ struct Ctx {
               auto b = g->col.begin() + g->rowptr[v], en = g->col.begin() + g->rowptr[v + 1];
               auto it = std::lower_bound(b, en, cur[t].parent);
               if (it != en && *it == cur[t].parent && R.estate[it - g->col.begin()])
-                R.estate[it - g->col.begin()] = 2;
+                R.estate[it - g->col.begin()] = 3;  // flag 1 set OUTSIDE LCC
             }
           }
         }

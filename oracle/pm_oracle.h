@@ -112,7 +112,9 @@ uint64_t orc_run_edges_processed(const orc_run*);
  *  [1] nem_1 >=2 distinct parents and an excluded parent was a viable target
  *  [2] LCC delivery along an edge the receiver no longer holds (A.6 #11)
  *  [3] T_arr grew between supersteps (bit resurrected, A.6 #4)
- *  [4] outer loop hit max_iterations                                         */
+ *  [4] outer loop hit max_iterations
+ *  [5] (not a hazard, a coverage counter) edges that survived an LCC post step only because nem_1 had
+ *      set their flag outside LCC (A.6 #11)                                  */
 const uint64_t* orc_run_hazards(const orc_run*);
 /* writes the reference's result tree under outdir (must pre-exist like the
  * reference requires, beta.cpp:413-414,504-535); returns 0 on success */

@@ -21,6 +21,21 @@ def random_multigraph(seed, n, m, dup=0.1, loops=0.05):
     return e
 
 
+def planted(seed, n, m, spec, labelset, copies=3):
+    """random multigraph + labels with `copies` instances of the template planted on random distinct vertices, so
+    that templates which random graphs of this size never contain (6-cycle with chords) end non-trivially"""
+    rng = random.Random(seed * 104729 + 7)
+    edges = random_multigraph(seed, n, m)
+    labels = random_labels(seed, n, labelset)
+    k = len(spec["labels"])
+    for _ in range(copies):
+        vs = rng.sample(range(n), k)
+        for i, v in enumerate(vs):
+            labels[v] = spec["labels"][i]
+        edges += [(vs[a], vs[b]) for a, b in spec["edges"]]
+    return edges, labels
+
+
 def random_labels(seed, n, labelset):
     rng = random.Random(seed * 7919 + 13)
     return np.array([rng.choice(labelset) for _ in range(n)], dtype=np.uint64)
@@ -45,6 +60,54 @@ SPECS = [
     # vertex map until the next call
     ("triangle_d1", dict(PT.triangle(1, 2, 3), diameter=1), [1, 2, 3], 1),
 ]
+
+
+# Inputs on which the reference's QUIRKS are exercised; deterministic in the reference, so the GPU must
+# reproduce them bit for bit.  (name, spec, labelset, tds_from_pl, edge divisor, index of the oracle counter that must fire)
+#  * twin templates: template vertices 0 and 2 share label and neighbourhood.  NLCC clears a bit in T_arr only; the
+#    next LCC post step rewrites T_arr from T_state and RESURRECTS it (A.6 #4, oracle counter [3]).
+#  * bowtie (two triangles sharing an edge) with interleave_lcc off: a successful cycle token flags E_s[sender]
+#    outside LCC; the sender is deactivated by the second constraint before the next LCC call, and the flagged edge
+#    survives that call's first post step (A.6 #11, oracle counter [5]).
+TWIN = {"labels": [1, 2, 1], "edges": [(0, 1), (1, 2)], "diameter": 2, "constraints": [{"walk": [0, 1, 2], "tds": True}]}
+TWIN_BRANCH = {"labels": [1, 2, 1, 3], "edges": [(0, 1), (1, 2), (1, 3)], "diameter": 3,
+               "constraints": [{"walk": [0, 1, 2], "tds": True}]}
+BOWTIE = {"labels": [1, 2, 3, 4], "edges": [(0, 1), (1, 2), (0, 2), (1, 3), (2, 3)], "diameter": 2,
+          "constraints": [{"walk": [0, 1, 2, 0], "cycle": True, "interleave": False},
+                          {"walk": [2, 3, 1, 2], "cycle": True, "interleave": False}]}
+QUIRK_SPECS = [
+    ("twin", TWIN, [1, 2], 0, 3, 3),
+    ("twin_branch", TWIN_BRANCH, [1, 2, 3], 0, 3, 3),
+    ("bowtie_no_interleave", BOWTIE, [1, 2, 3, 4], -1, 1, 5),
+]
+
+
+def quirk_inputs(name, divisor, seeds=range(24)):
+    for seed in seeds:
+        n, m = 60 + 10 * (seed % 4), (220 + 60 * (seed % 5)) // divisor
+        if name.startswith("bowtie"):
+            seed += 130
+        yield seed, n, m
+
+
+# the 3 x 5 grid graph the reference's own graph-construction test is written against
+# (/root/reference/test/include/input_graph.hpp:8-56: 44 directed slots; :58-68: the degrees and CSR offsets it
+# expects; test_delegate_graph_static.cpp:146-152: with delegate threshold 4 the hubs are 6, 7 and 8)
+def grid_graph_slots():
+    slots = []
+    for r in range(3):
+        for c in range(5):
+            v = 5 * r + c
+            for dr, dc in ((-1, 0), (0, -1), (0, 1), (1, 0)):
+                rr, cc = r + dr, c + dc
+                if 0 <= rr < 3 and 0 <= cc < 5:
+                    slots.append((v, 5 * rr + cc))
+    return sorted(slots)
+
+
+GRID_DEGREE = [2, 3, 3, 3, 2, 3, 4, 4, 4, 3, 2, 3, 3, 3, 2]
+GRID_OFFSET = [0, 2, 5, 8, 11, 13, 16, 20, 24, 28, 31, 33, 36, 39, 42, 44]
+GRID_HUBS_AT_THRESHOLD_4 = [6, 7, 8]
 
 
 def pattern_dir(spec):

@@ -18,12 +18,16 @@ def eng():
     e.close()
 
 
-def _compare(oracle, eng, n, edges, labels, spec, tds_from):
+def _compare(oracle, eng, n, edges, labels, spec, tds_from, quirks=False):
     d = cases.pattern_dir(spec)
     g = oracle.Graph.from_undirected(n, edges)
     pat = oracle.Pattern(d)
     ref = oracle.Run(g, labels, pat, tds_from_pl=tds_from, max_iterations=50)
-    assert not ref.hazards[:4].any(), "input makes the reference order dependent"
+    # counters 0..2: the reference itself is order dependent on this input (nothing to compare against);
+    # 3 (a bit resurrected, A.6 #4) and 5 (an edge kept by a flag set outside LCC, A.6 #11) are deterministic
+    # quirks the GPU must reproduce — only the quirk tests feed such inputs
+    assert not ref.hazards[:3].any() and not ref.hazards[4], "input makes the reference order dependent"
+    assert quirks or not ref.hazards[3], "resurrection outside the quirk tests"
     src, dst = cases.slots_of(edges)
     eng.graph_from_slots(n, src, dst)
     eng.labels_set(labels)
@@ -73,6 +77,51 @@ def test_medium_graphs_with_hubs(oracle, eng, name, spec, labelset, tds_from):
     _compare(oracle, eng, n, edges, labels, spec, tds_from)
 
 
+@pytest.mark.parametrize("name,spec,labelset,tds_from,div,counter", cases.QUIRK_SPECS, ids=[q[0] for q in cases.QUIRK_SPECS])
+def test_reference_quirks_are_reproduced(oracle, eng, name, spec, labelset, tds_from, div, counter):
+    """SURVEY A.6 #4 (twin template vertices: a bit NLCC cleared in T_arr is resurrected from T_state by the next
+    LCC post step) and A.6 #11 (an edge flagged by a successful cycle token outside LCC survives one post step
+    after its neighbour was deactivated): per-superstep rows and final sets equal the oracle's, on inputs where
+    the oracle's counters show the quirk occurred."""
+    fired = 0
+    for seed, n, m in cases.quirk_inputs(name, div):
+        edges = cases.random_multigraph(seed, n, m)
+        labels = cases.random_labels(seed, n, labelset)
+        ref = _compare(oracle, eng, n, edges, labels, spec, tds_from, quirks=True)
+        fired += int(ref.hazards[counter] > 0)
+    assert fired >= 5
+
+
+def test_planted_cycle6_ends_non_trivially(oracle, eng):
+    name, spec, labelset, tds_from = cases.SPECS[3]
+    nontrivial = 0
+    for seed in range(8):
+        n, m = 60 + 10 * (seed % 4), 220 + 60 * (seed % 5)
+        edges, labels = cases.planted(seed, n, m, spec, labelset)
+        ref = _compare(oracle, eng, n, edges, labels, spec, tds_from)
+        nontrivial += ref.rows[-1][3] > 0 and len(ref.subgraphs[3]) > 0
+    assert nontrivial >= 6
+
+
+def test_reference_grid_graph(oracle, eng):
+    """the reference's own graph fixture (test/include/input_graph.hpp:8-68) through the GPU graph store, and the
+    hand-derived LCC rows of tests/test_oracle_kat.py::test_grid_graph_lcc_by_hand"""
+    slots = cases.grid_graph_slots()
+    src = np.array([a for a, _ in slots], dtype=np.uint64)
+    dst = np.array([b for _, b in slots], dtype=np.uint64)
+    eng.graph_from_slots(15, src, dst)
+    assert eng.graph_degree().tolist() == cases.GRID_DEGREE
+    rowptr, col = eng.graph_csr()
+    assert rowptr.tolist() == cases.GRID_OFFSET and col.tolist() == [b for _, b in slots]
+    eng.labels_set(np.array(cases.GRID_DEGREE, dtype=np.uint64))
+    spec = {"labels": [2, 3, 4], "edges": [(0, 1), (1, 2)], "diameter": 2, "constraints": []}
+    eng.pattern_load_dir(cases.pattern_dir(spec))
+    eng.run(tds_from_pl=-1)
+    assert eng.rows() == [(0, "LP", 0, 13, 30), (0, "LP", 1, 12, 28)]
+    v, t = eng.active_vertices()
+    assert v.tolist() == [0, 1, 3, 4, 5, 6, 8, 9, 10, 11, 13, 14] and t.tolist() == [1, 2, 2, 1, 2, 4, 4, 2, 1, 2, 2, 1]
+
+
 def test_rmat_graph_is_bit_exact(oracle, eng):
     g = oracle.Graph.rmat(17, 4)
     eng.graph_rmat(17, 4)
@@ -99,6 +148,56 @@ def test_rmat_tree_search(oracle, eng, scale, gen_ranks):
     got, want = cases.engine_summary(eng, pat.n_constraints), cases.run_summary(ref)
     for k in ("rows", "iterations", "vertices", "edges", "subgraphs"):
         assert got[k] == want[k], k
+
+
+def test_baseline_config1_scale21_reference_pattern_dir(oracle, eng):
+    """BASELINE configs[0] exactly: generate_rmat -s 21 with 4 generating ranks, degree-log2 labels, the reference's
+    examples/rmat_log2_tree_pattern/0 verbatim (tests/golden/rmat_log2_tree_pattern/0; checked against
+    /root/reference by tests/test_oracle_kat.py), tree search + enumeration: per-superstep counts, final vertex and
+    edge sets, enumerated subgraph rows and their count."""
+    import os
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rmat_log2_tree_pattern", "0")
+    g = oracle.Graph.rmat(21, 4)
+    labels = g.labels_degree_log2()
+    pat = oracle.Pattern(d)
+    ref = oracle.Run(g, labels, pat, tds_from_pl=4)
+    assert not ref.hazards[:5].any()
+    eng.graph_rmat(21, 4)
+    gi = eng.graph_info()
+    assert gi["n_slots_multi"] == g.n_slots_multi == 2 ** 26 and gi["n_slots"] == g.n_slots
+    assert np.array_equal(eng.graph_degree(), g.degree)
+    eng.labels_degree_log2()
+    assert np.array_equal(eng.labels_get(), labels)
+    eng.pattern_load_dir(d)
+    eng.run(tds_from_pl=4)
+    got, want = cases.engine_summary(eng, pat.n_constraints), cases.run_summary(ref)
+    for k in ("rows", "iterations", "vertices", "edges", "subgraphs"):
+        assert got[k] == want[k], k
+    assert len(want["vertices"]) > 0 and len(want["subgraphs"][4]) > 0
+    assert eng.subgraph_count(4) == len(want["subgraphs"][4])
+
+
+def test_bench_templates_on_rmat_scale20(oracle, eng):
+    """bench.py's cyclic templates (BASELINE configs[2]: triangle, 4-cycle, 6-cycle with chords) with the bench's
+    label choices on R-MAT scale 20: rows, sets and enumerated walks against the oracle."""
+    from fuzzypatternmatching_b200 import patterns as PT
+    g = oracle.Graph.rmat(20, 4)
+    labels = g.labels_degree_log2()
+    eng.graph_rmat(20, 4)
+    eng.labels_degree_log2()
+    for nm, spec in (("triangle_678", PT.triangle(6, 7, 8)), ("cycle4_5678", PT.cycle4(5, 6, 7, 8)),
+                     ("cycle6_chords_456789", PT.cycle6_chords([4, 5, 6, 7, 8, 9]))):
+        d = cases.pattern_dir(spec)
+        tds = PT.tds_from_pl(spec)
+        pat = oracle.Pattern(d)
+        ref = oracle.Run(g, labels, pat, tds_from_pl=tds)
+        assert not ref.hazards[:5].any(), nm
+        eng.pattern_load_dir(d)
+        eng.run(tds_from_pl=tds)
+        got, want = cases.engine_summary(eng, pat.n_constraints), cases.run_summary(ref)
+        for k in ("rows", "iterations", "vertices", "edges", "subgraphs"):
+            assert got[k] == want[k], (nm, k)
+        assert len(want["rows"]) >= 8, nm
 
 
 def test_golden_fixtures_on_gpu(oracle, eng):

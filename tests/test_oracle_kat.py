@@ -191,6 +191,95 @@ def test_planted_tree_is_found_exactly_once(oracle):
     assert r.hazards[:5].tolist() == [0, 0, 0, 0, 0]
 
 
+def test_reference_grid_graph_fixture(oracle):
+    """The one fixture the reference holds for this path's graph store (test/include/input_graph.hpp:8-68,
+    test/test_delegate_graph_static.cpp:146-152): 3 x 5 grid, expected degrees, CSR offsets and hubs."""
+    slots = cases.grid_graph_slots()
+    assert len(slots) == 44
+    src = np.array([a for a, _ in slots], dtype=np.uint64)
+    dst = np.array([b for _, b in slots], dtype=np.uint64)
+    g = oracle.Graph.from_slots(15, src, dst)
+    assert g.degree.tolist() == cases.GRID_DEGREE
+    assert g.rowptr.tolist() == cases.GRID_OFFSET
+    assert [v for v in range(15) if g.degree[v] >= 4] == cases.GRID_HUBS_AT_THRESHOLD_4
+    assert g.labels_degree_log2().tolist() == [2, 2, 2, 2, 2, 2, 3, 3, 3, 2, 2, 2, 2, 2, 2]
+
+
+def test_grid_graph_lcc_by_hand(oracle):
+    """LCC on the reference's grid graph, labels = degree, template path 2 - 3 - 4 (two supersteps, no NLCC).
+    Superstep 0: the degree-3 vertices 2 and 12 have no degree-2 neighbour, enter the map (they hear 7) and leave
+    it.  Superstep 1: vertex 7 only heard 2 and 12 and leaves.  Edge maps hold template-adjacent label pairs only."""
+    slots = cases.grid_graph_slots()
+    spec = {"labels": [2, 3, 4], "edges": [(0, 1), (1, 2)], "diameter": 2, "constraints": []}
+    pat = oracle.Pattern(cases.pattern_dir(spec))
+    src = np.array([a for a, _ in slots], dtype=np.uint64)
+    dst = np.array([b for _, b in slots], dtype=np.uint64)
+    g = oracle.Graph.from_slots(15, src, dst)
+    r = oracle.Run(g, np.array(cases.GRID_DEGREE, dtype=np.uint64), pat, tds_from_pl=-1)
+    assert r.rows == [(0, "LP", 0, 13, 30), (0, "LP", 1, 12, 28)]
+    v, t = r.active_vertices()
+    assert v.tolist() == [0, 1, 3, 4, 5, 6, 8, 9, 10, 11, 13, 14]
+    assert t.tolist() == [1, 2, 2, 1, 2, 4, 4, 2, 1, 2, 2, 1]
+    e = set(map(tuple, r.active_edges.tolist()))
+    assert (6, 7) not in e and (1, 2) not in e and (6, 1) in e and (1, 6) in e and len(e) == 28
+
+
+def test_twin_template_bit_is_resurrected_by_hand(oracle):
+    """SURVEY A.6 #4 on two vertices v(1) - u(2), template path 1 - 2 - 1 (twins 0 and 2), TDS walk 0 1 2.
+    The walk fails (no second label-1 vertex): bit 0 of T_arr(v) is cleared.  In the next LCC superstep u hears
+    only {2} and leaves, while v's post step rewrites T_arr from T_state = {0, 2}: the bit is back for one
+    superstep, then v hears nobody and leaves."""
+    r = _run(oracle, 2, [(0, 1)], [1, 2], cases.TWIN, tds_from=0, max_iterations=10)
+    assert r.rows == [(0, "LP", 0, 2, 2), (0, "LP", 1, 2, 2), (0, "TP", 0, 2, 2),
+                      (0, "LP", 0, 1, 1), (0, "LP", 1, 0, 0), (1, "LP", 0, 0, 0), (1, "LP", 1, 0, 0)]
+    assert r.iterations == 2 and r.hazards[3] == 1 and not r.hazards[:3].any()
+
+
+@pytest.mark.parametrize("name,spec,labelset,tds_from,div,counter", cases.QUIRK_SPECS, ids=[s[0] for s in cases.QUIRK_SPECS])
+def test_quirk_inputs_equal_literal_execution(oracle, name, spec, labelset, tds_from, div, counter):
+    """The quirk inputs (A.6 #4 resurrection, A.6 #11 flag set outside LCC): the oracle equals the literal
+    transliteration of the reference visitors under randomised delivery, and the quirk really occurs."""
+    from oracle.ref_literal import LiteralRun, PatternFiles
+    d = cases.pattern_dir(spec)
+    fired = 0
+    for seed, n, m in cases.quirk_inputs(name, div, range(10)):
+        n, m = min(n, 50), m * 2 // 3
+        edges = cases.random_multigraph(seed, n, m)
+        labels = cases.random_labels(seed, n, labelset)
+        g = oracle.Graph.from_undirected(n, edges)
+        r = oracle.Run(g, labels, oracle.Pattern(d), tds_from_pl=tds_from, max_iterations=50)
+        assert not r.hazards[:3].any() and not r.hazards[4]
+        fired += int(r.hazards[counter] > 0)
+        want = cases.run_summary(r)
+        slots = []
+        for a, b in edges:
+            slots += [(a, b), (b, a)]
+        for s in (0, 1):
+            L = LiteralRun(n, slots, labels.tolist(), PatternFiles(d), seed=seed * 31 + s, tds_from_pl=tds_from)
+            assert not L.errors
+            assert L.rows == want["rows"] and L.iterations == want["iterations"]
+            assert L.final_vertices() == want["vertices"] and L.final_edges() == want["edges"]
+    assert fired >= 2
+
+
+def test_reference_example_pattern_fixture_is_verbatim():
+    """tests/golden/rmat_log2_tree_pattern/0 is the reference's examples/rmat_log2_tree_pattern/0 (data files,
+    BASELINE configs[0]); where the reference tree is present (not on the GPU box) the copy is checked byte for
+    byte, and the in-code spec PT.RMAT_LOG2_TREE must describe the same template."""
+    gold = os.path.join(HERE, "golden", "rmat_log2_tree_pattern", "0")
+    ref = "/root/reference/examples/rmat_log2_tree_pattern/0"
+    names = ["pattern_edge", "pattern_edge_data", "pattern_nlc", "pattern_non_local_constraint", "pattern_stat",
+             "pattern_vertex", "pattern_vertex_data"]
+    if os.path.isdir(ref):
+        for n in names:
+            assert open(os.path.join(gold, n), "rb").read() == open(os.path.join(ref, n), "rb").read(), n
+    mine = cases.pattern_dir(PT.RMAT_LOG2_TREE)
+    num = lambda p: [[int(x) for x in l.replace(":", " ").split()] for l in open(p).read().splitlines() if l.strip()]  # noqa: E731
+    for n in ("pattern_edge", "pattern_vertex_data", "pattern_nlc"):
+        assert num(os.path.join(gold, n)) == num(os.path.join(mine, n)), n
+    assert num(os.path.join(gold, "pattern_non_local_constraint"))[4] == num(os.path.join(mine, "pattern_non_local_constraint"))[4]
+
+
 def test_lcc_only_runs_to_a_vertex_fixed_point(oracle):
     spec = PT.RMAT_LOG2_TREE
     edges = cases.random_multigraph(4, 80, 300)

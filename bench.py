@@ -45,15 +45,39 @@ def write_patterns(workload):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md): NVML polled every 20 ms from a
+    thread (nvidia-smi -lms needs most of a second to start, longer than a short timed region); nvidia-smi is the
+    fallback when NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index):
         self.idx, self.proc, self.lines = gpu_index, None, []
+        self.sm, self.mask, self.stop_flag, self.t, self.max_mhz, self.nvml = [], 0, False, None, None, None
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.idx])
+            except (ValueError, IndexError):
+                pass
+        return self.idx
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.nvml = (pynvml, h)
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -63,11 +87,28 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        pynvml, h = self.nvml
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                self.mask |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+            except Exception:
+                pass
+            time.sleep(0.02)
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line)
 
     def stop(self):
+        if self.nvml:
+            self.stop_flag = True
+            self.t.join(timeout=1.0)
+            sm = sorted(self.sm)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(n for b, n in self.REASONS.items() if self.mask & b), "samples": len(sm),
+                    "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -87,7 +128,7 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def host_threads():
@@ -400,7 +441,9 @@ def main():
                          "templates, %d steps, %d host threads" % (cs, r["steps_done"], r["cores"])}
 
     if rank == 0:
+        free_b, total_b = torch.cuda.mem_get_info()
         config.update({"inputs_exceed_l2": gi["n_slots_padded"] * 4 > 126e6, "graph_build_seconds": build_s,
+                       "device_bytes_in_use_rank0": int(total_b - free_b), "graph_store_bytes_rank0": gi["device_bytes"],
                        "directed_edge_slots": n_global_edges, "distinct_slots_rank0": gi["n_slots"],
                        "multi_gpu": ("one graph, 1-D partition owner(v) = v mod %d, per-GPU share = scale %d" % (world, args.scale))
                        if world > 1 else "single gpu"})

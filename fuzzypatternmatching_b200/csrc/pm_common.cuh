@@ -146,11 +146,19 @@ struct pm_ctx {
   uint32_t* deg = nullptr;     // [V] distinct-neighbour degree
   uint32_t* degm = nullptr;    // [V] multigraph out-degree (duplicates + self loops) -> labels
   uint32_t* col0 = nullptr;    // [Epad] pristine adjacency: sorted, distinct, rows padded to 8 with PM_SENTINEL
-  uint32_t* colw = nullptr;    // [Epad] working adjacency: first adeg[v] slots of a row = keys(E_v)
+  uint32_t* colw = nullptr;    // [colw_cap] DENSE working adjacency (per pattern): row of local compact id i starts at sector
+                               // rowc[i] and has room for deg(v) slots; its first adeg[i] slots = keys(E_v)
+  uint64_t colw_cap = 0;       // slots allocated (grow only)
+  void* scan_tmp = nullptr;    // cub scratch of the row-start prefix
+  size_t scan_tmp_bytes = 0;
+  uint32_t* h_misc = nullptr;  // pinned: small read-backs ([0] = sectors the dense working adjacency needs)
   uint64_t* label = nullptr;   // [V] vertex labels
   uint8_t* lab8 = nullptr;     // [V] labels as bytes when every label is < 64 (degree labels always are)
   unsigned long long* sig = nullptr;  // [V] bit l set iff some distinct neighbour carries label l (labels < 64)
-  uint8_t* lab0 = nullptr;     // [Epad] label of the neighbour stored in col0 (labels < 64)
+  uint8_t* lab0 = nullptr;     // [Epad] label of the neighbour stored in col0 (labels < 64); with packed labels only the
+                               // run_fuzzy path asks for it (built on demand)
+  uint32_t col_shift = 0;      // != 0: PACKED labels — a col0 slot is (label of the neighbour << col_shift) | neighbour id,
+                               // chosen when id bits + label bits <= 32: the first scan streams ONE array
   bool labels_small = false;   // lab8 / sig are valid
   bool has_graph = false, has_labels = false;
 
@@ -162,8 +170,8 @@ struct pm_ctx {
   // ---- per-pattern state (device) -----------------------------------------------
   uint16_t* S = nullptr;    // [V] template_vertices[v] (T_arr) while v is active and in the map, else 0
                             // (vertex_state.template_vertices, T_state, lives in the frontier entries)
-  uint32_t* adeg = nullptr; // [nloc] |E_v|, by LOCAL compact id (cid - off[rank])
-  uint32_t* rowc = nullptr; // [nloc] row start (sectors), by local compact id
+  uint32_t* adeg = nullptr; // [nloc + 1] |E_v|, by LOCAL compact id (cid - off[rank])
+  uint32_t* rowc = nullptr; // [nloc + 1] row start (sectors) in colw, by local compact id
   uint32_t* vid = nullptr;  // [Vs] compact id -> slot (replicated)
   uint8_t* clsc = nullptr;  // [Vs] label class by compact id (replicated)
   uint32_t* fw = nullptr;   // [Vs / 16] per 16 slots: survivors before them in their tile << 16 | survivor bits (replicated)

@@ -37,6 +37,7 @@ struct FzArgs {
   uint16_t* S;
   DevCounters* cnt;
   RowStat* row;
+  uint32_t idmask;  // id bits of a col0 slot (packed labels ride above them)
 };
 
 __device__ __forceinline__ int fz_q0(uint32_t lm) { return __ffs(lm) - 1; }  // first template vertex of the label
@@ -119,7 +120,7 @@ __global__ void __launch_bounds__(kBlock) k_fz_scan(FzArgs a, uint4* __restrict_
         for (int k = 0; k < 4; ++k) need = need || (j0 + k < d && ((rq & ~heard) >> ((l4 >> (8 * k)) & 63u)) & 1ull);
         if (need) {
           const uint4 q = *reinterpret_cast<const uint4*>(a.col0 + row + j0);
-          const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+          const uint32_t u[4] = {q.x & a.idmask, q.y & a.idmask, q.z & a.idmask, q.w & a.idmask};
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint32_t lab = (l4 >> (8 * k)) & 63u;
@@ -265,7 +266,7 @@ __global__ void __launch_bounds__(kBlock) k_fz_expand(FzArgs a, NlcArgs t, int h
         q = *reinterpret_cast<const uint4*>(a.col0 + row + j0);
         l4 = *reinterpret_cast<const uint32_t*>(a.lab0 + row + j0);
       }
-      const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+      const uint32_t u[4] = {q.x & a.idmask, q.y & a.idmask, q.z & a.idmask, q.w & a.idmask};
       bool ins[4];
       uint2 tok[4];
 #pragma unroll
@@ -300,10 +301,10 @@ __global__ void __launch_bounds__(kBlock) k_fz_final(FzArgs a, NlcArgs t, int hl
     const uint32_t d = e;
     while (b < e) {
       const uint32_t mid = (b + e) >> 1;
-      const uint32_t x = a.col0[row + mid];
+      const uint32_t x = a.col0[row + mid] & a.idmask;
       if (x < s) b = mid + 1; else e = mid;
     }
-    if (b < d && a.col0[row + b] == s) {
+    if (b < d && (a.col0[row + b] & a.idmask) == s) {
       t.ok[s] = 1;
       t.cnt->found = 1u;
     }

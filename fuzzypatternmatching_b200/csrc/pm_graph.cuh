@@ -208,10 +208,12 @@ __global__ void k_labels_to_bytes(const uint64_t* __restrict__ label, uint64_t V
 // lets the first LCC superstep decide most candidates without walking their rows.
 // 8-lane groups take rows of up to kSigBig slots; longer rows are queued for k_build_sig_big.
 #define PM_SIG_BIG 2048u
+// idmask: the id bits of a col0 slot as it stands (a previous labelling may have packed labels into it);
+// shift != 0: pack the new label of every neighbour into its slot (and write no label stream), else strip.
 __global__ void __launch_bounds__(256) k_build_sig(const uint32_t* __restrict__ rowblk, const uint32_t* __restrict__ deg,
-                                                   const uint32_t* __restrict__ col0, const uint8_t* __restrict__ lab8,
+                                                   uint32_t* __restrict__ col0, const uint8_t* __restrict__ lab8,
                                                    uint64_t V, unsigned long long* __restrict__ sig,
-                                                   uint8_t* __restrict__ lab0,
+                                                   uint8_t* __restrict__ lab0, uint32_t idmask, uint32_t shift,
                                                    uint32_t* __restrict__ big_list, uint32_t* __restrict__ big_n) {
   const uint32_t lane = threadIdx.x & 31, gl = lane & 7, gw = lane >> 3;
   const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -230,18 +232,26 @@ __global__ void __launch_bounds__(256) k_build_sig(const uint32_t* __restrict__ 
     for (uint32_t p = 0; p < maxp; ++p) {
       const uint32_t j0 = p * 32 + gl * 4;
       if (j0 < d) {
-        const uint4 q = *reinterpret_cast<const uint4*>(col0 + row + j0);
-        const uint32_t l0 = lab8[q.x];
-        const uint32_t l1 = j0 + 1 < d ? (uint32_t)lab8[q.y] : 0u;
-        const uint32_t l2 = j0 + 2 < d ? (uint32_t)lab8[q.z] : 0u;
-        const uint32_t l3 = j0 + 3 < d ? (uint32_t)lab8[q.w] : 0u;
+        uint4 q = *reinterpret_cast<const uint4*>(col0 + row + j0);
+        const uint32_t i0 = q.x & idmask, i1 = q.y & idmask, i2 = q.z & idmask, i3 = q.w & idmask;
+        const uint32_t l0 = lab8[i0];
+        const uint32_t l1 = j0 + 1 < d ? (uint32_t)lab8[i1] : 0u;
+        const uint32_t l2 = j0 + 2 < d ? (uint32_t)lab8[i2] : 0u;
+        const uint32_t l3 = j0 + 3 < d ? (uint32_t)lab8[i3] : 0u;
         m |= 1ull << l0;
         if (j0 + 1 < d) m |= 1ull << l1;
         if (j0 + 2 < d) m |= 1ull << l2;
         if (j0 + 3 < d) m |= 1ull << l3;
-        // the label stream of the row (padding slots carry label 0); rows start sector aligned
-        *reinterpret_cast<uint32_t*>(lab0 + row + j0) = l0 | (l1 << 8) | (l2 << 16) | (l3 << 24);
-      } else if (j0 < ((d + 7u) & ~7u)) {
+        if (lab0)  // the label stream of the row (padding slots carry label 0); rows start sector aligned
+          *reinterpret_cast<uint32_t*>(lab0 + row + j0) = l0 | (l1 << 8) | (l2 << 16) | (l3 << 24);
+        if (shift != 0u || idmask != 0xFFFFFFFFu) {  // (re)pack or strip the labels carried by the slots themselves
+          q.x = i0 | (l0 << shift);
+          if (j0 + 1 < d) q.y = i1 | (l1 << shift);
+          if (j0 + 2 < d) q.z = i2 | (l2 << shift);
+          if (j0 + 3 < d) q.w = i3 | (l3 << shift);
+          *reinterpret_cast<uint4*>(col0 + row + j0) = q;
+        }
+      } else if (lab0 && j0 < ((d + 7u) & ~7u)) {
         *reinterpret_cast<uint32_t*>(lab0 + row + j0) = 0u;
       }
     }
@@ -253,8 +263,9 @@ __global__ void __launch_bounds__(256) k_build_sig(const uint32_t* __restrict__ 
 }
 
 __global__ void __launch_bounds__(1024) k_build_sig_big(const uint32_t* __restrict__ rowblk, const uint32_t* __restrict__ deg,
-                                                        const uint32_t* __restrict__ col0, const uint8_t* __restrict__ lab8,
+                                                        uint32_t* __restrict__ col0, const uint8_t* __restrict__ lab8,
                                                         unsigned long long* __restrict__ sig, uint8_t* __restrict__ lab0,
+                                                        uint32_t idmask, uint32_t shift,
                                                         const uint32_t* __restrict__ big_list, const uint32_t* __restrict__ big_n) {
   __shared__ unsigned long long s_m[32];
   const uint32_t n = *big_n;
@@ -264,9 +275,13 @@ __global__ void __launch_bounds__(1024) k_build_sig_big(const uint32_t* __restri
     unsigned long long m = 0;
     const uint32_t padded = (d + 7u) & ~7u;
     for (uint32_t j = threadIdx.x; j < padded; j += blockDim.x) {
-      const uint8_t l = j < d ? lab8[col0[row + j]] : (uint8_t)0;
-      if (j < d) m |= 1ull << l;
-      lab0[row + j] = l;
+      const uint32_t id = j < d ? col0[row + j] & idmask : 0u;
+      const uint8_t l = j < d ? lab8[id] : (uint8_t)0;
+      if (j < d) {
+        m |= 1ull << l;
+        if (shift != 0u || idmask != 0xFFFFFFFFu) col0[row + j] = id | ((uint32_t)l << shift);
+      }
+      if (lab0) lab0[row + j] = l;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m |= __shfl_xor_sync(0xffffffffu, m, o);
@@ -281,21 +296,65 @@ __global__ void __launch_bounds__(1024) k_build_sig_big(const uint32_t* __restri
   }
 }
 
+// col0 slots back to plain neighbour ids (the labels they carried no longer apply)
+__global__ void k_col0_strip(uint32_t* __restrict__ col0, uint64_t n, uint32_t idmask) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const uint32_t q = col0[i];
+    if (q != PM_SENTINEL) col0[i] = q & idmask;
+  }
+}
+
+// the label stream of the run_fuzzy path from packed slots (values in padding slots are never read: rows are
+// walked up to their degree)
+__global__ void k_unpack_lab0(const uint32_t* __restrict__ col0, uint64_t n, uint32_t shift, uint8_t* __restrict__ lab0) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) lab0[i] = (uint8_t)(col0[i] >> shift);
+}
+
+inline uint32_t col_idmask(const pm_ctx* c) { return c->col_shift ? (1u << c->col_shift) - 1u : 0xFFFFFFFFu; }
+
+inline int ensure_lab0(pm_ctx* c) {
+  if (c->lab0 || !c->labels_small) return 0;
+  int rc;
+  if ((rc = dev_alloc(c, &c->lab0, c->Epad + 64, &c->graph_bytes))) return rc;
+  k_unpack_lab0<<<grid_for(), kBlock, 0, c->stream>>>(c->col0, c->Epad + 64, c->col_shift, c->lab0);
+  c->launches++;
+  return 0;
+}
+
 // after the labels changed: byte labels + neighbour-label signatures (labels < 64 only).
 // c->label holds the labels of the LOCAL rows; lab8 is replicated (indexed by slot) because the
 // label of a neighbour owned by another rank is needed to build lab0 and the signatures.
-inline int labels_derive(pm_ctx* c, bool small) {
+// max_label: largest label value (sizes the packed label field)
+inline int labels_derive(pm_ctx* c, bool small, uint64_t max_label) {
   dev_free(c->lab8);
   dev_free(c->sig);
   dev_free(c->lab0);
   c->labels_small = false;
-  if (!small) return 0;
+  const uint32_t old_mask = col_idmask(c);
+  if (!small) {
+    if (c->col_shift) {
+      k_col0_strip<<<grid_for(), kBlock, 0, c->stream>>>(c->col0, c->Epad, old_mask);
+      c->launches++;
+      c->col_shift = 0;
+    }
+    return 0;
+  }
+  // packed labels: the label of every neighbour rides in the unused high bits of its slot when
+  // id bits + label bits <= 32 (R-MAT scale 26 on one GPU with degree labels: 26 + 6)
+  uint32_t idbits = 1, labbits = 1;
+  while (idbits < 32 && ((c->nlmax * c->n_ranks - 1) >> idbits)) ++idbits;
+  while (labbits < 7 && (max_label >> labbits)) ++labbits;
+  const uint32_t new_shift = (idbits + labbits <= 32 && !getenv("PM_NO_PACK")) ? idbits : 0u;
   int rc;
   uint32_t *big_list = nullptr, *big_n = nullptr;
   const uint64_t Vs = c->nlmax * c->n_ranks, base = c->nlmax * c->rank;
   if ((rc = dev_alloc(c, &c->lab8, Vs, &c->graph_bytes))) return rc;
   if ((rc = dev_alloc(c, &c->sig, c->nloc, &c->graph_bytes))) return rc;
-  if ((rc = dev_alloc(c, &c->lab0, c->Epad + 64, &c->graph_bytes))) return rc;
+  if (!new_shift && (rc = dev_alloc(c, &c->lab0, c->Epad + 64, &c->graph_bytes))) return rc;
   if ((rc = dev_alloc(c, &big_list, c->Epad / PM_SIG_BIG + 1024))) return rc;
   if ((rc = dev_alloc(c, &big_n, 1))) { dev_free(big_list); return rc; }
   cudaStream_t st = c->stream;
@@ -303,9 +362,11 @@ inline int labels_derive(pm_ctx* c, bool small) {
   k_labels_to_bytes<<<grid_for(), kBlock, 0, st>>>(c->label, c->nloc, c->lab8 + base);
   if ((rc = comm_allgather_slots(c, c->lab8))) { dev_free(big_list); dev_free(big_n); return rc; }
   // signatures and the label stream lab0 come out of the same pass over the adjacency (one gather per slot)
-  cudaMemsetAsync(c->lab0 + c->Epad, 0, 64, st);
-  k_build_sig<<<grid_for(), 256, 0, st>>>(c->rowblk, c->deg, c->col0, c->lab8, c->nloc, c->sig, c->lab0, big_list, big_n);
-  k_build_sig_big<<<148, 1024, 0, st>>>(c->rowblk, c->deg, c->col0, c->lab8, c->sig, c->lab0, big_list, big_n);
+  if (c->lab0) cudaMemsetAsync(c->lab0 + c->Epad, 0, 64, st);
+  k_build_sig<<<grid_for(), 256, 0, st>>>(c->rowblk, c->deg, c->col0, c->lab8, c->nloc, c->sig, c->lab0, old_mask, new_shift,
+                                          big_list, big_n);
+  k_build_sig_big<<<148, 1024, 0, st>>>(c->rowblk, c->deg, c->col0, c->lab8, c->sig, c->lab0, old_mask, new_shift, big_list, big_n);
+  c->col_shift = new_shift;
   c->launches += 3;
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -326,7 +387,7 @@ inline void graph_free(pm_ctx* c) {
   dev_free(c->deg);
   dev_free(c->degm);
   dev_free(c->col0);
-  dev_free(c->colw);
+  c->col_shift = 0;
   dev_free(c->label);
   c->has_graph = c->has_labels = false;
   c->graph_bytes = 0;
@@ -535,9 +596,7 @@ inline int graph_build_from_device_slots(pm_ctx* c, uint64_t V, uint64_t n_in, c
   c->Epad = (uint64_t)h_total_sectors * 8;
   const uint64_t alloc_slots = c->Epad + 64;
   PM_G(dev_alloc(c, &c->col0, alloc_slots, &bytes));
-  PM_G(dev_alloc(c, &c->colw, alloc_slots, &bytes));
   PM_GC(cudaMemsetAsync(c->col0, 0xFF, alloc_slots * sizeof(uint32_t), st));
-  PM_GC(cudaMemsetAsync(c->colw, 0xFF, alloc_slots * sizeof(uint32_t), st));
   if (h_nuniq) {
     k_scatter_cols<<<grid, kBlock, 0, st>>>(ukeys, h_nuniq, base, c->rowblk, ustart, c->col0);
     c->launches++;
@@ -586,8 +645,10 @@ inline int graph_build_from_host_csr(pm_ctx* c, uint64_t V, uint64_t n_rows, con
   void* tmp = nullptr;
   cudaStream_t cs = nullptr;
   std::vector<cudaEvent_t> evs;
+  uint32_t* stage[2] = {nullptr, nullptr};
   auto cleanup = [&]() {
     dev_free(d_rowptr); dev_free(d_degm64); dev_free(d_total); dev_free(sectors);
+    dev_free(stage[0]); dev_free(stage[1]);
     if (tmp) cudaFree(tmp);
     tmp = nullptr;
     for (auto e : evs) cudaEventDestroy(e);
@@ -634,39 +695,57 @@ inline int graph_build_from_host_csr(pm_ctx* c, uint64_t V, uint64_t n_rows, con
   c->Epad = (uint64_t)h_total * 8;
   lap("row pointers, degrees, scan");
   const uint64_t alloc_slots = c->Epad + 64;
-  if ((rc = dev_alloc(c, &c->col0, alloc_slots, &bytes)) || (rc = dev_alloc(c, &c->colw, alloc_slots, &bytes))) {
+  if ((rc = dev_alloc(c, &c->col0, alloc_slots, &bytes))) {
     cleanup();
     return rc;
   }
-  lap("alloc col0/colw");
+  lap("alloc col0");
   PM_GC(cudaMemsetAsync(c->col0 + c->Epad, 0xFF, 64 * 4, st));
   if (E) {
     PM_GC(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
-    const uint64_t n_chunks = std::max<uint64_t>(1, std::min<uint64_t>(32, E >> 24));  // >= 64 MiB per chunk
-    uint64_t v0 = 0;
+    // chunks of whole rows, >= 64 MiB each; two staging buffers: chunk k + 1 travels while chunk k is placed
+    const uint64_t n_chunks = std::max<uint64_t>(1, std::min<uint64_t>(32, E >> 24));
+    std::vector<std::pair<uint64_t, uint64_t>> chunks;
+    uint64_t v0 = 0, max_slots = 0;
     for (uint64_t k = 1; k <= n_chunks && v0 < n_rows; ++k) {
       // rows [v0, v1): v1 = first row that starts at or after the k-th share of the slots
       uint64_t v1 = n_rows;
       if (k < n_chunks) v1 = (uint64_t)(std::lower_bound(h_rowptr + v0, h_rowptr + n_rows, E / n_chunks * k) - h_rowptr);
       if (v1 <= v0) continue;
-      const uint64_t b = h_rowptr[v0], e = h_rowptr[v1];
+      chunks.push_back({v0, v1});
+      max_slots = std::max<uint64_t>(max_slots, h_rowptr[v1] - h_rowptr[v0]);
+      v0 = v1;
+    }
+    if ((rc = dev_alloc(c, &stage[0], max_slots + 4)) || (rc = dev_alloc(c, &stage[1], max_slots + 4))) {
+      cleanup();
+      return rc;
+    }
+    std::vector<cudaEvent_t> placed(chunks.size(), nullptr);
+    for (size_t k = 0; k < chunks.size(); ++k) {
+      const uint64_t a0 = chunks[k].first, a1 = chunks[k].second;
+      const uint64_t b = h_rowptr[a0], e = h_rowptr[a1];
+      uint32_t* buf = stage[k & 1];
       cudaEvent_t ev;
       PM_GC(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
       evs.push_back(ev);
-      if (e > b) PM_GC(cudaMemcpyAsync(c->colw + b, h_col + b, (e - b) * 4, cudaMemcpyHostToDevice, cs));
+      if (k >= 2) PM_GC(cudaStreamWaitEvent(cs, placed[k - 2], 0));  // the buffer's previous chunk has been placed
+      if (e > b) PM_GC(cudaMemcpyAsync(buf, h_col + b, (e - b) * 4, cudaMemcpyHostToDevice, cs));
       PM_GC(cudaEventRecord(ev, cs));
       PM_GC(cudaStreamWaitEvent(st, ev, 0));
+      // the kernels index the staged columns with the CSR's own offsets: hand them the buffer shifted by the chunk start
+      const uint32_t* col_view = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(buf) - (uintptr_t)b * 4);
       if (c->n_ranks == 1)
-        k_csr_place<<<grid, kBlock, 0, st>>>(d_rowptr, c->colw, v0, v1, c->rowblk, c->col0);
+        k_csr_place<<<grid, kBlock, 0, st>>>(d_rowptr, col_view, a0, a1, c->rowblk, c->col0);
       else  // vertex ids -> slots, rows re-ordered by slot
-        k_csr_place_slots<<<grid, kBlock, 0, st>>>(d_rowptr, c->colw, v0, v1, c->rowblk, c->col0, (uint32_t)c->n_ranks,
+        k_csr_place_slots<<<grid, kBlock, 0, st>>>(d_rowptr, col_view, a0, a1, c->rowblk, c->col0, (uint32_t)c->n_ranks,
                                                    (uint32_t)c->nlmax);
       c->launches++;
-      v0 = v1;
+      PM_GC(cudaEventCreateWithFlags(&placed[k], cudaEventDisableTiming));
+      evs.push_back(placed[k]);
+      PM_GC(cudaEventRecord(placed[k], st));
     }
     PM_GC(cudaGetLastError());
   }
-  PM_GC(cudaMemsetAsync(c->colw, 0xFF, alloc_slots * 4, st));  // the staging copy is spent
   PM_GC(cudaStreamSynchronize(st));
 #undef PM_GC
   lap("adjacency copy + placement");

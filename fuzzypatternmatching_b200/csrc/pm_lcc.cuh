@@ -117,6 +117,8 @@ struct LccArgs {
   uint32_t base;  // first compact id of this rank: rank-local arrays (adeg, rowc) are indexed by cid - base
   int par;        // delta inbox the commit of this superstep publishes into
   const uint2* fwx;        // slot -> compact id, per 16 slots: {cid of the word's first survivor, survivor bits}
+  const uint32_t* rowc;    // [n_c + 1] row start (sectors) in the DENSE working adjacency, by local compact id
+  uint32_t col_shift;      // packed labels: a col0 slot is (label << col_shift) | id
 };
 
 // frontier entry: x = compact id, y = row start in sectors (PM_TOMB: the row is in the big-row list),
@@ -342,8 +344,8 @@ __global__ void __launch_bounds__(kBlock) k_init_assign(const uint8_t* __restric
                                                          const uint32_t* __restrict__ fw, const uint32_t* __restrict__ tb,
                                                          uint64_t n_slots, uint32_t own_lo, uint32_t own_hi,
                                                          uint16_t* __restrict__ S, uint8_t* __restrict__ clsc,
-                                                         uint32_t* __restrict__ vid, uint32_t* __restrict__ rowc,
-                                                         uint2* __restrict__ fwx,
+                                                         uint32_t* __restrict__ vid, uint32_t* __restrict__ adeg,
+                                                         uint32_t* __restrict__ rowc, uint2* __restrict__ fwx,
                                                          const unsigned long long* __restrict__ sig,
                                                          uint4* fr_main, uint4* fr_big, DevCounters* cnt, int buf) {
   __shared__ uint8_t s_cl[64];
@@ -393,7 +395,8 @@ __global__ void __launch_bounds__(kBlock) k_init_assign(const uint8_t* __restric
       clsc[cid] = (uint8_t)c;
       if (slot >= own_lo && slot < own_hi) {
         const uint32_t lcid = cid - off_me, d = deg[slot - own_lo], rb = rowblk[slot - own_lo];
-        rowc[lcid] = rb;
+        adeg[lcid] = d;
+        rowc[lcid] = (d + 7u) >> 3;  // |E_v| can only shrink: the prefix of these is the row start in the dense working adjacency
         // behind the signature filter (sig != null) the T_state the first superstep ends with is known here:
         // heard(v) = OR of the labelmasks of the valid labels in v's signature (see the header above), so the
         // first scan only has to build the edge map
@@ -424,8 +427,9 @@ __global__ void __launch_bounds__(kBlock) k_init_assign(const uint8_t* __restric
 //   FIRST = first superstep of the first iteration: walk the pristine adjacency col0 (all deg[v] slots); a
 //   neighbour's mask is the labelmask of its label (ee.hpp:519-561 sender, :368-404 receiver) and the kept
 //   neighbours are COPIED into the working adjacency; otherwise walk keys(E_v) in colw and compact in place.
-//   STREAM (FIRST only) = labels are bytes < 64 and the label of every neighbour travels next to its id
-//   (lab0): validity is one bit test against the row's valid-label set and the scan needs no gather at all.
+//   STREAM (FIRST only) != 0: labels are bytes < 64 and the label of every neighbour travels with its id — 2: packed
+//   into the high bits of the col0 slot itself (one stream), 1: in the parallel byte array lab0 (ids and labels do
+//   not fit 32 bits together): validity is one bit test against the row's valid-label set, no gather at all.
 //   HEARD = accumulate heard(v) and derive T_state from it.  Off only for the first scan behind the signature
 //   filter, whose entries already carry the T_state the first superstep ends with (k_init_assign).
 //   XLATE (with !FIRST) = the first scan after the first superstep: the rows still hold SLOTS (the first scan
@@ -463,7 +467,7 @@ __device__ __forceinline__ void warp_prefix4(uint32_t n, uint32_t lt, uint32_t& 
   total = __popc(b0) + 2u * __popc(b1) + 4u * __popc(b2);
 }
 
-template <bool FIRST, bool STREAM, bool XLATE, bool HEARD>
+template <bool FIRST, int STREAM, bool XLATE, bool HEARD>
 __global__ void __launch_bounds__(kBlock, 4) k_lcc_scan(LccArgs a, uint4* __restrict__ list,
                                                       const uint32_t* __restrict__ n_ptr, int xlate_only) {
   static_assert(!(FIRST && XLATE) && (FIRST || !STREAM) && (HEARD || FIRST), "unsupported combination");
@@ -474,6 +478,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_lcc_scan(LccArgs a, uint4* __rest
   __shared__ uint4 s_rowp[kBlock / 32][32];
   __shared__ unsigned long long s_vl[(FIRST && STREAM) ? kBlock / 32 : 1][32];
   __shared__ uint32_t s_rout[kBlock / 32][32];
+  __shared__ uint32_t s_drow[FIRST ? kBlock / 32 : 1][32];  // FIRST: row start (sectors) in the dense working adjacency
   __shared__ uint32_t s_hrd[HEARD ? kBlock / 32 : 1][32];
   __shared__ uint8_t s_nz[kBlock / 32][32];
   if (threadIdx.x < 17) s_lm[threadIdx.x] = c_pat.LMc[threadIdx.x];
@@ -485,6 +490,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_lcc_scan(LccArgs a, uint4* __rest
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
   const uint32_t* __restrict__ src = FIRST ? a.col0 : a.colw;
+  const uint32_t idmask = STREAM == 2 ? (1u << a.col_shift) - 1u : 0xFFFFFFFFu;
   unsigned long long scanned = 0, verts = 0;
   for (uint32_t base = warp * 32; base < n; base += nwarps * 32) {
     const uint32_t idx = base + lane;
@@ -498,6 +504,10 @@ __global__ void __launch_bounds__(kBlock, 4) k_lcc_scan(LccArgs a, uint4* __rest
       if (live) Tv = a.S[e.x];
     }
     uint32_t d = Tv ? e.z : 0u;  // Tv == 0: deactivated by NLCC since the last commit (beta.cpp:990-992)
+    // FIRST: the row is read where the graph store keeps it (e.y) and its kept neighbours are written to the
+    // vertex's row of the dense working adjacency, which every later kernel walks (the entry is re-pointed below)
+    uint32_t drow = e.y;
+    if (FIRST && has && live) drow = a.rowc[e.x - a.base];
     const uint32_t NBv = nb_of(Tv);
     unsigned long long VL = 0;   // FIRST && STREAM: the labels a valid neighbour can carry
     if (FIRST && STREAM) VL = valid_labels(NBv);
@@ -522,6 +532,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_lcc_scan(LccArgs a, uint4* __rest
       s_rowp[wid][lane] = make_uint4(e.y, d, first, NBv);
       if (FIRST && STREAM) s_vl[wid][lane] = VL;
       s_rout[wid][lane] = 0u;
+      if (FIRST) s_drow[wid][lane] = drow;
       if (HEARD) s_hrd[wid][lane] = 0u;
       if (nch) s_nz[wid][__popc(longrows & lt)] = (uint8_t)lane;
       __syncwarp();
@@ -546,7 +557,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_lcc_scan(LccArgs a, uint4* __rest
         lN = 0u;
         if (jN < dN) {
           qN = *reinterpret_cast<const uint4*>(src + rowN + jN);
-          if (STREAM) lN = *reinterpret_cast<const uint32_t*>(a.lab0 + rowN + jN);
+          if (STREAM == 1) lN = *reinterpret_cast<const uint32_t*>(a.lab0 + rowN + jN);
         }
       };
       fetch(0u);
@@ -566,11 +577,11 @@ __global__ void __launch_bounds__(kBlock, 4) k_lcc_scan(LccArgs a, uint4* __rest
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const bool act = j0 + k < rd;
-          wr[k] = u[k] & PM_IDMASK;
+          wr[k] = STREAM == 2 ? u[k] & idmask : u[k] & PM_IDMASK;
           uint32_t m = 0;
           bool valid = false;
           if (FIRST && STREAM) {
-            const uint32_t lab = (l4 >> (8 * k)) & 63u;
+            const uint32_t lab = STREAM == 2 ? (u[k] >> a.col_shift) & 63u : (l4 >> (8 * k)) & 63u;
             valid = act && ((rVL >> lab) & 1ull);
             if (HEARD) m = s_lml[lab];
           } else if (act) {
@@ -591,7 +602,8 @@ __global__ void __launch_bounds__(kBlock, 4) k_lcc_scan(LccArgs a, uint4* __rest
         const uint32_t hl = 31u - __clz((H | 1u) & le);  // first lane of my row's segment in this pass
         const uint32_t off = below - __shfl_sync(0xffffffffu, below, hl);
         const uint32_t rout = s_rout[wid][r];
-        uint32_t* __restrict__ p = a.colw + rrow + rout + off;
+        const uint64_t wrow = FIRST ? (uint64_t)s_drow[wid][r] * 8 : rrow;
+        uint32_t* __restrict__ p = a.colw + wrow + rout + off;
         if (nk > 0u) p[0] = outv[0];
         if (nk > 1u) p[1] = outv[1];
         if (nk > 2u) p[2] = outv[2];
@@ -631,6 +643,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_lcc_scan(LccArgs a, uint4* __rest
       }
       scanned += d;
       verts += Tv != 0u;
+      if (FIRST) e.y = drow;
       e.z = out;
       e.w = ts;
       list[idx] = e;
@@ -649,7 +662,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_lcc_scan(LccArgs a, uint4* __rest
 }
 
 // one CTA per high-degree vertex ("delegates across warps and CTAs")
-template <bool FIRST, bool STREAM, bool XLATE, bool HEARD>
+template <bool FIRST, int STREAM, bool XLATE, bool HEARD>
 __global__ void __launch_bounds__(1024) k_lcc_scan_big(LccArgs a, uint4* __restrict__ list,
                                                         const uint32_t* __restrict__ n_ptr, int xlate_only) {
   __shared__ uint16_t s_lm[17];
@@ -670,6 +683,8 @@ __global__ void __launch_bounds__(1024) k_lcc_scan_big(LccArgs a, uint4* __restr
     unsigned long long VL = 0;
     if (FIRST && STREAM) VL = valid_labels(NBv);
     const uint64_t row = (uint64_t)e.y * 8;
+    const uint32_t drow = FIRST ? a.rowc[e.x - a.base] : e.y;  // FIRST: kept neighbours go to the dense working adjacency
+    const uint64_t wrow = (uint64_t)drow * 8;
     const uint32_t* __restrict__ src = FIRST ? a.col0 : a.colw;
     uint32_t outp = 0;  // slots kept so far (every thread tracks the same value)
     uint32_t heard = 0;
@@ -680,7 +695,7 @@ __global__ void __launch_bounds__(1024) k_lcc_scan_big(LccArgs a, uint4* __restr
       uint32_t l4 = 0;
       if (j0 < d) {
         q = *reinterpret_cast<const uint4*>(src + row + j0);
-        if (STREAM) l4 = *reinterpret_cast<const uint32_t*>(a.lab0 + row + j0);
+        if (STREAM == 1) l4 = *reinterpret_cast<const uint32_t*>(a.lab0 + row + j0);
       }
       const uint32_t u[4] = {q.x, q.y, q.z, q.w};
       uint32_t wr[4];  // what is stored back: the id as it stands, or (XLATE) the neighbour's compact id
@@ -688,11 +703,11 @@ __global__ void __launch_bounds__(1024) k_lcc_scan_big(LccArgs a, uint4* __restr
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const bool act = j0 + k < d;
-        wr[k] = u[k] & PM_IDMASK;
+        wr[k] = STREAM == 2 ? u[k] & ((1u << a.col_shift) - 1u) : u[k] & PM_IDMASK;
         uint32_t m = 0;
         bool valid = false;
         if (FIRST && STREAM) {
-          const uint32_t lab = (l4 >> (8 * k)) & 63u;
+          const uint32_t lab = STREAM == 2 ? (u[k] >> a.col_shift) & 63u : (l4 >> (8 * k)) & 63u;
           valid = act && ((VL >> lab) & 1ull);
           if (HEARD) m = s_lml[lab];
         } else if (act) {
@@ -716,7 +731,7 @@ __global__ void __launch_bounds__(1024) k_lcc_scan_big(LccArgs a, uint4* __restr
         if (w < wid) wbase += cw;
         ptotal += cw;
       }
-      uint32_t* __restrict__ p = a.colw + row + wbase + below;
+      uint32_t* __restrict__ p = a.colw + wrow + wbase + below;
       if (nk > 0u) p[0] = outv[0];
       if (nk > 1u) p[1] = outv[1];
       if (nk > 2u) p[2] = outv[2];
@@ -741,6 +756,7 @@ __global__ void __launch_bounds__(1024) k_lcc_scan_big(LccArgs a, uint4* __restr
         if (ts == 0 && (FIRST ? h != 0u : Tv != 0u)) a.cnt->nf = 1u;
       }
       uint4 e2 = e;
+      e2.y = drow;
       e2.z = outp;
       e2.w = ts;
       list[idx] = e2;

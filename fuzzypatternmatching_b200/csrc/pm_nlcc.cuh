@@ -161,6 +161,55 @@ __device__ __forceinline__ void stage_push(WarpStage& w, const bool (&flag)[4], 
   if (w.fill > PM_STAGE_FLUSH) stage_flush(w, dst, cap, counter, overflow);
 }
 
+// all 32 lanes call; a lane appends at most one value (order: lane)
+__device__ __forceinline__ void stage_push1(WarpStage& w, bool flag, uint2 val, uint2* __restrict__ dst,
+                                            unsigned long long cap, unsigned long long* counter, uint32_t* overflow) {
+  const uint32_t m = __ballot_sync(0xffffffffu, flag);
+  if (m == 0u) return;
+  if (flag) w.buf[w.fill + __popc(m & lanemask_lt())] = val;
+  w.fill += __popc(m);
+  if (w.fill > PM_STAGE_FLUSH) stage_flush(w, dst, cap, counter, overflow);
+}
+
+// ---------------------------------------------------------------------------
+// Dealing token rows to lanes.  A warp takes 32 tokens (one per lane), lays the rows E_v of their vertices end
+// to end and deals the SLOTS to its lanes, 32 per pass: every lane of every pass carries one neighbour whatever
+// the row lengths are (rows of pruned graphs hold a handful of slots: a fixed group of lanes per token idles most
+// of them).  Token parameters travel through shared memory; a lane finds its token by a 5-step search over the
+// inclusive prefix of the row lengths.
+// ---------------------------------------------------------------------------
+struct TokBatch {
+  uint32_t (*cum)[32];  // [warp][lane] inclusive prefix of the row lengths
+  uint4 (*tok)[32];     // [warp][lane] {vertex, source, row start (sectors), row length}
+};
+
+// returns the number of slots of the batch; all 32 lanes call
+__device__ __forceinline__ uint32_t deal_begin(const TokBatch& b, uint32_t wid, uint32_t lane, uint32_t v, uint32_t s,
+                                               uint32_t row, uint32_t d) {
+  uint32_t cum = d;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, cum, o);
+    if (lane >= (uint32_t)o) cum += t;
+  }
+  __syncwarp();
+  b.cum[wid][lane] = cum;
+  b.tok[wid][lane] = make_uint4(v, s, row, d);
+  __syncwarp();
+  return __shfl_sync(0xffffffffu, cum, 31);
+}
+
+// slot g of the batch (g < total): its token and the position inside the token's row
+__device__ __forceinline__ uint4 deal_slot(const TokBatch& b, uint32_t wid, uint32_t g, uint32_t& j) {
+  uint32_t idx = 0;  // number of tokens whose rows end at or before g
+#pragma unroll
+  for (int k = 16; k; k >>= 1)
+    if (b.cum[wid][idx + k - 1] <= g) idx += k;
+  const uint4 t = b.tok[wid][idx];
+  j = g - (b.cum[wid][idx] - t.w);
+  return t;
+}
+
 // ---------------------------------------------------------------------------
 // token sources (nem_1.hpp:387-527; tds_batch_1.hpp:1067-1135, 425-512)
 // ---------------------------------------------------------------------------
@@ -278,76 +327,64 @@ __global__ void __launch_bounds__(kBlock) k_nem1_final_cycle(NlcArgs a, int hlev
 // ---------------------------------------------------------------------------
 // nem_1: advance the tokens of level hlevel (accepted at hop hn-1) to hop hn
 // ---------------------------------------------------------------------------
+// dedupe: apply the (vertex, source) aggregation.  Off where duplicates cannot occur (hop 1: the neighbours of
+// a source are distinct) or cannot matter (the level that feeds k_nem1_close_cycle, whose effects are idempotent).
 template <bool FINAL>
-__global__ void __launch_bounds__(kBlock) k_nem1_expand(NlcArgs a, int hlevel, int hn) {
+__global__ void __launch_bounds__(kBlock) k_nem1_expand(NlcArgs a, int hlevel, int hn, int dedupe) {
   __shared__ uint2 s_stage[FINAL ? 1 : (kBlock / 32) * PM_STAGE_CAP];
+  __shared__ uint32_t s_cum[kBlock / 32][32];
+  __shared__ uint4 s_tok[kBlock / 32][32];
+  const TokBatch tb{s_cum, s_tok};
   WarpStage stage{s_stage + (FINAL ? 0 : (threadIdx.x >> 5) * PM_STAGE_CAP), 0u};
   const uint64_t lo = a.cnt->lvl[hlevel], hi = a.cnt->lvl[hlevel + 1];
-  constexpr int GROUP = 8;
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t gl = lane % GROUP, gw = lane / GROUP;
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  const uint32_t ibit = c_nlc.I[hn];
   unsigned long long fan = 0;
-  for (uint64_t base = lo + warp * 4; base < hi; base += nwarps * 4) {
-    const uint64_t t = base + gw;
-    const bool has = t < hi;
-    uint32_t v = 0, s = 0, d = 0;
-    if (has) {
+  for (uint64_t base = lo + warp * 32; base < hi; base += nwarps * 32) {
+    const uint64_t t = base + lane;
+    uint32_t v = 0, s = 0, d = 0, row = 0;
+    if (t < hi) {
       const uint2 tk = a.pool[t];
       v = tk.x;
       s = tk.y;
       d = a.adeg[v];
+      row = a.rowblk[v];
       // a path constraint needs ONE completed walk per source (ack_success just sets
       // token_source_map[s] = 1, nem_1.hpp:326-342): later tokens of an acknowledged source are moot
       if (FINAL && a.ok[s]) d = 0;
     }
-    const uint64_t row = has ? (uint64_t)a.rowblk[v] * 8 : 0;
-    const uint32_t passes = (d + GROUP * 4 - 1) / (GROUP * 4);
-    const uint32_t maxp = __reduce_max_sync(0xffffffffu, passes);
-    for (uint32_t p = 0; p < maxp; ++p) {
-      const uint32_t j0 = p * GROUP * 4 + gl * 4;
-      uint4 q = make_uint4(0, 0, 0, 0);
-      if (j0 < d) {
-        q = *reinterpret_cast<const uint4*>(a.colw + row + j0);
-      }
-      const uint32_t u[4] = {q.x & PM_IDMASK, q.y & PM_IDMASK, q.z & PM_IDMASK, q.w & PM_IDMASK};
-      bool pass_static[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        pass_static[k] = false;
-        bool may = j0 + k < d;
-        if (may) {
-          const uint32_t su = a.S[u[k]];
-          pass_static[k] = su != 0 && ((su >> c_nlc.I[hn]) & 1u);
-        }
+    fan += d;
+    const uint32_t total = deal_begin(tb, wid, lane, v, s, row, d);
+    for (uint32_t g0 = 0; g0 < total; g0 += 32) {
+      const uint32_t g = g0 + lane;
+      bool pass = false;
+      uint32_t u = 0, ts = 0, tv = 0;
+      if (g < total) {
+        uint32_t j;
+        const uint4 tk = deal_slot(tb, wid, g, j);
+        tv = tk.x;
+        ts = tk.y;
+        u = a.colw[(uint64_t)tk.z * 8 + j] & PM_IDMASK;
+        const uint32_t su = a.S[u];
+        pass = su != 0 && ((su >> ibit) & 1u);
       }
       if (FINAL) {
         // max_itr_count == itr_count (nem_1.hpp:661-791)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const bool succ = pass_static[k] && (c_nlc.valid_cycle ? u[k] == s : u[k] != s);
-          if (succ) {
-            a.ok[s] = 1;
-            a.cnt->found = 1u;
-            if (c_nlc.valid_cycle) mark_edge(a, s, v);
-          }
+        if (pass && (c_nlc.valid_cycle ? u == ts : u != ts)) {
+          a.ok[ts] = 1;
+          a.cnt->found = 1u;
+          if (c_nlc.valid_cycle) mark_edge(a, ts, tv);
         }
       } else {
         // interior hop: the source cannot relay (nem_1.hpp:174-177), one token per
         // (vertex, source) (nem_1.hpp:131-139, 270-285)
-        bool ins[4];
-        uint2 tok[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          ins[k] = pass_static[k] && u[k] != s;
-          if (ins[k]) ins[k] = hset_insert(a, u[k], s);
-          tok[k] = make_uint2(u[k], s);
-        }
-        stage_push(stage, ins, tok, a.pool, a.pool_cap, &a.cnt->pool_n, &a.cnt->overflow);
+        bool ins = pass && u != ts;
+        if (ins && dedupe) ins = hset_insert(a, u, ts);
+        stage_push1(stage, ins, make_uint2(u, ts), a.pool, a.pool_cap, &a.cnt->pool_n, &a.cnt->overflow);
       }
     }
-    if (has && gl == 0) fan += d;
   }
   if (!FINAL) stage_flush(stage, a.pool, a.pool_cap, &a.cnt->pool_n, &a.cnt->overflow);
 #pragma unroll
@@ -362,67 +399,65 @@ __global__ void __launch_bounds__(kBlock) k_nem1_expand(NlcArgs a, int hlevel, i
 // arriving at the source can succeed (max_itr_count == itr_count, nem_1.hpp:661-773).
 // So the walk closes iff some u passes the hop-C tests and lies in E_v AND E_s
 // (edge maps are symmetric between live vertices once an LCC call of >= 2 supersteps
-// has run, see pm_lcc.cuh; pm_nlcc checks that precondition): the row of v is
-// streamed and each label-matching neighbour is looked up in the (short, cached) row
-// of s before its mask is gathered.  No level-C tokens are stored or deduplicated.
+// has run, see pm_lcc.cuh; pm_nlcc checks that precondition): the slots of E_v are dealt
+// to the lanes, a neighbour that passes the hop test (one mask gather) is looked up in the
+// (short, cached) row of s.  No level-C tokens are stored or deduplicated.
 // Success acknowledges the source and flags the edge E_s[u] the token would have
 // come back on (nem_1.hpp:764-770).
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock) k_nem1_close_cycle(NlcArgs a, int hlevel, int hn) {
+  __shared__ uint32_t s_cum[kBlock / 32][32];
+  __shared__ uint4 s_tok[kBlock / 32][32];
+  __shared__ uint2 s_src[kBlock / 32][32];  // per token: {row start of E_s (sectors), |E_s|}
+  const TokBatch tb{s_cum, s_tok};
   const uint64_t lo = a.cnt->lvl[hlevel], hi = a.cnt->lvl[hlevel + 1];
-  constexpr int GROUP = 8;
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t gl = lane % GROUP, gw = lane / GROUP;
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  const uint32_t ibit = c_nlc.I[hn];
   unsigned long long fan = 0;
-  for (uint64_t base = lo + warp * 4; base < hi; base += nwarps * 4) {
-    const uint64_t t = base + gw;
-    const bool has = t < hi;
-    uint32_t v = 0, s = 0, d = 0, ds = 0;
-    uint64_t rs = 0;
-    if (has) {
+  for (uint64_t base = lo + warp * 32; base < hi; base += nwarps * 32) {
+    const uint64_t t = base + lane;
+    uint32_t s = 0, d = 0, row = 0, ds = 0, rs = 0;
+    if (t < hi) {
       const uint2 tk = a.pool[t];
-      v = tk.x;
       s = tk.y;
       const uint32_t ss = a.S[s];
       // receiver tests of the closing hop at the source (nem_1.hpp:557-581)
       if (ss != 0 && hop_ok(ss, a.cls[s], hn + 1)) {
-        d = a.adeg[v];
+        d = a.adeg[tk.x];
+        row = a.rowblk[tk.x];
         ds = a.adeg[s];
-        rs = (uint64_t)a.rowblk[s] * 8;
+        rs = a.rowblk[s];
       }
     }
-    const uint64_t row = has ? (uint64_t)a.rowblk[v] * 8 : 0;
-    const uint32_t passes = (d + GROUP * 4 - 1) / (GROUP * 4);
-    const uint32_t maxp = __reduce_max_sync(0xffffffffu, passes);
-    for (uint32_t p = 0; p < maxp; ++p) {
-      const uint32_t j0 = p * GROUP * 4 + gl * 4;
-      uint4 q = make_uint4(0, 0, 0, 0);
-      if (j0 < d) {
-        q = *reinterpret_cast<const uint4*>(a.colw + row + j0);
+    fan += d;
+    __syncwarp();
+    s_src[wid][lane] = make_uint2(rs, ds);
+    const uint32_t total = deal_begin(tb, wid, lane, lane, s, row, d);  // .x carries the token's lane: indexes s_src
+    for (uint32_t g0 = 0; g0 < total; g0 += 32) {
+      const uint32_t g = g0 + lane;
+      if (g >= total) continue;
+      uint32_t j;
+      const uint4 tk = deal_slot(tb, wid, g, j);
+      const uint32_t u = a.colw[(uint64_t)tk.z * 8 + j] & PM_IDMASK;
+      if (u == tk.y) continue;  // the source cannot relay (nem_1.hpp:174-177)
+      const uint32_t su = a.S[u];
+      if (su == 0 || !((su >> ibit) & 1u)) continue;
+      const uint2 sr = s_src[wid][tk.x];
+      const uint64_t rsrc = (uint64_t)sr.x * 8;
+      uint32_t b = 0, e = sr.y;
+      while (b < e) {  // rows stay ascending: compaction is stable
+        const uint32_t mid = (b + e) >> 1;
+        const uint32_t x = a.colw[rsrc + mid] & PM_IDMASK;
+        if (x < u) b = mid + 1; else e = mid;
       }
-      const uint32_t u[4] = {q.x & PM_IDMASK, q.y & PM_IDMASK, q.z & PM_IDMASK, q.w & PM_IDMASK};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        bool may = j0 + k < d && u[k] != s;  // the source cannot relay (nem_1.hpp:174-177)
-        if (!may) continue;
-        uint32_t b = 0, e = ds;
-        while (b < e) {  // rows stay ascending: compaction is stable
-          const uint32_t mid = (b + e) >> 1;
-          const uint32_t x = a.colw[rs + mid] & PM_IDMASK;
-          if (x < u[k]) b = mid + 1; else e = mid;
-        }
-        if (b >= ds || (a.colw[rs + b] & PM_IDMASK) != u[k]) continue;
-        const uint32_t su = a.S[u[k]];
-        if (su != 0 && ((su >> c_nlc.I[hn]) & 1u)) {
-          a.ok[s] = 1;
-          a.cnt->found = 1u;
-          atomicOr(&a.colw[rs + b], 0x80000000u);
-        }
+      if (b < sr.y && (a.colw[rsrc + b] & PM_IDMASK) == u) {
+        a.ok[tk.y] = 1;
+        a.cnt->found = 1u;
+        atomicOr(&a.colw[rsrc + b], 0x80000000u);
       }
     }
-    if (has && gl == 0) fan += d;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) fan += __shfl_xor_sync(0xffffffffu, fan, o);
@@ -550,9 +585,13 @@ __global__ void k_tds_materialize(const uint2* __restrict__ pool, const uint2* _
 // (T_arr ONLY — vertex_state.template_vertices keeps it); with no
 // bit left it is deactivated and leaves the vertex_state_map (S == 0).
 // ---------------------------------------------------------------------------
+// pool_cap / match_cap: a walk that ran out of token pool, key table or match list (match_cap = 0: none kept)
+// leaves the state untouched — the host retries the constraint with larger buffers.
 __global__ void __launch_bounds__(kBlock) k_nlcc_apply(uint16_t* __restrict__ S, const uint8_t* __restrict__ ok,
                                                         const uint32_t* __restrict__ src_list,
-                                                        DevCounters* cnt, int par) {
+                                                        DevCounters* cnt, int par, unsigned long long pool_cap,
+                                                        unsigned long long match_cap) {
+  if (cnt->overflow || cnt->pool_n > pool_cap || (match_cap && (cnt->matches > match_cap || cnt->match_drop))) return;
   const uint32_t n = cnt->n_src;
   const uint32_t nr = (n + 31u) & ~31u;  // whole warps: publish_mask is warp collective
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nr; i += gridDim.x * blockDim.x) {

@@ -55,6 +55,8 @@ LccArgs lcc_args(pm_ctx* c, int row) {
   a.base = c->cid_off[c->rank];
   a.par = c->step_parity;
   a.fwx = c->fwx;
+  a.rowc = c->rowc;
+  a.col_shift = c->col_shift;
   return a;
 }
 
@@ -117,6 +119,7 @@ void state_free(pm_ctx* c, bool keep_scratch = false) {
   c->h_step = nullptr;
   c->dcap = c->tcap = 0;
   dev_free(c->S); dev_free(c->adeg); dev_free(c->cls);
+  if (!keep) { dev_free(c->colw); c->colw_cap = 0; }
   dev_free(c->rowc); dev_free(c->vid); dev_free(c->clsc); dev_free(c->fw); dev_free(c->tb); dev_free(c->fwx);
   for (int b = 0; b < 2; ++b) for (int k = 0; k < 2; ++k) dev_free(c->fr[b][k]);
   dev_free(c->cnt); dev_free(c->ok); dev_free(c->src_list);
@@ -229,6 +232,8 @@ void pm_destroy(pm_ctx* c) {
   dev_free(c->rowstat);
   if (c->h_cnt) cudaFreeHost(c->h_cnt);
   if (c->h_rowstat) cudaFreeHost(c->h_rowstat);
+  if (c->h_misc) cudaFreeHost(c->h_misc);
+  if (c->scan_tmp) cudaFree(c->scan_tmp);
   dev_cache().flush(c->device);
   if (comm) ncclCommDestroy(comm);
   if (c->d_scratch) cudaFree(c->d_scratch);
@@ -345,9 +350,12 @@ int pm_graph_get_csr(const pm_ctx* cc, uint64_t* rowptr_out, uint32_t* col_out) 
   PM_CUDA(c, cudaMemcpy(blk.data(), c->rowblk, (own + 1) * 4, cudaMemcpyDeviceToHost));
   PM_CUDA(c, cudaMemcpy(col.data(), c->col0, c->Epad * 4, cudaMemcpyDeviceToHost));
   uint64_t o = 0;
+  const uint32_t idmask = col_idmask(c);
   for (uint64_t v = 0; v < own; ++v) {
     rowptr_out[v] = o;
     std::memcpy(col_out + o, col.data() + (uint64_t)blk[v] * 8, (size_t)deg[v] * 4);
+    if (idmask != 0xFFFFFFFFu)
+      for (uint32_t j = 0; j < deg[v]; ++j) col_out[o + j] &= idmask;  // packed labels ride in the high bits
     if (c->n_ranks > 1) {  // slots -> vertex ids, ascending
       for (uint32_t j = 0; j < deg[v]; ++j) col_out[o + j] = (uint32_t)vertex_of(c, col_out[o + j]);
       std::sort(col_out + o, col_out + o + deg[v]);
@@ -369,7 +377,12 @@ int pm_labels_degree_log2(pm_ctx* c) {
   c->has_labels = true;
   c->state_ready = false;
   c->labels_version = 0;  // a function of the graph alone
-  return labels_derive(c, true);  // bit lengths of 32-bit degrees are <= 32
+  // bit lengths of 32-bit degrees are <= 32; the largest label of ANY rank sizes the packed label field
+  uint64_t maxd = c->max_deg;
+  { int rc = comm_allreduce_max_u64(c, &maxd); if (rc) return rc; }
+  uint64_t max_label = 0;
+  while (maxd >> max_label) ++max_label;
+  return labels_derive(c, true, max_label);
 }
 
 int pm_labels_set(pm_ctx* c, const uint64_t* labels) {
@@ -390,8 +403,12 @@ int pm_labels_set(pm_ctx* c, const uint64_t* labels) {
   c->state_ready = false;
   c->labels_version = ++c->labels_counter;
   bool small = true;
-  for (uint64_t v = 0; v < c->V && small; ++v) small = labels[v] < 64;
-  return labels_derive(c, small);
+  uint64_t max_label = 0;
+  for (uint64_t v = 0; v < c->V && small; ++v) {
+    small = labels[v] < 64;
+    max_label = std::max<uint64_t>(max_label, labels[v]);
+  }
+  return labels_derive(c, small, max_label);
 }
 
 int pm_labels_get(const pm_ctx* cc, uint64_t* out) {
@@ -472,7 +489,11 @@ int pm_pattern_info(const pm_ctx* c, pm_pattern_info_t* o) {
 }
 
 // ------------------------------------------------------------------- state
-int pm_state_reset(pm_ctx* c) {
+}  // extern "C"
+
+namespace {
+// need_colw: the caller walks the working adjacency (the run_fuzzy path does not)
+int state_reset(pm_ctx* c, bool need_colw) {
   if (!c || !c->has_graph || !c->has_labels || !c->has_pattern)
     return fail(c, PM_ERR_ARG, "pm_state_reset needs a graph, labels and a pattern");
   PM_CUDA(c, cudaSetDevice(c->device));
@@ -483,8 +504,8 @@ int pm_state_reset(pm_ctx* c) {
   int rc;
   if (!c->S) {
     if ((rc = dev_alloc(c, &c->S, Vs))) return rc;
-    if ((rc = dev_alloc(c, &c->adeg, NL))) return rc;
-    if ((rc = dev_alloc(c, &c->rowc, NL))) return rc;
+    if ((rc = dev_alloc(c, &c->adeg, NL + 1))) return rc;
+    if ((rc = dev_alloc(c, &c->rowc, NL + 1))) return rc;
     if ((rc = dev_alloc(c, &c->vid, Vs))) return rc;
     if ((rc = dev_alloc(c, &c->clsc, Vs))) return rc;
     if ((rc = dev_alloc(c, &c->fw, Vs / 16 + 2))) return rc;
@@ -500,7 +521,8 @@ int pm_state_reset(pm_ctx* c) {
     }
     if ((rc = dev_alloc(c, &c->cnt, 1))) return rc;
     if (!c->h_cnt) PM_CUDA(c, cudaMallocHost((void**)&c->h_cnt, sizeof(DevCounters)));
-    PM_CUDA(c, cudaMemsetAsync(c->adeg, 0, NL * sizeof(uint32_t), c->stream));
+    PM_CUDA(c, cudaMemsetAsync(c->adeg, 0, (NL + 1) * sizeof(uint32_t), c->stream));
+    if (!c->h_misc) PM_CUDA(c, cudaMallocHost((void**)&c->h_misc, 16 * sizeof(uint32_t)));
     if (multi) {
       c->dcap = c->nlmax;  // a rank publishes at most one change per owned vertex and step
       if ((rc = dev_alloc(c, &c->din[0], c->dcap * c->n_ranks))) return rc;
@@ -592,18 +614,53 @@ int pm_state_reset(pm_ctx* c) {
     // pass 3: per-cid state of every survivor (all ranks), row starts and frontier entries of the local ones
     if (small)
       k_init_assign<true><<<grid, kBlock, 0, c->stream>>>(c->lab8, nullptr, c->deg, c->rowblk, c->fw, c->tb, multi ? Vs : NL,
-                                                          (uint32_t)base, (uint32_t)(base + NL), c->S, c->clsc, c->vid, c->rowc, c->fwx,
+                                                          (uint32_t)base, (uint32_t)(base + NL), c->S, c->clsc, c->vid, c->adeg, c->rowc, c->fwx,
                                                           use_sig ? c->sig : nullptr, c->fr[0][0], c->fr[0][1], c->cnt, 0);
     else
       k_init_assign<false><<<grid, kBlock, 0, c->stream>>>(nullptr, c->cls, c->deg, c->rowblk, c->fw, c->tb, multi ? Vs : NL,
-                                                           (uint32_t)base, (uint32_t)(base + NL), c->S, c->clsc, c->vid, c->rowc, c->fwx,
+                                                           (uint32_t)base, (uint32_t)(base + NL), c->S, c->clsc, c->vid, c->adeg, c->rowc, c->fwx,
                                                            nullptr, c->fr[0][0], c->fr[0][1], c->cnt, 0);
     PM_LAUNCH_CHECK(c);
+    // the DENSE working adjacency: the row of local compact id i starts at the exclusive prefix of the survivors'
+    // degrees (in 32-byte sectors, so rows stay sector aligned) — a few hundred million slots instead of the
+    // graph's billions, and contiguous for every scan after the first
+    const uint64_t n_c_local = c->cid_off[c->rank + 1] - c->cid_off[c->rank];
+    PM_CUDA(c, cudaMemsetAsync(c->rowc + n_c_local, 0, sizeof(uint32_t), c->stream));
+    {
+      const uint32_t* in = c->rowc;  // k_init_assign left every survivor's row length in sectors here: scanned in place
+      size_t tb = 0;
+      PM_CUDA(c, cub::DeviceScan::ExclusiveSum(nullptr, tb, in, c->rowc, (int64_t)(n_c_local + 1), c->stream));
+      if (tb > c->scan_tmp_bytes) {
+        if (c->scan_tmp) cudaFree(c->scan_tmp);
+        c->scan_tmp = nullptr;
+        c->scan_tmp_bytes = std::max<size_t>(tb * 2, 1 << 16);
+        PM_CUDA(c, cudaMalloc(&c->scan_tmp, c->scan_tmp_bytes));
+      }
+      tb = c->scan_tmp_bytes;
+      PM_CUDA(c, cub::DeviceScan::ExclusiveSum(c->scan_tmp, tb, in, c->rowc, (int64_t)(n_c_local + 1), c->stream));
+      c->launches += 2;
+      PM_CUDA(c, cudaMemcpyAsync(c->h_misc, c->rowc + n_c_local, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    }
   }
   PM_CUDA(c, cudaEventRecord(c->kev[3][1], c->stream));
   {
     int rc2 = sync_counters(c);
     if (rc2) return rc2;
+    if (need_colw) {
+      uint64_t want = (uint64_t)c->h_misc[0] * 8 + 64;  // + slack: the scan kernels read whole uint4 windows
+      if (multi) {  // peers map the working adjacency (remote edge flags): it grows on every rank together
+        if ((rc2 = comm_allreduce_max_u64(c, &want))) return rc2;
+      }
+      if (want > c->colw_cap) {
+        if (multi) comm_close_all(c);
+        dev_free(c->colw);
+        c->colw_cap = 0;
+        const uint64_t cap = want + want / 8;
+        if ((rc2 = dev_alloc(c, &c->colw, cap))) return rc2;
+        c->colw_cap = cap;
+        if (multi && (rc2 = comm_publish(c))) return rc2;
+      }
+    }
     for (int b = 0; b < 2; ++b) c->bin_live[b] = c->h_cnt->fr_n[0][b] != 0;
     c->init_ms = 0;
     c->init_candidates = c->h_cnt->filtered_init;
@@ -621,6 +678,11 @@ int pm_state_reset(pm_ctx* c) {
   c->state_ready = true;
   return 0;
 }
+}  // namespace
+
+extern "C" {
+
+int pm_state_reset(pm_ctx* c) { return state_reset(c, true); }
 
 // --------------------------------------------------------------------- LCC
 int pm_lcc(pm_ctx* c, int init_step, int* not_finished, pm_counts_t* counts_out) {
@@ -632,6 +694,7 @@ int pm_lcc(pm_ctx* c, int init_step, int* not_finished, pm_counts_t* counts_out)
   const int grid = grid_for();
   const bool sm0 = c->labels_small;      // first scan: neighbour labels are streamed next to the ids (lab0)
   const bool ts_known = c->filter_done;  // ... and the signature filter already settled every entry's T_state
+  const bool packed = c->col_shift != 0; // ... inside the col0 slots themselves (else in the parallel byte array lab0)
   const double t0 = wall_s();
   PM_CUDA(c, cudaMemsetAsync(c->rowstat, 0, D * sizeof(RowStat), st));
   PM_CUDA(c, cudaMemsetAsync(&c->cnt->nf, 0, sizeof(uint32_t), st));
@@ -650,22 +713,26 @@ int pm_lcc(pm_ctx* c, int init_step, int* not_finished, pm_counts_t* counts_out)
     if (c->bin_live[0]) {
       uint4* l = c->fr[cur][0];
       const uint32_t* np = &c->cnt->fr_n[cur][0];
-      if (first && ts_known) k_lcc_scan<true, true, false, false><<<grid, kBlock, 0, st>>>(a, l, np, 0);
-      else if (first && sm0) k_lcc_scan<true, true, false, true><<<grid, kBlock, 0, st>>>(a, l, np, 0);
-      else if (first) k_lcc_scan<true, false, false, true><<<grid, kBlock, 0, st>>>(a, l, np, 0);
-      else if (xlate) k_lcc_scan<false, false, true, true><<<grid, kBlock, 0, st>>>(a, l, np, 0);
-      else k_lcc_scan<false, false, false, true><<<grid, kBlock, 0, st>>>(a, l, np, 0);
+      if (first && ts_known && packed) k_lcc_scan<true, 2, false, false><<<grid, kBlock, 0, st>>>(a, l, np, 0);
+      else if (first && ts_known) k_lcc_scan<true, 1, false, false><<<grid, kBlock, 0, st>>>(a, l, np, 0);
+      else if (first && sm0 && packed) k_lcc_scan<true, 2, false, true><<<grid, kBlock, 0, st>>>(a, l, np, 0);
+      else if (first && sm0) k_lcc_scan<true, 1, false, true><<<grid, kBlock, 0, st>>>(a, l, np, 0);
+      else if (first) k_lcc_scan<true, 0, false, true><<<grid, kBlock, 0, st>>>(a, l, np, 0);
+      else if (xlate) k_lcc_scan<false, 0, true, true><<<grid, kBlock, 0, st>>>(a, l, np, 0);
+      else k_lcc_scan<false, 0, false, true><<<grid, kBlock, 0, st>>>(a, l, np, 0);
       PM_LAUNCH_CHECK(c);
     }
     PM_CUDA(c, cudaEventRecord(ev[1], st));
     if (c->bin_live[1]) {
       uint4* l = c->fr[cur][1];
       const uint32_t* np = &c->cnt->fr_n[cur][1];
-      if (first && ts_known) k_lcc_scan_big<true, true, false, false><<<148, 1024, 0, st>>>(a, l, np, 0);
-      else if (first && sm0) k_lcc_scan_big<true, true, false, true><<<148, 1024, 0, st>>>(a, l, np, 0);
-      else if (first) k_lcc_scan_big<true, false, false, true><<<148, 1024, 0, st>>>(a, l, np, 0);
-      else if (xlate) k_lcc_scan_big<false, false, true, true><<<148, 1024, 0, st>>>(a, l, np, 0);
-      else k_lcc_scan_big<false, false, false, true><<<148, 1024, 0, st>>>(a, l, np, 0);
+      if (first && ts_known && packed) k_lcc_scan_big<true, 2, false, false><<<148, 1024, 0, st>>>(a, l, np, 0);
+      else if (first && ts_known) k_lcc_scan_big<true, 1, false, false><<<148, 1024, 0, st>>>(a, l, np, 0);
+      else if (first && sm0 && packed) k_lcc_scan_big<true, 2, false, true><<<148, 1024, 0, st>>>(a, l, np, 0);
+      else if (first && sm0) k_lcc_scan_big<true, 1, false, true><<<148, 1024, 0, st>>>(a, l, np, 0);
+      else if (first) k_lcc_scan_big<true, 0, false, true><<<148, 1024, 0, st>>>(a, l, np, 0);
+      else if (xlate) k_lcc_scan_big<false, 0, true, true><<<148, 1024, 0, st>>>(a, l, np, 0);
+      else k_lcc_scan_big<false, 0, false, true><<<148, 1024, 0, st>>>(a, l, np, 0);
       PM_LAUNCH_CHECK(c);
     }
     PM_CUDA(c, cudaEventRecord(ev[2], st));
@@ -687,9 +754,9 @@ int pm_lcc(pm_ctx* c, int init_step, int* not_finished, pm_counts_t* counts_out)
     // no second scan in this call: rename the rows of the vertices still in the map to compact ids now
     LccArgs a = lcc_args(c, 0);
     const int cur = c->cur;
-    k_lcc_scan<false, false, true, true><<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], &c->cnt->fr_n[cur][0], 1);
+    k_lcc_scan<false, 0, true, true><<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], &c->cnt->fr_n[cur][0], 1);
     PM_LAUNCH_CHECK(c);
-    k_lcc_scan_big<false, false, true, true><<<148, 1024, 0, st>>>(a, c->fr[cur][1], &c->cnt->fr_n[cur][1], 1);
+    k_lcc_scan_big<false, 0, true, true><<<148, 1024, 0, st>>>(a, c->fr[cur][1], &c->cnt->fr_n[cur][1], 1);
     PM_LAUNCH_CHECK(c);
   }
   PM_CUDA(c, cudaEventRecord(c->events[D], st));
@@ -815,6 +882,11 @@ int pm_nlcc(pm_ctx* c, int pl, int mode, int* pattern_found, int* token_source_d
   // cycle constraints close their last two hops by intersecting E_v with E_s (k_nem1_close_cycle);
   // that needs symmetric edge maps, which flags set outside LCC can break only while diameter < 2
   const bool close2 = !tds && k.valid_cycle && (int)k.C >= 2 && c->pat.diameter >= 2;
+  // one rank: the (vertex, source) aggregation is skipped where it cannot change anything — hop 1 (the neighbours
+  // of a source are distinct) and, up to hop 2, the level that feeds the closing kernel (idempotent effects)
+  auto nem1_dedupe = [&](int hn) { return hn >= 2 && !(close2 && hn == (int)k.C - 1 && hn <= 2); };
+  bool any_dedupe = multi;
+  for (int hn = 1; !tds && hn <= (int)k.C; ++hn) any_dedupe = any_dedupe || (nem1_dedupe(hn) && !(close2 && hn == (int)k.C));
   for (int attempt = 0;; ++attempt) {
     if (tds && c->keep_subgraphs && !multi) {
       match_cap = c->pool_cap;
@@ -823,7 +895,7 @@ int pm_nlcc(pm_ctx* c, int pl, int mode, int* pattern_found, int* token_source_d
     }
     // zero found .. the end, keep the frontier counters and nf
     PM_CUDA(c, cudaMemsetAsync(&c->cnt->found, 0, sizeof(DevCounters) - offsetof(DevCounters, found), st));
-    if (!tds) PM_CUDA(c, cudaMemsetAsync(c->hset, 0xFF, c->hset_use * sizeof(unsigned long long), st));
+    if (!tds && any_dedupe) PM_CUDA(c, cudaMemsetAsync(c->hset, 0xFF, c->hset_use * sizeof(unsigned long long), st));
     // several ranks: `ok` doubles as this GPU's "already acknowledged" cache for foreign sources
     if (multi) PM_CUDA(c, cudaMemsetAsync(c->ok, 0, std::max<uint64_t>(1, c->cid_off[c->n_ranks]), st));
     const bool dbg = getenv("PM_DEBUG_HOPS") != nullptr;
@@ -863,9 +935,9 @@ int pm_nlcc(pm_ctx* c, int pl, int mode, int* pattern_found, int* token_source_d
           else k_tds_expand<false><<<grid, kBlock, 0, st>>>(a, lvl, hn);
         } else if (fin) {
           if (k.valid_cycle) k_nem1_final_cycle<<<grid, kBlock, 0, st>>>(a, lvl, hn);
-          else k_nem1_expand<true><<<grid, kBlock, 0, st>>>(a, lvl, hn);
+          else k_nem1_expand<true><<<grid, kBlock, 0, st>>>(a, lvl, hn, 0);
         } else {
-          k_nem1_expand<false><<<grid, kBlock, 0, st>>>(a, lvl, hn);
+          k_nem1_expand<false><<<grid, kBlock, 0, st>>>(a, lvl, hn, nem1_dedupe(hn) ? 1 : 0);
         }
         PM_LAUNCH_CHECK(c);
         if (!fin) {
@@ -873,6 +945,16 @@ int pm_nlcc(pm_ctx* c, int pl, int mode, int* pattern_found, int* token_source_d
           PM_LAUNCH_CHECK(c);
         }
       }
+      // post-processing of token_source_map (beta.cpp:956-1062) and the TP row (beta.cpp:1094-1120) follow
+      // without a host round trip: k_nlcc_apply does nothing if the walk ran out of room (the host then
+      // retries the constraint with larger buffers from unchanged state)
+      k_nlcc_apply<<<grid, kBlock, 0, st>>>(c->S, c->ok, c->src_list, c->cnt, c->step_parity, c->pool_cap, match_cap);
+      PM_LAUNCH_CHECK(c);
+      PM_CUDA(c, cudaMemsetAsync(c->rowstat + D, 0, sizeof(RowStat), st));
+      k_count_alive<<<grid, kBlock, 0, st>>>(lcc_args(c, D), c->fr[cur][0], c->fr[cur][1], cur);
+      PM_LAUNCH_CHECK(c);
+      PM_CUDA(c, cudaEventRecord(c->events[1], st));
+      PM_CUDA(c, cudaMemcpyAsync(c->h_rowstat + D, c->rowstat + D, sizeof(RowStat), cudaMemcpyDeviceToHost, st));
       if ((rc = sync_counters(c))) { dev_free(d_matches); return rc; }
     } else {
       // one kernel + one StepMsg all-gather per hop: tokens are stored into the owners' inboxes
@@ -978,22 +1060,23 @@ int pm_nlcc(pm_ctx* c, int pl, int mode, int* pattern_found, int* token_source_d
     }
   }
   dev_free(d_matches);
-  // post-processing of token_source_map (beta.cpp:956-1062) and the TP row (beta.cpp:1094-1120)
-  k_nlcc_apply<<<grid, kBlock, 0, st>>>(c->S, c->ok, c->src_list, c->cnt, c->step_parity);
-  PM_LAUNCH_CHECK(c);
-  if (multi) {  // the deactivations reach the peers' replicas (vertex_data all_min/max_reduce, beta.cpp:1020-1039)
+  if (multi) {
+    // post-processing of token_source_map (beta.cpp:956-1062) and the TP row (beta.cpp:1094-1120)
+    k_nlcc_apply<<<grid, kBlock, 0, st>>>(c->S, c->ok, c->src_list, c->cnt, c->step_parity, ~0ull, 0ull);
+    PM_LAUNCH_CHECK(c);
+    // the deactivations reach the peers' replicas (vertex_data all_min/max_reduce, beta.cpp:1020-1039)
     if ((rc = comm_step(c))) return rc;
     k_apply_deltas<<<grid, kBlock, 0, st>>>(c->S, c->step_msg + 1, c->step_parity);
     PM_LAUNCH_CHECK(c);
     c->step_parity ^= 1;
+    PM_CUDA(c, cudaMemsetAsync(c->rowstat + D, 0, sizeof(RowStat), st));
+    LccArgs la = lcc_args(c, D);
+    k_count_alive<<<grid, kBlock, 0, st>>>(la, c->fr[cur][0], c->fr[cur][1], cur);
+    PM_LAUNCH_CHECK(c);
+    PM_CUDA(c, cudaEventRecord(c->events[1], st));
+    PM_CUDA(c, cudaMemcpyAsync(c->h_rowstat + D, c->rowstat + D, sizeof(RowStat), cudaMemcpyDeviceToHost, st));
+    if ((rc = sync_counters(c))) return rc;
   }
-  PM_CUDA(c, cudaMemsetAsync(c->rowstat + D, 0, sizeof(RowStat), st));
-  LccArgs la = lcc_args(c, D);
-  k_count_alive<<<grid, kBlock, 0, st>>>(la, c->fr[cur][0], c->fr[cur][1], cur);
-  PM_LAUNCH_CHECK(c);
-  PM_CUDA(c, cudaEventRecord(c->events[1], st));
-  PM_CUDA(c, cudaMemcpyAsync(c->h_rowstat + D, c->rowstat + D, sizeof(RowStat), cudaMemcpyDeviceToHost, st));
-  if ((rc = sync_counters(c))) return rc;
   int deleted = c->h_cnt->deleted ? 1 : 0;
   if (multi) {  // token_source_deleted is reduced over the ranks (beta.cpp:1149)
     if ((rc = comm_step_fetch(c))) return rc;
@@ -1174,7 +1257,7 @@ int pm_run_fuzzy(pm_ctx* c, const pm_run_options_t* opt_in, pm_run_summary_t* ou
         if (k.I[x] == k.I[y]) return fail(c, PM_ERR_UNSUPPORTED, "token walk repeats a template vertex at interior hops (order dependent)");
   pm_run_options_t opt{-1, 0, 0, 0};
   if (opt_in) opt = *opt_in;
-  int rc = pm_state_reset(c);  // allocations, pattern constants, bookkeeping (beta.cpp:484-492 analogue)
+  int rc = state_reset(c, false);  // allocations, pattern constants, bookkeeping (beta.cpp:484-492 analogue)
   if (rc) return rc;
   c->fuzzy_ids = true;         // this path names vertices directly (no compact ids)
   load_nlcc_sizes(c, "fuzzy");
@@ -1182,7 +1265,9 @@ int pm_run_fuzzy(pm_ctx* c, const pm_run_options_t* opt_in, pm_run_summary_t* ou
   const int D = c->pat.diameter, grid = grid_for();
   const int max_it = opt.max_iterations > 0 ? opt.max_iterations : 1000;
   FzArgs a;
+  if ((rc = ensure_lab0(c))) return rc;  // packed labels: the byte label stream of this path is built on demand
   a.rowblk = c->rowblk; a.deg = c->deg; a.col0 = c->col0; a.lab0 = c->lab0; a.lab8 = c->lab8; a.S = c->S; a.cnt = c->cnt;
+  a.idmask = col_idmask(c);
   a.row = c->rowstat;
   PM_CUDA(c, cudaMemsetAsync(c->cnt, 0, sizeof(DevCounters), st));
   c->cur = 0;

@@ -245,10 +245,10 @@ __global__ void __launch_bounds__(256) k_build_sig(const uint32_t* __restrict__ 
         if (lab0)  // the label stream of the row (padding slots carry label 0); rows start sector aligned
           *reinterpret_cast<uint32_t*>(lab0 + row + j0) = l0 | (l1 << 8) | (l2 << 16) | (l3 << 24);
         if (shift != 0u || idmask != 0xFFFFFFFFu) {  // (re)pack or strip the labels carried by the slots themselves
-          q.x = i0 | (l0 << shift);
-          if (j0 + 1 < d) q.y = i1 | (l1 << shift);
-          if (j0 + 2 < d) q.z = i2 | (l2 << shift);
-          if (j0 + 3 < d) q.w = i3 | (l3 << shift);
+          q.x = shift ? i0 | (l0 << shift) : i0;
+          if (j0 + 1 < d) q.y = shift ? i1 | (l1 << shift) : i1;
+          if (j0 + 2 < d) q.z = shift ? i2 | (l2 << shift) : i2;
+          if (j0 + 3 < d) q.w = shift ? i3 | (l3 << shift) : i3;
           *reinterpret_cast<uint4*>(col0 + row + j0) = q;
         }
       } else if (lab0 && j0 < ((d + 7u) & ~7u)) {
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(1024) k_build_sig_big(const uint32_t* __restri
       const uint8_t l = j < d ? lab8[id] : (uint8_t)0;
       if (j < d) {
         m |= 1ull << l;
-        if (shift != 0u || idmask != 0xFFFFFFFFu) col0[row + j] = id | ((uint32_t)l << shift);
+        if (shift != 0u || idmask != 0xFFFFFFFFu) col0[row + j] = shift ? id | ((uint32_t)l << shift) : id;
       }
       if (lab0) lab0[row + j] = l;
     }
@@ -345,10 +345,13 @@ inline int labels_derive(pm_ctx* c, bool small, uint64_t max_label) {
   }
   // packed labels: the label of every neighbour rides in the unused high bits of its slot when
   // id bits + label bits <= 32 (R-MAT scale 26 on one GPU with degree labels: 26 + 6)
-  uint32_t idbits = 1, labbits = 1;
+  // The label field is at most 6 bits wide (labels index 64-bit sets) and its all-ones value is left to the padding
+  // slots (PM_SENTINEL), which therefore never test valid.
+  uint32_t idbits = 1;
   while (idbits < 32 && ((c->nlmax * c->n_ranks - 1) >> idbits)) ++idbits;
-  while (labbits < 7 && (max_label >> labbits)) ++labbits;
-  const uint32_t new_shift = (idbits + labbits <= 32 && !getenv("PM_NO_PACK")) ? idbits : 0u;
+  const uint32_t cand_shift = std::max<uint32_t>(idbits, 26u);
+  const bool fits = cand_shift < 32 && max_label < (1ull << (32 - cand_shift)) - 1;
+  const uint32_t new_shift = (fits && !getenv("PM_NO_PACK")) ? cand_shift : 0u;
   int rc;
   uint32_t *big_list = nullptr, *big_n = nullptr;
   const uint64_t Vs = c->nlmax * c->n_ranks, base = c->nlmax * c->rank;

@@ -661,6 +661,137 @@ __global__ void __launch_bounds__(kBlock, 4) k_lcc_scan(LccArgs a, uint4* __rest
   }
 }
 
+// ---------------------------------------------------------------------------
+// The first-superstep scan of the hot configuration: packed labels (col_shift != 0) behind the signature filter
+// (every entry already carries the T_state the superstep ends with, k_init_assign).  Same packing of rows into
+// lanes as k_lcc_scan, but a lane takes a whole 32-byte SECTOR (8 slots) per pass — rows of the graph store are
+// sector aligned and padded with PM_SENTINEL, whose label field is all ones and never valid, so there is no
+// per-slot bounds test — and the per-pass bookkeeping is spread over 256 slots instead of 128: the generic kernel
+// is instruction-issue bound at 1.4 warp instructions per slot, this one needs about half.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void warp_prefix8(uint32_t n, uint32_t lt, uint32_t& below, uint32_t& total) {
+  const uint32_t b0 = __ballot_sync(0xffffffffu, n & 1u), b1 = __ballot_sync(0xffffffffu, n & 2u),
+                 b2 = __ballot_sync(0xffffffffu, n & 4u), b3 = __ballot_sync(0xffffffffu, n & 8u);
+  below = __popc(b0 & lt) + 2u * __popc(b1 & lt) + 4u * __popc(b2 & lt) + 8u * __popc(b3 & lt);
+  total = __popc(b0) + 2u * __popc(b1) + 4u * __popc(b2) + 8u * __popc(b3);
+}
+
+__global__ void __launch_bounds__(kBlock, 3) k_lcc_first_packed(LccArgs a, uint4* __restrict__ list,
+                                                                const uint32_t* __restrict__ n_ptr) {
+  // per warp, the 32 rows of the batch in flight: {source row (sectors), sectors, first sector of the batch, dense row}
+  __shared__ uint4 s_rowp[kBlock / 32][32];
+  __shared__ unsigned long long s_vl[kBlock / 32][32];
+  __shared__ uint32_t s_rout[kBlock / 32][32];
+  __shared__ uint8_t s_nz[kBlock / 32][32];
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint32_t lt = lanemask_lt();
+  const uint32_t le = lt | (1u << lane);
+  const uint32_t n = *n_ptr;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t shift = a.col_shift, idmask = (1u << shift) - 1u;
+  const unsigned long long not_sentinel = ~(1ull << (0xFFFFFFFFu >> shift));
+  unsigned long long scanned = 0, verts = 0;
+  for (uint32_t base = warp * 32; base < n; base += nwarps * 32) {
+    const uint32_t idx = base + lane;
+    const bool has = idx < n;
+    uint4 e = make_uint4(0, 0, 0, 0);
+    uint32_t Tv = 0;
+    bool live = false;
+    if (has) {
+      e = list[idx];
+      live = e.y != PM_TOMB;
+      if (live) Tv = a.S[e.x];
+    }
+    const uint32_t d = Tv ? e.z : 0u;
+    uint32_t drow = e.y, out = 0;
+    if (has && live) drow = a.rowc[e.x - a.base];
+    const unsigned long long VL = valid_labels(nb_of(Tv)) & not_sentinel;
+    const uint32_t nch = (d + 7u) >> 3;
+    uint32_t cum = nch;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, cum, o);
+      if (lane >= (uint32_t)o) cum += t;
+    }
+    const uint32_t C = __shfl_sync(0xffffffffu, cum, 31);  // sectors of this batch
+    if (C) {
+      const uint32_t first = cum - nch;
+      const uint32_t longrows = __ballot_sync(0xffffffffu, nch != 0u);
+      __syncwarp();
+      s_rowp[wid][lane] = make_uint4(e.y, nch, first, drow);
+      s_vl[wid][lane] = VL;
+      s_rout[wid][lane] = 0u;
+      if (nch) s_nz[wid][__popc(longrows & lt)] = (uint8_t)lane;
+      __syncwarp();
+      // one pass ahead: the row a lane's sector belongs to and the sector itself
+      uint32_t rN = 0, hN = 0;
+      uint4 qa = make_uint4(PM_SENTINEL, PM_SENTINEL, PM_SENTINEL, PM_SENTINEL), qb = qa;
+      auto fetch = [&](uint32_t g0) {
+        const uint32_t hb = (nch && first >= g0 && first < g0 + 32u) ? 1u << (first - g0) : 0u;
+        hN = __reduce_or_sync(0xffffffffu, hb);
+        const uint32_t before = __popc(__ballot_sync(0xffffffffu, nch && first < g0));
+        rN = s_nz[wid][before + __popc(hN & le) - 1u];
+        const uint4 rp = s_rowp[wid][rN];
+        const uint32_t g = g0 + lane;
+        qa = make_uint4(PM_SENTINEL, PM_SENTINEL, PM_SENTINEL, PM_SENTINEL);
+        qb = qa;
+        if (g < C) {
+          const uint4* __restrict__ p = reinterpret_cast<const uint4*>(a.col0 + ((uint64_t)rp.x + (g - rp.z)) * 8);
+          qa = p[0];
+          qb = p[1];
+        }
+      };
+      fetch(0u);
+      for (uint32_t g0 = 0; g0 < C; g0 += 32u) {
+        const uint32_t r = rN, H = hN;
+        const uint4 q0 = qa, q1 = qb;
+        if (g0 + 32u < C) fetch(g0 + 32u);  // the next pass is on its way while this one is worked on
+        const unsigned long long rVL = s_vl[wid][r];
+        const uint32_t u[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+        uint32_t keep[8], nk = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          keep[k] = (uint32_t)(rVL >> (u[k] >> shift)) & 1u;  // a sentinel's label field is never valid
+          nk += keep[k];
+        }
+        uint32_t below, total;
+        warp_prefix8(nk, lt, below, total);
+        const uint32_t hl = 31u - __clz((H | 1u) & le);  // first lane of my row's segment in this pass
+        const uint32_t off = below - __shfl_sync(0xffffffffu, below, hl);
+        const uint32_t rout = s_rout[wid][r];
+        uint32_t* __restrict__ p = a.colw + (uint64_t)s_rowp[wid][r].w * 8 + rout + off;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (keep[k]) *p++ = u[k] & idmask;
+        const bool in_batch = g0 + lane < C;
+        const bool last = in_batch && (lane == 31u || ((H >> (lane + 1u)) & 1u) || g0 + lane + 1u == C);
+        __syncwarp();  // every lane has read its row's running count
+        if (last) s_rout[wid][r] = rout + off + nk;
+        __syncwarp();
+      }
+      if (nch) out = s_rout[wid][lane];
+    }
+    if (has && live) {
+      scanned += d;
+      verts += Tv != 0u;
+      e.y = drow;
+      e.z = out;
+      e.w = Tv ? e.w : 0u;  // decided by the signature filter (k_init_assign): never empty
+      list[idx] = e;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    scanned += __shfl_xor_sync(0xffffffffu, scanned, o);
+    verts += __shfl_xor_sync(0xffffffffu, verts, o);
+  }
+  if (lane == 0 && verts) {
+    atomicAdd(&a.row->scanned[0], scanned);
+    atomicAdd(&a.row->verts[0], verts);
+  }
+}
+
 // one CTA per high-degree vertex ("delegates across warps and CTAs")
 template <bool FIRST, int STREAM, bool XLATE, bool HEARD>
 __global__ void __launch_bounds__(1024) k_lcc_scan_big(LccArgs a, uint4* __restrict__ list,

@@ -713,7 +713,8 @@ int pm_lcc(pm_ctx* c, int init_step, int* not_finished, pm_counts_t* counts_out)
     if (c->bin_live[0]) {
       uint4* l = c->fr[cur][0];
       const uint32_t* np = &c->cnt->fr_n[cur][0];
-      if (first && ts_known && packed) k_lcc_scan<true, 2, false, false><<<grid, kBlock, 0, st>>>(a, l, np, 0);
+      if (first && ts_known && packed && !getenv("PM_GENERIC_FIRST")) k_lcc_first_packed<<<148 * 6, kBlock, 0, st>>>(a, l, np);
+      else if (first && ts_known && packed) k_lcc_scan<true, 2, false, false><<<grid, kBlock, 0, st>>>(a, l, np, 0);
       else if (first && ts_known) k_lcc_scan<true, 1, false, false><<<grid, kBlock, 0, st>>>(a, l, np, 0);
       else if (first && sm0 && packed) k_lcc_scan<true, 2, false, true><<<grid, kBlock, 0, st>>>(a, l, np, 0);
       else if (first && sm0) k_lcc_scan<true, 1, false, true><<<grid, kBlock, 0, st>>>(a, l, np, 0);

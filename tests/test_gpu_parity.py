@@ -200,6 +200,43 @@ def test_bench_templates_on_rmat_scale20(oracle, eng):
         assert len(want["rows"]) >= 8, nm
 
 
+def test_label_stream_path_without_packed_labels(oracle, eng):
+    """Neighbour labels normally ride in the high bits of the adjacency slots (id bits + label bits <= 32); larger
+    graphs fall back to a parallel byte stream.  PM_NO_PACK forces that path here; switching back re-packs."""
+    import os
+    from fuzzypatternmatching_b200 import patterns as PT
+    g = oracle.Graph.rmat(17, 4)
+    labels = g.labels_degree_log2()
+    eng.graph_rmat(17, 4)
+    for mode in ("1", None, "1"):
+        if mode:
+            os.environ["PM_NO_PACK"] = mode
+        else:
+            os.environ.pop("PM_NO_PACK", None)
+        try:
+            eng.labels_degree_log2()
+        finally:
+            os.environ.pop("PM_NO_PACK", None)
+        rowptr, col = eng.graph_csr()
+        assert np.array_equal(col, g.col)
+        for spec, tds in ((PT.RMAT_LOG2_TREE, 4), (PT.cycle4(5, 6, 7, 8), 1)):
+            d = cases.pattern_dir(spec)
+            pat = oracle.Pattern(d)
+            ref = oracle.Run(g, labels, pat, tds_from_pl=tds)
+            eng.pattern_load_dir(d)
+            eng.run(tds_from_pl=tds)
+            got, want = cases.engine_summary(eng, pat.n_constraints), cases.run_summary(ref)
+            for k in ("rows", "iterations", "vertices", "edges", "subgraphs"):
+                assert got[k] == want[k], (mode, k)
+    # the run_fuzzy path builds its byte label stream on demand from the packed slots
+    eng.labels_degree_log2()
+    d = cases.pattern_dir(PT.cycle4(5, 6, 7, 8))
+    ref = oracle.Run(g, labels, oracle.Pattern(d), fuzzy=True)
+    eng.pattern_load_dir(d)
+    eng.run_fuzzy()
+    assert eng.rows() == ref.rows
+
+
 def test_golden_fixtures_on_gpu(oracle, eng):
     import json
     import os

@@ -86,6 +86,12 @@ SYMBOLS = {
     "pm_get_subgraph_count": (_i, [_vp, _i, C.POINTER(_u64), C.POINTER(_i)]),
     "pm_get_subgraphs": (_i, [_vp, _i, _vp]),
     "pm_write_results": (_i, [_vp, C.c_char_p]),
+    "pm_write_results_ps": (_i, [_vp, C.c_char_p, _i]),
+    "pm_labels_from_files": (_i, [_vp, C.c_char_p]),
+    "pm_io_read_vertex_data": (_i, [C.c_char_p, _u64, _vp, C.POINTER(_u64), C.c_char_p, C.c_size_t]),
+    "pm_io_check_edge_data": (_i, [C.c_char_p, _u64, C.POINTER(_u64), C.c_char_p, C.c_size_t]),
+    "pm_io_read_edge_lists": (_i, [C.POINTER(C.c_char_p), _i, _i, C.POINTER(_u64), C.POINTER(_u64), _vp, _vp,
+                                   C.c_char_p, C.c_size_t]),
 }
 
 _LIB = None

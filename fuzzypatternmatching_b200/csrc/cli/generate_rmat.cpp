@@ -37,13 +37,12 @@ int main(int argc, char** argv) {
       case 'o': out = optarg; have_out = true; break;
       case 'b': backup = optarg; break;
       case 'r': gen_ranks = std::strtoull(optarg, nullptr, 10); break;
-      case 'p': case 'f': case 'c': break;  // partitioning knobs of the mmap store: accepted, unused
+      case 'p': case 'f': case 'c': break;  // knobs of the reference's mmap store and partitioning passes: nothing to tune here
       case 'h': help = true; break;
       default: help = true; break;
     }
   }
   if (help || !have_out) { usage(); return -1; }
-  (void)threshold;
   std::cout << "Building Graph500\nBuilding graph Scale: " << scale << "\nGenerating ranks = " << gen_ranks
             << "\nFile name = " << out << std::endl;
   pm_ctx* ctx = nullptr;
@@ -54,6 +53,7 @@ int main(int argc, char** argv) {
   pmcli::Container c;
   c.n_vertices = gi.n_vertices; c.n_slots = gi.n_slots; c.n_slots_multi = gi.n_slots_multi;
   c.scale = scale; c.gen_ranks = gen_ranks;
+  c.delegate_threshold = threshold;  // kept with the graph: run_pattern_matching_beta attributes hubs to their controllers
   c.rowptr.resize(gi.n_vertices + 1);
   c.degree_multi.resize(gi.n_vertices);
   c.col.resize(gi.n_slots);
@@ -63,6 +63,11 @@ int main(int argc, char** argv) {
   }
   std::cout << "Graph Ready, Calculating Stats. " << std::endl;
   std::cout << "Max Degree = " << gi.max_degree << std::endl;
+  {
+    uint64_t hubs = 0;
+    for (uint64_t d : c.degree_multi) hubs += d >= threshold;
+    std::cout << "Delegate threshold = " << threshold << ", delegates = " << hubs << std::endl;
+  }
   std::string err;
   if (!pmcli::write_container(pmcli::container_path(out), c, err)) { std::cerr << "Error: " << err << std::endl; return 1; }
   if (!backup.empty() && !pmcli::copy_file(pmcli::container_path(out), pmcli::container_path(backup), err)) {

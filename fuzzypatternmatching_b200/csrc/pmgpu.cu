@@ -19,6 +19,7 @@
 #include "pm_nlcc_multi.cuh"
 #include "pm_rmat.cuh"
 #include "pm_fuzzy.cuh"
+#include "pm_io.hpp"
 
 using namespace pm;
 
@@ -409,6 +410,56 @@ int pm_labels_set(pm_ctx* c, const uint64_t* labels) {
     max_label = std::max<uint64_t>(max_label, labels[v]);
   }
   return labels_derive(c, small, max_label);
+}
+
+int pm_labels_from_files(pm_ctx* c, const char* base) {
+  if (!c || !c->has_graph || !base) return fail(c, PM_ERR_ARG, "pm_labels_from_files: no graph or null base");
+  std::vector<uint64_t> labels(c->V, 0);  // VertexData is value-initialised (beta.cpp:344-349)
+  std::string err;
+  if (!io::read_vertex_data(base, c->V, labels.data(), nullptr, err)) return fail(c, PM_ERR_IO, err);
+  return pm_labels_set(c, labels.data());
+}
+
+static void copy_err(const std::string& why, char* err_out, size_t err_cap) {
+  if (!err_out || !err_cap) return;
+  std::strncpy(err_out, why.c_str(), err_cap - 1);
+  err_out[err_cap - 1] = 0;
+}
+
+int pm_io_read_vertex_data(const char* base, uint64_t n_vertices, uint64_t* labels_inout, uint64_t* n_pairs_out,
+                           char* err_out, size_t err_cap) {
+  if (err_out && err_cap) err_out[0] = 0;
+  if (!base || !labels_inout) return PM_ERR_ARG;
+  std::string err;
+  if (!io::read_vertex_data(base, n_vertices, labels_inout, n_pairs_out, err)) { copy_err(err, err_out, err_cap); return PM_ERR_IO; }
+  return 0;
+}
+
+int pm_io_check_edge_data(const char* base, uint64_t n_vertices, uint64_t* n_records_out, char* err_out, size_t err_cap) {
+  if (err_out && err_cap) err_out[0] = 0;
+  if (!base) return PM_ERR_ARG;
+  std::string err;
+  if (!io::check_edge_data(base, n_vertices, n_records_out, err)) { copy_err(err, err_out, err_cap); return PM_ERR_IO; }
+  return 0;
+}
+
+int pm_io_read_edge_lists(const char* const* files, int n_files, int undirected, uint64_t* n_vertices_out,
+                          uint64_t* n_slots_out, uint32_t* src_out, uint32_t* dst_out, char* err_out, size_t err_cap) {
+  if (err_out && err_cap) err_out[0] = 0;
+  if (!files || n_files < 0) return PM_ERR_ARG;
+  std::vector<std::string> fs;
+  for (int i = 0; i < n_files; ++i) fs.push_back(files[i] ? files[i] : "");
+  std::vector<uint32_t> src, dst;
+  uint64_t nv = 0;
+  std::string err;
+  if (!io::read_edge_lists(fs, undirected != 0, src, dst, nv, err)) { copy_err(err, err_out, err_cap); return PM_ERR_IO; }
+  if (n_vertices_out) *n_vertices_out = nv;
+  if (n_slots_out) *n_slots_out = src.size();
+  if (src_out && dst_out) {
+    std::copy(src.begin(), src.end(), src_out);
+    std::copy(dst.begin(), dst.end(), dst_out);
+  }
+  return 0;
 }
 
 int pm_labels_get(const pm_ctx* cc, uint64_t* out) {
@@ -1494,25 +1545,28 @@ int pm_get_subgraphs(const pm_ctx* c, int pl, uint32_t* rows_out) {
 }
 
 // result tree of beta.cpp:504-535, 713-717, 1375-1425 (row grammar: SURVEY A.5)
-int pm_write_results(const pm_ctx* cc, const char* outdir) {
+int pm_write_results(const pm_ctx* cc, const char* outdir) { return pm_write_results_ps(cc, outdir, 0); }
+
+int pm_write_results_ps(const pm_ctx* cc, const char* outdir, int ps_index) {
   pm_ctx* c = const_cast<pm_ctx*>(cc);
-  if (!c || !outdir || !c->state_ready) return PM_ERR_ARG;
-  const std::string base(outdir), ps = base + "/0";
+  if (!c || !outdir || !c->state_ready || ps_index < 0) return PM_ERR_ARG;
+  const std::string base(outdir), ps = base + "/" + std::to_string(ps_index);
   const std::string rk = std::to_string(c->rank);
-  auto open = [&](const std::string& p, std::ofstream& f) -> bool {
-    f.open(p, std::ofstream::out);
+  auto open = [&](const std::string& p, std::ofstream& f, bool append = false) -> bool {
+    f.open(p, append ? std::ofstream::app : std::ofstream::out);
     if (!f) c->err = "cannot open " + p + " (the result tree must pre-exist, like the reference's)";
     return (bool)f;
   };
   if (c->rank == 0) {
     std::ofstream f_set, f_itr, f_step, f_ss;
-    if (!open(base + "/result_pattern_set", f_set) || !open(ps + "/result_iteration", f_itr) ||
+    // one result_pattern_set per run (beta.cpp:413-414), one row per element of the set (:1375-1381)
+    if (!open(base + "/result_pattern_set", f_set, ps_index > 0) || !open(ps + "/result_iteration", f_itr) ||
         !open(ps + "/result_step", f_step) || !open(ps + "/result_superstep", f_ss))
       return PM_ERR_IO;
     for (size_t i = 0; i < c->iter_seconds.size(); ++i) f_itr << i << ", " << c->iter_seconds[i] << "\n";
     for (auto& s : c->step_rows) f_step << s.first << ", LP, " << s.second << "\n";
     for (auto& r : c->rows) f_ss << r.itr << (r.kind == 0 ? ", LP, " : ", TP, ") << r.index << ", " << r.seconds << "\n";
-    f_set << 0 << ", " << c->n_ranks << ", " << c->summary.iterations << ", " << c->summary.search_seconds << ", "
+    f_set << ps_index << ", " << c->n_ranks << ", " << c->summary.iterations << ", " << c->summary.search_seconds << ", "
           << c->pat.n_edges << ", " << c->pat.n_vertices << ", " << c->pat.constraints.size() << "\n";
   }
   std::ofstream fvc, fec, fv, fe, fm;

@@ -112,6 +112,10 @@ class Engine:
         labels = np.ascontiguousarray(labels, dtype=np.uint64)
         self._chk(self._lib.pm_labels_set(self._h, labels.ctypes.data))
 
+    def labels_from_files(self, base):
+        """-v <base>: "vertex label" files named <base>* (vertex_data_db.hpp:139-262)"""
+        self._chk(self._lib.pm_labels_from_files(self._h, base.encode()))
+
     def labels_get(self):
         out = np.empty(self.graph_info()["n_vertices"], dtype=np.uint64)
         self._chk(self._lib.pm_labels_get(self._h, out.ctypes.data))
@@ -205,8 +209,8 @@ class Engine:
         self._chk(self._lib.pm_get_subgraph_count(self._h, pl, C.byref(cnt), C.byref(w)))
         return int(cnt.value)
 
-    def write_results(self, outdir):
-        self._chk(self._lib.pm_write_results(self._h, outdir.encode()))
+    def write_results(self, outdir, ps=0):
+        self._chk(self._lib.pm_write_results_ps(self._h, outdir.encode(), ps))
 
     def kernel_stats(self, bin=0):
         ks = _lib.KernelStats()
@@ -215,6 +219,47 @@ class Engine:
 
     def kernel_launches(self):
         return int(self._lib.pm_kernel_launches(self._h))
+
+
+def read_vertex_data(base, n_vertices, labels=None):
+    """Host-only -v reader (pm_io_read_vertex_data).  Returns (labels, number of pairs read)."""
+    lib = _lib.load()
+    out = np.zeros(n_vertices, dtype=np.uint64) if labels is None else np.ascontiguousarray(labels, dtype=np.uint64).copy()
+    n = C.c_uint64(0)
+    err = C.create_string_buffer(512)
+    rc = lib.pm_io_read_vertex_data(base.encode(), n_vertices, out.ctypes.data, C.byref(n), err, len(err))
+    if rc != 0:
+        raise ValueError(err.value.decode() or "pm_io_read_vertex_data failed (%d)" % rc)
+    return out, int(n.value)
+
+
+def check_edge_data(base, n_vertices):
+    """Host-only validation of -e files (pm_io_check_edge_data).  Returns the number of records."""
+    lib = _lib.load()
+    n = C.c_uint64(0)
+    err = C.create_string_buffer(512)
+    rc = lib.pm_io_check_edge_data(base.encode(), n_vertices, C.byref(n), err, len(err))
+    if rc != 0:
+        raise ValueError(err.value.decode() or "pm_io_check_edge_data failed (%d)" % rc)
+    return int(n.value)
+
+
+def read_edge_lists(files, undirected=False):
+    """Host-only edge-list reader of ingest_edge_list (pm_io_read_edge_lists).  Returns (n_vertices, src, dst)."""
+    lib = _lib.load()
+    arr = (C.c_char_p * len(files))(*[f.encode() for f in files])
+    nv, ns = C.c_uint64(0), C.c_uint64(0)
+    err = C.create_string_buffer(512)
+    rc = lib.pm_io_read_edge_lists(arr, len(files), int(undirected), C.byref(nv), C.byref(ns), None, None, err, len(err))
+    if rc != 0:
+        raise ValueError(err.value.decode() or "pm_io_read_edge_lists failed (%d)" % rc)
+    src = np.empty(max(ns.value, 1), dtype=np.uint32)
+    dst = np.empty(max(ns.value, 1), dtype=np.uint32)
+    rc = lib.pm_io_read_edge_lists(arr, len(files), int(undirected), C.byref(nv), C.byref(ns), src.ctypes.data,
+                                   dst.ctypes.data, err, len(err))
+    if rc != 0:
+        raise ValueError(err.value.decode())
+    return int(nv.value), src[:ns.value], dst[:ns.value]
 
 
 def pattern_check_dir(directory, max_constraints=64):

@@ -107,6 +107,25 @@ int pm_labels_degree_log2(pm_ctx* ctx);
 int pm_labels_set(pm_ctx* ctx, const uint64_t* labels /* n_vertices, global ids */);
 int pm_labels_get(const pm_ctx* ctx, uint64_t* labels_out /* n_vertices */);
 
+/* -v <base>: every file of dirname(base) whose name starts with basename(base) holds "vertex label" lines
+ * (include/havoqgt/vertex_data_db.hpp:139-262); vertices without a line get label 0.  Collective over the ranks
+ * (every rank reads the same files).                                                                          */
+int pm_labels_from_files(pm_ctx* ctx, const char* base);
+
+/* ---- text inputs of the reference tools, host only (no context, no device) -------------------------------
+ * pm_io_read_vertex_data   the -v reader above into a caller buffer (labels_inout keeps the entries of
+ *                          vertices that have no line)
+ * pm_io_check_edge_data    the -e files (include/havoqgt/edge_data_db.hpp: "source target data" lines).  The
+ *                          path never reads the values (beta.cpp:906, an unused reference): parsed and validated only
+ * pm_io_read_edge_lists    "source target [weight]" lines (include/havoqgt/parallel_edge_list_reader.hpp:236-262)
+ *                          of src/ingest_edge_list.cpp; undirected != 0 adds the reverse of every edge (-u 1).
+ *                          Call with src_out = NULL for the sizes, then with buffers of n_slots entries.        */
+int pm_io_read_vertex_data(const char* base, uint64_t n_vertices, uint64_t* labels_inout, uint64_t* n_pairs_out,
+                           char* err_out, size_t err_cap);
+int pm_io_check_edge_data(const char* base, uint64_t n_vertices, uint64_t* n_records_out, char* err_out, size_t err_cap);
+int pm_io_read_edge_lists(const char* const* files, int n_files, int undirected, uint64_t* n_vertices_out,
+                          uint64_t* n_slots_out, uint32_t* src_out, uint32_t* dst_out, char* err_out, size_t err_cap);
+
 /* ---- pattern -------------------------------------------------------------
  * replaces ::graph 5-file ctor (include/havoqgt/graph.hpp:73-110) and
  * pattern_util (include/havoqgt/pattern_util.hpp:89-115); dir = "<p>/<ps>".   */
@@ -229,6 +248,9 @@ int pm_get_subgraphs(const pm_ctx* ctx, int pl, uint32_t* rows_out /* count * wi
 /* writes the reference's result tree (names and row grammar of beta.cpp:504-535,
  * 1375-1425); like the reference it never creates directories.               */
 int pm_write_results(const pm_ctx* ctx, const char* outdir);
+/* the same for element `ps` of a pattern set: files under <outdir>/<ps>/, one more row of <outdir>/result_pattern_set
+ * (appended for ps > 0).  The reference loops `for ps < 1` with a TODO (beta.cpp:424); the set loop is the drivers'. */
+int pm_write_results_ps(const pm_ctx* ctx, const char* outdir, int ps);
 
 #ifdef __cplusplus
 }

@@ -468,3 +468,102 @@ def test_full_size_properties(eng, which):
                 assert int(labels[x]) == spec["labels"][w[i]]
             for i in range(len(r) - 1):
                 assert (r[i], r[i + 1]) in es
+
+
+def _cli_compare(out_gpu, out_ref, ps, ranks, subgraph_pls):
+    import os
+    rels = []
+    for r in range(ranks):
+        rels += ["%d/all_ranks_active_vertices/active_vertices_%d" % (ps, r), "%d/all_ranks_active_edges/active_edges_%d" % (ps, r),
+                 "%d/all_ranks_active_vertices_count/active_vertices_%d" % (ps, r),
+                 "%d/all_ranks_active_edges_count/active_edges_%d" % (ps, r)]
+        rels += ["%d/all_ranks_subgraphs/subgraphs_%d_%d" % (ps, pl, r) for pl in subgraph_pls]
+    total = 0
+    for rel in rels:
+        a = sorted(open(os.path.join(out_gpu, rel)).read().splitlines())
+        b = sorted(open(os.path.join(out_ref, rel)).read().splitlines())
+        assert a == b, rel
+        total += len(a)
+    return total
+
+
+def test_cli_ingest_vertex_metadata_and_pattern_set(oracle, tmp_path):
+    """ingest_edge_list -u 1 + run_pattern_matching_beta -v -e over a pattern set <p>/0, <p>/1: the
+    result trees of both elements against the oracle's, one result_pattern_set row per element."""
+    import os
+    import subprocess
+    from fuzzypatternmatching_b200 import patterns as PT
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    bindir = os.path.join(root, "fuzzypatternmatching_b200", "bin")
+    n, m = 400, 2600
+    edges = cases.random_multigraph(31, n, m)
+    labels = cases.random_labels(31, n, [1, 2, 3, 4])
+    labels[n - 1] = 3
+    edges.append((n - 1, 0))  # the largest id appears in the edge list: ingest sizes the graph by it
+    with open(tmp_path / "edges_a.txt", "w") as f:
+        for a, b in edges[:1500]:
+            f.write("%d %d\n" % (a, b))
+    with open(tmp_path / "edges_b.txt", "w") as f:
+        for a, b in edges[1500:]:
+            f.write("%d %d 1\n" % (a, b))
+    gbase = str(tmp_path / "graph")
+    subprocess.check_call([os.path.join(bindir, "ingest_edge_list"), "-o", gbase, "-u", "1", "-d", "64",
+                           str(tmp_path / "edges_a.txt"), str(tmp_path / "edges_b.txt")], stdout=subprocess.DEVNULL)
+    meta = tmp_path / "meta"
+    meta.mkdir()
+    for part in range(2):
+        with open(meta / ("vlabel_%d" % part), "w") as f:
+            for v in range(part, n, 2):
+                if labels[v] != 0:
+                    f.write("%d %d\n" % (v, labels[v]))
+    with open(meta / "elabel_0", "w") as f:
+        for a, b in edges[:50]:
+            f.write("%d %d 7\n" % (a, b))
+    pdir = str(tmp_path / "pattern")
+    specs = [PT.triangle(1, 2, 3), PT.cycle4(1, 2, 3, 4)]
+    for ps, spec in enumerate(specs):
+        PT.write_pattern_dir(pdir, spec, ps=ps)
+    out_gpu = str(tmp_path / "gpu")
+    os.makedirs(out_gpu)
+    for ps in range(2):
+        oracle.make_result_tree(out_gpu, ps)
+    subprocess.check_call([os.path.join(bindir, "run_pattern_matching_beta"), "-i", gbase, "-p", pdir, "-o", out_gpu,
+                           "-v", str(meta / "vlabel"), "-e", str(meta / "elabel"), "-t", "1"], stdout=subprocess.DEVNULL)
+    g = oracle.Graph.from_undirected(n, edges)
+    for ps, spec in enumerate(specs):
+        out_ref = str(tmp_path / ("ref%d" % ps))
+        os.makedirs(out_ref)
+        oracle.make_result_tree(out_ref)
+        ref = oracle.Run(g, labels, oracle.Pattern(os.path.join(pdir, str(ps))), n_ranks=1, tds_from_pl=1)
+        ref.write_results(out_ref)
+        os.rename(os.path.join(out_ref, "0"), os.path.join(out_ref, "x"))
+        os.rename(os.path.join(out_ref, "x"), os.path.join(out_ref, str(ps)))
+        assert _cli_compare(out_gpu, out_ref, ps, 1, [1]) > 0
+    rows = open(os.path.join(out_gpu, "result_pattern_set")).read().splitlines()
+    assert [r.split(",")[0].strip() for r in rows] == ["0", "1"]
+
+
+def test_cli_two_ranks_write_every_rank_file(oracle, tmp_path):
+    """run_pattern_matching_beta -n 2: one process per GPU, per-rank files *_0 and *_1 equal to a 2-rank oracle run."""
+    import os
+    import subprocess
+    import torch
+    from fuzzypatternmatching_b200 import patterns as PT
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    bindir = os.path.join(root, "fuzzypatternmatching_b200", "bin")
+    gbase = str(tmp_path / "rmat")
+    subprocess.check_call([os.path.join(bindir, "generate_rmat"), "-s", "17", "-r", "4", "-o", gbase], stdout=subprocess.DEVNULL)
+    pdir = str(tmp_path / "pattern")
+    PT.write_pattern_dir(pdir, PT.RMAT_LOG2_TREE)
+    out_gpu, out_ref = str(tmp_path / "gpu"), str(tmp_path / "ref")
+    for o in (out_gpu, out_ref):
+        os.makedirs(o)
+        oracle.make_result_tree(o)
+    subprocess.check_call([os.path.join(bindir, "run_pattern_matching_beta"), "-i", gbase, "-p", pdir, "-o", out_gpu, "-n", "2"],
+                          stdout=subprocess.DEVNULL, timeout=600)
+    g = oracle.Graph.rmat(17, 4)
+    ref = oracle.Run(g, g.labels_degree_log2(), oracle.Pattern(os.path.join(pdir, "0")), n_ranks=2, tds_from_pl=4)
+    ref.write_results(out_ref)
+    assert _cli_compare(out_gpu, out_ref, 0, 2, [4]) > 0

@@ -29,7 +29,11 @@ namespace pm {
 
 // Template (pattern) constants, uploaded once per pattern.
 struct PatConst {
-  uint16_t N[16];      // N[p]: template neighbours of template vertex p
+  uint16_t N[16];      // N[p]: template neighbours of template vertex p over mandatory edges
+  uint16_t No[16];     // ... over optional edges (approximate matching; all zero for an exact pattern)
+  uint8_t min_opt[16]; // vertex_min_optional_edge_count (0: no requirement)
+  int approx;          // approximate local constraint (approximate_pattern_matching/local_constraint_checking.hpp)
+  uint32_t never;      // bit p: the minimum optional edge count of p exceeds its optional edges (p can never stay)
   uint16_t LMc[17];    // class -> bitmask of template vertices carrying that label; [16] = 0
   uint64_t clabel[16]; // class -> label value
   int ncls;

@@ -38,21 +38,31 @@ namespace pm {
 
 __constant__ PatConst c_pat;
 
+// template vertices a valid parent may carry: neighbours over mandatory AND optional edges
+// (ee.hpp:673-722; approximate_pattern_matching/local_constraint_checking.hpp:641-651)
 __device__ __forceinline__ uint32_t nb_of(uint32_t T) {
   uint32_t r = 0;
 #pragma unroll
   for (int p = 0; p < 16; ++p)
-    if ((T >> p) & 1u) r |= c_pat.N[p];
+    if ((T >> p) & 1u) r |= (uint32_t)c_pat.N[p] | c_pat.No[p];
   return r;
 }
 
-// bits p of T whose template neighbourhood is non-empty and entirely heard
+// bits p of T that keep their place: exact pattern — the template neighbourhood is non-empty and entirely heard
+// (ee.hpp:901-939); approximate pattern — every mandatory neighbour heard (none required: fine), and where a minimum
+// optional edge count is set, every optional neighbour heard and at least that many of them
+// (approximate_pattern_matching/local_constraint_checking.hpp:1062-1113)
 __device__ __forceinline__ uint32_t cover_of(uint32_t T, uint32_t heard) {
   uint32_t r = 0;
 #pragma unroll
   for (int p = 0; p < 16; ++p) {
-    uint32_t need = c_pat.N[p];
-    if (((T >> p) & 1u) && need != 0u && (need & ~heard) == 0u) r |= 1u << p;
+    const uint32_t need = c_pat.N[p];
+    bool ok = (need & ~heard) == 0u && (need != 0u || c_pat.approx);
+    if (c_pat.approx && c_pat.min_opt[p]) {
+      const uint32_t opt = c_pat.No[p];
+      ok = ok && (opt & ~heard) == 0u && __popc(opt) >= (int)c_pat.min_opt[p];
+    }
+    if (((T >> p) & 1u) && ok) r |= 1u << p;
   }
   return r;
 }
@@ -230,8 +240,12 @@ __global__ void __launch_bounds__(kBlock) k_init_flags(const uint8_t* __restrict
             const unsigned long long sg = sig[v0 + 4 * g + k];
             uint32_t surv = use_sig ? 0u : 1u;
             for (uint32_t rest = lm; rest; rest &= rest - 1) {
-              const unsigned long long rq = c_pat.req[__ffs(rest) - 1];
-              if (rq != 0ull && (sg & rq) == rq) surv = 1;
+              const int pp = __ffs(rest) - 1;
+              const unsigned long long rq = c_pat.req[pp];
+              // approximate pattern: nothing may be required (rq == 0), but only a vertex that heard a valid
+              // neighbour ever enters the map; never[pp]: the minimum optional edge count cannot be met
+              if (c_pat.approx ? ((sg & rq) == rq && (sg & s_rl[c]) != 0ull && !((c_pat.never >> pp) & 1u))
+                               : (rq != 0ull && (sg & rq) == rq)) surv = 1;
             }
             any_removed = any_removed || (!surv && (sg & s_rl[c]) != 0ull);  // entered the map and left it (ee.hpp:941-946)
             ncand++;
@@ -250,8 +264,10 @@ __global__ void __launch_bounds__(kBlock) k_init_flags(const uint8_t* __restrict
             const unsigned long long sg = sig[v];
             uint32_t surv = use_sig ? 0u : 1u;
             for (uint32_t rest = lm; rest; rest &= rest - 1) {
-              const unsigned long long rq = c_pat.req[__ffs(rest) - 1];
-              if (rq != 0ull && (sg & rq) == rq) surv = 1;
+              const int pp = __ffs(rest) - 1;
+              const unsigned long long rq = c_pat.req[pp];
+              if (c_pat.approx ? ((sg & rq) == rq && (sg & s_rl[c]) != 0ull && !((c_pat.never >> pp) & 1u))
+                               : (rq != 0ull && (sg & rq) == rq)) surv = 1;
             }
             any_removed = any_removed || (!surv && (sg & s_rl[c]) != 0ull);
             ncand++;
@@ -636,6 +652,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_lcc_scan(LccArgs a, uint4* __rest
       } else {
         const uint32_t T0 = FIRST ? Tv : e.w;
         ts = Tv ? cover_of(T0, heard) : 0u;
+        if (FIRST && heard == 0u) ts = 0u;   // never entered the map (ee.hpp:841-866; an approximate pattern may require nothing)
         if (xlate_only) ts = Tv ? e.w : 0u;  // renaming only: T_state stays as it is
         // a vertex leaves the vertex_state_map (ee.hpp:941-946, :968-970).  In the first
         // superstep only vertices that heard a valid neighbour ever entered the map (:841-852).
@@ -883,6 +900,7 @@ __global__ void __launch_bounds__(1024) k_lcc_scan_big(LccArgs a, uint4* __restr
       } else {
         const uint32_t T0 = FIRST ? Tv : e.w;
         ts = Tv ? cover_of(T0, h) : 0u;
+        if (FIRST && h == 0u) ts = 0u;       // never entered the map
         if (xlate_only) ts = Tv ? e.w : 0u;  // renaming only: T_state stays as it is
         if (ts == 0 && (FIRST ? h != 0u : Tv != 0u)) a.cnt->nf = 1u;
       }

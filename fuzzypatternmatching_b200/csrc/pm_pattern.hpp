@@ -12,6 +12,13 @@
 //                                (pattern_util.hpp:254-278)
 // pattern_vertex and pattern_edge_data are read by the reference but never used
 // on this path, so they are not required here.
+//
+// Approximate matching (run_pattern_matching_beta_2.cpp:459-476, include/havoqgt/approximate_pattern_matching/
+// pattern_graph.hpp:282-337, 604-622): a pattern_edge line may carry a third column, "s t flag" with flag 1 = mandatory
+// and 0 = optional edge (lines without the column are mandatory, the format above), and
+//   pattern_vertex_local_constraints   "v : min_optional_edge_count" per template vertex (-1 / 0: no requirement)
+// gives vertex_min_optional_edge_count.  Either one switches the local constraint to the approximate form of
+// approximate_pattern_matching/local_constraint_checking.hpp:625-651, 1062-1113.
 #pragma once
 
 #include <stdint.h>
@@ -41,7 +48,10 @@ struct Pattern {
   int n_edges = 0;   // lines of pattern_edge (= directed template edges)
   int diameter = 0;  // LCC supersteps per call
   std::vector<uint64_t> vertex_label;
-  uint16_t N[16] = {0};
+  uint16_t N[16] = {0};      // template neighbours over MANDATORY edges (every edge, for an exact pattern)
+  uint16_t No[16] = {0};     // template neighbours over OPTIONAL edges (approximate matching)
+  int min_opt[16] = {0};     // vertex_min_optional_edge_count (values <= 0: no requirement)
+  bool approximate = false;  // the pattern has an optional edge or a pattern_vertex_local_constraints file
   std::vector<Constraint> constraints;
 };
 
@@ -90,7 +100,12 @@ inline std::string load_pattern_dir(const std::string& dir, Pattern& pat) {
         return "pattern_edge: template vertex ids must be < 16 (std::bitset<16>, beta.cpp:270-271)";
       if ((long long)st[0] < prev) return "pattern_edge: lines must be sorted by source (graph.hpp:224-270)";
       prev = (long long)st[0];
-      pat.N[st[0]] |= (uint16_t)(1u << st[1]);
+      if (st.size() >= 3 && st[2] == 0) {  // optional edge (approximate_pattern_matching/pattern_graph.hpp:320-337, 609-616)
+        pat.No[st[0]] |= (uint16_t)(1u << st[1]);
+        pat.approximate = true;
+      } else {
+        pat.N[st[0]] |= (uint16_t)(1u << st[1]);
+      }
       pat.n_edges++;
     }
     if (prev < 0) return "pattern_edge is empty";
@@ -110,6 +125,23 @@ inline std::string load_pattern_dir(const std::string& dir, Pattern& pat) {
     if ((int)pat.vertex_label.size() != pat.n_vertices)
       return "pattern_vertex_data lists " + std::to_string(pat.vertex_label.size()) + " template vertices, pattern_edge " +
              std::to_string(pat.n_vertices);
+  }
+  {
+    // vertex_min_optional_edge_count (approximate_pattern_matching/pattern_graph.hpp:282-315), optional file
+    std::ifstream f(base + "_vertex_local_constraints");
+    while (f && std::getline(f, line)) {
+      if (strip(line).empty()) continue;
+      auto kv = fields(line);
+      std::vector<uint64_t> v;
+      if (kv.size() < 2 || !numbers(kv[0], v) || v.size() != 1 || v[0] > 15)
+        return "pattern_vertex_local_constraints: expected '<template vertex> : <min optional edge count>'";
+      const std::string cnt = strip(kv[1]);
+      char* end = nullptr;
+      const long k = std::strtol(cnt.c_str(), &end, 10);
+      if (cnt.empty() || *end != 0) return "pattern_vertex_local_constraints: bad count '" + cnt + "'";
+      pat.min_opt[v[0]] = (int)std::max<long>(k, 0);
+      pat.approximate = true;
+    }
   }
   {
     std::ifstream f(base + "_stat");

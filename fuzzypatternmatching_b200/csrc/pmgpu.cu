@@ -494,7 +494,13 @@ int pm_pattern_load_dir(pm_ctx* c, const char* dir) {
   if (!why.empty()) return fail(c, PM_ERR_PATTERN, why);
   PatConst pc;
   std::memset(&pc, 0, sizeof(pc));
-  for (int i = 0; i < 16; ++i) pc.N[i] = p.N[i];
+  for (int i = 0; i < 16; ++i) {
+    pc.N[i] = p.N[i];
+    pc.No[i] = p.No[i];
+    pc.min_opt[i] = (uint8_t)std::min(p.min_opt[i], 255);
+    if (p.min_opt[i] > __builtin_popcount(p.No[i])) pc.never |= 1u << i;
+  }
+  pc.approx = p.approximate ? 1 : 0;
   // distinct template labels -> classes (ee.hpp:371-380 compares every template label)
   for (size_t i = 0; i < p.vertex_label.size(); ++i) {
     int k = 0;
@@ -508,13 +514,16 @@ int pm_pattern_load_dir(pm_ctx* c, const char* dir) {
   // first-superstep tables over the neighbour-label signature (labels < 64): every neighbour u sends
   // labelmask(label[u]) (ee.hpp:519-561), a sender is valid iff its mask meets NB(T_v) (:673-722), and
   // template vertex p survives iff N(p) is covered by what was heard (:901-939)
+  // (approximate pattern: the optional neighbours count as required where a minimum optional edge count is set,
+  //  local_constraint_checking.hpp:1090-1099; valid senders come over mandatory and optional edges, :641-651)
   for (int i = 0; i < p.n_vertices && i < 16; ++i)
-    for (int b = 0; b < 16; ++b)
-      if (((pc.N[i] >> b) & 1u) && b < (int)p.vertex_label.size() && p.vertex_label[b] < 64)
-        pc.req[i] |= 1ull << p.vertex_label[b];
+    for (int b = 0; b < 16; ++b) {
+      const bool needed = ((pc.N[i] >> b) & 1u) || (pc.min_opt[i] && ((pc.No[i] >> b) & 1u));
+      if (needed && b < (int)p.vertex_label.size() && p.vertex_label[b] < 64) pc.req[i] |= 1ull << p.vertex_label[b];
+    }
   for (int k = 0; k < pc.ncls; ++k) {
     uint32_t nb = 0;
-    for (int a = 0; a < 16; ++a) if ((pc.LMc[k] >> a) & 1u) nb |= pc.N[a];
+    for (int a = 0; a < 16; ++a) if ((pc.LMc[k] >> a) & 1u) nb |= (uint32_t)pc.N[a] | pc.No[a];
     for (int q = 0; q < pc.ncls; ++q)
       if ((pc.LMc[q] & nb) && pc.clabel[q] < 64) pc.rl[k] |= 1ull << pc.clabel[q];
   }

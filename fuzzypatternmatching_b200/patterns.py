@@ -14,6 +14,11 @@ A spec is a dict:
   diameter    : number of LCC supersteps per call (pattern_stat "diameter")
   constraints : list of dicts {walk: [template ids], cycle: bool,
                                interleave: bool (default True), tds: bool}
+  optional_edges : (approximate matching, run_pattern_matching_beta_2.cpp:459-476) undirected (a, b) that are
+                   OPTIONAL: their pattern_edge lines carry the flag column "s t 0", every other line "s t 1"
+                   (approximate_pattern_matching/pattern_graph.hpp:320-337); must be a subset of `edges`
+  min_optional   : {template vertex: vertex_min_optional_edge_count} -> pattern_vertex_local_constraints
+                   ("v : count" per template vertex, -1 where none is given; pattern_graph.hpp:282-315)
 Constraints flagged tds must come last: the reference switches to template
 driven search by constraint INDEX (`pl >= 4`, beta.cpp:762), which the engine
 exposes as the `tds_from_pl` option; `tds_from_pl(spec)` returns that index.
@@ -44,9 +49,23 @@ def write_pattern_dir(base, spec, ps=0):
     eid = {}
     for a, b in spec["edges"]:
         eid[(a, b)] = eid[(b, a)] = len(eid) // 2
+    optional = set()
+    for a, b in spec.get("optional_edges", []):
+        optional |= {(a, b), (b, a)}
+    approximate = bool(optional) or "min_optional" in spec
     with open(os.path.join(d, "pattern_edge"), "w") as f:
         for a, b in both:
-            f.write("%d %d\n" % (a, b))
+            if approximate:
+                f.write("%d %d %d\n" % (a, b, 0 if (a, b) in optional else 1))
+            else:
+                f.write("%d %d\n" % (a, b))
+    lc = os.path.join(d, "pattern_vertex_local_constraints")
+    if approximate:
+        with open(lc, "w") as f:
+            for i in range(len(labels)):
+                f.write("%d : %d\n" % (i, spec.get("min_optional", {}).get(i, -1)))
+    elif os.path.exists(lc):
+        os.remove(lc)
     with open(os.path.join(d, "pattern_edge_data"), "w") as f:
         for a, b in both:
             f.write("%d %d %d 55\n" % (a, b, eid[(a, b)]))

@@ -304,7 +304,11 @@ struct orc_constraint {
 struct orc_pattern {
   int nv = 0, ne = 0, diameter = 0;
   std::vector<uint64_t> vlabel;
-  uint16_t N[16] = {0};
+  uint16_t N[16] = {0};     // template neighbours over mandatory edges (every edge of an exact pattern)
+  // approximate matching: approximate_pattern_matching/pattern_graph.hpp:282-337, 604-622
+  uint16_t No[16] = {0};    // ... over optional edges ("s t 0" lines of pattern_edge)
+  int min_opt[16] = {0};    // vertex_min_optional_edge_count (pattern_vertex_local_constraints, "v : count")
+  bool approximate = false;
   std::vector<orc_constraint> cons;
   std::string err;
 };
@@ -347,12 +351,18 @@ orc_pattern* orc_pattern_load(const char* dir) {
     while (std::getline(f, line)) {
       if (trim(line).empty()) continue;
       std::istringstream iss(line);
-      unsigned long long s = 0, t = 0;
+      unsigned long long s = 0, t = 0, flag = 1;
       iss >> s >> t;
+      const bool has_flag = (bool)(iss >> flag);  // "s t flag": 1 mandatory, 0 optional (approximate .. pattern_graph.hpp:320-337)
       if (s >= 16 || t >= 16) { p->err = "template vertex id >= 16 (beta.cpp:270-271)"; return p; }
       if ((long long)s < last_s) { p->err = "pattern_edge not sorted by source (graph.hpp:224-270)"; return p; }
       last_s = (long long)s;
-      p->N[s] |= (uint16_t)(1u << t);
+      if (has_flag && flag == 0) {
+        p->No[s] |= (uint16_t)(1u << t);
+        p->approximate = true;
+      } else {
+        p->N[s] |= (uint16_t)(1u << t);
+      }
       p->ne++;
     }
     p->nv = (int)(last_s + 1);  // vertex count = last source + 1 (graph.hpp:226,262)
@@ -369,6 +379,18 @@ orc_pattern* orc_pattern_load(const char* dir) {
       p->vlabel.push_back(lab);
     }
     if (p->vlabel.size() > 16) { p->err = "more than 16 template vertices"; return p; }
+  }
+  // pattern_vertex_local_constraints: "v : min_optional_edge_count" (approximate .. pattern_graph.hpp:282-315)
+  {
+    std::ifstream f(base + "_vertex_local_constraints");
+    while (f && std::getline(f, line)) {
+      auto t = split_colon(line);
+      if (t.size() < 2) continue;
+      const unsigned long long v = std::stoull(t[0]);
+      const long k = std::stol(t[1]);
+      if (v < 16) p->min_opt[v] = (int)std::max<long>(k, 0);
+      p->approximate = true;
+    }
   }
   // pattern_stat: "diameter : <int>", key case-insensitive (graph.hpp:337-358)
   {
@@ -489,7 +511,18 @@ struct Ctx {
     for (int p = 0; p < 16; ++p)
       if ((T >> p) & 1) {
         uint16_t need = pat->N[p];
-        if (need != 0 && (need & heard) == need) out |= (uint16_t)(1u << p);
+        if (!pat->approximate) {
+          if (need != 0 && (need & heard) == need) out |= (uint16_t)(1u << p);
+          continue;
+        }
+        // approximate local constraint, approximate_pattern_matching/local_constraint_checking.hpp:1062-1113
+        bool mandatory_ok = need == 0 || (need & heard) == need;                               // :1080-1088
+        bool optional_ok = true;                                                               // :1090-1099
+        if (pat->min_opt[p] > 0) {
+          uint16_t got = pat->No[p] & heard;
+          optional_ok = got == pat->No[p] && __builtin_popcount(got) >= pat->min_opt[p];
+        }
+        if (mandatory_ok && optional_ok) out |= (uint16_t)(1u << p);
       }
     return out;
   }
@@ -803,7 +836,7 @@ orc_run* orc_run_pattern(const orc_graph* g, const uint64_t* labels, const orc_p
   for (uint32_t T = 1; T < 65536; ++T) {
     uint32_t low = T & (~T + 1);
     int b = __builtin_ctz(low);
-    cx.NB[T] = (uint16_t)(cx.NB[T ^ low] | pat->N[b]);
+    cx.NB[T] = (uint16_t)(cx.NB[T ^ low] | pat->N[b] | pat->No[b]);  // valid parents come over mandatory and optional edges (approximate .. local_constraint_checking.hpp:641-651)
   }
 
   const int max_it = opt.max_iterations > 0 ? opt.max_iterations : 1000;

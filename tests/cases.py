@@ -82,6 +82,25 @@ QUIRK_SPECS = [
 ]
 
 
+# Approximate matching (approximate_pattern_matching/local_constraint_checking.hpp:641-651, 1062-1113):
+# optional template edges and minimum optional edge counts.  (name, spec, labelset, tds_from_pl)
+APPROX_SPECS = [
+    # a square with one optional diagonal: the diagonal's end points need not see each other
+    ("square_optional_diagonal", {"labels": [1, 2, 3, 4], "edges": [(0, 1), (1, 2), (2, 3), (0, 3), (0, 2)],
+                                  "optional_edges": [(0, 2)], "diameter": 3,
+                                  "constraints": [{"walk": [0, 1, 2, 3, 0], "cycle": True}]}, [1, 2, 3, 4], -1),
+    # a star whose centre must keep both optional leaves once a minimum optional count is set, next to a mandatory one
+    ("star_min_optional", {"labels": [1, 2, 3, 4], "edges": [(0, 1), (0, 2), (0, 3)], "optional_edges": [(0, 2), (0, 3)],
+                           "min_optional": {0: 2}, "diameter": 2, "constraints": []}, [1, 2, 3, 4], -1),
+    # a path whose middle vertex has only optional edges (nothing is required of it locally)
+    ("path_all_optional_middle", {"labels": [1, 2, 3, 2], "edges": [(0, 1), (1, 2), (2, 3)],
+                                  "optional_edges": [(0, 1), (1, 2)], "diameter": 3, "constraints": []}, [1, 2, 3], -1),
+    # a minimum optional count that cannot be met: the vertex can never stay
+    ("impossible_min_optional", {"labels": [1, 2, 3], "edges": [(0, 1), (1, 2)], "optional_edges": [(1, 2)],
+                                 "min_optional": {1: 2}, "diameter": 2, "constraints": []}, [1, 2, 3], -1),
+]
+
+
 def quirk_inputs(name, divisor, seeds=range(24)):
     for seed in seeds:
         n, m = 60 + 10 * (seed % 4), (220 + 60 * (seed % 5)) // divisor

@@ -567,3 +567,46 @@ def test_cli_two_ranks_write_every_rank_file(oracle, tmp_path):
     ref = oracle.Run(g, g.labels_degree_log2(), oracle.Pattern(os.path.join(pdir, "0")), n_ranks=2, tds_from_pl=4)
     ref.write_results(out_ref)
     assert _cli_compare(out_gpu, out_ref, 0, 2, [4]) > 0
+
+
+@pytest.mark.parametrize("name,spec,labelset,tds_from", cases.APPROX_SPECS, ids=[s[0] for s in cases.APPROX_SPECS])
+def test_approximate_patterns_match_oracle(oracle, eng, name, spec, labelset, tds_from):
+    """optional template edges, vertex_min_optional_edge_count and the mandatory / optional coverage test
+    (approximate_pattern_matching/local_constraint_checking.hpp:641-651, 1062-1113) — small-label signature path,
+    large-label gather path and an R-MAT graph."""
+    import copy
+    nontrivial = 0
+    for seed in range(10):
+        n, m = 60 + 10 * (seed % 4), 160 + 40 * (seed % 5)
+        edges = cases.random_multigraph(seed + 500, n, m)
+        labels = cases.random_labels(seed + 500, n, labelset)
+        ref = _compare(oracle, eng, n, edges, labels, spec, tds_from)
+        nontrivial += ref.rows[-1][3] > 0
+    assert nontrivial >= (0 if name == "impossible_min_optional" else 3)
+    big = copy.deepcopy(spec)
+    big["labels"] = [l + 1000 for l in spec["labels"]]
+    for seed in range(3):
+        edges = cases.random_multigraph(seed + 600, 200, 700)
+        labels = cases.random_labels(seed + 600, 200, labelset) + np.uint64(1000)
+        _compare(oracle, eng, 200, edges, labels, big, tds_from)
+
+
+def test_approximate_pattern_on_rmat(oracle, eng):
+    g = oracle.Graph.rmat(17, 4)
+    labels = g.labels_degree_log2()
+    eng.graph_rmat(17, 4)
+    eng.labels_degree_log2()
+    for min_optional in ({}, {0: 1}, {2: 1}):
+        spec = {"labels": [5, 6, 7, 8], "edges": [(0, 1), (1, 2), (2, 3), (0, 3), (0, 2)], "optional_edges": [(0, 2)],
+                "diameter": 3, "constraints": [{"walk": [0, 1, 2, 3, 0], "cycle": True}]}
+        if min_optional:
+            spec["min_optional"] = min_optional
+        d = cases.pattern_dir(spec)
+        pat = oracle.Pattern(d)
+        ref = oracle.Run(g, labels, pat, tds_from_pl=-1)
+        eng.pattern_load_dir(d)
+        eng.run(tds_from_pl=-1)
+        got, want = cases.engine_summary(eng, pat.n_constraints), cases.run_summary(ref)
+        for k in ("rows", "iterations", "vertices", "edges"):
+            assert got[k] == want[k], (min_optional, k)
+        assert min_optional == {2: 1} or len(want["vertices"]) > 0

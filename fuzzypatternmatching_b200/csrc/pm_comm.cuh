@@ -157,6 +157,8 @@ __global__ void k_step_msg(DevCounters* cnt, StepMsg* msg) {
     msg->deleted = cnt->deleted;
     msg->overflow = cnt->overflow;
     msg->accepted = cnt->pool_n;
+    msg->peak = cnt->peak_out;
+    msg->ce_n = cnt->ce_n;
     msg->n_c = cnt->n_c;
     msg->pad1 = 0;
     msg->seq = 0;
@@ -189,6 +191,8 @@ __global__ void k_step_sync(DevCounters* cnt, StepMsg* msg, StepMsg* all_out, ui
     msg->deleted = cnt->deleted;
     msg->overflow = cnt->overflow;
     msg->accepted = cnt->pool_n;
+    msg->peak = cnt->peak_out;
+    msg->ce_n = cnt->ce_n;
     msg->n_c = cnt->n_c;
     msg->pad1 = 0;
     msg->seq = seq;

@@ -84,6 +84,8 @@ struct StepMsg {
   unsigned long long out_n[PM_MAX_RANKS];
   uint32_t ndelta, nf, found, deleted, overflow, pad;  // pad: nf_init
   unsigned long long accepted;   // tokens accepted so far (pool_n)
+  unsigned long long peak;       // fullest inbox region this rank has written in the current constraint
+  unsigned long long ce_n;       // closing-edge keys this rank filed
   uint32_t n_c, pad1;            // compact ids this rank owns (published once per pattern)
   uint32_t seq;                  // step number: written LAST, polled by the receiver
   uint32_t timeout;              // a peer never arrived (the step barrier gave up)

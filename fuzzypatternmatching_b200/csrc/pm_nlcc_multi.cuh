@@ -71,12 +71,15 @@ __device__ __forceinline__ void mark_edge_m(uint32_t s, uint32_t parent) {
 
 // One warp appends its accepted tokens to the inbox regions of their owners.  All 32 lanes call.
 // Positions come from this rank's own counters (cnt->out_n[g]); the stores go over NVLink.
+// TO_SOURCE: the records go to the owner of the SOURCE s (closing requests, k_close_check_m) instead of the owner of u
+template <bool TO_SOURCE = false>
 __device__ __forceinline__ void route_tokens(const NlcArgs& a, const bool (&flag)[4], const uint32_t (&u)[4], uint32_t s) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t lt = (1u << lane) - 1u;
   uint32_t dest[4];
+  const uint32_t so = TO_SOURCE ? cid_owner(s) : 0u;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) dest[k] = flag[k] ? cid_owner(u[k]) : 0xFFFFFFFFu;
+  for (int k = 0; k < 4; ++k) dest[k] = flag[k] ? (TO_SOURCE ? so : cid_owner(u[k])) : 0xFFFFFFFFu;
   for (int g = 0; g < c_peer.G; ++g) {
     uint32_t m[4], total = 0;
 #pragma unroll
@@ -229,6 +232,8 @@ __device__ __forceinline__ bool close_edge_known(const NlcArgs& a, uint32_t s, u
 //   MODE 0: interior hop, 1: final hop of a path or (generic) cycle constraint, 2: closing two hops of a cycle
 //   first: the tokens are the sources themselves (no aggregation test)
 // ---------------------------------------------------------------------------
+// first: no aggregation test on arrival — the tokens are the sources themselves, or were accepted at a hop where
+//   duplicates cannot occur (hop 1) or cannot matter (the level feeding the closing mode, up to hop 2)
 template <int MODE>
 __global__ void __launch_bounds__(kBlock) k_nem1_hop_m(NlcArgs a, int hn, int first) {
   const TokSrc src = tok_src(a, c_peer.tcap);
@@ -257,7 +262,7 @@ __global__ void __launch_bounds__(kBlock) k_nem1_hop_m(NlcArgs a, int hn, int fi
       d = a.adeg[v - a.base];
       if (gl == 0) accepted++;
       if (MODE == 1 && !c_nlc.valid_cycle && a.ok[s]) d = 0;  // acknowledged path source: later tokens are moot
-      if (MODE == 2) {
+      if (MODE == 2 || MODE == 3) {
         const uint32_t ss = a.S[s];
         if (ss == 0 || !hop_ok(ss, a.cls[s], hn + 1)) d = 0;  // receiver tests of the closing hop at the source
       }
@@ -281,8 +286,10 @@ __global__ void __launch_bounds__(kBlock) k_nem1_hop_m(NlcArgs a, int hn, int fi
         if (!may) continue;
         if (MODE == 2) {
           // u must be a qualifying neighbour of the source: one probe of the closing-edge set (which
-          // already holds the label / template-bit tests of hop C, evaluated by the owner of s)
-          pass[k] = close_edge_known(a, s, u[k]);
+          // already holds the label / template-bit tests of hop C, evaluated by the owner of s); the template
+          // bit of u is tested first — a gather from the L2 resident mask replica that spares most probes
+          const uint32_t su = a.S[u[k]];
+          pass[k] = su != 0 && ((su >> c_nlc.I[hn]) & 1u) && close_edge_known(a, s, u[k]);
           if (pass[k]) {
             ack_source(a, s);
             a.cnt->found = 1u;
@@ -292,6 +299,14 @@ __global__ void __launch_bounds__(kBlock) k_nem1_hop_m(NlcArgs a, int hn, int fi
         }
         const uint32_t su = a.S[u[k]];
         pass[k] = su != 0 && ((su >> c_nlc.I[hn]) & 1u);
+      }
+      if (MODE == 3) {
+        // closing two hops of a cycle, routed: every neighbour u of v that passes the tests of the last interior hop
+        // becomes a closing request (u, s) for the owner of s, who looks u up in E_s (k_close_check_m)
+        bool req[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) req[k] = pass[k] && u[k] != s;  // the source cannot relay (nem_1.hpp:174-177)
+        route_tokens<true>(a, req, u, s);
       }
       if (MODE == 1) {
 #pragma unroll
@@ -320,6 +335,33 @@ __global__ void __launch_bounds__(kBlock) k_nem1_hop_m(NlcArgs a, int hn, int fi
   }
   if (lane == 0 && fan) atomicAdd(&a.cnt->fanout, fan);
   if (lane == 0 && accepted) atomicAdd(&a.cnt->pool_n, accepted);
+}
+
+// Closing requests (u, s) that arrived for the sources this rank owns: the cycle closes iff u is a key of E_s
+// (the edge maps are symmetric between live vertices, see k_nem1_close_cycle): a binary search in the short,
+// local row of s.  Success acknowledges the source and flags E_s[u] (nem_1.hpp:749-770) — all local, no remote
+// atomics, no key broadcast.
+__global__ void __launch_bounds__(kBlock) k_close_check_m(NlcArgs a) {
+  const TokSrc src = tok_src(a, c_peer.tcap);
+  const uint2* __restrict__ in = c_peer.tin[a.par ^ 1][c_peer.rank];
+  for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < src.total;
+       t += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint2 rq = in[tok_locate(src, t, c_peer.tcap)];
+    const uint32_t u = rq.x, s = rq.y, li = s - a.base;
+    const uint64_t row = (uint64_t)a.rowblk[li] * 8;
+    const uint32_t d = a.adeg[li];
+    uint32_t b = 0, e = d;
+    while (b < e) {  // rows stay ascending: compaction is stable
+      const uint32_t mid = (b + e) >> 1;
+      const uint32_t x = a.colw[row + mid] & PM_IDMASK;
+      if (x < u) b = mid + 1; else e = mid;
+    }
+    if (b < d && (a.colw[row + b] & PM_IDMASK) == u) {
+      a.ok[s] = 1;
+      a.cnt->found = 1u;
+      atomicOr(&a.colw[row + b], 0x80000000u);
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------

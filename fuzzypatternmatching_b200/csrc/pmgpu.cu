@@ -922,11 +922,18 @@ int pm_nlcc(pm_ctx* c, int pl, int mode, int* pattern_found, int* token_source_d
   // per pattern directory may come from a smaller graph)
   want_pool = std::max<uint64_t>(want_pool, (c->rows.empty() ? c->nloc : c->rows.back().n_vertices) + 4096);
   uint64_t want_keys = c->keys_seen[pl] ? c->keys_seen[pl] + c->keys_seen[pl] / 2 + 4096 : want_pool;
-  if (multi) {  // growing the inboxes is collective
-    uint64_t w[2] = {want_pool, want_keys};
+  // several ranks: growing the inboxes is collective, so every rank must ask for the same sizes.  They do without
+  // asking one another: pool_seen / keys_seen hold maxima over ALL ranks (taken from the step messages below) and
+  // the row counts are made global here.
+  if (multi && !c->pool_seen[pl]) {
+    uint64_t w[2] = {ne_now, c->rows.empty() ? c->nloc : c->rows.back().n_vertices};
     if ((rc = comm_allreduce_u64(c, w, 2, ncclMax))) return rc;
-    want_pool = w[0];
-    want_keys = w[1];
+    want_pool = std::max<uint64_t>(std::max<uint64_t>(2 * w[0] + 65536, 1ull << 18), w[1] + 4096);
+    want_keys = want_pool;
+  } else if (multi) {
+    want_pool = std::max<uint64_t>(c->pool_seen[pl] + c->pool_seen[pl] / 2 + 4096, 1ull << 18);
+    want_pool = std::max<uint64_t>(want_pool, c->nlmax / 8 + 4096);  // level 0: sources of this rank, bounded without a reduction
+    want_keys = c->keys_seen[pl] + c->keys_seen[pl] / 2 + 4096;
   }
   if ((rc = nlcc_reserve(c, want_pool, want_keys))) return rc;
   auto pick_table = [&]() {
@@ -946,7 +953,8 @@ int pm_nlcc(pm_ctx* c, int pl, int mode, int* pattern_found, int* token_source_d
   // one rank: the (vertex, source) aggregation is skipped where it cannot change anything — hop 1 (the neighbours
   // of a source are distinct) and, up to hop 2, the level that feeds the closing kernel (idempotent effects)
   auto nem1_dedupe = [&](int hn) { return hn >= 2 && !(close2 && hn == (int)k.C - 1 && hn <= 2); };
-  bool any_dedupe = multi;
+  const bool routed_close = !getenv("PM_CLOSE_KEYS");  // PM_CLOSE_KEYS: the earlier key-broadcast formulation (several ranks)
+  bool any_dedupe = multi && close2 && !routed_close;  // the broadcast closing keys live in the hash set
   for (int hn = 1; !tds && hn <= (int)k.C; ++hn) any_dedupe = any_dedupe || (nem1_dedupe(hn) && !(close2 && hn == (int)k.C));
   for (int attempt = 0;; ++attempt) {
     if (tds && c->keep_subgraphs && !multi) {
@@ -963,7 +971,7 @@ int pm_nlcc(pm_ctx* c, int pl, int mode, int* pattern_found, int* token_source_d
     std::vector<cudaEvent_t> dev;
     auto mark = [&]() { if (dbg) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); dev.push_back(e); } };
     mark();
-    if (multi && close2) {
+    if (multi && close2 && !routed_close) {
       // every rank learns the qualifying (source, neighbour) pairs of the closing hop (k_close_keys_m)
       NlcArgs ka = nlc_args(c, nullptr, 0);
       k_close_keys_m<<<grid, kBlock, 0, st>>>(ka, c->fr[cur][0], c->fr[cur][1], cur, (int)k.C);
@@ -1030,12 +1038,23 @@ int pm_nlcc(pm_ctx* c, int pl, int mode, int* pattern_found, int* token_source_d
       mark();
       for (int hn = 1; walk && hn <= (int)k.C + 1; ++hn) {
         const bool fin = hn == (int)k.C + 1;
-        const int first = hn == 1 ? 1 : 0;
+        // the tokens picked up now were accepted at hop hn - 1: aggregation only where duplicates can occur
+        const int first = (hn == 1 || tds || !nem1_dedupe(hn - 1)) ? 1 : 0;
         a = nlc_args(c, nullptr, 0);
         bool last = fin;
         if (tds) {
           if (fin) k_tds_hop_m<true><<<grid, kBlock, 0, st>>>(a, hn);
           else k_tds_hop_m<false><<<grid, kBlock, 0, st>>>(a, hn);
+        } else if (close2 && hn == (int)k.C && routed_close) {
+          // closing requests travel to the owners of the sources, who check them against their own rows
+          k_nem1_hop_m<3><<<grid, kBlock, 0, st>>>(a, hn, first);
+          PM_LAUNCH_CHECK(c);
+          mark();
+          if ((rc = comm_step(c))) return rc;
+          mark();
+          c->step_parity ^= 1;
+          k_close_check_m<<<grid, kBlock, 0, st>>>(nlc_args(c, nullptr, 0));
+          last = true;
         } else if (close2 && hn == (int)k.C) {
           k_nem1_hop_m<2><<<grid, kBlock, 0, st>>>(a, hn, first);
           last = true;
@@ -1075,8 +1094,15 @@ int pm_nlcc(pm_ctx* c, int pl, int mode, int* pattern_found, int* token_source_d
     if (!overflow) {
       n_matches = matches_here;
       // several ranks: what must fit is the fullest inbox region of any hop (tokens arrive undeduplicated)
-      c->pool_seen[pl] = std::max<uint64_t>(c->pool_seen[pl], multi ? (uint64_t)c->h_cnt->peak_out : (uint64_t)c->h_cnt->pool_n);
-      c->keys_seen[pl] = std::max<uint64_t>(c->keys_seen[pl], (uint64_t)c->h_cnt->pool_n + c->h_cnt->ce_n);
+      uint64_t peak = multi ? (uint64_t)c->h_cnt->peak_out : (uint64_t)c->h_cnt->pool_n;
+      uint64_t keys = (uint64_t)c->h_cnt->pool_n + c->h_cnt->ce_n;
+      if (multi)  // the same maxima on every rank (see the sizing above)
+        for (int g = 0; g < c->n_ranks; ++g) {
+          peak = std::max<uint64_t>(peak, c->h_step[g].peak);
+          keys = std::max<uint64_t>(keys, c->h_step[g].accepted + c->h_step[g].ce_n);
+        }
+      c->pool_seen[pl] = std::max<uint64_t>(c->pool_seen[pl], peak);
+      c->keys_seen[pl] = std::max<uint64_t>(c->keys_seen[pl], keys);
       c->pool_cache[c->pat_key] = c->pool_seen;
       c->keys_cache[c->pat_key] = c->keys_seen;
       break;

@@ -34,6 +34,12 @@ struct PatConst {
   uint8_t min_opt[16]; // vertex_min_optional_edge_count (0: no requirement)
   int approx;          // approximate local constraint (approximate_pattern_matching/local_constraint_checking.hpp)
   uint32_t never;      // bit p: the minimum optional edge count of p exceeds its optional edges (p can never stay)
+  // typed slot -> compact id table (one rank, every label class has at most two template vertices): the T_state a
+  // survivor ends the first superstep with is one of at most three subsets of its class — tsub[class][1..3], [0] = 0
+  // ("no survivor") — and its 2-bit number rides in the table next to the compact id, so the second superstep needs
+  // ONE gather per kept neighbour (k_lcc_first_fused, k_lcc_scan<XLATE> typed) instead of a table and a mask gather
+  uint16_t tsub[17][4];
+  int typed;           // every class has at most two template vertices: the typed table can be used
   uint16_t LMc[17];    // class -> bitmask of template vertices carrying that label; [16] = 0
   uint64_t clabel[16]; // class -> label value
   int ncls;
@@ -183,6 +189,8 @@ struct pm_ctx {
   uint32_t* fw = nullptr;   // [Vs / 16] per 16 slots: survivors before them in their tile << 16 | survivor bits (replicated)
   uint32_t* tb = nullptr;   // [tiles] compact id of every 4096-slot tile's first survivor (replicated)
   uint2* fwx = nullptr;     // [Vs / 16] {compact id of the word's first survivor, survivor bits}: what cid_of_slot reads
+  bool typed = false;       // fwx[w].y holds 2-bit T_state numbers (0 = no survivor) instead of survivor bits
+  bool fused01 = false;     // the current pattern's first LCC call runs supersteps 0 and 1 in one pass
   uint32_t cid_off[PM_MAX_RANKS + 1] = {0};  // host copy of the compact id ranges
   uint8_t* cls = nullptr;   // [V] label class (index into the template's distinct labels, PM_NOCLASS = none)
   uint4* fr[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // frontier entry lists [buffer][main, big rows]

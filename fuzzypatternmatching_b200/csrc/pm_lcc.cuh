@@ -129,6 +129,8 @@ struct LccArgs {
   const uint2* fwx;        // slot -> compact id, per 16 slots: {cid of the word's first survivor, survivor bits}
   const uint32_t* rowc;    // [n_c + 1] row start (sectors) in the DENSE working adjacency, by local compact id
   uint32_t col_shift;      // packed labels: a col0 slot is (label << col_shift) | id
+  int typed;               // fwx[w].y holds 2-bit T_state numbers per slot (see PatConst::tsub) instead of survivor bits
+  const uint8_t* clsc;     // label class by compact id
 };
 
 // frontier entry: x = compact id, y = row start in sectors (PM_TOMB: the row is in the big-row list),
@@ -352,6 +354,15 @@ __device__ __forceinline__ uint32_t cid_of_slot(const uint2* __restrict__ fwx, u
   return w.x + __popc(w.y & ((1u << b) - 1u));
 }
 
+// typed table: {cid of the word's first survivor, 2-bit T_state numbers of its 16 slots}; returns the number t of slot
+// u (0: no survivor) and its compact id
+__device__ __forceinline__ uint32_t typed_lookup(const uint2 w, uint32_t u, uint32_t& cid) {
+  const uint32_t j2 = (u & 15u) * 2u;
+  const uint32_t nz = (w.y | (w.y >> 1)) & 0x55555555u;  // one bit per survivor
+  cid = w.x + __popc(nz & ((1u << j2) - 1u));
+  return (w.y >> j2) & 3u;
+}
+
 // n_slots: every slot of every rank (replicated per-cid state); [own_lo, own_hi): this rank's slots, which also
 // get their row start and frontier entry.  deg / rowblk are indexed by slot - own_lo.
 template <bool SMALL>
@@ -363,7 +374,8 @@ __global__ void __launch_bounds__(kBlock) k_init_assign(const uint8_t* __restric
                                                          uint32_t* __restrict__ vid, uint32_t* __restrict__ adeg,
                                                          uint32_t* __restrict__ rowc, uint2* __restrict__ fwx,
                                                          const unsigned long long* __restrict__ sig,
-                                                         uint4* fr_main, uint4* fr_big, DevCounters* cnt, int buf) {
+                                                         uint4* fr_main, uint4* fr_big, DevCounters* cnt, int buf,
+                                                         int typed) {
   __shared__ uint8_t s_cl[64];
   __shared__ uint16_t s_lm[17];
   if (threadIdx.x < 64) s_cl[threadIdx.x] = c_pat.cls_of_label[threadIdx.x];
@@ -386,7 +398,8 @@ __global__ void __launch_bounds__(kBlock) k_init_assign(const uint8_t* __restric
       const uint32_t w = fw[wi];
       bits = w & 0xFFFFu;
       cid0 = tb[wi >> 8] + (w >> 16);
-      fwx[wi] = make_uint2(cid0, bits);  // the table the renaming scan reads (cid_of_slot)
+      // the table the renaming scan reads (cid_of_slot); typed: the survivors OR their T_state numbers in below
+      fwx[wi] = make_uint2(cid0, typed ? 0u : bits);
     }
     const uint32_t cnt_w = __popc(bits);
     uint32_t incl = cnt_w;
@@ -426,6 +439,12 @@ __global__ void __launch_bounds__(kBlock) k_init_assign(const uint8_t* __restric
             if (q < c_pat.ncls && c_pat.clabel[q] < 64ull && ((uint32_t)c_pat.LMc[q] & NBv) && ((sg >> c_pat.clabel[q]) & 1ull))
               heard |= c_pat.LMc[q];
           tw = cover_of(lm, heard);
+        }
+        if (typed) {  // T_state number of this vertex: 2 bits at its place in the word's entry
+          uint32_t t = 1;
+          if (tw == (uint32_t)c_pat.tsub[c][2]) t = 2;
+          if (tw == (uint32_t)c_pat.tsub[c][3]) t = 3;
+          atomicOr(&fwx[slot >> 4].y, t << ((slot & 15u) * 2u));
         }
         if (d <= PM_MID_MAX) {
           fr_main[lcid] = make_uint4(cid, rb, d, tw);
@@ -497,8 +516,10 @@ __global__ void __launch_bounds__(kBlock, 4) k_lcc_scan(LccArgs a, uint4* __rest
   __shared__ uint32_t s_drow[FIRST ? kBlock / 32 : 1][32];  // FIRST: row start (sectors) in the dense working adjacency
   __shared__ uint32_t s_hrd[HEARD ? kBlock / 32 : 1][32];
   __shared__ uint8_t s_nz[kBlock / 32][32];
+  __shared__ uint16_t s_ts[XLATE ? 256 : 1];  // typed table: (label, T_state number) -> mask
   if (threadIdx.x < 17) s_lm[threadIdx.x] = c_pat.LMc[threadIdx.x];
   if (threadIdx.x < 64) s_lml[threadIdx.x] = c_pat.LMc[c_pat.cls_of_label[threadIdx.x]];
+  if (XLATE) s_ts[threadIdx.x] = c_pat.tsub[c_pat.cls_of_label[threadIdx.x >> 2]][threadIdx.x & 3];
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const uint32_t lt = lanemask_lt();
@@ -506,7 +527,8 @@ __global__ void __launch_bounds__(kBlock, 4) k_lcc_scan(LccArgs a, uint4* __rest
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
   const uint32_t* __restrict__ src = FIRST ? a.col0 : a.colw;
-  const uint32_t idmask = STREAM == 2 ? (1u << a.col_shift) - 1u : 0xFFFFFFFFu;
+  // the rows the renaming scan reads still carry the packed labels of the first scan's slots
+  const uint32_t xmask = a.col_shift ? (1u << a.col_shift) - 1u : PM_IDMASK;
   unsigned long long scanned = 0, verts = 0;
   for (uint32_t base = warp * 32; base < n; base += nwarps * 32) {
     const uint32_t idx = base + lane;
@@ -593,15 +615,23 @@ __global__ void __launch_bounds__(kBlock, 4) k_lcc_scan(LccArgs a, uint4* __rest
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const bool act = j0 + k < rd;
-          wr[k] = STREAM == 2 ? u[k] & idmask : u[k] & PM_IDMASK;
+          wr[k] = STREAM == 2 ? u[k] : u[k] & PM_IDMASK;  // packed: the label stays in the slot for the renaming scan
           uint32_t m = 0;
           bool valid = false;
           if (FIRST && STREAM) {
             const uint32_t lab = STREAM == 2 ? (u[k] >> a.col_shift) & 63u : (l4 >> (8 * k)) & 63u;
             valid = act && ((rVL >> lab) & 1ull);
             if (HEARD) m = s_lml[lab];
+          } else if (act && XLATE && a.typed) {
+            // one gather: compact id and T_state number of the neighbour together; its label rides in the slot
+            const uint32_t id = u[k] & xmask;
+            const uint32_t t = typed_lookup(a.fwx[id >> 4], id, wr[k]);
+            m = s_ts[((u[k] >> a.col_shift) & 63u) * 4u + t];
+            if (xlate_only) m = t ? 0xFFFFu : 0u;
+            if (!t) wr[k] = PM_SENTINEL;
+            valid = xlate_only ? m != 0u : (m & rNB) != 0u;
           } else if (act) {
-            if (XLATE) wr[k] = cid_of_slot(a.fwx, wr[k]);
+            if (XLATE) wr[k] = cid_of_slot(a.fwx, u[k] & xmask);
             if (FIRST) m = s_lm[a.cls[wr[k]]];
             else if (!XLATE || wr[k] != PM_SENTINEL) m = xlate_only ? 0xFFFFu : (uint32_t)a.S[wr[k]];
             valid = xlate_only ? m != 0u : (m & rNB) != 0u;
@@ -706,7 +736,7 @@ __global__ void __launch_bounds__(kBlock, 3) k_lcc_first_packed(LccArgs a, uint4
   const uint32_t n = *n_ptr;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-  const uint32_t shift = a.col_shift, idmask = (1u << shift) - 1u;
+  const uint32_t shift = a.col_shift;
   const unsigned long long not_sentinel = ~(1ull << (0xFFFFFFFFu >> shift));
   unsigned long long scanned = 0, verts = 0;
   for (uint32_t base = warp * 32; base < n; base += nwarps * 32) {
@@ -780,7 +810,7 @@ __global__ void __launch_bounds__(kBlock, 3) k_lcc_first_packed(LccArgs a, uint4
         uint32_t* __restrict__ p = a.colw + (uint64_t)s_rowp[wid][r].w * 8 + rout + off;
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          if (keep[k]) *p++ = u[k] & idmask;
+          if (keep[k]) *p++ = u[k];  // label and id: the renaming scan strips the label
         const bool in_batch = g0 + lane < C;
         const bool last = in_batch && (lane == 31u || ((H >> (lane + 1u)) & 1u) || g0 + lane + 1u == C);
         __syncwarp();  // every lane has read its row's running count
@@ -809,6 +839,179 @@ __global__ void __launch_bounds__(kBlock, 3) k_lcc_first_packed(LccArgs a, uint4
   }
 }
 
+// The same scan carrying the SECOND superstep along (one rank, no big rows; typed slot table, see k_init_assign).
+// After the first superstep T_arr(u) of every survivor u equals the T_state the signature filter gave it, so the second
+// superstep's test of a kept neighbour — T_arr(u) & NB(T_arr(v)) != 0 (ee.hpp:673-722) — needs one 8-byte gather per
+// LABEL-VALID slot: compact id and mask number of u together.  The row written is E_v after the second superstep, in
+// compact ids; heard(v) and T_state(v) of the second superstep come out of the same pass.  This replaces the first
+// scan, its commit and the renaming scan (two dependent gathers per slot) of the unfused path.  Row counts: the first
+// superstep's (vertices = survivors, edges = label-valid slots) are accumulated here, the second's by the commit.
+__global__ void __launch_bounds__(kBlock, 3) k_lcc_first_fused(LccArgs a, uint4* __restrict__ list,
+                                                               const uint32_t* __restrict__ n_ptr, RowStat* __restrict__ row1) {
+  // per warp, the 32 rows of the batch in flight: {source row (sectors), sectors, first sector of the batch, dense row}
+  __shared__ uint4 s_rowp[kBlock / 32][32];
+  __shared__ unsigned long long s_vl[kBlock / 32][32];
+  __shared__ uint32_t s_rout[kBlock / 32][32];
+  __shared__ uint8_t s_nz[kBlock / 32][32];
+  __shared__ uint32_t s_nb1[kBlock / 32][32];  // NB(T_arr(v)) of the second superstep
+  __shared__ uint32_t s_hrd[kBlock / 32][32];  // masks heard in the second superstep
+  __shared__ uint16_t s_ts[256], s_lm[17];  // (label, T_state number) -> mask; class -> labelmask
+  s_ts[threadIdx.x] = c_pat.tsub[c_pat.cls_of_label[threadIdx.x >> 2]][threadIdx.x & 3];
+  if (threadIdx.x < 17) s_lm[threadIdx.x] = c_pat.LMc[threadIdx.x];
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint32_t lt = lanemask_lt();
+  const uint32_t le = lt | (1u << lane);
+  const uint32_t n = *n_ptr;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t shift = a.col_shift, idmask = (1u << shift) - 1u;
+  const unsigned long long not_sentinel = ~(1ull << (0xFFFFFFFFu >> shift));
+  unsigned long long scanned = 0, verts = 0, kept0 = 0;
+  for (uint32_t base = warp * 32; base < n; base += nwarps * 32) {
+    const uint32_t idx = base + lane;
+    const bool has = idx < n;
+    uint4 e = make_uint4(0, 0, 0, 0);
+    uint32_t Tv = 0;
+    bool live = false;
+    if (has) {
+      e = list[idx];
+      live = e.y != PM_TOMB;
+      if (live) Tv = s_lm[a.clsc[e.x]];  // T_arr of the first superstep: the labelmask (ee.hpp:541-546)
+    }
+    const uint32_t d = Tv ? e.z : 0u;
+    uint32_t drow = e.y, out = 0, heard = 0;
+    if (has && live) drow = a.rowc[e.x - a.base];
+    const unsigned long long VL = valid_labels(nb_of(Tv)) & not_sentinel;
+    const uint32_t nch = (d + 7u) >> 3;
+    uint32_t cum = nch;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, cum, o);
+      if (lane >= (uint32_t)o) cum += t;
+    }
+    const uint32_t C = __shfl_sync(0xffffffffu, cum, 31);  // sectors of this batch
+    if (C) {
+      const uint32_t first = cum - nch;
+      const uint32_t longrows = __ballot_sync(0xffffffffu, nch != 0u);
+      __syncwarp();
+      s_rowp[wid][lane] = make_uint4(e.y, nch, first, drow);
+      s_vl[wid][lane] = VL;
+      s_rout[wid][lane] = 0u;
+      s_nb1[wid][lane] = nb_of(e.w);  // e.w: T_state after the first superstep = T_arr of the second
+      s_hrd[wid][lane] = 0u;
+      if (nch) s_nz[wid][__popc(longrows & lt)] = (uint8_t)lane;
+      __syncwarp();
+      // one pass ahead: the row a lane's sector belongs to and the sector itself
+      uint32_t rN = 0, hN = 0;
+      uint4 qa = make_uint4(PM_SENTINEL, PM_SENTINEL, PM_SENTINEL, PM_SENTINEL), qb = qa;
+      auto fetch = [&](uint32_t g0) {
+        const uint32_t hb = (nch && first >= g0 && first < g0 + 32u) ? 1u << (first - g0) : 0u;
+        hN = __reduce_or_sync(0xffffffffu, hb);
+        const uint32_t before = __popc(__ballot_sync(0xffffffffu, nch && first < g0));
+        rN = s_nz[wid][before + __popc(hN & le) - 1u];
+        const uint4 rp = s_rowp[wid][rN];
+        const uint32_t g = g0 + lane;
+        qa = make_uint4(PM_SENTINEL, PM_SENTINEL, PM_SENTINEL, PM_SENTINEL);
+        qb = qa;
+        if (g < C) {
+          const uint4* __restrict__ p = reinterpret_cast<const uint4*>(a.col0 + ((uint64_t)rp.x + (g - rp.z)) * 8);
+          qa = p[0];
+          qb = p[1];
+        }
+      };
+      fetch(0u);
+      for (uint32_t g0 = 0; g0 < C; g0 += 32u) {
+        const uint32_t r = rN, H = hN;
+        const uint4 q0 = qa, q1 = qb;
+        if (g0 + 32u < C) fetch(g0 + 32u);  // the next pass is on its way while this one is worked on
+        const unsigned long long rVL = s_vl[wid][r];
+        const uint32_t rNB = s_nb1[wid][r];
+        const uint32_t u[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+        uint32_t cidv[8], nk = 0, hv = 0, n0 = 0;
+        // first superstep: label test (a sentinel's label field is never valid); second: the kept neighbour's entry
+        // of the typed table — every gather of the pass is issued before the first one is used
+        uint2 w[8];
+        uint32_t k0 = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t lab = u[k] >> shift;
+          if ((uint32_t)(rVL >> lab) & 1u) {
+            k0 |= 1u << k;
+            w[k] = a.fwx[(u[k] & idmask) >> 4];
+          }
+        }
+        n0 = __popc(k0);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          cidv[k] = PM_SENTINEL;
+          if ((k0 >> k) & 1u) {
+            uint32_t cid;
+            const uint32_t t = typed_lookup(w[k], u[k] & idmask, cid);
+            const uint32_t m = s_ts[(u[k] >> shift) * 4u + t];  // 0: u did not survive the first superstep
+            if (m & rNB) {
+              hv |= m;
+              cidv[k] = cid;
+              ++nk;
+            }
+          }
+        }
+        kept0 += n0;
+        uint32_t below, total;
+        warp_prefix8(nk, lt, below, total);
+        const uint32_t hl = 31u - __clz((H | 1u) & le);  // first lane of my row's segment in this pass
+        const uint32_t off = below - __shfl_sync(0xffffffffu, below, hl);
+        const uint32_t rout = s_rout[wid][r];
+        uint32_t* __restrict__ p = a.colw + (uint64_t)s_rowp[wid][r].w * 8 + rout + off;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (cidv[k] != PM_SENTINEL) *p++ = cidv[k];
+        const bool in_batch = g0 + lane < C;
+        const bool last = in_batch && (lane == 31u || ((H >> (lane + 1u)) & 1u) || g0 + lane + 1u == C);
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {  // OR over the lanes of my segment
+          const uint32_t t = __shfl_up_sync(0xffffffffu, hv, o);
+          if (lane >= (uint32_t)o + hl) hv |= t;
+        }
+        __syncwarp();  // every lane has read its row's running count
+        if (last) {
+          s_rout[wid][r] = rout + off + nk;
+          s_hrd[wid][r] |= hv;
+        }
+        __syncwarp();
+      }
+      if (nch) { out = s_rout[wid][lane]; heard = s_hrd[wid][lane]; }
+    }
+    if (has && live) {
+      scanned += d;
+      verts += Tv != 0u;
+      // second superstep: T_state &= { p : N(p) heard } (ee.hpp:901-939); an empty one leaves the map (:941-946)
+      const uint32_t ts = Tv ? cover_of(e.w, heard) : 0u;
+      if (Tv && ts == 0u) a.cnt->nf = 1u;
+      e.y = drow;
+      e.z = out;
+      e.w = ts;
+      list[idx] = e;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    scanned += __shfl_xor_sync(0xffffffffu, scanned, o);
+    verts += __shfl_xor_sync(0xffffffffu, verts, o);
+    kept0 += __shfl_xor_sync(0xffffffffu, kept0, o);
+  }
+  if (lane == 0 && verts) {
+    atomicAdd(&a.row->scanned[0], scanned);
+    atomicAdd(&a.row->verts[0], verts);
+    // the first superstep's row (ee.hpp:1112-1138): every survivor is in the map, E_v = the label-valid neighbours
+    atomicAdd(&a.row->nv, verts);
+    atomicAdd(&a.row->ne, kept0);
+    // the second superstep walked those label-valid slots
+    atomicAdd(&row1->scanned[0], kept0);
+    atomicAdd(&row1->verts[0], verts);
+  }
+}
+
 // one CTA per high-degree vertex ("delegates across warps and CTAs")
 template <bool FIRST, int STREAM, bool XLATE, bool HEARD>
 __global__ void __launch_bounds__(1024) k_lcc_scan_big(LccArgs a, uint4* __restrict__ list,
@@ -818,6 +1021,9 @@ __global__ void __launch_bounds__(1024) k_lcc_scan_big(LccArgs a, uint4* __restr
   if (threadIdx.x < 64) s_lml[threadIdx.x] = c_pat.LMc[c_pat.cls_of_label[threadIdx.x]];
   __shared__ uint32_t s_wcnt[32];
   __shared__ uint32_t s_heard[32];
+  __shared__ uint16_t s_ts[XLATE ? 256 : 1];  // typed table: (label, T_state number) -> mask
+  if (XLATE && threadIdx.x < 256) s_ts[threadIdx.x] = c_pat.tsub[c_pat.cls_of_label[threadIdx.x >> 2]][threadIdx.x & 3];
+  const uint32_t xmask = a.col_shift ? (1u << a.col_shift) - 1u : PM_IDMASK;
   if (threadIdx.x < 17) s_lm[threadIdx.x] = c_pat.LMc[threadIdx.x];
   const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const uint32_t lt = lanemask_lt();
@@ -851,15 +1057,22 @@ __global__ void __launch_bounds__(1024) k_lcc_scan_big(LccArgs a, uint4* __restr
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const bool act = j0 + k < d;
-        wr[k] = STREAM == 2 ? u[k] & ((1u << a.col_shift) - 1u) : u[k] & PM_IDMASK;
+        wr[k] = STREAM == 2 ? u[k] : u[k] & PM_IDMASK;  // packed: the label stays in the slot for the renaming scan
         uint32_t m = 0;
         bool valid = false;
         if (FIRST && STREAM) {
           const uint32_t lab = STREAM == 2 ? (u[k] >> a.col_shift) & 63u : (l4 >> (8 * k)) & 63u;
           valid = act && ((VL >> lab) & 1ull);
           if (HEARD) m = s_lml[lab];
+        } else if (act && XLATE && a.typed) {
+          const uint32_t id = u[k] & xmask;
+          const uint32_t t = typed_lookup(a.fwx[id >> 4], id, wr[k]);
+          m = s_ts[((u[k] >> a.col_shift) & 63u) * 4u + t];
+          if (xlate_only) m = t ? 0xFFFFu : 0u;
+          if (!t) wr[k] = PM_SENTINEL;
+          valid = xlate_only ? m != 0u : (m & NBv) != 0u;
         } else if (act) {
-          if (XLATE) wr[k] = cid_of_slot(a.fwx, wr[k]);
+          if (XLATE) wr[k] = cid_of_slot(a.fwx, u[k] & xmask);
           if (FIRST) m = s_lm[a.cls[wr[k]]];
           else if (!XLATE || wr[k] != PM_SENTINEL) m = xlate_only ? 0xFFFFu : (uint32_t)a.S[wr[k]];
           valid = xlate_only ? m != 0u : (m & NBv) != 0u;

@@ -58,6 +58,8 @@ LccArgs lcc_args(pm_ctx* c, int row) {
   a.fwx = c->fwx;
   a.rowc = c->rowc;
   a.col_shift = c->col_shift;
+  a.typed = c->typed ? 1 : 0;
+  a.clsc = c->clsc;
   return a;
 }
 
@@ -527,6 +529,14 @@ int pm_pattern_load_dir(pm_ctx* c, const char* dir) {
     for (int q = 0; q < pc.ncls; ++q)
       if ((pc.LMc[q] & nb) && pc.clabel[q] < 64) pc.rl[k] |= 1ull << pc.clabel[q];
   }
+  // typed slot table: the (at most three) non-empty subsets of every class with one or two template vertices
+  pc.typed = 1;
+  for (int k = 0; k < pc.ncls; ++k) {
+    const uint32_t lm = pc.LMc[k];
+    if (__builtin_popcount(lm) > 2 || pc.clabel[k] >= 64) { pc.typed = 0; continue; }
+    int n = 1;
+    for (uint32_t sub = lm; sub; sub = (sub - 1) & lm) pc.tsub[k][n++] = (uint16_t)sub;
+  }
   c->pat = p;
   c->pc = pc;
   c->has_pattern = true;
@@ -641,6 +651,10 @@ int state_reset(pm_ctx* c, bool need_colw) {
     // a single superstep per LCC call: no second scan could drop the neighbours the filter removed, so
     // the filter stays off and every label-matching vertex gets a compact id
     const bool use_sig = small && c->pat.diameter >= 2;
+    // one rank, packed labels: the slot -> compact id table also carries every survivor's T_state number (see
+    // PatConst::tsub), and supersteps 0 and 1 of the first LCC call can run as ONE pass (k_lcc_first_fused)
+    c->typed = use_sig && !multi && c->col_shift != 0 && c->pc.typed && !getenv("PM_NO_TYPED");
+    c->fused01 = c->typed && need_colw && getenv("PM_FUSE") != nullptr;
     if (small)
       k_init_flags<true><<<grid, kBlock, 0, c->stream>>>(c->lab8 + base, nullptr, c->deg, c->sig, NL, nullptr, fw_me, tb_me, c->cnt, use_sig ? 1 : 0);
     else
@@ -675,11 +689,12 @@ int state_reset(pm_ctx* c, bool need_colw) {
     if (small)
       k_init_assign<true><<<grid, kBlock, 0, c->stream>>>(c->lab8, nullptr, c->deg, c->rowblk, c->fw, c->tb, multi ? Vs : NL,
                                                           (uint32_t)base, (uint32_t)(base + NL), c->S, c->clsc, c->vid, c->adeg, c->rowc, c->fwx,
-                                                          use_sig ? c->sig : nullptr, c->fr[0][0], c->fr[0][1], c->cnt, 0);
+                                                          use_sig ? c->sig : nullptr, c->fr[0][0], c->fr[0][1], c->cnt, 0,
+                                                          c->typed ? 1 : 0);
     else
       k_init_assign<false><<<grid, kBlock, 0, c->stream>>>(nullptr, c->cls, c->deg, c->rowblk, c->fw, c->tb, multi ? Vs : NL,
                                                            (uint32_t)base, (uint32_t)(base + NL), c->S, c->clsc, c->vid, c->adeg, c->rowc, c->fwx,
-                                                           nullptr, c->fr[0][0], c->fr[0][1], c->cnt, 0);
+                                                           nullptr, c->fr[0][0], c->fr[0][1], c->cnt, 0, 0);
     PM_LAUNCH_CHECK(c);
     // the DENSE working adjacency: the row of local compact id i starts at the exclusive prefix of the survivors'
     // degrees (in 32-byte sectors, so rows stay sector aligned) — a few hundred million slots instead of the
@@ -722,6 +737,7 @@ int state_reset(pm_ctx* c, bool need_colw) {
       }
     }
     for (int b = 0; b < 2; ++b) c->bin_live[b] = c->h_cnt->fr_n[0][b] != 0;
+    if (c->bin_live[1]) c->fused01 = false;  // rows above PM_MID_MAX slots take the CTA-per-row kernels: unfused path
     c->init_ms = 0;
     c->init_candidates = c->h_cnt->filtered_init;
     if (c->filter_done) PM_CUDA(c, cudaEventElapsedTime(&c->init_ms, c->kev[3][0], c->kev[3][1]));
@@ -770,7 +786,18 @@ int pm_lcc(pm_ctx* c, int init_step, int* not_finished, pm_counts_t* counts_out)
     const int cls_main = first ? 0 : xlate ? 4 : 1;
     cudaEvent_t* ev = &c->kev2[(size_t)k * 4];
     PM_CUDA(c, cudaEventRecord(ev[0], st));
-    if (c->bin_live[0]) {
+    const bool fused = init_step && c->fused01;  // supersteps 0 and 1 in one pass: k == 0 scans, k == 1 only commits
+    if (fused && k == 0) {
+      k_lcc_first_fused<<<148 * 6, kBlock, 0, st>>>(a, c->fr[cur][0], &c->cnt->fr_n[cur][0], c->rowstat + 1);
+      PM_LAUNCH_CHECK(c);
+      PM_CUDA(c, cudaEventRecord(ev[1], st));
+      PM_CUDA(c, cudaEventRecord(ev[2], st));
+      c->kev2_cls[k] = 0;
+      continue;
+    }
+    if (fused && k == 1) {
+      PM_CUDA(c, cudaEventRecord(ev[1], st));
+    } else if (c->bin_live[0]) {
       uint4* l = c->fr[cur][0];
       const uint32_t* np = &c->cnt->fr_n[cur][0];
       if (first && ts_known && packed && !getenv("PM_GENERIC_FIRST")) k_lcc_first_packed<<<148 * 6, kBlock, 0, st>>>(a, l, np);
@@ -783,8 +810,8 @@ int pm_lcc(pm_ctx* c, int init_step, int* not_finished, pm_counts_t* counts_out)
       else k_lcc_scan<false, 0, false, true><<<grid, kBlock, 0, st>>>(a, l, np, 0);
       PM_LAUNCH_CHECK(c);
     }
-    PM_CUDA(c, cudaEventRecord(ev[1], st));
-    if (c->bin_live[1]) {
+    if (!(fused && k == 1)) PM_CUDA(c, cudaEventRecord(ev[1], st));
+    if (c->bin_live[1] && !(fused && k == 1)) {
       uint4* l = c->fr[cur][1];
       const uint32_t* np = &c->cnt->fr_n[cur][1];
       if (first && ts_known && packed) k_lcc_scan_big<true, 2, false, false><<<148, 1024, 0, st>>>(a, l, np, 0);
@@ -852,7 +879,10 @@ int pm_lcc(pm_ctx* c, int init_step, int* not_finished, pm_counts_t* counts_out)
       const cudaEvent_t* ev = &c->kev2[(size_t)k * 4];
       PM_CUDA(c, cudaEventElapsedTime(&kms, ev[0], ev[1]));
       pm_kernel_stats_t& ks = c->kstat[c->kev2_cls[k]];
-      if (rs.verts[0]) { ks.launches++; ks.ms += kms; ks.slots += rs.scanned[0]; ks.vertices += rs.verts[0]; }
+      if (init_step && c->fused01 && k == 1) {  // walked inside the fused first scan: its slots, no launch of its own
+        c->kstat[0].slots += rs.scanned[0];
+        c->kstat[0].vertices += rs.verts[0];
+      } else if (rs.verts[0]) { ks.launches++; ks.ms += kms; ks.slots += rs.scanned[0]; ks.vertices += rs.verts[0]; }
       PM_CUDA(c, cudaEventElapsedTime(&kms, ev[1], ev[2]));
       if (rs.verts[2]) { c->kstat[2].launches++; c->kstat[2].ms += kms; c->kstat[2].slots += rs.scanned[2]; c->kstat[2].vertices += rs.verts[2]; }
     }

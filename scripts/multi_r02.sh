@@ -10,6 +10,6 @@ PM_DEBUG_HOPS=${PM_DEBUG_HOPS:-} timeout 900 python -m torch.distributed.run --n
 echo "explore rc=$?"; grep -v "^\*\|OMP_NUM" gpurun_out/r02_multi_explore_n${N}_$tag.log | tail -70
 fi
 if [ -n "$4" ]; then
-timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps $4 --warmup 3 > gpurun_out/r02_bench_n${N}_$tag.log 2> gpurun_out/r02_bench_n${N}_$tag.err
+PM_DEBUG_BUILD=1 timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps $4 --warmup 3 > gpurun_out/r02_bench_n${N}_$tag.log 2> gpurun_out/r02_bench_n${N}_$tag.err
 echo "bench rc=$?"; tail -c 2500 gpurun_out/r02_bench_n${N}_$tag.log; tail -5 gpurun_out/r02_bench_n${N}_$tag.err
 fi

@@ -610,3 +610,28 @@ def test_approximate_pattern_on_rmat(oracle, eng):
         for k in ("rows", "iterations", "vertices", "edges"):
             assert got[k] == want[k], (min_optional, k)
         assert min_optional == {2: 1} or len(want["vertices"]) > 0
+
+
+def test_hub_class_template_on_rmat_scale20(oracle, eng):
+    """A template over hub classes (degree labels 12, 14, 16: rows of 2^11 .. 2^16 slots) on R-MAT scale 20: the
+    CTA-per-row kernels (rows above 4096 slots) carry the first scan, the renaming scan and the later scans; rows, final
+    sets and the number of enumerated walks against the oracle."""
+    from fuzzypatternmatching_b200 import patterns as PT
+    g = oracle.Graph.rmat(20, 4)
+    labels = g.labels_degree_log2()
+    eng.graph_rmat(20, 4)
+    eng.labels_degree_log2()
+    assert eng.graph_info()["max_degree"] > 4096
+    spec = PT.triangle(12, 14, 16)
+    d = cases.pattern_dir(spec)
+    ref = oracle.Run(g, labels, oracle.Pattern(d), tds_from_pl=1, keep_subgraphs=False)
+    assert not ref.hazards[:5].any()
+    eng.pattern_load_dir(d)
+    s = eng.run(tds_from_pl=1, keep_subgraphs=False)
+    assert eng.rows() == ref.rows and int(s["iterations"]) == ref.iterations
+    v, t = eng.active_vertices()
+    rv, rt = ref.active_vertices()
+    assert np.array_equal(v, rv) and np.array_equal(t, rt) and len(rv) > 100
+    assert np.array_equal(eng.active_edges(), ref.active_edges)
+    assert int(s["path_count"]) == ref.path_count > 0
+    assert eng.kernel_stats(2)["launches"] > 0  # the CTA-per-row class ran

@@ -69,7 +69,7 @@ struct DevCounters {
   uint32_t n_src;               // NLCC: number of sources
   uint32_t nf_init;             // the fused init filter removed a vertex that had entered the map
   uint32_t match_drop;          // TDS: a completed walk did not fit the match list
-  uint32_t pad1;
+  uint32_t ticket;              // k_lcc_commit: blocks finished (the last one re-arms the frontier counters it consumed)
   unsigned long long pool_n;    // NLCC: tokens in the pool
   unsigned long long matches;   // TDS: completed walks
   unsigned long long fanout;    // NLCC: adjacency slots walked by tokens
@@ -239,6 +239,7 @@ struct pm_ctx {
   // CUDA-event timing of the first-superstep scan kernels (the dominant kernels), per bin
   std::vector<cudaEvent_t> kev2;   // per superstep: before main scan, after it, after the big-row scan
   std::vector<int> kev2_cls;       // per superstep: kernel class of the main scan (0 first, 1 later)
+  std::vector<int> kev2_big;       // per superstep: the CTA-per-row scan ran (its end event was recorded)
   cudaEvent_t kev[4][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
   pm_kernel_stats_t kstat[5] = {};  // [3]: the first-superstep signature filter, [4]: the renaming scan
 };

@@ -1184,6 +1184,16 @@ __global__ void __launch_bounds__(kBlock) k_lcc_commit(LccArgs a, const uint4* _
     atomicAdd(&a.row->nv, nv);
     atomicAdd(&a.row->ne, ne);
   }
+  // the last block to finish re-arms the counters of the list just consumed: they are the NEXT commit's output
+  // counters (every block read them on entry; no other kernel of the stream reads them before that commit)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&a.cnt->ticket, 1u) == gridDim.x - 1u) {
+      a.cnt->fr_n[cur][0] = a.cnt->fr_n[cur][1] = a.cnt->fr_n[cur][2] = a.cnt->fr_n[cur][3] = 0u;
+      a.cnt->ticket = 0u;
+    }
+  }
 }
 
 // counts after an NLCC constraint (beta.cpp:1094-1120): vertices still in the map

@@ -630,6 +630,7 @@ int state_reset(pm_ctx* c, bool need_colw) {
     c->kev2.push_back(e);
   }
   c->kev2_cls.assign(nrow, 1);
+  c->kev2_big.assign(nrow, 0);
   if (g_const_owner[c->device & 63] && g_const_owner[c->device & 63] != c) {
     PM_CUDA(c, cudaDeviceSynchronize());  // another context of this device may still be running on the old tables
     if ((rc = comm_upload_peers(c))) return rc;
@@ -777,22 +778,20 @@ int pm_lcc(pm_ctx* c, int init_step, int* not_finished, pm_counts_t* counts_out)
   for (int k = 0; k < D; ++k) {  // fixed superstep count (ee.hpp:1069)
     const bool first = init_step && k == 0;
     const bool xlate = init_step && k == 1;  // rows still hold slots: this scan renames them to compact ids
-    PM_CUDA(c, cudaEventRecord(c->events[k], st));
-    PM_CUDA(c, cudaMemsetAsync(&c->cnt->fr_n[c->cur ^ 1][0], 0, 4 * sizeof(uint32_t), st));
+    PM_CUDA(c, cudaEventRecord(c->events[k], st));  // also the start of the main scan for the kernel-class timing
     LccArgs a = lcc_args(c, k);
     const int cur = c->cur, nxt = cur ^ 1;
     // kernel classes timed with CUDA events on this stream: 0 = first-superstep scan of the main list,
     // 1 = later scans of the main list, 2 = CTA-per-row scans, 4 = the renaming (XLATE) scan
     const int cls_main = first ? 0 : xlate ? 4 : 1;
     cudaEvent_t* ev = &c->kev2[(size_t)k * 4];
-    PM_CUDA(c, cudaEventRecord(ev[0], st));
     const bool fused = init_step && c->fused01;  // supersteps 0 and 1 in one pass: k == 0 scans, k == 1 only commits
     if (fused && k == 0) {
       k_lcc_first_fused<<<148 * 6, kBlock, 0, st>>>(a, c->fr[cur][0], &c->cnt->fr_n[cur][0], c->rowstat + 1);
       PM_LAUNCH_CHECK(c);
       PM_CUDA(c, cudaEventRecord(ev[1], st));
-      PM_CUDA(c, cudaEventRecord(ev[2], st));
       c->kev2_cls[k] = 0;
+      c->kev2_big[k] = 0;
       continue;
     }
     if (fused && k == 1) {
@@ -823,7 +822,8 @@ int pm_lcc(pm_ctx* c, int init_step, int* not_finished, pm_counts_t* counts_out)
       else k_lcc_scan_big<false, 0, false, true><<<148, 1024, 0, st>>>(a, l, np, 0);
       PM_LAUNCH_CHECK(c);
     }
-    PM_CUDA(c, cudaEventRecord(ev[2], st));
+    c->kev2_big[k] = (c->bin_live[1] && !(fused && k == 1)) ? 1 : 0;
+    if (c->kev2_big[k]) PM_CUDA(c, cudaEventRecord(ev[2], st));
     c->kev2_cls[k] = cls_main;
     k_lcc_commit<<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], c->fr[cur][1], c->fr[nxt][0], c->fr[nxt][1], cur, nxt);
     PM_LAUNCH_CHECK(c);
@@ -877,13 +877,14 @@ int pm_lcc(pm_ctx* c, int init_step, int* not_finished, pm_counts_t* counts_out)
     {
       float kms = 0;
       const cudaEvent_t* ev = &c->kev2[(size_t)k * 4];
-      PM_CUDA(c, cudaEventElapsedTime(&kms, ev[0], ev[1]));
+      PM_CUDA(c, cudaEventElapsedTime(&kms, c->events[k], ev[1]));
       pm_kernel_stats_t& ks = c->kstat[c->kev2_cls[k]];
       if (init_step && c->fused01 && k == 1) {  // walked inside the fused first scan: its slots, no launch of its own
         c->kstat[0].slots += rs.scanned[0];
         c->kstat[0].vertices += rs.verts[0];
       } else if (rs.verts[0]) { ks.launches++; ks.ms += kms; ks.slots += rs.scanned[0]; ks.vertices += rs.verts[0]; }
-      PM_CUDA(c, cudaEventElapsedTime(&kms, ev[1], ev[2]));
+      kms = 0;
+      if (c->kev2_big[k]) PM_CUDA(c, cudaEventElapsedTime(&kms, ev[1], ev[2]));
       if (rs.verts[2]) { c->kstat[2].launches++; c->kstat[2].ms += kms; c->kstat[2].slots += rs.scanned[2]; c->kstat[2].vertices += rs.verts[2]; }
     }
     if (k == 0 && init_step && c->labels_small) {

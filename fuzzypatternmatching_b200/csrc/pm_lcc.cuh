@@ -1012,6 +1012,148 @@ __global__ void __launch_bounds__(kBlock, 3) k_lcc_first_fused(LccArgs a, uint4*
   }
 }
 
+// ---------------------------------------------------------------------------
+// The renaming scan with the typed table (one rank; see PatConst::tsub): second superstep of the first LCC call over
+// the rows the first scan wrote (packed slots).  Same sector-per-lane packing as k_lcc_first_packed; one 8-byte gather
+// per slot gives the neighbour's compact id and T_state number, its label rides in the slot: mask = tsub[label][number].
+// The row is compacted in place (writes land at or before slots already read; the prefetched pass lies behind them).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock, 3) k_lcc_xlate8(LccArgs a, uint4* __restrict__ list,
+                                                          const uint32_t* __restrict__ n_ptr) {
+  __shared__ uint4 s_rowp[kBlock / 32][32];  // {row start (sectors), |E_v|, first sector of the batch, NB(T_arr(v))}
+  __shared__ uint32_t s_rout[kBlock / 32][32];
+  __shared__ uint32_t s_hrd[kBlock / 32][32];
+  __shared__ uint8_t s_nz[kBlock / 32][32];
+  __shared__ uint16_t s_ts[256];  // (label, T_state number) -> mask
+  s_ts[threadIdx.x] = c_pat.tsub[c_pat.cls_of_label[threadIdx.x >> 2]][threadIdx.x & 3];
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint32_t lt = lanemask_lt();
+  const uint32_t le = lt | (1u << lane);
+  const uint32_t n = *n_ptr;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t shift = a.col_shift, idmask = (1u << shift) - 1u;
+  unsigned long long scanned = 0, verts = 0;
+  for (uint32_t base = warp * 32; base < n; base += nwarps * 32) {
+    const uint32_t idx = base + lane;
+    const bool has = idx < n;
+    uint4 e = make_uint4(0, 0, 0, 0);
+    uint32_t Tv = 0;
+    bool live = false;
+    if (has) {
+      e = list[idx];
+      live = e.y != PM_TOMB;
+      if (live) Tv = a.S[e.x];
+    }
+    const uint32_t d = Tv ? e.z : 0u;
+    uint32_t out = 0, heard = 0;
+    const uint32_t nch = (d + 7u) >> 3;
+    uint32_t cum = nch;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, cum, o);
+      if (lane >= (uint32_t)o) cum += t;
+    }
+    const uint32_t C = __shfl_sync(0xffffffffu, cum, 31);  // sectors of this batch
+    if (C) {
+      const uint32_t first = cum - nch;
+      const uint32_t longrows = __ballot_sync(0xffffffffu, nch != 0u);
+      __syncwarp();
+      s_rowp[wid][lane] = make_uint4(e.y, d, first, nb_of(Tv));
+      s_rout[wid][lane] = 0u;
+      s_hrd[wid][lane] = 0u;
+      if (nch) s_nz[wid][__popc(longrows & lt)] = (uint8_t)lane;
+      __syncwarp();
+      uint32_t rN = 0, hN = 0, jN = 0;
+      uint4 qa = make_uint4(0, 0, 0, 0), qb = qa;
+      auto fetch = [&](uint32_t g0) {
+        const uint32_t hb = (nch && first >= g0 && first < g0 + 32u) ? 1u << (first - g0) : 0u;
+        hN = __reduce_or_sync(0xffffffffu, hb);
+        const uint32_t before = __popc(__ballot_sync(0xffffffffu, nch && first < g0));
+        rN = s_nz[wid][before + __popc(hN & le) - 1u];
+        const uint4 rp = s_rowp[wid][rN];
+        const uint32_t g = g0 + lane;
+        jN = (g - rp.z) * 8u;  // first slot of my sector inside its row
+        if (g < C) {
+          const uint4* __restrict__ p = reinterpret_cast<const uint4*>(a.colw + ((uint64_t)rp.x + (g - rp.z)) * 8);
+          qa = p[0];
+          qb = p[1];
+        }
+      };
+      fetch(0u);
+      for (uint32_t g0 = 0; g0 < C; g0 += 32u) {
+        const uint32_t r = rN, H = hN, j0 = jN;
+        const uint4 q0 = qa, q1 = qb;
+        const bool in_batch = g0 + lane < C;
+        if (g0 + 32u < C) fetch(g0 + 32u);  // the next pass is on its way while this one is worked on
+        const uint4 rp = s_rowp[wid][r];
+        const uint32_t rNB = rp.w, rd = in_batch ? rp.y : 0u;
+        const uint32_t u[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+        uint2 w[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (j0 + k < rd) w[k] = a.fwx[(u[k] & idmask) >> 4];  // every gather of the pass before the first use
+        uint32_t cidv[8], nk = 0, hv = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          cidv[k] = PM_SENTINEL;
+          if (j0 + k < rd) {
+            uint32_t cid;
+            const uint32_t t = typed_lookup(w[k], u[k] & idmask, cid);
+            const uint32_t m = s_ts[((u[k] >> shift) & 63u) * 4u + t];  // 0: the neighbour did not survive the first superstep
+            if (m & rNB) {
+              hv |= m;
+              cidv[k] = cid;
+              ++nk;
+            }
+          }
+        }
+        uint32_t below, total;
+        warp_prefix8(nk, lt, below, total);
+        const uint32_t hl = 31u - __clz((H | 1u) & le);  // first lane of my row's segment in this pass
+        const uint32_t off = below - __shfl_sync(0xffffffffu, below, hl);
+        const uint32_t rout = s_rout[wid][r];
+        uint32_t* __restrict__ p = a.colw + (uint64_t)rp.x * 8 + rout + off;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (cidv[k] != PM_SENTINEL) *p++ = cidv[k];
+        const bool last = in_batch && (lane == 31u || ((H >> (lane + 1u)) & 1u) || g0 + lane + 1u == C);
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {  // OR over the lanes of my segment
+          const uint32_t t = __shfl_up_sync(0xffffffffu, hv, o);
+          if (lane >= (uint32_t)o + hl) hv |= t;
+        }
+        __syncwarp();  // every lane has read its row's running count
+        if (last) {
+          s_rout[wid][r] = rout + off + nk;
+          s_hrd[wid][r] |= hv;
+        }
+        __syncwarp();
+      }
+      if (nch) { out = s_rout[wid][lane]; heard = s_hrd[wid][lane]; }
+    }
+    if (has && live) {
+      const uint32_t ts = Tv ? cover_of(e.w, heard) : 0u;   // ee.hpp:901-939
+      if (Tv && ts == 0u) a.cnt->nf = 1u;                    // left the map (:941-946, :968-970)
+      scanned += d;
+      verts += Tv != 0u;
+      e.z = out;
+      e.w = ts;
+      list[idx] = e;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    scanned += __shfl_xor_sync(0xffffffffu, scanned, o);
+    verts += __shfl_xor_sync(0xffffffffu, verts, o);
+  }
+  if (lane == 0 && verts) {
+    atomicAdd(&a.row->scanned[0], scanned);
+    atomicAdd(&a.row->verts[0], verts);
+  }
+}
+
 // one CTA per high-degree vertex ("delegates across warps and CTAs")
 template <bool FIRST, int STREAM, bool XLATE, bool HEARD>
 __global__ void __launch_bounds__(1024) k_lcc_scan_big(LccArgs a, uint4* __restrict__ list,

@@ -805,6 +805,7 @@ int pm_lcc(pm_ctx* c, int init_step, int* not_finished, pm_counts_t* counts_out)
       else if (first && sm0 && packed) k_lcc_scan<true, 2, false, true><<<grid, kBlock, 0, st>>>(a, l, np, 0);
       else if (first && sm0) k_lcc_scan<true, 1, false, true><<<grid, kBlock, 0, st>>>(a, l, np, 0);
       else if (first) k_lcc_scan<true, 0, false, true><<<grid, kBlock, 0, st>>>(a, l, np, 0);
+      else if (xlate && c->typed && getenv("PM_XLATE8")) k_lcc_xlate8<<<148 * 6, kBlock, 0, st>>>(a, l, np);  // measured: no faster
       else if (xlate) k_lcc_scan<false, 0, true, true><<<grid, kBlock, 0, st>>>(a, l, np, 0);
       else k_lcc_scan<false, 0, false, true><<<grid, kBlock, 0, st>>>(a, l, np, 0);
       PM_LAUNCH_CHECK(c);

@@ -32,6 +32,9 @@ WORKLOADS = {
     "cyclic": [("tree", PT.RMAT_LOG2_TREE), ("triangle_678", PT.triangle(6, 7, 8)),
                ("cycle4_5678", PT.cycle4(5, 6, 7, 8)), ("cycle6_chords_456789", PT.cycle6_chords([4, 5, 6, 7, 8, 9]))],
     "tree": [("tree", PT.RMAT_LOG2_TREE)],
+    # hub classes (degree labels 12, 14, 16: rows of 2^11 .. 2^16 slots): the CTA-per-row kernels carry the scans;
+    # cycle checking only (the enumeration walk over hub neighbourhoods is combinatorial)
+    "hubs": [("triangle_hubs_12_14_16", dict(PT.triangle(12, 14, 16), constraints=PT.triangle(12, 14, 16)["constraints"][:1]))],
 }
 
 

@@ -1102,14 +1102,20 @@ int pm_nlcc(pm_ctx* c, int pl, int mode, int* pattern_found, int* token_source_d
         c->step_parity ^= 1;
         if (last) break;
       }
-      if ((rc = sync_counters(c))) return rc;
+      if (walk) {
+        if ((rc = sync_counters(c))) return rc;
+      } else {
+        // no rank has a source (every rank saw the same level-0 message): nothing was walked, nothing to read back
+        c->h_cnt->overflow = c->h_cnt->found = 0;
+        c->h_cnt->pool_n = c->h_cnt->matches = c->h_cnt->fanout = c->h_cnt->peak_out = c->h_cnt->ce_n = 0;
+      }
       if (dbg) {
         fprintf(stderr, "[pm] rank %d pl=%d attempt %d tcap %llu hop kernel/barrier ms:", c->rank, pl, attempt, (unsigned long long)c->tcap);
         for (size_t i = 0; i + 1 < dev.size(); ++i) { float ms = 0; cudaEventElapsedTime(&ms, dev[i], dev[i + 1]); fprintf(stderr, " %.3f", ms); }
         fprintf(stderr, "\n");
         for (auto e : dev) cudaEventDestroy(e);
       }
-      if ((rc = comm_step_fetch(c))) return rc;
+      if (walk && (rc = comm_step_fetch(c))) return rc;
     }
     hi = c->h_cnt->pool_n;
     // the pool / hash set / an inbox region ran out, or more walks completed than the match list holds

@@ -25,6 +25,7 @@
 
 #include "pm_lcc.cuh"
 #include "pm_nlcc.cuh"
+#include "pm_nlcc_multi.cuh"
 
 namespace pm {
 
@@ -38,6 +39,8 @@ struct FzArgs {
   DevCounters* cnt;
   RowStat* row;
   uint32_t idmask;  // id bits of a col0 slot (packed labels ride above them)
+  uint32_t base;    // first slot of this rank: S / lab8 are indexed by slot, rowblk / deg / sig by slot - base
+  int par;          // several ranks: delta inbox of the current step
 };
 
 __device__ __forceinline__ int fz_q0(uint32_t lm) { return __ffs(lm) - 1; }  // first template vertex of the label
@@ -65,7 +68,7 @@ __global__ void __launch_bounds__(kBlock) k_fz_init(FzArgs a, const unsigned lon
       bin[k] = 0;
       val[k] = make_uint4(0, 0, 0, 0);
       if (v < V) {
-        const uint32_t lm = s_lm[s_cl[a.lab8[v] & 63]];
+        const uint32_t lm = s_lm[s_cl[a.lab8[a.base + v] & 63]];
         uint32_t s = 0;
         if (lm) {
           const int q0 = fz_q0(lm);
@@ -74,8 +77,8 @@ __global__ void __launch_bounds__(kBlock) k_fz_init(FzArgs a, const unsigned lon
           removed = removed || ((sg & rq) != 0ull && !alive[k]);   // entered the map and left it (bsp.hpp:566-579)
           if (alive[k]) s = 1u << q0;
         }
-        a.S[v] = (uint16_t)s;
-        if (alive[k]) { nv++; val[k] = make_uint4((uint32_t)v, a.rowblk[v], 0u, 1u); }
+        a.S[a.base + v] = (uint16_t)s;
+        if (alive[k]) { nv++; val[k] = make_uint4(a.base + (uint32_t)v, a.rowblk[v], 0u, 1u); }
       }
     }
     block_append2<IT>(alive, bin, val, fr, fr, &a.cnt->fr_n[buf][0]);
@@ -103,7 +106,7 @@ __global__ void __launch_bounds__(kBlock) k_fz_scan(FzArgs a, uint4* __restrict_
     if (has) {
       e = list[idx];
       Sv = a.S[e.x];
-      if (Sv) d = a.deg[e.x];  // erased by token passing since the last commit: nothing to do
+      if (Sv) d = a.deg[e.x - a.base];  // erased by token passing since the last commit: nothing to do
     }
     const unsigned long long rq = Sv ? c_pat.req[fz_q0(Sv)] : 0ull;
     const uint64_t row = (uint64_t)e.y * 8;
@@ -166,14 +169,17 @@ __global__ void __launch_bounds__(kBlock) k_fz_commit(FzArgs a, const uint4* __r
       alive[k] = false;
       bin[k] = 0;
       val[k] = make_uint4(0, 0, 0, 0);
+      bool changed = false;
+      uint32_t cslot = 0;
       if (i < total) {
         const uint4 e = l0[i];
         const bool was = a.S[e.x] != 0;
         alive[k] = was && e.w != 0;
-        if (was && !alive[k]) { a.S[e.x] = 0; a.cnt->nf = 1u; }
+        if (was && !alive[k]) { a.S[e.x] = 0; a.cnt->nf = 1u; changed = true; cslot = e.x; }
         if (alive[k]) nv++;
         val[k] = e;
       }
+      if (c_peer.G > 1) publish_mask(changed, cslot, 0u, a.cnt, a.par);  // peers drop the vertex from their replicas
     }
     block_append2<IT>(alive, bin, val, n0, n0, &a.cnt->fr_n[nxt][0]);
   }
@@ -225,7 +231,10 @@ __global__ void __launch_bounds__(kBlock) k_fz_sources(FzArgs a, const uint4* __
         const uint32_t pos = base + __popc(m & lanemask_lt());
         src_list[pos] = v;
         ok[v] = 0;
-        if (pos < pool_cap) pool[pos] = make_uint2(v, v);
+        if (c_peer.G > 1) {  // level 0 = my own region of my token inbox
+          if (pos < c_peer.tcap) c_peer.tin[a.par][c_peer.rank][(unsigned long long)c_peer.rank * c_peer.tcap + pos] = make_uint2(v, v);
+          else a.cnt->overflow = 1u;
+        } else if (pos < pool_cap) pool[pos] = make_uint2(v, v);
         else a.cnt->overflow = 1u;
       }
     }
@@ -313,11 +322,104 @@ __global__ void __launch_bounds__(kBlock) k_fz_final(FzArgs a, NlcArgs t, int hl
 
 // TP_ORIG post-processing (run_pattern_matching.cpp:583-629): failed sources leave the map
 __global__ void __launch_bounds__(kBlock) k_fz_apply(uint16_t* __restrict__ S, const uint8_t* __restrict__ ok,
-                                                      const uint32_t* __restrict__ src_list, DevCounters* cnt) {
+                                                      const uint32_t* __restrict__ src_list, DevCounters* cnt, int par) {
   const uint32_t n = cnt->n_src;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const uint32_t s = src_list[i];
-    if (!ok[s] && S[s] != 0) { S[s] = 0; cnt->deleted = 1u; }
+  const uint32_t nr = (n + 31u) & ~31u;  // whole warps: publish_mask is warp collective
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nr; i += gridDim.x * blockDim.x) {
+    bool changed = false;
+    uint32_t s = 0;
+    if (i < n) {
+      s = src_list[i];
+      if (!ok[s] && S[s] != 0) { S[s] = 0; cnt->deleted = 1u; changed = true; }
+    }
+    if (c_peer.G > 1) publish_mask(changed, s, 0u, cnt, par);
+  }
+}
+
+// ---- several ranks: tokens travel through the owners' inboxes (see pm_nlcc_multi.cuh); vertices are SLOTS here ----
+// tokens of the previous hop (inbox par ^ 1) -> hop hn (inbox par of the owners); first: the tokens are the sources
+__global__ void __launch_bounds__(kBlock) k_fz_expand_m(FzArgs a, NlcArgs t, int hn, int first) {
+  const TokSrc src = tok_src(t, c_peer.tcap);
+  const uint2* __restrict__ in = c_peer.tin[t.par ^ 1][c_peer.rank];
+  constexpr int GROUP = 8;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t gl = lane % GROUP, gw = lane / GROUP;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  const uint32_t want_lab = c_fz.lab[hn];
+  const uint32_t want_s = 1u << c_fz.I[hn];
+  unsigned long long fan = 0, accepted = 0;
+  for (uint64_t base = warp * 4; base < src.total; base += nwarps * 4) {
+    const uint64_t ti = base + gw;
+    bool has = ti < src.total;
+    uint32_t v = 0, s = 0, d = 0, fresh = 1;
+    if (has) {
+      const uint2 tk = in[tok_locate(src, ti, c_peer.tcap)];
+      v = tk.x;
+      s = tk.y;
+      // one token per (vertex, source) at interior hops (tp.hpp:104-109, 137-149), applied where the token arrives
+      if (!first && gl == 0) fresh = hset_insert(t, v, s) ? 1u : 0u;
+    }
+    fresh = __shfl_sync(0xffffffffu, fresh, gw * GROUP);
+    if (!fresh) has = false;
+    if (has) {
+      d = a.deg[v - a.base];
+      if (gl == 0) accepted++;
+    }
+    const uint64_t row = has ? (uint64_t)a.rowblk[v - a.base] * 8 : 0;
+    const uint32_t passes = (d + GROUP * 4 - 1) / (GROUP * 4);
+    const uint32_t maxp = __reduce_max_sync(0xffffffffu, passes);
+    for (uint32_t p = 0; p < maxp; ++p) {
+      const uint32_t j0 = p * GROUP * 4 + gl * 4;
+      uint4 q = make_uint4(0, 0, 0, 0);
+      uint32_t l4 = 0;
+      if (j0 < d) {
+        q = *reinterpret_cast<const uint4*>(a.col0 + row + j0);
+        l4 = *reinterpret_cast<const uint32_t*>(a.lab0 + row + j0);
+      }
+      const uint32_t u[4] = {q.x & a.idmask, q.y & a.idmask, q.z & a.idmask, q.w & a.idmask};
+      bool ins[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        ins[k] = j0 + k < d && ((l4 >> (8 * k)) & 0xffu) == want_lab && a.S[u[k]] == want_s;
+      route_tokens<2>(t, ins, u, s);
+    }
+    if (has && gl == 0) fan += d;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    fan += __shfl_xor_sync(0xffffffffu, fan, o);
+    accepted += __shfl_xor_sync(0xffffffffu, accepted, o);
+  }
+  if (lane == 0 && fan) atomicAdd(&t.cnt->fanout, fan);
+  if (lane == 0 && accepted) atomicAdd(&t.cnt->pool_n, accepted);
+}
+
+// final hop: the tokens that arrived at hop C complete a cycle iff their vertex is adjacent to the source
+// (tp.hpp:236-262); the acknowledgement is one byte stored at the owner of the source
+__global__ void __launch_bounds__(kBlock) k_fz_final_m(FzArgs a, NlcArgs t, int hn) {
+  const TokSrc src = tok_src(t, c_peer.tcap);
+  const uint2* __restrict__ in = c_peer.tin[t.par ^ 1][c_peer.rank];
+  for (unsigned long long ti = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; ti < src.total;
+       ti += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint2 tk = in[tok_locate(src, ti, c_peer.tcap)];
+    const uint32_t v = tk.x, s = tk.y;
+    if (t.ok[s]) continue;  // own source already done, or acknowledged from this GPU before
+    if (a.S[s] != (1u << c_fz.I[hn]) || a.lab8[s] != c_fz.lab[hn]) continue;
+    const uint64_t row = (uint64_t)a.rowblk[v - a.base] * 8;
+    uint32_t b = 0, e = a.deg[v - a.base];
+    const uint32_t d = e;
+    while (b < e) {
+      const uint32_t mid = (b + e) >> 1;
+      const uint32_t x = a.col0[row + mid] & a.idmask;
+      if (x < s) b = mid + 1; else e = mid;
+    }
+    if (b < d && (a.col0[row + b] & a.idmask) == s) {
+      t.ok[s] = 1;
+      const uint32_t o = s / c_peer.nlmax;
+      if ((int)o != c_peer.rank) c_peer.ok[o][s] = 1;
+      t.cnt->found = 1u;
+    }
   }
 }
 

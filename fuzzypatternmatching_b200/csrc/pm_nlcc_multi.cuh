@@ -71,15 +71,17 @@ __device__ __forceinline__ void mark_edge_m(uint32_t s, uint32_t parent) {
 
 // One warp appends its accepted tokens to the inbox regions of their owners.  All 32 lanes call.
 // Positions come from this rank's own counters (cnt->out_n[g]); the stores go over NVLink.
-// TO_SOURCE: the records go to the owner of the SOURCE s (closing requests, k_close_check_m) instead of the owner of u
-template <bool TO_SOURCE = false>
+// DEST 0: the records go to the owner of the compact id u; 1: to the owner of the SOURCE s (closing requests,
+// k_close_check_m); 2: u names a SLOT (run_fuzzy path), owner = u / nlmax
+template <int DEST = 0>
 __device__ __forceinline__ void route_tokens(const NlcArgs& a, const bool (&flag)[4], const uint32_t (&u)[4], uint32_t s) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t lt = (1u << lane) - 1u;
   uint32_t dest[4];
-  const uint32_t so = TO_SOURCE ? cid_owner(s) : 0u;
+  const uint32_t so = DEST == 1 ? cid_owner(s) : 0u;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) dest[k] = flag[k] ? (TO_SOURCE ? so : cid_owner(u[k])) : 0xFFFFFFFFu;
+  for (int k = 0; k < 4; ++k)
+    dest[k] = flag[k] ? (DEST == 1 ? so : DEST == 2 ? u[k] / c_peer.nlmax : cid_owner(u[k])) : 0xFFFFFFFFu;
   for (int g = 0; g < c_peer.G; ++g) {
     uint32_t m[4], total = 0;
 #pragma unroll
@@ -306,7 +308,7 @@ __global__ void __launch_bounds__(kBlock) k_nem1_hop_m(NlcArgs a, int hn, int fi
         bool req[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) req[k] = pass[k] && u[k] != s;  // the source cannot relay (nem_1.hpp:174-177)
-        route_tokens<true>(a, req, u, s);
+        route_tokens<1>(a, req, u, s);
       }
       if (MODE == 1) {
 #pragma unroll

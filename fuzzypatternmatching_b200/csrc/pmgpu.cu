@@ -1371,7 +1371,6 @@ int pm_run(pm_ctx* c, const pm_run_options_t* opt_in, pm_run_summary_t* out) {
 // ------------------------------------------------------ the run_fuzzy loop
 int pm_run_fuzzy(pm_ctx* c, const pm_run_options_t* opt_in, pm_run_summary_t* out) {
   if (!c) return PM_ERR_ARG;
-  if (c->n_ranks > 1) return fail(c, PM_ERR_UNSUPPORTED, "pm_run_fuzzy: one rank only");
   if (!c->has_graph || !c->has_labels || !c->has_pattern) return fail(c, PM_ERR_ARG, "pm_run_fuzzy needs a graph, labels and a pattern");
   if (!c->labels_small) return fail(c, PM_ERR_UNSUPPORTED, "pm_run_fuzzy: labels must be < 64");
   // a walk that repeats a template vertex at interior hops makes the source-keyed aggregation set of
@@ -1384,21 +1383,42 @@ int pm_run_fuzzy(pm_ctx* c, const pm_run_options_t* opt_in, pm_run_summary_t* ou
   if (opt_in) opt = *opt_in;
   int rc = state_reset(c, false);  // allocations, pattern constants, bookkeeping (beta.cpp:484-492 analogue)
   if (rc) return rc;
-  c->fuzzy_ids = true;         // this path names vertices directly (no compact ids)
+  c->fuzzy_ids = true;         // this path names vertices by slot (no compact ids)
   load_nlcc_sizes(c, "fuzzy");
   cudaStream_t st = c->stream;
   const int D = c->pat.diameter, grid = grid_for();
   const int max_it = opt.max_iterations > 0 ? opt.max_iterations : 1000;
+  const bool multi = c->n_ranks > 1;
+  // Several ranks (the reference runs this path under MPI like the other, bsp.hpp:591, 632): the mask array S is
+  // replicated by slot; a vertex that leaves the map is published to the peers as a (slot, 0) delta with the same
+  // step barrier as pm_lcc; tokens travel through the owners' inboxes (pm_nlcc_multi.cuh) keyed by slot.
+  if (multi) {  // the compact id ranges are not used on this path: every owner test goes by slot
+    for (int g = 0; g <= PM_MAX_RANKS; ++g) c->peers.off[g] = c->cid_off[g] = 0;
+    if ((rc = comm_upload_peers(c))) return rc;
+  }
   FzArgs a;
   if ((rc = ensure_lab0(c))) return rc;  // packed labels: the byte label stream of this path is built on demand
   a.rowblk = c->rowblk; a.deg = c->deg; a.col0 = c->col0; a.lab0 = c->lab0; a.lab8 = c->lab8; a.S = c->S; a.cnt = c->cnt;
   a.idmask = col_idmask(c);
+  a.base = (uint32_t)(c->nlmax * c->rank);
+  a.par = c->step_parity;
   a.row = c->rowstat;
   PM_CUDA(c, cudaMemsetAsync(c->cnt, 0, sizeof(DevCounters), st));
   c->cur = 0;
   bool init = true;
   int nf = 0;
   const double t_begin = wall_s();
+  // barrier + exchange of what the last kernel published (mask deltas)
+  auto step_and_apply = [&]() -> int {
+    if (!multi) return 0;
+    int r2 = comm_step(c);
+    if (r2) return r2;
+    k_apply_deltas<<<grid, kBlock, 0, st>>>(c->S, c->step_msg + 1, c->step_parity);
+    PM_LAUNCH_CHECK(c);
+    c->step_parity ^= 1;
+    a.par = c->step_parity;
+    return 0;
+  };
   do {
     const double it0 = wall_s();
     // ---- label_propagation_pattern_matching_bsp (bsp.hpp:598-699): `diameter` supersteps
@@ -1412,6 +1432,8 @@ int pm_run_fuzzy(pm_ctx* c, const pm_run_options_t* opt_in, pm_run_summary_t* ou
         k_fz_init<<<grid, kBlock, 0, st>>>(a, c->sig, c->nloc, c->fr[0][0], 0);
         PM_LAUNCH_CHECK(c);
         c->cur = 0;
+        // every rank decided its own vertices: the replicas get the whole array once
+        if (multi && (rc = comm_allgather_slots(c, c->S))) return rc;
       } else {
         const int cur = c->cur, nxt = cur ^ 1;
         PM_CUDA(c, cudaMemsetAsync(&c->cnt->fr_n[nxt][0], 0, 4 * sizeof(uint32_t), st));
@@ -1420,12 +1442,19 @@ int pm_run_fuzzy(pm_ctx* c, const pm_run_options_t* opt_in, pm_run_summary_t* ou
         k_fz_commit<<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], c->fr[nxt][0], cur, nxt);
         PM_LAUNCH_CHECK(c);
         c->cur = nxt;
+        if ((rc = step_and_apply())) return rc;
       }
     }
     PM_CUDA(c, cudaEventRecord(c->events[D], st));
+    if (multi && (rc = comm_step(c))) return rc;  // global_not_finished is reduced over the ranks (run_pattern_matching.cpp:497-505)
+    if (multi) { c->step_parity ^= 1; a.par = c->step_parity; }
     PM_CUDA(c, cudaMemcpyAsync(c->h_rowstat, c->rowstat, D * sizeof(RowStat), cudaMemcpyDeviceToHost, st));
     if ((rc = sync_counters(c))) return rc;
     nf = c->h_cnt->nf ? 1 : 0;
+    if (multi) {
+      if ((rc = comm_step_fetch(c))) return rc;
+      for (int g = 0; g < c->n_ranks; ++g) nf = nf || c->h_step[g].nf;
+    }
     for (int k = 0; k < D; ++k) {
       float ms = 0;
       PM_CUDA(c, cudaEventElapsedTime(&ms, c->events[k], c->events[k + 1]));
@@ -1454,8 +1483,11 @@ int pm_run_fuzzy(pm_ctx* c, const pm_run_options_t* opt_in, pm_run_summary_t* ou
         for (size_t h = 0; h < k.P.size(); ++h) { ft.lab[h] = (uint8_t)(k.P[h] < 64 ? k.P[h] : 255); ft.I[h] = (uint8_t)k.I[h]; }
         PM_CUDA(c, cudaMemcpyToSymbolAsync(c_fz, &ft, sizeof(ft), 0, cudaMemcpyHostToDevice, st));
         if (c->pool_seen.size() != c->pat.constraints.size()) c->pool_seen.assign(c->pat.constraints.size(), 0);
-        uint64_t want = c->pool_seen[pl] ? c->pool_seen[pl] + c->pool_seen[pl] / 2 + 4096 : std::max<uint64_t>(1ull << 20, 16 * c->rows.back().n_vertices);
-        want = std::max<uint64_t>(want, c->rows.back().n_vertices + 4096);  // level 0: one token per source
+        // the vertices still in the map bound the sources; several ranks agree on one size (growing the inboxes is collective)
+        uint64_t alive_now = c->rows.back().n_vertices;
+        if (multi && (rc = comm_allreduce_max_u64(c, &alive_now))) return rc;
+        uint64_t want = c->pool_seen[pl] ? c->pool_seen[pl] + c->pool_seen[pl] / 2 + 4096 : std::max<uint64_t>(1ull << 20, 16 * alive_now);
+        want = std::max<uint64_t>(want, alive_now + 4096);  // level 0: one token per source
         for (int attempt = 0;; ++attempt) {
           if ((rc = nlcc_reserve(c, want, want))) return rc;
           c->hset_use = c->hset_cap;
@@ -1464,24 +1496,57 @@ int pm_run_fuzzy(pm_ctx* c, const pm_run_options_t* opt_in, pm_run_summary_t* ou
           c->hset_use = std::min(use, c->hset_cap);
           PM_CUDA(c, cudaMemsetAsync(&c->cnt->found, 0, sizeof(DevCounters) - offsetof(DevCounters, found), st));
           PM_CUDA(c, cudaMemsetAsync(c->hset, 0xFF, c->hset_use * sizeof(unsigned long long), st));
+          // several ranks: `ok` doubles as this GPU's "already acknowledged" cache for foreign sources
+          if (multi) PM_CUDA(c, cudaMemsetAsync(c->ok, 0, c->nlmax * c->n_ranks, st));
+          a.par = c->step_parity;
           NlcArgs t = nlc_args(c, nullptr, 0);
           k_fz_sources<<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], cur, c->ok, c->src_list, c->pool, c->pool_cap);
           PM_LAUNCH_CHECK(c);
           k_nlcc_begin<<<1, 1, 0, st>>>(c->cnt);
           PM_LAUNCH_CHECK(c);
-          for (int hn = 1; hn <= (int)k.C; ++hn) {  // interior hops
-            k_fz_expand<<<grid, kBlock, 0, st>>>(a, t, hn - 1, hn);
-            PM_LAUNCH_CHECK(c);
-            k_nlcc_close_level<<<1, 1, 0, st>>>(c->cnt, hn, c->pool_cap);
-            PM_LAUNCH_CHECK(c);
+          if (!multi) {
+            for (int hn = 1; hn <= (int)k.C; ++hn) {  // interior hops
+              k_fz_expand<<<grid, kBlock, 0, st>>>(a, t, hn - 1, hn);
+              PM_LAUNCH_CHECK(c);
+              k_nlcc_close_level<<<1, 1, 0, st>>>(c->cnt, hn, c->pool_cap);
+              PM_LAUNCH_CHECK(c);
+            }
+            if (k.valid_cycle) {  // a path never marks its source in this path (tp.hpp:263-268)
+              k_fz_final<<<grid, kBlock, 0, st>>>(a, t, (int)k.C, (int)k.C + 1);
+              PM_LAUNCH_CHECK(c);
+            }
+            if ((rc = sync_counters(c))) return rc;
+          } else {
+            // one kernel + one step barrier per hop (see pm_nlcc): level 0, the sources, sits in inbox `par`
+            if ((rc = comm_step(c))) return rc;
+            c->step_parity ^= 1;
+            for (int hn = 1; hn <= (int)k.C; ++hn) {
+              t = nlc_args(c, nullptr, 0);
+              k_fz_expand_m<<<grid, kBlock, 0, st>>>(a, t, hn, hn == 1 ? 1 : 0);
+              PM_LAUNCH_CHECK(c);
+              if ((rc = comm_step(c))) return rc;
+              c->step_parity ^= 1;
+            }
+            if (k.valid_cycle) {
+              t = nlc_args(c, nullptr, 0);
+              k_fz_final_m<<<grid, kBlock, 0, st>>>(a, t, (int)k.C + 1);
+              PM_LAUNCH_CHECK(c);
+              if ((rc = comm_step(c))) return rc;  // the acknowledgements have landed at the owners
+              c->step_parity ^= 1;
+            }
+            a.par = c->step_parity;
+            if ((rc = sync_counters(c))) return rc;
+            if ((rc = comm_step_fetch(c))) return rc;
           }
-          if (k.valid_cycle) {  // a path never marks its source in this path (tp.hpp:263-268)
-            k_fz_final<<<grid, kBlock, 0, st>>>(a, t, (int)k.C, (int)k.C + 1);
-            PM_LAUNCH_CHECK(c);
-          }
-          if ((rc = sync_counters(c))) return rc;
-          if (!(c->h_cnt->overflow || c->h_cnt->pool_n > c->pool_cap)) {
-            c->pool_seen[pl] = std::max<uint64_t>(c->pool_seen[pl], c->h_cnt->pool_n);
+          bool overflow = c->h_cnt->overflow || (!multi && c->h_cnt->pool_n > c->pool_cap);
+          uint64_t peak = multi ? (uint64_t)c->h_cnt->peak_out : (uint64_t)c->h_cnt->pool_n;
+          if (multi)
+            for (int g = 0; g < c->n_ranks; ++g) {
+              overflow = overflow || c->h_step[g].overflow;
+              peak = std::max<uint64_t>(peak, std::max<uint64_t>(c->h_step[g].peak, c->h_step[g].accepted));
+            }
+          if (!overflow) {
+            c->pool_seen[pl] = std::max<uint64_t>(c->pool_seen[pl], peak);
             c->pool_cache[c->pat_key] = c->pool_seen;
             break;
           }
@@ -1490,10 +1555,16 @@ int pm_run_fuzzy(pm_ctx* c, const pm_run_options_t* opt_in, pm_run_summary_t* ou
         }
         c->summary.edges_processed += c->h_cnt->fanout;
         c->summary.algorithmic_bytes += c->h_cnt->fanout * 5 + c->h_cnt->pool_n * 16;
-        k_fz_apply<<<grid, kBlock, 0, st>>>(c->S, c->ok, c->src_list, c->cnt);
+        k_fz_apply<<<grid, kBlock, 0, st>>>(c->S, c->ok, c->src_list, c->cnt, c->step_parity);
         PM_LAUNCH_CHECK(c);
+        if ((rc = step_and_apply())) return rc;
         if ((rc = sync_counters(c))) return rc;
-        if (c->h_cnt->deleted) nf = 1;
+        int deleted = c->h_cnt->deleted ? 1 : 0;
+        if (multi) {
+          if ((rc = comm_step_fetch(c))) return rc;
+          for (int g = 0; g < c->n_ranks; ++g) deleted = deleted || c->h_step[g].deleted;
+        }
+        if (deleted) nf = 1;
       }
       // "itr, TP, 0, |map|" (run_pattern_matching.cpp:664-666)
       PM_CUDA(c, cudaMemsetAsync(c->rowstat + D, 0, sizeof(RowStat), st));

@@ -229,7 +229,8 @@ int pm_run(pm_ctx* ctx, const pm_run_options_t* opt, pm_run_summary_t* out);
  * unpruned adjacency (include/havoqgt/token_passing_pattern_matching.hpp:514-530) whose failed sources leave the
  * vertex_state_map.  Rows: (itr, LP, k, |map|, 0) and one (itr, TP, 0, |map|, 0) per iteration that passed
  * tokens; pm_get_active_vertices returns (vertex, 1 << vertex_pattern_index).  Only opt->max_iterations is used.
- * One rank, labels < 64. */
+ * Labels < 64.  Collective over the ranks of pm_comm_init (1-D partition; the mask array is replicated by slot,
+ * removals travel as deltas, tokens through the owners' inboxes). */
 int pm_run_fuzzy(pm_ctx* ctx, const pm_run_options_t* opt, pm_run_summary_t* out);
 /* For a host driver that spells the loop out over pm_lcc / pm_nlcc itself (as the
  * reference main does): closes outer iteration `global_itr_count` (beta.cpp:1327-1341)

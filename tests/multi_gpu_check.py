@@ -75,6 +75,45 @@ def partition_parity(eng, dist, rank, world, name, build_graph, oracle_graph, la
     return bool(ok)
 
 
+def partition_parity_fuzzy(eng, dist, rank, world, name, build_graph, oracle_graph, labels, spec, log=print):
+    """The run_fuzzy_pattern_matching path (pm_run_fuzzy) over `world` ranks against the oracle: per-superstep map sizes
+    summed over the ranks, iteration count, and every rank's final (vertex, 1 << vertex_pattern_index) list."""
+    d = cases.pattern_dir(spec) if rank == 0 else None
+    box = [d]
+    dist.broadcast_object_list(box, src=0)
+    d = box[0]
+    build_graph()
+    if labels is None:
+        eng.labels_degree_log2()
+    else:
+        eng.labels_set(labels)
+    eng.pattern_load_dir(d)
+    eng.run_fuzzy(max_iterations=50)
+    mine = dict(rows=eng.rows(), iterations=int(eng.summary["iterations"]),
+                vertices=[tuple(map(int, x)) for x in zip(*eng.active_vertices())])
+    got = [None] * world
+    dist.gather_object(mine, got if rank == 0 else None, dst=0)
+    if rank != 0:
+        return None
+    from oracle import oracle as O
+    g = oracle_graph()
+    lab = g.labels_degree_log2() if labels is None else labels
+    ref = O.Run(g, lab, O.Pattern(d), fuzzy=True, max_iterations=50)
+    rv, rt = ref.active_vertices()
+    want_v = list(zip(rv.tolist(), rt.tolist()))
+    rows = [(r[0], r[1], r[2], sum(gr["rows"][i][3] for gr in got), 0) for i, r in enumerate(got[0]["rows"])]
+    ok = rows == ref.rows and all(gr["iterations"] == ref.iterations for gr in got)
+    for r, gr in enumerate(got):
+        ok &= gr["vertices"] == [x for x in want_v if x[0] % world == r]
+    log("%-28s %s  rows %d final %d vertices" % (name, "ok" if ok else "MISMATCH", len(rows), len(want_v)))
+    if not ok and rows != ref.rows:
+        for a, b in zip(rows, ref.rows):
+            if a != b:
+                log("   first differing row: got %s want %s" % (a, b))
+                break
+    return bool(ok)
+
+
 def main():
     scale = int(sys.argv[1]) if len(sys.argv) > 1 else 17
     gen_ranks = int(sys.argv[2]) if len(sys.argv) > 2 else 4
@@ -121,6 +160,23 @@ def main():
         eng.graph_from_csr(rowptr, col, degm, n_vertices=nv)
     check("rmat%d/host_csr/triangle" % scale, reopen_from_host_csr, lambda: O.Graph.rmat(scale, gen_ranks),
           None, PT.triangle(6, 7, 8), 1)
+    # the run_fuzzy path over the same partition (unique-label LCC + cycle token passing over the unpruned adjacency)
+    def check_fuzzy(name, build_graph, oracle_graph, labels, spec):
+        ok = partition_parity_fuzzy(eng, dist, rank, world, name, build_graph, oracle_graph, labels, spec,
+                                    log=lambda m: print(m, flush=True))
+        if rank == 0 and not ok:
+            failures.append(name)
+
+    for nm, spec, labelset in (("triangle", PT.triangle(1, 2, 3), [1, 2, 3]), ("cycle4", PT.cycle4(1, 2, 3, 4), [1, 2, 3, 4])):
+        for seed in range(6):
+            n, m = 60 + 10 * (seed % 4), 220 + 60 * (seed % 5)
+            edges = cases.random_multigraph(seed, n, m)
+            labels = cases.random_labels(seed, n, labelset)
+            src, dst = cases.slots_of(edges)
+            check_fuzzy("fuzzy/%s/seed%d" % (nm, seed), lambda: eng.graph_from_slots(n, src, dst),
+                        lambda: O.Graph.from_undirected(n, edges), labels, spec)
+    check_fuzzy("fuzzy/rmat%d/cycle4" % scale, lambda: eng.graph_rmat(scale, gen_ranks), lambda: O.Graph.rmat(scale, gen_ranks),
+                None, PT.cycle4(5, 6, 7, 8))
     flag = [len(failures)]
     dist.broadcast_object_list(flag, src=0)
     eng.close()

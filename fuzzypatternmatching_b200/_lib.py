@@ -65,6 +65,8 @@ SYMBOLS = {
     "pm_graph_from_csr": (_i, [_vp, _u64, _vp, _vp, _vp]),
     "pm_get_kernel_stats": (_i, [_vp, _i, C.POINTER(KernelStats)]),
     "pm_graph_info": (_i, [_vp, C.POINTER(GraphInfo)]),
+    "pm_graph_set_delegate_threshold": (_i, [_vp, _u64]),
+    "pm_graph_num_delegates": (_i, [_vp, C.POINTER(_u64)]),
     "pm_graph_get_degree": (_i, [_vp, _vp]),
     "pm_graph_get_csr": (_i, [_vp, _vp, _vp]),
     "pm_labels_degree_log2": (_i, [_vp]),

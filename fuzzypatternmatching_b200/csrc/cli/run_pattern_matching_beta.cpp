@@ -105,7 +105,11 @@ static int run_rank(const Options& o, int rank, int n_ranks, const char* comm_id
     }
   }
   out << "Done Loading Graph." << std::endl;
-  out << "Delegate threshold : " << delegate_threshold << std::endl;
+  // several ranks: hubs are attributed to their controller ranks in the per-rank files, like a reference run with delegates
+  if (n_ranks > 1) CHECK(pm_graph_set_delegate_threshold(ctx, delegate_threshold));
+  uint64_t n_delegates = 0;
+  pm_graph_num_delegates(ctx, &n_delegates);
+  out << "Delegate threshold : " << delegate_threshold << ", delegates : " << n_delegates << std::endl;
 
   // ---- vertex data (beta.cpp:358-377), edge data (beta.cpp:379-400: loaded, never read by the search, :906)
   out << "Fuzzy Pattern Matching ... " << std::endl;

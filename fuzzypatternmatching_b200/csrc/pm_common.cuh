@@ -127,6 +127,9 @@ struct RowStat {                // one result row, accumulated on the device
   unsigned long long scanned[3];   // adjacency slots walked, per degree bin
   unsigned long long verts[3];     // live vertices whose row was walked, per degree bin
   unsigned long long filtered;     // candidates settled or passed on by the signature filter
+  // several ranks with a delegate threshold: hubs this rank holds, counted for their CONTROLLER rank
+  // (delegate_id % G, delegate_partitioned_graph.hpp:231-233) instead of into nv / ne
+  unsigned long long hub_nv[PM_MAX_RANKS], hub_ne[PM_MAX_RANKS];
 };
 
 }  // namespace pm
@@ -173,6 +176,12 @@ struct pm_ctx {
                                // chosen when id bits + label bits <= 32: the first scan streams ONE array
   bool labels_small = false;   // lab8 / sig are valid
   bool has_graph = false, has_labels = false;
+  // delegates (pm_graph_set_delegate_threshold): vertices whose multigraph out-degree reaches the threshold, ascending
+  // (their position is the delegate id, ipp:501-512, 681); hub_ctl[local vertex] = controller rank + 1, 0 for the rest
+  uint64_t delegate_threshold = 0;
+  std::vector<uint32_t> hubs;
+  uint8_t* hub_ctl = nullptr;
+  uint8_t* hubc = nullptr;     // [nloc] the same by local compact id (per pattern)
 
   // ---- pattern ----------------------------------------------------------------
   pm::Pattern pat;

@@ -391,6 +391,9 @@ inline void graph_free(pm_ctx* c) {
   dev_free(c->degm);
   dev_free(c->col0);
   c->col_shift = 0;
+  dev_free(c->hub_ctl);
+  c->hubs.clear();
+  c->delegate_threshold = 0;
   dev_free(c->label);
   c->has_graph = c->has_labels = false;
   c->graph_bytes = 0;

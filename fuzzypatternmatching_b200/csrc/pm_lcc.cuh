@@ -131,6 +131,7 @@ struct LccArgs {
   uint32_t col_shift;      // packed labels: a col0 slot is (label << col_shift) | id
   int typed;               // fwx[w].y holds 2-bit T_state numbers per slot (see PatConst::tsub) instead of survivor bits
   const uint8_t* clsc;     // label class by compact id
+  const uint8_t* hubc;     // controller rank + 1 of a hub, by local compact id (null: no delegates)
 };
 
 // frontier entry: x = compact id, y = row start in sectors (PM_TOMB: the row is in the big-row list),
@@ -375,7 +376,8 @@ __global__ void __launch_bounds__(kBlock) k_init_assign(const uint8_t* __restric
                                                          uint32_t* __restrict__ rowc, uint2* __restrict__ fwx,
                                                          const unsigned long long* __restrict__ sig,
                                                          uint4* fr_main, uint4* fr_big, DevCounters* cnt, int buf,
-                                                         int typed) {
+                                                         int typed, const uint8_t* __restrict__ hub_ctl = nullptr,
+                                                         uint8_t* __restrict__ hubc = nullptr) {
   __shared__ uint8_t s_cl[64];
   __shared__ uint16_t s_lm[17];
   if (threadIdx.x < 64) s_cl[threadIdx.x] = c_pat.cls_of_label[threadIdx.x];
@@ -425,6 +427,7 @@ __global__ void __launch_bounds__(kBlock) k_init_assign(const uint8_t* __restric
       if (slot >= own_lo && slot < own_hi) {
         const uint32_t lcid = cid - off_me, d = deg[slot - own_lo], rb = rowblk[slot - own_lo];
         adeg[lcid] = d;
+        if (hubc) hubc[lcid] = hub_ctl[slot - own_lo];
         rowc[lcid] = (d + 7u) >> 3;  // |E_v| can only shrink: the prefix of these is the row start in the dense working adjacency
         // behind the signature filter (sig != null) the T_state the first superstep ends with is known here:
         // heard(v) = OR of the labelmasks of the valid labels in v's signature (see the header above), so the
@@ -1308,7 +1311,11 @@ __global__ void __launch_bounds__(kBlock) k_lcc_commit(LccArgs a, const uint4* _
           a.S[cslot] = (uint16_t)ts;
           a.adeg[e.x - a.base] = d;
           alive[k] = ts != 0;
-          if (alive[k]) { nv++; ne += d; }
+          const uint32_t hc = a.hubc ? (uint32_t)a.hubc[e.x - a.base] : 0u;
+          if (alive[k] && hc) {  // a hub: its row of the count files belongs to its controller
+            atomicAdd(&a.row->hub_nv[hc - 1u], 1ull);
+            atomicAdd(&a.row->hub_ne[hc - 1u], (unsigned long long)d);
+          } else if (alive[k]) { nv++; ne += d; }
           bin[k] = bin_of(d);
           val[k] = e;
         }
@@ -1349,7 +1356,13 @@ __global__ void __launch_bounds__(kBlock) k_count_alive(LccArgs a, const uint4* 
   unsigned long long nv = 0, ne = 0;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const uint4 e = i < c0 ? l0[i] : l1[i - c0];
-    if (e.y != PM_TOMB && a.S[e.x]) { nv++; ne += e.z; }
+    if (e.y != PM_TOMB && a.S[e.x]) {
+      const uint32_t hc = a.hubc ? (uint32_t)a.hubc[e.x - a.base] : 0u;
+      if (hc) {
+        atomicAdd(&a.row->hub_nv[hc - 1u], 1ull);
+        atomicAdd(&a.row->hub_ne[hc - 1u], (unsigned long long)e.z);
+      } else { nv++; ne += e.z; }
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {

@@ -60,6 +60,7 @@ LccArgs lcc_args(pm_ctx* c, int row) {
   a.col_shift = c->col_shift;
   a.typed = c->typed ? 1 : 0;
   a.clsc = c->clsc;
+  a.hubc = (c->n_ranks > 1 && !c->hubs.empty() && !c->fuzzy_ids) ? c->hubc : nullptr;
   return a;
 }
 
@@ -123,7 +124,7 @@ void state_free(pm_ctx* c, bool keep_scratch = false) {
   c->dcap = c->tcap = 0;
   dev_free(c->S); dev_free(c->adeg); dev_free(c->cls);
   if (!keep) { dev_free(c->colw); c->colw_cap = 0; }
-  dev_free(c->rowc); dev_free(c->vid); dev_free(c->clsc); dev_free(c->fw); dev_free(c->tb); dev_free(c->fwx);
+  dev_free(c->rowc); dev_free(c->vid); dev_free(c->clsc); dev_free(c->fw); dev_free(c->hubc); dev_free(c->tb); dev_free(c->fwx);
   for (int b = 0; b < 2; ++b) for (int k = 0; k < 2; ++k) dev_free(c->fr[b][k]);
   dev_free(c->cnt); dev_free(c->ok); dev_free(c->src_list);
   if (!keep) {
@@ -149,6 +150,94 @@ void load_nlcc_sizes(pm_ctx* c, const char* path) {
   auto it2 = c->keys_cache.find(key);
   if (it2 != c->keys_cache.end() && it2->second.size() == n) c->keys_seen = it2->second;
   else c->keys_seen.assign(n, 0);
+}
+
+// ---- delegates: attribution of hubs to their controller ranks (several ranks) -----------------------------------
+// controller rank of vertex v if it is a hub, else -1 (delegate id = position in the ascending hub list,
+// impl/delegate_partitioned_graph.ipp:501-512, 681; controller = delegate_id % ranks, delegate_partitioned_graph.hpp:231-233)
+int hub_controller(const pm_ctx* c, uint64_t v) {
+  if (c->hubs.empty()) return -1;
+  auto it = std::lower_bound(c->hubs.begin(), c->hubs.end(), (uint32_t)v);
+  if (it == c->hubs.end() || *it != (uint32_t)v) return -1;
+  return (int)((it - c->hubs.begin()) % c->n_ranks);
+}
+bool hubs_on(const pm_ctx* c) { return c->n_ranks > 1 && !c->hubs.empty(); }
+
+// Collective.  Adds to rows[0 .. n) the hubs the PEERS hold for this rank's controller role (RowStat::hub_nv / hub_ne
+// of rowstat[first .. first + n) on every rank).  The device rows must be complete on the stream.
+int hub_rows_merge(pm_ctx* c, int first, int n, pm_row_t* rows) {
+  if (!hubs_on(c) || n <= 0) return 0;
+  RowStat* d_all = nullptr;
+  int rc = dev_alloc(c, &d_all, (uint64_t)n * c->n_ranks);
+  if (rc) return rc;
+  std::vector<RowStat> all((size_t)n * c->n_ranks);
+  ncclResult_t nr = ncclAllGather(c->rowstat + first, d_all, (size_t)n * sizeof(RowStat), ncclChar, comm_of(c), c->stream);
+  cudaError_t e = cudaMemcpyAsync(all.data(), d_all, all.size() * sizeof(RowStat), cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  dev_free(d_all);
+  if (nr != ncclSuccess) return fail(c, PM_ERR_COMM, ncclGetErrorString(nr));
+  if (e != cudaSuccess) return fail(c, PM_ERR_CUDA, cudaGetErrorString(e));
+  for (int k = 0; k < n; ++k)
+    for (int g = 0; g < c->n_ranks; ++g) {
+      rows[k].n_vertices += all[(size_t)g * n + k].hub_nv[c->rank];
+      rows[k].n_edges += all[(size_t)g * n + k].hub_ne[c->rank];
+    }
+  return 0;
+}
+
+// Collective.  Records of `width` words: those whose key vertex (word `key`) is a hub move to its controller rank;
+// `data` comes back holding this rank's records (its own non-hub ones + the hubs it controls), unsorted.
+int hub_records_exchange(pm_ctx* c, std::vector<uint32_t>& data, int width, int key) {
+  if (!hubs_on(c)) return 0;
+  const int G = c->n_ranks;
+  std::vector<std::vector<uint32_t>> out(G);
+  for (size_t i = 0; i + width <= data.size(); i += width) {
+    const int ctl = hub_controller(c, data[i + key]);
+    auto& dst = out[ctl < 0 ? c->rank : ctl];
+    dst.insert(dst.end(), data.begin() + i, data.begin() + i + width);
+  }
+  // counts of every (sender, receiver) pair
+  unsigned long long* d_cnt = nullptr;
+  int rc = dev_alloc(c, &d_cnt, (uint64_t)G * G);
+  if (rc) return rc;
+  std::vector<unsigned long long> mine(G), all((size_t)G * G);
+  for (int g = 0; g < G; ++g) mine[g] = out[g].size();
+  cudaMemcpyAsync(d_cnt + (size_t)c->rank * G, mine.data(), 8 * G, cudaMemcpyHostToDevice, c->stream);
+  ncclResult_t nr = ncclAllGather(d_cnt + (size_t)c->rank * G, d_cnt, G, ncclUint64, comm_of(c), c->stream);
+  cudaError_t e = cudaMemcpyAsync(all.data(), d_cnt, 8 * (size_t)G * G, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  dev_free(d_cnt);
+  if (nr != ncclSuccess) return fail(c, PM_ERR_COMM, ncclGetErrorString(nr));
+  if (e != cudaSuccess) return fail(c, PM_ERR_CUDA, cudaGetErrorString(e));
+  uint64_t n_send = 0, n_recv = 0;
+  std::vector<uint64_t> soff(G), roff(G);
+  for (int g = 0; g < G; ++g) {
+    soff[g] = n_send;
+    roff[g] = n_recv;
+    if (g != c->rank) { n_send += mine[g]; n_recv += all[(size_t)g * G + c->rank]; }
+  }
+  uint32_t *d_send = nullptr, *d_recv = nullptr;
+  if ((rc = dev_alloc(c, &d_send, n_send + 1)) || (rc = dev_alloc(c, &d_recv, n_recv + 1))) { dev_free(d_send); return rc; }
+  for (int g = 0; g < G; ++g)
+    if (g != c->rank && mine[g]) cudaMemcpyAsync(d_send + soff[g], out[g].data(), mine[g] * 4, cudaMemcpyHostToDevice, c->stream);
+  nr = ncclGroupStart();
+  for (int g = 0; g < G && nr == ncclSuccess; ++g) {
+    if (g == c->rank) continue;
+    if (mine[g]) nr = ncclSend(d_send + soff[g], (size_t)mine[g], ncclUint32, g, comm_of(c), c->stream);
+    const uint64_t rn = all[(size_t)g * G + c->rank];
+    if (rn && nr == ncclSuccess) nr = ncclRecv(d_recv + roff[g], (size_t)rn, ncclUint32, g, comm_of(c), c->stream);
+  }
+  if (nr == ncclSuccess) nr = ncclGroupEnd();
+  std::vector<uint32_t> got(n_recv);
+  if (n_recv) e = cudaMemcpyAsync(got.data(), d_recv, n_recv * 4, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  dev_free(d_send);
+  dev_free(d_recv);
+  if (nr != ncclSuccess) return fail(c, PM_ERR_COMM, ncclGetErrorString(nr));
+  if (e != cudaSuccess) return fail(c, PM_ERR_CUDA, cudaGetErrorString(e));
+  data = std::move(out[c->rank]);
+  data.insert(data.end(), got.begin(), got.end());
+  return 0;
 }
 
 // nem_1's result is independent of message arrival order iff interior hop labels
@@ -325,6 +414,94 @@ int pm_graph_rmat(pm_ctx* c, uint64_t scale, uint64_t gen_ranks) {
   PM_CUDA(c, cudaSetDevice(c->device));
   state_free(c, /*keep_scratch=*/true);
   return rmat_build(c, scale, gen_ranks);
+}
+
+// Delegates: vertices whose multigraph out-degree reaches the threshold (generate_rmat / ingest_edge_list -d).  The hub
+// rows stay with their home rank v mod G on the device; what follows the reference is the ATTRIBUTION: the count
+// files and the vertex / edge / subgraph rows of a hub belong to its controller rank delegate_id % G.  Collective.
+__global__ void k_find_hubs(const uint32_t* __restrict__ degm, uint64_t n_own, unsigned long long threshold, uint32_t G,
+                            uint32_t rank, uint32_t* __restrict__ out, uint32_t cap, uint32_t* __restrict__ n_out) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; i < n_own; i += stride)
+    if ((unsigned long long)degm[i] >= threshold) {
+      const uint32_t p = atomicAdd(n_out, 1u);
+      if (p < cap) out[p] = (uint32_t)(i * G + rank);
+    }
+}
+__global__ void k_mark_hubs(const uint32_t* __restrict__ local_idx, const uint8_t* __restrict__ ctl, uint32_t n, uint8_t* __restrict__ hub_ctl) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) hub_ctl[local_idx[i]] = ctl[i];
+}
+
+int pm_graph_set_delegate_threshold(pm_ctx* c, uint64_t threshold) {
+  if (!c || !c->has_graph) return fail(c, PM_ERR_ARG, "pm_graph_set_delegate_threshold: no graph");
+  PM_CUDA(c, cudaSetDevice(c->device));
+  c->delegate_threshold = threshold;
+  c->hubs.clear();
+  c->state_ready = false;
+  if (threshold == 0) return 0;
+  const uint32_t cap = 1u << 20;  // hubs per rank this call can carry
+  const int G = c->n_ranks;
+  uint32_t *d_list = nullptr, *d_n = nullptr, *d_all = nullptr;
+  int rc;
+  if ((rc = dev_alloc(c, &d_list, (uint64_t)cap + 1)) || (rc = dev_alloc(c, &d_n, 1)) || (rc = dev_alloc(c, &d_all, ((uint64_t)cap + 1) * G))) {
+    dev_free(d_list); dev_free(d_n); dev_free(d_all);
+    return rc;
+  }
+  cudaMemsetAsync(d_n, 0, 4, c->stream);
+  k_find_hubs<<<grid_for(), kBlock, 0, c->stream>>>(c->degm, n_owned(c), threshold, (uint32_t)G, (uint32_t)c->rank, d_list + 1, cap, d_n);
+  c->launches++;
+  cudaMemcpyAsync(d_list, d_n, 4, cudaMemcpyDeviceToDevice, c->stream);  // [0] = count, then the ids
+  std::vector<uint32_t> all(((size_t)cap + 1) * G);
+  cudaError_t e = cudaSuccess;
+  ncclResult_t nr = ncclSuccess;
+  if (G > 1) {
+    nr = ncclAllGather(d_list, d_all, (size_t)cap + 1, ncclUint32, comm_of(c), c->stream);
+    e = cudaMemcpyAsync(all.data(), d_all, all.size() * 4, cudaMemcpyDeviceToHost, c->stream);
+  } else {
+    e = cudaMemcpyAsync(all.data(), d_list, ((size_t)cap + 1) * 4, cudaMemcpyDeviceToHost, c->stream);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  dev_free(d_list); dev_free(d_n); dev_free(d_all);
+  if (nr != ncclSuccess) return fail(c, PM_ERR_COMM, ncclGetErrorString(nr));
+  if (e != cudaSuccess) return fail(c, PM_ERR_CUDA, cudaGetErrorString(e));
+  for (int g = 0; g < G; ++g) {
+    const uint32_t n = all[(size_t)g * (cap + 1)];
+    if (n > cap) return fail(c, PM_ERR_CAPACITY, "delegate threshold leaves more than 2^20 hubs on one rank");
+    c->hubs.insert(c->hubs.end(), all.begin() + (size_t)g * (cap + 1) + 1, all.begin() + (size_t)g * (cap + 1) + 1 + n);
+  }
+  std::sort(c->hubs.begin(), c->hubs.end());
+  // controller + 1 of every hub this rank holds, by local vertex
+  dev_free(c->hub_ctl);
+  if ((rc = dev_alloc(c, &c->hub_ctl, c->nloc + 1))) return rc;
+  PM_CUDA(c, cudaMemsetAsync(c->hub_ctl, 0, c->nloc + 1, c->stream));
+  std::vector<uint32_t> idx;
+  std::vector<uint8_t> ctl;
+  for (size_t i = 0; i < c->hubs.size(); ++i)
+    if ((int)(c->hubs[i] % (uint32_t)G) == c->rank) {
+      idx.push_back(c->hubs[i] / (uint32_t)G);
+      ctl.push_back((uint8_t)(i % (size_t)G + 1));
+    }
+  if (!idx.empty()) {
+    uint32_t* d_idx = nullptr;
+    uint8_t* d_ctl = nullptr;
+    if ((rc = dev_alloc(c, &d_idx, idx.size())) || (rc = dev_alloc(c, &d_ctl, ctl.size()))) { dev_free(d_idx); return rc; }
+    cudaMemcpyAsync(d_idx, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice, c->stream);
+    cudaMemcpyAsync(d_ctl, ctl.data(), ctl.size(), cudaMemcpyHostToDevice, c->stream);
+    k_mark_hubs<<<grid_for(), kBlock, 0, c->stream>>>(d_idx, d_ctl, (uint32_t)idx.size(), c->hub_ctl);
+    c->launches++;
+    e = cudaStreamSynchronize(c->stream);
+    dev_free(d_idx);
+    dev_free(d_ctl);
+    if (e != cudaSuccess) return fail(c, PM_ERR_CUDA, cudaGetErrorString(e));
+  }
+  return 0;
+}
+
+int pm_graph_num_delegates(const pm_ctx* c, uint64_t* n_out) {
+  if (!c || !n_out) return PM_ERR_ARG;
+  *n_out = c->hubs.size();
+  return 0;
 }
 
 int pm_graph_info(const pm_ctx* c, pm_graph_info_t* o) {
@@ -579,6 +756,7 @@ int state_reset(pm_ctx* c, bool need_colw) {
     if ((rc = dev_alloc(c, &c->vid, Vs))) return rc;
     if ((rc = dev_alloc(c, &c->clsc, Vs))) return rc;
     if ((rc = dev_alloc(c, &c->fw, Vs / 16 + 2))) return rc;
+    if ((rc = dev_alloc(c, &c->hubc, NL + 1))) return rc;
     if ((rc = dev_alloc(c, &c->tb, Vs / PM_TILE + 2))) return rc;
     if ((rc = dev_alloc(c, &c->fwx, Vs / 16 + 2))) return rc;
     if ((rc = dev_alloc(c, &c->cls, Vs))) return rc;
@@ -691,11 +869,13 @@ int state_reset(pm_ctx* c, bool need_colw) {
       k_init_assign<true><<<grid, kBlock, 0, c->stream>>>(c->lab8, nullptr, c->deg, c->rowblk, c->fw, c->tb, multi ? Vs : NL,
                                                           (uint32_t)base, (uint32_t)(base + NL), c->S, c->clsc, c->vid, c->adeg, c->rowc, c->fwx,
                                                           use_sig ? c->sig : nullptr, c->fr[0][0], c->fr[0][1], c->cnt, 0,
-                                                          c->typed ? 1 : 0);
+                                                          c->typed ? 1 : 0, hubs_on(c) ? c->hub_ctl : nullptr,
+                                                          hubs_on(c) ? c->hubc : nullptr);
     else
       k_init_assign<false><<<grid, kBlock, 0, c->stream>>>(nullptr, c->cls, c->deg, c->rowblk, c->fw, c->tb, multi ? Vs : NL,
                                                            (uint32_t)base, (uint32_t)(base + NL), c->S, c->clsc, c->vid, c->adeg, c->rowc, c->fwx,
-                                                           nullptr, c->fr[0][0], c->fr[0][1], c->cnt, 0, 0);
+                                                           nullptr, c->fr[0][0], c->fr[0][1], c->cnt, 0, 0, hubs_on(c) ? c->hub_ctl : nullptr,
+                                                           hubs_on(c) ? c->hubc : nullptr);
     PM_LAUNCH_CHECK(c);
     // the DENSE working adjacency: the row of local compact id i starts at the exclusive prefix of the survivors'
     // degrees (in 32-byte sectors, so rows stay sector aligned) — a few hundred million slots instead of the
@@ -903,6 +1083,13 @@ int pm_lcc(pm_ctx* c, int init_step, int* not_finished, pm_counts_t* counts_out)
     // 12 B per scanned vertex (row start, own masks read + written, |E_v|)
     // 6.25 B per scanned slot + 12.25 B per scanned vertex
     c->summary.algorithmic_bytes += sc * 25 / 4 + vs * 49 / 4;
+  }
+  if (hubs_on(c)) {  // the hubs peers hold for this rank's controller role (count files, ee.hpp:1131-1138)
+    if ((rc = hub_rows_merge(c, 0, D, &c->rows[c->rows.size() - D]))) return rc;
+    for (int k = 0; counts_out && k < D; ++k) {
+      counts_out[k].n_vertices = c->rows[c->rows.size() - D + k].n_vertices;
+      counts_out[k].n_edges = c->rows[c->rows.size() - D + k].n_edges;
+    }
   }
   c->step_rows.push_back({c->itr, wall_s() - t0});
   return 0;
@@ -1183,6 +1370,11 @@ int pm_nlcc(pm_ctx* c, int pl, int mode, int* pattern_found, int* token_source_d
       if (multi)
         for (auto& x : c->subgraphs[pl]) x = (uint32_t)vertex_of(c, x);  // slots -> vertex ids
     }
+    if (hubs_on(c) && c->keep_subgraphs) {
+      // the subgraph line is written by the rank that owns the walk's final vertex (tds_batch_1.hpp:684-693): a hub's controller
+      if ((rc = hub_records_exchange(c, c->subgraphs[pl], n, n - 1))) { dev_free(d_matches); return rc; }
+      c->subgraph_count[pl] = c->subgraphs[pl].size() / (size_t)n;
+    }
   }
   dev_free(d_matches);
   if (multi) {
@@ -1212,6 +1404,7 @@ int pm_nlcc(pm_ctx* c, int pl, int mode, int* pattern_found, int* token_source_d
   pm_row_t r;
   r.itr = c->itr; r.kind = 1; r.index = pl;
   r.n_vertices = c->h_rowstat[D].nv; r.n_edges = c->h_rowstat[D].ne; r.seconds = ms * 1e-3;
+  if (hubs_on(c) && (rc = hub_rows_merge(c, D, 1, &r))) return rc;
   c->rows.push_back(r);
   if (counts_out) { counts_out->n_vertices = r.n_vertices; counts_out->n_edges = r.n_edges; counts_out->seconds = r.seconds; }
   if (pattern_found) *pattern_found = found;
@@ -1282,9 +1475,11 @@ int fetch_pairs(pm_ctx* c, bool edges, std::vector<uint2>& host) {
   PM_LAUNCH_CHECK(c);
   PM_CUDA(c, cudaMemcpyAsync(c->h_rowstat + D, c->rowstat + D, sizeof(RowStat), cudaMemcpyDeviceToHost, st));
   PM_CUDA(c, cudaStreamSynchronize(st));
-  const uint64_t n = edges ? c->h_rowstat[D].ne : c->h_rowstat[D].nv;
+  uint64_t n = edges ? c->h_rowstat[D].ne : c->h_rowstat[D].nv;
+  for (int g = 0; g < PM_MAX_RANKS; ++g)  // the hubs this rank holds are counted apart (for their controllers)
+    n += edges ? c->h_rowstat[D].hub_ne[g] : c->h_rowstat[D].hub_nv[g];
   host.resize(n);
-  if (!n) return 0;
+  if (!n && !(hubs_on(c) && !c->fuzzy_ids)) return 0;
   uint2* d_out = nullptr;
   unsigned long long* d_n = nullptr;
   int rc;
@@ -1305,6 +1500,15 @@ int fetch_pairs(pm_ctx* c, bool edges, std::vector<uint2>& host) {
       p.x = (uint32_t)vertex_of(c, p.x);
       if (edges) p.y = (uint32_t)vertex_of(c, p.y);
     }
+  if (hubs_on(c) && !c->fuzzy_ids) {
+    // a hub's rows of the result files belong to its controller rank (beta.cpp:1386-1403 iterate the controller's maps)
+    std::vector<uint32_t> flat(host.size() * 2);
+    for (size_t i = 0; i < host.size(); ++i) { flat[2 * i] = host[i].x; flat[2 * i + 1] = host[i].y; }
+    int rc2 = hub_records_exchange(c, flat, 2, 0);
+    if (rc2) return rc2;
+    host.resize(flat.size() / 2);
+    for (size_t i = 0; i < host.size(); ++i) host[i] = make_uint2(flat[2 * i], flat[2 * i + 1]);
+  }
   std::sort(host.begin(), host.end(), [](const uint2& x, const uint2& y) { return x.x != y.x ? x.x < y.x : x.y < y.y; });
   return 0;
 }
@@ -1733,7 +1937,30 @@ int pm_write_results_ps(const pm_ctx* cc, const char* outdir, int ps_index) {
   // labels of the vertices this rank owns (local row of v = v / n_ranks)
   std::vector<uint64_t> lab(c->nloc);
   PM_CUDA(c, cudaMemcpy(lab.data(), c->label, c->nloc * 8, cudaMemcpyDeviceToHost));
-  for (auto& p : hv) fv << c->rank << ", " << p.x << ", 0, " << lab[p.x / c->n_ranks] << ", " << bitset16(p.y) << "\n";
+  // ... and of the hubs (their rows are written by the controller, which need not hold them): every rank contributes the
+  // labels of the hubs it holds, a max-reduction hands everybody the whole table
+  std::vector<uint64_t> hub_lab(c->hubs.size(), 0);
+  if (hubs_on(c)) {
+    for (size_t i = 0; i < c->hubs.size(); ++i)
+      if ((int)(c->hubs[i] % (uint32_t)c->n_ranks) == c->rank) hub_lab[i] = lab[c->hubs[i] / (uint32_t)c->n_ranks];
+    unsigned long long* d = nullptr;
+    if ((rc = dev_alloc(c, &d, hub_lab.size() + 1))) return rc;
+    cudaMemcpyAsync(d, hub_lab.data(), hub_lab.size() * 8, cudaMemcpyHostToDevice, c->stream);
+    ncclResult_t nr = ncclAllReduce(d, d, hub_lab.size(), ncclUint64, ncclMax, comm_of(c), c->stream);
+    cudaError_t e = cudaMemcpyAsync(hub_lab.data(), d, hub_lab.size() * 8, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    dev_free(d);
+    if (nr != ncclSuccess) return fail(c, PM_ERR_COMM, ncclGetErrorString(nr));
+    if (e != cudaSuccess) return fail(c, PM_ERR_CUDA, cudaGetErrorString(e));
+  }
+  auto label_of = [&](uint32_t v) -> uint64_t {
+    if (hubs_on(c)) {
+      auto it = std::lower_bound(c->hubs.begin(), c->hubs.end(), v);
+      if (it != c->hubs.end() && *it == v) return hub_lab[it - c->hubs.begin()];
+    }
+    return lab[v / c->n_ranks];
+  };
+  for (auto& p : hv) fv << c->rank << ", " << p.x << ", 0, " << label_of(p.x) << ", " << bitset16(p.y) << "\n";
   for (auto& p : he) fe << c->rank << ", " << p.x << ", " << p.y << "\n";
   for (size_t pl = 0; pl < c->pat.constraints.size(); ++pl) {
     std::ofstream fs;

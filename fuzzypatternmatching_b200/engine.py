@@ -87,6 +87,13 @@ class Engine:
         """generate_rmat -s <scale> on <gen_ranks> ranks, on the GPU."""
         self._chk(self._lib.pm_graph_rmat(self._h, scale, gen_ranks))
 
+    def graph_set_delegate_threshold(self, threshold):
+        """hubs = vertices with multigraph out-degree >= threshold; returns their number (collective)"""
+        self._chk(self._lib.pm_graph_set_delegate_threshold(self._h, int(threshold)))
+        n = C.c_uint64(0)
+        self._chk(self._lib.pm_graph_num_delegates(self._h, C.byref(n)))
+        return int(n.value)
+
     def graph_info(self):
         gi = _lib.GraphInfo()
         self._chk(self._lib.pm_graph_info(self._h, C.byref(gi)))

@@ -85,6 +85,14 @@ int pm_graph_rmat(pm_ctx* ctx, uint64_t scale, uint64_t gen_ranks);
 int pm_graph_from_csr(pm_ctx* ctx, uint64_t n_vertices, const uint64_t* rowptr /* n_vertices+1 */,
                       const uint32_t* col, const uint64_t* degree_multi /* n_vertices */);
 
+/* Delegates (generate_rmat / ingest_edge_list -d; include/havoqgt/impl/delegate_partitioned_graph.ipp:501-512): the vertices
+ * whose multigraph out-degree reaches `threshold` are hubs, numbered in ascending vertex order; a hub's controller is
+ * delegate_id % n_ranks (delegate_partitioned_graph.hpp:231-233).  With several ranks the count files and the vertex / edge /
+ * subgraph rows of a hub are attributed to its controller, like a reference run with delegates writes them; the hub's
+ * adjacency itself stays with rank v mod n_ranks (deviations).  0 switches delegates off.  Collective. */
+int pm_graph_set_delegate_threshold(pm_ctx* ctx, uint64_t threshold);
+int pm_graph_num_delegates(const pm_ctx* ctx, uint64_t* n_out);
+
 typedef struct {
   uint64_t n_vertices;      /* global                                  */
   uint64_t n_local;         /* vertices owned by this rank             */

@@ -8,7 +8,7 @@ from fuzzypatternmatching_b200.engine import Engine
 scales = [int(x) for x in sys.argv[1].split(",")]
 gen_ranks = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
 check = len(sys.argv) > 3 and sys.argv[3] == "check"
-pats = bench.write_patterns("cyclic")
+pats = bench.write_patterns(os.environ.get("PM_WORKLOAD", "cyclic"))
 eng = Engine(0)
 for s in scales:
     t = time.time(); eng.graph_rmat(s, gen_ranks); eng.labels_degree_log2(); gi = eng.graph_info()

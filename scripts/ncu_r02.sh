@@ -10,3 +10,4 @@ ncu --set full --clock-control none --import-source on -k regex:'k_lcc_first_pac
 tail -3 gpurun_out/r02_ncu_full_$tag.log
 ncu -i gpurun_out/r02_prof_$tag.ncu-rep --page raw --csv > gpurun_out/r02_prof_${tag}_raw.csv 2>/dev/null
 ls -la gpurun_out/ | tail -8
+timeout 600 python bench.py --scale 22 --gen-ranks 4 --workload hubs --no-cpu-baseline --e2e-steps 0 --steps 5 --warmup 3 > gpurun_out/r02_bench_s22_hubs.log 2>&1; echo "hubs rc=$?"

@@ -1,5 +1,5 @@
-"""Markdown table + traffic.json from an `ncu -i X.ncu-rep --page raw --csv` export of the LCC scan kernels.
-usage: ncu_raw_table.py raw.csv [traffic.json]"""
+"""Markdown table + per-class DRAM traffic from an `ncu -i X.ncu-rep --page raw --csv` export of the hot kernels.
+usage: ncu_raw_table.py raw.csv [traffic.json [workload key]]   (launches under 50 us are left out of the table)"""
 import csv
 import json
 import sys
@@ -15,11 +15,16 @@ SCALE = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-6, "us": 
 
 
 def klass(name):
-    if "k_lcc_scan<1" in name:
+    if "k_lcc_scan<1" in name or "k_lcc_first" in name:
         return "scan_first"
-    if "k_lcc_scan<0, 0, 1" in name:
+    if "k_lcc_scan<0, 0, 1" in name or "k_lcc_xlate8" in name:
         return "scan_xlate"
-    return "scan_later"
+    if "k_lcc_scan" in name:
+        return "scan_later"
+    for k in ("k_nem1_close_cycle", "k_nem1_expand", "k_init_flags", "k_init_assign", "k_lcc_commit"):
+        if k in name:
+            return k
+    return "other"
 
 
 def main():
@@ -36,6 +41,8 @@ def main():
             if c in ix:
                 vals[c] = float(r[ix[c]].replace(",", "")) * SCALE.get(units[ix[c]], 1)
         k = klass(name)
+        if vals.get("gpu__time_duration.sum", 0) < 0.05:
+            continue
         cells = []
         for c, _ in COLS:
             if c not in ix:
@@ -58,7 +65,13 @@ def main():
                "dram_gbs": a["bytes"] / (a["ms"] * 1e-3) / 1e9} for k, a in agg.items()}
     print("\n```json\n" + json.dumps(out, indent=1) + "\n```")
     if len(sys.argv) > 2:
-        json.dump(out, open(sys.argv[2], "w"), indent=1)
+        key = sys.argv[3] if len(sys.argv) > 3 else "rmat_s26_cyclic_n1"
+        try:
+            doc = json.load(open(sys.argv[2]))
+        except Exception:
+            doc = {}
+        doc[key] = out
+        json.dump(doc, open(sys.argv[2], "w"), indent=1)
 
 
 if __name__ == "__main__":

@@ -21,7 +21,23 @@ from fuzzypatternmatching_b200 import patterns as PT  # noqa: E402
 from tests import cases  # noqa: E402
 
 
-def partition_parity(eng, dist, rank, world, name, build_graph, oracle_graph, labels, spec, tds_from, log=print):
+def _oracle_rank_rows(ref, world):
+    """per-rank (vertices, edges) of every row from the count files the oracle writes (beta.cpp:504-535 layout)"""
+    import tempfile
+    from oracle import oracle as O
+    d = tempfile.mkdtemp(prefix="pm_orc_")
+    O.make_result_tree(d)
+    ref.write_results(d)
+    out = []
+    for r in range(world):
+        nv = [int(l.split(",")[-1]) for l in open(os.path.join(d, "0", "all_ranks_active_vertices_count", "active_vertices_%d" % r))]
+        ne = [int(l.split(",")[-1]) for l in open(os.path.join(d, "0", "all_ranks_active_edges_count", "active_edges_%d" % r))]
+        out.append(list(zip(nv, ne)))
+    return out
+
+
+def partition_parity(eng, dist, rank, world, name, build_graph, oracle_graph, labels, spec, tds_from, log=print,
+                     delegate_threshold=0):
     """Collective.  Every rank searches its partition with `eng`; rank 0 compares the per-rank rows, vertex / edge
     lists and enumerated subgraphs with the CPU oracle run with n_ranks = world.  Returns True / False on rank 0
     (None elsewhere).  `dist` is torch.distributed with an initialised group (any backend)."""
@@ -30,6 +46,7 @@ def partition_parity(eng, dist, rank, world, name, build_graph, oracle_graph, la
     dist.broadcast_object_list(box, src=0)
     d = box[0]
     build_graph()
+    n_hubs = eng.graph_set_delegate_threshold(delegate_threshold) if delegate_threshold else 0
     if labels is None:
         eng.labels_degree_log2()
     else:
@@ -49,9 +66,19 @@ def partition_parity(eng, dist, rank, world, name, build_graph, oracle_graph, la
     from oracle import oracle as O
     g = oracle_graph()
     lab = g.labels_degree_log2() if labels is None else labels
-    ref = O.Run(g, lab, O.Pattern(d), n_ranks=world, tds_from_pl=tds_from, max_iterations=50)
+    ref = O.Run(g, lab, O.Pattern(d), n_ranks=world, tds_from_pl=tds_from, max_iterations=50,
+                delegate_threshold=delegate_threshold)
     want = cases.run_summary(ref)
     ok = True
+    # who writes a vertex's rows: v mod ranks, or — for a hub — its controller, delegate id mod ranks
+    hubs = np.nonzero(g.degree >= delegate_threshold)[0].tolist() if delegate_threshold else []
+    ctl = {v: i % world for i, v in enumerate(hubs)}
+    owner = lambda v: ctl.get(v, v % world)  # noqa: E731
+    if delegate_threshold:
+        ok &= n_hubs == len(hubs) and len(hubs) > 0
+        want_rows = _oracle_rank_rows(ref, world)
+        for r, gr in enumerate(got):  # every rank's count file, row by row
+            ok &= [(x[3], x[4]) for x in gr["rows"]] == want_rows[r]
     if labels is None:
         ok &= all(gr["labels"] == lab.tolist() for gr in got)
     # rows: per-rank counts sum to the oracle's totals
@@ -60,10 +87,10 @@ def partition_parity(eng, dist, rank, world, name, build_graph, oracle_graph, la
     ok &= rows == want["rows"]
     ok &= all(gr["iterations"] == want["iterations"] for gr in got)
     for r, gr in enumerate(got):
-        ok &= gr["vertices"] == [x for x in want["vertices"] if x[0] % world == r]
-        ok &= gr["edges"] == [x for x in want["edges"] if x[0] % world == r]
+        ok &= gr["vertices"] == [x for x in want["vertices"] if owner(x[0]) == r]
+        ok &= gr["edges"] == [x for x in want["edges"] if owner(x[0]) == r]
         for pl in range(ncons):
-            ok &= gr["subgraphs"][pl] == [w for w in want["subgraphs"][pl] if w[-1] % world == r]
+            ok &= gr["subgraphs"][pl] == [w for w in want["subgraphs"][pl] if owner(w[-1]) == r]
     log("%-28s %s  rows %d final (%d, %d) subgraphs %s" % (
         name, "ok" if ok else "MISMATCH", len(rows), rows[-1][3] if rows else -1, rows[-1][4] if rows else -1,
         [len(x) for x in want["subgraphs"]]))
@@ -126,9 +153,9 @@ def main():
     eng.comm_init(rank, world, ids[0])
     failures = []
 
-    def check(name, build_graph, oracle_graph, labels, spec, tds_from):
+    def check(name, build_graph, oracle_graph, labels, spec, tds_from, delegate_threshold=0):
         ok = partition_parity(eng, dist, rank, world, name, build_graph, oracle_graph, labels, spec, tds_from,
-                              log=lambda m: print(m, flush=True))
+                              log=lambda m: print(m, flush=True), delegate_threshold=delegate_threshold)
         if rank == 0 and not ok:
             failures.append(name)
 
@@ -160,6 +187,11 @@ def main():
         eng.graph_from_csr(rowptr, col, degm, n_vertices=nv)
     check("rmat%d/host_csr/triangle" % scale, reopen_from_host_csr, lambda: O.Graph.rmat(scale, gen_ranks),
           None, PT.triangle(6, 7, 8), 1)
+    # delegates: hubs (multigraph degree >= threshold) are attributed to their controller ranks in every per-rank output
+    for nm, spec, tds, thr in (("tree", PT.RMAT_LOG2_TREE, 4, 64), ("triangle", PT.triangle(6, 7, 8), 1, 96),
+                               ("cycle4", PT.cycle4(5, 6, 7, 8), 1, 40)):
+        check("delegates%d/rmat%d/%s" % (thr, scale, nm), lambda: eng.graph_rmat(scale, gen_ranks),
+              lambda: O.Graph.rmat(scale, gen_ranks), None, spec, tds, delegate_threshold=thr)
     # the run_fuzzy path over the same partition (unique-label LCC + cycle token passing over the unpruned adjacency)
     def check_fuzzy(name, build_graph, oracle_graph, labels, spec):
         ok = partition_parity_fuzzy(eng, dist, rank, world, name, build_graph, oracle_graph, labels, spec,

@@ -543,8 +543,10 @@ def test_cli_ingest_vertex_metadata_and_pattern_set(oracle, tmp_path):
     assert [r.split(",")[0].strip() for r in rows] == ["0", "1"]
 
 
-def test_cli_two_ranks_write_every_rank_file(oracle, tmp_path):
-    """run_pattern_matching_beta -n 2: one process per GPU, per-rank files *_0 and *_1 equal to a 2-rank oracle run."""
+@pytest.mark.parametrize("threshold", [0, 64])
+def test_cli_two_ranks_write_every_rank_file(oracle, tmp_path, threshold):
+    """run_pattern_matching_beta -n 2: one process per GPU, per-rank files *_0 and *_1 equal to a 2-rank oracle run.
+    threshold: generate_rmat -d — hubs above it appear in their CONTROLLER's files (delegate id mod ranks)."""
     import os
     import subprocess
     import torch
@@ -554,7 +556,8 @@ def test_cli_two_ranks_write_every_rank_file(oracle, tmp_path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     bindir = os.path.join(root, "fuzzypatternmatching_b200", "bin")
     gbase = str(tmp_path / "rmat")
-    subprocess.check_call([os.path.join(bindir, "generate_rmat"), "-s", "17", "-r", "4", "-o", gbase], stdout=subprocess.DEVNULL)
+    subprocess.check_call([os.path.join(bindir, "generate_rmat"), "-s", "17", "-r", "4", "-o", gbase] +
+                          (["-d", str(threshold)] if threshold else []), stdout=subprocess.DEVNULL)
     pdir = str(tmp_path / "pattern")
     PT.write_pattern_dir(pdir, PT.RMAT_LOG2_TREE)
     out_gpu, out_ref = str(tmp_path / "gpu"), str(tmp_path / "ref")
@@ -564,7 +567,8 @@ def test_cli_two_ranks_write_every_rank_file(oracle, tmp_path):
     subprocess.check_call([os.path.join(bindir, "run_pattern_matching_beta"), "-i", gbase, "-p", pdir, "-o", out_gpu, "-n", "2"],
                           stdout=subprocess.DEVNULL, timeout=600)
     g = oracle.Graph.rmat(17, 4)
-    ref = oracle.Run(g, g.labels_degree_log2(), oracle.Pattern(os.path.join(pdir, "0")), n_ranks=2, tds_from_pl=4)
+    ref = oracle.Run(g, g.labels_degree_log2(), oracle.Pattern(os.path.join(pdir, "0")), n_ranks=2, tds_from_pl=4,
+                     delegate_threshold=threshold)
     ref.write_results(out_ref)
     assert _cli_compare(out_gpu, out_ref, 0, 2, [4]) > 0
 

@@ -733,6 +733,12 @@ __global__ void __launch_bounds__(kBlock, 3) k_lcc_first_packed(LccArgs a, uint4
   __shared__ unsigned long long s_vl[kBlock / 32][32];
   __shared__ uint32_t s_rout[kBlock / 32][32];
   __shared__ uint8_t s_nz[kBlock / 32][32];
+  // per label class: the labelmask (T_arr of the first superstep, ee.hpp:541-546) and the labels a valid neighbour
+  // can carry (PatConst::rl) — one byte gather per entry instead of two 16-step loops over the template
+  __shared__ uint16_t s_lm[17];
+  __shared__ unsigned long long s_rl[17];
+  if (threadIdx.x < 17) { s_lm[threadIdx.x] = c_pat.LMc[threadIdx.x]; s_rl[threadIdx.x] = c_pat.rl[threadIdx.x]; }
+  __syncthreads();
   const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const uint32_t lt = lanemask_lt();
   const uint32_t le = lt | (1u << lane);
@@ -746,17 +752,18 @@ __global__ void __launch_bounds__(kBlock, 3) k_lcc_first_packed(LccArgs a, uint4
     const uint32_t idx = base + lane;
     const bool has = idx < n;
     uint4 e = make_uint4(0, 0, 0, 0);
-    uint32_t Tv = 0;
+    uint32_t cl = PM_NOCLASS;
     bool live = false;
     if (has) {
       e = list[idx];
       live = e.y != PM_TOMB;
-      if (live) Tv = a.S[e.x];
+      if (live) cl = a.clsc[e.x];
     }
+    const uint32_t Tv = s_lm[cl];
     const uint32_t d = Tv ? e.z : 0u;
     uint32_t drow = e.y, out = 0;
     if (has && live) drow = a.rowc[e.x - a.base];
-    const unsigned long long VL = valid_labels(nb_of(Tv)) & not_sentinel;
+    const unsigned long long VL = s_rl[cl] & not_sentinel;
     const uint32_t nch = (d + 7u) >> 3;
     uint32_t cum = nch;
 #pragma unroll

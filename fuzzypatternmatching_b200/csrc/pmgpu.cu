@@ -1149,6 +1149,7 @@ int pm_nlcc(pm_ctx* c, int pl, int mode, int* pattern_found, int* token_source_d
     if ((rc = comm_allreduce_u64(c, w, 2, ncclMax))) return rc;
     want_pool = std::max<uint64_t>(std::max<uint64_t>(2 * w[0] + 65536, 1ull << 18), w[1] + 4096);
     want_keys = want_pool;
+    want_pool = std::max<uint64_t>(want_pool, c->nlmax / 8 + 4096);  // the floor of the later calls: grow once, now
   } else if (multi) {
     want_pool = std::max<uint64_t>(c->pool_seen[pl] + c->pool_seen[pl] / 2 + 4096, 1ull << 18);
     want_pool = std::max<uint64_t>(want_pool, c->nlmax / 8 + 4096);  // level 0: sources of this rank, bounded without a reduction

@@ -339,6 +339,8 @@ __global__ void __launch_bounds__(kBlock) k_fz_apply(uint16_t* __restrict__ S, c
 // ---- several ranks: tokens travel through the owners' inboxes (see pm_nlcc_multi.cuh); vertices are SLOTS here ----
 // tokens of the previous hop (inbox par ^ 1) -> hop hn (inbox par of the owners); first: the tokens are the sources
 __global__ void __launch_bounds__(kBlock) k_fz_expand_m(FzArgs a, NlcArgs t, int hn, int first) {
+  __shared__ RouteStage st;
+  route_init(st);
   const TokSrc src = tok_src(t, c_peer.tcap);
   const uint2* __restrict__ in = c_peer.tin[t.par ^ 1][c_peer.rank];
   constexpr int GROUP = 8;
@@ -382,10 +384,11 @@ __global__ void __launch_bounds__(kBlock) k_fz_expand_m(FzArgs a, NlcArgs t, int
 #pragma unroll
       for (int k = 0; k < 4; ++k)
         ins[k] = j0 + k < d && ((l4 >> (8 * k)) & 0xffu) == want_lab && a.S[u[k]] == want_s;
-      route_tokens<2>(t, ins, u, s);
+      route_tokens<2>(t, st, ins, u, s);
     }
     if (has && gl == 0) fan += d;
   }
+  route_finish(t, st);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     fan += __shfl_xor_sync(0xffffffffu, fan, o);

@@ -1295,39 +1295,50 @@ __global__ void __launch_bounds__(kBlock) k_lcc_commit(LccArgs a, const uint4* _
   const uint32_t total = c0 + c1;
   unsigned long long nv = 0, ne = 0;
   constexpr int IT = 4;
+  const bool publish = c_peer.G > 1;  // several ranks: mask changes go to the peers' delta inboxes
   const uint32_t tile = blockDim.x * IT;
   for (uint32_t base = blockIdx.x * tile; base < total; base += gridDim.x * tile) {
     bool alive[IT];
     int bin[IT];
     uint4 val[IT];
+    uint32_t was[IT];
+    // all loads of the tile first: the stores to S below may alias the loads of the next item as far as the compiler
+    // knows, which would chain the items' load latencies one behind the other
 #pragma unroll
     for (int k = 0; k < IT; ++k) {
       const uint32_t i = base + k * blockDim.x + threadIdx.x;
+      val[k] = make_uint4(0, PM_TOMB, 0, 0);
+      was[k] = 0;
+      if (i < total) {
+        val[k] = i < c0 ? l0[i] : l1[i - c0];
+        if (publish && val[k].y != PM_TOMB) was[k] = a.S[val[k].x];  // peers only need the changes
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < IT; ++k) {
       alive[k] = false;
       bin[k] = 0;
-      val[k] = make_uint4(0, 0, 0, 0);
       bool changed = false;
       uint32_t cslot = 0, cmask = 0;
-      if (i < total) {
-        const uint4 e = i < c0 ? l0[i] : l1[i - c0];
-        if (e.y != PM_TOMB) {
-          const uint32_t ts = e.w, d = e.z;
-          cslot = e.x;
-          cmask = ts;
-          if (c_peer.G > 1) changed = ts != a.S[cslot];  // peers only need the changes
-          a.S[cslot] = (uint16_t)ts;
-          a.adeg[e.x - a.base] = d;
-          alive[k] = ts != 0;
-          const uint32_t hc = a.hubc ? (uint32_t)a.hubc[e.x - a.base] : 0u;
-          if (alive[k] && hc) {  // a hub: its row of the count files belongs to its controller
-            atomicAdd(&a.row->hub_nv[hc - 1u], 1ull);
-            atomicAdd(&a.row->hub_ne[hc - 1u], (unsigned long long)d);
-          } else if (alive[k]) { nv++; ne += d; }
-          bin[k] = bin_of(d);
-          val[k] = e;
-        }
+      const uint4 e = val[k];
+      if (e.y != PM_TOMB) {
+        const uint32_t ts = e.w, d = e.z;
+        cslot = e.x;
+        cmask = ts;
+        changed = publish && ts != was[k];
+        a.S[cslot] = (uint16_t)ts;
+        a.adeg[e.x - a.base] = d;
+        alive[k] = ts != 0;
+        const uint32_t hc = a.hubc ? (uint32_t)a.hubc[e.x - a.base] : 0u;
+        if (alive[k] && hc) {  // a hub: its row of the count files belongs to its controller
+          atomicAdd(&a.row->hub_nv[hc - 1u], 1ull);
+          atomicAdd(&a.row->hub_ne[hc - 1u], (unsigned long long)d);
+        } else if (alive[k]) { nv++; ne += d; }
+        bin[k] = bin_of(d);
+      } else {
+        val[k] = make_uint4(0, 0, 0, 0);
       }
-      if (c_peer.G > 1) publish_mask(changed, cslot, cmask, a.cnt, a.par);
+      if (publish) publish_mask(changed, cslot, cmask, a.cnt, a.par);
     }
     block_append2<IT>(alive, bin, val, n0, n1, &a.cnt->fr_n[nxt][0]);
   }

@@ -69,42 +69,71 @@ __device__ __forceinline__ void mark_edge_m(uint32_t s, uint32_t parent) {
   if (lo < d && (cw[row + lo] & PM_IDMASK) == parent) atomicOr(&cw[row + lo], 0x80000000u);
 }
 
-// One warp appends its accepted tokens to the inbox regions of their owners.  All 32 lanes call.
-// Positions come from this rank's own counters (cnt->out_n[g]); the stores go over NVLink.
+// Routing of accepted tokens to the inbox regions of their owners.  Every warp stages its tokens per destination
+// in shared memory and only when a destination's buffer runs full reserves inbox room — ONE atomicAdd on this rank's
+// counter cnt->out_n[g] for up to kRouteCap tokens (a counter per destination is a single address: reserving per
+// warp pass serialised several hundred thousand atomics per hop in the L2) — and stores the batch as whole
+// 256-byte lines over NVLink.  All 32 lanes call; route_finish() at the end of the kernel drains the buffers.
 // DEST 0: the records go to the owner of the compact id u; 1: to the owner of the SOURCE s (closing requests,
 // k_close_check_m); 2: u names a SLOT (run_fuzzy path), owner = u / nlmax
+constexpr int kRouteCap = 64;
+struct RouteStage {
+  uint2 buf[kBlock / 32][PM_MAX_RANKS][kRouteCap];
+  uint32_t fill[kBlock / 32][PM_MAX_RANKS];
+};
+
+__device__ __forceinline__ void route_init(RouteStage& st) {
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane < PM_MAX_RANKS) st.fill[wid][lane] = 0u;
+  __syncwarp();
+}
+
+__device__ __forceinline__ void route_flush(const NlcArgs& a, RouteStage& st, int g) {
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint32_t n = st.fill[wid][g];
+  if (n == 0u) return;  // the same value in every lane
+  unsigned long long basep = 0;
+  if (lane == 0) basep = atomicAdd(&a.cnt->out_n[g], (unsigned long long)n);
+  basep = __shfl_sync(0xffffffffu, basep, 0);
+  uint2* __restrict__ dst = c_peer.tin[a.par][g] + (unsigned long long)c_peer.rank * c_peer.tcap;
+  for (uint32_t i = lane; i < n; i += 32) {
+    const unsigned long long pos = basep + i;
+    if (pos < c_peer.tcap) dst[pos] = st.buf[wid][g][i];
+    else a.cnt->overflow = 1u;
+  }
+  __syncwarp();
+  if (lane == 0) st.fill[wid][g] = 0u;
+  __syncwarp();
+}
+
 template <int DEST = 0>
-__device__ __forceinline__ void route_tokens(const NlcArgs& a, const bool (&flag)[4], const uint32_t (&u)[4], uint32_t s) {
-  const uint32_t lane = threadIdx.x & 31;
+__device__ __forceinline__ void route_tokens(const NlcArgs& a, RouteStage& st, const bool (&flag)[4], const uint32_t (&u)[4], uint32_t s) {
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const uint32_t lt = (1u << lane) - 1u;
-  uint32_t dest[4];
   const uint32_t so = DEST == 1 ? cid_owner(s) : 0u;
 #pragma unroll
-  for (int k = 0; k < 4; ++k)
-    dest[k] = flag[k] ? (DEST == 1 ? so : DEST == 2 ? u[k] / c_peer.nlmax : cid_owner(u[k])) : 0xFFFFFFFFu;
-  for (int g = 0; g < c_peer.G; ++g) {
-    uint32_t m[4], total = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      m[k] = __ballot_sync(0xffffffffu, dest[k] == (uint32_t)g);
-      total += __popc(m[k]);
-    }
-    if (total == 0) continue;
-    // order inside the warp: (k, lane)
-    unsigned long long basep = 0;
-    if (lane == 0) basep = atomicAdd(&a.cnt->out_n[g], (unsigned long long)total);
-    basep = __shfl_sync(0xffffffffu, basep, 0);
-    uint32_t before = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (dest[k] == (uint32_t)g) {
-        const unsigned long long pos = basep + before + __popc(m[k] & lt);
-        if (pos < c_peer.tcap) c_peer.tin[a.par][g][(unsigned long long)c_peer.rank * c_peer.tcap + pos] = make_uint2(u[k], s);
-        else a.cnt->overflow = 1u;
+  for (int k = 0; k < 4; ++k) {
+    if (__ballot_sync(0xffffffffu, flag[k]) == 0u) continue;
+    const uint32_t dest = flag[k] ? (DEST == 1 ? so : DEST == 2 ? u[k] / c_peer.nlmax : cid_owner(u[k])) : 0xFFFFFFFFu;
+    for (int g = 0; g < c_peer.G; ++g) {
+      const uint32_t m = __ballot_sync(0xffffffffu, dest == (uint32_t)g);
+      if (m == 0u) continue;
+      const uint32_t add = __popc(m);
+      uint32_t fill = st.fill[wid][g];
+      if (fill + add > (uint32_t)kRouteCap) {
+        route_flush(a, st, g);
+        fill = 0u;
       }
-      before += __popc(m[k]);
+      if (dest == (uint32_t)g) st.buf[wid][g][fill + __popc(m & lt)] = make_uint2(u[k], s);
+      __syncwarp();
+      if (lane == 0) st.fill[wid][g] = fill + add;
+      __syncwarp();
     }
   }
+}
+
+__device__ __forceinline__ void route_finish(const NlcArgs& a, RouteStage& st) {
+  for (int g = 0; g < c_peer.G; ++g) route_flush(a, st, g);
 }
 
 // ---------------------------------------------------------------------------
@@ -238,98 +267,105 @@ __device__ __forceinline__ bool close_edge_known(const NlcArgs& a, uint32_t s, u
 //   duplicates cannot occur (hop 1) or cannot matter (the level feeding the closing mode, up to hop 2)
 template <int MODE>
 __global__ void __launch_bounds__(kBlock) k_nem1_hop_m(NlcArgs a, int hn, int first) {
+  __shared__ RouteStage st;
+  route_init(st);
   const TokSrc src = tok_src(a, c_peer.tcap);
   const uint2* __restrict__ in = c_peer.tin[a.par ^ 1][c_peer.rank];
-  constexpr int GROUP = 8;
+  constexpr int GROUP = 4;         // lanes per token: 16 slots of its row per pass (the pruned rows are short)
+  constexpr int TPW = 32 / GROUP;  // tokens per warp and iteration
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t gl = lane % GROUP, gw = lane / GROUP;
   const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
   unsigned long long fan = 0, accepted = 0;
-  for (uint64_t base = warp * 4; base < src.total; base += nwarps * 4) {
-    const uint64_t t = base + gw;
-    bool has = t < src.total;
-    uint32_t v = 0, s = 0, d = 0;
-    uint32_t fresh = 1;
-    if (has) {
-      const uint2 tk = in[tok_locate(src, t, c_peer.tcap)];
-      v = tk.x;
-      s = tk.y;
+  for (uint64_t base = warp * 32; base < src.total; base += nwarps * 32) {
+    // every lane picks up ONE token: 32 independent chains token -> aggregation -> row header are in flight per warp
+    // (a group of lanes per token would serialise them eight at a time); the rows are then walked TPW tokens at a time
+    const uint64_t tl = base + lane;
+    uint32_t v_l = 0, s_l = 0, d_l = 0, rb_l = 0;
+    if (tl < src.total) {
+      const uint2 tk = in[tok_locate(src, tl, c_peer.tcap)];
       // work aggregation at the receiver: one token per (vertex, source) (nem_1.hpp:131-139, 270-285)
-      if (!first && gl == 0) fresh = hset_insert(a, v, s) ? 1u : 0u;
-    }
-    fresh = __shfl_sync(0xffffffffu, fresh, gw * GROUP);
-    if (!fresh) has = false;
-    if (has) {
-      d = a.adeg[v - a.base];
-      if (gl == 0) accepted++;
-      if (MODE == 1 && !c_nlc.valid_cycle && a.ok[s]) d = 0;  // acknowledged path source: later tokens are moot
-      if (MODE == 2 || MODE == 3) {
-        const uint32_t ss = a.S[s];
-        if (ss == 0 || !hop_ok(ss, a.cls[s], hn + 1)) d = 0;  // receiver tests of the closing hop at the source
-      }
-    }
-    const uint64_t row = has ? (uint64_t)a.rowblk[v - a.base] * 8 : 0;
-    const uint32_t passes = (d + GROUP * 4 - 1) / (GROUP * 4);
-    const uint32_t maxp = __reduce_max_sync(0xffffffffu, passes);
-    for (uint32_t p = 0; p < maxp; ++p) {
-      const uint32_t j0 = p * GROUP * 4 + gl * 4;
-      uint4 q = make_uint4(0, 0, 0, 0);
-      if (j0 < d) {
-        q = *reinterpret_cast<const uint4*>(a.colw + row + j0);
-      }
-      const uint32_t u[4] = {q.x & PM_IDMASK, q.y & PM_IDMASK, q.z & PM_IDMASK, q.w & PM_IDMASK};
-      bool pass[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        pass[k] = false;
-        bool may = j0 + k < d;
-        if (MODE == 2) may = may && u[k] != s;
-        if (!may) continue;
-        if (MODE == 2) {
-          // u must be a qualifying neighbour of the source: one probe of the closing-edge set (which
-          // already holds the label / template-bit tests of hop C, evaluated by the owner of s); the template
-          // bit of u is tested first — a gather from the L2 resident mask replica that spares most probes
-          const uint32_t su = a.S[u[k]];
-          pass[k] = su != 0 && ((su >> c_nlc.I[hn]) & 1u) && close_edge_known(a, s, u[k]);
-          if (pass[k]) {
-            ack_source(a, s);
-            a.cnt->found = 1u;
-            mark_edge_m(s, u[k]);  // rare: only completed cycles get here
-          }
-          continue;
+      if (first || hset_insert(a, tk.x, tk.y)) {
+        v_l = tk.x;
+        s_l = tk.y;
+        d_l = a.adeg[v_l - a.base];
+        rb_l = a.rowblk[v_l - a.base];
+        accepted++;
+        if (MODE == 1 && !c_nlc.valid_cycle && a.ok[s_l]) d_l = 0;  // acknowledged path source: later tokens are moot
+        if (MODE == 2 || MODE == 3) {
+          const uint32_t ss = a.S[s_l];
+          if (ss == 0 || !hop_ok(ss, a.cls[s_l], hn + 1)) d_l = 0;  // receiver tests of the closing hop at the source
         }
-        const uint32_t su = a.S[u[k]];
-        pass[k] = su != 0 && ((su >> c_nlc.I[hn]) & 1u);
+        fan += d_l;
       }
-      if (MODE == 3) {
-        // closing two hops of a cycle, routed: every neighbour u of v that passes the tests of the last interior hop
-        // becomes a closing request (u, s) for the owner of s, who looks u up in E_s (k_close_check_m)
-        bool req[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) req[k] = pass[k] && u[k] != s;  // the source cannot relay (nem_1.hpp:174-177)
-        route_tokens<1>(a, req, u, s);
-      }
-      if (MODE == 1) {
+    }
+    for (int sub = 0; sub < GROUP; ++sub) {
+      const int from = sub * TPW + (int)gw;
+      const uint32_t v = __shfl_sync(0xffffffffu, v_l, from), s = __shfl_sync(0xffffffffu, s_l, from);
+      const uint32_t d = __shfl_sync(0xffffffffu, d_l, from);
+      const uint64_t row = (uint64_t)__shfl_sync(0xffffffffu, rb_l, from) * 8;
+      const uint32_t passes = (d + GROUP * 4 - 1) / (GROUP * 4);
+      const uint32_t maxp = __reduce_max_sync(0xffffffffu, passes);
+      for (uint32_t p = 0; p < maxp; ++p) {
+        const uint32_t j0 = p * GROUP * 4 + gl * 4;
+        uint4 q = make_uint4(0, 0, 0, 0);
+        if (j0 < d) {
+          q = *reinterpret_cast<const uint4*>(a.colw + row + j0);
+        }
+        const uint32_t u[4] = {q.x & PM_IDMASK, q.y & PM_IDMASK, q.z & PM_IDMASK, q.w & PM_IDMASK};
+        bool pass[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const bool succ = pass[k] && (c_nlc.valid_cycle ? u[k] == s : u[k] != s);
-          if (succ) {
-            ack_source(a, s);
-            a.cnt->found = 1u;
-            if (c_nlc.valid_cycle) mark_edge_m(s, v);
+          pass[k] = false;
+          bool may = j0 + k < d;
+          if (MODE == 2) may = may && u[k] != s;
+          if (!may) continue;
+          if (MODE == 2) {
+            // u must be a qualifying neighbour of the source: one probe of the closing-edge set (which
+            // already holds the label / template-bit tests of hop C, evaluated by the owner of s); the template
+            // bit of u is tested first — a gather from the L2 resident mask replica that spares most probes
+            const uint32_t su = a.S[u[k]];
+            pass[k] = su != 0 && ((su >> c_nlc.I[hn]) & 1u) && close_edge_known(a, s, u[k]);
+            if (pass[k]) {
+              ack_source(a, s);
+              a.cnt->found = 1u;
+              mark_edge_m(s, u[k]);  // rare: only completed cycles get here
+            }
+            continue;
           }
+          const uint32_t su = a.S[u[k]];
+          pass[k] = su != 0 && ((su >> c_nlc.I[hn]) & 1u);
         }
-      } else if (MODE == 0) {
-        bool ins[4];
+        if (MODE == 3) {
+          // closing two hops of a cycle, routed: every neighbour u of v that passes the tests of the last interior hop
+          // becomes a closing request (u, s) for the owner of s, who looks u up in E_s (k_close_check_m)
+          bool req[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) ins[k] = pass[k] && u[k] != s;  // the source cannot relay (nem_1.hpp:174-177)
-        // one source per group: lanes of a group share s, lanes of different groups do not
-        route_tokens(a, ins, u, s);
+          for (int k = 0; k < 4; ++k) req[k] = pass[k] && u[k] != s;  // the source cannot relay (nem_1.hpp:174-177)
+          route_tokens<1>(a, st, req, u, s);
+        }
+        if (MODE == 1) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const bool succ = pass[k] && (c_nlc.valid_cycle ? u[k] == s : u[k] != s);
+            if (succ) {
+              ack_source(a, s);
+              a.cnt->found = 1u;
+              if (c_nlc.valid_cycle) mark_edge_m(s, v);
+            }
+          }
+        } else if (MODE == 0) {
+          bool ins[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) ins[k] = pass[k] && u[k] != s;  // the source cannot relay (nem_1.hpp:174-177)
+          // one source per group: lanes of a group share s, lanes of different groups do not
+          route_tokens(a, st, ins, u, s);
+        }
       }
     }
-    if (has && gl == 0) fan += d;
   }
+  if (MODE == 0 || MODE == 3) route_finish(a, st);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     fan += __shfl_xor_sync(0xffffffffu, fan, o);

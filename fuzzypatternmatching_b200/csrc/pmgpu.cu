@@ -953,6 +953,7 @@ int pm_lcc(pm_ctx* c, int init_step, int* not_finished, pm_counts_t* counts_out)
   const bool ts_known = c->filter_done;  // ... and the signature filter already settled every entry's T_state
   const bool packed = c->col_shift != 0; // ... inside the col0 slots themselves (else in the parallel byte array lab0)
   const double t0 = wall_s();
+  const bool dbg_steps = getenv("PM_DEBUG_LCC") != nullptr && !c->fused01;  // per-superstep split of the row times on stderr
   PM_CUDA(c, cudaMemsetAsync(c->rowstat, 0, D * sizeof(RowStat), st));
   PM_CUDA(c, cudaMemsetAsync(&c->cnt->nf, 0, sizeof(uint32_t), st));
   for (int k = 0; k < D; ++k) {  // fixed superstep count (ee.hpp:1069)
@@ -1008,6 +1009,7 @@ int pm_lcc(pm_ctx* c, int init_step, int* not_finished, pm_counts_t* counts_out)
     c->kev2_cls[k] = cls_main;
     k_lcc_commit<<<grid, kBlock, 0, st>>>(a, c->fr[cur][0], c->fr[cur][1], c->fr[nxt][0], c->fr[nxt][1], cur, nxt);
     PM_LAUNCH_CHECK(c);
+    if (dbg_steps) PM_CUDA(c, cudaEventRecord(ev[3], st));
     c->cur = nxt;
     if (c->n_ranks > 1) {
       // the commit stored this rank's mask changes into every peer's delta inbox; the StepMsg
@@ -1041,6 +1043,18 @@ int pm_lcc(pm_ctx* c, int init_step, int* not_finished, pm_counts_t* counts_out)
   if (removed && not_finished) *not_finished = 1;
   {
     for (int b = 0; b < 2; ++b) c->bin_live[b] = c->h_cnt->fr_n[c->cur][b] != 0;
+  }
+  if (dbg_steps) {
+    fprintf(stderr, "[pm] rank %d lcc itr %d init %.3f scan/commit/barrier+deltas ms:", c->rank, (int)c->itr, init_step ? c->init_ms : 0.f);
+    for (int k = 0; k < D; ++k) {
+      const cudaEvent_t* ev = &c->kev2[(size_t)k * 4];
+      float a_ms = 0, b_ms = 0, c_ms = 0;
+      cudaEventElapsedTime(&a_ms, c->events[k], c->kev2_big[k] ? ev[2] : ev[1]);
+      cudaEventElapsedTime(&b_ms, c->kev2_big[k] ? ev[2] : ev[1], ev[3]);
+      cudaEventElapsedTime(&c_ms, ev[3], c->events[k + 1]);
+      fprintf(stderr, " %.3f/%.3f/%.3f", a_ms, b_ms, c_ms);
+    }
+    fprintf(stderr, "\n");
   }
   for (int k = 0; k < D; ++k) {
     float ms = 0;

@@ -1,0 +1,2 @@
+// boost/bind.hpp — included by the driver, nothing of it is used on this path.
+#pragma once

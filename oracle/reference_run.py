@@ -1,0 +1,93 @@
+"""Runs the reference's own driver (oracle/_ref/run_pattern_matching_beta: src/run_pattern_matching_beta.cpp and the
+visitor headers it includes, compiled from /root/reference over the single-rank runtime stand-in of oracle/ref_shim) on an
+input and returns its result files in the comparable form the tests use.  TEST INFRASTRUCTURE, like everything under oracle/.
+
+The binary exists only where the reference tree was present when `make -C oracle ref` ran (the build container); it travels to
+the GPU box with the repository snapshot.  available() says whether it can be used."""
+import os
+import shutil
+import subprocess
+import tempfile
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+BINARY = os.path.join(_HERE, "_ref", "run_pattern_matching_beta")
+REFERENCE = "/root/reference"
+
+_TREE = ("all_ranks_active_vertices", "all_ranks_active_vertices_count", "all_ranks_active_edges",
+         "all_ranks_active_edges_count", "all_ranks_messages", "all_ranks_subgraphs", "all_ranks_vertex_data")
+
+
+def build():
+    """compiles the binary if the reference tree is here; returns its path or None"""
+    if os.path.isdir(os.path.join(REFERENCE, "src")):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "ref", "REFERENCE=" + REFERENCE])
+    return BINARY if os.path.exists(BINARY) else None
+
+
+def available():
+    return os.path.exists(BINARY) and os.access(BINARY, os.X_OK)
+
+
+def write_slot_file(path, n_vertices, src, dst):
+    """the text graph the stand-in's distributed_db reads: vertex count, then one directed slot per line"""
+    with open(path, "w") as f:
+        f.write("%d\n" % n_vertices)
+        f.write("".join("%d %d\n" % st for st in zip(src, dst)))
+
+
+def run(n_vertices, src, dst, pattern_dir, labels=None, workdir=None, timeout=600):
+    """pattern_dir: the directory that holds the pattern set (<pattern_dir>/0/pattern_*).  labels: None = the reference's own
+    degree labels (vertex_data_db_degree.hpp), else one value per vertex, passed through its -v metadata loader.
+    Returns dict(rows, iterations, vertices, edges, subgraphs, stdout) — the same keys as tests.cases.run_summary."""
+    own = workdir is None
+    work = tempfile.mkdtemp(prefix="pmref_") if own else workdir
+    try:
+        graph = os.path.join(work, "graph.slots")
+        write_slot_file(graph, n_vertices, src, dst)
+        out = os.path.join(work, "out")
+        for d in _TREE:
+            os.makedirs(os.path.join(out, "0", d), exist_ok=True)
+        cmd = [BINARY, "-i", graph, "-p", pattern_dir, "-o", out]
+        if labels is not None:
+            vdir = os.path.join(work, "vertex_data")
+            os.makedirs(vdir)
+            with open(os.path.join(vdir, "labels_0"), "w") as f:
+                f.write("".join("%d %d\n" % (v, int(l)) for v, l in enumerate(labels)))
+            cmd += ["-v", os.path.join(vdir, "labels")]
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+        if p.returncode != 0:
+            raise RuntimeError("reference driver failed (%d): %s" % (p.returncode, p.stderr[-2000:]))
+        res = parse_result_tree(out)
+        res["stdout"] = p.stdout
+        return res
+    finally:
+        if own:
+            shutil.rmtree(work, ignore_errors=True)
+
+
+def parse_result_tree(out, ps=0, rank=0):
+    """result files of one rank (src/run_pattern_matching_beta.cpp:504-535, 1094-1138, 1375-1425) -> comparable view"""
+    base = os.path.join(out, str(ps))
+
+    def lines(rel):
+        p = os.path.join(base, rel)
+        return [l for l in open(p).read().splitlines() if l.strip()] if os.path.exists(p) else []
+
+    # count files: "itr, LP|TP, index, count" per row, vertices and edges in the same row order
+    vc = [[t.strip() for t in l.split(",")] for l in lines("all_ranks_active_vertices_count/active_vertices_%d" % rank)]
+    ec = [[t.strip() for t in l.split(",")] for l in lines("all_ranks_active_edges_count/active_edges_%d" % rank)]
+    assert [r[:3] for r in vc] == [r[:3] for r in ec], "count files disagree on their rows"
+    rows = [(int(a[0]), a[1], int(a[2]), int(a[3]), int(b[3])) for a, b in zip(vc, ec)]
+    # vertices: "rank, vertex, pattern index, label, bitset"; edges: "rank, vertex, neighbour"
+    vertices = sorted((int(t[1]), int(t[4].strip(), 2)) for t in (l.split(",") for l in lines("all_ranks_active_vertices/active_vertices_%d" % rank)))
+    edges = sorted((int(t[1]), int(t[2])) for t in (l.split(",") for l in lines("all_ranks_active_edges/active_edges_%d" % rank)))
+    subgraphs = {}
+    sdir = os.path.join(base, "all_ranks_subgraphs")
+    for name in sorted(os.listdir(sdir)) if os.path.isdir(sdir) else []:
+        parts = name.split("_")
+        if len(parts) == 3 and parts[0] == "subgraphs" and int(parts[2]) == rank:
+            # "[rank], v0, v1, ..., v_last, [v_last]" per completed walk (tds_batch_1.hpp:684-693)
+            subgraphs[int(parts[1])] = sorted(tuple(int(x) for x in l.replace(",", " ").split() if not x.startswith("["))
+                                              for l in lines("all_ranks_subgraphs/" + name))
+    itr = [l for l in lines("result_iteration")]
+    return dict(rows=rows, iterations=len(itr), vertices=vertices, edges=edges, subgraphs=subgraphs)

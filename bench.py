@@ -172,6 +172,69 @@ def cpu_reference(scale, gen_ranks, pats, steps, warmup, budget_s=150.0):
             "steps_done": len(times), "cores": threads, "scale": scale, "edges_per_step": edges}
 
 
+def cpu_reference_binary(scale, gen_ranks, workload, steps, warmup, budget_s=150.0):
+    """The reference's OWN code for the same templates: oracle/_ref/run_pattern_matching_beta — the reference driver and
+    visitor headers compiled from /root/reference over the single-rank runtime stand-in of oracle/ref_shim (the binary
+    travels with the repository).  One rank is all that runtime gives a process, so the host cores are used the way an
+    MPI job would use them, minus the communication: one independent instance per host thread, each searching its own
+    copy of the sample graph; the value is the aggregate.  Returns None where the binary is absent."""
+    from oracle import oracle as O
+    from oracle import reference_run as R
+    if not R.available():
+        return None
+    import shutil
+    import numpy as np
+    copies = host_threads()
+    work = tempfile.mkdtemp(prefix="pm_bench_ref_")
+    try:
+        per = (16 << scale) // gen_ranks
+        edges = np.concatenate([O.rmat_stream(scale, r, per) for r in range(gen_ranks)])
+        both = np.empty((2 * len(edges), 2), dtype=np.uint64)  # "(s, t) then (t, s)" per generated edge, like ingest -u 1
+        both[0::2] = edges
+        both[1::2] = edges[:, ::-1]
+        graph = os.path.join(work, "graph.slots")
+        with open(graph, "w") as f:
+            f.write("%d\n" % (1 << scale))
+            np.savetxt(f, both, fmt="%d")
+        pdirs = []
+        for name, spec in WORKLOADS[workload]:
+            spec4, _ = R.tds_at_constraint_4(spec)
+            pdirs.append(os.path.dirname(PT.write_pattern_dir(os.path.join(work, "pattern_" + name), spec4)))
+        run_no = [0]
+
+        def one_step():
+            total = 0.0
+            for pd in pdirs:
+                procs = []
+                for c in range(copies):
+                    run_no[0] += 1
+                    procs.append(R.launch(graph, pd, os.path.join(work, "out_%d" % (run_no[0] % (2 * copies)))))
+                slowest = 0.0
+                for p in procs:
+                    out, err = p.communicate()
+                    if p.returncode != 0:
+                        raise RuntimeError("reference driver failed: " + err[-500:])
+                    slowest = max(slowest, R.search_seconds(out))
+                total += slowest
+            return total
+
+        t_begin = time.time()
+        for _ in range(warmup):
+            one_step()
+            if time.time() - t_begin > budget_s / 3:
+                break
+        times = []
+        for _ in range(steps):
+            times.append(one_step())
+            if time.time() - t_begin > budget_s:
+                break
+        edges_per_step = 2 * len(edges) * len(pdirs)
+        return {"value": copies * edges_per_step * len(times) / sum(times), "seconds_per_step": sum(times) / len(times),
+                "steps_done": len(times), "cores": copies, "scale": scale, "edges_per_step": edges_per_step, "copies": copies}
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -182,6 +245,8 @@ def main():
     ap.add_argument("--gen-ranks", type=int, default=1024, help="generating ranks of the R-MAT stream (part of the graph's identity)")
     ap.add_argument("--workload", default="cyclic", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-scale", type=int, default=int(os.environ.get("PM_BENCH_CPU_SCALE", "20")))
+    ap.add_argument("--ref-scale", type=int, default=int(os.environ.get("PM_BENCH_REF_SCALE", "16")),
+                    help="R-MAT scale of the sample the reference's own binary (oracle/_ref) is timed on")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -204,20 +269,39 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        cpu_scale = min(scale, args.cpu_scale)
-        cpu_gen = min(args.gen_ranks, 4) if cpu_scale != scale else args.gen_ranks
-        r = cpu_reference(cpu_scale, cpu_gen, pats, args.steps, max(args.warmup, 1))
-        sample = ("oracle port of the reference CPU path, R-MAT scale %d with %d generating ranks (bounded sample of the "
-                  "scale-%d workload), same templates, %d host threads" % (cpu_scale, cpu_gen, scale, r["cores"]))
+        # the reference's own code where its binary is here (oracle/_ref, built in the container that holds the reference
+        # tree and shipped with the repository); PM_BENCH_REF_PORT=1 or a missing / failing binary: the oracle port
+        r, kind = None, "reference"
+        if os.environ.get("PM_BENCH_REF_PORT", "0") != "1":
+            try:
+                cpu_scale, cpu_gen = min(scale, args.ref_scale), 4
+                r = cpu_reference_binary(cpu_scale, cpu_gen, args.workload, args.steps, max(args.warmup, 1))
+            except Exception as e:  # noqa: BLE001 — the arm must still print its line
+                print("reference binary leg failed, falling back to the oracle port: %s" % e, file=sys.stderr)
+                r = None
+        if r is not None:
+            sample = ("the reference's own driver + visitor headers (oracle/_ref/run_pattern_matching_beta, single-rank runtime "
+                      "stand-in oracle/ref_shim), %d independent instances (one per host thread), each on R-MAT scale %d with %d "
+                      "generating ranks (bounded sample of the scale-%d workload), same templates; its own clock around each "
+                      "template's search loop, slowest instance per template" % (r["copies"], cpu_scale, cpu_gen, scale))
+            par = "independent_single_rank_instances_x%d" % r["copies"]
+        else:
+            kind = "port"
+            cpu_scale = min(scale, args.cpu_scale)
+            cpu_gen = min(args.gen_ranks, 4) if cpu_scale != scale else args.gen_ranks
+            r = cpu_reference(cpu_scale, cpu_gen, pats, args.steps, max(args.warmup, 1))
+            sample = ("oracle port of the reference CPU path, R-MAT scale %d with %d generating ranks (bounded sample of the "
+                      "scale-%d workload), same templates, %d host threads" % (cpu_scale, cpu_gen, scale, r["cores"]))
+            par = "openmp_x%d" % r["cores"]
         # the config states what RAN; the workload it samples stays named beside it
         config.update({"scale": cpu_scale, "gen_ranks": cpu_gen, "directed_edge_slots": r["edges_per_step"] // len(pats),
                        "sample_of": {"workload": config["workload"], "scale": scale, "gen_ranks": args.gen_ranks},
-                       "parallelism": "openmp_x%d" % r["cores"]})
+                       "parallelism": par})
         line = {"impl": "reference", "metric": metric, "value": r["value"], "unit": unit, "n_gpus": args.gpus,
                 "steps": r["steps_done"], "warmup": args.warmup, "ms_per_step": r["seconds_per_step"] * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16",
                 "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": r["value"], "unit": unit, "cores": r["cores"], "kind": "port", "sample": sample},
+                "cpu_baseline": {"value": r["value"], "unit": unit, "cores": r["cores"], "kind": kind, "sample": sample},
                 "e2e": {"value": r["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line))
@@ -445,11 +529,25 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cs = min(scale, args.cpu_scale)
-        r = cpu_reference(cs, 4 if cs != scale else args.gen_ranks, pats, 2, 1, budget_s=60.0)
-        cpu = {"value": r["value"], "unit": unit, "cores": r["cores"], "kind": "port",
-               "sample": "oracle port (reference binary needs MPI+Boost, unbuildable here) on R-MAT scale %d, same "
-                         "templates, %d steps, %d host threads" % (cs, r["steps_done"], r["cores"])}
+        r = None
+        if os.environ.get("PM_BENCH_REF_PORT", "0") != "1":
+            try:
+                cs = min(scale, args.ref_scale)
+                r = cpu_reference_binary(cs, 4, args.workload, 2, 1, budget_s=45.0)
+            except Exception as e:  # noqa: BLE001 — the bench line must still be printed
+                print("reference binary leg failed, falling back to the oracle port: %s" % e, file=sys.stderr)
+                r = None
+        if r is not None:
+            cpu = {"value": r["value"], "unit": unit, "cores": r["cores"], "kind": "reference",
+                   "sample": "the reference's own driver + visitor headers (oracle/_ref, single-rank runtime stand-in), %d "
+                             "independent instances (one per host thread) on R-MAT scale %d, same templates, %d steps"
+                             % (r["copies"], cs, r["steps_done"])}
+        else:
+            cs = min(scale, args.cpu_scale)
+            r = cpu_reference(cs, 4 if cs != scale else args.gen_ranks, pats, 2, 1, budget_s=60.0)
+            cpu = {"value": r["value"], "unit": unit, "cores": r["cores"], "kind": "port",
+                   "sample": "oracle port on R-MAT scale %d, same templates, %d steps, %d host threads"
+                             % (cs, r["steps_done"], r["cores"])}
 
     if rank == 0:
         free_b, total_b = torch.cuda.mem_get_info()

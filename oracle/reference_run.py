@@ -35,6 +35,45 @@ def write_slot_file(path, n_vertices, src, dst):
         f.write("".join("%d %d\n" % st for st in zip(src, dst)))
 
 
+def make_result_tree(out, ps=0):
+    """the directories the driver expects to exist under its -o argument"""
+    for d in _TREE:
+        os.makedirs(os.path.join(out, str(ps), d), exist_ok=True)
+
+
+def launch(graph_path, pattern_dir, out_dir, vertex_data_base=None):
+    """starts the driver on a slot file that is already on disk; returns the Popen (stdout captured as text)"""
+    make_result_tree(out_dir)
+    cmd = [BINARY, "-i", graph_path, "-p", pattern_dir, "-o", out_dir]
+    if vertex_data_base:
+        cmd += ["-v", vertex_data_base]
+    return subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+
+
+def search_seconds(stdout):
+    """the driver's own clock around one template's do/while (beta.cpp:543, 1352-1357): graph load and label
+    construction are outside it"""
+    import re
+    m = re.search(r"Fuzzy Pattern Matching Time \| Pattern \[0\] : ([0-9.eE+-]+)", stdout)
+    if not m:
+        raise RuntimeError("the reference driver printed no pattern time")
+    return float(m.group(1))
+
+
+def tds_at_constraint_4(spec):
+    """The driver runs template-driven search from constraint index 4 on, whatever the pattern files say
+    (beta.cpp:725-730).  A template whose enumeration constraint sits earlier gets copies of its FIRST constraint
+    (a check that has already passed: no further pruning, same final sets) inserted before it, so that the reference
+    does the same work as an engine told to start template-driven search at the template's own index.
+    Returns (spec, index of the enumeration constraint or -1)."""
+    cons = list(spec.get("constraints", []))
+    at = next((i for i, c in enumerate(cons) if c.get("tds")), -1)
+    if at < 0 or at >= 4:
+        return spec, at
+    pad = [{k: v for k, v in cons[0].items() if k != "tds"} for _ in range(4 - at)]
+    return dict(spec, constraints=cons[:at] + pad + cons[at:]), 4
+
+
 def run(n_vertices, src, dst, pattern_dir, labels=None, workdir=None, timeout=600):
     """pattern_dir: the directory that holds the pattern set (<pattern_dir>/0/pattern_*).  labels: None = the reference's own
     degree labels (vertex_data_db_degree.hpp), else one value per vertex, passed through its -v metadata loader.

@@ -1,0 +1,45 @@
+"""Writes tests/golden/reference_runs/*.json: outputs of THE REFERENCE ITSELF (oracle/_ref/run_pattern_matching_beta, see
+oracle/ref_shim/README.md) on seeded inputs that tests/cases.py regenerates anywhere.  Run it in the container that holds
+/root/reference:   python oracle/make_reference_golden.py
+Each file names its input generator and carries the reference's count rows, iteration count, final vertex -> template
+bitset map, final edge set and enumerated subgraphs (template-driven search starts at constraint 4 in the driver,
+beta.cpp:725-730)."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path = [p for p in sys.path if os.path.abspath(p or ".") != os.path.join(ROOT, "oracle")]  # `oracle` is the package
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+from oracle import reference_run as R  # noqa: E402
+from tests import cases  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden", "reference_runs")
+
+
+def main():
+    if R.build() is None:
+        sys.exit("oracle/_ref is not built and /root/reference is not here")
+    O.build()
+    os.makedirs(OUT, exist_ok=True)
+    n_files = 0
+    for case in cases.reference_golden_cases():
+        n, edges, labels, spec = cases.reference_golden_input(case, O)
+        d = cases.pattern_dir(spec)
+        src, dst = cases.slots_of(edges)
+        got = R.run(n, src.tolist(), dst.tolist(), os.path.dirname(d),
+                    labels=None if case["labels"] == "degree_log2" else np.asarray(labels).tolist())
+        got.pop("stdout")
+        got["subgraphs"] = {str(k): v for k, v in got["subgraphs"].items() if v}
+        with open(os.path.join(OUT, case["name"] + ".json"), "w") as f:
+            json.dump({"case": case, "reference": got,
+                       "produced_by": "oracle/_ref/run_pattern_matching_beta (reference driver + visitor headers, single-rank "
+                                      "runtime stand-in) via oracle/make_reference_golden.py"}, f, separators=(",", ":"))
+        n_files += 1
+    print("wrote %d files to %s" % (n_files, OUT))
+
+
+if __name__ == "__main__":
+    main()

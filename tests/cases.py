@@ -173,3 +173,77 @@ def edge_cases():
         out.append(("lcc_only_seed%d" % seed, 200, random_multigraph(seed + 70, 200, 900),
                     random_labels(seed + 70, 200, [1, 2]), lcc_only, 0))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Inputs of the committed reference outputs (tests/golden/reference_runs/*.json, written by oracle/make_reference_golden.py
+# from the reference's own binary).  A case is a small dict that regenerates its input here; "gpu": the engine is run on it
+# too (only inputs whose settings the other GPU tests already use: template-driven search from constraint 4, or none).
+def _spec_by_name(name):
+    for n, spec, labelset, _ in SPECS:
+        if n == name:
+            return spec, labelset
+    for q in QUIRK_SPECS:
+        if q[0] == name:
+            return q[1], q[2]
+    raise KeyError(name)
+
+
+def reference_golden_cases():
+    out = []
+    for name, _, _, _ in SPECS:
+        for seed in range(4):
+            out.append({"name": "%s_random_%d" % (name, seed), "kind": "random", "spec": name, "seed": seed,
+                        "labels": "random", "gpu": name == "tree"})
+        out.append({"name": "%s_planted_1" % name, "kind": "planted", "spec": name, "seed": 1, "labels": "random",
+                    "gpu": name == "tree"})
+    for seed, n, m in list(quirk_inputs("bowtie_no_interleave", 1))[:4]:
+        out.append({"name": "bowtie_no_interleave_%d" % seed, "kind": "quirk", "spec": "bowtie_no_interleave", "seed": seed,
+                    "n": n, "m": m, "labels": "random", "gpu": True})
+    for seed, n, m in list(quirk_inputs("twin", 3))[:4]:
+        out.append({"name": "twin_at_constraint_4_%d" % seed, "kind": "quirk", "spec": "twin", "seed": seed, "n": n, "m": m,
+                    "labels": "random", "pad_to_constraint_4": True, "gpu": False})
+    out.append({"name": "rmat15_tree_degree_labels", "kind": "rmat", "spec": "tree", "scale": 15, "gen_ranks": 4,
+                "labels": "degree_log2", "gpu": True})
+    return out
+
+
+def reference_golden_input(case, oracle):
+    """(n, undirected edges, labels or None, spec) of a case; `oracle` supplies the R-MAT stream (rmat kind only)"""
+    spec, labelset = _spec_by_name(case["spec"])
+    if case.get("pad_to_constraint_4"):
+        spec = dict(spec, constraints=[{"walk": [0, 1]} for _ in range(4)] + list(spec["constraints"]))
+    if case["kind"] == "rmat":
+        scale, gen = case["scale"], case["gen_ranks"]
+        e = np.concatenate([oracle.rmat_stream(scale, r, (16 << scale) // gen) for r in range(gen)])
+        return 1 << scale, [tuple(x) for x in e.tolist()], None, spec
+    seed = case["seed"]
+    if case["kind"] == "planted":
+        edges, labels = planted(seed, 300, 900, spec, labelset)
+        return 300, edges, labels, spec
+    if case["kind"] == "quirk":
+        n, m = case["n"], case["m"]
+    else:
+        n, m = 60 + 10 * (seed % 4), 220 + 60 * (seed % 5)
+    return n, random_multigraph(seed, n, m), random_labels(seed, n, labelset), spec
+
+
+def reference_golden_load(path):
+    """the stored reference output in the comparable form of run_summary / engine_summary"""
+    import json
+    with open(path) as f:
+        doc = json.load(f)
+    r = doc["reference"]
+    return doc["case"], dict(rows=[(a, b, c, d, e) for a, b, c, d, e in r["rows"]], iterations=r["iterations"],
+                             vertices=[tuple(x) for x in r["vertices"]], edges=[tuple(x) for x in r["edges"]],
+                             subgraphs={int(k): [tuple(x) for x in v] for k, v in r["subgraphs"].items()})
+
+
+def assert_equals_reference_golden(summary, golden):
+    """summary: run_summary(oracle run) or engine_summary(engine); only template-driven search writes subgraph files"""
+    assert summary["rows"] == golden["rows"], "rows"
+    assert summary["iterations"] == golden["iterations"], "iterations"
+    assert sorted(summary["vertices"]) == golden["vertices"], "vertices"
+    assert sorted(summary["edges"]) == golden["edges"], "edges"
+    for pl in range(4, len(summary["subgraphs"])):
+        assert sorted(summary["subgraphs"][pl]) == golden["subgraphs"].get(pl, []), "subgraphs of constraint %d" % pl

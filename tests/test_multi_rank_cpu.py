@@ -61,8 +61,8 @@ def test_two_rank_result_layout(tmp_path, oracle):
 
 def test_reference_arm_runs_on_rank0_only(oracle):
     """bench.py --impl reference under a 2-rank launch: rank 0 prints the JSON line, rank 1 exits 0 silently."""
-    env = dict(os.environ, PM_BENCH_SCALE="17", PM_BENCH_CPU_SCALE="17", MASTER_ADDR="127.0.0.1", MASTER_PORT="29542",
-               WORLD_SIZE="2")
+    env = dict(os.environ, PM_BENCH_SCALE="17", PM_BENCH_CPU_SCALE="17", PM_BENCH_REF_SCALE="13", MASTER_ADDR="127.0.0.1",
+               MASTER_PORT="29542", WORLD_SIZE="2")
     outs = []
     for rank in (0, 1):
         e = dict(env, RANK=str(rank), LOCAL_RANK=str(rank))
@@ -73,5 +73,8 @@ def test_reference_arm_runs_on_rank0_only(oracle):
         outs.append(p.stdout.strip())
     assert outs[1] == ""
     line = json.loads(outs[0].splitlines()[-1])
-    assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port" and line["value"] > 0
+    # the reference's own binary where oracle/_ref was built (the container with the reference tree), else the oracle port
+    from oracle import reference_run as R
+    assert line["cpu_baseline"]["kind"] == ("reference" if R.available() else "port")
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["value"] == line["value"]
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["n_gpus"] == 2

@@ -3,8 +3,10 @@
 // TEST INFRASTRUCTURE ONLY: loaded by tests/, __graft_entry__.smoke() and
 // bench.py's cpu_baseline / --impl reference legs.  Never part of the product.
 //
-// PARITY STATUS: "parity unpinned" — the reference has no golden vectors for
-// this path and cannot be built here (MPI + Boost missing); see pm_oracle.h.
+// PARITY STATUS: pinned by the reference's own code — its driver and visitor
+// headers compile over the single-rank runtime stand-in of oracle/ref_shim
+// (oracle/_ref); tests/test_oracle_vs_reference.py and tests/golden/reference_runs
+// hold this oracle to that binary's result files.  See pm_oracle.h.
 //
 // What is restated (paths relative to /root/reference):
 //   R-MAT stream      src/generate_rmat.cpp:197-205,

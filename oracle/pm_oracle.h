@@ -7,9 +7,13 @@
  * --impl reference legs may load it.  The product path (libpmgpu.so) never
  * links, loads or calls anything declared here.
  *
- * PARITY STATUS: "parity unpinned" by the reference itself — the reference
- * ships no golden vectors / tests for this path and cannot
- * be compiled here (needs MPI + Boost).  The oracle is pinned instead by
+ * PARITY STATUS: pinned by the reference's own code.  The reference ships no
+ * golden vectors / tests for this path and cannot be built
+ * as it ships (cmake, MPI, Boost), but its driver and visitor headers compile
+ * from /root/reference over a single-rank runtime stand-in (oracle/ref_shim ->
+ * oracle/_ref/run_pattern_matching_beta).  The oracle is held to
+ *   (0) that binary's result files: tests/test_oracle_vs_reference.py (live) and
+ *       the JSON files of tests/golden/reference_runs (committed outputs),
  *   (1) a literal, dict/set based Python transliteration of the reference
  *       visitors with randomised message delivery (oracle/ref_literal.py),
  *   (2) a brute-force subgraph-isomorphism property check (networkx),

@@ -29,14 +29,19 @@ def main():
         n, edges, labels, spec = cases.reference_golden_input(case, O)
         d = cases.pattern_dir(spec)
         src, dst = cases.slots_of(edges)
-        got = R.run(n, src.tolist(), dst.tolist(), os.path.dirname(d),
-                    labels=None if case["labels"] == "degree_log2" else np.asarray(labels).tolist())
-        got.pop("stdout")
-        got["subgraphs"] = {str(k): v for k, v in got["subgraphs"].items() if v}
+        if case.get("path") == "run_fuzzy":
+            got = R.run_fuzzy(n, src.tolist(), dst.tolist(), os.path.dirname(d), np.asarray(labels).tolist())
+            got.pop("stdout")
+        else:
+            got = R.run(n, src.tolist(), dst.tolist(), os.path.dirname(d),
+                        labels=None if case["labels"] == "degree_log2" else np.asarray(labels).tolist())
+            got.pop("stdout")
+            got["subgraphs"] = {str(k): v for k, v in got["subgraphs"].items() if v}
         with open(os.path.join(OUT, case["name"] + ".json"), "w") as f:
             json.dump({"case": case, "reference": got,
-                       "produced_by": "oracle/_ref/run_pattern_matching_beta (reference driver + visitor headers, single-rank "
-                                      "runtime stand-in) via oracle/make_reference_golden.py"}, f, separators=(",", ":"))
+                       "produced_by": "oracle/_ref/%s (reference driver + visitor headers, single-rank runtime stand-in) via "
+                                      "oracle/make_reference_golden.py"
+                                      % ("run_pattern_matching" if case.get("path") == "run_fuzzy" else "run_pattern_matching_beta")}, f, separators=(",", ":"))
         n_files += 1
     print("wrote %d files to %s" % (n_files, OUT))
 

@@ -15,11 +15,13 @@
 
 #include <cassert>
 #include <cstdint>
+#include <deque>
 #include <fstream>
 #include <functional>
 #include <iostream>
 #include <memory>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 namespace havoqgt {
@@ -101,7 +103,8 @@ class delegate_partitioned_graph {
     size_t size() const { return m_data.size(); }
 
    private:
-    std::vector<T> m_data;
+    // std::deque<bool> hands out real references (std::vector<bool> would not)
+    typename std::conditional<std::is_same<T, bool>::value, std::deque<bool>, std::vector<T>>::type m_data;
   };
 
   template <typename T, typename Allocator = std::allocator<T>>

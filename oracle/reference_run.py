@@ -11,6 +11,7 @@ import tempfile
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 BINARY = os.path.join(_HERE, "_ref", "run_pattern_matching_beta")
+BINARY_FUZZY = os.path.join(_HERE, "_ref", "run_pattern_matching")  # the driver of the run_fuzzy path
 REFERENCE = "/root/reference"
 
 _TREE = ("all_ranks_active_vertices", "all_ranks_active_vertices_count", "all_ranks_active_edges",
@@ -26,6 +27,10 @@ def build():
 
 def available():
     return os.path.exists(BINARY) and os.access(BINARY, os.X_OK)
+
+
+def fuzzy_available():
+    return os.path.exists(BINARY_FUZZY) and os.access(BINARY_FUZZY, os.X_OK)
 
 
 def write_slot_file(path, n_vertices, src, dst):
@@ -130,3 +135,43 @@ def parse_result_tree(out, ps=0, rank=0):
                                               for l in lines("all_ranks_subgraphs/" + name))
     itr = [l for l in lines("result_iteration")]
     return dict(rows=rows, iterations=len(itr), vertices=vertices, edges=edges, subgraphs=subgraphs)
+
+
+def run_fuzzy(n_vertices, src, dst, pattern_dir, labels, timeout=600):
+    """The run_fuzzy path: the reference's src/run_pattern_matching.cpp with
+    label_propagation_pattern_matching_bsp.hpp and token_passing_pattern_matching.hpp.  Its arguments are positional
+    (run_pattern_matching.cpp:62-72: graph, vertex data base name, pattern directory, vertex rank output, backup graph,
+    result directory, use-degree flag) and it reads the constraint list from <pattern_dir>/0/pattern — the same format as
+    pattern_nlc (pattern_util::read_pattern_list), so that file is copied.  labels: one value per vertex, or None for the
+    degree labels.  Returns dict(rows, iterations, vertices): rows (itr, "LP"|"TP", index, vertices, 0) — the driver has no
+    edge counts —, vertices sorted (vertex, template vertex index)."""
+    work = tempfile.mkdtemp(prefix="pmreff_")
+    try:
+        graph = os.path.join(work, "graph.slots")
+        write_slot_file(graph, n_vertices, src, dst)
+        pdir = os.path.join(work, "pattern")
+        shutil.copytree(pattern_dir, pdir)
+        shutil.copy(os.path.join(pdir, "0", "pattern_nlc"), os.path.join(pdir, "0", "pattern"))
+        out = os.path.join(work, "out")
+        make_result_tree(out)
+        vbase = os.path.join(work, "vertex_data", "labels")
+        os.makedirs(os.path.dirname(vbase))
+        if labels is not None:
+            with open(vbase + "_0", "w") as f:
+                f.write("".join("%d %d\n" % (v, int(l)) for v, l in enumerate(labels)))
+        cmd = [BINARY_FUZZY, graph, vbase, pdir, os.path.join(work, "vertex_rank"), "", out, "1" if labels is None else "0"]
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+        if p.returncode != 0:
+            raise RuntimeError("reference driver (run_fuzzy path) failed (%d): %s" % (p.returncode, p.stderr[-2000:]))
+        base = os.path.join(out, "0")
+        rows = []
+        for l in open(os.path.join(base, "all_ranks_active_vertices_count", "active_vertices_0")).read().splitlines():
+            t = [x.strip() for x in l.split(",")]
+            if len(t) >= 4:
+                rows.append((int(t[0]), t[1], int(t[2]), int(t[3]), 0))
+        vertices = sorted((int(t[1]), int(t[2])) for t in (l.split(",") for l in
+                          open(os.path.join(base, "all_ranks_active_vertices", "active_vertices_0")).read().splitlines() if l.strip()))
+        itr = [l for l in open(os.path.join(base, "result_itr")).read().splitlines() if l.strip()]
+        return dict(rows=rows, iterations=len(itr), vertices=vertices, stdout=p.stdout)
+    finally:
+        shutil.rmtree(work, ignore_errors=True)

@@ -205,6 +205,11 @@ def reference_golden_cases():
                     "labels": "random", "pad_to_constraint_4": True, "gpu": False})
     out.append({"name": "rmat15_tree_degree_labels", "kind": "rmat", "spec": "tree", "scale": 15, "gen_ranks": 4,
                 "labels": "degree_log2", "gpu": True})
+    # the run_fuzzy path (the reference's src/run_pattern_matching.cpp): inputs of the GPU fuzzy parity test
+    for name in ("triangle", "cycle4"):
+        for seed in range(5):
+            out.append({"name": "fuzzy_%s_random_%d" % (name, seed), "kind": "random", "spec": name, "seed": seed,
+                        "labels": "random", "path": "run_fuzzy", "gpu": True})
     return out
 
 
@@ -234,6 +239,9 @@ def reference_golden_load(path):
     with open(path) as f:
         doc = json.load(f)
     r = doc["reference"]
+    if doc["case"].get("path") == "run_fuzzy":  # count rows without edge counts, vertex -> template vertex index
+        return doc["case"], dict(rows=[(a, b, c, d, e) for a, b, c, d, e in r["rows"]], iterations=r["iterations"],
+                                 vertices=[tuple(x) for x in r["vertices"]])
     return doc["case"], dict(rows=[(a, b, c, d, e) for a, b, c, d, e in r["rows"]], iterations=r["iterations"],
                              vertices=[tuple(x) for x in r["vertices"]], edges=[tuple(x) for x in r["edges"]],
                              subgraphs={int(k): [tuple(x) for x in v] for k, v in r["subgraphs"].items()})

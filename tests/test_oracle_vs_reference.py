@@ -111,3 +111,48 @@ def test_edge_cases(oracle):
             continue
         compared += _check(oracle, n, edges, labels, spec) is not None
     assert compared >= 4
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The run_fuzzy path: the reference's src/run_pattern_matching.cpp over label_propagation_pattern_matching_bsp.hpp
+# and token_passing_pattern_matching.hpp, against the oracle's fuzzy run: count rows, iterations, vertex -> template vertex.
+def _check_fuzzy(oracle, n, edges, labels, spec):
+    d = cases.pattern_dir(spec)
+    g = oracle.Graph.from_undirected(n, edges)
+    run = oracle.Run(g, labels, oracle.Pattern(d), fuzzy=True, max_iterations=50)
+    src, dst = cases.slots_of(edges)
+    got = R.run_fuzzy(n, src.tolist(), dst.tolist(), os.path.dirname(d), labels.tolist())
+    assert got["rows"] == [(a, b, c, nv, 0) for a, b, c, nv, _ in run.rows]
+    assert got["iterations"] == run.iterations
+    v, t = run.active_vertices()
+    assert got["vertices"] == sorted((int(a), int(b).bit_length() - 1) for a, b in zip(v, t))
+    return run
+
+
+@pytest.mark.skipif(not R.fuzzy_available(), reason="needs oracle/_ref/run_pattern_matching")
+@pytest.mark.parametrize("name", ["triangle", "cycle4"])
+def test_run_fuzzy_path(oracle, name):
+    from fuzzypatternmatching_b200 import patterns as PT
+    spec, labelset = (PT.triangle(1, 2, 3), [1, 2, 3]) if name == "triangle" else (PT.cycle4(1, 2, 3, 4), [1, 2, 3, 4])
+    nontrivial = walked = 0
+    for seed in range(12):
+        n, m = 50 + 7 * (seed % 3), 200 + 50 * (seed % 4)
+        edges = cases.random_multigraph(seed, n, m)
+        labels = cases.random_labels(seed, n, labelset)
+        run = _check_fuzzy(oracle, n, edges, labels, spec)
+        nontrivial += run.rows[-1][3] > 0
+        walked += any(r[1] == "TP" for r in run.rows)
+    assert nontrivial >= 3 and walked >= 3
+
+
+@pytest.mark.skipif(not R.fuzzy_available(), reason="needs oracle/_ref/run_pattern_matching")
+def test_run_fuzzy_known_answers(oracle):
+    """the hand-derived cases of tests/test_oracle_fuzzy.py, answered by the reference itself"""
+    from fuzzypatternmatching_b200 import patterns as PT
+    spec = PT.triangle(1, 2, 3)
+    ring = [(i, (i + 1) % 6) for i in range(6)]
+    for n, edges, labels in ((5, [(0, 1), (1, 2), (2, 0), (2, 3), (3, 4)], [1, 2, 3, 1, 2]),
+                             (3, [(0, 1), (1, 2)], [1, 2, 3]),
+                             (6, ring, [1, 2, 3, 1, 2, 3]),
+                             (7, ring + [(1, 6)], [1, 2, 3, 1, 2, 3, 1])):
+        _check_fuzzy(oracle, n, edges, np.array(labels, dtype=np.uint64), spec)

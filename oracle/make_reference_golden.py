@@ -29,7 +29,9 @@ def main():
         n, edges, labels, spec = cases.reference_golden_input(case, O)
         d = cases.pattern_dir(spec)
         src, dst = cases.slots_of(edges)
-        if case.get("path") == "run_fuzzy":
+        if case.get("path") == "approx_first_lcc":
+            got = {"rows": R.run_approx_first_lcc(n, src.tolist(), dst.tolist(), os.path.dirname(d), np.asarray(labels).tolist(), spec)}
+        elif case.get("path") == "run_fuzzy":
             got = R.run_fuzzy(n, src.tolist(), dst.tolist(), os.path.dirname(d), np.asarray(labels).tolist())
             got.pop("stdout")
         else:
@@ -41,7 +43,7 @@ def main():
             json.dump({"case": case, "reference": got,
                        "produced_by": "oracle/_ref/%s (reference driver + visitor headers, single-rank runtime stand-in) via "
                                       "oracle/make_reference_golden.py"
-                                      % ("run_pattern_matching" if case.get("path") == "run_fuzzy" else "run_pattern_matching_beta")}, f, separators=(",", ":"))
+                                      % {"run_fuzzy": "run_pattern_matching", "approx_first_lcc": "run_pattern_matching_beta_2"}.get(case.get("path"), "run_pattern_matching_beta")}, f, separators=(",", ":"))
         n_files += 1
     print("wrote %d files to %s" % (n_files, OUT))
 

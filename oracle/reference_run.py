@@ -11,6 +11,7 @@ import tempfile
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 BINARY = os.path.join(_HERE, "_ref", "run_pattern_matching_beta")
+BINARY_APPROX = os.path.join(_HERE, "_ref", "run_pattern_matching_beta_2")  # the driver of approximate matching
 BINARY_FUZZY = os.path.join(_HERE, "_ref", "run_pattern_matching")  # the driver of the run_fuzzy path
 REFERENCE = "/root/reference"
 
@@ -27,6 +28,10 @@ def build():
 
 def available():
     return os.path.exists(BINARY) and os.access(BINARY, os.X_OK)
+
+
+def approx_available():
+    return os.path.exists(BINARY_APPROX) and os.access(BINARY_APPROX, os.X_OK)
 
 
 def fuzzy_available():
@@ -173,5 +178,46 @@ def run_fuzzy(n_vertices, src, dst, pattern_dir, labels, timeout=600):
                           open(os.path.join(base, "all_ranks_active_vertices", "active_vertices_0")).read().splitlines() if l.strip()))
         itr = [l for l in open(os.path.join(base, "result_itr")).read().splitlines() if l.strip()]
         return dict(rows=rows, iterations=len(itr), vertices=vertices, stdout=p.stdout)
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
+def run_approx_first_lcc(n_vertices, src, dst, pattern_dir, labels, spec, timeout=600):
+    """Approximate matching: the reference's src/run_pattern_matching_beta_2.cpp over
+    approximate_pattern_matching/{pattern_graph,local_constraint_checking}.hpp.  Its non-local side (generated constraints,
+    tds_batch_5) is not what this repository builds, so only the count rows of the FIRST local constraint checking call are
+    returned: [(0, "LP", k, vertices, edges)] for k < diameter.  The driver indexes its constraint list unconditionally
+    (beta_2.cpp:524-525), so one constraint in ITS file format (pattern_non_local_constraints: "vertices : enumeration :
+    aggregation : cyclic : tds : lcc") is written: a two-edge walk of the template, which only runs after the rows wanted."""
+    work = tempfile.mkdtemp(prefix="pmrefa_")
+    try:
+        graph = os.path.join(work, "graph.slots")
+        write_slot_file(graph, n_vertices, src, dst)
+        pdir = os.path.join(work, "pattern")
+        shutil.copytree(pattern_dir, pdir)
+        a, b = spec["edges"][0]
+        third = next((x if y == b else y for x, y in spec["edges"][1:] if b in (x, y) and {x, y} != {a, b}), a)
+        walk = " ".join(str(v) for v in (a, b, third))
+        with open(os.path.join(pdir, "0", "pattern_non_local_constraints"), "w") as f:
+            f.write("%s : %s : 0 0 0 : 0 : 0 : 0\n" % (walk, walk))
+        out = os.path.join(work, "out")
+        make_result_tree(out)
+        vbase = os.path.join(work, "vertex_data", "labels")
+        os.makedirs(os.path.dirname(vbase))
+        with open(vbase + "_0", "w") as f:
+            f.write("".join("%d %d\n" % (v, int(l)) for v, l in enumerate(labels)))
+        p = subprocess.run([BINARY_APPROX, "-i", graph, "-v", vbase, "-p", pdir, "-o", out], capture_output=True, text=True,
+                           timeout=timeout)
+        vfile = os.path.join(out, "0", "all_ranks_active_vertices_count", "active_vertices_0")
+        efile = os.path.join(out, "0", "all_ranks_active_edges_count", "active_edges_0")
+        if not os.path.exists(vfile) or not os.path.getsize(vfile):
+            raise RuntimeError("reference driver (approximate matching) wrote no rows (%d): %s" % (p.returncode, p.stderr[-2000:]))
+        rows = []
+        for lv, le in zip(open(vfile).read().splitlines(), open(efile).read().splitlines()):
+            tv, te = [x.strip() for x in lv.split(",")], [x.strip() for x in le.split(",")]
+            if tv[1] != "LP" or int(tv[0]) != 0 or (rows and int(tv[2]) <= rows[-1][2]):
+                break
+            rows.append((0, "LP", int(tv[2]), int(tv[3]), int(te[3])))
+        return rows
     finally:
         shutil.rmtree(work, ignore_errors=True)

@@ -186,6 +186,9 @@ def _spec_by_name(name):
     for q in QUIRK_SPECS:
         if q[0] == name:
             return q[1], q[2]
+    for n, spec, labelset, _ in APPROX_SPECS:
+        if n == name:
+            return spec, labelset
     raise KeyError(name)
 
 
@@ -210,6 +213,12 @@ def reference_golden_cases():
         for seed in range(5):
             out.append({"name": "fuzzy_%s_random_%d" % (name, seed), "kind": "random", "spec": name, "seed": seed,
                         "labels": "random", "path": "run_fuzzy", "gpu": True})
+    # approximate matching (the reference's src/run_pattern_matching_beta_2.cpp): the rows of the first local
+    # constraint checking call, on inputs of the GPU approximate-pattern test
+    for name, _, _, _ in APPROX_SPECS:
+        for seed in range(3):
+            out.append({"name": "approx_%s_%d" % (name, seed), "kind": "approx", "spec": name, "seed": seed,
+                        "labels": "random", "path": "approx_first_lcc", "gpu": True})
     return out
 
 
@@ -226,6 +235,9 @@ def reference_golden_input(case, oracle):
     if case["kind"] == "planted":
         edges, labels = planted(seed, 300, 900, spec, labelset)
         return 300, edges, labels, spec
+    if case["kind"] == "approx":
+        n, m = 60 + 10 * (seed % 4), 160 + 40 * (seed % 5)
+        return n, random_multigraph(seed + 500, n, m), random_labels(seed + 500, n, labelset), spec
     if case["kind"] == "quirk":
         n, m = case["n"], case["m"]
     else:
@@ -239,6 +251,8 @@ def reference_golden_load(path):
     with open(path) as f:
         doc = json.load(f)
     r = doc["reference"]
+    if doc["case"].get("path") == "approx_first_lcc":  # the count rows of the first local constraint checking call
+        return doc["case"], dict(rows=[(a, b, c, d, e) for a, b, c, d, e in r["rows"]])
     if doc["case"].get("path") == "run_fuzzy":  # count rows without edge counts, vertex -> template vertex index
         return doc["case"], dict(rows=[(a, b, c, d, e) for a, b, c, d, e in r["rows"]], iterations=r["iterations"],
                                  vertices=[tuple(x) for x in r["vertices"]])

@@ -156,3 +156,26 @@ def test_run_fuzzy_known_answers(oracle):
                              (6, ring, [1, 2, 3, 1, 2, 3]),
                              (7, ring + [(1, 6)], [1, 2, 3, 1, 2, 3, 1])):
         _check_fuzzy(oracle, n, edges, np.array(labels, dtype=np.uint64), spec)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Approximate matching: the reference's src/run_pattern_matching_beta_2.cpp over
+# approximate_pattern_matching/local_constraint_checking.hpp — the rows of its first local constraint checking call.
+@pytest.mark.skipif(not R.approx_available(), reason="needs oracle/_ref/run_pattern_matching_beta_2")
+@pytest.mark.parametrize("name,spec,labelset,tds_from", cases.APPROX_SPECS, ids=[s[0] for s in cases.APPROX_SPECS])
+def test_approximate_local_constraint_checking(oracle, name, spec, labelset, tds_from):
+    pruned = 0
+    for seed in range(10):
+        n, m = 60 + 10 * (seed % 4), 160 + 40 * (seed % 5)
+        edges = cases.random_multigraph(seed + 500, n, m)
+        labels = cases.random_labels(seed + 500, n, labelset)
+        d = cases.pattern_dir(spec)
+        g = oracle.Graph.from_undirected(n, edges)
+        run = oracle.Run(g, labels, oracle.Pattern(d), tds_from_pl=tds_from, max_iterations=50)
+        want = [r for r in run.rows[:spec["diameter"]]]
+        assert [r[:3] for r in want] == [(0, "LP", k) for k in range(spec["diameter"])]
+        src, dst = cases.slots_of(edges)
+        got = R.run_approx_first_lcc(n, src.tolist(), dst.tolist(), os.path.dirname(d), labels.tolist(), spec)
+        assert got == want
+        pruned += want[-1][3] < n
+    assert pruned >= 5

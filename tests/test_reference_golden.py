@@ -31,6 +31,10 @@ def test_oracle_equals_reference_output(oracle, path):
     g = oracle.Graph.from_undirected(n, edges)
     if labels is None:
         labels = g.labels_degree_log2()
+    if case.get("path") == "approx_first_lcc":
+        run = oracle.Run(g, labels, oracle.Pattern(cases.pattern_dir(spec)), tds_from_pl=-1, max_iterations=50)
+        assert run.rows[:spec["diameter"]] == golden["rows"] and len(golden["rows"]) == spec["diameter"]
+        return
     if case.get("path") == "run_fuzzy":
         run = oracle.Run(g, labels, oracle.Pattern(cases.pattern_dir(spec)), fuzzy=True, max_iterations=50)
         _assert_fuzzy(run.rows, run.iterations, *run.active_vertices(), golden)
@@ -52,6 +56,8 @@ def test_fixtures_are_not_trivial(oracle):
     ends, enumerated, multi = 0, 0, 0
     for path in GOLDEN:
         _, golden = cases.reference_golden_load(path)
+        if "vertices" not in golden:
+            continue
         ends += len(golden["vertices"]) > 0
         enumerated += any(len(v) > 0 for v in golden.get("subgraphs", {}).values())
         multi += golden["iterations"] > 1
@@ -85,6 +91,10 @@ def test_engine_equals_reference_output(oracle, eng, path):
     else:
         eng.labels_set(labels)
     eng.pattern_load_dir(d)
+    if case.get("path") == "approx_first_lcc":  # the calls of test_gpu_parity.py::_compare on an approximate template
+        eng.run(tds_from_pl=-1, max_iterations=50)
+        assert eng.rows()[:spec["diameter"]] == golden["rows"]
+        return
     if case.get("path") == "run_fuzzy":  # the calls of test_gpu_parity.py::test_run_fuzzy_path_matches_oracle
         eng.run_fuzzy(max_iterations=50)
         _assert_fuzzy(eng.rows(), eng.summary["iterations"], *eng.active_vertices(), golden)

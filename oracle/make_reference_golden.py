@@ -25,7 +25,26 @@ def main():
     O.build()
     os.makedirs(OUT, exist_ok=True)
     n_files = 0
+    large = "--large" in sys.argv
     for case in cases.reference_golden_cases():
+        if case.get("large"):
+            if not large:
+                continue  # kept as committed; regenerate with --large
+            scale, gen = case["scale"], case["gen_ranks"]
+            e = np.concatenate([O.rmat_stream(scale, r, (16 << scale) // gen) for r in range(gen)])
+            src = np.empty(2 * len(e), dtype=np.uint64)
+            dst = np.empty(2 * len(e), dtype=np.uint64)
+            src[0::2], dst[0::2] = e[:, 0], e[:, 1]
+            src[1::2], dst[1::2] = e[:, 1], e[:, 0]
+            got = R.run(1 << scale, src, dst, os.path.join(ROOT, "tests", case["pattern_dir"]), labels=None, timeout=3600)
+            got.pop("stdout")
+            got["subgraphs"] = {str(k): v for k, v in got["subgraphs"].items() if v}
+            with open(os.path.join(OUT, case["name"] + ".json"), "w") as f:
+                json.dump({"case": case, "reference": got,
+                           "produced_by": "oracle/_ref/run_pattern_matching_beta (reference driver + visitor headers, single-rank "
+                                          "runtime stand-in) via oracle/make_reference_golden.py --large"}, f, separators=(",", ":"))
+            n_files += 1
+            continue
         n, edges, labels, spec = cases.reference_golden_input(case, O)
         d = cases.pattern_dir(spec)
         src, dst = cases.slots_of(edges)

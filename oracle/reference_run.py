@@ -42,7 +42,13 @@ def write_slot_file(path, n_vertices, src, dst):
     """the text graph the stand-in's distributed_db reads: vertex count, then one directed slot per line"""
     with open(path, "w") as f:
         f.write("%d\n" % n_vertices)
-        f.write("".join("%d %d\n" % st for st in zip(src, dst)))
+        if hasattr(src, "dtype"):  # numpy arrays: large graphs
+            import numpy as np
+            both = np.stack([np.asarray(src, dtype=np.uint64), np.asarray(dst, dtype=np.uint64)], axis=1)
+            for at in range(0, len(both), 1 << 22):
+                np.savetxt(f, both[at:at + (1 << 22)], fmt="%d")
+        else:
+            f.write("".join("%d %d\n" % st for st in zip(src, dst)))
 
 
 def make_result_tree(out, ps=0):

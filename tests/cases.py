@@ -213,6 +213,12 @@ def reference_golden_cases():
         for seed in range(5):
             out.append({"name": "fuzzy_%s_random_%d" % (name, seed), "kind": "random", "spec": name, "seed": seed,
                         "labels": "random", "path": "run_fuzzy", "gpu": True})
+    # BASELINE configs[0] exactly: R-MAT scale 21 with 4 generating ranks, the reference's own degree labels and its
+    # examples/rmat_log2_tree_pattern (tests/golden/rmat_log2_tree_pattern).  The graph comes from the oracle's generator
+    # (Graph.rmat), not from an edge list in Python; written by `make_reference_golden.py --large` (a 1 GB slot file, minutes).
+    # The engine is held to this fixture inside tests/test_gpu_parity.py::test_baseline_config1_scale21_reference_pattern_dir.
+    out.append({"name": "rmat21_config0_reference_pattern_dir", "kind": "rmat_generated", "scale": 21, "gen_ranks": 4,
+                "labels": "degree_log2", "pattern_dir": "golden/rmat_log2_tree_pattern", "gpu": False, "large": True})
     # approximate matching (the reference's src/run_pattern_matching_beta_2.cpp): the rows of the first local
     # constraint checking call, on inputs of the GPU approximate-pattern test
     for name, _, _, _ in APPROX_SPECS:

@@ -175,6 +175,11 @@ def test_baseline_config1_scale21_reference_pattern_dir(oracle, eng):
         assert got[k] == want[k], k
     assert len(want["vertices"]) > 0 and len(want["subgraphs"][4]) > 0
     assert eng.subgraph_count(4) == len(want["subgraphs"][4])
+    # ... and against what THE REFERENCE ITSELF wrote for this input (its own driver + visitor headers over the single-rank
+    # runtime stand-in; fixture written by oracle/make_reference_golden.py --large)
+    _, golden = cases.reference_golden_load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_runs",
+                                                         "rmat21_config0_reference_pattern_dir.json"))
+    cases.assert_equals_reference_golden(got, golden)
 
 
 def test_bench_templates_on_rmat_scale20(oracle, eng):

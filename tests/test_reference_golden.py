@@ -27,6 +27,14 @@ def test_fixture_set_is_complete():
 @pytest.mark.parametrize("path", GOLDEN, ids=_ids(GOLDEN))
 def test_oracle_equals_reference_output(oracle, path):
     case, golden = cases.reference_golden_load(path)
+    if case["kind"] == "rmat_generated":  # BASELINE configs[0]: the oracle's own generator and the reference's pattern directory
+        g = oracle.Graph.rmat(case["scale"], case["gen_ranks"])
+        d = os.path.join(os.path.dirname(os.path.abspath(__file__)), case["pattern_dir"], "0")
+        run = oracle.Run(g, g.labels_degree_log2(), oracle.Pattern(d), tds_from_pl=4)
+        assert not run.hazards[:5].any()
+        cases.assert_equals_reference_golden(cases.run_summary(run), golden)
+        assert len(golden["vertices"]) == 147 and len(golden["edges"]) == 262 and len(golden["subgraphs"][4]) == 74
+        return
     n, edges, labels, spec = cases.reference_golden_input(case, oracle)
     g = oracle.Graph.from_undirected(n, edges)
     if labels is None:

@@ -1,6 +1,7 @@
 """Writes tests/golden/reference_runs/*.json: outputs of THE REFERENCE ITSELF (oracle/_ref/run_pattern_matching_beta, see
 oracle/ref_shim/README.md) on seeded inputs that tests/cases.py regenerates anywhere.  Run it in the container that holds
 /root/reference:   python oracle/make_reference_golden.py
+(`--large` also writes the R-MAT scale-20 / scale-21 fixtures, minutes each; `--only=<name>` restricts that to one of them.)
 Each file names its input generator and carries the reference's count rows, iteration count, final vertex -> template
 bitset map, final edge set and enumerated subgraphs (template-driven search starts at constraint 4 in the driver,
 beta.cpp:725-730)."""
@@ -30,14 +31,24 @@ def main():
         if case.get("large"):
             if not large:
                 continue  # kept as committed; regenerate with --large
+            only = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--only=")]
+            if only and case["name"] not in only:
+                continue
             scale, gen = case["scale"], case["gen_ranks"]
             e = np.concatenate([O.rmat_stream(scale, r, (16 << scale) // gen) for r in range(gen)])
             src = np.empty(2 * len(e), dtype=np.uint64)
             dst = np.empty(2 * len(e), dtype=np.uint64)
             src[0::2], dst[0::2] = e[:, 0], e[:, 1]
             src[1::2], dst[1::2] = e[:, 1], e[:, 0]
-            got = R.run(1 << scale, src, dst, os.path.join(ROOT, "tests", case["pattern_dir"]), labels=None, timeout=3600)
+            if "bench_template" in case:  # a template of bench.py's workload, enumeration walk at constraint 4
+                pdir = os.path.dirname(cases.pattern_dir(cases.bench_template_at_constraint_4(case["bench_template"])[0]))
+            else:
+                pdir = os.path.join(ROOT, "tests", case["pattern_dir"])
+            got = R.run(1 << scale, src, dst, pdir, labels=None, timeout=3600)
             got.pop("stdout")
+            if case.get("digest_subgraphs"):  # too many walks to commit: their count and digest
+                got["subgraphs_digest"] = {str(k): cases.subgraphs_digest(v) for k, v in got["subgraphs"].items() if v}
+                got["subgraphs"] = {}
             got["subgraphs"] = {str(k): v for k, v in got["subgraphs"].items() if v}
             with open(os.path.join(OUT, case["name"] + ".json"), "w") as f:
                 json.dump({"case": case, "reference": got,

@@ -189,7 +189,35 @@ def _spec_by_name(name):
     for n, spec, labelset, _ in APPROX_SPECS:
         if n == name:
             return spec, labelset
+    if name in BENCH_TEMPLATES:
+        return BENCH_TEMPLATES[name], sorted(set(BENCH_TEMPLATES[name]["labels"]))
     raise KeyError(name)
+
+
+# the cyclic templates of bench.py's default workload (BASELINE configs[2]), with its label choices
+BENCH_TEMPLATES = {"triangle_678": PT.triangle(6, 7, 8), "cycle4_5678": PT.cycle4(5, 6, 7, 8),
+                   "cycle6_chords_456789": PT.cycle6_chords([4, 5, 6, 7, 8, 9])}
+
+
+HUB_TEMPLATES = {"triangle_hubs_12_14_16": PT.triangle(12, 14, 16)}
+
+
+def rmat20_template(name):
+    return BENCH_TEMPLATES[name] if name in BENCH_TEMPLATES else HUB_TEMPLATES[name]
+
+
+def bench_template_at_constraint_4(name):
+    """(spec as the reference driver ran it, index of its enumeration constraint there)"""
+    from oracle import reference_run as R
+    return R.tds_at_constraint_4(rmat20_template(name))
+
+
+def subgraphs_digest(rows):
+    """count and SHA-256 of the sorted enumerated walks (one "a,b,c,..." line per walk): what a fixture keeps when the
+    walks themselves are too many to commit"""
+    import hashlib
+    rows = sorted(tuple(int(x) for x in r) for r in rows)
+    return {"count": len(rows), "sha256": hashlib.sha256("\n".join(",".join(map(str, r)) for r in rows).encode()).hexdigest()}
 
 
 def reference_golden_cases():
@@ -213,12 +241,29 @@ def reference_golden_cases():
         for seed in range(5):
             out.append({"name": "fuzzy_%s_random_%d" % (name, seed), "kind": "random", "spec": name, "seed": seed,
                         "labels": "random", "path": "run_fuzzy", "gpu": True})
+    # ... and its R-MAT input: scale 17 with the reference's own degree labels, the 4-cycle of bench.py's workload (the engine is
+    # held to this fixture inside tests/test_gpu_parity.py::test_run_fuzzy_path_matches_oracle)
+    out.append({"name": "fuzzy_rmat17_cycle4_5678", "kind": "rmat", "spec": "cycle4_5678", "scale": 17, "gen_ranks": 4,
+                "labels": "degree_log2", "path": "run_fuzzy", "gpu": False})
     # BASELINE configs[0] exactly: R-MAT scale 21 with 4 generating ranks, the reference's own degree labels and its
     # examples/rmat_log2_tree_pattern (tests/golden/rmat_log2_tree_pattern).  The graph comes from the oracle's generator
     # (Graph.rmat), not from an edge list in Python; written by `make_reference_golden.py --large` (a 1 GB slot file, minutes).
     # The engine is held to this fixture inside tests/test_gpu_parity.py::test_baseline_config1_scale21_reference_pattern_dir.
     out.append({"name": "rmat21_config0_reference_pattern_dir", "kind": "rmat_generated", "scale": 21, "gen_ranks": 4,
                 "labels": "degree_log2", "pattern_dir": "golden/rmat_log2_tree_pattern", "gpu": False, "large": True})
+    # BASELINE configs[2]'s templates as bench.py writes them (triangle, 4-cycle, 6-cycle with chords over populous degree
+    # classes) on R-MAT scale 20 with 4 generating ranks and the reference's own degree labels — the input of
+    # tests/test_gpu_parity.py::test_bench_templates_on_rmat_scale20.  The driver starts template-driven search at constraint
+    # 4 (beta.cpp:725-730), so the reference ran the template with its enumeration walk moved there
+    # (oracle/reference_run.py::tds_at_constraint_4: copies of the first, already satisfied constraint in front of it).
+    for name in sorted(BENCH_TEMPLATES):
+        out.append({"name": "rmat20_bench_%s" % name, "kind": "rmat_generated", "scale": 20, "gen_ranks": 4,
+                    "labels": "degree_log2", "bench_template": name, "gpu": False, "large": True})
+    # the hub-class template of tests/test_gpu_parity.py::test_hub_class_template_on_rmat_scale20 (degree labels 12, 14, 16:
+    # rows of 2^11 .. 2^16 slots) on the same graph; its 135 126 enumerated walks are stored as a count and a digest
+    out.append({"name": "rmat20_hubs_triangle_12_14_16", "kind": "rmat_generated", "scale": 20, "gen_ranks": 4,
+                "labels": "degree_log2", "bench_template": "triangle_hubs_12_14_16", "digest_subgraphs": True,
+                "gpu": False, "large": True})
     # approximate matching (the reference's src/run_pattern_matching_beta_2.cpp): the rows of the first local
     # constraint checking call, on inputs of the GPU approximate-pattern test
     for name, _, _, _ in APPROX_SPECS:
@@ -262,9 +307,12 @@ def reference_golden_load(path):
     if doc["case"].get("path") == "run_fuzzy":  # count rows without edge counts, vertex -> template vertex index
         return doc["case"], dict(rows=[(a, b, c, d, e) for a, b, c, d, e in r["rows"]], iterations=r["iterations"],
                                  vertices=[tuple(x) for x in r["vertices"]])
-    return doc["case"], dict(rows=[(a, b, c, d, e) for a, b, c, d, e in r["rows"]], iterations=r["iterations"],
-                             vertices=[tuple(x) for x in r["vertices"]], edges=[tuple(x) for x in r["edges"]],
-                             subgraphs={int(k): [tuple(x) for x in v] for k, v in r["subgraphs"].items()})
+    out = dict(rows=[(a, b, c, d, e) for a, b, c, d, e in r["rows"]], iterations=r["iterations"],
+               vertices=[tuple(x) for x in r["vertices"]], edges=[tuple(x) for x in r["edges"]],
+               subgraphs={int(k): [tuple(x) for x in v] for k, v in r.get("subgraphs", {}).items()})
+    if "subgraphs_digest" in r:  # {constraint: {"count", "sha256"}} instead of the walks (subgraphs_digest above)
+        out["subgraphs_digest"] = {int(k): v for k, v in r["subgraphs_digest"].items()}
+    return doc["case"], out
 
 
 def assert_equals_reference_golden(summary, golden):
@@ -274,4 +322,23 @@ def assert_equals_reference_golden(summary, golden):
     assert sorted(summary["vertices"]) == golden["vertices"], "vertices"
     assert sorted(summary["edges"]) == golden["edges"], "edges"
     for pl in range(4, len(summary["subgraphs"])):
-        assert sorted(summary["subgraphs"][pl]) == golden["subgraphs"].get(pl, []), "subgraphs of constraint %d" % pl
+        if pl in golden.get("subgraphs_digest", {}):
+            assert subgraphs_digest(summary["subgraphs"][pl]) == golden["subgraphs_digest"][pl], "walks of constraint %d" % pl
+        else:
+            assert sorted(summary["subgraphs"][pl]) == golden["subgraphs"].get(pl, []), "subgraphs of constraint %d" % pl
+
+
+def assert_final_sets_equal_reference_golden(summary, tds_pl, golden):
+    """A template run with its enumeration walk at its OWN constraint index `tds_pl`, against a fixture of the reference
+    driver, which ran the same template with that walk moved to constraint 4 behind copies of an already satisfied
+    constraint (oracle/reference_run.py::tds_at_constraint_4): the count rows differ by those extra constraints' rows, the
+    final vertex -> template bitset map, the final edge set and the enumerated walks do not."""
+    assert sorted(summary["vertices"]) == golden["vertices"], "vertices"
+    assert sorted(summary["edges"]) == golden["edges"], "edges"
+    if 4 in golden.get("subgraphs_digest", {}):
+        if summary["subgraphs"][tds_pl] is not None:  # None: the caller kept no walks and compares the count itself
+            assert subgraphs_digest(summary["subgraphs"][tds_pl]) == golden["subgraphs_digest"][4], "enumerated walks"
+    else:
+        assert sorted(summary["subgraphs"][tds_pl]) == golden["subgraphs"].get(4, []), "enumerated walks"
+    first_call = lambda rows: [r for r in rows if r[0] == 0 and r[1] == "LP"]  # noqa: E731
+    assert first_call(summary["rows"]) == first_call(golden["rows"]), "rows of the first local constraint checking call"

@@ -2,6 +2,8 @@
 seeded inputs.  Bit-exact: per-superstep active vertex / edge counts, final
 vertex -> template bitset map, final edge set, iteration count and the enumerated
 subgraph rows."""
+import os
+
 import numpy as np
 import pytest
 
@@ -203,6 +205,11 @@ def test_bench_templates_on_rmat_scale20(oracle, eng):
         for k in ("rows", "iterations", "vertices", "edges", "subgraphs"):
             assert got[k] == want[k], (nm, k)
         assert len(want["rows"]) >= 8, nm
+        # ... and against what THE REFERENCE ITSELF wrote for this graph and template (its driver enumerates from constraint
+        # 4 on, so it ran the template with the enumeration walk moved there: same final sets and walks)
+        _, golden = cases.reference_golden_load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
+                                                             "reference_runs", "rmat20_bench_%s.json" % nm))
+        cases.assert_final_sets_equal_reference_golden(got, tds, golden)
 
 
 def test_label_stream_path_without_packed_labels(oracle, eng):
@@ -400,6 +407,12 @@ def test_run_fuzzy_path_matches_oracle(oracle, eng):
     v, t = eng.active_vertices()
     rv, rt = ref.active_vertices()
     assert np.array_equal(v, rv) and np.array_equal(t, rt) and len(rv) > 0
+    # ... and against what the reference's own run_pattern_matching driver wrote for this input (vertex counts per row; one
+    # template vertex index per vertex)
+    _, golden = cases.reference_golden_load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_runs",
+                                                         "fuzzy_rmat17_cycle4_5678.json"))
+    assert [(a, b, c, nv, 0) for a, b, c, nv, _ in eng.rows()] == golden["rows"]
+    assert sorted((int(a), int(b).bit_length() - 1) for a, b in zip(v, t)) == golden["vertices"]
 
 
 def test_edge_cases_match_oracle(oracle, eng):
@@ -644,3 +657,10 @@ def test_hub_class_template_on_rmat_scale20(oracle, eng):
     assert np.array_equal(eng.active_edges(), ref.active_edges)
     assert int(s["path_count"]) == ref.path_count > 0
     assert eng.kernel_stats(2)["launches"] > 0  # the CTA-per-row class ran
+    # ... and against what THE REFERENCE ITSELF wrote for this graph and template (enumeration walk moved to constraint 4,
+    # where its driver starts template-driven search: same final sets, same number of enumerated walks)
+    _, golden = cases.reference_golden_load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_runs",
+                                                         "rmat20_hubs_triangle_12_14_16.json"))
+    assert sorted(zip(v.tolist(), t.tolist())) == golden["vertices"]
+    assert sorted(map(tuple, eng.active_edges().tolist())) == golden["edges"]
+    assert int(s["path_count"]) == golden["subgraphs_digest"][4]["count"]

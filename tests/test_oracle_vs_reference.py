@@ -179,3 +179,65 @@ def test_approximate_local_constraint_checking(oracle, name, spec, labelset, tds
         assert got == want
         pruned += want[-1][3] < n
     assert pruned >= 5
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The result tree itself, file by file: what a user of the reference finds under -o (beta.cpp:504-535, 1094-1138, 1375-1425)
+# against what the oracle's writer — the one the engine's C++ CLI is compared with in the GPU suite — puts there.
+
+def _tree_files(root):
+    out = []
+    for base, _, files in os.walk(root):
+        out += [os.path.relpath(os.path.join(base, f), root) for f in files]
+    return sorted(out)
+
+
+def test_result_tree_is_the_reference_result_tree_file_by_file(oracle, tmp_path):
+    """Same files, same rows, same row grammar (separator ", ", bitset column, "[rank]" brackets of the subgraph rows).
+    Files whose rows carry wall-clock times are compared with the time column removed; all_ranks_messages counts the
+    transport's messages and is compared by row count only."""
+    from fuzzypatternmatching_b200 import patterns as PT
+    scale, gen = 17, 4  # the input of the GPU suite's CLI test: the tree template leaves vertices, edges and enumerated walks
+    edges = np.concatenate([oracle.rmat_stream(scale, r, (16 << scale) // gen) for r in range(gen)])
+    edges = [tuple(e) for e in edges.tolist()]
+    pbase = str(tmp_path / "pattern")
+    d = PT.write_pattern_dir(pbase, PT.RMAT_LOG2_TREE)
+    src, dst = cases.slots_of(edges)
+    work = str(tmp_path / "ref")
+    os.makedirs(work)
+    R.run(1 << scale, src.tolist(), dst.tolist(), pbase, labels=None, workdir=work)
+    ref_out = os.path.join(work, "out")
+    g = oracle.Graph.from_undirected(1 << scale, edges)
+    run = oracle.Run(g, g.labels_degree_log2(), oracle.Pattern(d), n_ranks=1, tds_from_pl=4)
+    assert not run.hazards[:5].any() and run.rows[-1][3] > 0
+    ours = str(tmp_path / "ours")
+    os.makedirs(ours)
+    oracle.make_result_tree(ours)
+    run.write_results(ours)
+
+    ref_files, our_files = _tree_files(ref_out), _tree_files(ours)
+    # every file the reference wrote is there (an empty subgraph file of a constraint that enumerated nothing included)
+    assert [f for f in ref_files if f not in our_files] == []
+    read = lambda root, rel: open(os.path.join(root, rel)).read()  # noqa: E731
+    exact = ["0/all_ranks_active_vertices/active_vertices_0", "0/all_ranks_active_edges/active_edges_0",
+             "0/all_ranks_active_vertices_count/active_vertices_0", "0/all_ranks_active_edges_count/active_edges_0"]
+    for rel in exact:
+        a, b = read(ref_out, rel).splitlines(), read(ours, rel).splitlines()
+        assert len(a) > 0 and sorted(a) == sorted(b), rel
+    for rel in ("0/all_ranks_active_vertices_count/active_vertices_0", "0/all_ranks_active_edges_count/active_edges_0"):
+        assert read(ref_out, rel) == read(ours, rel), rel  # count rows are written in order: byte for byte
+    sub = [f for f in ref_files if f.startswith("0/all_ranks_subgraphs/")]
+    assert "0/all_ranks_subgraphs/subgraphs_4_0" in sub
+    for rel in sub:
+        assert sorted(read(ref_out, rel).splitlines()) == sorted(read(ours, rel).splitlines()), rel
+    assert len(read(ref_out, "0/all_ranks_subgraphs/subgraphs_4_0").splitlines()) > 0
+    # rows with a time column: "<itr>, <LP|TP>, <index>, <seconds>" — same keys in the same order
+    keys = lambda text: [[t.strip() for t in l.split(",")][:3] for l in text.splitlines() if l.strip()]  # noqa: E731
+    assert keys(read(ref_out, "0/result_superstep")) == keys(read(ours, "0/result_superstep"))
+    for rel in ("0/result_iteration", "0/result_step"):
+        a, b = read(ref_out, rel).splitlines(), read(ours, rel).splitlines()
+        assert len(a) == len(b) and [len(l.split(",")) for l in a] == [len(l.split(",")) for l in b], rel
+    a, b = read(ref_out, "result_pattern_set").split(","), read(ours, "result_pattern_set").split(",")
+    assert len(a) == len(b) and [x.strip() for x in a[:3] + a[4:]] == [x.strip() for x in b[:3] + b[4:]]
+    assert len(read(ref_out, "0/all_ranks_messages/messages_0").splitlines()) == \
+        len(read(ours, "0/all_ranks_messages/messages_0").splitlines())

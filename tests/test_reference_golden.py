@@ -11,6 +11,7 @@ import os
 
 import pytest
 
+from fuzzypatternmatching_b200 import patterns as PT
 from tests import cases
 
 GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_runs", "*.json")))
@@ -27,6 +28,19 @@ def test_fixture_set_is_complete():
 @pytest.mark.parametrize("path", GOLDEN, ids=_ids(GOLDEN))
 def test_oracle_equals_reference_output(oracle, path):
     case, golden = cases.reference_golden_load(path)
+    if case["kind"] == "rmat_generated" and "bench_template" in case:
+        # BASELINE configs[2]'s templates on R-MAT scale 20: the reference ran the template with its enumeration walk at
+        # constraint 4; the oracle equals it on that template — and on the template as bench.py and the GPU test run it
+        # (enumeration at its own index) the final sets and the enumerated walks are the same
+        g, labels = _rmat_graph(oracle, case["scale"], case["gen_ranks"])
+        spec4, at4 = cases.bench_template_at_constraint_4(case["bench_template"])
+        run = oracle.Run(g, labels, oracle.Pattern(cases.pattern_dir(spec4)), tds_from_pl=4)
+        assert not run.hazards[:5].any()
+        cases.assert_equals_reference_golden(cases.run_summary(run), golden)
+        spec = cases.rmat20_template(case["bench_template"])
+        own = oracle.Run(g, labels, oracle.Pattern(cases.pattern_dir(spec)), tds_from_pl=PT.tds_from_pl(spec))
+        cases.assert_final_sets_equal_reference_golden(cases.run_summary(own), PT.tds_from_pl(spec), golden)
+        return
     if case["kind"] == "rmat_generated":  # BASELINE configs[0]: the oracle's own generator and the reference's pattern directory
         g = oracle.Graph.rmat(case["scale"], case["gen_ranks"])
         d = os.path.join(os.path.dirname(os.path.abspath(__file__)), case["pattern_dir"], "0")
@@ -51,6 +65,17 @@ def test_oracle_equals_reference_output(oracle, path):
     if run.hazards[:3].any() or run.hazards[4]:
         pytest.skip("the reference is order dependent on this input")
     cases.assert_equals_reference_golden(cases.run_summary(run), golden)
+
+
+_RMAT = {}
+
+
+def _rmat_graph(oracle, scale, gen_ranks):
+    if (scale, gen_ranks) not in _RMAT:
+        g = oracle.Graph.rmat(scale, gen_ranks)
+        _RMAT.clear()
+        _RMAT[(scale, gen_ranks)] = (g, g.labels_degree_log2())
+    return _RMAT[(scale, gen_ranks)]
 
 
 def _assert_fuzzy(rows, iterations, v, t, golden):

@@ -241,3 +241,50 @@ def test_result_tree_is_the_reference_result_tree_file_by_file(oracle, tmp_path)
     assert len(a) == len(b) and [x.strip() for x in a[:3] + a[4:]] == [x.strip() for x in b[:3] + b[4:]]
     assert len(read(ref_out, "0/all_ranks_messages/messages_0").splitlines()) == \
         len(read(ours, "0/all_ranks_messages/messages_0").splitlines())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The -v metadata loader: the reference's own vertex_data_db.hpp reads every file "<prefix>.*" of a directory;
+# the engine's host reader (pm_io_read_vertex_data, csrc/pm_io.hpp) must hand the search the same labels.
+
+def test_vertex_metadata_files_read_like_the_reference_loader(oracle, tmp_path):
+    from fuzzypatternmatching_b200 import engine as E
+    name, spec, labelset, _ = cases.SPECS[0]  # the tree template
+    compared = 0
+    for seed in (1, 2, 3):
+        edges, labels = cases.planted(seed, 300, 900, spec, labelset)
+        n = 300
+        work = tmp_path / ("run%d" % seed)
+        (work / "meta").mkdir(parents=True)
+        # three files under one prefix, vertices dealt round robin (no vertex twice: the reference applies the files of a
+        # directory in directory order, so duplicates across files have no defined winner); a file of another prefix
+        names = ["vlabel_0", "vlabel_1", "vlabel.part2"]
+        for i, fname in enumerate(names):
+            with open(work / "meta" / fname, "w") as f:
+                f.write("".join("%d %d\n" % (v, int(labels[v])) for v in range(i, n, len(names))))
+        with open(work / "meta" / "other_0", "w") as f:
+            f.write("".join("%d 1\n" % v for v in range(n)))
+        base = str(work / "meta" / "vlabel")
+        ours, n_pairs = E.read_vertex_data(base, n)
+        assert n_pairs == n and np.array_equal(ours, labels)
+        # the reference driver with the same -v argument
+        d = cases.pattern_dir(spec)
+        src, dst = cases.slots_of(edges)
+        graph = str(work / "graph.slots")
+        R.write_slot_file(graph, n, src.tolist(), dst.tolist())
+        out = str(work / "out")
+        p = R.launch(graph, os.path.dirname(d), out, vertex_data_base=base)
+        so, se = p.communicate(timeout=300)
+        assert p.returncode == 0, se[-500:]
+        got = R.parse_result_tree(out)
+        g = oracle.Graph.from_undirected(n, edges)
+        run = oracle.Run(g, ours, oracle.Pattern(d), tds_from_pl=4, max_iterations=50)
+        if run.hazards[:3].any() or run.hazards[4]:
+            continue
+        want = cases.run_summary(run)
+        assert got["rows"] == want["rows"] and got["vertices"] == sorted(want["vertices"]) and got["edges"] == sorted(want["edges"])
+        # the label column of the reference's vertex rows ("rank, vertex, pattern index, label, bitset") is what our reader read
+        rows = [l.split(",") for l in open(os.path.join(out, "0", "all_ranks_active_vertices", "active_vertices_0")) if l.strip()]
+        assert len(rows) > 0 and all(int(t[3]) == int(ours[int(t[1])]) for t in rows)
+        compared += 1
+    assert compared >= 2

@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 BINARY = os.path.join(_HERE, "_ref", "run_pattern_matching_beta")
 BINARY_APPROX = os.path.join(_HERE, "_ref", "run_pattern_matching_beta_2")  # the driver of approximate matching
 BINARY_FUZZY = os.path.join(_HERE, "_ref", "run_pattern_matching")  # the driver of the run_fuzzy path
+BINARY_EDGE_LIST = os.path.join(_HERE, "_ref", "edge_list_dump")  # the reference's own edge list reader
 REFERENCE = "/root/reference"
 
 _TREE = ("all_ranks_active_vertices", "all_ranks_active_vertices_count", "all_ranks_active_edges",
@@ -36,6 +37,19 @@ def approx_available():
 
 def fuzzy_available():
     return os.path.exists(BINARY_FUZZY) and os.access(BINARY_FUZZY, os.X_OK)
+
+
+def edge_list_dump(files, undirected):
+    """What the reference's own parallel_edge_list_reader.hpp iterates over the listed "source target [weight]" files — the
+    edges src/ingest_edge_list.cpp hands the graph constructor: (max vertex id, has edge data, [(source, target), ...])."""
+    p = subprocess.run([BINARY_EDGE_LIST, "1" if undirected else "0"] + list(files), capture_output=True, text=True, timeout=300)
+    if p.returncode != 0:
+        raise RuntimeError("edge_list_dump failed: " + p.stderr[-500:])
+    lines = [l for l in p.stdout.splitlines() if not l.startswith("Ingesting from")]
+    maxv, has_data, n = (int(x) for x in lines[0].split())
+    edges = [tuple(int(x) for x in l.split()) for l in lines[1:]]
+    assert len(edges) == n
+    return maxv, bool(has_data), edges
 
 
 def write_slot_file(path, n_vertices, src, dst):

@@ -288,3 +288,30 @@ def test_vertex_metadata_files_read_like_the_reference_loader(oracle, tmp_path):
         assert len(rows) > 0 and all(int(t[3]) == int(ours[int(t[1])]) for t in rows)
         compared += 1
     assert compared >= 2
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Edge-list ingest: the reference's own parallel_edge_list_reader.hpp (oracle/_ref/edge_list_dump) against the
+# engine's host reader (pm_io_read_edge_lists, csrc/pm_io.hpp) — the edges ingest_edge_list hands the graph constructor.
+
+@pytest.mark.skipif(not os.access(R.BINARY_EDGE_LIST, os.X_OK), reason="needs oracle/_ref/edge_list_dump")
+@pytest.mark.parametrize("undirected", [False, True])
+def test_edge_lists_read_like_the_reference_reader(tmp_path, undirected):
+    import random
+    from fuzzypatternmatching_b200 import engine as E
+    rng = random.Random(11)
+    for weights in (False, True):
+        files = []
+        for i in range(3):
+            path = tmp_path / ("edges_%s_%d.txt" % ("w" if weights else "p", i))
+            with open(path, "w") as f:
+                for _ in range(200 + 50 * i):
+                    s, t = rng.randrange(500), rng.randrange(500)  # duplicates and self loops included
+                    f.write("%d %d%s\n" % (s, t, " %d" % rng.randrange(1, 200) if weights else ""))
+            files.append(str(path))
+        maxv, has_data, ref_edges = R.edge_list_dump(files, undirected)
+        nv, src, dst = E.read_edge_lists(files, undirected=undirected)
+        assert has_data == weights
+        assert nv == maxv + 1  # the reference builds the graph over [0, max vertex id]
+        assert list(zip(src.tolist(), dst.tolist())) == ref_edges  # same edges in the same order: (s, t) then (t, s) with -u 1
+        assert len(ref_edges) == (2 if undirected else 1) * (200 + 250 + 300)

@@ -315,3 +315,47 @@ def test_edge_lists_read_like_the_reference_reader(tmp_path, undirected):
         assert nv == maxv + 1  # the reference builds the graph over [0, max vertex id]
         assert list(zip(src.tolist(), dst.tolist())) == ref_edges  # same edges in the same order: (s, t) then (t, s) with -u 1
         assert len(ref_edges) == (2 if undirected else 1) * (200 + 250 + 300)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The pattern directory as THE REFERENCE parsed it (::graph of graph.hpp and pattern_util.hpp print what they read:
+# beta.cpp:446-468, 770-790) against the engine's host reader (pm_pattern_check_dir / pm_pattern_load_dir, csrc/pm_pattern.hpp).
+
+def _reference_parsed_pattern(stdout):
+    import re
+    verts = [(int(a), int(b), int(c), int(d)) for a, b, c, d in
+             re.findall(r"^(\d+) : off-set (\d+) vertex_data (\d+) vertex_degree (\d+)$", stdout, flags=re.M)]
+    nbrs = [[int(x) for x in l.split(",") if x.strip()] for l in re.findall(r"^ neighbours : (.*)$", stdout, flags=re.M)]
+    diameter = int(re.search(r"^diameter : (\d+)$", stdout, flags=re.M).group(1))
+    cons = {}
+    for pl, walk in re.findall(r"^Token Passing \[(\d+)\] \| Pattern Vertices : (.*)$", stdout, flags=re.M):
+        cons.setdefault(int(pl), {})["walk"] = [int(x) for x in walk.split(",") if x.strip()]
+    for pl, args in re.findall(r"^Token Passing \[(\d+)\] \| Arguments : (.*)$", stdout, flags=re.M):
+        cons.setdefault(int(pl), {})["args"] = [int(x) for x in args.split()]
+    return verts, nbrs, diameter, cons
+
+
+@pytest.mark.parametrize("name,spec,labelset,tds_from", cases.SPECS, ids=[s[0] for s in cases.SPECS])
+def test_pattern_directory_parsed_like_the_reference(oracle, name, spec, labelset, tds_from):
+    from fuzzypatternmatching_b200 import engine as E
+    edges, labels = cases.planted(1, 300, 900, spec, labelset)
+    d = cases.pattern_dir(spec)
+    src, dst = cases.slots_of(edges)
+    got = R.run(300, src.tolist(), dst.tolist(), os.path.dirname(d), labels=labels.tolist())
+    verts, nbrs, diameter, cons = _reference_parsed_pattern(got["stdout"])
+    ours = E.pattern_check_dir(d)
+    assert ours["n_vertices"] == len(verts) == len(spec["labels"])
+    assert [v[2] for v in verts] == list(spec["labels"])  # vertex_data in vertex order
+    assert ours["n_edges"] in (sum(v[3] for v in verts), sum(v[3] for v in verts) // 2)  # directed slots or undirected edges
+    both = sorted(set((a, b) for a, b in spec["edges"]) | set((b, a) for a, b in spec["edges"]))
+    assert [(v, u) for v, row in enumerate(nbrs) for u in row] == both  # the template CSR, rows ascending
+    assert ours["diameter"] == diameter == spec["diameter"]
+    assert ours["n_constraints"] == len(spec["constraints"])
+    assert len(cons) == len(spec["constraints"])  # planted copies survive LCC: every constraint was reached and printed
+    for pl, c in enumerate(spec["constraints"]):
+        ref, mine = cons[pl], ours["constraints"][pl]
+        assert ref["walk"] == list(c["walk"])
+        assert mine["walk_length"] == len(ref["walk"])
+        # "Arguments : <cycle length> <valid cycle> <interleave label propagation> <selected vertices>" (beta.cpp:776-780)
+        assert ref["args"][0] == len(ref["walk"]) - 2
+        assert mine["valid_cycle"] == ref["args"][1] and mine["interleave_lcc"] == ref["args"][2] and ref["args"][3] == 0

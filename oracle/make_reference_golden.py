@@ -76,6 +76,34 @@ def main():
                                       % {"run_fuzzy": "run_pattern_matching", "approx_first_lcc": "run_pattern_matching_beta_2"}.get(case.get("path"), "run_pattern_matching_beta")}, f, separators=(",", ":"))
         n_files += 1
     print("wrote %d files to %s" % (n_files, OUT))
+    write_rmat_fixture()
+
+
+RMAT_FIXTURE = os.path.join(ROOT, "tests", "golden", "rmat_reference_generator.json")
+RMAT_FIXTURE_STREAMS = [(17, 0, 4), (17, 3, 4), (21, 0, 4), (21, 2, 4), (25, 0, 1024), (26, 0, 1024), (26, 1023, 1024),
+                        (28, 517, 1024), (32, 1, 4)]
+
+
+def write_rmat_fixture():
+    """tests/golden/rmat_reference_generator.json: the first 64 generated edges of a few generating ranks and hash_nbits of
+    a few values, from the reference's OWN rmat_edge_generator.hpp / detail/hash.hpp (oracle/_ref/rmat_edge_dump)"""
+    if not os.access(R.BINARY_RMAT, os.X_OK):
+        return
+    import random
+    rng = random.Random(7)
+    doc = {"produced_by": "oracle/_ref/rmat_edge_dump (the reference's rmat_edge_generator.hpp + detail/hash.hpp, constructed like "
+                          "src/generate_rmat.cpp:202-205) via oracle/make_reference_golden.py",
+           "streams": [], "hash_nbits": []}
+    for scale, rank, ranks in RMAT_FIXTURE_STREAMS:
+        pairs = R.rmat_edge_dump(scale, rank, ranks, 64)
+        assert np.array_equal(pairs[0::2], pairs[1::2][:, ::-1])
+        doc["streams"].append({"scale": scale, "rank": rank, "ranks": ranks, "edges": pairs[0::2].tolist()})
+    for n in range(17, 33):
+        xs = [0, 1, (1 << n) - 1] + [rng.randrange(1 << n) for _ in range(13)]
+        doc["hash_nbits"].append({"n": n, "x": xs, "hash": R.reference_hash_nbits(xs, n)})
+    with open(RMAT_FIXTURE, "w") as f:
+        json.dump(doc, f, separators=(",", ":"))
+    print("wrote " + RMAT_FIXTURE)
 
 
 if __name__ == "__main__":

@@ -14,6 +14,7 @@ BINARY = os.path.join(_HERE, "_ref", "run_pattern_matching_beta")
 BINARY_APPROX = os.path.join(_HERE, "_ref", "run_pattern_matching_beta_2")  # the driver of approximate matching
 BINARY_FUZZY = os.path.join(_HERE, "_ref", "run_pattern_matching")  # the driver of the run_fuzzy path
 BINARY_EDGE_LIST = os.path.join(_HERE, "_ref", "edge_list_dump")  # the reference's own edge list reader
+BINARY_RMAT = os.path.join(_HERE, "_ref", "rmat_edge_dump")  # the reference's own R-MAT generator + hash
 REFERENCE = "/root/reference"
 
 _TREE = ("all_ranks_active_vertices", "all_ranks_active_vertices_count", "all_ranks_active_edges",
@@ -50,6 +51,29 @@ def edge_list_dump(files, undirected):
     edges = [tuple(int(x) for x in l.split()) for l in lines[1:]]
     assert len(edges) == n
     return maxv, bool(has_data), edges
+
+
+def rmat_edge_dump(scale, rank, ranks, max_edges=None):
+    """The directed pairs the reference's own rmat_edge_generator.hpp yields for generating rank `rank` of `ranks`
+    (src/generate_rmat.cpp:202-205): numpy (n, 2) uint64 — every generated edge (u, v) is followed by (v, u)."""
+    import numpy as np
+    cmd = [BINARY_RMAT, str(scale), str(rank), str(ranks)] + ([str(max_edges)] if max_edges is not None else [])
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    if p.returncode != 0:
+        raise RuntimeError("rmat_edge_dump failed: " + p.stderr[-500:])
+    head, _, body = p.stdout.partition("\n")
+    maxv, n = (int(x) for x in head.split())
+    pairs = np.array(body.split(), dtype=np.uint64).reshape(-1, 2)
+    assert len(pairs) == n and maxv == (1 << scale) - 1
+    return pairs
+
+
+def reference_hash_nbits(values, n):
+    """detail::hash_nbits(x, n) of the reference's own include/havoqgt/detail/hash.hpp for every x"""
+    p = subprocess.run([BINARY_RMAT, "hash", str(n)] + [str(int(v)) for v in values], capture_output=True, text=True, timeout=60)
+    if p.returncode != 0:
+        raise RuntimeError("rmat_edge_dump hash failed: " + p.stderr[-500:])
+    return [int(x) for x in p.stdout.split()]
 
 
 def write_slot_file(path, n_vertices, src, dst):

@@ -90,6 +90,19 @@ def test_rmat_stream_golden(oracle):
         assert oracle.rmat_stream(scale, rank, len(edges)).tolist() == edges
 
 
+def test_rmat_stream_and_hash_equal_the_reference_generators_output(oracle):
+    """tests/golden/rmat_reference_generator.json was written by the reference's OWN rmat_edge_generator.hpp and
+    detail/hash.hpp (oracle/_ref/rmat_edge_dump via oracle/make_reference_golden.py): first edges of generating ranks of
+    BASELINE's graphs (scale 21 / 4 ranks; scales 25, 26, 28 / 1024 ranks as the bench generates them) and hash_nbits for
+    every supported width up to 32.  tests/test_oracle_vs_reference.py compares whole streams where the binary is present."""
+    gold = json.load(open(os.path.join(HERE, "golden", "rmat_reference_generator.json")))
+    assert len(gold["streams"]) >= 8
+    for s in gold["streams"]:
+        assert oracle.rmat_stream(s["scale"], s["rank"], len(s["edges"])).tolist() == s["edges"], (s["scale"], s["rank"], s["ranks"])
+    for h in gold["hash_nbits"]:
+        assert [oracle.hash_nbits(x, h["n"]) for x in h["x"]] == h["hash"], h["n"]
+
+
 def test_hash_nbits_is_a_permutation_of_17_bits(oracle):
     xs = {oracle.hash_nbits(x, 17) for x in range(0, 1 << 17, 7)}
     assert len(xs) == len(range(0, 1 << 17, 7)) and max(xs) < (1 << 17)

@@ -359,3 +359,37 @@ def test_pattern_directory_parsed_like_the_reference(oracle, name, spec, labelse
         # "Arguments : <cycle length> <valid cycle> <interleave label propagation> <selected vertices>" (beta.cpp:776-780)
         assert ref["args"][0] == len(ref["walk"]) - 2
         assert mine["valid_cycle"] == ref["args"][1] and mine["interleave_lcc"] == ref["args"][2] and ref["args"][3] == 0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The R-MAT stream: the reference's own rmat_edge_generator.hpp + detail/hash.hpp (oracle/_ref/rmat_edge_dump,
+# constructed like src/generate_rmat.cpp:202-205) against the oracle's generator — the one the engine's k_rmat_stream is
+# bit-exact with in the GPU suite.  Boost.Random (not on this image) is restated in oracle/ref_shim/boost/random.hpp.
+
+_needs_rmat = pytest.mark.skipif(not os.access(R.BINARY_RMAT, os.X_OK), reason="needs oracle/_ref/rmat_edge_dump")
+
+
+@_needs_rmat
+def test_rmat_stream_is_the_reference_generators_stream(oracle):
+    # every edge of BASELINE configs[0]'s generating ranks in small (scale 17, 4 ranks), the (u, v) then (v, u) order included
+    for rank in range(4):
+        per = (16 << 17) // 4
+        got = R.rmat_edge_dump(17, rank, 4)
+        want = oracle.rmat_stream(17, rank, per)
+        assert len(got) == 2 * per
+        assert np.array_equal(got[0::2], want) and np.array_equal(got[1::2], want[:, ::-1]), rank
+    # the first 20 000 edges of ranks of the larger configurations: scale 21 / 4 ranks (configs[0]), scale 26 / 1024 ranks
+    # (the bench's graph: its last rank has seed 5489 + 3 * 1023), scale 28 / 1024 and scale 32 (hash32 branch of hash_nbits)
+    for scale, rank, ranks in ((21, 3, 4), (26, 0, 1024), (26, 1023, 1024), (28, 517, 1024), (32, 1, 4)):
+        got = R.rmat_edge_dump(scale, rank, ranks, 20000)
+        want = oracle.rmat_stream(scale, rank, 20000)
+        assert np.array_equal(got[0::2], want), (scale, rank, ranks)
+
+
+@_needs_rmat
+def test_hash_nbits_is_the_reference_hash(oracle):
+    import random
+    rng = random.Random(5)
+    for n in list(range(17, 33)):  # the reference refuses fewer than 17 bits (detail/hash.hpp:130)
+        xs = [0, 1, (1 << n) - 1] + [rng.randrange(1 << n) for _ in range(200)]
+        assert [oracle.hash_nbits(x, n) for x in xs] == R.reference_hash_nbits(xs, n), n

@@ -371,8 +371,8 @@ _needs_rmat = pytest.mark.skipif(not os.access(R.BINARY_RMAT, os.X_OK), reason="
 
 @_needs_rmat
 def test_rmat_stream_is_the_reference_generators_stream(oracle):
-    # every edge of BASELINE configs[0]'s generating ranks in small (scale 17, 4 ranks), the (u, v) then (v, u) order included
-    for rank in range(4):
+    # every edge of two of BASELINE configs[0]'s generating ranks in small (scale 17, 4 ranks), the (u, v) then (v, u) order included
+    for rank in (0, 3):
         per = (16 << 17) // 4
         got = R.rmat_edge_dump(17, rank, 4)
         want = oracle.rmat_stream(17, rank, per)

@@ -393,3 +393,31 @@ def test_hash_nbits_is_the_reference_hash(oracle):
     for n in list(range(17, 33)):  # the reference refuses fewer than 17 bits (detail/hash.hpp:130)
         xs = [0, 1, (1 << n) - 1] + [rng.randrange(1 << n) for _ in range(200)]
         assert [oracle.hash_nbits(x, n) for x in xs] == R.reference_hash_nbits(xs, n), n
+
+
+def test_edge_metadata_flag_changes_nothing_in_the_reference(oracle, tmp_path):
+    """-e is parsed and never used by the reference driver (beta.cpp:115; the EdgeMetadata container is commented out, :331,
+    SURVEY A.6 #9): the same result files with and without it — which is why the engine only VALIDATES those files."""
+    import subprocess
+    name, spec, labelset, _ = cases.SPECS[0]
+    edges, labels = cases.planted(1, 300, 900, spec, labelset)
+    d = cases.pattern_dir(spec)
+    src, dst = cases.slots_of(edges)
+    graph = str(tmp_path / "g.slots")
+    R.write_slot_file(graph, 300, src.tolist(), dst.tolist())
+    (tmp_path / "meta").mkdir()
+    with open(tmp_path / "meta" / "vl_0", "w") as f:
+        f.write("".join("%d %d\n" % (v, int(l)) for v, l in enumerate(labels)))
+    with open(tmp_path / "meta" / "el_0", "w") as f:
+        f.write("".join("%d %d %d\n" % (s, t, 1 + (s + t) % 5) for s, t in zip(src.tolist(), dst.tolist())))
+    res = []
+    for extra in ([], ["-e", str(tmp_path / "meta" / "el")]):
+        out = str(tmp_path / ("out%d" % len(res)))
+        R.make_result_tree(out)
+        p = subprocess.run([R.BINARY, "-i", graph, "-p", os.path.dirname(d), "-o", out, "-v", str(tmp_path / "meta" / "vl")] + extra,
+                           capture_output=True, text=True, timeout=300)
+        assert p.returncode == 0, p.stderr[-500:]
+        res.append(R.parse_result_tree(out))
+    assert res[0] == res[1] and len(res[0]["vertices"]) > 0
+    from fuzzypatternmatching_b200 import engine as E
+    assert E.check_edge_data(str(tmp_path / "meta" / "el"), 300) == len(src)

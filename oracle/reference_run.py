@@ -114,6 +114,33 @@ def search_seconds(stdout):
     return float(m.group(1))
 
 
+def parsed_pattern(stdout):
+    """What the reference driver prints of the template it parsed (beta.cpp:446-468, 770-790):
+    ([(vertex, offset, label, degree)], [neighbour list per vertex], diameter, {constraint: {"walk", "args"}})."""
+    import re
+    verts = [(int(a), int(b), int(c), int(d)) for a, b, c, d in
+             re.findall(r"^(\d+) : off-set (\d+) vertex_data (\d+) vertex_degree (\d+)$", stdout, flags=re.M)]
+    nbrs = [[int(x) for x in l.split(",") if x.strip()] for l in re.findall(r"^ neighbours : (.*)$", stdout, flags=re.M)]
+    diameter = int(re.search(r"^diameter : (\d+)$", stdout, flags=re.M).group(1))
+    cons = {}
+    for pl, walk in re.findall(r"^Token Passing \[(\d+)\] \| Pattern Vertices : (.*)$", stdout, flags=re.M):
+        cons.setdefault(int(pl), {})["walk"] = [int(x) for x in walk.split(",") if x.strip()]
+    for pl, args in re.findall(r"^Token Passing \[(\d+)\] \| Arguments : (.*)$", stdout, flags=re.M):
+        cons.setdefault(int(pl), {})["args"] = [int(x) for x in args.split()]
+    return verts, nbrs, diameter, cons
+
+
+def template_read_intact(stdout, spec):
+    """False when the reference itself mis-read the template: ::graph::generate_vertex_list (graph.hpp:244-270) reads
+    edge_list[l] one element PAST THE END on its last round (undefined behaviour); when the stale heap value there happens to
+    equal the last template vertex's id, that vertex gains phantom neighbours read from beyond the edge array (seen on 12-vertex
+    graphs with the README tree template: "6 : ... vertex_degree 2 / neighbours : 5, 6,").  Such a run searched a different
+    template than the files describe and is not compared."""
+    _, nbrs, _, _ = parsed_pattern(stdout)
+    both = sorted(set((a, b) for a, b in spec["edges"]) | set((b, a) for a, b in spec["edges"]))
+    return [(v, u) for v, row in enumerate(nbrs) for u in row] == both
+
+
 def tds_at_constraint_4(spec):
     """The driver runs template-driven search from constraint index 4 on, whatever the pattern files say
     (beta.cpp:725-730).  A template whose enumeration constraint sits earlier gets copies of its FIRST constraint

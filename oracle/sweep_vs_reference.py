@@ -1,0 +1,169 @@
+"""A long randomized sweep of the oracle against THE REFERENCE ITSELF (oracle/_ref/run_pattern_matching_beta, see
+oracle/ref_shim/README.md): many more seeds, sizes and densities than tests/test_oracle_vs_reference.py runs in the CPU
+suite.  Every input the oracle does not flag as order dependent in the reference must give the same count rows, iteration
+count, final vertex -> bitset map, final edge set and enumerated walks.  TEST INFRASTRUCTURE.
+    python oracle/sweep_vs_reference.py [--path beta|fuzzy|approx] [--seeds N] [--jobs J]
+(prints one summary line per template, exit 1 on a mismatch)
+"""
+import argparse
+import multiprocessing as mp
+import os
+import random
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path = [p for p in sys.path if os.path.abspath(p or ".") != os.path.join(ROOT, "oracle")]
+sys.path.insert(0, ROOT)
+
+
+def templates():
+    from tests import cases
+    from oracle import reference_run as R
+    out = []
+    for name, spec, labelset, _ in cases.SPECS:
+        out.append((name, spec, labelset))
+    for name, spec, labelset, tds_from, _, _ in cases.QUIRK_SPECS:
+        if tds_from >= 0:  # the driver enumerates from constraint 4 on: one-hop path checks in front
+            spec = dict(spec, constraints=[{"walk": [0, 1]} for _ in range(4)] + list(spec["constraints"]))
+        out.append((name, spec, labelset))
+    for name, spec in cases.BENCH_TEMPLATES.items():
+        out.append(("bench_" + name, R.tds_at_constraint_4(spec)[0], sorted(set(spec["labels"]))))
+    return out
+
+
+def fuzzy_templates():
+    from fuzzypatternmatching_b200 import patterns as PT
+    return [("fuzzy_triangle", PT.triangle(1, 2, 3), [1, 2, 3]), ("fuzzy_cycle4", PT.cycle4(1, 2, 3, 4), [1, 2, 3, 4])]
+
+
+def approx_templates():
+    from tests import cases
+    return [("approx_" + name, spec, labelset) for name, spec, labelset, _ in cases.APPROX_SPECS]
+
+
+def _random_input(cases, rng, seed, labelset):
+    n = rng.choice([12, 40, 90, 200, 500])
+    m = int(n * rng.choice([1.0, 2.0, 3.5, 6.0]))
+    edges = cases.random_multigraph(seed, n, m, dup=rng.choice([0.0, 0.1, 0.4]), loops=rng.choice([0.0, 0.05, 0.3]))
+    labels = cases.random_labels(seed, n, labelset + ([labelset[0] + 50] if rng.random() < 0.3 else []))
+    return n, edges, labels
+
+
+def one_fuzzy(args):
+    """the run_fuzzy path: the reference's src/run_pattern_matching.cpp"""
+    t_index, seed = args
+    from oracle import oracle as O
+    from oracle import reference_run as R
+    from tests import cases
+    name, spec, labelset = fuzzy_templates()[t_index]
+    n, edges, labels = _random_input(cases, random.Random(seed * 104729 + t_index), seed, labelset)
+    if not len(edges):
+        return name, "skipped", None
+    d = cases.pattern_dir(spec)
+    run = O.Run(O.Graph.from_undirected(n, edges), labels, O.Pattern(d), fuzzy=True, max_iterations=60)
+    src, dst = cases.slots_of(edges)
+    got = R.run_fuzzy(n, src.tolist(), dst.tolist(), os.path.dirname(d), labels.tolist())
+    v, t = run.active_vertices()
+    ok = (got["rows"] == [(a, b, c, nv, 0) for a, b, c, nv, _ in run.rows] and got["iterations"] == run.iterations
+          and got["vertices"] == sorted((int(a), int(b).bit_length() - 1) for a, b in zip(v, t)))
+    if not ok:
+        return name, "MISMATCH", dict(seed=seed, n=n)
+    return name, ("nontrivial" if run.rows[-1][3] > 0 else "empty") + ("+walked" if any(r[1] == "TP" for r in run.rows) else ""), None
+
+
+def one_approx(args):
+    """approximate matching: the rows of the first local constraint checking call of run_pattern_matching_beta_2.cpp"""
+    t_index, seed = args
+    from oracle import oracle as O
+    from oracle import reference_run as R
+    from tests import cases
+    name, spec, labelset = approx_templates()[t_index]
+    n, edges, labels = _random_input(cases, random.Random(seed * 1299709 + t_index), seed, labelset)
+    if not len(edges):
+        return name, "skipped", None
+    d = cases.pattern_dir(spec)
+    run = O.Run(O.Graph.from_undirected(n, edges), labels, O.Pattern(d), tds_from_pl=-1, max_iterations=60)
+    want = [r for r in run.rows[:spec["diameter"]]]
+    src, dst = cases.slots_of(edges)
+    got = R.run_approx_first_lcc(n, src.tolist(), dst.tolist(), os.path.dirname(d), labels.tolist(), spec)
+    if got != want:
+        return name, "MISMATCH", dict(seed=seed, n=n)
+    return name, "pruned" if want[-1][3] < n else "kept_all", None
+
+
+def one(args):
+    t_index, seed = args
+    import numpy as np  # noqa: F401
+    from oracle import oracle as O
+    from oracle import reference_run as R
+    from tests import cases
+    name, spec, labelset = templates()[t_index]
+    rng = random.Random(seed * 7919 + t_index)
+    n = rng.choice([12, 40, 90, 200, 500])
+    m = int(n * rng.choice([1.0, 2.0, 3.5, 6.0]))
+    kind = rng.choice(["random", "random", "planted"])
+    if kind == "planted" and n >= 90:
+        edges, labels = cases.planted(seed, n, m, spec, labelset, copies=rng.choice([1, 3, 6]))
+    else:
+        edges = cases.random_multigraph(seed, n, m, dup=rng.choice([0.0, 0.1, 0.4]), loops=rng.choice([0.0, 0.05, 0.3]))
+        labels = cases.random_labels(seed, n, labelset + ([labelset[0] + 50] if rng.random() < 0.3 else []))
+    if not len(edges):
+        return name, "skipped", None
+    d = cases.pattern_dir(spec)
+    g = O.Graph.from_undirected(n, edges)
+    run = O.Run(g, labels, O.Pattern(d), tds_from_pl=4, max_iterations=60)
+    if run.hazards[:3].any() or run.hazards[4]:
+        return name, "order_dependent", None
+    want = cases.run_summary(run)
+    src, dst = cases.slots_of(edges)
+    got = R.run(n, src.tolist(), dst.tolist(), os.path.dirname(d), labels=labels.tolist())
+    ok = (got["rows"] == want["rows"] and got["iterations"] == want["iterations"] and got["vertices"] == sorted(want["vertices"])
+          and got["edges"] == sorted(want["edges"])
+          and all(got["subgraphs"].get(pl, []) == sorted(want["subgraphs"][pl]) for pl in range(4, len(want["subgraphs"]))))
+    if not R.template_read_intact(got["stdout"], spec):
+        return name, "reference_misread_its_template", None  # undefined behaviour in graph.hpp, see template_read_intact
+    if not ok:
+        return name, "MISMATCH", dict(seed=seed, n=n, m=m, kind=kind)
+    flags = ("nontrivial" if want["rows"][-1][3] > 0 else "empty") + ("+multi_iteration" if want["iterations"] > 1 else "") + \
+        ("+resurrection" if run.hazards[3] else "") + ("+flag_outside_lcc" if run.hazards[5] else "")
+    return name, flags, None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seeds", type=int, default=100)
+    ap.add_argument("--jobs", type=int, default=max(1, (os.cpu_count() or 2) - 1))
+    ap.add_argument("--path", default="beta", choices=["beta", "fuzzy", "approx"],
+                    help="beta: run_pattern_matching_beta (LCC / NLCC); fuzzy: run_pattern_matching (run_fuzzy path); "
+                         "approx: run_pattern_matching_beta_2 (first local constraint checking call)")
+    a = ap.parse_args()
+    from oracle import oracle as O
+    from oracle import reference_run as R
+    O.build()
+    if R.build() is None:
+        sys.exit("oracle/_ref is not built and /root/reference is not here")
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    ts, fn = {"beta": (templates, one), "fuzzy": (fuzzy_templates, one_fuzzy), "approx": (approx_templates, one_approx)}[a.path]
+    ts = ts()
+    work = [(t, s) for t in range(len(ts)) for s in range(a.seeds)]
+    stats, bad = {}, []
+    with mp.Pool(a.jobs) as pool:
+        for name, flags, info in pool.imap_unordered(fn, work, chunksize=8):
+            st = stats.setdefault(name, {})
+            st[flags] = st.get(flags, 0) + 1
+            if info:
+                bad.append((name, info))
+    total = 0
+    for name, _, _ in ts:
+        st = stats.get(name, {})
+        compared = sum(v for k, v in st.items() if k not in ("skipped", "order_dependent", "MISMATCH", "reference_misread_its_template"))
+        total += compared
+        print("%-28s compared %4d  %s" % (name, compared, " ".join("%s=%d" % kv for kv in sorted(st.items()))))
+    print("path %s: oracle == reference on %d inputs, %d mismatches" % (a.path, total, len(bad)))
+    for b in bad:
+        print("MISMATCH", b)
+    sys.exit(1 if bad else 0)
+
+
+if __name__ == "__main__":
+    main()

@@ -321,18 +321,7 @@ def test_edge_lists_read_like_the_reference_reader(tmp_path, undirected):
 # The pattern directory as THE REFERENCE parsed it (::graph of graph.hpp and pattern_util.hpp print what they read:
 # beta.cpp:446-468, 770-790) against the engine's host reader (pm_pattern_check_dir / pm_pattern_load_dir, csrc/pm_pattern.hpp).
 
-def _reference_parsed_pattern(stdout):
-    import re
-    verts = [(int(a), int(b), int(c), int(d)) for a, b, c, d in
-             re.findall(r"^(\d+) : off-set (\d+) vertex_data (\d+) vertex_degree (\d+)$", stdout, flags=re.M)]
-    nbrs = [[int(x) for x in l.split(",") if x.strip()] for l in re.findall(r"^ neighbours : (.*)$", stdout, flags=re.M)]
-    diameter = int(re.search(r"^diameter : (\d+)$", stdout, flags=re.M).group(1))
-    cons = {}
-    for pl, walk in re.findall(r"^Token Passing \[(\d+)\] \| Pattern Vertices : (.*)$", stdout, flags=re.M):
-        cons.setdefault(int(pl), {})["walk"] = [int(x) for x in walk.split(",") if x.strip()]
-    for pl, args in re.findall(r"^Token Passing \[(\d+)\] \| Arguments : (.*)$", stdout, flags=re.M):
-        cons.setdefault(int(pl), {})["args"] = [int(x) for x in args.split()]
-    return verts, nbrs, diameter, cons
+_reference_parsed_pattern = R.parsed_pattern
 
 
 @pytest.mark.parametrize("name,spec,labelset,tds_from", cases.SPECS, ids=[s[0] for s in cases.SPECS])

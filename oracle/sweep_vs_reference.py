@@ -91,6 +91,117 @@ def one_approx(args):
     return name, "pruned" if want[-1][3] < n else "kept_all", None
 
 
+def random_template(rng):
+    """A random connected template of 3..6 vertices: a random tree plus up to two extra edges; labels distinct or with
+    repeats; one cycle constraint per extra edge (tree path + the closing edge), one path constraint per pair of equally
+    labelled vertices (both directions, like the README tree), then — at constraint index >= 4, where the driver starts
+    template-driven search — a closed depth-first walk over every template edge as the enumeration constraint."""
+    k = rng.randint(3, 6)
+    parent = {i: rng.randrange(i) for i in range(1, k)}
+    edges = [(parent[i], i) for i in range(1, k)]
+    for _ in range(rng.randint(0, 2)):
+        a, b = sorted(rng.sample(range(k), 2))
+        if (a, b) not in edges:
+            edges.append((a, b))
+    labels = list(range(1, k + 1))
+    if rng.random() < 0.5:
+        for _ in range(rng.randint(1, 2)):
+            labels[rng.randrange(k)] = labels[rng.randrange(k)]
+    adj = {i: set() for i in range(k)}
+    for a, b in edges:
+        adj[a].add(b); adj[b].add(a)  # noqa: E702
+
+    def tree_path(a, b):
+        up = lambda x: [x] + (up(parent[x]) if x else [])  # noqa: E731
+        pa, pb = up(a), up(b)
+        common = next(x for x in pa if x in pb)
+        return pa[:pa.index(common) + 1] + pb[:pb.index(common)][::-1]
+
+    def bfs_ecc(src):
+        dist, todo = {src: 0}, [src]
+        for x in todo:
+            for y in adj[x]:
+                if y not in dist:
+                    dist[y] = dist[x] + 1
+                    todo.append(y)
+        return max(dist.values())
+    cons = []
+    for a, b in edges[k - 1:]:
+        walk = tree_path(a, b)
+        if len(walk) >= 3:
+            cons.append({"walk": walk + [a], "cycle": True})
+    for a in range(k):
+        for b in range(k):
+            if a != b and labels[a] == labels[b] and len(tree_path(a, b)) >= 3:
+                cons.append({"walk": tree_path(a, b)})
+    cons = cons[:6]
+    while len(cons) < 4:
+        cons.append({"walk": [0, 1] if (0, 1) in edges else list(edges[0])})  # one-hop checks LCC has already settled
+    walk, seen, last_new = [0], set(), [0]
+
+    def dfs(x):
+        for y in sorted(adj[x]):
+            e = (min(x, y), max(x, y))
+            if e in seen:
+                continue
+            seen.add(e)
+            walk.append(y)
+            last_new[0] = len(walk)
+            dfs(y)
+            walk.append(x)
+    dfs(0)
+    walk = walk[:last_new[0]]  # no backtracking behind the last new edge (the README walk ends at its last discovered vertex)
+    tds = {"walk": walk, "tds": True}
+    if walk[-1] == walk[0]:
+        tds["cycle"] = True  # a walk that closes at its source is a cycle constraint (valid_cycle = 1)
+    cons.append(tds)
+    return {"labels": labels, "edges": edges, "diameter": max(1, max(bfs_ecc(i) for i in range(k))) + rng.randint(0, 1),
+            "constraints": cons}
+
+
+def one_random_template(args):
+    _, seed = args
+    from oracle import oracle as O
+    from oracle import reference_run as R
+    from tests import cases
+    rng = random.Random(seed * 15485863 + 11)
+    spec = random_template(rng)
+    labelset = sorted(set(spec["labels"]))
+    name = "random_templates"
+    n = rng.choice([12, 40, 90, 200])
+    m = int(n * rng.choice([1.0, 2.0, 3.5, 6.0]))
+    if rng.random() < 0.4 and n >= 40:
+        edges, labels = cases.planted(seed, n, m, spec, labelset, copies=rng.choice([1, 3]))
+    else:
+        edges = cases.random_multigraph(seed, n, m, dup=rng.choice([0.0, 0.1, 0.4]), loops=rng.choice([0.0, 0.05, 0.3]))
+        labels = cases.random_labels(seed, n, labelset)
+    if not len(edges):
+        return name, "skipped", None
+    d = cases.pattern_dir(spec)
+    try:
+        pat = O.Pattern(d)
+    except Exception:  # noqa: BLE001 — a template the pattern reader refuses
+        return name, "refused_by_the_reader", None
+    run = O.Run(O.Graph.from_undirected(n, edges), labels, pat, tds_from_pl=4, max_iterations=60)
+    if run.hazards[:3].any() or run.hazards[4]:
+        return name, "order_dependent", None
+    want = cases.run_summary(run)
+    src, dst = cases.slots_of(edges)
+    try:
+        got = R.run(n, src.tolist(), dst.tolist(), os.path.dirname(d), labels=labels.tolist(), timeout=120)
+    except Exception as e:  # noqa: BLE001
+        return name, "reference_failed", dict(seed=seed, spec=spec, error=str(e)[-200:])
+    if not R.template_read_intact(got["stdout"], spec):
+        return name, "reference_misread_its_template", None
+    ok = (got["rows"] == want["rows"] and got["iterations"] == want["iterations"] and got["vertices"] == sorted(want["vertices"])
+          and got["edges"] == sorted(want["edges"])
+          and all(got["subgraphs"].get(pl, []) == sorted(want["subgraphs"][pl]) for pl in range(4, len(want["subgraphs"]))))
+    if not ok:
+        return name, "MISMATCH", dict(seed=seed, n=n, m=m, spec=spec)
+    return name, ("nontrivial" if want["rows"][-1][3] > 0 else "empty") + ("+multi_iteration" if want["iterations"] > 1 else "") + \
+        ("+enumerated" if any(len(x) for x in want["subgraphs"]) else ""), None
+
+
 def one(args):
     t_index, seed = args
     import numpy as np  # noqa: F401
@@ -133,9 +244,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seeds", type=int, default=100)
     ap.add_argument("--jobs", type=int, default=max(1, (os.cpu_count() or 2) - 1))
-    ap.add_argument("--path", default="beta", choices=["beta", "fuzzy", "approx"],
+    ap.add_argument("--path", default="beta", choices=["beta", "fuzzy", "approx", "random_templates"],
                     help="beta: run_pattern_matching_beta (LCC / NLCC); fuzzy: run_pattern_matching (run_fuzzy path); "
-                         "approx: run_pattern_matching_beta_2 (first local constraint checking call)")
+                         "approx: run_pattern_matching_beta_2 (first local constraint checking call); random_templates: the beta driver over "
+                         "random 3..6 vertex templates")
     a = ap.parse_args()
     from oracle import oracle as O
     from oracle import reference_run as R
@@ -143,7 +255,8 @@ def main():
     if R.build() is None:
         sys.exit("oracle/_ref is not built and /root/reference is not here")
     os.environ.setdefault("OMP_NUM_THREADS", "1")
-    ts, fn = {"beta": (templates, one), "fuzzy": (fuzzy_templates, one_fuzzy), "approx": (approx_templates, one_approx)}[a.path]
+    ts, fn = {"beta": (templates, one), "fuzzy": (fuzzy_templates, one_fuzzy), "approx": (approx_templates, one_approx),
+              "random_templates": (lambda: [("random_templates", None, None)], one_random_template)}[a.path]
     ts = ts()
     work = [(t, s) for t in range(len(ts)) for s in range(a.seeds)]
     stats, bad = {}, []
@@ -156,7 +269,8 @@ def main():
     total = 0
     for name, _, _ in ts:
         st = stats.get(name, {})
-        compared = sum(v for k, v in st.items() if k not in ("skipped", "order_dependent", "MISMATCH", "reference_misread_its_template"))
+        compared = sum(v for k, v in st.items() if k not in ("skipped", "order_dependent", "MISMATCH", "reference_misread_its_template",
+                                                             "refused_by_the_reader", "reference_failed"))
         total += compared
         print("%-28s compared %4d  %s" % (name, compared, " ".join("%s=%d" % kv for kv in sorted(st.items()))))
     print("path %s: oracle == reference on %d inputs, %d mismatches" % (a.path, total, len(bad)))

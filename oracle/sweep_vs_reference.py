@@ -202,6 +202,72 @@ def one_random_template(args):
         ("+enumerated" if any(len(x) for x in want["subgraphs"]) else ""), None
 
 
+_RMAT_STATE = {}
+
+
+def _rmat_state(scale=17, gen=4):
+    """the R-MAT graph every `rmat_templates` input searches: built once per worker; the slot file once per sweep"""
+    if not _RMAT_STATE:
+        import numpy as np
+        from oracle import oracle as O
+        from oracle import reference_run as R
+        path = os.path.join(os.environ["PM_SWEEP_DIR"], "rmat%d_%d.slots" % (scale, gen))
+        g = O.Graph.rmat(scale, gen)
+        if not os.path.exists(path):
+            e = np.concatenate([O.rmat_stream(scale, r, (16 << scale) // gen) for r in range(gen)])
+            src = np.empty(2 * len(e), dtype=np.uint64)
+            dst = np.empty(2 * len(e), dtype=np.uint64)
+            src[0::2], dst[0::2] = e[:, 0], e[:, 1]
+            src[1::2], dst[1::2] = e[:, 1], e[:, 0]
+            R.write_slot_file(path + ".tmp%d" % os.getpid(), 1 << scale, src, dst)
+            os.replace(path + ".tmp%d" % os.getpid(), path)
+        _RMAT_STATE.update(g=g, labels=g.labels_degree_log2(), path=path)
+    return _RMAT_STATE
+
+
+def one_rmat_template(args):
+    """random templates over the populous degree classes of an R-MAT graph (scale 17, 4 generating ranks), labelled by the
+    reference's OWN degree labels (no -v): skewed degrees, hubs, parallel edges and self loops as in BASELINE's configurations"""
+    _, seed = args
+    from oracle import oracle as O
+    from oracle import reference_run as R
+    from tests import cases
+    name = "rmat17_random_templates"
+    st = _rmat_state()
+    rng = random.Random(seed * 32452843 + 5)
+    spec = random_template(rng)
+    classes = rng.sample(range(2, 10), 6)  # degree classes 2..9 hold thousands of vertices each at scale 17
+    # existence checks only (cycle / path constraints with work aggregation): a generated enumeration walk over populous degree
+    # classes is combinatorial on an R-MAT graph; enumeration on R-MAT is covered by the committed scale-17..21 fixtures
+    spec = dict(spec, labels=[classes[l - 1] for l in spec["labels"]], constraints=[c for c in spec["constraints"] if not c.get("tds")][:4])  # the driver enumerates from constraint 4 on
+    d = cases.pattern_dir(spec)
+    try:
+        pat = O.Pattern(d)
+    except Exception:  # noqa: BLE001
+        return name, "refused_by_the_reader", None
+    run = O.Run(st["g"], st["labels"], pat, tds_from_pl=4, max_iterations=60)
+    if run.hazards[:3].any() or run.hazards[4]:
+        return name, "order_dependent", None
+    want = cases.run_summary(run)
+    out = os.path.join(os.environ["PM_SWEEP_DIR"], "out_%d_%d" % (os.getpid(), seed))
+    p = R.launch(st["path"], os.path.dirname(d), out)
+    so, se = p.communicate(timeout=900)
+    if p.returncode != 0:
+        return name, "reference_failed", dict(seed=seed, spec=spec, error=se[-200:])
+    got = R.parse_result_tree(out)
+    import shutil
+    shutil.rmtree(out, ignore_errors=True)
+    if not R.template_read_intact(so, spec):
+        return name, "reference_misread_its_template", None
+    ok = (got["rows"] == want["rows"] and got["iterations"] == want["iterations"] and got["vertices"] == sorted(want["vertices"])
+          and got["edges"] == sorted(want["edges"])
+          and all(got["subgraphs"].get(pl, []) == sorted(want["subgraphs"][pl]) for pl in range(4, len(want["subgraphs"]))))
+    if not ok:
+        return name, "MISMATCH", dict(seed=seed, spec=spec)
+    return name, ("nontrivial" if want["rows"][-1][3] > 0 else "empty") + ("+multi_iteration" if want["iterations"] > 1 else "") + \
+        ("+enumerated" if any(len(x) for x in want["subgraphs"]) else ""), None
+
+
 def one(args):
     t_index, seed = args
     import numpy as np  # noqa: F401
@@ -244,10 +310,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seeds", type=int, default=100)
     ap.add_argument("--jobs", type=int, default=max(1, (os.cpu_count() or 2) - 1))
-    ap.add_argument("--path", default="beta", choices=["beta", "fuzzy", "approx", "random_templates"],
+    ap.add_argument("--path", default="beta", choices=["beta", "fuzzy", "approx", "random_templates", "rmat_templates"],
                     help="beta: run_pattern_matching_beta (LCC / NLCC); fuzzy: run_pattern_matching (run_fuzzy path); "
                          "approx: run_pattern_matching_beta_2 (first local constraint checking call); random_templates: the beta driver over "
-                         "random 3..6 vertex templates")
+                         "random 3..6 vertex templates; rmat_templates: the same templates over the degree classes of an R-MAT scale-17 graph")
     a = ap.parse_args()
     from oracle import oracle as O
     from oracle import reference_run as R
@@ -255,8 +321,13 @@ def main():
     if R.build() is None:
         sys.exit("oracle/_ref is not built and /root/reference is not here")
     os.environ.setdefault("OMP_NUM_THREADS", "1")
+    import tempfile
+    os.environ.setdefault("PM_SWEEP_DIR", tempfile.mkdtemp(prefix="pm_sweep_"))
+    if a.path == "rmat_templates":
+        _rmat_state()  # the slot file is written once, before the workers start
     ts, fn = {"beta": (templates, one), "fuzzy": (fuzzy_templates, one_fuzzy), "approx": (approx_templates, one_approx),
-              "random_templates": (lambda: [("random_templates", None, None)], one_random_template)}[a.path]
+              "random_templates": (lambda: [("random_templates", None, None)], one_random_template),
+              "rmat_templates": (lambda: [("rmat17_random_templates", None, None)], one_rmat_template)}[a.path]
     ts = ts()
     work = [(t, s) for t in range(len(ts)) for s in range(a.seeds)]
     stats, bad = {}, []

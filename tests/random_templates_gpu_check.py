@@ -65,6 +65,40 @@ def main():
         out["compared"] += 1
         out["nontrivial"] += want["rows"][-1][3] > 0
         out["enumerated"] += any(len(x) for x in want["subgraphs"])
+    # the same generator over the degree classes of an R-MAT graph (scale 17, 4 generating ranks, degree labels): skewed
+    # degrees, hubs, parallel edges; existence constraints only (oracle/sweep_vs_reference.py::one_rmat_template)
+    out.update({"rmat_compared": 0, "rmat_nontrivial": 0})
+    g = O.Graph.rmat(17, 4)
+    glabels = g.labels_degree_log2()
+    eng.graph_rmat(17, 4)
+    eng.labels_degree_log2()
+    for seed in range(max(1, n_seeds // 6)):
+        rng = random.Random(seed * 32452843 + 5)
+        spec = SW.random_template(rng)
+        classes = rng.sample(range(2, 10), 6)
+        spec = dict(spec, labels=[classes[l - 1] for l in spec["labels"]],
+                    constraints=[c for c in spec["constraints"] if not c.get("tds")][:4])
+        d = cases.pattern_dir(spec)
+        ref = O.Run(g, glabels, O.Pattern(d), tds_from_pl=4, max_iterations=60)
+        if ref.hazards[:3].any() or ref.hazards[4]:
+            out["order_dependent"] += 1
+            continue
+        try:
+            eng.pattern_load_dir(d)
+            eng.run(tds_from_pl=4, max_iterations=60)
+        except PmError as e:
+            if "UNSUPPORTED" in str(e).upper() or "order" in str(e).lower():
+                out["refused"] += 1
+                continue
+            out["mismatches"].append({"rmat_seed": seed, "error": str(e)[-300:]})
+            continue
+        got, want = cases.engine_summary(eng, len(spec["constraints"])), cases.run_summary(ref)
+        bad = [k for k in ("rows", "iterations", "vertices", "edges") if got[k] != want[k]]
+        if bad:
+            out["mismatches"].append({"rmat_seed": seed, "differs": bad, "spec": spec})
+            continue
+        out["rmat_compared"] += 1
+        out["rmat_nontrivial"] += want["rows"][-1][3] > 0
     eng.close()
     print(json.dumps(out))
     return 1 if out["mismatches"] else 0

@@ -5,7 +5,8 @@ STATUS, stated plainly: this test was written after the round's GPU budget was s
 harness, with a stand-in engine) and its first execution on a B200 is the driver's round-end `pytest -m gpu`.  Because it could
 not be run beforehand, a mismatch is reported as XFAIL with the offending seeds in the reason instead of failing the suite; a
 clean run is an ordinary PASS.  The templates the other GPU tests use are fixed (tree, triangle, 4-cycle, 6-cycle with chords,
-twins, bowtie, approximate ones); here they are generated (oracle/sweep_vs_reference.py::random_template), and the oracle was
+twins, bowtie, approximate ones); here they are generated (oracle/sweep_vs_reference.py::random_template; on random and planted multigraphs, then over the degree
+classes of an R-MAT scale-17 graph), and the oracle was
 held to the reference's own driver on 19 152 inputs of this generator (profiles/r02_oracle_vs_reference_sweep.log)."""
 import json
 import os
@@ -35,3 +36,4 @@ def test_random_templates_match_oracle(oracle):
                      % (len(out["mismatches"]), out["compared"] + len(out["mismatches"]), json.dumps(out["mismatches"][:3])[:1500]))
     assert p.returncode == 0
     assert out["compared"] >= 60 and out["nontrivial"] >= 20 and out["enumerated"] >= 20, out
+    assert out["rmat_compared"] >= 8 and out["rmat_nontrivial"] >= 4, out

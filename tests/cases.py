@@ -342,3 +342,61 @@ def assert_final_sets_equal_reference_golden(summary, tds_pl, golden):
         assert sorted(summary["subgraphs"][tds_pl]) == golden["subgraphs"].get(4, []), "enumerated walks"
     first_call = lambda rows: [r for r in rows if r[0] == 0 and r[1] == "LP"]  # noqa: E731
     assert first_call(summary["rows"]) == first_call(golden["rows"]), "rows of the first local constraint checking call"
+
+
+def check_multi_rank_attribution(oracle, n, edges, labels, spec, tds_from, ranks, threshold, workdir):
+    """The oracle's per-rank files of a `ranks`-rank run with delegate threshold `threshold` (0: no hubs) against the reference's
+    rules restated from the raw edge list (see tests/test_oracle_delegates.py).  Returns a few counts for the caller's
+    non-triviality checks; skips nothing — raises AssertionError on any deviation."""
+    import collections
+    import os
+
+    def rows_of(path):
+        return [[t.strip() for t in l.split(",")] for l in open(path).read().splitlines() if l.strip()]
+
+    out_degree = collections.Counter()
+    for a, b in edges:  # an undirected input edge is two directed slots; a self loop is two slots of the same vertex
+        out_degree[a] += 1
+        out_degree[b] += 1
+    hubs = sorted(v for v in range(n) if threshold and out_degree[v] >= threshold)
+    controller = {v: i % ranks for i, v in enumerate(hubs)}
+    owner = lambda v: controller[v] if v in controller else v % ranks  # noqa: E731
+    d = pattern_dir(spec)
+    g = oracle.Graph.from_undirected(n, edges)
+    assert np.array_equal(g.degree, np.array([out_degree[v] for v in range(n)], dtype=np.uint64))
+    one = oracle.Run(g, labels, oracle.Pattern(d), n_ranks=1, tds_from_pl=tds_from, max_iterations=50)
+    many = oracle.Run(g, labels, oracle.Pattern(d), n_ranks=ranks, tds_from_pl=tds_from, max_iterations=50,
+                      delegate_threshold=threshold)
+    assert many.rows == one.rows and many.iterations == one.iterations  # aggregate rows = the single-rank rows
+    os.makedirs(workdir, exist_ok=True)
+    oracle.make_result_tree(workdir)
+    many.write_results(workdir)
+    v1, t1 = one.active_vertices()
+    final_vertices = dict(zip(v1.tolist(), t1.tolist()))
+    final_edges = set(map(tuple, one.active_edges.tolist()))
+    seen_v, seen_e = {}, set()
+    base = os.path.join(workdir, "0")
+    for r in range(ranks):
+        rows = rows_of(os.path.join(base, "all_ranks_active_vertices", "active_vertices_%d" % r))
+        for t in rows:  # "rank, vertex, pattern index, label, bitset"
+            v = int(t[1])
+            assert int(t[0]) == r == owner(v), (r, v)
+            assert v not in seen_v
+            seen_v[v] = int(t[4], 2)
+            assert int(t[3]) == int(labels[v])
+        erows = rows_of(os.path.join(base, "all_ranks_active_edges", "active_edges_%d" % r))
+        for t in erows:  # "rank, vertex, neighbour"
+            assert int(t[0]) == r == owner(int(t[1]))
+            seen_e.add((int(t[1]), int(t[2])))
+        vc = rows_of(os.path.join(base, "all_ranks_active_vertices_count", "active_vertices_%d" % r))
+        ec = rows_of(os.path.join(base, "all_ranks_active_edges_count", "active_edges_%d" % r))
+        assert int(vc[-1][3]) == len(rows) and int(ec[-1][3]) == len(erows)  # the last row counts what this rank wrote
+    assert seen_v == final_vertices and seen_e == final_edges  # the union over the ranks is the single-rank result
+    per_v = [rows_of(os.path.join(base, "all_ranks_active_vertices_count", "active_vertices_%d" % r)) for r in range(ranks)]
+    per_e = [rows_of(os.path.join(base, "all_ranks_active_edges_count", "active_edges_%d" % r)) for r in range(ranks)]
+    assert all(len(p) == len(one.rows) for p in per_v + per_e)
+    for i, row in enumerate(one.rows):  # row by row, the ranks' counts add up to the single-rank rows
+        assert sum(int(p[i][3]) for p in per_v) == row[3] and sum(int(p[i][3]) for p in per_e) == row[4], i
+        assert all((int(p[i][0]), p[i][1], int(p[i][2])) == tuple(row[:3]) for p in per_v)
+    return {"hubs": len(hubs), "final_vertices": len(final_vertices),
+            "hubs_moved": sum(1 for v in final_vertices if v in controller and controller[v] != v % ranks)}

@@ -392,6 +392,18 @@ def check_multi_rank_attribution(oracle, n, edges, labels, spec, tds_from, ranks
         ec = rows_of(os.path.join(base, "all_ranks_active_edges_count", "active_edges_%d" % r))
         assert int(vc[-1][3]) == len(rows) and int(ec[-1][3]) == len(erows)  # the last row counts what this rank wrote
     assert seen_v == final_vertices and seen_e == final_edges  # the union over the ranks is the single-rank result
+    # enumerated walks: "[rank], v0, ..., v_last, [v_last]" written where the walk completes (tds_batch_1.hpp:684-689) — the
+    # rank that runs the final vertex's visit: its controller for a hub, its modulo owner otherwise
+    for pl, want_rows in enumerate(one.subgraphs):
+        got_rows = []
+        for r in range(ranks):
+            path = os.path.join(base, "all_ranks_subgraphs", "subgraphs_%d_%d" % (pl, r))
+            for l in (open(path).read().splitlines() if os.path.exists(path) else []):
+                toks = [t.strip() for t in l.split(",")]
+                assert toks[0] == "[%d]" % r and toks[-1] == "[%s]" % toks[-2]
+                assert owner(int(toks[-2])) == r, (pl, r, l)
+                got_rows.append(tuple(int(t) for t in toks[1:-1]))
+        assert sorted(got_rows) == sorted(map(tuple, want_rows.tolist())), pl
     per_v = [rows_of(os.path.join(base, "all_ranks_active_vertices_count", "active_vertices_%d" % r)) for r in range(ranks)]
     per_e = [rows_of(os.path.join(base, "all_ranks_active_edges_count", "active_edges_%d" % r)) for r in range(ranks)]
     assert all(len(p) == len(one.rows) for p in per_v + per_e)
